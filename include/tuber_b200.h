@@ -1,0 +1,217 @@
+/* tuber_b200.h — C ABI of the B200-native tuber hot path.
+ *
+ * One shared library (libtuber_b200.so, sm_100a only, no CPU fallback) that a host ECS binds
+ * over FFI. It replaces, for the per-frame data-parallel path only:
+ *
+ *   tuber-ecs    dense component storage + query   crates/tuber-ecs/src/ecs.rs:16-53,93-129
+ *                                                   crates/tuber-ecs/src/query.rs:94-141
+ *   tuber-core   Transform::as_matrix4             crates/tuber-core/src/transform.rs:28-38
+ *   tuber-math   Matrix4::mul / transform_vec3     crates/tuber-math/src/matrix.rs:160-194
+ *   tuber-graphics  GraphicsAPI::render_scene      crates/tuber-graphics/src/lib.rs:34-36,134-156
+ *   tuber-engine    system step / render           crates/tuber-engine/src/state.rs:81-87,
+ *                                                   crates/tuber-engine/src/lib.rs:105-111
+ *
+ * Conventions: every call returns tb_status (0 == ok) and never aborts the process; the
+ * caller owns every host pointer, the library owns all device memory; one tb_ctx per GPU,
+ * used from one host thread at a time (the reference ECS is single-threaded, ecs.rs:12,17).
+ * All pointers are plain C; nothing in this header needs CUDA or PyTorch headers.
+ * The reference-side binding (Rust `extern "C"` block) is shown in INTEGRATION.md.
+ */
+#ifndef TUBER_B200_H
+#define TUBER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_API __attribute__((visibility("default")))
+
+typedef struct tb_ctx tb_ctx;
+typedef int32_t tb_status;
+
+enum {
+    TB_OK = 0,
+    TB_ERR_INVALID = 1,     /* bad argument (null pointer, range outside entity_count, ...) */
+    TB_ERR_CUDA = 2,        /* a CUDA runtime call failed; see tb_last_error */
+    TB_ERR_OOM = 3,         /* device or host allocation failed */
+    TB_ERR_RANGE = 4,       /* a component value is outside the SPEC range (layer/texture) */
+    TB_ERR_NO_DEVICE = 5,   /* no usable sm_100 device: there is NO CPU fallback */
+    TB_ERR_CAPACITY = 6,    /* more entities / batches than the context was created for */
+    TB_ERR_CYCLE = 7,       /* the Parent links contain a cycle */
+    TB_ERR_COMM = 8,        /* NCCL / peer communication failure */
+    TB_ERR_UNSUPPORTED = 9
+};
+
+/* ---- component layouts ------------------------------------------------------------------ */
+
+/* tuber_core::transform::Transform (transform.rs:5-11): 4 x Vector3<f32>, this order. */
+typedef struct tb_transform {
+    float translation[3];
+    float angle[3];           /* Euler radians: x roll, y pitch, z yaw (quaternion.rs:39-42) */
+    float rotation_center[3];
+    float scale[3];
+} tb_transform;               /* 48 bytes */
+
+/* [SPEC] the renderable component (absent from the reference snapshot). layer <= 65534,
+ * texture <= 65535 (the sort key keeps 16 bits of each). */
+typedef struct tb_sprite {
+    float size[2];
+    uint32_t texture;
+    uint32_t layer;
+} tb_sprite;                  /* 16 bytes */
+
+/* [SPEC] */
+typedef struct tb_velocity {
+    float v[3];
+} tb_velocity;                /* 12 bytes */
+
+/* tuber_ecs::Parent(EntityIndex) (tuber-ecs/src/lib.rs:18-19), narrowed to u32 on device. */
+#define TB_NO_PARENT 0xFFFFFFFFu
+
+/* ---- outputs ([SPEC]) ----------------------------------------------------- */
+
+typedef struct tb_instance {
+    float model[16];          /* column-major world matrix (matrix.rs:219-251) */
+    float size[2];
+    uint32_t texture;
+    uint32_t layer;
+} tb_instance;                /* 80 bytes */
+
+typedef struct tb_quad_vertex {
+    float x, y, z;            /* transform_vec3(world, corner) (matrix.rs:168-171) */
+    uint32_t uv;              /* corner k: 0 -> 0x00000000, 1 -> 0x00000001, 2 -> 0x00010001, 3 -> 0x00010000 */
+} tb_quad_vertex;             /* 16 bytes, 4 per instance */
+
+typedef struct tb_batch {
+    uint32_t layer;
+    uint32_t texture;
+    uint32_t first_instance;
+    uint32_t count;
+} tb_batch;                   /* 16 bytes: one per maximal run of equal (layer, texture) */
+
+enum tb_component { TB_TRANSFORM = 0, TB_SPRITE = 1, TB_VELOCITY = 2, TB_PARENT = 3, TB_COMPONENT_COUNT = 4 };
+
+/* Which batching path a frame took (both give identical results). */
+enum tb_path {
+    TB_PATH_NONE = 0,
+    TB_PATH_BUCKET = 1,   /* <= 256 distinct key buckets: histogram -> scan -> fused compose+scatter emit */
+    TB_PATH_SORT = 2      /* general: key-gen -> LSD radix sort of (key, index) pairs -> gather emit */
+};
+
+typedef struct tb_frame_out {
+    uint64_t num_instances;            /* entities that have Transform and Sprite */
+    uint64_t num_batches;
+    const tb_instance* d_instances;    /* DEVICE pointers, valid until the next frame / destroy */
+    const tb_quad_vertex* d_vertices;
+    const tb_batch* d_batches;
+    const uint32_t* d_order;           /* entity index per sorted position */
+    uint32_t path;                     /* enum tb_path */
+    uint32_t key_bits;                 /* sort-key bits that actually vary this frame */
+    uint32_t sort_passes;              /* radix passes run (TB_PATH_SORT) */
+    uint32_t kernel_launches;          /* kernels this frame launched */
+    uint32_t hierarchy_levels;         /* 0 when no entity has a Parent */
+    uint32_t replanned;                /* 1 when the cached plan was stale and the frame re-ran batching */
+} tb_frame_out;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+TB_API const char* tb_version(void);
+TB_API const char* tb_status_string(tb_status s);
+/* Creates a context on CUDA device `device` with room for `max_entities` entity indices.
+ * Fails with TB_ERR_NO_DEVICE when there is no sm_100 GPU. */
+TB_API tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out);
+TB_API void tb_ctx_destroy(tb_ctx* ctx);
+TB_API const char* tb_last_error(tb_ctx* ctx);
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*),
+ * e.g. the host framework's current stream. NULL restores the context's own stream. */
+TB_API tb_status tb_ctx_set_stream(tb_ctx* ctx, void* cuda_stream);
+TB_API tb_status tb_ctx_synchronize(tb_ctx* ctx);
+/* Cap on the batch table (default 65536 entries). */
+TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
+
+/* ---- storage: replaces ComponentStore / Ecs::insert (ecs.rs:16-53, 93-98) ---------------- */
+
+/* Ecs::entity_count (ecs.rs:178-180): indices [0, n) exist. Growing keeps existing rows. */
+TB_API tb_status tb_set_entity_count(tb_ctx* ctx, uint64_t n);
+TB_API tb_status tb_entity_count(tb_ctx* ctx, uint64_t* n);
+/* Column uploads for entity indices [first, first + n). Uploading a column marks the
+ * component present on that range (ComponentStore::add_to_entity, ecs.rs:40-43). */
+TB_API tb_status tb_upload_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_transform* src);
+TB_API tb_status tb_upload_sprites(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_sprite* src);
+TB_API tb_status tb_upload_velocities(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_velocity* src);
+TB_API tb_status tb_upload_parents(tb_ctx* ctx, uint64_t first, uint64_t n, const uint32_t* src);
+/* Presence bitset words of one component, same bit layout as bitset.rs:15-36
+ * (entity e -> word e/64, bit e%64). Clearing a bit is remove_from_entity (ecs.rs:35-38). */
+TB_API tb_status tb_upload_presence(tb_ctx* ctx, int component, uint64_t first_word, uint64_t nwords,
+                                    const uint64_t* words);
+TB_API tb_status tb_download_presence(tb_ctx* ctx, int component, uint64_t first_word, uint64_t nwords,
+                                      uint64_t* words);
+TB_API tb_status tb_download_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, tb_transform* dst);
+
+/* ---- query: replaces QueryIterator::new (query.rs:94-129) -------------------------------- */
+
+/* AND of the presence bitsets of the components whose bit is set in `required_components`
+ * (bit c == enum tb_component c) over [0, entity_count); writes the matching entity
+ * indices in ASCENDING order (QueryIterator pops them from the back, query.rs:138) to
+ * `out_indices` (host, capacity `cap`, may be NULL) and the match count to `count`. */
+TB_API tb_status tb_query(tb_ctx* ctx, uint32_t required_components, uint32_t* out_indices, uint64_t cap,
+                          uint64_t* count);
+
+/* ---- compose: replaces AsMatrix4::as_matrix4 (transform.rs:24-38) ------------------------ */
+
+/* n host Transforms -> n row-major Matrix4f (16 f32 each, matrix.rs:9-12) on the host. */
+TB_API tb_status tb_as_matrix4(tb_ctx* ctx, const tb_transform* src, uint64_t n, float* dst16);
+
+/* ---- systems: what SystemBundle::step (system.rs:17-23) runs per tick -------------------- */
+
+/* [SPEC] velocity integration for every entity with Transform and Velocity:
+ * translation += velocity * dt, dt = DeltaTime.0 as f32 (state.rs:81). Queued on the
+ * context's stream; when a frame follows it is fused into that frame's first pass. */
+TB_API tb_status tb_system_integrate(tb_ctx* ctx, float dt);
+
+/* ---- frame: what a batching render_scene(&Ecs) does (tuber-graphics/src/lib.rs:134-156) -- */
+
+/* query (&Transform, &Sprite, Opt<&Parent>) -> world matrices (with parent propagation)
+ * -> sort key (layer, texture, world z, entity) -> instances + quad vertices + batch table.
+ * Synchronises the stream before returning (the counts in `out` are host values). */
+TB_API tb_status tb_frame_transform_batch(tb_ctx* ctx, tb_frame_out* out);
+/* Force one path (enum tb_path; TB_PATH_NONE == automatic). Results never depend on it. */
+TB_API tb_status tb_frame_force_path(tb_ctx* ctx, uint32_t path);
+
+/* Copies of the last frame's outputs for parity checks / CPU presenters. */
+TB_API tb_status tb_download_instances(tb_ctx* ctx, uint64_t first, uint64_t n, tb_instance* dst);
+TB_API tb_status tb_download_vertices(tb_ctx* ctx, uint64_t first_instance, uint64_t n_instances, tb_quad_vertex* dst);
+TB_API tb_status tb_download_batches(tb_ctx* ctx, uint64_t first, uint64_t n, tb_batch* dst);
+TB_API tb_status tb_download_order(tb_ctx* ctx, uint64_t first, uint64_t n, uint32_t* dst);
+/* World matrices (row-major 4x4) of entities [first, first+n) as of the last frame; entities
+ * without a Transform get the identity. Runs the compose/propagate kernels if needed. */
+TB_API tb_status tb_download_world_matrices(tb_ctx* ctx, uint64_t first, uint64_t n, float* dst16);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+
+/* Per-kernel device times of the last frame, measured with CUDA events on the launching
+ * stream (enable before the frame). Names are static strings. */
+TB_API tb_status tb_profile_enable(tb_ctx* ctx, int on);
+TB_API tb_status tb_profile_count(tb_ctx* ctx, uint32_t* n);
+TB_API tb_status tb_profile_get(tb_ctx* ctx, uint32_t i, const char** name, float* ms, uint64_t* algorithmic_bytes);
+/* Total kernels launched by this context since creation. */
+TB_API tb_status tb_launch_count(tb_ctx* ctx, uint64_t* n);
+
+/* ---- sharding across GPUs ------------------------------------------------- */
+
+/* This context holds entity indices [global_first, global_first + entity_count) of a
+ * scene partitioned by contiguous ID range over `nranks` contexts. d_order and parents
+ * are then global indices. */
+TB_API tb_status tb_shard_set(tb_ctx* ctx, int rank, int nranks, uint64_t global_first);
+/* Emit the next frames' instances / vertices / order into caller-provided DEVICE buffers
+ * (e.g. a slice of a gather buffer, or memory shared with the presenter). NULL restores
+ * the context's own buffers. Capacities are in elements. */
+TB_API tb_status tb_frame_set_output(tb_ctx* ctx, void* d_instances, void* d_vertices, void* d_order,
+                                     uint64_t capacity_instances);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TUBER_B200_H */
