@@ -130,6 +130,19 @@ TB_API tb_status tb_ctx_set_stream(tb_ctx* ctx, void* cuda_stream);
 TB_API tb_status tb_ctx_synchronize(tb_ctx* ctx);
 /* Cap on the batch table (default 65536 entries). */
 TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
+/* Tuning / test knobs; results never depend on them. Names:
+ *   "interleaved_rows" 0|1  one 64-byte row per entity instead of two 32-byte sector arrays
+ *                           (only before the first upload)
+ *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
+ *   "digit_bits"       1..8 widest radix digit (default 8)
+ *   "lt_limit"         0..16 widest (layer, texture) histogram kept as direct bins (default 16);
+ *                           wider scenes find batch boundaries by run-head detection */
+TB_API tb_status tb_ctx_set_option(tb_ctx* ctx, const char* name, int64_t value);
+
+/* Page-locked host memory for the caller's component / output arrays (uploads and downloads
+ * from pageable memory work too, at the driver's staging speed). */
+TB_API tb_status tb_host_alloc(uint64_t bytes, void** out);
+TB_API void tb_host_free(void* p);
 
 /* ---- storage: replaces ComponentStore / Ecs::insert (ecs.rs:16-53, 93-98) ---------------- */
 

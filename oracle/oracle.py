@@ -1,0 +1,217 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path.
+
+ctypes binding of oracle/_build/liboracle.so: the C++ CPU restatement of the reference's
+tuber-math / tuber-core / tuber-ecs code on the hot path (ref_math.hpp, ref_ecs.hpp) plus the
+builder-SPEC frame built from those primitives (ref_frame.hpp). The reference itself cannot be
+compiled here (Rust, no cargo/rustc in the image), so there is no oracle/_ref.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "liboracle.so")
+SOURCES = ["oracle_capi.cpp", "ref_math.hpp", "ref_ecs.hpp", "ref_frame.hpp", "Makefile"]
+
+INSTANCE_DTYPE = np.dtype([("model", "<f4", 16), ("size", "<f4", 2), ("texture", "<u4"), ("layer", "<u4")])
+VERTEX_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("uv", "<u4")])
+BATCH_DTYPE = np.dtype([("layer", "<u4"), ("texture", "<u4"), ("first_instance", "<u4"), ("count", "<u4")])
+
+_lib = None
+
+
+def build(force=False):
+    stale = force or not os.path.exists(LIB)
+    if not stale:
+        t = os.path.getmtime(LIB)
+        stale = any(os.path.getmtime(os.path.join(HERE, s)) > t for s in SOURCES)
+    if stale:
+        subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, u64, u32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_double
+        L.orc_scene_create.restype = vp
+        L.orc_scene_create.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, u64]
+        L.orc_ecs_free.argtypes = [vp]
+        L.orc_ecs_new.restype = vp
+        L.orc_ecs_new.argtypes = [u64]
+        L.orc_ecs_entity_count.restype = u64
+        L.orc_ecs_entity_count.argtypes = [vp]
+        L.orc_ecs_last_error.restype = C.c_char_p
+        L.orc_ecs_last_error.argtypes = [vp]
+        L.orc_scene_step.restype = dbl
+        L.orc_scene_step.argtypes = [vp, dbl]
+        L.orc_scene_read_transforms.argtypes = [vp, vp]
+        L.orc_frame_run.restype = vp
+        L.orc_frame_run.argtypes = [vp]
+        L.orc_frame_free.argtypes = [vp]
+        L.orc_frame_seconds.restype = dbl
+        L.orc_frame_seconds.argtypes = [vp]
+        for f in ("orc_frame_num_instances", "orc_frame_num_batches", "orc_frame_num_entities"):
+            getattr(L, f).restype = u64
+            getattr(L, f).argtypes = [vp]
+        L.orc_frame_read_world.argtypes = [vp, vp, vp]
+        for f in ("orc_frame_read_order", "orc_frame_read_keys", "orc_frame_read_instances",
+                  "orc_frame_read_vertices", "orc_frame_read_batches"):
+            getattr(L, f).argtypes = [vp, vp]
+        L.orc_sort_key.restype = u64
+        L.orc_sort_key.argtypes = [u32, u32, C.c_float]
+        L.orc_ecs_insert.restype = C.c_int64
+        L.orc_ecs_insert.argtypes = [vp, u32, vp, vp, vp]
+        L.orc_ecs_query.restype = u64
+        L.orc_ecs_query.argtypes = [vp, u32, vp, vp, vp, vp, vp, u64]
+        L.orc_ecs_query_by_ids.restype = u64
+        L.orc_ecs_query_by_ids.argtypes = [vp, u32, vp, vp, vp, vp, u64, vp, u64]
+        L.orc_ecs_query_one.restype = C.c_int64
+        L.orc_ecs_query_one.argtypes = [vp, u32, vp, vp, vp, vp]
+        L.orc_ecs_get.restype = C.c_int64
+        L.orc_ecs_get.argtypes = [vp, u64, u64, vp, u64]
+        L.orc_ecs_set.restype = C.c_int
+        L.orc_ecs_set.argtypes = [vp, u64, u64, vp, u64]
+        L.orc_ecs_delete_by_ids.argtypes = [vp, vp, u64]
+        L.orc_ecs_delete_by_query.argtypes = [vp, u32, vp, vp, vp]
+        L.orc_ecs_add_component.argtypes = [vp, u64, vp, u64, u64]
+        L.orc_ecs_remove_component.argtypes = [vp, u64, u64]
+        L.orc_ecs_insert_shared_resource.argtypes = [vp, u64, vp, u64]
+        L.orc_ecs_shared_resource.restype = C.c_int64
+        L.orc_ecs_shared_resource.argtypes = [vp, u64, vp, u64]
+        L.orc_ecs_double_borrow_conflicts.restype = C.c_int
+        L.orc_ecs_double_borrow_conflicts.argtypes = [vp, u64, u64]
+        L.orc_bundle_new.restype = vp
+        L.orc_bundle_free.argtypes = [vp]
+        L.orc_bundle_len.restype = u64
+        L.orc_bundle_len.argtypes = [vp]
+        L.orc_bundle_step.restype = C.c_int
+        L.orc_bundle_step.argtypes = [vp, vp, vp]
+        L.orc_as_matrix4.argtypes = [vp, u64, vp]
+        L.orc_as_matrix4_closed.argtypes = [vp, u64, vp]
+        L.orc_u64_set_bit.restype = u64
+        L.orc_u64_set_bit.argtypes = [u64, u64]
+        L.orc_u64_unset_bit.restype = u64
+        L.orc_u64_unset_bit.argtypes = [u64, u64]
+        L.orc_u64_bit.restype = C.c_int
+        L.orc_u64_bit.argtypes = [u64, u64]
+        for f in ("orc_words_set_bit", "orc_words_unset_bit", "orc_words_bit"):
+            getattr(L, f).restype = C.c_int
+            getattr(L, f).argtypes = [vp, u64, u64]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _f32(a, cols):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a)
+    if a.dtype.names is not None or a.dtype != np.float32:
+        a = a.view(np.float32) if a.dtype.itemsize == cols * 4 or a.dtype.names is not None else a.astype(np.float32)
+    return np.ascontiguousarray(a.reshape(-1, cols))
+
+
+def _u32(a, cols):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a)
+    if a.dtype.names is not None:
+        a = a.view(np.uint32)
+    return np.ascontiguousarray(a.reshape(-1, cols).view(np.uint32))
+
+
+class Frame:
+    """Result of ref::render_scene over a restated-reference Ecs."""
+
+    def __init__(self, h):
+        L = lib()
+        n = L.orc_frame_num_entities(h)
+        m = L.orc_frame_num_instances(h)
+        b = L.orc_frame_num_batches(h)
+        self.seconds = L.orc_frame_seconds(h)
+        self.world = np.zeros((n, 16), np.float32)
+        self.has_world = np.zeros(n, np.uint8)
+        L.orc_frame_read_world(h, _p(self.world), _p(self.has_world))
+        self.order = np.zeros(m, np.uint32)
+        self.keys = np.zeros(m, np.uint64)
+        self.instances = np.zeros(m, INSTANCE_DTYPE)
+        self.vertices = np.zeros((m, 4), VERTEX_DTYPE)
+        self.batches = np.zeros(b, BATCH_DTYPE)
+        if m:
+            L.orc_frame_read_order(h, _p(self.order))
+            L.orc_frame_read_keys(h, _p(self.keys))
+            L.orc_frame_read_instances(h, _p(self.instances))
+            L.orc_frame_read_vertices(h, _p(self.vertices))
+        if b:
+            L.orc_frame_read_batches(h, _p(self.batches))
+        L.orc_frame_free(h)
+
+
+class Scene:
+    """A restated-reference Ecs filled from component arrays (NULL array == no such store)."""
+
+    def __init__(self, n, transforms=None, sprites=None, velocities=None, parents=None,
+                 mask_transform=None, mask_sprite=None, mask_velocity=None, bitset_words=0):
+        L = lib()
+        self.n = int(n)
+        t = _f32(transforms, 12)
+        s = _u32(sprites, 4)
+        v = _f32(velocities, 3)
+        p = None if parents is None else np.ascontiguousarray(parents, dtype=np.uint32)
+        masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint64)
+                 for m in (mask_transform, mask_sprite, mask_velocity)]
+        self._h = L.orc_scene_create(self.n, _p(t), _p(masks[0]), _p(s), _p(masks[1]), _p(v), _p(masks[2]), _p(p),
+                                     int(bitset_words))
+        if not self._h:
+            raise OverflowError("entity index beyond the presence bitset (the reference panics)")
+
+    def close(self):
+        if self._h:
+            lib().orc_ecs_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, dt):
+        """One engine tick running the velocity system; returns elapsed seconds."""
+        r = lib().orc_scene_step(self._h, float(dt))
+        if r < 0:
+            raise RuntimeError(lib().orc_ecs_last_error(self._h).decode())
+        return r
+
+    def transforms(self):
+        out = np.zeros((self.n, 12), np.float32)
+        lib().orc_scene_read_transforms(self._h, _p(out))
+        return out
+
+    def frame(self):
+        return Frame(lib().orc_frame_run(self._h))
+
+
+def as_matrix4(transforms):
+    t = _f32(transforms, 12)
+    out = np.zeros((t.shape[0], 16), np.float32)
+    lib().orc_as_matrix4(_p(t), t.shape[0], _p(out))
+    return out
+
+
+def as_matrix4_closed(transforms):
+    t = _f32(transforms, 12)
+    out = np.zeros((t.shape[0], 16), np.float32)
+    lib().orc_as_matrix4_closed(_p(t), t.shape[0], _p(out))
+    return out
+
+
+def sort_key(layer, texture, z):
+    return lib().orc_sort_key(int(layer), int(texture), float(np.float32(z)))

@@ -1,0 +1,391 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded scenes (sizes the oracle finishes in seconds). Integer outputs (sorted order, batch
+table, texture/layer fields) are compared bit-exact; matrices and vertex positions within 1e-5
+(norm-wise). All scenes here rotate about z only, so the sort key's z is free of
+sin/cos and the order is exactly reproducible; test_3d_rotation covers the general rotation.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tuber_legacy_b200 import capi, scenes
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(scene, masks=None, ticks=0, dt=0.01, **options):
+    ctx = util.make_ctx(scene, masks, **options)
+    ref = util.make_oracle(scene, masks)
+    try:
+        for _ in range(ticks):
+            ctx.system_integrate(dt)
+            ref.step(dt)
+        g = util.GpuFrame(ctx)
+        r = ref.frame()
+        return ctx, ref, g, r
+    except Exception:
+        ctx.close()
+        raise
+
+
+# ---- BASELINE configs at oracle-sized N ---------------------------------------------------------
+
+def test_config1_10k_flat():
+    """configs[0]: 10k flat sprites, 1 texture, no hierarchy — the reference's own CPU-runnable case
+    (fits the reference's 65 536-entity presence bitset)."""
+    sc = scenes.config1()
+    ctx, ref, g, r = run_both(sc)
+    util.assert_frame_parity(g, r)
+    assert g.info.path == capi.TB_PATH_BUCKET and g.info.num_batches == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 2047, 2048, 2049, 3072, 6145, 70_001])
+def test_flat_sizes(n):
+    """ragged sizes around the warp / tile boundaries of the rank and emit kernels"""
+    sc = scenes.config2(n=n, seed=20 + n % 7)
+    ctx, ref, g, r = run_both(sc)
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+@pytest.mark.parametrize("z_mode", ["steps", "random"])
+def test_config2_flat_64_textures_16_layers(z_mode):
+    sc = scenes.config2(n=150_000, z_mode=z_mode)
+    ctx, ref, g, r = run_both(sc)
+    util.assert_frame_parity(g, r)
+    assert g.info.path == capi.TB_PATH_SORT
+    if z_mode == "random":
+        assert g.info.key_bits > 32  # 64-bit short keys
+    ctx.close()
+
+
+@pytest.mark.parametrize("random_parents", [False, True])
+def test_config3_hierarchy_depth8(random_parents):
+    sc = scenes.config3(n=120_000, random_parents=random_parents)
+    ctx, ref, g, r = run_both(sc)
+    assert g.info.hierarchy_levels == 8
+    util.assert_frame_parity(g, r)
+    w = ctx.download_world_matrices(0, sc.n)
+    scale = np.abs(r.world).max(axis=1, keepdims=True)
+    util.float_close(w, r.world, scale, "world matrix")
+    ctx.close()
+
+
+def test_hierarchy_shuffled_ids_uses_level_lists():
+    """ids not in BFS order: levels are not id ranges, the level kernels walk sorted lists"""
+    sc = scenes.config3(n=30_000, seed=31)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(sc.n).astype(np.uint32)  # new id of old entity i
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(sc.n, dtype=np.uint32)
+    sc.transforms = sc.transforms[inv]
+    sc.sprites = sc.sprites[inv]
+    old_parents = sc.parents[inv]
+    sc.parents = np.where(old_parents == capi.TB_NO_PARENT, capi.TB_NO_PARENT, perm[np.minimum(old_parents, sc.n - 1)]).astype(np.uint32)
+    ctx, ref, g, r = run_both(sc)
+    assert g.info.hierarchy_levels == 8
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+def test_config4_particles_velocity_system():
+    sc = scenes.config4(n=200_000)
+    ctx, ref, g, r = run_both(sc, ticks=1, dt=sc.dt)
+    util.assert_frame_parity(g, r)
+    assert g.info.path == capi.TB_PATH_BUCKET and g.info.num_batches == 4
+    # the velocity system's write-back is bit-exact
+    t = ctx.download_transforms(0, sc.n)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
+    # several more ticks and frames (steady state reuses the cached plan)
+    for _ in range(3):
+        ctx.system_integrate(sc.dt)
+        ref.step(sc.dt)
+        g = util.GpuFrame(ctx)
+        r = ref.frame()
+        util.assert_frame_parity(g, r)
+        assert g.info.replanned == 0
+    # two ticks before one frame: both are applied, in order
+    for _ in range(2):
+        ctx.system_integrate(sc.dt)
+        ref.step(sc.dt)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, ref.frame())
+    ctx.close()
+
+
+def test_velocity_moves_z_and_replans():
+    """z velocities change the key bits between frames without any upload: the cached plan goes
+    stale, the frame re-plans itself and still matches"""
+    sc = scenes.config4(n=50_000, seed=44)
+    idx = np.arange(sc.n)
+    sc.velocities["v"][:, 2] = ((idx % 7) - 3).astype(np.float32) * 10
+    ctx = util.make_ctx(sc)
+    ref = util.make_oracle(sc)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, ref.frame())
+    replans = 0
+    for _ in range(4):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        g = util.GpuFrame(ctx)
+        util.assert_frame_parity(g, ref.frame())
+        replans += g.info.replanned
+    assert replans >= 1
+    t = ctx.download_transforms(0, sc.n)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
+    ctx.close()
+
+
+def test_hierarchy_with_velocity():
+    sc = scenes.config3(n=40_000, seed=33)
+    v = np.zeros(sc.n, capi.VELOCITY_DTYPE)
+    v["v"][:, 0] = np.linspace(-50, 50, sc.n, dtype=np.float32)
+    v["v"][:, 1] = 3.0
+    sc.velocities = v
+    ctx, ref, g, r = run_both(sc, ticks=2, dt=0.01)
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+# ---- presence masks / query ------------------------------------------------------------------------
+
+def test_sparse_presence_masks():
+    sc = scenes.config4(n=90_001, seed=7)
+    sc.sprites["texture"] = np.arange(sc.n) % 5
+    sc.sprites["layer"] = np.arange(sc.n) % 3
+    masks = {capi.TB_TRANSFORM: util.random_mask(sc.n, 0.8, 1), capi.TB_SPRITE: util.random_mask(sc.n, 0.6, 2),
+             capi.TB_VELOCITY: util.random_mask(sc.n, 0.5, 3)}
+    ctx, ref, g, r = run_both(sc, masks, ticks=1)
+    assert 0 < g.info.num_instances < sc.n
+    util.assert_frame_parity(g, r)
+    t = ctx.download_transforms(0, sc.n)
+    tm = masks[capi.TB_TRANSFORM]
+    present = ((tm[np.arange(sc.n) // 64] >> (np.arange(sc.n) % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12)[present], ref.transforms().view(np.uint32)[present])
+    ctx.close()
+
+
+def test_sparse_masks_multipass():
+    sc = scenes.config2(n=80_000, seed=9, z_mode="random")
+    masks = {capi.TB_TRANSFORM: util.random_mask(sc.n, 0.7, 4), capi.TB_SPRITE: util.random_mask(sc.n, 0.7, 5)}
+    ctx, ref, g, r = run_both(sc, masks)
+    assert g.info.sort_passes > 1
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+def test_query_matches_reference_iteration():
+    """Ecs::query: same matches as the reference's QueryIterator (which yields them descending)"""
+    sc = scenes.config4(n=70_003, seed=8)
+    masks = {capi.TB_TRANSFORM: util.random_mask(sc.n, 0.9, 11), capi.TB_SPRITE: util.random_mask(sc.n, 0.5, 12),
+             capi.TB_VELOCITY: util.random_mask(sc.n, 0.3, 13)}
+    ctx = util.make_ctx(sc, masks)
+    ref = util.make_oracle(sc, masks)
+    L = oracle.lib()
+    import ctypes as C
+    from oracle.oracle import _p
+    TY = {capi.TB_TRANSFORM: 0x7472616e73666f72, capi.TB_SPRITE: 0x7370726974650000, capi.TB_VELOCITY: 0x76656c6f63697479}
+    for comps in ([capi.TB_TRANSFORM], [capi.TB_TRANSFORM, capi.TB_SPRITE], [capi.TB_TRANSFORM, capi.TB_SPRITE, capi.TB_VELOCITY]):
+        got = ctx.query(comps)
+        types = np.array([TY[c] for c in comps], np.uint64)
+        req = np.ones(len(comps), np.uint8)
+        exc = np.zeros(len(comps), np.uint8)
+        out = np.zeros(sc.n, np.uint64)
+        cnt = L.orc_ecs_query(ref._h, len(comps), _p(types), _p(req), _p(exc), _p(out), C.c_void_p(0), sc.n)
+        want = out[:cnt][::-1].astype(np.uint32)  # reference pops from the back: descending
+        np.testing.assert_array_equal(got, want)
+        assert ctx.query(comps, want_indices=False) == cnt
+    # a required component with no store matches nothing (query.rs:110)
+    assert ctx.query([capi.TB_PARENT], want_indices=False) == 0
+    ctx.close()
+
+
+# ---- compose -----------------------------------------------------------------------------------------
+
+def test_as_matrix4_matches_reference_compose():
+    rng = np.random.default_rng(0)
+    n = 50_000
+    t = np.zeros((n, 12), np.float32)
+    t[:, 0:3] = rng.uniform(-1000, 1000, (n, 3))
+    t[:, 3:6] = rng.uniform(-7, 7, (n, 3))
+    t[:, 6:9] = rng.uniform(-64, 64, (n, 3))
+    t[:, 9:12] = rng.uniform(-3, 3, (n, 3))
+    t[: n // 2, 3:5] = 0  # planar half: rotation about z only
+    # the survey's golden vectors + Transform::default()
+    t[0] = [10, 20, 0, 0, 0, 0.5, 0, 0, 0, 2, 3, 1]
+    t[1] = [1.5, -2.25, 0.75, 0.1, 0.2, 0.3, 4, 5, 6, 1, 2, 3]
+    t[2] = [100, -50, 3, 0, 0, 2.5, 16, 16, 0, 1.5, 1.5, 1]
+    t[3] = [0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1]
+    with capi.Context(16) as ctx:
+        got = ctx.as_matrix4(t)
+    want = oracle.as_matrix4(t)
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    util.float_close(got, want, scale, "as_matrix4")
+    assert np.array_equal(got[3], np.eye(4, dtype=np.float32).reshape(-1))
+    # everything that does not pass through sin/cos is exact: translation column of planar rows with c == 0
+    t2 = t[: n // 2].copy()
+    t2[:, 6:9] = 0
+    with capi.Context(16) as ctx:
+        got2 = ctx.as_matrix4(t2)
+    want2 = oracle.as_matrix4(t2)
+    assert np.array_equal(got2[:, [3, 7, 11]], want2[:, [3, 7, 11]])
+
+
+def test_3d_rotation():
+    """general Euler rotation (three sincos); rotation centre 0 keeps world z free of sin/cos, so the
+    order is still exact"""
+    sc = scenes.config2(n=60_000, seed=12)
+    rng = np.random.default_rng(3)
+    sc.transforms["angle"][:, 0] = rng.uniform(-3, 3, sc.n)
+    sc.transforms["angle"][:, 1] = rng.uniform(-3, 3, sc.n)
+    sc.transforms["rotation_center"][:] = 0
+    ctx, ref, g, r = run_both(sc)
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+# ---- every internal path gives the same bytes --------------------------------------------------------
+
+@pytest.mark.parametrize("options", [
+    {"interleaved_rows": 1},
+    {"staged_emit": 0},
+    {"digit_bits": 3},
+    {"lt_limit": 0},
+    {"lt_limit": 0, "digit_bits": 5, "staged_emit": 0, "interleaved_rows": 1},
+])
+def test_options_do_not_change_results(options):
+    for sc in (scenes.config2(n=50_000, seed=14), scenes.config4(n=50_000, seed=15), scenes.config3(n=30_000, seed=16)):
+        ctx, ref, g, r = run_both(sc, ticks=1 if sc.velocities is not None else 0, **options)
+        util.assert_frame_parity(g, r)
+        ctx.close()
+
+
+def test_force_sort_path_on_bucket_scene():
+    sc = scenes.config4(n=40_000, seed=17)
+    ctx = util.make_ctx(sc)
+    ctx.force_path(capi.TB_PATH_SORT)
+    g = util.GpuFrame(ctx)
+    assert g.info.path == capi.TB_PATH_SORT and g.info.sort_passes >= 2
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    ctx.close()
+
+
+def test_many_layer_texture_pairs_generic_batches():
+    """more than 2^16 distinct (layer, texture) bins: batch boundaries by run-head detection"""
+    n = 200_000
+    sc = scenes.config2(n=n, seed=18)
+    rng = np.random.default_rng(1)
+    sc.sprites["texture"] = rng.integers(0, 65536, n)
+    sc.sprites["layer"] = rng.integers(0, 65535, n)
+    ctx = util.make_ctx(sc)
+    ctx.set_max_batches(n)
+    g = util.GpuFrame(ctx)
+    r = util.make_oracle(sc).frame()
+    util.assert_frame_parity(g, r)
+    assert g.info.num_batches > 65536
+    ctx.close()
+
+
+# ---- edge cases --------------------------------------------------------------------------------------
+
+def test_empty_and_missing_stores():
+    with capi.Context(1024) as ctx:
+        out = ctx.frame()
+        assert out.num_instances == 0 and out.num_batches == 0
+        ctx.set_entity_count(100)
+        assert ctx.frame().num_instances == 0  # no stores at all
+        sc = scenes.config1(n=100)
+        ctx.upload_transforms(0, sc.transforms)
+        assert ctx.frame().num_instances == 0  # Transform only: (&Transform, &Sprite) matches nothing
+        ctx.upload_sprites(0, sc.sprites)
+        assert ctx.frame().num_instances == 100
+
+
+def test_identical_keys_keep_entity_order():
+    sc = scenes.config1(n=5000)
+    sc.transforms["translation"][:, 2] = 0
+    ctx, ref, g, r = run_both(sc)
+    np.testing.assert_array_equal(g.order, np.arange(sc.n, dtype=np.uint32))
+    util.assert_frame_parity(g, r)
+    assert g.info.key_bits == 0
+    ctx.close()
+
+
+def test_negative_zero_and_negative_z():
+    sc = scenes.config2(n=20_000, seed=19)
+    z = np.linspace(-5, 5, sc.n).astype(np.float32)
+    z[::97] = -0.0
+    z[::89] = 0.0
+    sc.transforms["translation"][:, 2] = z
+    ctx, ref, g, r = run_both(sc)
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+def test_errors_are_statuses_not_crashes():
+    with capi.Context(1000) as ctx:
+        with pytest.raises(capi.TuberError) as e:
+            ctx.set_entity_count(1001)
+        assert e.value.status == capi.TB_ERR_CAPACITY
+        ctx.set_entity_count(10)
+        sc = scenes.config1(n=11)
+        with pytest.raises(capi.TuberError) as e:
+            ctx.upload_transforms(0, sc.transforms)
+        assert e.value.status == capi.TB_ERR_INVALID
+        bad = scenes.config1(n=10)
+        bad.sprites["layer"][3] = 70000
+        with pytest.raises(capi.TuberError) as e:
+            ctx.upload_sprites(0, bad.sprites)
+        assert e.value.status == capi.TB_ERR_RANGE
+        # a cycle in the Parent links
+        ok = scenes.config1(n=10)
+        ctx.upload_transforms(0, ok.transforms)
+        ctx.upload_sprites(0, ok.sprites)
+        parents = np.full(10, capi.TB_NO_PARENT, np.uint32)
+        parents[2], parents[5] = 5, 2
+        ctx.upload_parents(0, parents)
+        with pytest.raises(capi.TuberError) as e:
+            ctx.frame()
+        assert e.value.status == capi.TB_ERR_CYCLE
+        parents[5] = capi.TB_NO_PARENT
+        ctx.upload_parents(0, parents)
+        assert ctx.frame().num_instances == 10
+
+
+def test_parent_without_transform_is_a_root():
+    sc = scenes.config3(n=5000, seed=21)
+    masks = {capi.TB_TRANSFORM: util.random_mask(sc.n, 0.9, 6)}
+    ctx, ref, g, r = run_both(sc, masks)
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+def test_reupload_and_growth():
+    sc = scenes.config2(n=30_000, seed=22)
+    ctx = util.make_ctx(sc, max_entities=60_000)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    # grow the entity count and change some sprites
+    sc2 = scenes.config2(n=60_000, seed=22)
+    sc2.sprites["texture"][:100] = 63
+    ctx.set_entity_count(sc2.n)
+    ctx.upload_transforms(30_000, sc2.transforms[30_000:])
+    ctx.upload_sprites(30_000, sc2.sprites[30_000:])
+    ctx.upload_sprites(0, sc2.sprites[:100])
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, util.make_oracle(sc2).frame())
+    ctx.close()
+
+
+def test_frames_are_idempotent():
+    sc = scenes.config2(n=40_000, seed=23)
+    ctx = util.make_ctx(sc)
+    a = util.GpuFrame(ctx)
+    b = util.GpuFrame(ctx)
+    assert a.instances.tobytes() == b.instances.tobytes()
+    assert a.vertices.tobytes() == b.vertices.tobytes()
+    assert a.order.tobytes() == b.order.tobytes() and a.batches.tobytes() == b.batches.tobytes()
+    ctx.close()

@@ -1,0 +1,324 @@
+"""ctypes binding of libtuber_b200.so (include/tuber_b200.h).
+
+This is the same boundary the reference's Rust FFI crate would bind: plain
+pointers and sizes, no torch types. There is no fallback: if the library is missing or no
+sm_100 GPU is present, loading / context creation raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+TB_OK = 0
+TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_OOM, TB_ERR_RANGE, TB_ERR_NO_DEVICE = 1, 2, 3, 4, 5
+TB_ERR_CAPACITY, TB_ERR_CYCLE, TB_ERR_COMM, TB_ERR_UNSUPPORTED = 6, 7, 8, 9
+TB_TRANSFORM, TB_SPRITE, TB_VELOCITY, TB_PARENT = 0, 1, 2, 3
+TB_PATH_NONE, TB_PATH_BUCKET, TB_PATH_SORT = 0, 1, 2
+TB_NO_PARENT = 0xFFFFFFFF
+
+# numpy views of the C structs
+TRANSFORM_DTYPE = np.dtype([("translation", "<f4", 3), ("angle", "<f4", 3),
+                            ("rotation_center", "<f4", 3), ("scale", "<f4", 3)])
+SPRITE_DTYPE = np.dtype([("size", "<f4", 2), ("texture", "<u4"), ("layer", "<u4")])
+VELOCITY_DTYPE = np.dtype([("v", "<f4", 3)])
+INSTANCE_DTYPE = np.dtype([("model", "<f4", 16), ("size", "<f4", 2), ("texture", "<u4"), ("layer", "<u4")])
+VERTEX_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("uv", "<u4")])
+BATCH_DTYPE = np.dtype([("layer", "<u4"), ("texture", "<u4"), ("first_instance", "<u4"), ("count", "<u4")])
+assert TRANSFORM_DTYPE.itemsize == 48 and SPRITE_DTYPE.itemsize == 16 and INSTANCE_DTYPE.itemsize == 80
+assert VERTEX_DTYPE.itemsize == 16 and BATCH_DTYPE.itemsize == 16
+
+
+class FrameOut(C.Structure):
+    _fields_ = [
+        ("num_instances", C.c_uint64),
+        ("num_batches", C.c_uint64),
+        ("d_instances", C.c_void_p),
+        ("d_vertices", C.c_void_p),
+        ("d_batches", C.c_void_p),
+        ("d_order", C.c_void_p),
+        ("path", C.c_uint32),
+        ("key_bits", C.c_uint32),
+        ("sort_passes", C.c_uint32),
+        ("kernel_launches", C.c_uint32),
+        ("hierarchy_levels", C.c_uint32),
+        ("replanned", C.c_uint32),
+    ]
+
+
+class TuberError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"tb_status {status}: {message}")
+        self.status = status
+
+
+_SIGNATURES = {
+    "tb_version": (C.c_char_p, []),
+    "tb_status_string": (C.c_char_p, [C.c_int32]),
+    "tb_ctx_create": (C.c_int32, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "tb_ctx_destroy": (None, [C.c_void_p]),
+    "tb_last_error": (C.c_char_p, [C.c_void_p]),
+    "tb_ctx_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "tb_ctx_synchronize": (C.c_int32, [C.c_void_p]),
+    "tb_ctx_set_max_batches": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "tb_ctx_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "tb_set_entity_count": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "tb_entity_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_upload_transforms": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_upload_sprites": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_upload_velocities": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_upload_parents": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_upload_presence": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_presence": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_transforms": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_query": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "tb_as_matrix4": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_system_integrate": (C.c_int32, [C.c_void_p, C.c_float]),
+    "tb_frame_transform_batch": (C.c_int32, [C.c_void_p, C.POINTER(FrameOut)]),
+    "tb_frame_force_path": (C.c_int32, [C.c_void_p, C.c_uint32]),
+    "tb_download_instances": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_vertices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_batches": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_order": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_download_world_matrices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
+    "tb_profile_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "tb_profile_get": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_uint64)]),
+    "tb_launch_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_shard_set": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_uint64]),
+    "tb_frame_set_output": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "tb_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "tb_host_free": (None, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Loads (building first if the sources are newer) the CUDA library. Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("TB_REBUILD"):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    return list(_SIGNATURES.keys())
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _as(a, dtype):
+    """`a` as a contiguous 1-D array of `dtype` records: either already that dtype, or a
+    2-D array of 4-byte scalars whose rows are exactly one record."""
+    a = np.ascontiguousarray(a)
+    if a.dtype == dtype:
+        return a.reshape(-1)
+    if a.ndim == 2 and a.dtype.itemsize == 4 and a.shape[1] * 4 == dtype.itemsize:
+        return a.view(dtype).reshape(-1)
+    raise TypeError(f"cannot view array of dtype {a.dtype} shape {a.shape} as {dtype}")
+
+
+class Context:
+    """One tb_ctx: the device-resident ECS columns and frame pipeline of one GPU."""
+
+    def __init__(self, max_entities, device=0, **options):
+        self._lib = load()
+        h = C.c_void_p()
+        st = self._lib.tb_ctx_create(int(device), int(max_entities), C.byref(h))
+        if st != TB_OK:
+            raise TuberError(st, self._lib.tb_status_string(st).decode())
+        self._h = h
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, st):
+        if st != TB_OK:
+            raise TuberError(st, self._lib.tb_last_error(self._h).decode() or self._lib.tb_status_string(st).decode())
+
+    # -- context
+    def set_option(self, name, value):
+        self._check(self._lib.tb_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.tb_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.tb_ctx_synchronize(self._h))
+
+    def set_max_batches(self, n):
+        self._check(self._lib.tb_ctx_set_max_batches(self._h, int(n)))
+
+    # -- storage
+    def set_entity_count(self, n):
+        self._check(self._lib.tb_set_entity_count(self._h, int(n)))
+
+    def entity_count(self):
+        n = C.c_uint64()
+        self._check(self._lib.tb_entity_count(self._h, C.byref(n)))
+        return n.value
+
+    def upload_transforms(self, first, transforms):
+        a = _as(transforms, TRANSFORM_DTYPE)
+        self._check(self._lib.tb_upload_transforms(self._h, int(first), a.shape[0], _ptr(a)))
+
+    def upload_sprites(self, first, sprites):
+        a = _as(sprites, SPRITE_DTYPE)
+        self._check(self._lib.tb_upload_sprites(self._h, int(first), a.shape[0], _ptr(a)))
+
+    def upload_velocities(self, first, velocities):
+        a = _as(velocities, VELOCITY_DTYPE)
+        self._check(self._lib.tb_upload_velocities(self._h, int(first), a.shape[0], _ptr(a)))
+
+    def upload_parents(self, first, parents):
+        a = np.ascontiguousarray(parents, dtype=np.uint32)
+        self._check(self._lib.tb_upload_parents(self._h, int(first), a.shape[0], _ptr(a)))
+
+    def upload_presence(self, component, first_word, words):
+        a = np.ascontiguousarray(words, dtype=np.uint64)
+        self._check(self._lib.tb_upload_presence(self._h, int(component), int(first_word), a.shape[0], _ptr(a)))
+
+    def download_presence(self, component, first_word, nwords):
+        a = np.zeros(int(nwords), dtype=np.uint64)
+        self._check(self._lib.tb_download_presence(self._h, int(component), int(first_word), int(nwords), _ptr(a)))
+        return a
+
+    def download_transforms(self, first, n):
+        a = np.zeros(int(n), dtype=TRANSFORM_DTYPE)
+        self._check(self._lib.tb_download_transforms(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    # -- query / compose / systems
+    def query(self, required_components, want_indices=True):
+        """Ascending indices of entities holding every component in `required_components`."""
+        bits = 0
+        for c in required_components:
+            bits |= 1 << c
+        count = C.c_uint64()
+        cap = self.entity_count() if want_indices else 0
+        out = np.zeros(max(cap, 1), dtype=np.uint32)
+        self._check(self._lib.tb_query(self._h, bits, _ptr(out) if want_indices else C.c_void_p(0), cap, C.byref(count)))
+        return out[:count.value] if want_indices else count.value
+
+    def as_matrix4(self, transforms):
+        a = _as(transforms, TRANSFORM_DTYPE)
+        out = np.zeros((a.shape[0], 16), dtype=np.float32)
+        self._check(self._lib.tb_as_matrix4(self._h, _ptr(a), a.shape[0], _ptr(out)))
+        return out
+
+    def system_integrate(self, dt):
+        self._check(self._lib.tb_system_integrate(self._h, float(np.float32(dt))))
+
+    # -- frame
+    def force_path(self, path):
+        self._check(self._lib.tb_frame_force_path(self._h, int(path)))
+
+    def frame(self):
+        out = FrameOut()
+        self._check(self._lib.tb_frame_transform_batch(self._h, C.byref(out)))
+        return out
+
+    def download_instances(self, n, first=0, out=None):
+        a = out if out is not None else np.zeros(int(n), dtype=INSTANCE_DTYPE)
+        self._check(self._lib.tb_download_instances(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    def download_vertices(self, n, first=0, out=None):
+        a = out if out is not None else np.zeros((int(n), 4), dtype=VERTEX_DTYPE)
+        self._check(self._lib.tb_download_vertices(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    def download_batches(self, n, first=0):
+        a = np.zeros(int(n), dtype=BATCH_DTYPE)
+        self._check(self._lib.tb_download_batches(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    def download_order(self, n, first=0, out=None):
+        a = out if out is not None else np.zeros(int(n), dtype=np.uint32)
+        self._check(self._lib.tb_download_order(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    def download_world_matrices(self, first, n):
+        a = np.zeros((int(n), 16), dtype=np.float32)
+        self._check(self._lib.tb_download_world_matrices(self._h, int(first), int(n), _ptr(a)))
+        return a
+
+    # -- instrumentation
+    def profile_enable(self, on=True):
+        self._check(self._lib.tb_profile_enable(self._h, 1 if on else 0))
+
+    def profile(self):
+        n = C.c_uint32()
+        self._check(self._lib.tb_profile_count(self._h, C.byref(n)))
+        rows = []
+        for i in range(n.value):
+            name, ms, b = C.c_char_p(), C.c_float(), C.c_uint64()
+            self._check(self._lib.tb_profile_get(self._h, i, C.byref(name), C.byref(ms), C.byref(b)))
+            rows.append((name.value.decode(), ms.value, b.value))
+        return rows
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(self._lib.tb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # -- sharding
+    def shard_set(self, rank, nranks, global_first):
+        self._check(self._lib.tb_shard_set(self._h, int(rank), int(nranks), int(global_first)))
+
+    def set_output(self, d_instances, d_vertices, d_order, capacity):
+        self._check(self._lib.tb_frame_set_output(self._h, C.c_void_p(d_instances or 0), C.c_void_p(d_vertices or 0),
+                                                  C.c_void_p(d_order or 0), int(capacity)))
+
+
+def host_alloc(nbytes):
+    """Page-locked host buffer (cudaMallocHost) as a uint8 numpy array; free with host_free."""
+    lib = load()
+    p = C.c_void_p()
+    st = lib.tb_host_alloc(int(nbytes), C.byref(p))
+    if st != TB_OK:
+        raise TuberError(st, "tb_host_alloc failed")
+    buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.uint8), p.value
+
+
+def host_free(ptr):
+    load().tb_host_free(C.c_void_p(ptr))

@@ -9,14 +9,24 @@
 
 namespace tb {
 
-// One packed 64-byte row of the (Transform, Sprite) table — exactly two 32-byte DRAM
-// sectors, so a random gather of one entity moves no wasted bytes.
-//   a = {t.x, t.y, t.z, angle.x}   b = {angle.y, angle.z, c.x, c.y}
-//   c = {c.z, s.x, s.y, s.z}       d = {size.w, size.h, texture, layer}
-struct __align__(16) Row {
-    float4 a, b, c, d;
+// Device row of the (Transform, Sprite) table: two 32-byte DRAM sectors per entity
+// (DESIGN.md §2). Sector A holds everything the sort key and the velocity system touch,
+// sector B the rest, so the key pass reads 32 B/entity and the integrate write-back dirties
+// one sector only.
+//   A0 = {t.x, t.y, t.z, c.z}        A1 = {s.z, angle.x, angle.y, texture | layer << 16}
+//   B0 = {angle.z, c.x, c.y, s.x}    B1 = {s.y, size.w, size.h, 0}
+// `stride` is in float4 units: 2 when A and B are separate arrays, 4 when they are
+// interleaved into one 64-byte row (b == a + 2).
+struct RowView {
+    float4* a;
+    float4* b;
+    uint32_t stride;
 };
-static_assert(sizeof(Row) == 64, "Row is 64 bytes");
+
+// The four 16-byte quarters of one row, in registers.
+struct Row {
+    float4 a0, a1, b0, b1;
+};
 
 // Affine 3x4 world matrix, row-major rows 0..2 (row 3 is always 0,0,0,1).
 struct Affine {
@@ -83,10 +93,11 @@ __device__ __forceinline__ float4 compose_row(const float* Rj, float sj, float c
 }
 
 // Full local matrix of a row.
-__device__ __forceinline__ Affine compose_local(const float4 a, const float4 b, const float4 c) {
-    const float tx = a.x, ty = a.y, tz = a.z, ax = a.w;
-    const float ay = b.x, az = b.y, cx = b.z, cy = b.w;
-    const float cz = c.x, sx = c.y, sy = c.z, sz = c.w;
+__device__ __forceinline__ Affine compose_local(const Row& r) {
+    const float tx = r.a0.x, ty = r.a0.y, tz = r.a0.z, cz = r.a0.w;
+    const float sz = r.a1.x, ax = r.a1.y, ay = r.a1.z;
+    const float az = r.b0.x, cx = r.b0.y, cy = r.b0.z, sx = r.b0.w;
+    const float sy = r.b1.x;
     float R[9];
     rotation3x3(ax, ay, az, R);
     Affine m;
@@ -96,16 +107,24 @@ __device__ __forceinline__ Affine compose_local(const float4 a, const float4 b, 
     return m;
 }
 
-// Only M[2][3] (the world z of a flat entity) — all the key pass needs. For a 2-D
-// transform this is trig-free: R[2] = (0, 0, 1).
-__device__ __forceinline__ float compose_local_z(const float4 a, const float4 b, const float4 c) {
-    const float tz = a.z, ax = a.w;
-    const float ay = b.x, az = b.y, cx = b.z, cy = b.w;
-    const float cz = c.x, sz = c.w;
-    if (ax == 0.0f && ay == 0.0f) {
-        const float R2[3] = {0.0f, 0.0f, 1.0f};
-        return compose_row(R2, sz, cz, tz, cx, cy, cz).w;
-    }
+// True when the row's rotation is about z only (every 2-D sprite): then M[2][3] needs no
+// trigonometry and nothing from sector B.
+__device__ __forceinline__ bool is_planar(const float4 a1) { return a1.y == 0.0f && a1.z == 0.0f; }
+
+// M[2][3] (the world z of a flat entity) from sector A alone, valid when is_planar(a1):
+// R[2] = (0, 0, 1), so with finite c.x, c.y the row-2 sum is
+//   ((+-0 + +-0) + s.z*(-c.z)) + (s.z*c.z + s.z*t.z).
+__device__ __forceinline__ float planar_z(const float4 a0, const float4 a1) {
+    const float tz = a0.z, cz = a0.w, sz = a1.x;
+    float trj = addr(mulr(sz, cz), mulr(sz, tz));
+    float acc = addr(0.0f, mulr(sz, -cz));
+    return addr(acc, trj);
+}
+
+// M[2][3] of any row (general 3-D rotation needs sector B too).
+__device__ __forceinline__ float local_z(const Row& r) {
+    const float tz = r.a0.z, cz = r.a0.w, sz = r.a1.x, ax = r.a1.y, ay = r.a1.z;
+    const float az = r.b0.x, cx = r.b0.y, cy = r.b0.z;
     float R[9];
     rotation3x3(ax, ay, az, R);
     return compose_row(R + 6, sz, cz, tz, cx, cy, cz).w;
@@ -142,44 +161,6 @@ __device__ __forceinline__ uint64_t sort_key(uint32_t layer, uint32_t texture, f
 //   ((m0*x + m1*y) + m2*0) + m3*1  — the m2*0 term is a value-neutral +-0.
 __device__ __forceinline__ float corner_coord(float m0, float m1, float m3, float x, float y) {
     return addr(addr(mulr(m0, x), mulr(m1, y)), m3);
-}
-
-// Bit-gather (pext) of the varying key bits, as up to 8 contiguous runs. Built on the host
-// (or by make_plan_kernel) from the frame's OR/AND masks.
-struct PextPlan {
-    uint32_t nruns;
-    uint32_t nbits;       // total extracted bits
-    uint8_t src_shift[16];
-    uint8_t width[16];
-    uint8_t dst_shift[16];
-};
-
-__device__ __forceinline__ uint64_t pext_runs(uint64_t key, const PextPlan& p) {
-    uint64_t out = 0;
-#pragma unroll 4
-    for (uint32_t r = 0; r < p.nruns; ++r) {
-        uint64_t m = (p.width[r] >= 64) ? ~0ull : ((1ull << p.width[r]) - 1ull);
-        out |= ((key >> p.src_shift[r]) & m) << p.dst_shift[r];
-    }
-    return out;
-}
-
-__host__ __device__ inline bool build_pext_plan(uint64_t varying, PextPlan* p) {
-    p->nruns = 0;
-    p->nbits = 0;
-    uint32_t bit = 0;
-    while (bit < 64) {
-        if (!((varying >> bit) & 1ull)) { ++bit; continue; }
-        uint32_t start = bit;
-        while (bit < 64 && ((varying >> bit) & 1ull)) ++bit;
-        if (p->nruns >= 16) return false;
-        p->src_shift[p->nruns] = (uint8_t)start;
-        p->width[p->nruns] = (uint8_t)(bit - start);
-        p->dst_shift[p->nruns] = (uint8_t)p->nbits;
-        p->nbits += bit - start;
-        p->nruns += 1;
-    }
-    return true;
 }
 
 }  // namespace tb

@@ -1,0 +1,1115 @@
+// sm_100a kernels of the tuber hot path. HBM-bound integer/float streaming
+// work: no tensor cores. What matters here is 128-bit coalesced access, one pass over each
+// byte, grids sized in multiples of the SM count, and a single stable counting/radix
+// placement fused with the emit so sorted payloads are written exactly once.
+//
+//   convert_*            AoS host layouts  -> two-sector device rows           (upload)
+//   prepare_flat         velocity system + sort key + key masks + histograms   (frame pass A)
+//   prepare_level        same for one hierarchy level, plus parent * local     (frame pass A, hierarchy)
+//   scan_hist            digit histograms -> bucket bases
+//   build_batches        (layer, texture) histogram -> batch table
+//   radix_scatter        one stable LSD pass of (short key, entity) pairs, decoupled look-back
+//   emit                 final stable pass fused with compose + instance/vertex emission
+//   query_*              presence-mask AND -> packed ascending entity indices  (Ecs::query)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "compose.cuh"
+#include "plan.h"
+
+namespace tb {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
+constexpr uint32_t kFlagLocal = 1u << 30;
+constexpr uint32_t kFlagIncl = 2u << 30;
+constexpr uint32_t kCountMask = (1u << 30) - 1u;
+
+// ---- small helpers ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Streaming (evict-first) 128-bit store: emitted buffers are written once and not re-read by
+// this frame, so they should not displace the rows / keys that are.
+__device__ __forceinline__ void st_cs_f4(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ bool mask_bit(const uint64_t* mask, uint32_t i) {
+    return mask == nullptr || ((__ldg(mask + (i >> 6)) >> (i & 63u)) & 1ull);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ Row load_row(const RowView& rv, uint32_t i) {
+    Row r;
+    const size_t o = (size_t)i * rv.stride;
+    r.a0 = rv.a[o];
+    r.a1 = rv.a[o + 1];
+    r.b0 = rv.b[o];
+    r.b1 = rv.b[o + 1];
+    return r;
+}
+
+// Full 64-bit sort key of a flat row (sector A only when planar).
+__device__ __forceinline__ uint64_t flat_key(const RowView& rv, uint32_t i, const float4 a0, const float4 a1) {
+    const uint32_t tl = __float_as_uint(a1.w);
+    float z;
+    if (is_planar(a1)) {
+        z = planar_z(a0, a1);
+    } else {
+        Row r;
+        r.a0 = a0;
+        r.a1 = a1;
+        const size_t o = (size_t)i * rv.stride;
+        r.b0 = rv.b[o];
+        r.b1 = rv.b[o + 1];
+        z = local_z(r);
+    }
+    return sort_key(tl >> 16, tl & 0xFFFFu, z);
+}
+
+// World row written by the hierarchy path: {r0, r1, r2, {size.w, size.h, texlayer, 0}}.
+struct WorldRow {
+    float4 r0, r1, r2, s;
+};
+
+__device__ __forceinline__ uint64_t world_key(const float4 r2, const float4 s) {
+    const uint32_t tl = __float_as_uint(s.z);
+    return sort_key(tl >> 16, tl & 0xFFFFu, r2.w);
+}
+
+// ---- upload conversion -----------------------------------------------------------------------
+
+// tb_transform[first..first+n) (12 f32 each, transform.rs:5-11 order) -> row sectors.
+__global__ void __launch_bounds__(kThreads) convert_transforms_kernel(const float* __restrict__ src, RowView rv,
+                                                                       uint32_t first, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = src + (size_t)i * 12;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = __ldg(t + k);
+    const size_t o = (size_t)(first + i) * rv.stride;
+    // A0 = {t.x, t.y, t.z, c.z}
+    rv.a[o] = make_float4(v[0], v[1], v[2], v[8]);
+    // A1 = {s.z, angle.x, angle.y, texlayer}: keep .w
+    float* a1 = reinterpret_cast<float*>(rv.a + o + 1);
+    a1[0] = v[11];
+    a1[1] = v[3];
+    a1[2] = v[4];
+    // B0 = {angle.z, c.x, c.y, s.x}
+    rv.b[o] = make_float4(v[5], v[6], v[7], v[9]);
+    // B1 = {s.y, size.w, size.h, 0}: keep .y .z
+    float* b1 = reinterpret_cast<float*>(rv.b + o + 1);
+    b1[0] = v[10];
+}
+
+__global__ void __launch_bounds__(kThreads) convert_sprites_kernel(const uint32_t* __restrict__ src, RowView rv,
+                                                                    uint32_t first, uint32_t n, uint32_t* range_err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    if (s.z > 0xFFFFu || s.w > 0xFFFEu) atomicAdd(range_err, 1u);
+    const size_t o = (size_t)(first + i) * rv.stride;
+    float* a1 = reinterpret_cast<float*>(rv.a + o + 1);
+    a1[3] = __uint_as_float((s.z & 0xFFFFu) | (s.w << 16));
+    float* b1 = reinterpret_cast<float*>(rv.b + o + 1);
+    b1[1] = __uint_as_float(s.x);
+    b1[2] = __uint_as_float(s.y);
+    b1[3] = 0.0f;
+}
+
+// rows -> tb_transform (download for parity checks of the velocity system)
+__global__ void __launch_bounds__(kThreads) unconvert_transforms_kernel(RowView rv, uint32_t first, uint32_t n,
+                                                                         float* __restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Row r = load_row(rv, first + i);
+    float* t = dst + (size_t)i * 12;
+    t[0] = r.a0.x; t[1] = r.a0.y; t[2] = r.a0.z;
+    t[3] = r.a1.y; t[4] = r.a1.z; t[5] = r.b0.x;
+    t[6] = r.b0.y; t[7] = r.b0.z; t[8] = r.a0.w;
+    t[9] = r.b0.w; t[10] = r.b1.x; t[11] = r.a1.x;
+}
+
+// Sets or clears presence bits [first, first+n) of one mask (whole words in the middle).
+__global__ void __launch_bounds__(kThreads) mark_presence_kernel(uint64_t* mask, uint64_t first, uint64_t n, int set) {
+    uint64_t w0 = first >> 6, w1 = (first + n - 1) >> 6;
+    uint64_t w = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (w > w1) return;
+    uint64_t m = ~0ull;
+    if (w == w0) m &= ~0ull << (first & 63);
+    if (w == w1) {
+        uint32_t last = (uint32_t)((first + n - 1) & 63);
+        m &= (last == 63) ? ~0ull : ((1ull << (last + 1)) - 1ull);
+    }
+    if (set) atomicOr((unsigned long long*)&mask[w], m);
+    else atomicAnd((unsigned long long*)&mask[w], ~m);
+}
+
+// Presence of the Parent component over [first, first+n): bit e == (parent[e] != TB_NO_PARENT).
+__global__ void __launch_bounds__(kThreads) mark_parent_presence_kernel(uint64_t* mask, const uint32_t* __restrict__ parent,
+                                                                         uint64_t first, uint64_t n) {
+    const uint64_t w0 = first >> 6, w1 = (first + n - 1) >> 6;
+    const uint64_t w = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (w > w1) return;
+    uint64_t set = 0, range = 0;
+    for (uint32_t b = 0; b < 64; ++b) {
+        const uint64_t e = w * 64 + b;
+        if (e < first || e >= first + n) continue;
+        range |= 1ull << b;
+        if (parent[e] != 0xFFFFFFFFu) set |= 1ull << b;
+    }
+    atomicAnd((unsigned long long*)&mask[w], ~range);
+    atomicOr((unsigned long long*)&mask[w], set);
+}
+
+// ---- frame pass A: velocity system + key + masks + histograms --------------------------------
+
+struct PrepParams {
+    uint32_t n;            // entity_count
+    RowView rows;
+    const uint64_t* mask_t;  // presence masks, nullptr == present on every entity
+    const uint64_t* mask_s;
+    const uint64_t* mask_v;
+    const float* vel;      // tb_velocity AoS (3 f32), nullptr when no Velocity store
+    float dt;
+    uint32_t integrate;    // run the velocity system in this pass
+    uint32_t have_plan;    // 0: only masks + count (plan discovery)
+    uint32_t write_keys;   // short keys to keys_out (multi-pass plans)
+    uint32_t lt_mode;      // 0: none (aliases digit pass 0), 1: shared-memory bins, 2: global bins
+    void* keys_out;
+    uint32_t* hist;        // [kMaxPasses][256]
+    uint32_t* lt_hist;     // [1 << ltbits]
+    unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+    FramePlan plan;
+};
+
+constexpr int kPrepItems = 4;
+
+struct PrepShared {
+    uint32_t hist[kMaxPasses][256];
+    uint32_t lt[2048];
+    unsigned long long k_or, k_and;
+    uint32_t count;
+};
+
+// Accumulates one key into the per-block plan statistics and histograms.
+__device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, bool renderable, uint64_t key,
+                                             uint32_t i) {
+    // key masks: warp-reduce then one shared atomic per warp
+    const uint32_t act = __ballot_sync(0xffffffffu, renderable);
+    if (act == 0) return;
+    uint32_t lo = renderable ? (uint32_t)key : 0u, hi = renderable ? (uint32_t)(key >> 32) : 0u;
+    uint32_t nlo = renderable ? (uint32_t)key : 0xFFFFFFFFu, nhi = renderable ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    nlo = __reduce_and_sync(0xffffffffu, nlo);
+    nhi = __reduce_and_sync(0xffffffffu, nhi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&sh.k_or, ((unsigned long long)hi << 32) | lo);
+        atomicAnd(&sh.k_and, ((unsigned long long)nhi << 32) | nlo);
+        atomicAdd(&sh.count, (uint32_t)__popc(act));
+    }
+    if (!p.have_plan || !renderable) return;
+    const uint64_t sk = pext_runs(key, p.plan.pext);
+    for (uint32_t q = 0; q < p.plan.npasses; ++q) {
+        const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
+        atomicAdd(&sh.hist[q][d], 1u);
+    }
+    if (p.lt_mode == 1) atomicAdd(&sh.lt[(uint32_t)(sk >> p.plan.zbits)], 1u);
+    else if (p.lt_mode == 2) atomicAdd(&p.lt_hist[(uint32_t)(sk >> p.plan.zbits)], 1u);
+    if (p.write_keys) {
+        if (p.plan.key64) reinterpret_cast<uint64_t*>(p.keys_out)[i] = sk;
+        else reinterpret_cast<uint32_t*>(p.keys_out)[i] = (uint32_t)sk;
+    }
+}
+
+__device__ __forceinline__ void prep_init(const PrepParams& p, PrepShared& sh) {
+    for (uint32_t k = threadIdx.x; k < kMaxPasses * 256; k += blockDim.x) (&sh.hist[0][0])[k] = 0;
+    for (uint32_t k = threadIdx.x; k < 2048; k += blockDim.x) sh.lt[k] = 0;
+    if (threadIdx.x == 0) {
+        sh.k_or = 0ull;
+        sh.k_and = ~0ull;
+        sh.count = 0;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh) {
+    __syncthreads();
+    if (p.have_plan) {
+        for (uint32_t q = 0; q < p.plan.npasses; ++q) {
+            const uint32_t R = 1u << p.plan.bits[q];
+            for (uint32_t d = threadIdx.x; d < R; d += blockDim.x) {
+                const uint32_t c = sh.hist[q][d];
+                if (c) atomicAdd(&p.hist[q * 256 + d], c);
+            }
+        }
+        if (p.lt_mode == 1) {
+            const uint32_t B = 1u << p.plan.ltbits;
+            for (uint32_t d = threadIdx.x; d < B; d += blockDim.x) {
+                const uint32_t c = sh.lt[d];
+                if (c) atomicAdd(&p.lt_hist[d], c);
+            }
+        }
+    }
+    if (threadIdx.x == 0 && sh.count) {
+        atomicOr(&p.stats[0], sh.k_or);
+        atomicOr(&p.stats[1], ~sh.k_and);  // OR of ~key: all-zero scratch is the neutral element
+        atomicAdd(&p.stats[2], (unsigned long long)sh.count);
+    }
+}
+
+// Flat scenes (no Parent anywhere): per entity, the velocity system
+// (translation += velocity * dt, [SPEC]; idiom of system.rs:132-137) then the sort key of
+// (&Transform, &Sprite) matches (query.rs:109-120 presence AND).
+__global__ void __launch_bounds__(kThreads) prepare_flat_kernel(const PrepParams p) {
+    __shared__ PrepShared sh;
+    prep_init(p, sh);
+    const uint32_t tile_elems = kThreads * kPrepItems;
+    const uint32_t ntiles = (p.n + tile_elems - 1) / tile_elems;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t base = tile * tile_elems + threadIdx.x;
+        float4 a0[kPrepItems], a1[kPrepItems];
+        bool has_t[kPrepItems], rend[kPrepItems];
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {
+            const uint32_t i = base + k * kThreads;
+            has_t[k] = i < p.n && mask_bit(p.mask_t, i);
+            rend[k] = has_t[k] && mask_bit(p.mask_s, i);
+            if (has_t[k]) {
+                const size_t o = (size_t)i * p.rows.stride;
+                a0[k] = p.rows.a[o];
+                a1[k] = p.rows.a[o + 1];
+            }
+        }
+        if (p.integrate) {
+#pragma unroll
+            for (int k = 0; k < kPrepItems; ++k) {
+                const uint32_t i = base + k * kThreads;
+                if (has_t[k] && p.vel != nullptr && mask_bit(p.mask_v, i)) {
+                    const float* v = p.vel + (size_t)i * 3;
+                    const float vx = __ldg(v), vy = __ldg(v + 1), vz = __ldg(v + 2);
+                    a0[k].x = addr(a0[k].x, mulr(vx, p.dt));
+                    a0[k].y = addr(a0[k].y, mulr(vy, p.dt));
+                    a0[k].z = addr(a0[k].z, mulr(vz, p.dt));
+                    p.rows.a[(size_t)i * p.rows.stride] = a0[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {
+            const uint32_t i = base + k * kThreads;
+            uint64_t key = 0;
+            if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
+            prep_account(p, sh, rend[k], key, i);
+        }
+    }
+    prep_flush(p, sh);
+}
+
+// ---- hierarchy: one level of world = world[parent] * local ------------------------------------
+
+struct LevelParams {
+    PrepParams prep;
+    const uint32_t* parent;      // per entity, TB_NO_PARENT for roots (already sanitised: see levels)
+    const uint32_t* list;        // entities of this level, nullptr when the level is an id range
+    uint32_t first;              // first entity id (range mode) / first list slot
+    uint32_t count;              // entities in this level
+    uint32_t level;              // 0 == roots
+    uint32_t global_first;       // id of this shard's entity 0 in the parents' index space
+    WorldRow* world;             // per entity
+};
+
+// Level L of the scene graph. Siblings are usually contiguous, so lanes with the same parent
+// elect one loader and share the parent's world row by warp shuffle.
+__global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelParams lp) {
+    __shared__ PrepShared sh;
+    const PrepParams& p = lp.prep;
+    prep_init(p, sh);
+    const uint32_t nchunks = (lp.count + kThreads - 1) / kThreads;
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const uint32_t slot = chunk * kThreads + threadIdx.x;
+        bool live = slot < lp.count;
+        uint32_t e = 0;
+        if (live) {
+            e = lp.list ? __ldg(lp.list + lp.first + slot) : lp.first + slot;
+            live = mask_bit(p.mask_t, e);  // level 0 also lists entities without a Transform
+        }
+        Row r;
+        Affine w;
+        uint32_t par = 0xFFFFFFFFu;
+        if (live) {
+            r = load_row(p.rows, e);
+            if (p.integrate && p.vel != nullptr && mask_bit(p.mask_v, e)) {
+                const float* v = p.vel + (size_t)e * 3;
+                const float vx = __ldg(v), vy = __ldg(v + 1), vz = __ldg(v + 2);
+                r.a0.x = addr(r.a0.x, mulr(vx, p.dt));
+                r.a0.y = addr(r.a0.y, mulr(vy, p.dt));
+                r.a0.z = addr(r.a0.z, mulr(vz, p.dt));
+                p.rows.a[(size_t)e * p.rows.stride] = r.a0;
+            }
+            w = compose_local(r);
+            if (lp.level > 0) par = __ldg(lp.parent + e) - lp.global_first;
+        }
+        if (lp.level > 0) {
+            // warp-shuffle parent broadcast
+            const uint32_t peers = __match_any_sync(0xffffffffu, par);
+            const int leader = __ffs(peers) - 1;
+            float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0;
+            if (live && (int)(threadIdx.x & 31) == leader) {
+                const float4* pw = reinterpret_cast<const float4*>(lp.world + par);
+                p0 = pw[0];
+                p1 = pw[1];
+                p2 = pw[2];
+            }
+            Affine P;
+            P.r0.x = __shfl_sync(0xffffffffu, p0.x, leader); P.r0.y = __shfl_sync(0xffffffffu, p0.y, leader);
+            P.r0.z = __shfl_sync(0xffffffffu, p0.z, leader); P.r0.w = __shfl_sync(0xffffffffu, p0.w, leader);
+            P.r1.x = __shfl_sync(0xffffffffu, p1.x, leader); P.r1.y = __shfl_sync(0xffffffffu, p1.y, leader);
+            P.r1.z = __shfl_sync(0xffffffffu, p1.z, leader); P.r1.w = __shfl_sync(0xffffffffu, p1.w, leader);
+            P.r2.x = __shfl_sync(0xffffffffu, p2.x, leader); P.r2.y = __shfl_sync(0xffffffffu, p2.y, leader);
+            P.r2.z = __shfl_sync(0xffffffffu, p2.z, leader); P.r2.w = __shfl_sync(0xffffffffu, p2.w, leader);
+            if (live) w = mul_affine(P, w);
+        }
+        bool rend = false;
+        uint64_t key = 0;
+        if (live) {
+            WorldRow wr;
+            wr.r0 = w.r0;
+            wr.r1 = w.r1;
+            wr.r2 = w.r2;
+            wr.s = make_float4(r.b1.y, r.b1.z, r.a1.w, 0.0f);
+            float4* dst = reinterpret_cast<float4*>(lp.world + e);
+            dst[0] = wr.r0;
+            dst[1] = wr.r1;
+            dst[2] = wr.r2;
+            dst[3] = wr.s;
+            rend = mask_bit(p.mask_s, e);
+            if (rend) key = world_key(wr.r2, wr.s);
+        }
+        prep_account(p, sh, rend, key, e);
+    }
+    prep_flush(p, sh);
+}
+
+// ---- histogram -> bucket bases; (layer, texture) histogram -> batch table -----------------------
+
+// One block per radix pass: exclusive scan of its 256-bin digit histogram, in place.
+__global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
+    __shared__ uint32_t wsum[8];
+    uint32_t* h = hist + blockIdx.x * 256;
+    const uint32_t v = h[threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t add = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) add += wsum[w];
+    h[threadIdx.x] = x + add - v;
+}
+
+struct BatchOut {
+    uint32_t layer, texture, first_instance, count;
+};
+
+// Every non-empty (layer, texture) bin is one batch: first = exclusive prefix, count = bin.
+// `bins` has 1 << ltbits entries (when it aliases digit pass 0 it must be read BEFORE
+// scan_hist_kernel rewrites it: the host orders the launches). Single block.
+__global__ void __launch_bounds__(1024) build_batches_kernel(const uint32_t* __restrict__ bins, uint32_t nbins,
+                                                              FramePlan plan, BatchOut* out, uint32_t max_batches,
+                                                              uint32_t* num_batches) {
+    __shared__ uint32_t s_cnt[1024], s_sum[1024];
+    const uint32_t per = (nbins + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t nz = 0, sum = 0;
+    for (uint32_t b = b0; b < b0 + per && b < nbins; ++b) {
+        const uint32_t c = bins[b];
+        nz += c != 0;
+        sum += c;
+    }
+    s_cnt[threadIdx.x] = nz;
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t c = 0, s = 0;
+        if (threadIdx.x >= o) {
+            c = s_cnt[threadIdx.x - o];
+            s = s_sum[threadIdx.x - o];
+        }
+        __syncthreads();
+        s_cnt[threadIdx.x] += c;
+        s_sum[threadIdx.x] += s;
+        __syncthreads();
+    }
+    uint32_t slot = s_cnt[threadIdx.x] - nz;
+    uint32_t first = s_sum[threadIdx.x] - sum;
+    for (uint32_t b = b0; b < b0 + per && b < nbins; ++b) {
+        const uint32_t c = bins[b];
+        if (c) {
+            if (slot < max_batches) {
+                const uint64_t key = plan.constant | pdep_runs((uint64_t)b << plan.zbits, plan.pext);
+                BatchOut o;
+                o.layer = (uint32_t)(key >> 48);
+                o.texture = (uint32_t)(key >> 32) & 0xFFFFu;
+                o.first_instance = first;
+                o.count = c;
+                out[slot] = o;
+            }
+            ++slot;
+            first += c;
+        }
+    }
+    if (threadIdx.x == 1023) *num_batches = s_cnt[1023];
+}
+
+// ---- stable tile ranking with decoupled look-back (shared by scatter and emit) ------------------
+
+struct RankShared {
+    uint32_t wcnt[kWarps][256];  // per-warp digit counters, then per-warp exclusive prefixes
+    uint32_t dstart[256];        // first tile slot of each digit
+    uint32_t dbase[256];         // destination of digit d's slot s is dbase[d] + s
+    uint32_t wsum[kWarps];
+    uint32_t tile;
+    uint32_t tile_count;
+};
+
+struct PassParams {
+    uint32_t n;              // positions to visit
+    const unsigned long long* count_ptr;  // when non-null only positions < *count_ptr hold elements
+                                          // (passes after the first: the renderable count lives on the device)
+    uint32_t shift, bits;    // this pass's digit of the short key
+    const uint32_t* gbase;   // exclusive scan of this pass's digit histogram
+    uint32_t* status;        // [tiles][1 << bits] look-back words, zeroed per frame
+    uint32_t* tile_counter;  // zeroed per frame
+};
+
+// Ranks ITEMS digits per thread (warp-striped order: item k of lane l in warp w is element
+// w*ITEMS*32 + k*32 + l of the tile) into stable tile slots, publishes the tile's digit counts,
+// looks back for the tile's global digit offsets and leaves dbase[] ready. Invalid items
+// (kInvalidDigit) get no slot.
+template <int ITEMS>
+__device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, const uint32_t (&digit)[ITEMS],
+                                          uint32_t (&slot)[ITEMS]) {
+    const uint32_t R = 1u << pp.bits;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t k = threadIdx.x; k < kWarps * 256; k += kThreads) (&rs.wcnt[0][0])[k] = 0;
+    __syncthreads();
+    uint32_t* wc = rs.wcnt[warp];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = digit[k];
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader && d != kInvalidDigit) {
+            base = wc[d];
+            wc[d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        slot[k] = base + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, tile total
+    uint32_t total = 0;
+    if (threadIdx.x < R) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = rs.wcnt[w][threadIdx.x];
+            rs.wcnt[w][threadIdx.x] = total;
+            total += c;
+        }
+    }
+    // publish the local count as early as possible
+    uint32_t* st = pp.status + (size_t)rs.tile * R + threadIdx.x;
+    if (threadIdx.x < R) st_relaxed_u32(st, (rs.tile == 0 ? kFlagIncl : kFlagLocal) | total);
+    // block exclusive scan of the totals -> dstart
+    uint32_t x = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) rs.wsum[warp] = x;
+    __syncthreads();
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if ((uint32_t)w < warp) add += rs.wsum[w];
+    const uint32_t dstart = x + add - total;
+    if (threadIdx.x == kThreads - 1) rs.tile_count = x + add;
+    if (threadIdx.x < R) {
+        rs.dstart[threadIdx.x] = dstart;
+        uint32_t excl = 0;
+        if (rs.tile > 0) {
+            for (int t = (int)rs.tile - 1; t >= 0; --t) {
+                uint32_t v;
+                do {
+                    v = ld_relaxed_u32(pp.status + (size_t)t * R + threadIdx.x);
+                } while ((v >> 30) == 0u);
+                excl += v & kCountMask;
+                if ((v >> 30) == 2u) break;
+            }
+            st_relaxed_u32(st, kFlagIncl | (excl + total));
+        }
+        rs.dbase[threadIdx.x] = pp.gbase[threadIdx.x] + excl - dstart;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = digit[k];
+        if (d != kInvalidDigit) slot[k] += rs.dstart[d] + rs.wcnt[warp][d];
+    }
+}
+
+__device__ __forceinline__ void claim_tile(RankShared& rs, const PassParams& pp) {
+    if (threadIdx.x == 0) rs.tile = atomicAdd(pp.tile_counter, 1u);
+    __syncthreads();
+}
+
+// ---- one LSD scatter pass of (short key, entity) pairs ------------------------------------------
+
+template <typename KeyT>
+struct ScatterParams {
+    PassParams pass;
+    const KeyT* keys_in;
+    const uint32_t* idx_in;  // nullptr on the first pass: the entity is the position
+    const uint64_t* mask_t;  // first pass only: which positions are renderable
+    const uint64_t* mask_s;
+    KeyT* keys_out;
+    uint32_t* idx_out;
+};
+
+constexpr int kScatterItems = 12;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const ScatterParams<KeyT> sp) {
+    constexpr int ITEMS = kScatterItems;
+    constexpr uint32_t TILE = kThreads * ITEMS;
+    __shared__ RankShared rs;
+    __shared__ KeyT s_key[TILE];
+    __shared__ uint32_t s_idx[TILE];
+    claim_tile(rs, sp.pass);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile_base = rs.tile * TILE;
+    const uint32_t mask = (1u << sp.pass.bits) - 1u;
+    KeyT key[ITEMS];
+    uint32_t idx[ITEMS], digit[ITEMS], slot[ITEMS];
+    const uint32_t n_eff = sp.pass.count_ptr ? min(sp.pass.n, (uint32_t)*sp.pass.count_ptr) : sp.pass.n;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t pos = tile_base + warp * (ITEMS * 32) + k * 32 + lane;
+        bool valid = pos < n_eff;
+        if (valid && sp.idx_in == nullptr) valid = mask_bit(sp.mask_t, pos) && mask_bit(sp.mask_s, pos);
+        key[k] = 0;
+        idx[k] = pos;
+        if (valid) {
+            key[k] = sp.keys_in[pos];
+            if (sp.idx_in != nullptr) idx[k] = sp.idx_in[pos];
+        }
+        digit[k] = valid ? ((uint32_t)(key[k] >> sp.pass.shift) & mask) : kInvalidDigit;
+    }
+    rank_tile<ITEMS>(rs, sp.pass, digit, slot);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (digit[k] != kInvalidDigit) {
+            s_key[slot[k]] = key[k];
+            s_idx[slot[k]] = idx[k];
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = rs.tile_count;
+    for (uint32_t s = threadIdx.x; s < cnt; s += kThreads) {
+        const KeyT kk = s_key[s];
+        const uint32_t d = (uint32_t)(kk >> sp.pass.shift) & mask;
+        const uint32_t dst = rs.dbase[d] + s;
+        sp.keys_out[dst] = kk;
+        sp.idx_out[dst] = s_idx[s];
+    }
+}
+
+// ---- final pass fused with compose + emit -------------------------------------------------------
+
+struct InstanceOut {
+    float4 c0, c1, c2, c3, s;  // column-major model (matrix.rs:219-251) + {size.w, size.h, texture, layer}
+};
+static_assert(sizeof(InstanceOut) == 80, "instance is 80 bytes");
+
+template <typename KeyT>
+struct EmitParams {
+    PassParams pass;
+    const KeyT* keys_in;     // nullptr when `first` and keys are recomputed from the rows
+    const uint32_t* idx_in;  // nullptr: the entity is the position (single-pass plans)
+    const uint64_t* mask_t;
+    const uint64_t* mask_s;
+    RowView rows;
+    const WorldRow* world;   // non-null: hierarchy path, world rows instead of composing
+    FramePlan plan;
+    float4* instances;       // 5 float4 per position
+    float4* vertices;        // 4 float4 per position
+    uint32_t* order;         // entity per position
+    uint32_t* texlayer;      // optional per-position texture|layer<<16 (generic batch path)
+    uint32_t global_first;   // added to the entity ids written to `order`
+    uint32_t staged;         // stage outputs through shared memory for full-line stores
+};
+
+constexpr int kEmitItems = 8;
+constexpr int kStageWords = 36;  // 144 B per item: 80 B instance + 64 B vertices; 36-word stride is
+                                 // conflict-free for 128-bit shared accesses of a quarter warp
+
+__device__ __forceinline__ void make_outputs(const Affine& w, float sw, float shh, uint32_t tl, InstanceOut& inst,
+                                             float4 (&vtx)[4]) {
+    inst.c0 = make_float4(w.r0.x, w.r1.x, w.r2.x, 0.0f);
+    inst.c1 = make_float4(w.r0.y, w.r1.y, w.r2.y, 0.0f);
+    inst.c2 = make_float4(w.r0.z, w.r1.z, w.r2.z, 0.0f);
+    inst.c3 = make_float4(w.r0.w, w.r1.w, w.r2.w, 1.0f);
+    inst.s = make_float4(sw, shh, __uint_as_float(tl & 0xFFFFu), __uint_as_float(tl >> 16));
+    // corners (0,0) (w,0) (w,h) (0,h), transform_vec3 (matrix.rs:160-171)
+    const float cx[4] = {0.0f, sw, sw, 0.0f};
+    const float cy[4] = {0.0f, 0.0f, shh, shh};
+    const uint32_t uv[4] = {0x00000000u, 0x00000001u, 0x00010001u, 0x00010000u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        vtx[k] = make_float4(corner_coord(w.r0.x, w.r0.y, w.r0.w, cx[k], cy[k]),
+                             corner_coord(w.r1.x, w.r1.y, w.r1.w, cx[k], cy[k]),
+                             corner_coord(w.r2.x, w.r2.y, w.r2.w, cx[k], cy[k]), __uint_as_float(uv[k]));
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) emit_kernel(const EmitParams<KeyT> ep) {
+    constexpr int ITEMS = kEmitItems;
+    constexpr uint32_t TILE = kThreads * ITEMS;
+    __shared__ RankShared rs;
+    __shared__ uint32_t s_idx[TILE];
+    __shared__ uint32_t s_dst[TILE];
+    extern __shared__ float4 s_stage[];  // staged mode: kWarps * 32 * 144 B
+    claim_tile(rs, ep.pass);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile_base = rs.tile * TILE;
+    const uint32_t mask = (1u << ep.pass.bits) - 1u;
+    uint32_t idx[ITEMS], digit[ITEMS], slot[ITEMS];
+    const uint32_t n_eff = ep.pass.count_ptr ? min(ep.pass.n, (uint32_t)*ep.pass.count_ptr) : ep.pass.n;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t pos = tile_base + warp * (ITEMS * 32) + k * 32 + lane;
+        bool valid = pos < n_eff;
+        if (valid && ep.idx_in == nullptr) valid = mask_bit(ep.mask_t, pos) && mask_bit(ep.mask_s, pos);
+        idx[k] = pos;
+        uint64_t sk = 0;
+        if (valid) {
+            if (ep.keys_in != nullptr) {
+                sk = (uint64_t)ep.keys_in[pos];
+                if (ep.idx_in != nullptr) idx[k] = ep.idx_in[pos];
+            } else if (ep.world != nullptr) {
+                const float4* wr = reinterpret_cast<const float4*>(ep.world + pos);
+                sk = pext_runs(world_key(wr[2], wr[3]), ep.plan.pext);
+            } else {
+                const size_t o = (size_t)pos * ep.rows.stride;
+                sk = pext_runs(flat_key(ep.rows, pos, ep.rows.a[o], ep.rows.a[o + 1]), ep.plan.pext);
+            }
+        }
+        digit[k] = valid ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
+    }
+    rank_tile<ITEMS>(rs, ep.pass, digit, slot);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (digit[k] != kInvalidDigit) {
+            s_idx[slot[k]] = idx[k];
+            s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k];
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = rs.tile_count;
+    // Each warp takes 32 consecutive tile slots per step: consecutive slots of one digit are
+    // consecutive output positions, so a warp's stores cover whole 128-byte lines.
+    float* stage = reinterpret_cast<float*>(s_stage) + warp * (32 * kStageWords);
+    for (uint32_t s0 = warp * 32; s0 < cnt; s0 += kThreads) {
+        const uint32_t s = s0 + lane;
+        const bool live = s < cnt;
+        uint32_t e = 0, dst = 0;
+        InstanceOut inst;
+        float4 vtx[4];
+        if (live) {
+            e = s_idx[s];
+            dst = s_dst[s];
+            Affine w;
+            float sw, shh;
+            uint32_t tl;
+            if (ep.world != nullptr) {
+                const float4* wr = reinterpret_cast<const float4*>(ep.world + e);
+                w.r0 = ld_nc_f4(wr);
+                w.r1 = ld_nc_f4(wr + 1);
+                w.r2 = ld_nc_f4(wr + 2);
+                const float4 sv = ld_nc_f4(wr + 3);
+                sw = sv.x;
+                shh = sv.y;
+                tl = __float_as_uint(sv.z);
+            } else {
+                const Row r = load_row(ep.rows, e);
+                w = compose_local(r);
+                sw = r.b1.y;
+                shh = r.b1.z;
+                tl = __float_as_uint(r.a1.w);
+            }
+            make_outputs(w, sw, shh, tl, inst, vtx);
+            ep.order[dst] = e + ep.global_first;
+            if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
+        }
+        if (!ep.staged) {
+            if (live) {
+                float4* ip = ep.instances + (size_t)dst * 5;
+                st_cs_f4(ip, inst.c0);
+                st_cs_f4(ip + 1, inst.c1);
+                st_cs_f4(ip + 2, inst.c2);
+                st_cs_f4(ip + 3, inst.c3);
+                st_cs_f4(ip + 4, inst.s);
+                float4* vp = ep.vertices + (size_t)dst * 4;
+                st_cs_f4(vp, vtx[0]);
+                st_cs_f4(vp + 1, vtx[1]);
+                st_cs_f4(vp + 2, vtx[2]);
+                st_cs_f4(vp + 3, vtx[3]);
+            }
+        } else {
+            // stage this warp's 32 items, then write them out 16 B per lane, line by line
+            float4* my = reinterpret_cast<float4*>(stage + lane * kStageWords);
+            if (live) {
+                my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
+                my[5] = vtx[0]; my[6] = vtx[1]; my[7] = vtx[2]; my[8] = vtx[3];
+            }
+            const uint32_t nlive = min(32u, cnt - s0);
+            __syncwarp();
+            // destinations of the 32 items live in the lanes; fetch per chunk by shuffle
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const uint32_t q = j * 32 + lane;
+                const uint32_t item = q / 5, part = q - item * 5;
+                const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+                if (item < nlive) {
+                    const float4 v = reinterpret_cast<const float4*>(stage + item * kStageWords)[part];
+                    st_cs_f4(ep.instances + (size_t)d * 5 + part, v);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t q = j * 32 + lane;
+                const uint32_t item = q >> 2, part = q & 3u;
+                const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+                if (item < nlive) {
+                    const float4 v = reinterpret_cast<const float4*>(stage + item * kStageWords)[5 + part];
+                    st_cs_f4(ep.vertices + (size_t)d * 4 + part, v);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- generic batch boundaries (more than 2^16 distinct (layer, texture) bins) -------------------
+
+// Counts run heads of texlayer[0..n) per block of 1024 positions.
+__global__ void __launch_bounds__(kThreads) batch_heads_count_kernel(const uint32_t* __restrict__ tl, uint32_t n,
+                                                                      uint32_t* block_counts) {
+    __shared__ uint32_t s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    const uint32_t base = blockIdx.x * 1024;
+    for (uint32_t k = threadIdx.x; k < 1024; k += kThreads) {
+        const uint32_t i = base + k;
+        if (i < n) c += (i == 0) || (tl[i] != tl[i - 1]);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_c;
+}
+
+// Exclusive scan of up to 2^20 block counts by one block (in place), total to *total.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* counts, uint32_t nblocks, uint32_t* total) {
+    __shared__ uint32_t s[1024];
+    const uint32_t per = (nblocks + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b0 + per && b < nblocks; ++b) sum += counts[b];
+    s[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t v = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s[threadIdx.x] - sum;
+    for (uint32_t b = b0; b < b0 + per && b < nblocks; ++b) {
+        const uint32_t c = counts[b];
+        counts[b] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) *total = s[1023];
+}
+
+// Writes run heads in order; one block per 1024 positions, ordered inside the block by a
+// ballot scan. The count of each batch is filled by batch_counts_kernel.
+__global__ void __launch_bounds__(kThreads) batch_heads_write_kernel(const uint32_t* __restrict__ tl, uint32_t n,
+                                                                      const uint32_t* __restrict__ block_offsets,
+                                                                      BatchOut* out, uint32_t max_batches) {
+    __shared__ uint32_t s_w[kWarps];
+    __shared__ uint32_t s_run;
+    if (threadIdx.x == 0) s_run = block_offsets[blockIdx.x];
+    __syncthreads();
+    const uint32_t base = blockIdx.x * 1024;
+    for (uint32_t k0 = 0; k0 < 1024; k0 += kThreads) {
+        const uint32_t i = base + k0 + threadIdx.x;
+        const bool head = i < n && ((i == 0) || (tl[i] != tl[i - 1]));
+        const uint32_t b = __ballot_sync(0xffffffffu, head);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
+        __syncthreads();
+        uint32_t off = s_run;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) off += s_w[w];
+        if (head) {
+            const uint32_t slot = off + __popc(b & lanemask_lt());
+            if (slot < max_batches) {
+                BatchOut o;
+                o.layer = tl[i] >> 16;
+                o.texture = tl[i] & 0xFFFFu;
+                o.first_instance = i;
+                o.count = 0;
+                out[slot] = o;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kWarps; ++w) t += s_w[w];
+            s_run += t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) batch_counts_kernel(BatchOut* out, const uint32_t* num_batches,
+                                                                 uint32_t max_batches, uint32_t n) {
+    const uint32_t nb = min(*num_batches, max_batches);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const uint32_t next = (i + 1 < *num_batches && i + 1 < max_batches) ? out[i + 1].first_instance : n;
+    out[i].count = next - out[i].first_instance;
+}
+
+// ---- Ecs::query: presence AND -> packed ascending indices --------------------------------------
+
+struct QueryParams {
+    const uint64_t* masks[4];
+    uint32_t nmasks;
+    uint32_t nwords;
+    uint32_t n;  // entity_count
+};
+
+__device__ __forceinline__ uint64_t query_word(const QueryParams& q, uint32_t w) {
+    uint64_t m = ~0ull;
+    for (uint32_t k = 0; k < q.nmasks; ++k) m &= q.masks[k] ? q.masks[k][w] : ~0ull;
+    const uint32_t lo = w * 64u;
+    if (lo + 64u > q.n) m &= (q.n > lo) ? ((q.n - lo == 64u) ? ~0ull : ((1ull << (q.n - lo)) - 1ull)) : 0ull;
+    return m;
+}
+
+// popcount of 1024 mask words per block
+__global__ void __launch_bounds__(kThreads) query_count_kernel(const QueryParams q, uint32_t* block_counts) {
+    __shared__ uint32_t s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    for (uint32_t k = threadIdx.x; k < 1024; k += kThreads) {
+        const uint32_t w = blockIdx.x * 1024 + k;
+        if (w < q.nwords) c += __popcll(query_word(q, w));
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(kThreads) query_write_kernel(const QueryParams q, const uint32_t* block_offsets,
+                                                                uint32_t* out, uint32_t cap) {
+    __shared__ uint32_t s_w[kWarps];
+    __shared__ uint32_t s_run;
+    if (threadIdx.x == 0) s_run = block_offsets[blockIdx.x];
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < 1024; k0 += kThreads) {
+        const uint32_t w = blockIdx.x * 1024 + k0 + threadIdx.x;
+        uint64_t m = w < q.nwords ? query_word(q, w) : 0ull;
+        const uint32_t c = __popcll(m);
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t off = s_run + x - c;
+        for (uint32_t ww = 0; ww < (threadIdx.x >> 5); ++ww) off += s_w[ww];
+        while (m) {
+            const uint32_t b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (off < cap) out[off] = w * 64u + b;
+            ++off;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int ww = 0; ww < kWarps; ++ww) t += s_w[ww];
+            s_run += t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- hierarchy planning (on upload of parents, not per frame) -----------------------------------
+
+// hop[e] = sanitised parent (TB_NO_PARENT when the entity or its parent has no Transform, or
+// the parent is outside this shard); dist[e] = 1 for a child, 0 for a root.
+__global__ void __launch_bounds__(kThreads) level_init_kernel(const uint32_t* __restrict__ parent,
+                                                               const uint64_t* mask_t, const uint64_t* mask_p,
+                                                               uint32_t n, uint32_t global_first, uint32_t* hop,
+                                                               uint32_t* dist, uint32_t* sane_parent) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint32_t p = 0xFFFFFFFFu;
+    if (parent != nullptr && mask_bit(mask_t, e) && mask_bit(mask_p, e)) {
+        const uint32_t g = parent[e];
+        if (g != 0xFFFFFFFFu && g >= global_first && g - global_first < n && mask_bit(mask_t, g - global_first))
+            p = g - global_first;
+    }
+    hop[e] = p;
+    dist[e] = p != 0xFFFFFFFFu;
+    sane_parent[e] = p == 0xFFFFFFFFu ? 0xFFFFFFFFu : p + global_first;
+}
+
+// One pointer-jumping round (Wyllie): dist += dist[hop]; hop = hop[hop]. `pending` counts
+// entities that have not reached a root yet.
+__global__ void __launch_bounds__(kThreads) level_jump_kernel(const uint32_t* __restrict__ hop_in,
+                                                               const uint32_t* __restrict__ dist_in, uint32_t n,
+                                                               uint32_t* hop_out, uint32_t* dist_out, uint32_t* pending) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint32_t h = hop_in[e], d = dist_in[e];
+    if (h != 0xFFFFFFFFu) {
+        d += dist_in[h];
+        h = hop_in[h];
+        if (h != 0xFFFFFFFFu) atomicAdd(pending, 1u);
+    }
+    hop_out[e] = h;
+    dist_out[e] = d;
+}
+
+// max level, and whether levels are non-decreasing with the entity id (then every level is
+// an id range and no list is needed). stats[0] = max level, stats[1] = number of descents.
+__global__ void __launch_bounds__(kThreads) level_stats_kernel(const uint32_t* __restrict__ level, const uint64_t* mask_t,
+                                                                uint32_t n, uint32_t* stats) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t l = level[e];
+    atomicMax(&stats[0], l);
+    if (e > 0 && level[e - 1] > l) atomicAdd(&stats[1], 1u);
+    (void)mask_t;
+}
+
+__global__ void __launch_bounds__(kThreads) level_hist_kernel(const uint32_t* __restrict__ level, const uint64_t* mask_t,
+                                                               uint32_t n, uint32_t* hist, uint32_t nlevels) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (!mask_bit(mask_t, e)) return;
+    const uint32_t l = level[e];
+    if (l < nlevels) atomicAdd(&hist[l], 1u);
+}
+
+// world rows -> row-major 4x4 (identity where the entity has no Transform)
+__global__ void __launch_bounds__(kThreads) world_to_mat4_kernel(const WorldRow* __restrict__ world, const uint64_t* mask_t,
+                                                                  uint32_t first, uint32_t n, float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 r0 = make_float4(1, 0, 0, 0), r1 = make_float4(0, 1, 0, 0), r2 = make_float4(0, 0, 1, 0);
+    if (mask_bit(mask_t, first + i)) {
+        const float4* w = reinterpret_cast<const float4*>(world + first + i);
+        r0 = w[0];
+        r1 = w[1];
+        r2 = w[2];
+    }
+    float4* o = reinterpret_cast<float4*>(dst + (size_t)i * 16);
+    o[0] = r0;
+    o[1] = r1;
+    o[2] = r2;
+    o[3] = make_float4(0, 0, 0, 1);
+}
+
+// Transform -> local world row for flat scenes (tb_download_world_matrices / tb_as_matrix4)
+__global__ void __launch_bounds__(kThreads) compose_world_kernel(RowView rows, const uint64_t* mask_t, uint32_t n,
+                                                                  WorldRow* world) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (!mask_bit(mask_t, e)) return;
+    const Row r = load_row(rows, e);
+    const Affine w = compose_local(r);
+    float4* dst = reinterpret_cast<float4*>(world + e);
+    dst[0] = w.r0;
+    dst[1] = w.r1;
+    dst[2] = w.r2;
+    dst[3] = make_float4(r.b1.y, r.b1.z, r.a1.w, 0.0f);
+}
+
+// ---- standalone velocity system (when no frame follows the tick) --------------------------------
+
+__global__ void __launch_bounds__(kThreads) integrate_kernel(RowView rows, const uint64_t* mask_t, const uint64_t* mask_v,
+                                                              const float* __restrict__ vel, float dt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!mask_bit(mask_t, i) || !mask_bit(mask_v, i)) return;
+    const size_t o = (size_t)i * rows.stride;
+    float4 a0 = rows.a[o];
+    const float* v = vel + (size_t)i * 3;
+    a0.x = addr(a0.x, mulr(__ldg(v), dt));
+    a0.y = addr(a0.y, mulr(__ldg(v + 1), dt));
+    a0.z = addr(a0.z, mulr(__ldg(v + 2), dt));
+    rows.a[o] = a0;
+}
+
+// ---- generic digit histograms of a u32 key array (hierarchy level lists) -------------------------
+
+struct DigitSplit {
+    uint32_t npasses;
+    uint32_t shift[kMaxPasses];
+    uint32_t bits[kMaxPasses];
+};
+
+__global__ void __launch_bounds__(kThreads) key_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n,
+                                                             const DigitSplit ds, uint32_t* hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    for (uint32_t q = 0; q < ds.npasses; ++q)
+        atomicAdd(&hist[q * 256 + ((k >> ds.shift[q]) & ((1u << ds.bits[q]) - 1u))], 1u);
+}
+
+}  // namespace tb

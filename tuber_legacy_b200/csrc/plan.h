@@ -1,0 +1,143 @@
+// Frame plan: which bits of the 64-bit sort key actually vary in this scene, how they are
+// packed into a short key, and how that short key is split into radix digits.
+// Shared by host code (plan construction, tests of the planner) and device code.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define TB_HD __host__ __device__
+#else
+#define TB_HD
+#endif
+
+namespace tb {
+
+constexpr int kMaxRuns = 16;
+constexpr int kMaxPasses = 8;
+constexpr int kMaxDigitBits = 8;
+constexpr uint32_t kMaxLtBits = 16;  // (layer, texture) bins kept as a direct histogram up to 2^16
+
+// Bit-gather (pext) of the varying key bits, as up to 16 contiguous runs.
+struct PextPlan {
+    uint32_t nruns;
+    uint32_t nbits;  // total extracted bits
+    uint8_t src_shift[kMaxRuns];
+    uint8_t width[kMaxRuns];
+    uint8_t dst_shift[kMaxRuns];
+};
+
+struct FramePlan {
+    PextPlan pext;
+    uint64_t varying;   // key bits that differ between at least two renderables (possibly widened)
+    uint64_t constant;  // value of the non-varying key bits
+    uint32_t npasses;   // >= 1 radix passes, least significant digit first
+    uint32_t shift[kMaxPasses];
+    uint32_t bits[kMaxPasses];
+    uint32_t ltbits;  // varying bits among key[63:32] (layer, texture)
+    uint32_t zbits;   // varying bits among key[31:0]  (orderable world z)
+    uint32_t key64;   // short key needs more than 32 bits
+};
+
+TB_HD inline uint64_t pext_runs(uint64_t key, const PextPlan& p) {
+    uint64_t out = 0;
+    for (uint32_t r = 0; r < p.nruns; ++r) {
+        uint64_t m = (p.width[r] >= 64) ? ~0ull : ((1ull << p.width[r]) - 1ull);
+        out |= ((key >> p.src_shift[r]) & m) << p.dst_shift[r];
+    }
+    return out;
+}
+
+// Inverse of pext_runs on the varying bits (pdep).
+TB_HD inline uint64_t pdep_runs(uint64_t shortkey, const PextPlan& p) {
+    uint64_t out = 0;
+    for (uint32_t r = 0; r < p.nruns; ++r) {
+        uint64_t m = (p.width[r] >= 64) ? ~0ull : ((1ull << p.width[r]) - 1ull);
+        out |= ((shortkey >> p.dst_shift[r]) & m) << p.src_shift[r];
+    }
+    return out;
+}
+
+inline uint32_t popcount64(uint64_t v) {
+    uint32_t c = 0;
+    while (v) {
+        v &= v - 1;
+        ++c;
+    }
+    return c;
+}
+
+// Builds the plan from the OR and AND of every renderable's key. Runs of varying bits are
+// kept as they are; when there are more than kMaxRuns of them the smallest gaps are filled
+// (a filled gap bit is constant, so it only costs sort width, never correctness). Runs never
+// straddle bit 32, so the short key is always [ (layer,texture) bits | z bits ].
+inline void build_frame_plan(uint64_t key_or, uint64_t key_and, FramePlan* out) {
+    FramePlan& f = *out;
+    uint64_t varying = key_or & ~key_and;
+    for (;;) {
+        // collect runs, split at bit 32
+        uint32_t nruns = 0;
+        uint32_t starts[64], ends[64];
+        uint32_t bit = 0;
+        while (bit < 64) {
+            if (!((varying >> bit) & 1ull)) {
+                ++bit;
+                continue;
+            }
+            uint32_t s = bit;
+            while (bit < 64 && ((varying >> bit) & 1ull) && !(bit == 32 && s < 32)) ++bit;
+            starts[nruns] = s;
+            ends[nruns] = bit;
+            ++nruns;
+        }
+        if (nruns <= (uint32_t)kMaxRuns) {
+            f.pext.nruns = nruns;
+            f.pext.nbits = 0;
+            for (uint32_t r = 0; r < (uint32_t)kMaxRuns; ++r) f.pext.src_shift[r] = f.pext.width[r] = f.pext.dst_shift[r] = 0;
+            for (uint32_t r = 0; r < nruns; ++r) {
+                f.pext.src_shift[r] = (uint8_t)starts[r];
+                f.pext.width[r] = (uint8_t)(ends[r] - starts[r]);
+                f.pext.dst_shift[r] = (uint8_t)f.pext.nbits;
+                f.pext.nbits += ends[r] - starts[r];
+            }
+            break;
+        }
+        // fill the smallest gap between two runs on the same side of bit 32 (a gap that
+        // straddles bit 32 would be split again, so filling it cannot reduce the run count)
+        uint32_t best = 0, best_gap = 65;
+        for (uint32_t r = 0; r + 1 < nruns; ++r) {
+            if (ends[r] <= 32 && starts[r + 1] >= 32) continue;
+            uint32_t gap = starts[r + 1] - ends[r];
+            if (gap < best_gap) {
+                best_gap = gap;
+                best = r;
+            }
+        }
+        for (uint32_t b = ends[best]; b < starts[best + 1]; ++b) varying |= 1ull << b;
+    }
+    f.varying = varying;
+    f.constant = key_and & ~varying;
+    f.zbits = popcount64(varying & 0xFFFFFFFFull);
+    f.ltbits = popcount64(varying >> 32);
+    const uint32_t nbits = f.pext.nbits;
+    f.key64 = nbits > 32 ? 1u : 0u;
+    uint32_t np = (nbits + kMaxDigitBits - 1) / kMaxDigitBits;
+    if (np == 0) np = 1;
+    f.npasses = np;
+    uint32_t base = nbits / np, rem = nbits % np, sh = 0;
+    for (uint32_t p = 0; p < (uint32_t)kMaxPasses; ++p) f.shift[p] = f.bits[p] = 0;
+    for (uint32_t p = 0; p < np; ++p) {
+        f.shift[p] = sh;
+        f.bits[p] = base + (p < rem ? 1u : 0u);
+        sh += f.bits[p];
+    }
+}
+
+// A plan stays valid for a frame whose keys vary only inside plan.varying and agree with
+// plan.constant elsewhere.
+inline bool plan_covers(const FramePlan& f, uint64_t key_or, uint64_t key_and) {
+    uint64_t varying = key_or & ~key_and;
+    if (varying & ~f.varying) return false;
+    return (key_and & ~f.varying) == f.constant && (key_or & ~f.varying) == f.constant;
+}
+
+}  // namespace tb

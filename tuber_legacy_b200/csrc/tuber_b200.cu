@@ -1,0 +1,1311 @@
+// libtuber_b200.so — host side of the C ABI in include/tuber_b200.h.
+//
+// One tb_ctx per GPU owns the device-resident ECS columns (two-sector rows, presence bitsets,
+// velocity and parent columns), the frame scratch (key statistics, histograms, look-back
+// words, sort ping-pong buffers) and the emitted buffers. A frame is a short fixed sequence
+// of kernel launches on the context's stream; the only host round trip is the
+// read-back of the counts and key statistics that tb_frame_transform_batch returns.
+//
+// There is no CPU fallback anywhere in this file: without an sm_100 device tb_ctx_create
+// fails with TB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tuber_b200.h"
+#include "kernels.cuh"
+
+using namespace tb;
+
+namespace {
+
+struct ProfEntry {
+    const char* name;
+    cudaEvent_t e0, e1;
+    uint64_t bytes;
+};
+
+}  // namespace
+
+struct tb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint64_t cap = 0, n = 0;
+    std::string err;
+
+    // storage
+    int interleaved = 0;
+    bool rows_touched = false;
+    float4* rows_mem = nullptr;
+    RowView rows{};
+    uint64_t* mask[TB_COMPONENT_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+    bool store[TB_COMPONENT_COUNT] = {false, false, false, false};
+    float* vel = nullptr;
+    uint32_t* parent = nullptr;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    // frame scratch
+    uint32_t* scratch = nullptr;
+    size_t scratch_words = 0;
+    void* keys[2] = {nullptr, nullptr};
+    uint32_t* idx[2] = {nullptr, nullptr};
+    size_t sort_cap = 0, sort_keybytes = 0;
+    uint32_t* texlayer = nullptr;
+    size_t texlayer_cap = 0;
+    WorldRow* world = nullptr;
+    size_t world_cap = 0;
+    bool world_valid = false;
+
+    // outputs
+    float4* inst = nullptr;
+    float4* vtx = nullptr;
+    uint32_t* order = nullptr;
+    size_t out_cap = 0;
+    BatchOut* batches = nullptr;
+    uint64_t max_batches = 65536, batches_cap = 0;
+    void* ext_inst = nullptr;
+    void* ext_vtx = nullptr;
+    void* ext_order = nullptr;
+    uint64_t ext_cap = 0;
+    uint64_t last_instances = 0, last_batches = 0;
+    bool frame_valid = false;
+
+    // plan
+    FramePlan plan{};
+    bool plan_valid = false;
+    uint32_t force_path = TB_PATH_NONE;
+    int digit_bits = kMaxDigitBits;
+    int staged_emit = 1;
+    int lt_limit = (int)kMaxLtBits;
+
+    // hierarchy
+    bool levels_dirty = true;
+    uint32_t nlevels = 1;
+    bool level_ranges = true;
+    std::vector<uint32_t> level_first, level_count;
+    uint32_t* level_list = nullptr;
+    uint32_t* sane_parent = nullptr;
+    size_t level_cap = 0;
+
+    // velocity system
+    bool pending = false;
+    float pending_dt = 0.0f;
+
+    // shard
+    int rank = 0, nranks = 1;
+    uint64_t global_first = 0;
+
+    // pinned host mirror of the scratch header
+    uint64_t* h_hdr = nullptr;
+
+    // instrumentation
+    bool prof = false;
+    std::vector<ProfEntry> prof_entries;
+    std::vector<float> prof_ms;
+    uint64_t launches = 0;
+    uint32_t frame_launches = 0;
+};
+
+namespace {
+
+// scratch header layout (32-bit words)
+constexpr size_t kHdrStats = 0;        // 3 x u64: OR(key), OR(~key), renderable count
+constexpr size_t kHdrNumBatches = 6;   // u32
+constexpr size_t kHdrRangeErr = 7;     // u32 (sprite range violations since last check)
+constexpr size_t kHdrPending = 8;      // u32 scratch for level planning
+constexpr size_t kHdrLevelStats = 9;   // 2 x u32
+constexpr size_t kHdrTileCounters = 12;  // kMaxPasses + 1 x u32
+constexpr size_t kHdrHist = 32;          // kMaxPasses * 256 u32
+constexpr size_t kHdrWords = kHdrHist + kMaxPasses * 256;  // then lt_hist, then look-back words
+
+tb_status fail(tb_ctx* c, tb_status s, const std::string& msg) {
+    if (c) c->err = msg;
+    return s;
+}
+
+tb_status cuda_fail(tb_ctx* c, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    return fail(c, e == cudaErrorMemoryAllocation ? TB_ERR_OOM : TB_ERR_CUDA, m);
+}
+
+#define TB_CUDA(c, call)                                   \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail((c), e__, #call); \
+    } while (0)
+
+void prof_begin(tb_ctx* c, const char* name, uint64_t bytes) {
+    if (!c->prof) return;
+    ProfEntry pe{name, nullptr, nullptr, bytes};
+    cudaEventCreate(&pe.e0);
+    cudaEventCreate(&pe.e1);
+    cudaEventRecord(pe.e0, c->stream);
+    c->prof_entries.push_back(pe);
+}
+void prof_end(tb_ctx* c) {
+    if (!c->prof) return;
+    cudaEventRecord(c->prof_entries.back().e1, c->stream);
+}
+void prof_clear(tb_ctx* c) {
+    for (auto& pe : c->prof_entries) {
+        cudaEventDestroy(pe.e0);
+        cudaEventDestroy(pe.e1);
+    }
+    c->prof_entries.clear();
+    c->prof_ms.clear();
+}
+
+#define TB_LAUNCH(c, name, bytes, kern, grid, block, smem, ...)        \
+    do {                                                               \
+        prof_begin((c), (name), (bytes));                              \
+        kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);   \
+        prof_end((c));                                                 \
+        (c)->launches++;                                               \
+        (c)->frame_launches++;                                         \
+    } while (0)
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <typename T>
+tb_status grow(tb_ctx* c, T** p, size_t* cap, size_t need, size_t elem) {
+    if (*cap >= need && *p) return TB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, need * elem);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc");
+    *p = (T*)q;
+    *cap = need;
+    return TB_OK;
+}
+
+tb_status ensure_stage(tb_ctx* c, size_t bytes) {
+    size_t cap = c->stage_bytes;
+    char* p = (char*)c->stage;
+    tb_status s = grow(c, &p, &cap, bytes, 1);
+    c->stage = p;
+    c->stage_bytes = cap;
+    return s;
+}
+
+const uint64_t* mask_or_null(tb_ctx* c, int comp) { return c->mask[comp]; }
+
+tb_status check_range(tb_ctx* c, uint64_t first, uint64_t n, const void* p) {
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!p) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (first + n > c->n) return fail(c, TB_ERR_INVALID, "range outside entity_count");
+    return TB_OK;
+}
+
+constexpr size_t kStageChunk = 64u << 20;
+
+tb_status mark_presence(tb_ctx* c, int comp, uint64_t first, uint64_t n, int set) {
+    if (n == 0) return TB_OK;
+    uint64_t nw = ((first + n - 1) >> 6) - (first >> 6) + 1;
+    TB_LAUNCH(c, "mark_presence", 0, mark_presence_kernel, div_up(nw, kThreads), kThreads, 0, c->mask[comp], first, n, set);
+    return TB_OK;
+}
+
+tb_status flush_integrate(tb_ctx* c) {
+    if (!c->pending) return TB_OK;
+    c->pending = false;
+    if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_VELOCITY]) return TB_OK;
+    TB_LAUNCH(c, "integrate", c->n * 36ull, integrate_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows,
+              mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, (uint32_t)c->n);
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+// Scratch layout for one frame under a plan.
+struct ScratchLayout {
+    size_t lt_off = 0, lt_words = 0;
+    size_t status_off[kMaxPasses];
+    uint32_t tiles[kMaxPasses];
+    size_t total_words = 0;
+};
+
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt) {
+    ScratchLayout L;
+    size_t off = kHdrWords;
+    L.lt_off = off;
+    L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
+    off += L.lt_words;
+    for (uint32_t p = 0; p < plan.npasses; ++p) {
+        const bool last = p + 1 == plan.npasses;
+        const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
+        L.tiles[p] = div_up(n, tile);
+        L.status_off[p] = off;
+        off += (size_t)L.tiles[p] << plan.bits[p];
+    }
+    L.total_words = off;
+    return L;
+}
+
+tb_status ensure_scratch(tb_ctx* c, size_t words) {
+    if (c->scratch_words >= words) return TB_OK;
+    // keep the header values that outlive a frame (range error counter)
+    uint32_t* old = c->scratch;
+    size_t old_words = c->scratch_words;
+    void* q = nullptr;
+    size_t want = std::max(words, kHdrWords);
+    cudaError_t e = cudaMalloc(&q, want * 4);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(scratch)");
+    cudaMemsetAsync(q, 0, want * 4, c->stream);
+    if (old) {
+        cudaMemcpyAsync(q, old, std::min(old_words, kHdrWords) * 4, cudaMemcpyDeviceToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(old);
+    }
+    c->scratch = (uint32_t*)q;
+    c->scratch_words = want;
+    return TB_OK;
+}
+
+tb_status realloc_dev(tb_ctx* c, void** p, size_t bytes) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc");
+    return TB_OK;
+}
+
+tb_status ensure_outputs(tb_ctx* c, uint64_t n) {
+    tb_status s;
+    if (c->ext_inst) {
+        if (c->ext_cap < n) return fail(c, TB_ERR_CAPACITY, "external output buffers too small");
+    } else if (c->out_cap < n || !c->inst) {
+        c->out_cap = 0;
+        if ((s = realloc_dev(c, (void**)&c->inst, (size_t)n * 80))) return s;
+        if ((s = realloc_dev(c, (void**)&c->vtx, (size_t)n * 64))) return s;
+        if ((s = realloc_dev(c, (void**)&c->order, (size_t)n * 4))) return s;
+        c->out_cap = n;
+    }
+    if (!c->batches || c->batches_cap < c->max_batches) {
+        c->batches_cap = 0;
+        if ((s = realloc_dev(c, (void**)&c->batches, (size_t)c->max_batches * sizeof(BatchOut)))) return s;
+        c->batches_cap = c->max_batches;
+    }
+    return TB_OK;
+}
+
+tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
+    if (c->sort_cap >= n && c->sort_keybytes >= keybytes && c->keys[0]) return TB_OK;
+    for (int k = 0; k < 2; ++k) {
+        if (c->keys[k]) cudaFree(c->keys[k]);
+        if (c->idx[k]) cudaFree(c->idx[k]);
+        c->keys[k] = nullptr;
+        c->idx[k] = nullptr;
+    }
+    c->sort_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        cudaError_t e = cudaMalloc(&c->keys[k], (size_t)n * keybytes);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(sort keys)");
+        e = cudaMalloc((void**)&c->idx[k], (size_t)n * 4);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(sort idx)");
+    }
+    c->sort_cap = n;
+    c->sort_keybytes = keybytes;
+    return TB_OK;
+}
+
+tb_status ensure_world(tb_ctx* c, uint64_t n) {
+    size_t cap = c->world ? c->world_cap : 0;
+    tb_status s = grow(c, &c->world, &cap, (size_t)n, sizeof(WorldRow));
+    c->world_cap = cap;
+    return s;
+}
+
+// ---- hierarchy planning ---------------------------------------------------------------------------
+
+void split_digits(uint32_t nbits, int digit_bits, DigitSplit* ds) {
+    uint32_t np = (nbits + digit_bits - 1) / digit_bits;
+    if (np == 0) np = 1;
+    ds->npasses = np;
+    uint32_t base = nbits / np, rem = nbits % np, sh = 0;
+    for (uint32_t p = 0; p < (uint32_t)kMaxPasses; ++p) ds->shift[p] = ds->bits[p] = 0;
+    for (uint32_t p = 0; p < np; ++p) {
+        ds->shift[p] = sh;
+        ds->bits[p] = base + (p < rem ? 1u : 0u);
+        sh += ds->bits[p];
+    }
+}
+
+// Stable sort of entity ids by a u32 key (hierarchy level), using the frame's own radix
+// machinery. keys are consumed; the sorted ids land in *out (one of c->idx[]).
+tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbits, uint32_t** out) {
+    DigitSplit ds;
+    split_digits(nbits, kMaxDigitBits, &ds);
+    tb_status s = ensure_sort_buffers(c, n, 4);
+    if (s) return s;
+    const uint32_t tile = kThreads * kScatterItems;
+    const uint32_t tiles = div_up(n, tile);
+    size_t words = kHdrWords;
+    size_t status_off[kMaxPasses];
+    for (uint32_t p = 0; p < ds.npasses; ++p) {
+        status_off[p] = words;
+        words += (size_t)tiles << ds.bits[p];
+    }
+    s = ensure_scratch(c, words);
+    if (s) return s;
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (words - kHdrTileCounters) * 4, c->stream));
+    uint32_t* hist = c->scratch + kHdrHist;
+    TB_LAUNCH(c, "level_key_hist", 0, key_hist_kernel, div_up(n, kThreads), kThreads, 0, d_keys, n, ds, hist);
+    TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, ds.npasses, 256, 0, hist);
+    const uint32_t* kin = d_keys;
+    const uint32_t* iin = nullptr;
+    int cur = 0;
+    for (uint32_t p = 0; p < ds.npasses; ++p) {
+        ScatterParams<uint32_t> sp{};
+        sp.pass.n = n;
+        sp.pass.count_ptr = nullptr;
+        sp.pass.shift = ds.shift[p];
+        sp.pass.bits = ds.bits[p];
+        sp.pass.gbase = hist + p * 256;
+        sp.pass.status = c->scratch + status_off[p];
+        sp.pass.tile_counter = c->scratch + kHdrTileCounters + p;
+        sp.keys_in = kin;
+        sp.idx_in = iin;
+        sp.mask_t = nullptr;
+        sp.mask_s = nullptr;
+        sp.keys_out = (uint32_t*)c->keys[cur];
+        sp.idx_out = c->idx[cur];
+        TB_LAUNCH(c, "level_sort", 0, radix_scatter_kernel<uint32_t>, tiles, kThreads, 0, sp);
+        kin = (const uint32_t*)c->keys[cur];
+        iin = c->idx[cur];
+        cur ^= 1;
+    }
+    *out = (uint32_t*)iin;
+    return TB_OK;
+}
+
+tb_status plan_levels(tb_ctx* c) {
+    c->levels_dirty = false;
+    c->nlevels = 1;
+    c->level_ranges = true;
+    c->level_first.clear();
+    c->level_count.clear();
+    const uint32_t n = (uint32_t)c->n;
+    if (!c->store[TB_PARENT] || n == 0) return TB_OK;
+    // hop / dist ping-pong + sane_parent + list
+    if (c->level_cap < n) {
+        if (c->level_list) cudaFree(c->level_list);
+        if (c->sane_parent) cudaFree(c->sane_parent);
+        c->level_list = c->sane_parent = nullptr;
+        TB_CUDA(c, cudaMalloc((void**)&c->level_list, (size_t)n * 4));
+        TB_CUDA(c, cudaMalloc((void**)&c->sane_parent, (size_t)n * 4));
+        c->level_cap = n;
+    }
+    uint32_t* tmp = nullptr;
+    TB_CUDA(c, cudaMalloc((void**)&tmp, (size_t)n * 4 * 4));
+    uint32_t* hop[2] = {tmp, tmp + n};
+    uint32_t* dist[2] = {tmp + 2 * (size_t)n, tmp + 3 * (size_t)n};
+    tb_status s = ensure_scratch(c, kHdrWords);
+    if (s) {
+        cudaFree(tmp);
+        return s;
+    }
+    const uint32_t grid = div_up(n, kThreads);
+    TB_LAUNCH(c, "level_init", 0, level_init_kernel, grid, kThreads, 0, c->parent, mask_or_null(c, TB_TRANSFORM),
+              mask_or_null(c, TB_PARENT), n, (uint32_t)c->global_first, hop[0], dist[0], c->sane_parent);
+    int cur = 0;
+    bool done = false;
+    for (int round = 0; round < 33 && !done; ++round) {
+        cudaMemsetAsync(c->scratch + kHdrPending, 0, 4, c->stream);
+        TB_LAUNCH(c, "level_jump", 0, level_jump_kernel, grid, kThreads, 0, hop[cur], dist[cur], n, hop[cur ^ 1],
+                  dist[cur ^ 1], c->scratch + kHdrPending);
+        cur ^= 1;
+        uint32_t pending = 0;
+        cudaMemcpyAsync(&pending, c->scratch + kHdrPending, 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            return cuda_fail(c, e, "plan_levels");
+        }
+        done = pending == 0;
+    }
+    if (!done) {
+        cudaFree(tmp);
+        c->levels_dirty = true;
+        return fail(c, TB_ERR_CYCLE, "the Parent links contain a cycle");
+    }
+    uint32_t* level = dist[cur];
+    cudaMemsetAsync(c->scratch + kHdrLevelStats, 0, 8, c->stream);
+    TB_LAUNCH(c, "level_stats", 0, level_stats_kernel, grid, kThreads, 0, level, mask_or_null(c, TB_TRANSFORM), n,
+              c->scratch + kHdrLevelStats);
+    uint32_t stats[2] = {0, 0};
+    cudaMemcpyAsync(stats, c->scratch + kHdrLevelStats, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        cudaFree(tmp);
+        return cuda_fail(c, e, "plan_levels");
+    }
+    c->nlevels = stats[0] + 1;
+    c->level_ranges = stats[1] == 0;
+    if (c->nlevels > 1) {
+        if (c->nlevels > 65536) {
+            cudaFree(tmp);
+            c->levels_dirty = true;
+            return fail(c, TB_ERR_UNSUPPORTED, "hierarchy deeper than 65536 levels");
+        }
+        uint32_t* d_hist = nullptr;
+        TB_CUDA(c, cudaMalloc((void**)&d_hist, (size_t)c->nlevels * 4));
+        cudaMemsetAsync(d_hist, 0, (size_t)c->nlevels * 4, c->stream);
+        TB_LAUNCH(c, "level_hist", 0, level_hist_kernel, grid, kThreads, 0, level, (const uint64_t*)nullptr, n, d_hist,
+                  c->nlevels);
+        c->level_count.resize(c->nlevels);
+        cudaMemcpyAsync(c->level_count.data(), d_hist, (size_t)c->nlevels * 4, cudaMemcpyDeviceToHost, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        cudaFree(d_hist);
+        if (e != cudaSuccess) {
+            cudaFree(tmp);
+            return cuda_fail(c, e, "plan_levels");
+        }
+        c->level_first.resize(c->nlevels);
+        uint32_t run = 0;
+        for (uint32_t l = 0; l < c->nlevels; ++l) {
+            c->level_first[l] = run;
+            run += c->level_count[l];
+        }
+        if (!c->level_ranges) {
+            uint32_t nbits = 0;
+            while ((1u << nbits) < c->nlevels) ++nbits;
+            uint32_t* sorted = nullptr;
+            s = sort_ids_by_key(c, level, n, nbits, &sorted);
+            if (s) {
+                cudaFree(tmp);
+                return s;
+            }
+            cudaMemcpyAsync(c->level_list, sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    return TB_OK;
+}
+
+// ---- the frame --------------------------------------------------------------------------------
+
+void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and) {
+    build_frame_plan(key_or, key_and, &c->plan);
+    // optional narrower digits (tests, tb_frame_force_path(TB_PATH_SORT))
+    int db = c->digit_bits;
+    if (c->force_path == TB_PATH_SORT && c->plan.pext.nbits >= 2) db = std::min<int>(db, (c->plan.pext.nbits + 1) / 2);
+    if (db < kMaxDigitBits && c->plan.pext.nbits > 0) {
+        DigitSplit ds;
+        uint32_t np = (c->plan.pext.nbits + db - 1) / db;
+        if (np > (uint32_t)kMaxPasses) db = (c->plan.pext.nbits + kMaxPasses - 1) / kMaxPasses;
+        split_digits(c->plan.pext.nbits, db, &ds);
+        c->plan.npasses = ds.npasses;
+        for (int p = 0; p < kMaxPasses; ++p) {
+            c->plan.shift[p] = ds.shift[p];
+            c->plan.bits[p] = ds.bits[p];
+        }
+    }
+    c->plan_valid = true;
+}
+
+struct FrameMode {
+    bool hier;
+    bool lt_alias;    // (layer, texture) bins are digit pass 0 itself
+    bool lt_hist;     // separate (layer, texture) histogram
+    bool lt_generic;  // run-head detection over an emitted texlayer array
+};
+
+tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode& fm, const ScratchLayout* L) {
+    const uint32_t n = (uint32_t)c->n;
+    PrepParams p{};
+    p.n = n;
+    p.rows = c->rows;
+    p.mask_t = mask_or_null(c, TB_TRANSFORM);
+    p.mask_s = mask_or_null(c, TB_SPRITE);
+    p.mask_v = mask_or_null(c, TB_VELOCITY);
+    p.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
+    p.dt = c->pending_dt;
+    p.integrate = integrate && p.vel != nullptr;
+    p.have_plan = have_plan;
+    p.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    p.hist = c->scratch + kHdrHist;
+    if (have_plan) {
+        p.plan = c->plan;
+        p.write_keys = c->plan.npasses > 1;
+        p.keys_out = c->keys[0];
+        p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
+        p.lt_hist = c->scratch + L->lt_off;
+    }
+    const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 32 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
+    if (!fm.hier) {
+        const uint32_t tiles = div_up(n, kThreads * kPrepItems);
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)c->sm_count * 8u);
+        TB_LAUNCH(c, have_plan ? "prepare_flat" : "discover_flat", bytes_in, prepare_flat_kernel, grid, kThreads, 0, p);
+    } else {
+        for (uint32_t l = 0; l < c->nlevels; ++l) {
+            LevelParams lp{};
+            lp.prep = p;
+            lp.parent = c->sane_parent;
+            lp.list = c->level_ranges ? nullptr : c->level_list;
+            lp.first = c->level_first[l];
+            lp.count = c->level_count[l];
+            lp.level = l;
+            lp.global_first = (uint32_t)c->global_first;
+            lp.world = c->world;
+            if (lp.count == 0) continue;
+            const uint32_t chunks = div_up(lp.count, kThreads);
+            const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)c->sm_count * 8u);
+            TB_LAUNCH(c, have_plan ? "prepare_level" : "discover_level", (uint64_t)lp.count * (64 + 4 + 64 + (p.integrate ? 44 : 0)),
+                      prepare_level_kernel, grid, kThreads, 0, lp);
+        }
+        c->world_valid = true;
+    }
+    return TB_OK;
+}
+
+tb_status read_header(tb_ctx* c) {
+    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+template <typename KeyT>
+tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, float4* d_inst, float4* d_vtx,
+                            uint32_t* d_order) {
+    const uint32_t n = (uint32_t)c->n;
+    const FramePlan& plan = c->plan;
+    uint32_t* hist = c->scratch + kHdrHist;
+    const KeyT* kin = (const KeyT*)c->keys[0];
+    const uint32_t* iin = nullptr;
+    uint32_t count_in = n;  // positions in the first pass, renderables afterwards (unknown on host: use n)
+    int cur = 1;
+    for (uint32_t p = 0; p + 1 < plan.npasses; ++p) {
+        ScatterParams<KeyT> sp{};
+        sp.pass.n = count_in;
+        sp.pass.count_ptr = iin ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2 : nullptr;
+        sp.pass.shift = plan.shift[p];
+        sp.pass.bits = plan.bits[p];
+        sp.pass.gbase = hist + p * 256;
+        sp.pass.status = c->scratch + L.status_off[p];
+        sp.pass.tile_counter = c->scratch + kHdrTileCounters + p;
+        sp.keys_in = kin;
+        sp.idx_in = iin;
+        sp.mask_t = mask_or_null(c, TB_TRANSFORM);
+        sp.mask_s = mask_or_null(c, TB_SPRITE);
+        sp.keys_out = (KeyT*)c->keys[cur];
+        sp.idx_out = c->idx[cur];
+        const uint64_t kb = sizeof(KeyT);
+        TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>, L.tiles[p],
+                  kThreads, 0, sp);
+        kin = (const KeyT*)c->keys[cur];
+        iin = c->idx[cur];
+        cur ^= 1;
+    }
+    const uint32_t p = plan.npasses - 1;
+    EmitParams<KeyT> ep{};
+    ep.pass.n = count_in;
+    ep.pass.count_ptr = iin ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2 : nullptr;
+    ep.pass.shift = plan.shift[p];
+    ep.pass.bits = plan.bits[p];
+    ep.pass.gbase = hist + p * 256;
+    ep.pass.status = c->scratch + L.status_off[p];
+    ep.pass.tile_counter = c->scratch + kHdrTileCounters + p;
+    ep.keys_in = plan.npasses > 1 ? kin : nullptr;
+    ep.idx_in = iin;
+    ep.mask_t = mask_or_null(c, TB_TRANSFORM);
+    ep.mask_s = mask_or_null(c, TB_SPRITE);
+    ep.rows = c->rows;
+    ep.world = fm.hier ? c->world : nullptr;
+    ep.plan = plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.texlayer = fm.lt_generic ? c->texlayer : nullptr;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    const size_t smem = c->staged_emit ? (size_t)kWarps * 32 * kStageWords * 4 : 0;
+    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (iin ? sizeof(KeyT) + 4 : 0)), emit_kernel<KeyT>, L.tiles[p],
+              kThreads, smem, ep);
+    return TB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+
+extern "C" {
+
+const char* tb_version(void) { return "tuber_b200 0.1 (sm_100a)"; }
+
+const char* tb_status_string(tb_status s) {
+    switch (s) {
+        case TB_OK: return "ok";
+        case TB_ERR_INVALID: return "invalid argument";
+        case TB_ERR_CUDA: return "CUDA error";
+        case TB_ERR_OOM: return "out of memory";
+        case TB_ERR_RANGE: return "component value out of range";
+        case TB_ERR_NO_DEVICE: return "no sm_100 device (there is no CPU fallback)";
+        case TB_ERR_CAPACITY: return "capacity exceeded";
+        case TB_ERR_CYCLE: return "cycle in Parent links";
+        case TB_ERR_COMM: return "communication failure";
+        case TB_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
+    if (!out) return TB_ERR_INVALID;
+    *out = nullptr;
+    if (max_entities == 0 || max_entities >= (1ull << 30)) return TB_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return TB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    if (prop.major != 10) return TB_ERR_NO_DEVICE;  // the only code in this library is sm_100a
+    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    tb_ctx* c = new (std::nothrow) tb_ctx();
+    if (!c) return TB_ERR_OOM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cap = max_entities;
+    const char* env = getenv("TB_INTERLEAVED_ROWS");
+    if (env) c->interleaved = atoi(env);
+    env = getenv("TB_STAGED_EMIT");
+    if (env) c->staged_emit = atoi(env);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return TB_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    const size_t words = (max_entities + 63) / 64;
+    bool ok = cudaMalloc((void**)&c->rows_mem, max_entities * 64) == cudaSuccess;
+    for (int k = 0; ok && k < TB_COMPONENT_COUNT; ++k) {
+        ok = cudaMalloc((void**)&c->mask[k], words * 8) == cudaSuccess;
+        if (ok) cudaMemsetAsync(c->mask[k], 0, words * 8, c->stream);
+    }
+    ok = ok && cudaMallocHost((void**)&c->h_hdr, 64) == cudaSuccess;
+    if (ok) ok = ensure_scratch(c, kHdrWords) == TB_OK;
+    if (!ok) {
+        cudaGetLastError();
+        tb_ctx_destroy(c);
+        return TB_ERR_OOM;
+    }
+    cudaMemsetAsync(c->rows_mem, 0, max_entities * 64, c->stream);
+    c->rows.a = c->rows_mem;
+    c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * max_entities;
+    c->rows.stride = c->interleaved ? 4 : 2;
+    cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 32 * kStageWords * 4);
+    cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 32 * kStageWords * 4);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        tb_ctx_destroy(c);
+        return TB_ERR_CUDA;
+    }
+    *out = c;
+    return TB_OK;
+}
+
+void tb_ctx_destroy(tb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    prof_clear(c);
+    cudaFree(c->rows_mem);
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k) cudaFree(c->mask[k]);
+    cudaFree(c->vel);
+    cudaFree(c->parent);
+    cudaFree(c->stage);
+    cudaFree(c->scratch);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->keys[k]);
+        cudaFree(c->idx[k]);
+    }
+    cudaFree(c->texlayer);
+    cudaFree(c->world);
+    cudaFree(c->inst);
+    cudaFree(c->vtx);
+    cudaFree(c->order);
+    cudaFree(c->batches);
+    cudaFree(c->level_list);
+    cudaFree(c->sane_parent);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* tb_last_error(tb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+tb_status tb_ctx_set_stream(tb_ctx* c, void* cuda_stream) {
+    if (!c) return TB_ERR_INVALID;
+    cudaStreamSynchronize(c->stream);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return TB_OK;
+}
+
+tb_status tb_ctx_synchronize(tb_ctx* c) {
+    if (!c) return TB_ERR_INVALID;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+tb_status tb_ctx_set_max_batches(tb_ctx* c, uint64_t max_batches) {
+    if (!c || max_batches == 0 || max_batches >= (1ull << 30)) return TB_ERR_INVALID;
+    c->max_batches = max_batches;
+    return TB_OK;
+}
+
+tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return TB_ERR_INVALID;
+    std::string k(name);
+    if (k == "interleaved_rows") {
+        if (c->rows_touched) return fail(c, TB_ERR_INVALID, "interleaved_rows must be set before the first upload");
+        c->interleaved = value != 0;
+        c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * c->cap;
+        c->rows.stride = c->interleaved ? 4 : 2;
+    } else if (k == "staged_emit") {
+        c->staged_emit = value != 0;
+    } else if (k == "digit_bits") {
+        if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
+        c->digit_bits = (int)value;
+        c->plan_valid = false;
+    } else if (k == "lt_limit") {
+        if (value < 0 || value > (int64_t)kMaxLtBits) return fail(c, TB_ERR_INVALID, "lt_limit must be 0..16");
+        c->lt_limit = (int)value;
+        c->plan_valid = false;
+    } else {
+        return fail(c, TB_ERR_INVALID, "unknown option " + k);
+    }
+    return TB_OK;
+}
+
+tb_status tb_host_alloc(uint64_t bytes, void** out) {
+    if (!out || bytes == 0) return TB_ERR_INVALID;
+    *out = nullptr;
+    if (cudaMallocHost(out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return TB_ERR_OOM;
+    }
+    return TB_OK;
+}
+
+void tb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- storage ------------------------------------------------------------------------------------
+
+tb_status tb_set_entity_count(tb_ctx* c, uint64_t n) {
+    if (!c) return TB_ERR_INVALID;
+    if (n > c->cap) return fail(c, TB_ERR_CAPACITY, "entity_count beyond max_entities");
+    tb_status s = flush_integrate(c);
+    if (s) return s;
+    if (n < c->n) {
+        // shrinking drops the components of the removed indices
+        for (int k = 0; k < TB_COMPONENT_COUNT; ++k) mark_presence(c, k, n, c->n - n, 0);
+    }
+    c->n = n;
+    c->plan_valid = false;
+    c->levels_dirty = true;
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_entity_count(tb_ctx* c, uint64_t* n) {
+    if (!c || !n) return TB_ERR_INVALID;
+    *n = c->n;
+    return TB_OK;
+}
+
+static tb_status upload_chunks(tb_ctx* c, const void* src, uint64_t n, size_t elem,
+                               void (*launch)(tb_ctx*, const void*, uint64_t, uint64_t, void*), uint64_t first, void* user) {
+    const uint64_t per = kStageChunk / elem;
+    tb_status s = ensure_stage(c, (size_t)std::min<uint64_t>(n, per) * elem);
+    if (s) return s;
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint64_t m = std::min<uint64_t>(per, n - off);
+        TB_CUDA(c, cudaMemcpyAsync(c->stage, (const char*)src + off * elem, m * elem, cudaMemcpyHostToDevice, c->stream));
+        launch(c, c->stage, first + off, m, user);
+        // the staging buffer is reused by the next chunk: same stream, so ordering is implicit
+    }
+    return TB_OK;
+}
+
+tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_transform* src) {
+    tb_status s = check_range(c, first, n, src);
+    if (s || n == 0) return s;
+    if ((s = flush_integrate(c))) return s;
+    c->rows_touched = true;
+    s = upload_chunks(
+        c, src, n, sizeof(tb_transform),
+        [](tb_ctx* c, const void* d, uint64_t f, uint64_t m, void*) {
+            TB_LAUNCH(c, "convert_transforms", m * 96, convert_transforms_kernel, div_up(m, kThreads), kThreads, 0,
+                      (const float*)d, c->rows, (uint32_t)f, (uint32_t)m);
+        },
+        first, nullptr);
+    if (s) return s;
+    c->store[TB_TRANSFORM] = true;
+    mark_presence(c, TB_TRANSFORM, first, n, 1);
+    c->plan_valid = false;
+    c->levels_dirty = true;
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_sprite* src) {
+    tb_status s = check_range(c, first, n, src);
+    if (s || n == 0) return s;
+    c->rows_touched = true;
+    s = upload_chunks(
+        c, src, n, sizeof(tb_sprite),
+        [](tb_ctx* c, const void* d, uint64_t f, uint64_t m, void*) {
+            TB_LAUNCH(c, "convert_sprites", m * 32, convert_sprites_kernel, div_up(m, kThreads), kThreads, 0,
+                      (const uint32_t*)d, c->rows, (uint32_t)f, (uint32_t)m, c->scratch + kHdrRangeErr);
+        },
+        first, nullptr);
+    if (s) return s;
+    c->store[TB_SPRITE] = true;
+    mark_presence(c, TB_SPRITE, first, n, 1);
+    c->plan_valid = false;
+    c->world_valid = false;
+    c->frame_valid = false;
+    // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
+    uint32_t bad = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&bad, c->scratch + kHdrRangeErr, 4, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (bad) {
+        cudaMemsetAsync(c->scratch + kHdrRangeErr, 0, 4, c->stream);
+        return fail(c, TB_ERR_RANGE, "sprite layer > 65534 or texture > 65535");
+    }
+    return TB_OK;
+}
+
+tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_velocity* src) {
+    tb_status s = check_range(c, first, n, src);
+    if (s || n == 0) return s;
+    if ((s = flush_integrate(c))) return s;
+    if (!c->vel) {
+        TB_CUDA(c, cudaMalloc((void**)&c->vel, c->cap * sizeof(tb_velocity)));
+        TB_CUDA(c, cudaMemsetAsync(c->vel, 0, c->cap * sizeof(tb_velocity), c->stream));
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->vel + first * 3, src, n * sizeof(tb_velocity), cudaMemcpyHostToDevice, c->stream));
+    c->store[TB_VELOCITY] = true;
+    mark_presence(c, TB_VELOCITY, first, n, 1);
+    return TB_OK;
+}
+
+tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_t* src) {
+    tb_status s = check_range(c, first, n, src);
+    if (s || n == 0) return s;
+    if (!c->parent) {
+        TB_CUDA(c, cudaMalloc((void**)&c->parent, c->cap * 4));
+        TB_CUDA(c, cudaMemsetAsync(c->parent, 0xFF, c->cap * 4, c->stream));
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->parent + first, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+    c->store[TB_PARENT] = true;
+    // presence == "has a Parent component": every uploaded index whose value is not TB_NO_PARENT
+    {
+        const uint64_t nw = ((first + n - 1) >> 6) - (first >> 6) + 1;
+        TB_LAUNCH(c, "mark_parent_presence", n * 4, mark_parent_presence_kernel, div_up(nw, kThreads), kThreads, 0,
+                  c->mask[TB_PARENT], c->parent, first, n);
+    }
+    c->levels_dirty = true;
+    c->plan_valid = false;
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t nwords, const uint64_t* words) {
+    if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
+    if (nwords == 0) return TB_OK;
+    if (!words) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (first_word + nwords > (c->cap + 63) / 64) return fail(c, TB_ERR_INVALID, "presence words outside max_entities");
+    tb_status s = flush_integrate(c);
+    if (s) return s;
+    TB_CUDA(c, cudaMemcpyAsync(c->mask[comp] + first_word, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
+    c->store[comp] = true;
+    c->plan_valid = false;
+    c->levels_dirty = true;
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_download_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t nwords, uint64_t* words) {
+    if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
+    if (nwords == 0) return TB_OK;
+    if (!words) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (first_word + nwords > (c->cap + 63) / 64) return fail(c, TB_ERR_INVALID, "presence words outside max_entities");
+    TB_CUDA(c, cudaMemcpyAsync(words, c->mask[comp] + first_word, nwords * 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+tb_status tb_download_transforms(tb_ctx* c, uint64_t first, uint64_t n, tb_transform* dst) {
+    tb_status s = check_range(c, first, n, dst);
+    if (s || n == 0) return s;
+    if ((s = flush_integrate(c))) return s;
+    const uint64_t per = kStageChunk / sizeof(tb_transform);
+    if ((s = ensure_stage(c, (size_t)std::min<uint64_t>(n, per) * sizeof(tb_transform)))) return s;
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint64_t m = std::min<uint64_t>(per, n - off);
+        TB_LAUNCH(c, "unconvert_transforms", m * 112, unconvert_transforms_kernel, div_up(m, kThreads), kThreads, 0, c->rows,
+                  (uint32_t)(first + off), (uint32_t)m, (float*)c->stage);
+        TB_CUDA(c, cudaMemcpyAsync(dst + off, c->stage, m * sizeof(tb_transform), cudaMemcpyDeviceToHost, c->stream));
+    }
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+// ---- query ----------------------------------------------------------------------------------------
+
+tb_status tb_query(tb_ctx* c, uint32_t required, uint32_t* out_indices, uint64_t cap, uint64_t* count) {
+    if (!c || !count) return TB_ERR_INVALID;
+    *count = 0;
+    if (required >> TB_COMPONENT_COUNT) return fail(c, TB_ERR_INVALID, "unknown component bit");
+    // query.rs:110 — a required component without a store matches nothing
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k)
+        if (((required >> k) & 1u) && !c->store[k]) return TB_OK;
+    if (c->n == 0) return TB_OK;
+    QueryParams q{};
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k)
+        if ((required >> k) & 1u) q.masks[q.nmasks++] = c->mask[k];
+    q.nwords = div_up(c->n, 64);
+    q.n = (uint32_t)c->n;
+    const uint32_t nblocks = div_up(q.nwords, 1024);
+    tb_status s = ensure_stage(c, (size_t)nblocks * 4 + 16 + (out_indices ? std::min<uint64_t>(cap, c->n) * 4 : 0));
+    if (s) return s;
+    uint32_t* d_counts = (uint32_t*)c->stage;
+    uint32_t* d_total = d_counts + nblocks;
+    uint32_t* d_out = d_counts + nblocks + 4;
+    TB_LAUNCH(c, "query_count", q.nwords * 8ull * q.nmasks, query_count_kernel, nblocks, kThreads, 0, q, d_counts);
+    TB_LAUNCH(c, "query_scan", 0, scan_blocks_kernel, 1, 1024, 0, d_counts, nblocks, d_total);
+    const uint64_t wcap = out_indices ? std::min<uint64_t>(cap, c->n) : 0;
+    if (wcap) TB_LAUNCH(c, "query_write", q.nwords * 8ull * q.nmasks, query_write_kernel, nblocks, kThreads, 0, q, d_counts, d_out, (uint32_t)wcap);
+    uint32_t total = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (wcap) {
+        TB_CUDA(c, cudaMemcpyAsync(out_indices, d_out, std::min<uint64_t>(wcap, total) * 4, cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *count = total;
+    return TB_OK;
+}
+
+// ---- compose ----------------------------------------------------------------------------------------
+
+tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* dst16) {
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!src || !dst16) return fail(c, TB_ERR_INVALID, "null pointer");
+    // temporary rows + world rows, chunked
+    const uint64_t per = 1u << 20;
+    float4* d_rows = nullptr;
+    WorldRow* d_world = nullptr;
+    float* d_in = nullptr;
+    float* d_out = nullptr;
+    const uint64_t m0 = std::min<uint64_t>(n, per);
+    TB_CUDA(c, cudaMalloc((void**)&d_rows, m0 * 64));
+    cudaError_t e = cudaMalloc((void**)&d_world, m0 * 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_in, m0 * 48);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, m0 * 64);
+    if (e != cudaSuccess) {
+        cudaFree(d_rows); cudaFree(d_world); cudaFree(d_in); cudaFree(d_out);
+        return cuda_fail(c, e, "cudaMalloc(as_matrix4)");
+    }
+    RowView rv{d_rows, d_rows + 2 * m0, 2};
+    tb_status s = TB_OK;
+    for (uint64_t off = 0; off < n && s == TB_OK; off += per) {
+        const uint64_t m = std::min<uint64_t>(per, n - off);
+        cudaMemcpyAsync(d_in, src + off, m * 48, cudaMemcpyHostToDevice, c->stream);
+        TB_LAUNCH(c, "convert_transforms", m * 96, convert_transforms_kernel, div_up(m, kThreads), kThreads, 0, d_in, rv, 0u, (uint32_t)m);
+        TB_LAUNCH(c, "compose_world", m * 128, compose_world_kernel, div_up(m, kThreads), kThreads, 0, rv, (const uint64_t*)nullptr, (uint32_t)m, d_world);
+        TB_LAUNCH(c, "world_to_mat4", m * 128, world_to_mat4_kernel, div_up(m, kThreads), kThreads, 0, d_world, (const uint64_t*)nullptr, 0u, (uint32_t)m, d_out);
+        cudaMemcpyAsync(dst16 + off * 16, d_out, m * 64, cudaMemcpyDeviceToHost, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) s = cuda_fail(c, e, "tb_as_matrix4");
+    }
+    cudaFree(d_rows); cudaFree(d_world); cudaFree(d_in); cudaFree(d_out);
+    return s;
+}
+
+// ---- systems ------------------------------------------------------------------------------------------
+
+tb_status tb_system_integrate(tb_ctx* c, float dt) {
+    if (!c) return TB_ERR_INVALID;
+    tb_status s = flush_integrate(c);  // an earlier tick that no frame consumed
+    if (s) return s;
+    c->pending = true;
+    c->pending_dt = dt;
+    c->world_valid = false;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+// ---- frame ----------------------------------------------------------------------------------------------
+
+tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
+    if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
+    c->force_path = path;
+    c->plan_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
+    if (!c || !out) return TB_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    c->frame_launches = 0;
+    if (c->prof) prof_clear(c);
+    c->frame_valid = false;
+    c->last_instances = c->last_batches = 0;
+    const uint64_t n = c->n;
+    // query::<(&Transform, &Sprite)>: no store for either => no matches (query.rs:110)
+    if (n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
+        tb_status s = flush_integrate(c);
+        if (s) return s;
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->frame_valid = true;
+        out->kernel_launches = c->frame_launches;
+        return TB_OK;
+    }
+    tb_status s;
+    if (c->levels_dirty && (s = plan_levels(c))) return s;
+    FrameMode fm{};
+    fm.hier = c->nlevels > 1;
+    if ((s = ensure_outputs(c, n))) return s;
+    if (fm.hier && (s = ensure_world(c, n))) return s;
+    float4* d_inst = c->ext_inst ? (float4*)c->ext_inst : c->inst;
+    float4* d_vtx = c->ext_vtx ? (float4*)c->ext_vtx : c->vtx;
+    uint32_t* d_order = c->ext_order ? (uint32_t*)c->ext_order : c->order;
+
+    bool integrate = c->pending;
+    c->pending = false;
+    uint32_t replanned = 0;
+    uint64_t count = 0, num_batches = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (!c->plan_valid) {
+            // discovery: key statistics only (and the velocity system, exactly once)
+            TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+            if ((s = run_prepare(c, false, integrate, fm, nullptr))) return s;
+            integrate = false;
+            if ((s = read_header(c))) return s;
+            count = c->h_hdr[2];
+            if (count == 0) break;
+            make_plan(c, c->h_hdr[0], ~c->h_hdr[1]);
+        }
+        const FramePlan& plan = c->plan;
+        if (c->force_path == TB_PATH_BUCKET && plan.npasses > 1)
+            return fail(c, TB_ERR_UNSUPPORTED, "TB_PATH_BUCKET needs at most 256 distinct key buckets");
+        fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
+        fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
+        fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist);
+        if ((s = ensure_scratch(c, L.total_words))) return s;
+        if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        if (fm.lt_generic) {
+            size_t cap = c->texlayer ? c->texlayer_cap : 0;
+            if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
+            c->texlayer_cap = cap;
+        }
+        // zero: stats, num_batches | tile counters, histograms, lt bins, look-back words
+        TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (L.total_words - kHdrTileCounters) * 4, c->stream));
+        if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
+        integrate = false;
+        uint32_t* hist = c->scratch + kHdrHist;
+        if (!fm.lt_generic) {
+            const uint32_t* bins = fm.lt_alias ? hist : c->scratch + L.lt_off;
+            TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
+                      (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
+        }
+        TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
+        if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, d_inst, d_vtx, d_order);
+        else s = run_sort_and_emit<uint32_t>(c, fm, L, d_inst, d_vtx, d_order);
+        if (s) return s;
+        if ((s = read_header(c))) return s;
+        count = c->h_hdr[2];
+        const uint64_t k_or = c->h_hdr[0], k_and = ~c->h_hdr[1];
+        if (count == 0) break;
+        if (!plan_covers(plan, k_or, k_and)) {
+            // the scene's keys moved outside the cached plan: re-plan from this frame's statistics
+            make_plan(c, k_or, k_and);
+            replanned = 1;
+            continue;
+        }
+        if (fm.lt_generic) {
+            const uint32_t nb = div_up(count, 1024);
+            if ((s = ensure_stage(c, (size_t)nb * 4))) return s;
+            uint32_t* d_counts = (uint32_t*)c->stage;
+            TB_LAUNCH(c, "batch_heads_count", count * 4, batch_heads_count_kernel, nb, kThreads, 0, c->texlayer, (uint32_t)count, d_counts);
+            TB_LAUNCH(c, "batch_heads_scan", 0, scan_blocks_kernel, 1, 1024, 0, d_counts, nb, c->scratch + kHdrNumBatches);
+            TB_LAUNCH(c, "batch_heads_write", count * 4, batch_heads_write_kernel, nb, kThreads, 0, c->texlayer, (uint32_t)count,
+                      d_counts, c->batches, (uint32_t)c->max_batches);
+            TB_LAUNCH(c, "batch_counts", 0, batch_counts_kernel, div_up(c->max_batches, kThreads), kThreads, 0, c->batches,
+                      c->scratch + kHdrNumBatches, (uint32_t)c->max_batches, (uint32_t)count);
+            if ((s = read_header(c))) return s;
+        }
+        num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
+        break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, "frame");
+    if (num_batches > c->max_batches) return fail(c, TB_ERR_CAPACITY, "more batches than tb_ctx_set_max_batches allows");
+    c->last_instances = count;
+    c->last_batches = num_batches;
+    c->frame_valid = true;
+    out->num_instances = count;
+    out->num_batches = num_batches;
+    out->d_instances = (const tb_instance*)d_inst;
+    out->d_vertices = (const tb_quad_vertex*)d_vtx;
+    out->d_batches = (const tb_batch*)c->batches;
+    out->d_order = d_order;
+    out->path = count == 0 ? TB_PATH_NONE : (c->plan.npasses == 1 ? TB_PATH_BUCKET : TB_PATH_SORT);
+    out->key_bits = count == 0 ? 0 : c->plan.pext.nbits;
+    out->sort_passes = count == 0 ? 0 : c->plan.npasses;
+    out->kernel_launches = c->frame_launches;
+    out->hierarchy_levels = fm.hier ? c->nlevels : 0;
+    out->replanned = replanned;
+    return TB_OK;
+}
+
+static tb_status download(tb_ctx* c, const void* d_src, uint64_t first, uint64_t n, uint64_t limit, size_t elem, void* dst) {
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!dst) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (!c->frame_valid) return fail(c, TB_ERR_INVALID, "no frame has been run since the last change");
+    if (first + n > limit) return fail(c, TB_ERR_INVALID, "range outside the last frame's output");
+    TB_CUDA(c, cudaMemcpyAsync(dst, (const char*)d_src + first * elem, n * elem, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+tb_status tb_download_instances(tb_ctx* c, uint64_t first, uint64_t n, tb_instance* dst) {
+    if (!c) return TB_ERR_INVALID;
+    return download(c, c->ext_inst ? c->ext_inst : (void*)c->inst, first, n, c->last_instances, sizeof(tb_instance), dst);
+}
+tb_status tb_download_vertices(tb_ctx* c, uint64_t first, uint64_t n, tb_quad_vertex* dst) {
+    if (!c) return TB_ERR_INVALID;
+    return download(c, c->ext_vtx ? c->ext_vtx : (void*)c->vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
+}
+tb_status tb_download_batches(tb_ctx* c, uint64_t first, uint64_t n, tb_batch* dst) {
+    if (!c) return TB_ERR_INVALID;
+    return download(c, c->batches, first, n, c->last_batches, sizeof(tb_batch), dst);
+}
+tb_status tb_download_order(tb_ctx* c, uint64_t first, uint64_t n, uint32_t* dst) {
+    if (!c) return TB_ERR_INVALID;
+    return download(c, c->ext_order ? c->ext_order : (void*)c->order, first, n, c->last_instances, 4, dst);
+}
+
+tb_status tb_download_world_matrices(tb_ctx* c, uint64_t first, uint64_t n, float* dst16) {
+    tb_status s = check_range(c, first, n, dst16);
+    if (s || n == 0) return s;
+    if ((s = flush_integrate(c))) return s;
+    if (c->levels_dirty && (s = plan_levels(c))) return s;
+    if (!c->world_valid) {
+        if ((s = ensure_world(c, c->n))) return s;
+        if (c->nlevels > 1) {
+            FrameMode fm{};
+            fm.hier = true;
+            if ((s = ensure_scratch(c, kHdrWords))) return s;
+            TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+            if ((s = run_prepare(c, false, false, fm, nullptr))) return s;
+        } else {
+            TB_LAUNCH(c, "compose_world", c->n * 128, compose_world_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows,
+                      mask_or_null(c, TB_TRANSFORM), (uint32_t)c->n, c->world);
+        }
+        c->world_valid = true;
+    }
+    const uint64_t per = kStageChunk / 64;
+    if ((s = ensure_stage(c, (size_t)std::min<uint64_t>(n, per) * 64))) return s;
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint64_t m = std::min<uint64_t>(per, n - off);
+        TB_LAUNCH(c, "world_to_mat4", m * 128, world_to_mat4_kernel, div_up(m, kThreads), kThreads, 0, c->world,
+                  c->store[TB_TRANSFORM] ? mask_or_null(c, TB_TRANSFORM) : c->mask[TB_TRANSFORM], (uint32_t)(first + off),
+                  (uint32_t)m, (float*)c->stage);
+        TB_CUDA(c, cudaMemcpyAsync(dst16 + off * 16, c->stage, m * 64, cudaMemcpyDeviceToHost, c->stream));
+    }
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+// ---- instrumentation ----------------------------------------------------------------------------------------
+
+tb_status tb_profile_enable(tb_ctx* c, int on) {
+    if (!c) return TB_ERR_INVALID;
+    cudaStreamSynchronize(c->stream);
+    prof_clear(c);
+    c->prof = on != 0;
+    return TB_OK;
+}
+
+tb_status tb_profile_count(tb_ctx* c, uint32_t* n) {
+    if (!c || !n) return TB_ERR_INVALID;
+    *n = (uint32_t)c->prof_entries.size();
+    return TB_OK;
+}
+
+tb_status tb_profile_get(tb_ctx* c, uint32_t i, const char** name, float* ms, uint64_t* bytes) {
+    if (!c || i >= c->prof_entries.size()) return TB_ERR_INVALID;
+    if (c->prof_ms.empty()) {
+        cudaStreamSynchronize(c->stream);
+        c->prof_ms.resize(c->prof_entries.size());
+        for (size_t k = 0; k < c->prof_entries.size(); ++k)
+            cudaEventElapsedTime(&c->prof_ms[k], c->prof_entries[k].e0, c->prof_entries[k].e1);
+    }
+    if (name) *name = c->prof_entries[i].name;
+    if (ms) *ms = c->prof_ms[i];
+    if (bytes) *bytes = c->prof_entries[i].bytes;
+    return TB_OK;
+}
+
+tb_status tb_launch_count(tb_ctx* c, uint64_t* n) {
+    if (!c || !n) return TB_ERR_INVALID;
+    *n = c->launches;
+    return TB_OK;
+}
+
+// ---- sharding ------------------------------------------------------------------------------------------------
+
+tb_status tb_shard_set(tb_ctx* c, int rank, int nranks, uint64_t global_first) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return TB_ERR_INVALID;
+    if (global_first + c->cap > (1ull << 32)) return fail(c, TB_ERR_INVALID, "global entity ids must fit 32 bits");
+    c->rank = rank;
+    c->nranks = nranks;
+    c->global_first = global_first;
+    c->levels_dirty = true;
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_frame_set_output(tb_ctx* c, void* d_instances, void* d_vertices, void* d_order, uint64_t capacity) {
+    if (!c) return TB_ERR_INVALID;
+    if (!d_instances && !d_vertices && !d_order) {
+        c->ext_inst = c->ext_vtx = c->ext_order = nullptr;
+        c->ext_cap = 0;
+    } else {
+        if (!d_instances || !d_vertices || !d_order) return fail(c, TB_ERR_INVALID, "all three output buffers are required");
+        c->ext_inst = d_instances;
+        c->ext_vtx = d_vertices;
+        c->ext_order = d_order;
+        c->ext_cap = capacity;
+    }
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+}  // extern "C"
