@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline metric on B200 (contract in the task statement).
+
+A "step" is one engine tick + one render of the north-star workload, BASELINE.json configs[3]:
+2^24 particle-style entities per GPU (Transform + Velocity + Sprite, 4 textures, 1 layer):
+velocity system -> Transform->Matrix4 compose -> stable sort on (layer, texture, z) -> instance +
+quad-vertex emission + batch table. Every rank owns a contiguous entity-id range of the same
+seeded scene (weak scaling: 2^24 entities per rank, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+value  = entities/s, all ranks, inputs resident in HBM, K steps between CUDA events (max over ranks)
+e2e    = the same through the C ABI with host buffers: H2D of every component array and D2H of
+         instances, vertices, order and batch table inside the timed region, every step
+roofline = the emit kernel (dominant): algorithmic bytes / its CUDA-event time vs measured HBM peak
+cpu_baseline = the CPU oracle (restated reference path, 1 thread) on a bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "entities/sec per frame (transform+batch)"
+UNIT = "entities/s"
+N_PER_GPU = 1 << 24
+ALG_BYTES_FRAME = 232   # SURVEY.md §8d, particles: 48+16+12 read, 80+64+12 written
+ALG_BYTES_EMIT = 208    # the emit kernel's share: Transform+Sprite read, Instance+4 QuadVertex written
+CPU_SAMPLE = 1 << 22
+
+
+def workload_name(n):
+    return (f"configs[3]: {n} particle-style entities per GPU (Transform+Velocity+Sprite, 4 textures, 1 layer, "
+            "dt=0.01): velocity system + transform + sprite batching per frame")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for k in dir(nv):
+            if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason"):
+                v = getattr(nv, k)
+                if isinstance(v, int) and v:
+                    names.setdefault(v, k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit and bit & (bit - 1) == 0:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        reasons = sorted(r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference(steps, warmup, n_sample):
+    """The CPU oracle (oracle/: restated tuber-ecs query + tuber-math compose + SPEC batching), single
+    thread like the reference, on the first n_sample entities of the same scene."""
+    from oracle import oracle
+    from tuber_legacy_b200 import scenes
+    sc = scenes.config4(n=N_PER_GPU, count=n_sample)
+    ref = oracle.Scene(sc.n, sc.transforms, sc.sprites, sc.velocities)
+    times = []
+    for i in range(warmup + steps):
+        t = ref.step(sc.dt)
+        t += ref.frame().seconds
+        if i >= warmup:
+            times.append(t)
+    ref.close()
+    total = sum(times)
+    return {"value": n_sample * len(times) / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {n_sample} entities of the workload scene, {len(times)} frames "
+                      f"(velocity system + render_scene), {total:.1f} s of CPU time"}, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # bounded: ~1.5 M entities/s -> about 0.7 s per step at 2^20
+    n_sample = 1 << 20
+    cb, step_s = cpu_reference(args.steps, args.warmup, n_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(N_PER_GPU),
+                   "note": "reference arm: the Rust reference cannot be built here (no cargo/rustc); this is the CPU "
+                           "oracle port of its path, single thread like the reference (RefCell storage, "
+                           "sequential systems), each step a bounded sample"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--entities", type=int, default=N_PER_GPU, help="entities per GPU (default: the named workload)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--option", action="append", default=[], help="tb_ctx_set_option name=value")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tuber_legacy_b200 import capi, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.entities
+    first = rank * n
+    sc = scenes.config4(n=world * n, first=first, count=n)
+    options = dict(kv.split("=") for kv in args.option)
+    ctx = capi.Context(n, device=local_rank, **{k: int(v) for k, v in options.items()})
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.shard_set(rank, world, first)
+    ctx.set_entity_count(n)
+
+    # pinned host copies of the component arrays and of the outputs (the e2e leg's buffers)
+    def pinned(a):
+        buf, ptr = capi.host_alloc(a.nbytes)
+        out = buf.view(a.dtype).reshape(a.shape)
+        out[...] = a
+        return out, ptr
+
+    h_t, p_t = pinned(sc.transforms)
+    h_s, p_s = pinned(sc.sprites)
+    h_v, p_v = pinned(sc.velocities)
+    del sc.transforms, sc.sprites, sc.velocities
+    ctx.upload_transforms(0, h_t)
+    ctx.upload_sprites(0, h_s)
+    ctx.upload_velocities(0, h_v)
+    dt = sc.dt
+
+    def step():
+        ctx.system_integrate(dt)
+        return ctx.frame()
+
+    # ---- device-resident measurement ---------------------------------------------------------
+    for _ in range(args.warmup):
+        info = step()
+    assert info.num_instances == n and info.replanned == 0
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        info = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    gpu_launches = ctx.launch_count() - launches0
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    assert info.num_instances == n
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    h_inst, p_i = capi.host_alloc(n * 80)
+    h_vtx, p_x = capi.host_alloc(n * 64)
+    h_ord, p_o = capi.host_alloc(n * 4)
+    inst = h_inst.view(capi.INSTANCE_DTYPE)
+    vtx = h_vtx.view(capi.VERTEX_DTYPE).reshape(n, 4)
+    order = h_ord.view(np.uint32)
+
+    def e2e_step():
+        ctx.upload_transforms(0, h_t)
+        ctx.upload_sprites(0, h_s)
+        ctx.upload_velocities(0, h_v)
+        ctx.system_integrate(dt)
+        out = ctx.frame()
+        ctx.download_instances(out.num_instances, out=inst)
+        ctx.download_vertices(out.num_instances, out=vtx)
+        ctx.download_order(out.num_instances, out=order)
+        return out, ctx.download_batches(out.num_batches)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.e2e_steps):
+        out, batches = e2e_step()
+    f1.record(stream)
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    h2d = h_t.nbytes + h_s.nbytes + h_v.nbytes
+    d2h = int(out.num_instances) * (80 + 64 + 4) + int(out.num_batches) * 16
+    checksum = int(order[:: max(1, n // 4096)].astype(np.uint64).sum())
+
+    # ---- reduce over ranks: max time, summed work -------------------------------------------------
+    vals = torch.tensor([ms_total, e2e_ms, float(gpu_launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms, gpu_launches = float(mx[0]), float(mx[1]), float(sm[2])
+    total_entities = n * world
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms_per_step = ms_total / args.steps
+        value = total_entities * args.steps / (ms_total * 1e-3)
+        emit_ms, _, emit_launches = prof.get("emit", (0.0, 0, 0))
+        emit_ms_avg = emit_ms / max(emit_launches, 1)
+        achieved = n * ALG_BYTES_EMIT / (emit_ms_avg * 1e-3) / 1e9 if emit_ms_avg > 0 else None
+        kernels = {k: {"ms_per_launch": v[0] / max(v[2], 1), "launches_per_step": v[2] / args.steps,
+                       "share_of_step": v[0] / ms_total} for k, v in prof.items()}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n), "entities_per_gpu": n, "sharding": f"contiguous id range x{world}",
+                       "l2": "no flush needed: each pass streams >= 0.5 GB per GPU, far larger than the 126 MB L2",
+                       "path": {1: "bucket (one fused rank+compose+emit pass)", 2: "sort"}.get(info.path),
+                       "key_bits": info.key_bits, "sort_passes": info.sort_passes, "options": options},
+            "clocks": clocks,
+            "e2e": {"value": total_entities * args.e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.e2e_steps,
+                    "steps": args.e2e_steps, "host_buffers": "pinned (tb_host_alloc)", "order_checksum": checksum},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "kernel": "emit_kernel<uint32_t>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_entity": ALG_BYTES_EMIT,
+                         "ms_per_launch": emit_ms_avg},
+            "frame_roofline": {"algorithmic_bytes_per_entity": ALG_BYTES_FRAME,
+                               "achieved": n * ALG_BYTES_FRAME / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": n * ALG_BYTES_FRAME / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "note": "whole step (all kernels + the per-frame host sync) against the same peak"},
+            "kernels": kernels,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "emit_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_reference(3, 1, CPU_SAMPLE)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    ctx.close()
+    for p in (p_t, p_s, p_v, p_i, p_x, p_o):
+        capi.host_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -204,11 +204,13 @@ TB_API tb_status tb_download_world_matrices(tb_ctx* ctx, uint64_t first, uint64_
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 
-/* Per-kernel device times of the last frame, measured with CUDA events on the launching
- * stream (enable before the frame). Names are static strings. */
+/* Per-kernel device times, measured with CUDA events on the launching stream and summed per
+ * kernel name since tb_profile_enable(ctx, 1) (which also resets the totals). `bytes` is the
+ * memory traffic the host code expects of those launches. Names are static strings. */
 TB_API tb_status tb_profile_enable(tb_ctx* ctx, int on);
 TB_API tb_status tb_profile_count(tb_ctx* ctx, uint32_t* n);
-TB_API tb_status tb_profile_get(tb_ctx* ctx, uint32_t i, const char** name, float* ms, uint64_t* algorithmic_bytes);
+TB_API tb_status tb_profile_get(tb_ctx* ctx, uint32_t i, const char** name, double* total_ms, uint64_t* total_bytes,
+                                uint32_t* launches);
 /* Total kernels launched by this context since creation. */
 TB_API tb_status tb_launch_count(tb_ctx* ctx, uint64_t* n);
 

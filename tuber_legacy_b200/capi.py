@@ -84,8 +84,8 @@ _SIGNATURES = {
     "tb_download_world_matrices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
     "tb_profile_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
-    "tb_profile_get": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
-                                   C.POINTER(C.c_uint64)]),
+    "tb_profile_get": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "tb_launch_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "tb_shard_set": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_uint64]),
     "tb_frame_set_output": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -286,13 +286,14 @@ class Context:
         self._check(self._lib.tb_profile_enable(self._h, 1 if on else 0))
 
     def profile(self):
+        """{kernel name: (total ms, expected bytes, launches)} since profile_enable()."""
         n = C.c_uint32()
         self._check(self._lib.tb_profile_count(self._h, C.byref(n)))
-        rows = []
+        rows = {}
         for i in range(n.value):
-            name, ms, b = C.c_char_p(), C.c_float(), C.c_uint64()
-            self._check(self._lib.tb_profile_get(self._h, i, C.byref(name), C.byref(ms), C.byref(b)))
-            rows.append((name.value.decode(), ms.value, b.value))
+            name, ms, b, k = C.c_char_p(), C.c_double(), C.c_uint64(), C.c_uint32()
+            self._check(self._lib.tb_profile_get(self._h, i, C.byref(name), C.byref(ms), C.byref(b), C.byref(k)))
+            rows[name.value.decode()] = (ms.value, b.value, k.value)
         return rows
 
     def launch_count(self):

@@ -30,6 +30,14 @@ struct ProfEntry {
     uint64_t bytes;
 };
 
+// per-kernel-name totals since tb_profile_enable
+struct ProfTotal {
+    const char* name;
+    double ms;
+    uint64_t bytes;
+    uint32_t launches;
+};
+
 }  // namespace
 
 struct tb_ctx {
@@ -107,8 +115,9 @@ struct tb_ctx {
 
     // instrumentation
     bool prof = false;
-    std::vector<ProfEntry> prof_entries;
-    std::vector<float> prof_ms;
+    std::vector<ProfEntry> prof_entries;   // launched, not yet harvested
+    std::vector<ProfTotal> prof_totals;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
     uint64_t launches = 0;
     uint32_t frame_launches = 0;
 };
@@ -144,8 +153,14 @@ tb_status cuda_fail(tb_ctx* c, cudaError_t e, const char* what) {
 void prof_begin(tb_ctx* c, const char* name, uint64_t bytes) {
     if (!c->prof) return;
     ProfEntry pe{name, nullptr, nullptr, bytes};
-    cudaEventCreate(&pe.e0);
-    cudaEventCreate(&pe.e1);
+    if (!c->prof_pool.empty()) {
+        pe.e0 = c->prof_pool.back().first;
+        pe.e1 = c->prof_pool.back().second;
+        c->prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&pe.e0);
+        cudaEventCreate(&pe.e1);
+    }
     cudaEventRecord(pe.e0, c->stream);
     c->prof_entries.push_back(pe);
 }
@@ -153,13 +168,36 @@ void prof_end(tb_ctx* c) {
     if (!c->prof) return;
     cudaEventRecord(c->prof_entries.back().e1, c->stream);
 }
-void prof_clear(tb_ctx* c) {
+// Folds finished launches into the per-name totals. Call only when the stream is idle.
+void prof_harvest(tb_ctx* c) {
     for (auto& pe : c->prof_entries) {
-        cudaEventDestroy(pe.e0);
-        cudaEventDestroy(pe.e1);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, pe.e0, pe.e1) != cudaSuccess) {
+            cudaGetLastError();
+            ms = 0.0f;
+        }
+        ProfTotal* t = nullptr;
+        for (auto& pt : c->prof_totals)
+            if (pt.name == pe.name || strcmp(pt.name, pe.name) == 0) t = &pt;
+        if (!t) {
+            c->prof_totals.push_back(ProfTotal{pe.name, 0.0, 0, 0});
+            t = &c->prof_totals.back();
+        }
+        t->ms += ms;
+        t->bytes += pe.bytes;
+        t->launches += 1;
+        c->prof_pool.emplace_back(pe.e0, pe.e1);
     }
     c->prof_entries.clear();
-    c->prof_ms.clear();
+}
+void prof_clear(tb_ctx* c) {
+    prof_harvest(c);
+    for (auto& ev : c->prof_pool) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    c->prof_pool.clear();
+    c->prof_totals.clear();
 }
 
 #define TB_LAUNCH(c, name, bytes, kern, grid, block, smem, ...)        \
@@ -1070,7 +1108,6 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     if (!c || !out) return TB_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     c->frame_launches = 0;
-    if (c->prof) prof_clear(c);
     c->frame_valid = false;
     c->last_instances = c->last_batches = 0;
     const uint64_t n = c->n;
@@ -1164,6 +1201,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(c, e, "frame");
+    if (c->prof) prof_harvest(c);
     if (num_batches > c->max_batches) return fail(c, TB_ERR_CAPACITY, "more batches than tb_ctx_set_max_batches allows");
     c->last_instances = count;
     c->last_batches = num_batches;
@@ -1255,21 +1293,18 @@ tb_status tb_profile_enable(tb_ctx* c, int on) {
 
 tb_status tb_profile_count(tb_ctx* c, uint32_t* n) {
     if (!c || !n) return TB_ERR_INVALID;
-    *n = (uint32_t)c->prof_entries.size();
+    cudaStreamSynchronize(c->stream);
+    prof_harvest(c);
+    *n = (uint32_t)c->prof_totals.size();
     return TB_OK;
 }
 
-tb_status tb_profile_get(tb_ctx* c, uint32_t i, const char** name, float* ms, uint64_t* bytes) {
-    if (!c || i >= c->prof_entries.size()) return TB_ERR_INVALID;
-    if (c->prof_ms.empty()) {
-        cudaStreamSynchronize(c->stream);
-        c->prof_ms.resize(c->prof_entries.size());
-        for (size_t k = 0; k < c->prof_entries.size(); ++k)
-            cudaEventElapsedTime(&c->prof_ms[k], c->prof_entries[k].e0, c->prof_entries[k].e1);
-    }
-    if (name) *name = c->prof_entries[i].name;
-    if (ms) *ms = c->prof_ms[i];
-    if (bytes) *bytes = c->prof_entries[i].bytes;
+tb_status tb_profile_get(tb_ctx* c, uint32_t i, const char** name, double* ms, uint64_t* bytes, uint32_t* launches) {
+    if (!c || i >= c->prof_totals.size()) return TB_ERR_INVALID;
+    if (name) *name = c->prof_totals[i].name;
+    if (ms) *ms = c->prof_totals[i].ms;
+    if (bytes) *bytes = c->prof_totals[i].bytes;
+    if (launches) *launches = c->prof_totals[i].launches;
     return TB_OK;
 }
 
