@@ -194,13 +194,17 @@ struct PrepParams {
     uint32_t* hist;        // [kMaxPasses][256]
     uint32_t* lt_hist;     // [1 << ltbits]
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+    uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per 512-entity emit tile
+    uint32_t emit_tiles;
     FramePlan plan;
 };
 
 constexpr int kPrepItems = 4;
+constexpr uint32_t kEmitTileConst = 512;  // == kEmitTile (two per prepare tile)
 
 struct PrepShared {
     uint32_t hist[kMaxPasses][256];
+    uint32_t tcnt[2][2][256];  // [iteration parity][half of the 1024-entity tile][pass-0 digit]
     uint32_t lt[2048];
     unsigned long long k_or, k_and;
     uint32_t count;
@@ -208,7 +212,7 @@ struct PrepShared {
 
 // Accumulates one key into the per-block plan statistics and histograms.
 __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, bool renderable, uint64_t key,
-                                             uint32_t i) {
+                                             uint32_t i, uint32_t* tcnt = nullptr) {
     // key masks: warp-reduce then one shared atomic per warp
     const uint32_t act = __ballot_sync(0xffffffffu, renderable);
     if (act == 0) return;
@@ -228,6 +232,7 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
         const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
         atomicAdd(&sh.hist[q][d], 1u);
+        if (q == 0 && tcnt != nullptr) atomicAdd(&tcnt[d], 1u);
     }
     if (p.lt_mode == 1) atomicAdd(&sh.lt[(uint32_t)(sk >> p.plan.zbits)], 1u);
     else if (p.lt_mode == 2) atomicAdd(&p.lt_hist[(uint32_t)(sk >> p.plan.zbits)], 1u);
@@ -281,41 +286,69 @@ __global__ void __launch_bounds__(kThreads) prepare_flat_kernel(const PrepParams
     prep_init(p, sh);
     const uint32_t tile_elems = kThreads * kPrepItems;
     const uint32_t ntiles = (p.n + tile_elems - 1) / tile_elems;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const bool do_int = p.integrate && p.vel != nullptr;
+    const bool tiles_out = p.have_plan && p.tile_counts != nullptr;
+    const uint32_t R0 = 1u << p.plan.bits[0];
+    uint32_t par = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1u) {
         const uint32_t base = tile * tile_elems + threadIdx.x;
+        if (tiles_out) {
+            for (uint32_t d = threadIdx.x; d < 2 * 256; d += kThreads) (&sh.tcnt[par][0][0])[d] = 0;
+        }
         float4 a0[kPrepItems], a1[kPrepItems];
-        bool has_t[kPrepItems], rend[kPrepItems];
+        float vx[kPrepItems], vy[kPrepItems], vz[kPrepItems];
+        bool has_t[kPrepItems], rend[kPrepItems], has_v[kPrepItems];
+        // Every load of the tile is issued before anything is consumed: rows and velocities exist
+        // (zero-filled) for every id below max_entities, so they do not wait for the presence bits.
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
             const uint32_t i = base + k * kThreads;
-            has_t[k] = i < p.n && mask_bit(p.mask_t, i);
-            rend[k] = has_t[k] && mask_bit(p.mask_s, i);
-            if (has_t[k]) {
+            const bool inb = i < p.n;
+            a0[k] = a1[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            vx[k] = vy[k] = vz[k] = 0.0f;
+            has_t[k] = rend[k] = has_v[k] = false;
+            if (inb) {
                 const size_t o = (size_t)i * p.rows.stride;
                 a0[k] = p.rows.a[o];
                 a1[k] = p.rows.a[o + 1];
-            }
-        }
-        if (p.integrate) {
-#pragma unroll
-            for (int k = 0; k < kPrepItems; ++k) {
-                const uint32_t i = base + k * kThreads;
-                if (has_t[k] && p.vel != nullptr && mask_bit(p.mask_v, i)) {
+                if (do_int) {
                     const float* v = p.vel + (size_t)i * 3;
-                    const float vx = __ldg(v), vy = __ldg(v + 1), vz = __ldg(v + 2);
-                    a0[k].x = addr(a0[k].x, mulr(vx, p.dt));
-                    a0[k].y = addr(a0[k].y, mulr(vy, p.dt));
-                    a0[k].z = addr(a0[k].z, mulr(vz, p.dt));
-                    p.rows.a[(size_t)i * p.rows.stride] = a0[k];
+                    vx[k] = __ldg(v);
+                    vy[k] = __ldg(v + 1);
+                    vz[k] = __ldg(v + 2);
+                    has_v[k] = mask_bit(p.mask_v, i);
                 }
+                has_t[k] = mask_bit(p.mask_t, i);
+                rend[k] = mask_bit(p.mask_s, i);
             }
         }
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {
+            const uint32_t i = base + k * kThreads;
+            rend[k] = rend[k] && has_t[k];
+            if (do_int && has_t[k] && has_v[k]) {
+                a0[k].x = addr(a0[k].x, mulr(vx[k], p.dt));
+                a0[k].y = addr(a0[k].y, mulr(vy[k], p.dt));
+                a0[k].z = addr(a0[k].z, mulr(vz[k], p.dt));
+                p.rows.a[(size_t)i * p.rows.stride] = a0[k];
+            }
+        }
+        if (tiles_out) __syncthreads();
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
             const uint32_t i = base + k * kThreads;
             uint64_t key = 0;
             if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
-            prep_account(p, sh, rend[k], key, i);
+            prep_account(p, sh, rend[k], key, i, tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
+        }
+        if (tiles_out) {
+            // this 1024-entity tile is two 512-entity emit tiles
+            __syncthreads();
+            for (uint32_t d = threadIdx.x; d < 2 * R0; d += kThreads) {
+                const uint32_t h = d / R0, dd = d - h * R0;
+                const uint32_t et = tile * 2 + h;
+                if (et < p.emit_tiles) p.tile_counts[(size_t)dd * p.emit_tiles + et] = sh.tcnt[par][h][dd];
+            }
         }
     }
     prep_flush(p, sh);
@@ -426,6 +459,74 @@ __global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
     h[threadIdx.x] = x + add - v;
 }
 
+// First output position of every (digit, tile) of one pass from its per-tile digit counts
+// (reduce-then-scan radix placement: no inter-CTA waiting anywhere). counts and tile_off are
+// digit-major [R][ntiles]; hist is the pass's raw 256-bin digit histogram. Grid (chunks of 1024
+// tiles, R): every block sums the chunks before its own (coalesced, L2-resident) instead of
+// waiting for them.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ counts, uint32_t ntiles,
+                                                          const uint32_t* __restrict__ hist, uint32_t* tile_off) {
+    __shared__ uint32_t s[1024];
+    __shared__ uint32_t s_base;
+    const uint32_t d = blockIdx.y, chunk = blockIdx.x;
+    const uint32_t* row = counts + (size_t)d * ntiles;
+    // base = all smaller digits (global) + this digit's tiles before the chunk
+    uint32_t pre = 0;
+    for (uint32_t k = threadIdx.x; k < d; k += 1024) pre += hist[k];
+    for (uint32_t t = threadIdx.x; t < chunk * 1024u; t += 1024) pre += row[t];
+    const uint32_t t = chunk * 1024u + threadIdx.x;
+    const uint32_t v = t < ntiles ? row[t] : 0u;
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && pre) atomicAdd(&s_base, pre);
+    // inclusive scan of v over the block
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = s[threadIdx.x];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (threadIdx.x >= (uint32_t)o) w += y;
+        }
+        s[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t wbase = (threadIdx.x >> 5) ? s[(threadIdx.x >> 5) - 1] : 0u;
+    if (t < ntiles) tile_off[(size_t)d * ntiles + t] = s_base + wbase + x - v;
+}
+
+// Per-tile digit counts of one pass's input (positions in the pass's input order).
+// counts is digit-major [R][ntiles]. One block per tile.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) tile_hist_kernel(const KeyT* __restrict__ keys, uint32_t n,
+                                                              const unsigned long long* count_ptr,
+                                                              const uint64_t* mask_t, const uint64_t* mask_s, uint32_t first,
+                                                              uint32_t tile_elems, uint32_t shift, uint32_t bits,
+                                                              uint32_t ntiles, uint32_t* counts) {
+    __shared__ uint32_t h[256];
+    const uint32_t R = 1u << bits, mask = R - 1u;
+    const uint32_t n_eff = count_ptr ? min(n, (uint32_t)*count_ptr) : n;
+    for (uint32_t d = threadIdx.x; d < R; d += kThreads) h[d] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * tile_elems;
+    for (uint32_t k = threadIdx.x; k < tile_elems; k += kThreads) {
+        const uint32_t pos = base + k;
+        bool valid = pos < n_eff;
+        if (valid && first) valid = mask_bit(mask_t, pos) && mask_bit(mask_s, pos);
+        if (valid) atomicAdd(&h[(uint32_t)(keys[pos] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (uint32_t d = threadIdx.x; d < R; d += kThreads) counts[(size_t)d * ntiles + blockIdx.x] = h[d];
+}
+
 struct BatchOut {
     uint32_t layer, texture, first_instance, count;
 };
@@ -484,9 +585,9 @@ __global__ void __launch_bounds__(1024) build_batches_kernel(const uint32_t* __r
 // ---- stable tile ranking with decoupled look-back (shared by scatter and emit) ------------------
 
 struct RankShared {
-    uint32_t wcnt[kWarps][256];  // per-warp digit counters, then per-warp exclusive prefixes
-    uint32_t dstart[256];        // first tile slot of each digit
-    uint32_t dbase[256];         // destination of digit d's slot s is dbase[d] + s
+    uint32_t wcnt[kWarps * 256];  // [warp][R] per-warp digit counters, then per-warp exclusive prefixes
+    uint32_t dstart[256];         // first tile slot of each digit
+    uint32_t dbase[256];          // destination of digit d's slot s is dbase[d] + s
     uint32_t wsum[kWarps];
     uint32_t tile;
     uint32_t tile_count;
@@ -500,20 +601,24 @@ struct PassParams {
     const uint32_t* gbase;   // exclusive scan of this pass's digit histogram
     uint32_t* status;        // [tiles][1 << bits] look-back words, zeroed per frame
     uint32_t* tile_counter;  // zeroed per frame
+    const uint32_t* tile_off;  // optional [1 << bits][ntiles]: first output position of each (digit, tile),
+                               // precomputed from per-tile counts; replaces the look-back
+    uint32_t ntiles;           // tiles of this pass (row length of tile_off)
 };
 
 // Ranks ITEMS digits per thread (warp-striped order: item k of lane l in warp w is element
-// w*ITEMS*32 + k*32 + l of the tile) into stable tile slots, publishes the tile's digit counts,
-// looks back for the tile's global digit offsets and leaves dbase[] ready. Invalid items
-// (kInvalidDigit) get no slot.
+// w*ITEMS*32 + k*32 + l of the tile) into stable tile slots and leaves dbase[] ready: from the
+// precomputed tile offsets when the pass has them, else by publishing the tile's digit counts
+// and looking back over the preceding tiles (decoupled look-back). Invalid items (kInvalidDigit)
+// get no slot. The caller must __syncthreads() before calling it again.
 template <int ITEMS>
-__device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, const uint32_t (&digit)[ITEMS],
-                                          uint32_t (&slot)[ITEMS]) {
+__device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, const uint32_t tile,
+                                          const uint32_t (&digit)[ITEMS], uint32_t (&slot)[ITEMS]) {
     const uint32_t R = 1u << pp.bits;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t k = threadIdx.x; k < kWarps * 256; k += kThreads) (&rs.wcnt[0][0])[k] = 0;
+    for (uint32_t k = threadIdx.x; k < kWarps * R; k += kThreads) rs.wcnt[k] = 0;
     __syncthreads();
-    uint32_t* wc = rs.wcnt[warp];
+    uint32_t* wc = rs.wcnt + warp * R;
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -535,14 +640,15 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
     if (threadIdx.x < R) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = rs.wcnt[w][threadIdx.x];
-            rs.wcnt[w][threadIdx.x] = total;
+            const uint32_t c = rs.wcnt[w * R + threadIdx.x];
+            rs.wcnt[w * R + threadIdx.x] = total;
             total += c;
         }
     }
+    const bool lookback = pp.tile_off == nullptr;
     // publish the local count as early as possible
-    uint32_t* st = pp.status + (size_t)rs.tile * R + threadIdx.x;
-    if (threadIdx.x < R) st_relaxed_u32(st, (rs.tile == 0 ? kFlagIncl : kFlagLocal) | total);
+    uint32_t* st = pp.status + (size_t)tile * R + threadIdx.x;
+    if (lookback && threadIdx.x < R) st_relaxed_u32(st, (tile == 0 ? kFlagIncl : kFlagLocal) | total);
     // block exclusive scan of the totals -> dstart
     uint32_t x = total;
 #pragma unroll
@@ -560,25 +666,29 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
     if (threadIdx.x == kThreads - 1) rs.tile_count = x + add;
     if (threadIdx.x < R) {
         rs.dstart[threadIdx.x] = dstart;
-        uint32_t excl = 0;
-        if (rs.tile > 0) {
-            for (int t = (int)rs.tile - 1; t >= 0; --t) {
-                uint32_t v;
-                do {
-                    v = ld_relaxed_u32(pp.status + (size_t)t * R + threadIdx.x);
-                } while ((v >> 30) == 0u);
-                excl += v & kCountMask;
-                if ((v >> 30) == 2u) break;
+        if (lookback) {
+            uint32_t excl = 0;
+            if (tile > 0) {
+                for (int t = (int)tile - 1; t >= 0; --t) {
+                    uint32_t v;
+                    do {
+                        v = ld_relaxed_u32(pp.status + (size_t)t * R + threadIdx.x);
+                    } while ((v >> 30) == 0u);
+                    excl += v & kCountMask;
+                    if ((v >> 30) == 2u) break;
+                }
+                st_relaxed_u32(st, kFlagIncl | (excl + total));
             }
-            st_relaxed_u32(st, kFlagIncl | (excl + total));
+            rs.dbase[threadIdx.x] = pp.gbase[threadIdx.x] + excl - dstart;
+        } else {
+            rs.dbase[threadIdx.x] = __ldg(pp.tile_off + (size_t)threadIdx.x * pp.ntiles + tile) - dstart;
         }
-        rs.dbase[threadIdx.x] = pp.gbase[threadIdx.x] + excl - dstart;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = digit[k];
-        if (d != kInvalidDigit) slot[k] += rs.dstart[d] + rs.wcnt[warp][d];
+        if (d != kInvalidDigit) slot[k] += rs.dstart[d] + rs.wcnt[warp * R + d];
     }
 }
 
@@ -629,7 +739,7 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const ScatterPa
         }
         digit[k] = valid ? ((uint32_t)(key[k] >> sp.pass.shift) & mask) : kInvalidDigit;
     }
-    rank_tile<ITEMS>(rs, sp.pass, digit, slot);
+    rank_tile<ITEMS>(rs, sp.pass, rs.tile, digit, slot);
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         if (digit[k] != kInvalidDigit) {
@@ -673,9 +783,57 @@ struct EmitParams {
     uint32_t staged;         // stage outputs through shared memory for full-line stores
 };
 
-constexpr int kEmitItems = 8;
-constexpr int kStageWords = 36;  // 144 B per item: 80 B instance + 64 B vertices; 36-word stride is
-                                 // conflict-free for 128-bit shared accesses of a quarter warp
+constexpr int kEmitItems = 2;
+constexpr uint32_t kEmitTile = kThreads * kEmitItems;  // 512 entities per tile
+constexpr int kStageF4 = 5;  // per-lane staging slot: 80 B (one instance, or 64 B of vertices)
+
+// Dynamic shared memory of emit_kernel: ~101 KB, two persistent CTAs per SM.
+struct EmitShared {
+    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's
+    RankShared rs;
+    uint32_t s_dst[kEmitTile];          // output position per sorted tile slot
+    uint32_t s_ent[kEmitTile];          // entity id per sorted tile slot
+    uint16_t s_li[kEmitTile];           // tile-local item index per sorted tile slot
+    float4 stage[kWarps][32 * kStageF4];  // per-warp staging for full-line stores
+    unsigned long long mbar[2];         // completion barriers of the bulk copies, one per row buffer
+    uint32_t s_tile[2];                 // tile id held by each row buffer
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map): size and both addresses multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 __device__ __forceinline__ void make_outputs(const Affine& w, float sw, float shh, uint32_t tl, InstanceOut& inst,
                                              float4 (&vtx)[4]) {
@@ -696,132 +854,231 @@ __device__ __forceinline__ void make_outputs(const Affine& w, float sw, float sh
     }
 }
 
+// Final radix pass fused with compose + emit. Persistent CTAs (two per SM) claim 512-position
+// tiles in order from an atomic counter:
+//   1. the tile's rows come into shared memory asynchronously, so no register holds a row while
+//      the tile is ranked: when the pass reads positions in entity order (single-pass plans) the
+//      NEXT tile's rows are prefetched by TMA bulk copies while this tile is processed; otherwise
+//      every row is gathered with cp.async while the tile is ranked;
+//   2. stable rank of the tile's digits -> final output position per item, from precomputed
+//      per-tile offsets (first pass of a flat scene) or by decoupled look-back;
+//   3. warps walk the tile in sorted order (consecutive slots of a digit are consecutive output
+//      positions), compose from shared memory, stage 32 results and write whole 128-byte lines.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) emit_kernel(const EmitParams<KeyT> ep) {
+__global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT> ep) {
     constexpr int ITEMS = kEmitItems;
-    constexpr uint32_t TILE = kThreads * ITEMS;
-    __shared__ RankShared rs;
-    __shared__ uint32_t s_idx[TILE];
-    __shared__ uint32_t s_dst[TILE];
-    extern __shared__ float4 s_stage[];  // staged mode: kWarps * 32 * 144 B
-    claim_tile(rs, ep.pass);
+    constexpr uint32_t TILE = kEmitTile;
+    extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    EmitShared& sm = *reinterpret_cast<EmitShared*>(emit_smem_raw);
+    RankShared& rs = sm.rs;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile_base = rs.tile * TILE;
-    const uint32_t mask = (1u << ep.pass.bits) - 1u;
-    uint32_t idx[ITEMS], digit[ITEMS], slot[ITEMS];
+    const bool in_order = ep.idx_in == nullptr;  // positions are entity ids: contiguous rows
+    const bool from_world = ep.world != nullptr;
     const uint32_t n_eff = ep.pass.count_ptr ? min(ep.pass.n, (uint32_t)*ep.pass.count_ptr) : ep.pass.n;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const uint32_t pos = tile_base + warp * (ITEMS * 32) + k * 32 + lane;
-        bool valid = pos < n_eff;
-        if (valid && ep.idx_in == nullptr) valid = mask_bit(ep.mask_t, pos) && mask_bit(ep.mask_s, pos);
-        idx[k] = pos;
-        uint64_t sk = 0;
-        if (valid) {
-            if (ep.keys_in != nullptr) {
-                sk = (uint64_t)ep.keys_in[pos];
-                if (ep.idx_in != nullptr) idx[k] = ep.idx_in[pos];
-            } else if (ep.world != nullptr) {
-                const float4* wr = reinterpret_cast<const float4*>(ep.world + pos);
-                sk = pext_runs(world_key(wr[2], wr[3]), ep.plan.pext);
+    const uint32_t ntiles = (ep.pass.n + TILE - 1) / TILE;
+    // shared-memory row addressing: sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]
+    const bool split = in_order && !from_world && ep.rows.stride == 2;
+    const uint32_t sstride = split ? 2u : 4u;
+    const uint32_t boff = split ? 2u * TILE : 2u;
+    const uint32_t mask = (1u << ep.pass.bits) - 1u;
+
+    // thread 0 claims tiles and, for in-order passes, starts their bulk copies
+    auto claim_and_fetch = [&](uint32_t buf) {
+        const uint32_t tile = atomicAdd(ep.pass.tile_counter, 1u);
+        sm.s_tile[buf] = tile;
+        if (in_order && tile < ntiles) {
+            const uint32_t base = tile * TILE;
+            const uint32_t cnt = min(TILE, n_eff - base);
+            float4* dst = sm.rows[buf];
+            mbar_expect_tx(&sm.mbar[buf], cnt * 64u);
+            if (from_world) {
+                bulk_g2s(dst, ep.world + base, cnt * 64u, &sm.mbar[buf]);
+            } else if (split) {
+                bulk_g2s(dst, ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+                bulk_g2s(dst + 2 * TILE, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
             } else {
-                const size_t o = (size_t)pos * ep.rows.stride;
-                sk = pext_runs(flat_key(ep.rows, pos, ep.rows.a[o], ep.rows.a[o + 1]), ep.plan.pext);
+                bulk_g2s(dst, ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
             }
         }
-        digit[k] = valid ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
-    }
-    rank_tile<ITEMS>(rs, ep.pass, digit, slot);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (digit[k] != kInvalidDigit) {
-            s_idx[slot[k]] = idx[k];
-            s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k];
-        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        claim_and_fetch(0);
     }
     __syncthreads();
-    const uint32_t cnt = rs.tile_count;
-    // Each warp takes 32 consecutive tile slots per step: consecutive slots of one digit are
-    // consecutive output positions, so a warp's stores cover whole 128-byte lines.
-    float* stage = reinterpret_cast<float*>(s_stage) + warp * (32 * kStageWords);
-    for (uint32_t s0 = warp * 32; s0 < cnt; s0 += kThreads) {
-        const uint32_t s = s0 + lane;
-        const bool live = s < cnt;
-        uint32_t e = 0, dst = 0;
-        InstanceOut inst;
-        float4 vtx[4];
-        if (live) {
-            e = s_idx[s];
-            dst = s_dst[s];
-            Affine w;
-            float sw, shh;
-            uint32_t tl;
-            if (ep.world != nullptr) {
-                const float4* wr = reinterpret_cast<const float4*>(ep.world + e);
-                w.r0 = ld_nc_f4(wr);
-                w.r1 = ld_nc_f4(wr + 1);
-                w.r2 = ld_nc_f4(wr + 2);
-                const float4 sv = ld_nc_f4(wr + 3);
-                sw = sv.x;
-                shh = sv.y;
-                tl = __float_as_uint(sv.z);
-            } else {
-                const Row r = load_row(ep.rows, e);
-                w = compose_local(r);
-                sw = r.b1.y;
-                shh = r.b1.z;
-                tl = __float_as_uint(r.a1.w);
+    uint32_t cur = 0, parity0 = 0, parity1 = 0;
+    for (;;) {
+        const uint32_t tile = sm.s_tile[cur];
+        if (tile >= ntiles) break;
+        if (threadIdx.x == 0) claim_and_fetch(cur ^ 1u);  // buffer cur^1 was released by the barrier below
+        const float4* rows = sm.rows[cur];
+        const uint32_t tile_base = tile * TILE;
+        uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS];
+        bool valid[ITEMS];
+        KeyT key_in[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+            const uint32_t pos = tile_base + li;
+            valid[k] = pos < n_eff;
+            ent[k] = pos;
+            key_in[k] = 0;
+            if (in_order) {
+                if (valid[k]) valid[k] = mask_bit(ep.mask_t, pos) && mask_bit(ep.mask_s, pos);
+            } else if (valid[k]) {
+                key_in[k] = ep.keys_in[pos];
+                ent[k] = ep.idx_in[pos];
+                // gather this entity's row into the item's shared-memory slot
+                float4* d = sm.rows[cur] + (size_t)li * 4;
+                if (from_world) {
+                    const float4* src = reinterpret_cast<const float4*>(ep.world + ent[k]);
+                    cp_async16(d, src);
+                    cp_async16(d + 1, src + 1);
+                    cp_async16(d + 2, src + 2);
+                    cp_async16(d + 3, src + 3);
+                } else {
+                    const size_t o = (size_t)ent[k] * ep.rows.stride;
+                    cp_async16(d, ep.rows.a + o);
+                    cp_async16(d + 1, ep.rows.a + o + 1);
+                    cp_async16(d + 2, ep.rows.b + o);
+                    cp_async16(d + 3, ep.rows.b + o + 1);
+                }
             }
-            make_outputs(w, sw, shh, tl, inst, vtx);
-            ep.order[dst] = e + ep.global_first;
-            if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
         }
-        if (!ep.staged) {
-            if (live) {
-                float4* ip = ep.instances + (size_t)dst * 5;
-                st_cs_f4(ip, inst.c0);
-                st_cs_f4(ip + 1, inst.c1);
-                st_cs_f4(ip + 2, inst.c2);
-                st_cs_f4(ip + 3, inst.c3);
-                st_cs_f4(ip + 4, inst.s);
-                float4* vp = ep.vertices + (size_t)dst * 4;
-                st_cs_f4(vp, vtx[0]);
-                st_cs_f4(vp + 1, vtx[1]);
-                st_cs_f4(vp + 2, vtx[2]);
-                st_cs_f4(vp + 3, vtx[3]);
+        if (in_order) {
+            mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
+            if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+                uint64_t sk = 0;
+                if (valid[k]) {
+                    if (ep.keys_in != nullptr) {
+                        sk = (uint64_t)ep.keys_in[tile_base + li];
+                    } else if (from_world) {
+                        sk = pext_runs(world_key(rows[li * 4 + 2], rows[li * 4 + 3]), ep.plan.pext);
+                    } else {
+                        const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
+                        float z;
+                        if (is_planar(a1)) {
+                            z = planar_z(a0, a1);
+                        } else {
+                            Row r;
+                            r.a0 = a0;
+                            r.a1 = a1;
+                            r.b0 = rows[boff + li * sstride];
+                            r.b1 = rows[boff + li * sstride + 1];
+                            z = local_z(r);
+                        }
+                        const uint32_t tl = __float_as_uint(a1.w);
+                        sk = pext_runs(sort_key(tl >> 16, tl & 0xFFFFu, z), ep.plan.pext);
+                    }
+                }
+                digit[k] = valid[k] ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
             }
         } else {
-            // stage this warp's 32 items, then write them out 16 B per lane, line by line
-            float4* my = reinterpret_cast<float4*>(stage + lane * kStageWords);
-            if (live) {
-                my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
-                my[5] = vtx[0]; my[6] = vtx[1]; my[7] = vtx[2]; my[8] = vtx[3];
-            }
-            const uint32_t nlive = min(32u, cnt - s0);
-            __syncwarp();
-            // destinations of the 32 items live in the lanes; fetch per chunk by shuffle
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const uint32_t q = j * 32 + lane;
-                const uint32_t item = q / 5, part = q - item * 5;
-                const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
-                if (item < nlive) {
-                    const float4 v = reinterpret_cast<const float4*>(stage + item * kStageWords)[part];
-                    st_cs_f4(ep.instances + (size_t)d * 5 + part, v);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t q = j * 32 + lane;
-                const uint32_t item = q >> 2, part = q & 3u;
-                const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
-                if (item < nlive) {
-                    const float4 v = reinterpret_cast<const float4*>(stage + item * kStageWords)[5 + part];
-                    st_cs_f4(ep.vertices + (size_t)d * 4 + part, v);
-                }
-            }
-            __syncwarp();
+            for (int k = 0; k < ITEMS; ++k)
+                digit[k] = valid[k] ? ((uint32_t)(key_in[k] >> ep.pass.shift) & mask) : kInvalidDigit;
         }
+        rank_tile<ITEMS>(rs, ep.pass, tile, digit, slot);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (digit[k] != kInvalidDigit) {
+                sm.s_li[slot[k]] = (uint16_t)(warp * (ITEMS * 32) + k * 32 + lane);
+                sm.s_ent[slot[k]] = ent[k];
+                sm.s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k];
+            }
+        }
+        if (!in_order) cp_async_wait_all();
+        __syncthreads();
+        const uint32_t cnt = rs.tile_count;
+        float4* stage = sm.stage[warp];
+        for (uint32_t s0 = warp * 32; s0 < cnt; s0 += kThreads) {
+            const uint32_t s = s0 + lane;
+            const bool live = s < cnt;
+            uint32_t dst = 0;
+            InstanceOut inst;
+            float4 vtx[4];
+            if (live) {
+                const uint32_t li = sm.s_li[s];
+                const uint32_t e = sm.s_ent[s];
+                dst = sm.s_dst[s];
+                Affine w;
+                float sw, shh;
+                uint32_t tl;
+                if (from_world) {
+                    w.r0 = rows[li * 4];
+                    w.r1 = rows[li * 4 + 1];
+                    w.r2 = rows[li * 4 + 2];
+                    const float4 sv = rows[li * 4 + 3];
+                    sw = sv.x;
+                    shh = sv.y;
+                    tl = __float_as_uint(sv.z);
+                } else {
+                    Row r;
+                    r.a0 = rows[li * sstride];
+                    r.a1 = rows[li * sstride + 1];
+                    r.b0 = rows[boff + li * sstride];
+                    r.b1 = rows[boff + li * sstride + 1];
+                    w = compose_local(r);
+                    sw = r.b1.y;
+                    shh = r.b1.z;
+                    tl = __float_as_uint(r.a1.w);
+                }
+                make_outputs(w, sw, shh, tl, inst, vtx);
+                ep.order[dst] = e + ep.global_first;
+                if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
+            }
+            if (!ep.staged) {
+                if (live) {
+                    float4* ip = ep.instances + (size_t)dst * 5;
+                    st_cs_f4(ip, inst.c0);
+                    st_cs_f4(ip + 1, inst.c1);
+                    st_cs_f4(ip + 2, inst.c2);
+                    st_cs_f4(ip + 3, inst.c3);
+                    st_cs_f4(ip + 4, inst.s);
+                    float4* vp = ep.vertices + (size_t)dst * 4;
+                    st_cs_f4(vp, vtx[0]);
+                    st_cs_f4(vp + 1, vtx[1]);
+                    st_cs_f4(vp + 2, vtx[2]);
+                    st_cs_f4(vp + 3, vtx[3]);
+                }
+            } else {
+                const uint32_t nlive = min(32u, cnt - s0);
+                // instances: 32 x 80 B staged lane-major (20-word stride: conflict-free 128-bit
+                // stores), then streamed out as 160 consecutive 16-byte chunks
+                float4* my = stage + lane * kStageF4;
+                if (live) {
+                    my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const uint32_t q = j * 32 + lane;
+                    const uint32_t item = q / 5, part = q - item * 5;
+                    const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+                    if (item < nlive) st_cs_f4(ep.instances + (size_t)d * 5 + part, stage[q]);
+                }
+                __syncwarp();
+                // vertices: 32 x 64 B in the same buffer (same 20-word stride)
+                if (live) {
+                    my[0] = vtx[0]; my[1] = vtx[1]; my[2] = vtx[2]; my[3] = vtx[3];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t q = j * 32 + lane;
+                    const uint32_t item = q >> 2, part = q & 3u;
+                    const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+                    if (item < nlive) st_cs_f4(ep.vertices + (size_t)d * 4 + part, stage[item * kStageF4 + part]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();  // releases rows[cur], the rank scratch and s_tile[cur] for reuse
+        cur ^= 1u;
     }
 }
 

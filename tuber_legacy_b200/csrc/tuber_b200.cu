@@ -91,6 +91,7 @@ struct tb_ctx {
     uint32_t force_path = TB_PATH_NONE;
     int digit_bits = kMaxDigitBits;
     int staged_emit = 1;
+    int tile_offsets = 1;
     int lt_limit = (int)kMaxLtBits;
 
     // hierarchy
@@ -267,13 +268,17 @@ tb_status flush_integrate(tb_ctx* c) {
 // Scratch layout for one frame under a plan.
 struct ScratchLayout {
     size_t lt_off = 0, lt_words = 0;
-    size_t status_off[kMaxPasses];
     uint32_t tiles[kMaxPasses];
-    size_t total_words = 0;
+    size_t status_off[kMaxPasses];   // look-back words (only with tile_offsets == 0)
+    size_t counts_off[kMaxPasses];   // per-tile digit counts  [R][tiles]  (tile_offsets == 1)
+    size_t offs_off[kMaxPasses];     // per-tile digit offsets [R][tiles]
+    bool tile_offsets = true;
+    size_t total_words = 0, alloc_words = 0;
 };
 
-ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt) {
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets) {
     ScratchLayout L;
+    L.tile_offsets = tile_offsets;
     size_t off = kHdrWords;
     L.lt_off = off;
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
@@ -283,9 +288,16 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt) {
         const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
         L.tiles[p] = div_up(n, tile);
         L.status_off[p] = off;
-        off += (size_t)L.tiles[p] << plan.bits[p];
+        if (!tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
     }
-    L.total_words = off;
+    L.total_words = off;  // everything up to here is zeroed every frame
+    for (uint32_t p = 0; p < plan.npasses; ++p) {
+        L.counts_off[p] = off;
+        if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        L.offs_off[p] = off;
+        if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+    }
+    L.alloc_words = off;
     return L;
 }
 
@@ -388,29 +400,38 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     const uint32_t tile = kThreads * kScatterItems;
     const uint32_t tiles = div_up(n, tile);
     size_t words = kHdrWords;
-    size_t status_off[kMaxPasses];
+    size_t counts_off[kMaxPasses], offs_off[kMaxPasses];
     for (uint32_t p = 0; p < ds.npasses; ++p) {
-        status_off[p] = words;
+        counts_off[p] = words;
+        words += (size_t)tiles << ds.bits[p];
+        offs_off[p] = words;
         words += (size_t)tiles << ds.bits[p];
     }
     s = ensure_scratch(c, words);
     if (s) return s;
-    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (words - kHdrTileCounters) * 4, c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (kHdrWords - kHdrTileCounters) * 4, c->stream));
     uint32_t* hist = c->scratch + kHdrHist;
     TB_LAUNCH(c, "level_key_hist", 0, key_hist_kernel, div_up(n, kThreads), kThreads, 0, d_keys, n, ds, hist);
-    TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, ds.npasses, 256, 0, hist);
     const uint32_t* kin = d_keys;
     const uint32_t* iin = nullptr;
     int cur = 0;
     for (uint32_t p = 0; p < ds.npasses; ++p) {
+        uint32_t* counts = c->scratch + counts_off[p];
+        uint32_t* offs = c->scratch + offs_off[p];
+        TB_LAUNCH(c, "tile_hist", 0, tile_hist_kernel<uint32_t>, tiles, kThreads, 0, kin, n, (const unsigned long long*)nullptr,
+                  (const uint64_t*)nullptr, (const uint64_t*)nullptr, 0u, tile, ds.shift[p], ds.bits[p], tiles, counts);
+        TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(div_up(tiles, 1024), 1u << ds.bits[p]), 1024, 0, counts, tiles,
+                  hist + p * 256, offs);
         ScatterParams<uint32_t> sp{};
         sp.pass.n = n;
         sp.pass.count_ptr = nullptr;
         sp.pass.shift = ds.shift[p];
         sp.pass.bits = ds.bits[p];
-        sp.pass.gbase = hist + p * 256;
-        sp.pass.status = c->scratch + status_off[p];
+        sp.pass.gbase = nullptr;
+        sp.pass.status = nullptr;
         sp.pass.tile_counter = c->scratch + kHdrTileCounters + p;
+        sp.pass.tile_off = offs;
+        sp.pass.ntiles = tiles;
         sp.keys_in = kin;
         sp.idx_in = iin;
         sp.mask_t = nullptr;
@@ -576,10 +597,14 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     p.hist = c->scratch + kHdrHist;
     if (have_plan) {
         p.plan = c->plan;
-        p.write_keys = c->plan.npasses > 1;
+        p.write_keys = c->plan.npasses > 1 || fm.hier;
         p.keys_out = c->keys[0];
         p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
         p.lt_hist = c->scratch + L->lt_off;
+        if (L->tile_offsets && !fm.hier && c->plan.npasses == 1) {
+            p.tile_counts = c->scratch + L->counts_off[0];
+            p.emit_tiles = L->tiles[0];
+        }
     }
     const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 32 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
     if (!fm.hier) {
@@ -615,62 +640,74 @@ tb_status read_header(tb_ctx* c) {
 }
 
 template <typename KeyT>
-tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, float4* d_inst, float4* d_vtx,
-                            uint32_t* d_order) {
+tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, bool prepare_made_counts,
+                            float4* d_inst, float4* d_vtx, uint32_t* d_order) {
     const uint32_t n = (uint32_t)c->n;
     const FramePlan& plan = c->plan;
     uint32_t* hist = c->scratch + kHdrHist;
-    const KeyT* kin = (const KeyT*)c->keys[0];
+    const unsigned long long* d_count = reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2;
+    const bool have_keys = plan.npasses > 1 || fm.hier;  // pass A wrote short keys (entity order)
+    const KeyT* kin = have_keys ? (const KeyT*)c->keys[0] : nullptr;
     const uint32_t* iin = nullptr;
-    uint32_t count_in = n;  // positions in the first pass, renderables afterwards (unknown on host: use n)
+    const uint64_t kb = sizeof(KeyT);
     int cur = 1;
-    for (uint32_t p = 0; p + 1 < plan.npasses; ++p) {
-        ScatterParams<KeyT> sp{};
-        sp.pass.n = count_in;
-        sp.pass.count_ptr = iin ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2 : nullptr;
-        sp.pass.shift = plan.shift[p];
-        sp.pass.bits = plan.bits[p];
-        sp.pass.gbase = hist + p * 256;
-        sp.pass.status = c->scratch + L.status_off[p];
-        sp.pass.tile_counter = c->scratch + kHdrTileCounters + p;
-        sp.keys_in = kin;
-        sp.idx_in = iin;
-        sp.mask_t = mask_or_null(c, TB_TRANSFORM);
-        sp.mask_s = mask_or_null(c, TB_SPRITE);
-        sp.keys_out = (KeyT*)c->keys[cur];
-        sp.idx_out = c->idx[cur];
-        const uint64_t kb = sizeof(KeyT);
-        TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>, L.tiles[p],
-                  kThreads, 0, sp);
-        kin = (const KeyT*)c->keys[cur];
-        iin = c->idx[cur];
-        cur ^= 1;
+    for (uint32_t p = 0; p < plan.npasses; ++p) {
+        const bool last = p + 1 == plan.npasses;
+        const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
+        PassParams pp{};
+        pp.n = n;  // passes after the first only hold the renderables: bounded by the device-side count
+        pp.count_ptr = iin ? d_count : nullptr;
+        pp.shift = plan.shift[p];
+        pp.bits = plan.bits[p];
+        pp.gbase = hist + p * 256;
+        pp.status = c->scratch + L.status_off[p];
+        pp.tile_counter = c->scratch + kHdrTileCounters + p;
+        pp.ntiles = L.tiles[p];
+        if (L.tile_offsets) {
+            uint32_t* counts = c->scratch + L.counts_off[p];
+            uint32_t* offs = c->scratch + L.offs_off[p];
+            if (!(p == 0 && prepare_made_counts))
+                TB_LAUNCH(c, "tile_hist", (uint64_t)n * kb, tile_hist_kernel<KeyT>, L.tiles[p], kThreads, 0, kin, n, pp.count_ptr,
+                          mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_SPRITE), iin ? 0u : 1u, tile, pp.shift, pp.bits,
+                          L.tiles[p], counts);
+            TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(div_up(L.tiles[p], 1024), 1u << pp.bits), 1024, 0, counts,
+                      L.tiles[p], hist + p * 256, offs);
+            pp.tile_off = offs;
+        }
+        if (!last) {
+            ScatterParams<KeyT> sp{};
+            sp.pass = pp;
+            sp.keys_in = kin;
+            sp.idx_in = iin;
+            sp.mask_t = mask_or_null(c, TB_TRANSFORM);
+            sp.mask_s = mask_or_null(c, TB_SPRITE);
+            sp.keys_out = (KeyT*)c->keys[cur];
+            sp.idx_out = c->idx[cur];
+            TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>, L.tiles[p],
+                      kThreads, 0, sp);
+            kin = (const KeyT*)c->keys[cur];
+            iin = c->idx[cur];
+            cur ^= 1;
+        } else {
+            EmitParams<KeyT> ep{};
+            ep.pass = pp;
+            ep.keys_in = kin;
+            ep.idx_in = iin;
+            ep.mask_t = mask_or_null(c, TB_TRANSFORM);
+            ep.mask_s = mask_or_null(c, TB_SPRITE);
+            ep.rows = c->rows;
+            ep.world = fm.hier ? c->world : nullptr;
+            ep.plan = plan;
+            ep.instances = d_inst;
+            ep.vertices = d_vtx;
+            ep.order = d_order;
+            ep.texlayer = fm.lt_generic ? c->texlayer : nullptr;
+            ep.global_first = (uint32_t)c->global_first;
+            ep.staged = c->staged_emit;
+            TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
+                      std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared), ep);
+        }
     }
-    const uint32_t p = plan.npasses - 1;
-    EmitParams<KeyT> ep{};
-    ep.pass.n = count_in;
-    ep.pass.count_ptr = iin ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2 : nullptr;
-    ep.pass.shift = plan.shift[p];
-    ep.pass.bits = plan.bits[p];
-    ep.pass.gbase = hist + p * 256;
-    ep.pass.status = c->scratch + L.status_off[p];
-    ep.pass.tile_counter = c->scratch + kHdrTileCounters + p;
-    ep.keys_in = plan.npasses > 1 ? kin : nullptr;
-    ep.idx_in = iin;
-    ep.mask_t = mask_or_null(c, TB_TRANSFORM);
-    ep.mask_s = mask_or_null(c, TB_SPRITE);
-    ep.rows = c->rows;
-    ep.world = fm.hier ? c->world : nullptr;
-    ep.plan = plan;
-    ep.instances = d_inst;
-    ep.vertices = d_vtx;
-    ep.order = d_order;
-    ep.texlayer = fm.lt_generic ? c->texlayer : nullptr;
-    ep.global_first = (uint32_t)c->global_first;
-    ep.staged = c->staged_emit;
-    const size_t smem = c->staged_emit ? (size_t)kWarps * 32 * kStageWords * 4 : 0;
-    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (iin ? sizeof(KeyT) + 4 : 0)), emit_kernel<KeyT>, L.tiles[p],
-              kThreads, smem, ep);
     return TB_OK;
 }
 
@@ -745,8 +782,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->rows.a = c->rows_mem;
     c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * max_entities;
     c->rows.stride = c->interleaved ? 4 : 2;
-    cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 32 * kStageWords * 4);
-    cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 32 * kStageWords * 4);
+    cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
+    cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         tb_ctx_destroy(c);
         return TB_ERR_CUDA;
@@ -814,6 +851,8 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->rows.stride = c->interleaved ? 4 : 2;
     } else if (k == "staged_emit") {
         c->staged_emit = value != 0;
+    } else if (k == "tile_offsets") {
+        c->tile_offsets = value != 0;
     } else if (k == "digit_bits") {
         if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
         c->digit_bits = (int)value;
@@ -1151,9 +1190,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
-        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist);
-        if ((s = ensure_scratch(c, L.total_words))) return s;
-        if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0);
+        if ((s = ensure_scratch(c, L.alloc_words))) return s;
+        if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        const bool prepare_made_counts = L.tile_offsets && !fm.hier && plan.npasses == 1;
         if (fm.lt_generic) {
             size_t cap = c->texlayer ? c->texlayer_cap : 0;
             if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
@@ -1170,9 +1210,9 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
                       (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
         }
-        TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
-        if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, d_inst, d_vtx, d_order);
-        else s = run_sort_and_emit<uint32_t>(c, fm, L, d_inst, d_vtx, d_order);
+        if (!L.tile_offsets) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
+        if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+        else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
         if ((s = read_header(c))) return s;
         count = c->h_hdr[2];
