@@ -606,18 +606,24 @@ struct PassParams {
     uint32_t ntiles;           // tiles of this pass (row length of tile_off)
 };
 
+// Zeroes the per-warp digit counters of the next rank_tile call; a __syncthreads() must
+// separate it from that call.
+__device__ __forceinline__ void rank_reset(RankShared& rs, uint32_t bits) {
+    const uint32_t R = 1u << bits;
+    for (uint32_t k = threadIdx.x; k < kWarps * R; k += kThreads) rs.wcnt[k] = 0;
+}
+
 // Ranks ITEMS digits per thread (warp-striped order: item k of lane l in warp w is element
 // w*ITEMS*32 + k*32 + l of the tile) into stable tile slots and leaves dbase[] ready: from the
 // precomputed tile offsets when the pass has them, else by publishing the tile's digit counts
 // and looking back over the preceding tiles (decoupled look-back). Invalid items (kInvalidDigit)
-// get no slot. The caller must __syncthreads() before calling it again.
+// get no slot. Needs rank_reset() + __syncthreads() before, and a __syncthreads() before the
+// next rank_reset().
 template <int ITEMS>
 __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, const uint32_t tile,
                                           const uint32_t (&digit)[ITEMS], uint32_t (&slot)[ITEMS]) {
     const uint32_t R = 1u << pp.bits;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t k = threadIdx.x; k < kWarps * R; k += kThreads) rs.wcnt[k] = 0;
-    __syncthreads();
     uint32_t* wc = rs.wcnt + warp * R;
     const uint32_t lt = lanemask_lt();
 #pragma unroll
@@ -649,21 +655,25 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
     // publish the local count as early as possible
     uint32_t* st = pp.status + (size_t)tile * R + threadIdx.x;
     if (lookback && threadIdx.x < R) st_relaxed_u32(st, (tile == 0 ? kFlagIncl : kFlagLocal) | total);
-    // block exclusive scan of the totals -> dstart
+    // block exclusive scan of the totals -> dstart (all digits live in warp 0 when R <= 32)
     uint32_t x = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= (uint32_t)o) x += y;
     }
-    if (lane == 31) rs.wsum[warp] = x;
-    __syncthreads();
     uint32_t add = 0;
+    if (R > 32) {
+        if (lane == 31) rs.wsum[warp] = x;
+        __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w)
-        if ((uint32_t)w < warp) add += rs.wsum[w];
+        for (int w = 0; w < kWarps; ++w)
+            if ((uint32_t)w < warp) add += rs.wsum[w];
+        if (threadIdx.x == kThreads - 1) rs.tile_count = x + add;
+    } else if (threadIdx.x == 31) {
+        rs.tile_count = x;
+    }
     const uint32_t dstart = x + add - total;
-    if (threadIdx.x == kThreads - 1) rs.tile_count = x + add;
     if (threadIdx.x < R) {
         rs.dstart[threadIdx.x] = dstart;
         if (lookback) {
@@ -694,6 +704,7 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
 
 __device__ __forceinline__ void claim_tile(RankShared& rs, const PassParams& pp) {
     if (threadIdx.x == 0) rs.tile = atomicAdd(pp.tile_counter, 1u);
+    rank_reset(rs, pp.bits);
     __syncthreads();
 }
 
@@ -787,17 +798,25 @@ constexpr int kEmitItems = 2;
 constexpr uint32_t kEmitTile = kThreads * kEmitItems;  // 512 entities per tile
 constexpr int kStageF4 = 5;  // per-lane staging slot: 80 B (one instance, or 64 B of vertices)
 
-// Dynamic shared memory of emit_kernel: ~101 KB, two persistent CTAs per SM.
+// Dynamic shared memory of emit_kernel: ~108 KB, two persistent CTAs per SM.
 struct EmitShared {
-    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's
+    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's,
+                                        // 16-byte chunks XOR-swizzled (row_slot) against bank conflicts
+    unsigned long long keys[2][kEmitTile];  // short keys of in-order passes that read them (hierarchy)
+    unsigned long long masks[2][2][8];  // presence words (Transform, Sprite) of the tile
     RankShared rs;
     uint32_t s_dst[kEmitTile];          // output position per sorted tile slot
     uint32_t s_ent[kEmitTile];          // entity id per sorted tile slot
     uint16_t s_li[kEmitTile];           // tile-local item index per sorted tile slot
     float4 stage[kWarps][32 * kStageF4];  // per-warp staging for full-line stores
-    unsigned long long mbar[2];         // completion barriers of the bulk copies, one per row buffer
-    uint32_t s_tile[2];                 // tile id held by each row buffer
+    unsigned long long mbar[2];         // completion barriers of the TMA bulk copies, one per buffer
+    uint32_t s_tile[3];                 // ring of claimed tile ids
 };
+
+// 16-byte chunk c (0..3) of tile-local row li lives at rows[row_slot(li, c)]: the 128-byte
+// swizzle (chunk index XOR line index), so both consecutive rows and the scattered rows of one
+// sort bucket spread over all eight 16-byte bank groups.
+__device__ __forceinline__ uint32_t row_slot(uint32_t li, uint32_t c) { return ((li << 2) | c) ^ ((li >> 1) & 7u); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -856,12 +875,13 @@ __device__ __forceinline__ void make_outputs(const Affine& w, float sw, float sh
 
 // Final radix pass fused with compose + emit. Persistent CTAs (two per SM) claim 512-position
 // tiles in order from an atomic counter:
-//   1. the tile's rows come into shared memory asynchronously, so no register holds a row while
-//      the tile is ranked: when the pass reads positions in entity order (single-pass plans) the
-//      NEXT tile's rows are prefetched by TMA bulk copies while this tile is processed; otherwise
-//      every row is gathered with cp.async while the tile is ranked;
+//   1. the tile's rows come into shared memory asynchronously (cp.async, 16-byte chunks into a
+//      bank-swizzled layout), so no register holds a row while the tile is ranked: when the pass
+//      reads positions in entity order (single-pass plans) the NEXT tile's rows, presence words
+//      and keys are prefetched while this tile is processed; otherwise every row is gathered
+//      while the tile is ranked;
 //   2. stable rank of the tile's digits -> final output position per item, from precomputed
-//      per-tile offsets (first pass of a flat scene) or by decoupled look-back;
+//      per-tile offsets (reduce-then-scan) or by decoupled look-back;
 //   3. warps walk the tile in sorted order (consecutive slots of a digit are consecutive output
 //      positions), compose from shared memory, stage 32 results and write whole 128-byte lines.
 template <typename KeyT>
@@ -874,92 +894,90 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_order = ep.idx_in == nullptr;  // positions are entity ids: contiguous rows
     const bool from_world = ep.world != nullptr;
+    const bool keys_given = ep.keys_in != nullptr;
     const uint32_t n_eff = ep.pass.count_ptr ? min(ep.pass.n, (uint32_t)*ep.pass.count_ptr) : ep.pass.n;
     const uint32_t ntiles = (ep.pass.n + TILE - 1) / TILE;
-    // shared-memory row addressing: sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]
+    const uint32_t mask = (1u << ep.pass.bits) - 1u;
+
+    // Shared-memory row layouts. In-order passes land rows with TMA bulk copies, i.e. linearly
+    // (sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]); gathered rows
+    // are placed chunk by chunk with cp.async into the bank-swizzled layout (row_slot).
     const bool split = in_order && !from_world && ep.rows.stride == 2;
     const uint32_t sstride = split ? 2u : 4u;
     const uint32_t boff = split ? 2u * TILE : 2u;
-    const uint32_t mask = (1u << ep.pass.bits) - 1u;
-
-    // thread 0 claims tiles and, for in-order passes, starts their bulk copies
-    auto claim_and_fetch = [&](uint32_t buf) {
-        const uint32_t tile = atomicAdd(ep.pass.tile_counter, 1u);
-        sm.s_tile[buf] = tile;
-        if (in_order && tile < ntiles) {
-            const uint32_t base = tile * TILE;
-            const uint32_t cnt = min(TILE, n_eff - base);
-            float4* dst = sm.rows[buf];
-            mbar_expect_tx(&sm.mbar[buf], cnt * 64u);
-            if (from_world) {
-                bulk_g2s(dst, ep.world + base, cnt * 64u, &sm.mbar[buf]);
-            } else if (split) {
-                bulk_g2s(dst, ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
-                bulk_g2s(dst + 2 * TILE, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
-            } else {
-                bulk_g2s(dst, ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
-            }
-        }
+    auto chunk = [&](uint32_t li, uint32_t c) -> uint32_t {
+        if (!in_order) return row_slot(li, c);
+        return (c < 2 ? 0u : boff - 2u) + li * sstride + c;
     };
+
+    // in-order passes: TMA bulk copies of one tile's rows / presence words / keys into buffer `buf`
+    // (issued by one thread, completion counted in bytes on the buffer's mbarrier)
+    auto fetch_tile = [&](uint32_t tile, uint32_t buf) {
+        const uint32_t base = tile * TILE;
+        const uint32_t cnt = min(TILE, n_eff - base);
+        const uint32_t mwords = ((cnt + 127u) >> 7) * 2u;  // presence words, padded to 16 bytes
+        const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
+        const uint32_t mbytes = ((ep.mask_t ? 1u : 0u) + (ep.mask_s ? 1u : 0u)) * mwords * 8u;
+        float4* dst = sm.rows[buf];
+        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + mbytes + kbytes);
+        if (from_world) {
+            bulk_g2s(dst, ep.world + base, cnt * 64u, &sm.mbar[buf]);
+        } else if (split) {
+            bulk_g2s(dst, ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(dst + 2 * TILE, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+        } else {
+            bulk_g2s(dst, ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+        }
+        if (ep.mask_t) bulk_g2s(sm.masks[buf][0], ep.mask_t + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+        if (ep.mask_s) bulk_g2s(sm.masks[buf][1], ep.mask_s + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+        if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+    };
+
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
-        claim_and_fetch(0);
+        const uint32_t t0 = atomicAdd(ep.pass.tile_counter, 1u);
+        sm.s_tile[0] = t0;
+        sm.s_tile[1] = atomicAdd(ep.pass.tile_counter, 1u);
+        if (in_order && t0 < ntiles) fetch_tile(t0, 0);
     }
+    rank_reset(rs, ep.pass.bits);
     __syncthreads();
-    uint32_t cur = 0, parity0 = 0, parity1 = 0;
+    uint32_t cur = 0, ring = 0, parity0 = 0, parity1 = 0;
     for (;;) {
-        const uint32_t tile = sm.s_tile[cur];
+        const uint32_t tile = sm.s_tile[ring];
         if (tile >= ntiles) break;
-        if (threadIdx.x == 0) claim_and_fetch(cur ^ 1u);  // buffer cur^1 was released by the barrier below
+        const uint32_t next = sm.s_tile[ring == 2 ? 0 : ring + 1];
+        if (threadIdx.x == 0) {
+            sm.s_tile[ring == 0 ? 2 : ring - 1] = atomicAdd(ep.pass.tile_counter, 1u);
+            if (in_order && next < ntiles) fetch_tile(next, cur ^ 1u);  // prefetch; buffer freed by the last barrier
+        }
         const float4* rows = sm.rows[cur];
         const uint32_t tile_base = tile * TILE;
         uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS];
         bool valid[ITEMS];
-        KeyT key_in[ITEMS];
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
-            const uint32_t pos = tile_base + li;
-            valid[k] = pos < n_eff;
-            ent[k] = pos;
-            key_in[k] = 0;
-            if (in_order) {
-                if (valid[k]) valid[k] = mask_bit(ep.mask_t, pos) && mask_bit(ep.mask_s, pos);
-            } else if (valid[k]) {
-                key_in[k] = ep.keys_in[pos];
-                ent[k] = ep.idx_in[pos];
-                // gather this entity's row into the item's shared-memory slot
-                float4* d = sm.rows[cur] + (size_t)li * 4;
-                if (from_world) {
-                    const float4* src = reinterpret_cast<const float4*>(ep.world + ent[k]);
-                    cp_async16(d, src);
-                    cp_async16(d + 1, src + 1);
-                    cp_async16(d + 2, src + 2);
-                    cp_async16(d + 3, src + 3);
-                } else {
-                    const size_t o = (size_t)ent[k] * ep.rows.stride;
-                    cp_async16(d, ep.rows.a + o);
-                    cp_async16(d + 1, ep.rows.a + o + 1);
-                    cp_async16(d + 2, ep.rows.b + o);
-                    cp_async16(d + 3, ep.rows.b + o + 1);
-                }
-            }
-        }
         if (in_order) {
             mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
             if (cur) parity1 ^= 1u; else parity0 ^= 1u;
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+                const uint32_t pos = tile_base + li;
+                ent[k] = pos;
+                valid[k] = pos < n_eff;
+                if (valid[k]) {
+                    const bool t_ok = ep.mask_t == nullptr || ((sm.masks[cur][0][li >> 6] >> (li & 63u)) & 1ull);
+                    const bool s_ok = ep.mask_s == nullptr || ((sm.masks[cur][1][li >> 6] >> (li & 63u)) & 1ull);
+                    valid[k] = t_ok && s_ok;
+                }
                 uint64_t sk = 0;
                 if (valid[k]) {
-                    if (ep.keys_in != nullptr) {
-                        sk = (uint64_t)ep.keys_in[tile_base + li];
+                    if (keys_given) {
+                        sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
                     } else if (from_world) {
-                        sk = pext_runs(world_key(rows[li * 4 + 2], rows[li * 4 + 3]), ep.plan.pext);
+                        sk = pext_runs(world_key(rows[chunk(li, 2)], rows[chunk(li, 3)]), ep.plan.pext);
                     } else {
-                        const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
+                        const float4 a0 = rows[chunk(li, 0)], a1 = rows[chunk(li, 1)];
                         float z;
                         if (is_planar(a1)) {
                             z = planar_z(a0, a1);
@@ -967,8 +985,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                             Row r;
                             r.a0 = a0;
                             r.a1 = a1;
-                            r.b0 = rows[boff + li * sstride];
-                            r.b1 = rows[boff + li * sstride + 1];
+                            r.b0 = rows[chunk(li, 2)];
+                            r.b1 = rows[chunk(li, 3)];
                             z = local_z(r);
                         }
                         const uint32_t tl = __float_as_uint(a1.w);
@@ -979,8 +997,33 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k)
-                digit[k] = valid[k] ? ((uint32_t)(key_in[k] >> ep.pass.shift) & mask) : kInvalidDigit;
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+                const uint32_t pos = tile_base + li;
+                valid[k] = pos < n_eff;
+                ent[k] = pos;
+                digit[k] = kInvalidDigit;
+                if (valid[k]) {
+                    const KeyT key = ep.keys_in[pos];
+                    ent[k] = ep.idx_in[pos];
+                    digit[k] = (uint32_t)(key >> ep.pass.shift) & mask;
+                    // gather this entity's row into the item's shared-memory slot
+                    float4* d = sm.rows[cur];
+                    if (from_world) {
+                        const float4* src = reinterpret_cast<const float4*>(ep.world + ent[k]);
+                        cp_async16(d + row_slot(li, 0), src);
+                        cp_async16(d + row_slot(li, 1), src + 1);
+                        cp_async16(d + row_slot(li, 2), src + 2);
+                        cp_async16(d + row_slot(li, 3), src + 3);
+                    } else {
+                        const size_t o = (size_t)ent[k] * ep.rows.stride;
+                        cp_async16(d + row_slot(li, 0), ep.rows.a + o);
+                        cp_async16(d + row_slot(li, 1), ep.rows.a + o + 1);
+                        cp_async16(d + row_slot(li, 2), ep.rows.b + o);
+                        cp_async16(d + row_slot(li, 3), ep.rows.b + o + 1);
+                    }
+                }
+            }
         }
         rank_tile<ITEMS>(rs, ep.pass, tile, digit, slot);
 #pragma unroll
@@ -1009,19 +1052,19 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 float sw, shh;
                 uint32_t tl;
                 if (from_world) {
-                    w.r0 = rows[li * 4];
-                    w.r1 = rows[li * 4 + 1];
-                    w.r2 = rows[li * 4 + 2];
-                    const float4 sv = rows[li * 4 + 3];
+                    w.r0 = rows[chunk(li, 0)];
+                    w.r1 = rows[chunk(li, 1)];
+                    w.r2 = rows[chunk(li, 2)];
+                    const float4 sv = rows[chunk(li, 3)];
                     sw = sv.x;
                     shh = sv.y;
                     tl = __float_as_uint(sv.z);
                 } else {
                     Row r;
-                    r.a0 = rows[li * sstride];
-                    r.a1 = rows[li * sstride + 1];
-                    r.b0 = rows[boff + li * sstride];
-                    r.b1 = rows[boff + li * sstride + 1];
+                    r.a0 = rows[chunk(li, 0)];
+                    r.a1 = rows[chunk(li, 1)];
+                    r.b0 = rows[chunk(li, 2)];
+                    r.b1 = rows[chunk(li, 3)];
                     w = compose_local(r);
                     sw = r.b1.y;
                     shh = r.b1.z;
@@ -1077,8 +1120,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 __syncwarp();
             }
         }
-        __syncthreads();  // releases rows[cur], the rank scratch and s_tile[cur] for reuse
+        rank_reset(rs, ep.pass.bits);
+        __syncthreads();  // releases rows[cur], the rank scratch and the tile ring slot for reuse
         cur ^= 1u;
+        ring = ring == 2 ? 0 : ring + 1;
     }
 }
 

@@ -358,7 +358,8 @@ tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
     }
     c->sort_cap = 0;
     for (int k = 0; k < 2; ++k) {
-        cudaError_t e = cudaMalloc(&c->keys[k], (size_t)n * keybytes);
+        // +16 bytes: the emit kernel prefetches keys in 16-byte chunks
+        cudaError_t e = cudaMalloc(&c->keys[k], (size_t)n * keybytes + 16);
         if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(sort keys)");
         e = cudaMalloc((void**)&c->idx[k], (size_t)n * 4);
         if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(sort idx)");
@@ -768,8 +769,9 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     const size_t words = (max_entities + 63) / 64;
     bool ok = cudaMalloc((void**)&c->rows_mem, max_entities * 64) == cudaSuccess;
     for (int k = 0; ok && k < TB_COMPONENT_COUNT; ++k) {
-        ok = cudaMalloc((void**)&c->mask[k], words * 8) == cudaSuccess;
-        if (ok) cudaMemsetAsync(c->mask[k], 0, words * 8, c->stream);
+        // +2 words: the emit kernel copies presence words two at a time (16-byte cp.async)
+        ok = cudaMalloc((void**)&c->mask[k], (words + 2) * 8) == cudaSuccess;
+        if (ok) cudaMemsetAsync(c->mask[k], 0, (words + 2) * 8, c->stream);
     }
     ok = ok && cudaMallocHost((void**)&c->h_hdr, 64) == cudaSuccess;
     if (ok) ok = ensure_scratch(c, kHdrWords) == TB_OK;
