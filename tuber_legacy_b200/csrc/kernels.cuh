@@ -210,25 +210,39 @@ struct PrepShared {
     uint32_t count;
 };
 
-// Accumulates one key into the per-block plan statistics and histograms.
-__device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, bool renderable, uint64_t key,
-                                             uint32_t i, uint32_t* tcnt = nullptr) {
-    // key masks: warp-reduce then one shared atomic per warp
-    const uint32_t act = __ballot_sync(0xffffffffu, renderable);
-    if (act == 0) return;
-    uint32_t lo = renderable ? (uint32_t)key : 0u, hi = renderable ? (uint32_t)(key >> 32) : 0u;
-    uint32_t nlo = renderable ? (uint32_t)key : 0xFFFFFFFFu, nhi = renderable ? (uint32_t)(key >> 32) : 0xFFFFFFFFu;
-    lo = __reduce_or_sync(0xffffffffu, lo);
-    hi = __reduce_or_sync(0xffffffffu, hi);
-    nlo = __reduce_and_sync(0xffffffffu, nlo);
-    nhi = __reduce_and_sync(0xffffffffu, nhi);
-    if ((threadIdx.x & 31) == 0) {
-        atomicOr(&sh.k_or, ((unsigned long long)hi << 32) | lo);
-        atomicAnd(&sh.k_and, ((unsigned long long)nhi << 32) | nlo);
-        atomicAdd(&sh.count, (uint32_t)__popc(act));
+// Per-thread running key statistics, folded into the block's once at the end of the kernel.
+struct PrepAcc {
+    unsigned long long k_or = 0ull, k_and = ~0ull;
+    uint32_t count = 0;
+};
+
+// Accounts one entity: key statistics in registers, digit histograms in shared memory, optional
+// short key write. Must be called by all 32 lanes of a warp (it contains warp collectives).
+//   small == true  (single pass, <= 32 buckets): one match.any per entity aggregates the warp's
+//     histogram update, and the per-emit-tile counts go straight to global memory with one RED per
+//     distinct digit per warp - no block barrier anywhere in the key pass;
+//   small == false: plain shared atomics (many distinct digits, little contention), per-tile counts
+//     through `tcnt` in shared memory when the caller wants them.
+__device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, PrepAcc& acc, bool renderable,
+                                             uint64_t key, uint32_t i, bool small, uint32_t emit_tile, uint32_t* tcnt) {
+    if (renderable) {
+        acc.k_or |= key;
+        acc.k_and &= key;
+        acc.count += 1;
     }
-    if (!p.have_plan || !renderable) return;
+    if (!p.have_plan) return;
     const uint64_t sk = pext_runs(key, p.plan.pext);
+    if (small) {
+        const uint32_t d = renderable ? (uint32_t)sk & ((1u << p.plan.bits[0]) - 1u) : kInvalidDigit;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (d != kInvalidDigit && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) {
+            const uint32_t c = __popc(peers);
+            atomicAdd(&sh.hist[0][d], c);
+            if (p.tile_counts != nullptr) atomicAdd(&p.tile_counts[(size_t)d * p.emit_tiles + emit_tile], c);
+        }
+        return;
+    }
+    if (!renderable) return;
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
         const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
         atomicAdd(&sh.hist[q][d], 1u);
@@ -242,6 +256,11 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
     }
 }
 
+// The single-pass few-bucket plan the `small` accounting path serves.
+__device__ __forceinline__ bool prep_small(const PrepParams& p) {
+    return p.have_plan && p.plan.npasses == 1 && p.plan.bits[0] <= 5 && p.lt_mode == 0 && !p.write_keys;
+}
+
 __device__ __forceinline__ void prep_init(const PrepParams& p, PrepShared& sh) {
     for (uint32_t k = threadIdx.x; k < kMaxPasses * 256; k += blockDim.x) (&sh.hist[0][0])[k] = 0;
     for (uint32_t k = threadIdx.x; k < 2048; k += blockDim.x) sh.lt[k] = 0;
@@ -253,7 +272,20 @@ __device__ __forceinline__ void prep_init(const PrepParams& p, PrepShared& sh) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh) {
+__device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh, const PrepAcc& acc) {
+    // fold the per-thread key statistics: warp reduce, then one shared atomic per warp
+    {
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc.k_or);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc.k_or >> 32));
+        const uint32_t nlo = __reduce_and_sync(0xffffffffu, (uint32_t)acc.k_and);
+        const uint32_t nhi = __reduce_and_sync(0xffffffffu, (uint32_t)(acc.k_and >> 32));
+        const uint32_t cnt = __reduce_add_sync(0xffffffffu, acc.count);
+        if ((threadIdx.x & 31) == 0 && cnt) {
+            atomicOr(&sh.k_or, ((unsigned long long)hi << 32) | lo);
+            atomicAnd(&sh.k_and, ((unsigned long long)nhi << 32) | nlo);
+            atomicAdd(&sh.count, cnt);
+        }
+    }
     __syncthreads();
     if (p.have_plan) {
         for (uint32_t q = 0; q < p.plan.npasses; ++q) {
@@ -281,14 +313,16 @@ __device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh) 
 // Flat scenes (no Parent anywhere): per entity, the velocity system
 // (translation += velocity * dt, [SPEC]; idiom of system.rs:132-137) then the sort key of
 // (&Transform, &Sprite) matches (query.rs:109-120 presence AND).
-__global__ void __launch_bounds__(kThreads) prepare_flat_kernel(const PrepParams p) {
+__global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepParams p) {
     __shared__ PrepShared sh;
     prep_init(p, sh);
     const uint32_t tile_elems = kThreads * kPrepItems;
     const uint32_t ntiles = (p.n + tile_elems - 1) / tile_elems;
     const bool do_int = p.integrate && p.vel != nullptr;
-    const bool tiles_out = p.have_plan && p.tile_counts != nullptr;
+    const bool small = prep_small(p);
+    const bool tiles_out = !small && p.have_plan && p.tile_counts != nullptr;  // shared-memory per-tile counts
     const uint32_t R0 = 1u << p.plan.bits[0];
+    PrepAcc acc;
     uint32_t par = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1u) {
         const uint32_t base = tile * tile_elems + threadIdx.x;
@@ -339,10 +373,10 @@ __global__ void __launch_bounds__(kThreads) prepare_flat_kernel(const PrepParams
             const uint32_t i = base + k * kThreads;
             uint64_t key = 0;
             if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
-            prep_account(p, sh, rend[k], key, i, tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
+            // this 1024-entity tile is two 512-entity emit tiles
+            prep_account(p, sh, acc, rend[k], key, i, small, tile * 2 + (k >> 1), tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
         }
         if (tiles_out) {
-            // this 1024-entity tile is two 512-entity emit tiles
             __syncthreads();
             for (uint32_t d = threadIdx.x; d < 2 * R0; d += kThreads) {
                 const uint32_t h = d / R0, dd = d - h * R0;
@@ -351,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) prepare_flat_kernel(const PrepParams
             }
         }
     }
-    prep_flush(p, sh);
+    prep_flush(p, sh, acc);
 }
 
 // ---- hierarchy: one level of world = world[parent] * local ------------------------------------
@@ -373,6 +407,7 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
     __shared__ PrepShared sh;
     const PrepParams& p = lp.prep;
     prep_init(p, sh);
+    PrepAcc acc;
     const uint32_t nchunks = (lp.count + kThreads - 1) / kThreads;
     for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const uint32_t slot = chunk * kThreads + threadIdx.x;
@@ -434,9 +469,9 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
             rend = mask_bit(p.mask_s, e);
             if (rend) key = world_key(wr.r2, wr.s);
         }
-        prep_account(p, sh, rend, key, e);
+        prep_account(p, sh, acc, rend, key, e, false, 0u, nullptr);
     }
-    prep_flush(p, sh);
+    prep_flush(p, sh, acc);
 }
 
 // ---- histogram -> bucket bases; (layer, texture) histogram -> batch table -----------------------

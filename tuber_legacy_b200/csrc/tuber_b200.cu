@@ -276,13 +276,19 @@ struct ScratchLayout {
     size_t total_words = 0, alloc_words = 0;
 };
 
-ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets) {
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets, bool zero_counts0) {
     ScratchLayout L;
     L.tile_offsets = tile_offsets;
     size_t off = kHdrWords;
     L.lt_off = off;
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
     off += L.lt_words;
+    const uint32_t last_tile = kThreads * kEmitItems;
+    if (tile_offsets && zero_counts0) {
+        // the key pass accumulates pass-0 per-tile counts with REDs: they start from zero
+        L.counts_off[0] = off;
+        off += (size_t)div_up(n, plan.npasses == 1 ? last_tile : kThreads * kScatterItems) << plan.bits[0];
+    }
     for (uint32_t p = 0; p < plan.npasses; ++p) {
         const bool last = p + 1 == plan.npasses;
         const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
@@ -292,8 +298,10 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
     }
     L.total_words = off;  // everything up to here is zeroed every frame
     for (uint32_t p = 0; p < plan.npasses; ++p) {
-        L.counts_off[p] = off;
-        if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        if (!(p == 0 && tile_offsets && zero_counts0)) {
+            L.counts_off[p] = off;
+            if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        }
         L.offs_off[p] = off;
         if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
     }
@@ -1192,10 +1200,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
-        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0);
+        const bool prepare_made_counts = c->tile_offsets != 0 && !fm.hier && plan.npasses == 1;
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0, prepare_made_counts);
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
-        const bool prepare_made_counts = L.tile_offsets && !fm.hier && plan.npasses == 1;
         if (fm.lt_generic) {
             size_t cap = c->texlayer ? c->texlayer_cap : 0;
             if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
