@@ -1,0 +1,109 @@
+"""BASELINE.json's full-size configs on the GPU, checked through size-independent properties (the
+CPU oracle would need minutes per frame at these sizes): the order is a permutation of the
+renderables, keys recomputed from the emitted instances are sorted with ties in entity order, the
+batch table tiles [0, M) at exactly the (layer, texture) run heads, frames are idempotent, every
+internal path emits the same bytes, and a random sample of entities matches the oracle's compose."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tuber_legacy_b200 import capi, scenes
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def checksum(g):
+    return (zlib.crc32(g.order.tobytes()), zlib.crc32(g.instances.tobytes()), zlib.crc32(g.vertices.tobytes()),
+            zlib.crc32(g.batches.tobytes()))
+
+
+def sample_matches_oracle(sc, g, k=4096, seed=0):
+    """flat scenes: instance of sorted position p is the oracle's compose of entity order[p]"""
+    rng = np.random.default_rng(seed)
+    pos = rng.integers(0, len(g.order), k)
+    ent = g.order[pos]
+    want = oracle.as_matrix4(sc.transforms[ent].view(np.float32).reshape(-1, 12))
+    got = g.instances["model"][pos].reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1, 16)  # column-major -> row-major
+    util.float_close(got, want, np.abs(want).max(axis=1, keepdims=True), "sampled instance matrix")
+    np.testing.assert_array_equal(g.instances["texture"][pos], sc.sprites["texture"][ent])
+    np.testing.assert_array_equal(g.instances["layer"][pos], sc.sprites["layer"][ent])
+
+
+def test_config2_1M_flat_full_size():
+    sc = scenes.config2()
+    ctx = util.make_ctx(sc)
+    g = util.GpuFrame(ctx)
+    util.check_frame_properties(ctx, g, sc.n)
+    sample_matches_oracle(sc, g)
+    assert checksum(g) == checksum(util.GpuFrame(ctx))  # idempotent
+    ctx.close()
+    # narrower digits / look-back placement / unstaged stores: same bytes
+    for opts in ({"digit_bits": 5}, {"tile_offsets": 0}, {"staged_emit": 0, "lt_limit": 0}):
+        c2 = util.make_ctx(sc, **opts)
+        assert checksum(util.GpuFrame(c2)) == checksum(g), opts
+        c2.close()
+
+
+def test_config2_1M_random_z_full_size():
+    sc = scenes.config2(z_mode="random")
+    ctx = util.make_ctx(sc)
+    g = util.GpuFrame(ctx)
+    assert g.info.key_bits > 32
+    util.check_frame_properties(ctx, g, sc.n)
+    sample_matches_oracle(sc, g)
+    ctx.close()
+
+
+def test_config3_4M_hierarchy_full_size():
+    sc = scenes.config3()
+    ctx = util.make_ctx(sc)
+    g = util.GpuFrame(ctx)
+    assert g.info.hierarchy_levels == 8
+    util.check_frame_properties(ctx, g, sc.n)
+    # world matrices of a sample of chains, recomputed on the CPU with the oracle's multiply
+    w = ctx.download_world_matrices(0, sc.n)
+    L = oracle.lib()
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    local = None
+    for e in rng.integers(0, sc.n, 300):
+        chain = [int(e)]
+        while sc.parents[chain[-1]] != capi.TB_NO_PARENT:
+            chain.append(int(sc.parents[chain[-1]]))
+        local = oracle.as_matrix4(sc.transforms[chain].view(np.float32).reshape(-1, 12))
+        m = local[-1].copy()
+        for k in range(len(chain) - 2, -1, -1):
+            out = np.zeros(16, np.float32)
+            L.orc_mat4_mul_f32(C.c_void_p(m.ctypes.data), C.c_void_p(local[k].ctypes.data), C.c_void_p(out.ctypes.data))
+            m = out
+        util.float_close(w[e], m, np.abs(m).max(), "world matrix of a depth-%d chain" % len(chain))
+    ctx.close()
+
+
+def test_config4_16M_particles_full_size():
+    sc = scenes.config4()
+    ctx = util.make_ctx(sc)
+    t0 = sc.transforms["translation"].copy()
+    for _ in range(2):
+        ctx.system_integrate(sc.dt)
+    g = util.GpuFrame(ctx)
+    assert g.info.path == capi.TB_PATH_BUCKET and g.info.num_batches == 4
+    util.check_frame_properties(ctx, g, sc.n)
+    # velocity system: translation advanced twice, each product and sum individually rounded
+    dt = np.float32(sc.dt)
+    want = t0.copy()
+    for _ in range(2):
+        want = want + sc.velocities["v"] * dt
+    got = ctx.download_transforms(0, sc.n)["translation"]
+    np.testing.assert_array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
+    sc.transforms["translation"][:] = got
+    sample_matches_oracle(sc, g)
+    # the look-back placement gives the same bytes
+    c2 = util.make_ctx(sc, tile_offsets=0)
+    assert checksum(util.GpuFrame(c2)) == checksum(g)
+    c2.close()
+    ctx.close()
