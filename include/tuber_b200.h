@@ -228,6 +228,40 @@ TB_API tb_status tb_shard_set(tb_ctx* ctx, int rank, int nranks, uint64_t global
 TB_API tb_status tb_frame_set_output(tb_ctx* ctx, void* d_instances, void* d_vertices, void* d_order,
                                      uint64_t capacity_instances);
 
+/* ---- one scene over several GPUs: exact global draw order --------------------
+ *
+ * Every rank holds a contiguous id range (tb_shard_set). A multi-GPU frame is five calls per rank,
+ * with two small exchanges done by the caller (NCCL / any transport) in between:
+ *
+ *   tb_shard_key_stats        -> 3 words; caller ORs words 0,1 and sums word 2 over the ranks
+ *   tb_shard_plan             <- the reduced words: every rank now sorts by the same short key
+ *   tb_shard_key_histogram    -> this rank's histogram over the short key (caller-provided device memory)
+ *   tb_shard_place            <- all ranks' histograms, rank-major (an all-gather of the above)
+ *   tb_frame_transform_batch  emits every element at its position in the GLOBAL order, into the
+ *                             buffers given to tb_frame_set_output (e.g. the presenting rank's
+ *                             buffers mapped with tb_ipc_open: the emit kernel then stores straight
+ *                             over NVLink), and builds the global batch table.
+ *
+ * Exact for short keys up to TB_SHARD_MAX_KEY_BITS bits (tb_shard_plan returns TB_ERR_UNSUPPORTED
+ * beyond, e.g. continuous z: such scenes need a merge at the presenting rank). Scenes with Parent
+ * links across shards are not supported yet. */
+#define TB_SHARD_MAX_KEY_BITS 22
+TB_API tb_status tb_shard_key_stats(tb_ctx* ctx, uint64_t stats[3]);
+TB_API tb_status tb_shard_plan(tb_ctx* ctx, const uint64_t global_stats[3], uint64_t* nbins);
+TB_API tb_status tb_shard_key_histogram(tb_ctx* ctx, void* d_hist /* nbins x u32, device */);
+TB_API tb_status tb_shard_place(tb_ctx* ctx, const void* d_all_hists /* nranks x nbins x u32, device */,
+                                uint64_t* global_instances);
+
+/* Raw device buffers that can be shared with other processes of the node (CUDA IPC). */
+#define TB_IPC_HANDLE_BYTES 64
+TB_API tb_status tb_device_alloc(int device, uint64_t bytes, void** d_ptr);
+TB_API tb_status tb_device_free(void* d_ptr);
+TB_API tb_status tb_ipc_export(void* d_ptr, uint8_t handle[TB_IPC_HANDLE_BYTES]);
+TB_API tb_status tb_ipc_open(int device, const uint8_t handle[TB_IPC_HANDLE_BYTES], void** d_ptr);
+TB_API tb_status tb_ipc_close(void* d_ptr);
+/* Device-to-host copy of n bytes from any device pointer (peer-mapped ones included). */
+TB_API tb_status tb_device_read(tb_ctx* ctx, const void* d_src, uint64_t bytes, void* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -389,3 +389,126 @@ def test_frames_are_idempotent():
     assert a.vertices.tobytes() == b.vertices.tobytes()
     assert a.order.tobytes() == b.order.tobytes() and a.batches.tobytes() == b.batches.tobytes()
     ctx.close()
+
+
+# ---- one scene over several contexts: exact global draw order (multi-GPU placement) ---------------
+
+def _sharded_frame(sc, nranks, **options):
+    """Emulates `nranks` ranks as contexts on this GPU (run one after another, no waiting between
+    them), all emitting into one set of output buffers; returns the frame read back from them."""
+    n = sc.n
+    bufs = [capi.device_alloc(max(n, 1) * 80), capi.device_alloc(max(n, 1) * 64), capi.device_alloc(max(n, 1) * 4)]
+    ctxs = []
+    for r in range(nranks):
+        first, cnt = scenes.shard_range(n, r, nranks)
+        part = scenes.Scene(sc.name, n, first, cnt)
+        part.transforms, part.sprites = sc.transforms[first:first + cnt], sc.sprites[first:first + cnt]
+        part.velocities = None if sc.velocities is None else sc.velocities[first:first + cnt]
+        ctx = util.make_ctx(part, **options)
+        ctx.shard_set(r, nranks, first)
+        ctx.set_output(bufs[0], bufs[1], bufs[2], n)
+        ctxs.append(ctx)
+    return ctxs, bufs
+
+
+def _run_sharded(ctxs, bufs, ticks=0, dt=0.01):
+    for _ in range(ticks):
+        for c in ctxs:
+            c.system_integrate(dt)
+    stats = [c.shard_key_stats() for c in ctxs]
+    from tuber_legacy_b200.shard import reduce_stats
+    g = reduce_stats(stats)
+    nbins = [c.shard_plan(g) for c in ctxs]
+    assert len(set(nbins)) == 1
+    nb = nbins[0]
+    d_all = capi.device_alloc(len(ctxs) * nb * 4)
+    for r, c in enumerate(ctxs):
+        c.shard_key_histogram(d_all + r * nb * 4)
+    totals = [c.shard_place(d_all) for c in ctxs]
+    assert len(set(totals)) == 1 and totals[0] == g[2]
+    outs = [c.frame() for c in ctxs]
+    m, b = totals[0], outs[0].num_batches
+
+    class G:
+        pass
+    gpu = G()
+    gpu.info = outs[0]
+    c0 = ctxs[0]
+    gpu.order = c0.device_read(bufs[2], m * 4, np.uint32)
+    gpu.instances = c0.device_read(bufs[0], m * 80, np.uint8).view(capi.INSTANCE_DTYPE)
+    gpu.vertices = c0.device_read(bufs[1], m * 64, np.uint8).view(capi.VERTEX_DTYPE).reshape(-1, 4)
+    gpu.batches = c0.download_batches(b)
+    for c in ctxs[1:]:
+        np.testing.assert_array_equal(c.download_batches(b), gpu.batches)  # every rank has the global table
+    capi.device_free(d_all)
+    return gpu
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+def test_sharded_scene_matches_single_oracle_frame(nranks):
+    """ranks own contiguous id ranges; their emits interleave into the exact global order"""
+    sc = scenes.config2(n=90_001, seed=40)  # 21 key bits: layers x textures x z steps, 3 radix passes
+    ctxs, bufs = _sharded_frame(sc, nranks)
+    g = _run_sharded(ctxs, bufs)
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    for c in ctxs:
+        c.close()
+    for b in bufs:
+        capi.device_free(b)
+
+
+def test_sharded_particles_with_velocity_system():
+    sc = scenes.config4(n=120_000, seed=41)
+    ref = util.make_oracle(sc)
+    ctxs, bufs = _sharded_frame(sc, 4)
+    for _ in range(2):
+        ref.step(sc.dt)
+        g = _run_sharded(ctxs, bufs, ticks=1, dt=sc.dt)
+        util.assert_frame_parity(g, ref.frame())
+    for c in ctxs:
+        c.close()
+    for b in bufs:
+        capi.device_free(b)
+
+
+def test_sharded_sparse_and_empty_shards():
+    sc = scenes.config2(n=40_000, seed=42)
+    masks = {capi.TB_SPRITE: util.random_mask(sc.n, 0.5, 9)}
+    words = masks[capi.TB_SPRITE]
+    words[: 10_000 // 64 + 1] = 0  # the first shard ends up with no renderables at all
+    ref = util.make_oracle(sc, masks)
+    n, nranks = sc.n, 4
+    bufs = [capi.device_alloc(n * 80), capi.device_alloc(n * 64), capi.device_alloc(n * 4)]
+    ctxs = []
+    bits = ((words[np.arange(n) // 64] >> (np.arange(n) % 64).astype(np.uint64)) & np.uint64(1)).astype(bool)
+    for r in range(nranks):
+        first, cnt = scenes.shard_range(n, r, nranks)
+        part = scenes.Scene(sc.name, n, first, cnt)
+        part.transforms, part.sprites = sc.transforms[first:first + cnt], sc.sprites[first:first + cnt]
+        local = np.zeros((cnt + 63) // 64, np.uint64)
+        idx = np.nonzero(bits[first:first + cnt])[0]
+        np.bitwise_or.at(local, idx // 64, np.uint64(1) << (idx % 64).astype(np.uint64))
+        ctx = util.make_ctx(part, {capi.TB_SPRITE: local})
+        ctx.shard_set(r, nranks, first)
+        ctx.set_output(bufs[0], bufs[1], bufs[2], n)
+        ctxs.append(ctx)
+    g = _run_sharded(ctxs, bufs)
+    util.assert_frame_parity(g, ref.frame())
+    for c in ctxs:
+        c.close()
+    for b in bufs:
+        capi.device_free(b)
+
+
+def test_sharded_wide_keys_are_refused_not_wrong():
+    sc = scenes.config2(n=20_000, seed=43, z_mode="random")
+    ctxs, bufs = _sharded_frame(sc, 2)
+    from tuber_legacy_b200.shard import reduce_stats
+    g = reduce_stats([c.shard_key_stats() for c in ctxs])
+    with pytest.raises(capi.TuberError) as e:
+        ctxs[0].shard_plan(g)
+    assert e.value.status == capi.TB_ERR_UNSUPPORTED
+    for c in ctxs:
+        c.close()
+    for b in bufs:
+        capi.device_free(b)

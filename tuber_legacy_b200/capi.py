@@ -89,6 +89,16 @@ _SIGNATURES = {
     "tb_launch_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "tb_shard_set": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_uint64]),
     "tb_frame_set_output": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "tb_shard_key_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_shard_plan": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tb_shard_key_histogram": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "tb_shard_place": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_device_alloc": (C.c_int32, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "tb_device_free": (C.c_int32, [C.c_void_p]),
+    "tb_ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "tb_ipc_open": (C.c_int32, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "tb_ipc_close": (C.c_int32, [C.c_void_p]),
+    "tb_device_read": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tb_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "tb_host_free": (None, [C.c_void_p]),
 }
@@ -305,6 +315,31 @@ class Context:
     def shard_set(self, rank, nranks, global_first):
         self._check(self._lib.tb_shard_set(self._h, int(rank), int(nranks), int(global_first)))
 
+    def shard_key_stats(self):
+        """(OR of keys, OR of ~keys, renderable count) of this shard; reduce over ranks with OR, OR, +."""
+        st = (C.c_uint64 * 3)()
+        self._check(self._lib.tb_shard_key_stats(self._h, st))
+        return [int(st[0]), int(st[1]), int(st[2])]
+
+    def shard_plan(self, global_stats):
+        st = (C.c_uint64 * 3)(*[int(v) for v in global_stats])
+        nbins = C.c_uint64()
+        self._check(self._lib.tb_shard_plan(self._h, st, C.byref(nbins)))
+        return nbins.value
+
+    def shard_key_histogram(self, d_hist):
+        self._check(self._lib.tb_shard_key_histogram(self._h, C.c_void_p(d_hist)))
+
+    def shard_place(self, d_all_hists):
+        total = C.c_uint64()
+        self._check(self._lib.tb_shard_place(self._h, C.c_void_p(d_all_hists), C.byref(total)))
+        return total.value
+
+    def device_read(self, d_ptr, nbytes, dtype=np.uint8):
+        out = np.zeros(int(nbytes) // np.dtype(dtype).itemsize, dtype=dtype)
+        self._check(self._lib.tb_device_read(self._h, C.c_void_p(d_ptr), int(nbytes), _ptr(out)))
+        return out
+
     def set_output(self, d_instances, d_vertices, d_order, capacity):
         self._check(self._lib.tb_frame_set_output(self._h, C.c_void_p(d_instances or 0), C.c_void_p(d_vertices or 0),
                                                   C.c_void_p(d_order or 0), int(capacity)))
@@ -323,3 +358,36 @@ def host_alloc(nbytes):
 
 def host_free(ptr):
     load().tb_host_free(C.c_void_p(ptr))
+
+
+def device_alloc(nbytes, device=0):
+    p = C.c_void_p()
+    st = load().tb_device_alloc(int(device), int(nbytes), C.byref(p))
+    if st != TB_OK:
+        raise TuberError(st, "tb_device_alloc failed")
+    return p.value
+
+
+def device_free(ptr):
+    load().tb_device_free(C.c_void_p(ptr))
+
+
+def ipc_export(ptr):
+    h = (C.c_uint8 * 64)()
+    st = load().tb_ipc_export(C.c_void_p(ptr), h)
+    if st != TB_OK:
+        raise TuberError(st, "tb_ipc_export failed")
+    return bytes(h)
+
+
+def ipc_open(handle, device=0):
+    p = C.c_void_p()
+    h = (C.c_uint8 * 64)(*handle)
+    st = load().tb_ipc_open(int(device), h, C.byref(p))
+    if st != TB_OK:
+        raise TuberError(st, "tb_ipc_open failed")
+    return p.value
+
+
+def ipc_close(ptr):
+    load().tb_ipc_close(C.c_void_p(ptr))

@@ -196,6 +196,7 @@ struct PrepParams {
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
     uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per 512-entity emit tile
     uint32_t emit_tiles;
+    uint32_t* key_hist;     // optional [1 << nbits]: histogram over the whole short key (multi-GPU placement)
     FramePlan plan;
 };
 
@@ -239,10 +240,12 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
             const uint32_t c = __popc(peers);
             atomicAdd(&sh.hist[0][d], c);
             if (p.tile_counts != nullptr) atomicAdd(&p.tile_counts[(size_t)d * p.emit_tiles + emit_tile], c);
+            if (p.key_hist != nullptr) atomicAdd(&p.key_hist[d], c);  // single pass: the digit is the short key
         }
         return;
     }
     if (!renderable) return;
+    if (p.key_hist != nullptr) atomicAdd(&p.key_hist[(uint32_t)sk], 1u);
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
         const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
         atomicAdd(&sh.hist[q][d], 1u);
@@ -827,6 +830,8 @@ struct EmitParams {
     uint32_t* texlayer;      // optional per-position texture|layer<<16 (generic batch path)
     uint32_t global_first;   // added to the entity ids written to `order`
     uint32_t staged;         // stage outputs through shared memory for full-line stores
+    const uint32_t* remap;   // optional [1 << nbits]: added to the shard-local position of every element
+                             // with that short key -> position in the global (all ranks) draw order
 };
 
 constexpr int kEmitItems = 2;
@@ -989,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
         }
         const float4* rows = sm.rows[cur];
         const uint32_t tile_base = tile * TILE;
-        uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS];
+        uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS], shift_g[ITEMS];
         bool valid[ITEMS];
         if (in_order) {
             mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
@@ -1029,6 +1034,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                     }
                 }
                 digit[k] = valid[k] ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
+                shift_g[k] = (ep.remap != nullptr && valid[k]) ? __ldg(ep.remap + (uint32_t)sk) : 0u;
             }
         } else {
 #pragma unroll
@@ -1038,10 +1044,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 valid[k] = pos < n_eff;
                 ent[k] = pos;
                 digit[k] = kInvalidDigit;
+                shift_g[k] = 0u;
                 if (valid[k]) {
                     const KeyT key = ep.keys_in[pos];
                     ent[k] = ep.idx_in[pos];
                     digit[k] = (uint32_t)(key >> ep.pass.shift) & mask;
+                    if (ep.remap != nullptr) shift_g[k] = __ldg(ep.remap + (uint32_t)key);
                     // gather this entity's row into the item's shared-memory slot
                     float4* d = sm.rows[cur];
                     if (from_world) {
@@ -1066,7 +1074,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
             if (digit[k] != kInvalidDigit) {
                 sm.s_li[slot[k]] = (uint16_t)(warp * (ITEMS * 32) + k * 32 + lane);
                 sm.s_ent[slot[k]] = ent[k];
-                sm.s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k];
+                sm.s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k] + shift_g[k];
             }
         }
         if (!in_order) cp_async_wait_all();
@@ -1447,6 +1455,92 @@ __global__ void __launch_bounds__(kThreads) key_hist_kernel(const uint32_t* __re
     const uint32_t k = keys[i];
     for (uint32_t q = 0; q < ds.npasses; ++q)
         atomicAdd(&hist[q * 256 + ((k >> ds.shift[q]) & ((1u << ds.bits[q]) - 1u))], 1u);
+}
+
+// ---- multi-GPU placement --------------------------------------------------------------
+
+// hists: [nranks][nbins] short-key histograms of every shard. Per block of 1024 bins: the sum over
+// all ranks and this rank's own sum.
+__global__ void __launch_bounds__(kThreads) place_sums_kernel(const uint32_t* __restrict__ hists, uint32_t nranks,
+                                                               uint32_t rank, uint32_t nbins, uint32_t* bsum_total,
+                                                               uint32_t* bsum_local) {
+    __shared__ uint32_t s_t, s_l;
+    if (threadIdx.x == 0) s_t = s_l = 0;
+    __syncthreads();
+    uint32_t t = 0, l = 0;
+    for (uint32_t k = blockIdx.x * 1024 + threadIdx.x; k < min(nbins, (blockIdx.x + 1) * 1024); k += kThreads) {
+        for (uint32_t r = 0; r < nranks; ++r) t += hists[(size_t)r * nbins + k];
+        l += hists[(size_t)rank * nbins + k];
+    }
+    t = __reduce_add_sync(0xffffffffu, t);
+    l = __reduce_add_sync(0xffffffffu, l);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_t, t);
+        atomicAdd(&s_l, l);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bsum_total[blockIdx.x] = s_t;
+        bsum_local[blockIdx.x] = s_l;
+    }
+}
+
+// remap[k] = (elements of all ranks with a smaller key) + (elements of lower ranks with key k)
+//            - (elements of this rank with a smaller key):
+// added to an element's shard-local sorted position it gives its position in the global order
+// (id ranges ascend with the rank, so ties between ranks resolve like ties between entity ids).
+// Also accumulates the global (layer, texture) bins for the batch table.
+__global__ void __launch_bounds__(kThreads) place_write_kernel(const uint32_t* __restrict__ hists, uint32_t nranks,
+                                                                uint32_t rank, uint32_t nbins,
+                                                                const uint32_t* __restrict__ boff_total,
+                                                                const uint32_t* __restrict__ boff_local, uint32_t zbits,
+                                                                uint32_t* remap, uint32_t* lt_global) {
+    __shared__ uint32_t s_wt[kWarps], s_wl[kWarps];
+    const uint32_t k0 = blockIdx.x * 1024 + threadIdx.x * 4;
+    uint32_t t[4], l[4], lower[4];
+    uint32_t st = 0, sl = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t k = k0 + j;
+        t[j] = l[j] = lower[j] = 0;
+        if (k < nbins) {
+            for (uint32_t r = 0; r < nranks; ++r) {
+                const uint32_t h = hists[(size_t)r * nbins + k];
+                t[j] += h;
+                if (r < rank) lower[j] += h;
+                if (r == rank) l[j] = h;
+            }
+            if (t[j]) atomicAdd(&lt_global[k >> zbits], t[j]);
+        }
+        st += t[j];
+        sl += l[j];
+    }
+    uint32_t xt = st, xl = sl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yt = __shfl_up_sync(0xffffffffu, xt, o), yl = __shfl_up_sync(0xffffffffu, xl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) {
+            xt += yt;
+            xl += yl;
+        }
+    }
+    if ((threadIdx.x & 31) == 31) {
+        s_wt[threadIdx.x >> 5] = xt;
+        s_wl[threadIdx.x >> 5] = xl;
+    }
+    __syncthreads();
+    uint32_t bt = boff_total[blockIdx.x] + xt - st, bl = boff_local[blockIdx.x] + xl - sl;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) {
+        bt += s_wt[w];
+        bl += s_wl[w];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t k = k0 + j;
+        if (k < nbins) remap[k] = bt + lower[j] - bl;
+        bt += t[j];
+        bl += l[j];
+    }
 }
 
 }  // namespace tb

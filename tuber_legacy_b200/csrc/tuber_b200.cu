@@ -110,6 +110,12 @@ struct tb_ctx {
     // shard
     int rank = 0, nranks = 1;
     uint64_t global_first = 0;
+    int shard_state = 0;  // 0 idle, 1 stats taken, 2 global plan set, 3 pass A done (histogram out), 4 placed
+    uint64_t shard_count = 0, shard_global_count = 0;
+    uint32_t* remap = nullptr;      // [1 << nbits]
+    uint32_t* lt_global = nullptr;  // [1 << ltbits]
+    uint32_t* place_tmp = nullptr;  // block sums of the placement scans
+    size_t remap_cap = 0, lt_global_cap = 0, place_tmp_cap = 0;
 
     // pinned host mirror of the scratch header
     uint64_t* h_hdr = nullptr;
@@ -590,7 +596,8 @@ struct FrameMode {
     bool lt_generic;  // run-head detection over an emitted texlayer array
 };
 
-tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode& fm, const ScratchLayout* L) {
+tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode& fm, const ScratchLayout* L,
+                      uint32_t* key_hist = nullptr) {
     const uint32_t n = (uint32_t)c->n;
     PrepParams p{};
     p.n = n;
@@ -604,6 +611,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     p.have_plan = have_plan;
     p.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     p.hist = c->scratch + kHdrHist;
+    p.key_hist = key_hist;
     if (have_plan) {
         p.plan = c->plan;
         p.write_keys = c->plan.npasses > 1 || fm.hier;
@@ -713,6 +721,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             ep.texlayer = fm.lt_generic ? c->texlayer : nullptr;
             ep.global_first = (uint32_t)c->global_first;
             ep.staged = c->staged_emit;
+            ep.remap = c->shard_state == 4 ? c->remap : nullptr;
             TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
                       std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared), ep);
         }
@@ -727,6 +736,8 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
 // =================================================================================================
 
 extern "C" {
+
+static tb_status shard_frame(tb_ctx* c, tb_frame_out* out);
 
 const char* tb_version(void) { return "tuber_b200 0.1 (sm_100a)"; }
 
@@ -825,6 +836,9 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->batches);
     cudaFree(c->level_list);
     cudaFree(c->sane_parent);
+    cudaFree(c->remap);
+    cudaFree(c->lt_global);
+    cudaFree(c->place_tmp);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1159,6 +1173,8 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     c->frame_launches = 0;
     c->frame_valid = false;
     c->last_instances = c->last_batches = 0;
+    if (c->shard_state == 4) return shard_frame(c, out);
+    c->shard_state = 0;
     const uint64_t n = c->n;
     // query::<(&Transform, &Sprite)>: no store for either => no matches (query.rs:110)
     if (n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
@@ -1268,6 +1284,207 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     out->kernel_launches = c->frame_launches;
     out->hierarchy_levels = fm.hier ? c->nlevels : 0;
     out->replanned = replanned;
+    return TB_OK;
+}
+
+// ---- multi-GPU frame -------------------------------------------------------------------------------------
+
+tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
+    if (!c || !stats) return TB_ERR_INVALID;
+    stats[0] = 0;
+    stats[1] = ~0ull;
+    stats[2] = 0;
+    c->shard_state = 0;
+    c->frame_valid = false;
+    if (c->store[TB_PARENT] && c->nranks > 1)
+        return fail(c, TB_ERR_UNSUPPORTED, "Parent links are not supported in a multi-GPU frame yet");
+    tb_status s;
+    c->shard_count = 0;
+    if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
+        if ((s = flush_integrate(c))) return s;
+        stats[1] = 0;  // neutral element of the OR-reduction of ~key
+        c->shard_state = 1;
+        return TB_OK;
+    }
+    c->nlevels = 1;
+    c->levels_dirty = false;
+    FrameMode fm{};
+    const bool integrate = c->pending;
+    c->pending = false;
+    TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+    if ((s = run_prepare(c, false, integrate, fm, nullptr))) return s;
+    if ((s = read_header(c))) return s;
+    stats[0] = c->h_hdr[0];
+    stats[1] = c->h_hdr[1];  // OR of ~key: reduces over ranks with OR, like word 0
+    stats[2] = c->h_hdr[2];
+    c->shard_count = c->h_hdr[2];
+    c->shard_state = 1;
+    return TB_OK;
+}
+
+tb_status tb_shard_plan(tb_ctx* c, const uint64_t g[3], uint64_t* nbins) {
+    if (!c || !g || !nbins) return TB_ERR_INVALID;
+    *nbins = 0;
+    if (c->shard_state != 1) return fail(c, TB_ERR_INVALID, "tb_shard_plan follows tb_shard_key_stats");
+    c->shard_global_count = g[2];
+    if (g[2] == 0) {
+        c->shard_state = 2;
+        *nbins = 1;
+        build_frame_plan(0, ~0ull, &c->plan);
+        return TB_OK;
+    }
+    build_frame_plan(g[0], ~g[1], &c->plan);
+    c->plan_valid = false;  // a later single-GPU frame re-plans for itself
+    if (c->plan.pext.nbits > TB_SHARD_MAX_KEY_BITS)
+        return fail(c, TB_ERR_UNSUPPORTED, "sort key too wide for histogram placement across GPUs");
+    if ((int)c->plan.ltbits > (int)kMaxLtBits) return fail(c, TB_ERR_UNSUPPORTED, "too many (layer, texture) bins");
+    *nbins = 1ull << c->plan.pext.nbits;
+    c->shard_state = 2;
+    return TB_OK;
+}
+
+tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
+    if (!c || !d_hist) return TB_ERR_INVALID;
+    if (c->shard_state != 2) return fail(c, TB_ERR_INVALID, "tb_shard_key_histogram follows tb_shard_plan");
+    const FramePlan& plan = c->plan;
+    const uint64_t nbins = 1ull << plan.pext.nbits;
+    TB_CUDA(c, cudaMemsetAsync(d_hist, 0, nbins * 4, c->stream));
+    if (c->shard_count > 0) {
+        tb_status s;
+        const uint64_t n = c->n;
+        FrameMode fm{};  // flat; the batch table comes from the global bins, not from pass A
+        const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
+        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts);
+        if ((s = ensure_scratch(c, L.alloc_words))) return s;
+        if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (L.total_words - kHdrTileCounters) * 4, c->stream));
+        if ((s = run_prepare(c, true, false, fm, &L, (uint32_t*)d_hist))) return s;
+    }
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller's collective may run on another stream
+    c->shard_state = 3;
+    return TB_OK;
+}
+
+tb_status tb_shard_place(tb_ctx* c, const void* d_all_hists, uint64_t* global_instances) {
+    if (!c || !d_all_hists) return TB_ERR_INVALID;
+    if (c->shard_state != 3) return fail(c, TB_ERR_INVALID, "tb_shard_place follows tb_shard_key_histogram");
+    const FramePlan& plan = c->plan;
+    const uint32_t nbins = 1u << plan.pext.nbits, nlt = 1u << plan.ltbits;
+    const uint32_t nblocks = div_up(nbins, 1024);
+    tb_status s;
+    if ((s = grow(c, &c->remap, &c->remap_cap, (size_t)nbins, 4))) return s;
+    if ((s = grow(c, &c->lt_global, &c->lt_global_cap, (size_t)nlt, 4))) return s;
+    if ((s = grow(c, &c->place_tmp, &c->place_tmp_cap, (size_t)nblocks * 2 + 2, 4))) return s;
+    uint32_t* bt = c->place_tmp;
+    uint32_t* bl = c->place_tmp + nblocks;
+    uint32_t* totals = c->place_tmp + 2 * nblocks;
+    TB_CUDA(c, cudaMemsetAsync(c->lt_global, 0, (size_t)nlt * 4, c->stream));
+    const uint32_t* H = (const uint32_t*)d_all_hists;
+    TB_LAUNCH(c, "place_sums", 0, place_sums_kernel, nblocks, kThreads, 0, H, (uint32_t)c->nranks, (uint32_t)c->rank, nbins, bt, bl);
+    TB_LAUNCH(c, "place_scan", 0, scan_blocks_kernel, 1, 1024, 0, bt, nblocks, totals);
+    TB_LAUNCH(c, "place_scan", 0, scan_blocks_kernel, 1, 1024, 0, bl, nblocks, totals + 1);
+    TB_LAUNCH(c, "place_write", 0, place_write_kernel, nblocks, kThreads, 0, H, (uint32_t)c->nranks, (uint32_t)c->rank, nbins,
+              (const uint32_t*)bt, (const uint32_t*)bl, plan.zbits, c->remap, c->lt_global);
+    uint32_t h[2] = {0, 0};
+    TB_CUDA(c, cudaMemcpyAsync(h, totals, 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[1] != c->shard_count) return fail(c, TB_ERR_INVALID, "histograms do not match this shard's renderable count");
+    c->shard_global_count = h[0];
+    if (global_instances) *global_instances = h[0];
+    c->shard_state = 4;
+    return TB_OK;
+}
+
+// The rest of a placed multi-GPU frame: batch table from the global bins, radix passes, emit at
+// global positions.
+static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
+    const uint64_t n = c->n;
+    const FramePlan& plan = c->plan;
+    tb_status s;
+    if ((s = ensure_outputs(c, std::max<uint64_t>(c->ext_inst ? 0 : c->shard_global_count, 1)))) return s;
+    if (c->ext_inst && c->ext_cap < c->shard_global_count)
+        return fail(c, TB_ERR_CAPACITY, "output buffers smaller than the global instance count");
+    float4* d_inst = c->ext_inst ? (float4*)c->ext_inst : c->inst;
+    float4* d_vtx = c->ext_vtx ? (float4*)c->ext_vtx : c->vtx;
+    uint32_t* d_order = c->ext_order ? (uint32_t*)c->ext_order : c->order;
+    uint64_t num_batches = 0;
+    if (c->shard_global_count > 0) {
+        TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, (const uint32_t*)c->lt_global, 1u << plan.ltbits, plan,
+                  c->batches, (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
+    }
+    if (c->shard_count > 0) {
+        FrameMode fm{};
+        const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
+        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts);
+        uint32_t* hist = c->scratch + kHdrHist;
+        if (!L.tile_offsets) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
+        if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+        else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+        if (s) return s;
+    }
+    if ((s = read_header(c))) return s;
+    if (c->shard_global_count > 0) num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, "frame");
+    if (c->prof) prof_harvest(c);
+    c->shard_state = 0;
+    if (num_batches > c->max_batches) return fail(c, TB_ERR_CAPACITY, "more batches than tb_ctx_set_max_batches allows");
+    c->last_instances = c->shard_global_count;  // the output buffers hold the global order
+    c->last_batches = num_batches;
+    c->frame_valid = true;
+    out->num_instances = c->shard_global_count;
+    out->num_batches = num_batches;
+    out->d_instances = (const tb_instance*)d_inst;
+    out->d_vertices = (const tb_quad_vertex*)d_vtx;
+    out->d_batches = (const tb_batch*)c->batches;
+    out->d_order = d_order;
+    out->path = c->shard_count == 0 ? TB_PATH_NONE : (plan.npasses == 1 ? TB_PATH_BUCKET : TB_PATH_SORT);
+    out->key_bits = plan.pext.nbits;
+    out->sort_passes = plan.npasses;
+    out->kernel_launches = c->frame_launches;
+    return TB_OK;
+}
+
+tb_status tb_device_alloc(int device, uint64_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return TB_ERR_INVALID;
+    *d_ptr = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return TB_ERR_OOM;
+    }
+    return TB_OK;
+}
+tb_status tb_device_free(void* d_ptr) { return cudaFree(d_ptr) == cudaSuccess ? TB_OK : TB_ERR_CUDA; }
+tb_status tb_ipc_export(void* d_ptr, uint8_t handle[TB_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == TB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_ptr || !handle) return TB_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, d_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return TB_ERR_COMM;
+    }
+    memcpy(handle, &h, sizeof(h));
+    return TB_OK;
+}
+tb_status tb_ipc_open(int device, const uint8_t handle[TB_IPC_HANDLE_BYTES], void** d_ptr) {
+    if (!d_ptr || !handle) return TB_ERR_INVALID;
+    *d_ptr = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    if (cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return TB_ERR_COMM;
+    }
+    return TB_OK;
+}
+tb_status tb_ipc_close(void* d_ptr) { return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? TB_OK : TB_ERR_COMM; }
+tb_status tb_device_read(tb_ctx* c, const void* d_src, uint64_t bytes, void* dst) {
+    if (!c || !d_src || !dst) return TB_ERR_INVALID;
+    TB_CUDA(c, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
 
