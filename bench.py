@@ -89,7 +89,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -268,6 +268,65 @@ def main():
     d2h = int(out.num_instances) * (80 + 64 + 4) + int(out.num_batches) * 16
     checksum = int(order[:: max(1, n // 4096)].astype(np.uint64).sum())
 
+    # ---- N > 1: the same scene as ONE draw list on the presenting rank -------------------------------
+    # Exact global draw order by key-histogram placement (two small NCCL collectives per frame) with
+    # every rank's emit kernel storing its instances straight into rank 0's buffers over NVLink
+    # (CUDA IPC peer mapping): the payload never goes through a collective. Reported next to `value`.
+    gather = None
+    if world > 1:
+        from tuber_legacy_b200.shard import CudaShard, ShardedFrame
+        n_total = n * world
+        ptrs = [0, 0, 0]
+        handles = [None]
+        if rank == 0:
+            ptrs = [capi.device_alloc(n_total * 80, local_rank), capi.device_alloc(n_total * 64, local_rank),
+                    capi.device_alloc(n_total * 4, local_rank)]
+            handles = [[capi.ipc_export(p) for p in ptrs]]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            ptrs = [capi.ipc_open(h, local_rank) for h in handles[0]]
+        ctx.set_output(ptrs[0], ptrs[1], ptrs[2], n_total)
+        drv = ShardedFrame(CudaShard(ctx, torch.device("cuda", local_rank)), rank, world)
+        for _ in range(2):
+            ctx.system_integrate(dt)
+            gout, gtotal = drv.step()
+        assert gtotal == n_total
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gsteps = max(5, args.steps // 2)
+        barrier()
+        tg = time.perf_counter()
+        g0.record(stream)
+        for _ in range(gsteps):
+            ctx.system_integrate(dt)
+            gout, gtotal = drv.step()
+        g1.record(stream)
+        barrier()
+        gather_ms = max(g0.elapsed_time(g1), (time.perf_counter() - tg) * 1e3) / gsteps
+        gcheck = None
+        if rank == 0:
+            b = ctx.download_batches(gout.num_batches)
+            assert int(b["count"].sum()) == n_total
+            sample = ctx.device_read(ptrs[2], 4 * 65536, np.uint32)  # head of the global order: texture 0 bucket
+            gcheck = {"batches": int(gout.num_batches), "order_head_sorted_by_id": bool(np.all(np.diff(sample.astype(np.int64)) > 0))}
+        gt = torch.tensor([gather_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gather_ms = float(gt[0])
+        remote_bytes = (world - 1) * n * (80 + 64 + 4)
+        gather = {"value": n_total / (gather_ms * 1e-3), "unit": UNIT, "ms_per_step": gather_ms, "steps": gsteps,
+                  "global_instances": n_total, "bytes_into_rank0_per_step": remote_bytes,
+                  "rank0_ingress_GBps": remote_bytes / (gather_ms * 1e-3) / 1e9,
+                  "method": "histogram placement + P2P stores from the emit kernel into rank 0 (CUDA IPC), 2 small NCCL "
+                            "all-gathers per frame (3 words, 1<<key_bits counters)", "check": gcheck}
+        ctx.set_output(0, 0, 0, 0)
+        dist.barrier()
+        if rank != 0:
+            for p_ in ptrs:
+                capi.ipc_close(p_)
+        dist.barrier()
+        if rank == 0:
+            for p_ in ptrs:
+                capi.device_free(p_)
+
     # ---- reduce over ranks: max time, summed work -------------------------------------------------
     vals = torch.tensor([ms_total, e2e_ms, float(gpu_launches)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -316,6 +375,8 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
             except Exception:
                 pass
+        if gather is not None:
+            line["gather_to_rank0"] = gather
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_reference(3, 1, CPU_SAMPLE)
             line["cpu_baseline"] = cb
