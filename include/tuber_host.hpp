@@ -1,0 +1,468 @@
+// tuber_host.hpp — C++17 host side above the C ABI (include/tuber_b200.h).
+//
+// The reference's host code is Rust; no Rust toolchain exists in this image, so this header is
+// the host-language mirror of the reference interface for the hot path: the same names, argument
+// meaning and error behaviour as
+//
+//   tuber_ecs::ecs::Ecs                    crates/tuber-ecs/src/ecs.rs:56-181
+//   tuber_ecs::query (iteration order, Opt) crates/tuber-ecs/src/query.rs:94-141, 226-245
+//   tuber_ecs::system::SystemBundle        crates/tuber-ecs/src/system.rs:8-24
+//   tuber_core::transform::Transform       crates/tuber-core/src/transform.rs:5-38
+//   tuber_graphics::GraphicsAPI            crates/tuber-graphics/src/lib.rs:34-36
+//
+// Any `'static` type can be a component (type-erased host columns, like the reference). Four
+// component types are *device-visible* — Transform, Sprite, Velocity, Parent — and are mirrored
+// into the tb_ctx columns: structural changes and writes mark index ranges dirty, and the next
+// device call (a device system, render_scene, a device-side query) pushes exactly those ranges
+// with tb_upload_* / tb_upload_presence. After a device system has moved Transforms the host copy
+// is refreshed lazily from the device the next time it is read.
+//
+// Header-only; link with -ltuber_b200. No CPU fallback: Ecs's constructor throws without a B200.
+#ifndef TUBER_HOST_HPP
+#define TUBER_HOST_HPP
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <typeindex>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "tuber_b200.h"
+
+namespace tuber {
+
+using EntityIndex = std::size_t;  // tuber-ecs/src/lib.rs:16
+
+struct Vector3f {
+    float x = 0, y = 0, z = 0;
+};
+
+// tuber_core::transform::Transform (transform.rs:5-22): Default is identity.
+struct Transform {
+    Vector3f translation{0, 0, 0};
+    Vector3f angle{0, 0, 0};
+    Vector3f rotation_center{0, 0, 0};
+    Vector3f scale{1, 1, 1};
+};
+static_assert(sizeof(Transform) == sizeof(tb_transform), "Transform is the 48-byte reference layout");
+
+struct Sprite {  // [SPEC]
+    float width = 0, height = 0;
+    uint32_t texture = 0, layer = 0;
+};
+static_assert(sizeof(Sprite) == sizeof(tb_sprite), "Sprite is 16 bytes");
+
+struct Velocity {  // [SPEC]
+    float x = 0, y = 0, z = 0;
+};
+static_assert(sizeof(Velocity) == sizeof(tb_velocity), "Velocity is 12 bytes");
+
+struct Parent {  // tuber-ecs/src/lib.rs:18-19
+    EntityIndex index = 0;
+};
+
+struct DeltaTime {  // tuber-core/src/lib.rs:13
+    double dt = 0;
+};
+
+// Opt<T> accessor marker (query.rs:226-245): never filters.
+template <class T>
+struct Opt {};
+
+struct Error : std::runtime_error {
+    tb_status status;
+    Error(tb_status s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+
+namespace detail {
+
+template <class T> struct device_component { static constexpr int id = -1; };
+template <> struct device_component<Transform> { static constexpr int id = TB_TRANSFORM; };
+template <> struct device_component<Sprite> { static constexpr int id = TB_SPRITE; };
+template <> struct device_component<Velocity> { static constexpr int id = TB_VELOCITY; };
+template <> struct device_component<Parent> { static constexpr int id = TB_PARENT; };
+
+template <class T> struct accessor { using type = T; static constexpr bool required = true; };
+template <class T> struct accessor<Opt<T>> { using type = T; static constexpr bool required = false; };
+
+// One type-erased component column: ComponentStore (ecs.rs:16-53).
+struct Store {
+    std::vector<std::shared_ptr<void>> data;  // nullptr == None
+    std::vector<uint64_t> bits;               // entities_bitset, bit layout of bitset.rs:15-36
+    bool test(EntityIndex e) const { return e / 64 < bits.size() && ((bits[e / 64] >> (e % 64)) & 1u); }
+    void set(EntityIndex e) {
+        if (e / 64 >= bits.size()) bits.resize(e / 64 + 1, 0);
+        bits[e / 64] |= uint64_t(1) << (e % 64);
+    }
+    void unset(EntityIndex e) {
+        if (e / 64 < bits.size()) bits[e / 64] &= ~(uint64_t(1) << (e % 64));
+    }
+};
+
+struct DirtyRange {
+    EntityIndex lo = SIZE_MAX, hi = 0;  // [lo, hi)
+    void mark(EntityIndex e) {
+        lo = std::min(lo, e);
+        hi = std::max(hi, e + 1);
+    }
+    bool any() const { return lo < hi; }
+    void clear() {
+        lo = SIZE_MAX;
+        hi = 0;
+    }
+};
+
+}  // namespace detail
+
+class Ecs {
+public:
+    // The reference's presence bitset is a fixed [u64; 1024] (ecs.rs:14): 65 536 entities, beyond
+    // which insert panics. `max_entities` is that cap here (insert throws TB_ERR_CAPACITY).
+    explicit Ecs(uint64_t max_entities = 65536, int device = 0) : cap_(max_entities) {
+        tb_status s = tb_ctx_create(device, max_entities, &ctx_);
+        if (s != TB_OK) throw Error(s, std::string("tb_ctx_create: ") + tb_status_string(s));
+    }
+    ~Ecs() { tb_ctx_destroy(ctx_); }
+    Ecs(const Ecs&) = delete;
+    Ecs& operator=(const Ecs&) = delete;
+
+    // ecs.rs:93-98 — returns the new entity's index; indices are never reused.
+    template <class... Cs>
+    EntityIndex insert(Cs... components) {
+        if (next_ >= cap_) throw Error(TB_ERR_CAPACITY, "entity index beyond the presence bitset (the reference panics)");
+        const EntityIndex e = next_++;
+        for (auto& kv : stores_) kv.second.data.push_back(nullptr);  // ecs.rs:194-196
+        (put(e, std::move(components)), ...);
+        count_dirty_ = true;
+        return e;
+    }
+    std::size_t entity_count() const { return next_; }  // ecs.rs:178-180
+
+    // ecs.rs:120-124 — silently does nothing when no store for the type exists yet.
+    template <class C>
+    void add_component(C c, EntityIndex e) {
+        auto it = stores_.find(std::type_index(typeid(C)));
+        if (it == stores_.end() || e >= next_) return;
+        write(it->second, e, std::move(c));
+    }
+    // ecs.rs:114-118
+    template <class C>
+    void remove_component(EntityIndex e) {
+        auto it = stores_.find(std::type_index(typeid(C)));
+        if (it == stores_.end() || e >= next_) return;
+        erase(it->first, it->second, e);
+    }
+    // ecs.rs:105-112
+    void delete_by_ids(const std::vector<EntityIndex>& ids) {
+        for (EntityIndex e : ids)
+            for (auto& kv : stores_)
+                if (e < next_) erase(kv.first, kv.second, e);
+    }
+    // ecs.rs:100-103
+    template <class... As>
+    void delete_by_query() { delete_by_ids(query<As...>()); }
+
+    // ecs.rs:127-129 + query.rs:94-141 — the matching entity indices IN THE REFERENCE'S ITERATION
+    // ORDER (descending: QueryIterator pops matches from the back). Opt<T> accessors never filter;
+    // a required component without a store matches nothing. When every accessor is device-visible
+    // the presence AND and the compaction run on the GPU (tb_query).
+    template <class... As>
+    std::vector<EntityIndex> query() {
+        std::vector<const detail::Store*> req;
+        uint32_t device_bits = 0;
+        bool all_device = true, missing = false;
+        (collect<As>(req, device_bits, all_device, missing), ...);
+        std::vector<EntityIndex> out;
+        if (missing) return out;
+        if (all_device && next_ > 0) {
+            flush();
+            std::vector<uint32_t> idx(next_);
+            uint64_t count = 0;
+            check(tb_query(ctx_, device_bits, idx.data(), idx.size(), &count), "tb_query");
+            out.resize(count);
+            for (uint64_t k = 0; k < count; ++k) out[k] = idx[count - 1 - k];
+            return out;
+        }
+        for (EntityIndex e = next_; e-- > 0;) {
+            bool all = true;
+            for (auto* s : req) all = all && s->test(e);
+            if (all) out.push_back(e);
+        }
+        return out;
+    }
+    // ecs.rs:137-169 — the LOWEST matching index.
+    template <class... As>
+    std::optional<EntityIndex> query_one() {
+        auto ids = query<As...>();
+        if (ids.empty()) return std::nullopt;
+        return ids.back();
+    }
+    // ecs.rs:132-134 — matches whose index is in `ids`, still descending.
+    template <class... As>
+    std::vector<EntityIndex> query_by_ids(const std::unordered_set<EntityIndex>& ids) {
+        std::vector<EntityIndex> out;
+        for (EntityIndex e : query<As...>())
+            if (ids.count(e)) out.push_back(e);
+        return out;
+    }
+
+    // Component access (what the Ref / RefMut guards of query.rs:166-208 give). nullptr == None.
+    template <class C>
+    const C* get(EntityIndex e) {
+        if constexpr (std::is_same_v<C, Transform>) refresh_transforms();
+        auto it = stores_.find(std::type_index(typeid(C)));
+        if (it == stores_.end() || e >= it->second.data.size()) return nullptr;
+        return static_cast<const C*>(it->second.data[e].get());
+    }
+    template <class C>
+    C* get_mut(EntityIndex e) {
+        C* p = const_cast<C*>(get<C>(e));
+        if (p) mark_dirty<C>(e);
+        return p;
+    }
+
+    // ecs.rs:64-86
+    template <class T>
+    void insert_shared_resource(T value) { resources_[std::type_index(typeid(T))] = std::make_shared<T>(std::move(value)); }
+    template <class T>
+    T* shared_resource() {
+        auto it = resources_.find(std::type_index(typeid(T)));
+        return it == resources_.end() ? nullptr : static_cast<T*>(it->second.get());
+    }
+
+    // ---- device side -------------------------------------------------------------------------
+    tb_ctx* ctx() { return ctx_; }
+
+    // Pushes every dirty range of the device-visible columns.
+    void flush() {
+        if (count_dirty_) {
+            check(tb_set_entity_count(ctx_, next_), "tb_set_entity_count");
+            count_dirty_ = false;
+        }
+        push<Transform>();
+        push<Sprite>();
+        push<Velocity>();
+        push<Parent>();
+    }
+    // A device system has written Transforms: host copies are stale until read again.
+    void device_wrote_transforms() { transforms_stale_ = true; }
+
+    void check(tb_status s, const char* what) const {
+        if (s != TB_OK) throw Error(s, std::string(what) + ": " + tb_last_error(ctx_));
+    }
+
+private:
+    template <class C>
+    void put(EntityIndex e, C c) {
+        const std::type_index ty(typeid(C));
+        auto it = stores_.find(ty);
+        if (it == stores_.end()) {  // ecs.rs:199: ComponentStore::with_size(index)
+            it = stores_.emplace(ty, detail::Store{}).first;
+            it->second.data.assign(e + 1, nullptr);
+        }
+        write(it->second, e, std::move(c));
+    }
+    template <class C>
+    void write(detail::Store& s, EntityIndex e, C c) {
+        if (e >= s.data.size()) s.data.resize(e + 1, nullptr);
+        s.data[e] = std::make_shared<C>(std::move(c));
+        s.set(e);
+        mark_dirty<C>(e);
+    }
+    void erase(std::type_index ty, detail::Store& s, EntityIndex e) {
+        if (e < s.data.size()) s.data[e] = nullptr;
+        s.unset(e);
+        for (int k = 0; k < TB_COMPONENT_COUNT; ++k)
+            if (device_type_[k] && *device_type_[k] == ty) presence_dirty_[k].mark(e);
+    }
+    template <class C>
+    void mark_dirty(EntityIndex e) {
+        constexpr int id = detail::device_component<C>::id;
+        if constexpr (id >= 0) {
+            if (!device_type_[id]) device_type_[id] = std::make_unique<std::type_index>(typeid(C));
+            value_dirty_[id].mark(e);
+            presence_dirty_[id].mark(e);
+        }
+    }
+    template <class A>
+    void collect(std::vector<const detail::Store*>& req, uint32_t& bits, bool& all_device, bool& missing) {
+        using T = typename detail::accessor<A>::type;
+        if (!detail::accessor<A>::required) return;  // query.rs:105
+        auto it = stores_.find(std::type_index(typeid(T)));
+        if (it == stores_.end()) {
+            missing = true;  // query.rs:110
+            return;
+        }
+        req.push_back(&it->second);
+        constexpr int id = detail::device_component<T>::id;
+        if constexpr (id >= 0) bits |= 1u << id;
+        else all_device = false;
+    }
+    template <class C>
+    void push() {
+        constexpr int id = detail::device_component<C>::id;
+        auto it = stores_.find(std::type_index(typeid(C)));
+        if (it == stores_.end()) return;
+        detail::Store& s = it->second;
+        if (value_dirty_[id].any()) {
+            const EntityIndex lo = value_dirty_[id].lo, hi = std::min<EntityIndex>(value_dirty_[id].hi, next_);
+            if constexpr (std::is_same_v<C, Parent>) {
+                std::vector<uint32_t> buf(hi - lo, TB_NO_PARENT);
+                for (EntityIndex e = lo; e < hi; ++e)
+                    if (auto* p = static_cast<Parent*>(s.data[e].get())) buf[e - lo] = (uint32_t)p->index;
+                check(tb_upload_parents(ctx_, lo, hi - lo, buf.data()), "tb_upload_parents");
+            } else {
+                std::vector<C> buf(hi - lo);
+                for (EntityIndex e = lo; e < hi; ++e)
+                    if (auto* p = static_cast<C*>(s.data[e].get())) buf[e - lo] = *p;
+                if constexpr (std::is_same_v<C, Transform>)
+                    check(tb_upload_transforms(ctx_, lo, hi - lo, reinterpret_cast<const tb_transform*>(buf.data())), "tb_upload_transforms");
+                else if constexpr (std::is_same_v<C, Sprite>)
+                    check(tb_upload_sprites(ctx_, lo, hi - lo, reinterpret_cast<const tb_sprite*>(buf.data())), "tb_upload_sprites");
+                else
+                    check(tb_upload_velocities(ctx_, lo, hi - lo, reinterpret_cast<const tb_velocity*>(buf.data())), "tb_upload_velocities");
+            }
+            value_dirty_[id].clear();
+        }
+        if (presence_dirty_[id].any()) {
+            // uploads mark whole ranges present: restore the store's own bitset words over the range
+            const uint64_t w0 = presence_dirty_[id].lo / 64, w1 = (std::min<EntityIndex>(presence_dirty_[id].hi, next_) + 63) / 64;
+            if (w1 > w0) {
+                std::vector<uint64_t> words(w1 - w0, 0);
+                for (uint64_t w = w0; w < w1 && w < s.bits.size(); ++w) words[w - w0] = s.bits[w];
+                check(tb_upload_presence(ctx_, id, w0, w1 - w0, words.data()), "tb_upload_presence");
+            }
+            presence_dirty_[id].clear();
+        }
+    }
+    void refresh_transforms() {
+        if (!transforms_stale_) return;
+        transforms_stale_ = false;
+        auto it = stores_.find(std::type_index(typeid(Transform)));
+        if (it == stores_.end() || next_ == 0) return;
+        std::vector<Transform> buf(next_);
+        check(tb_download_transforms(ctx_, 0, next_, reinterpret_cast<tb_transform*>(buf.data())), "tb_download_transforms");
+        for (EntityIndex e = 0; e < next_ && e < it->second.data.size(); ++e)
+            if (auto* p = static_cast<Transform*>(it->second.data[e].get())) *p = buf[e];
+    }
+
+    tb_ctx* ctx_ = nullptr;
+    uint64_t cap_;
+    EntityIndex next_ = 0;
+    std::unordered_map<std::type_index, detail::Store> stores_;             // Components (ecs.rs:11)
+    std::unordered_map<std::type_index, std::shared_ptr<void>> resources_;  // Resources (ecs.rs:12)
+    std::unique_ptr<std::type_index> device_type_[TB_COMPONENT_COUNT];
+    detail::DirtyRange value_dirty_[TB_COMPONENT_COUNT], presence_dirty_[TB_COMPONENT_COUNT];
+    bool count_dirty_ = false, transforms_stale_ = false;
+};
+
+// system.rs:5-6 — Ok(()) is an empty optional, Err(e) carries the message.
+using SystemResult = std::optional<std::string>;
+inline SystemResult Ok() { return std::nullopt; }
+inline SystemResult Err(std::string what) { return what; }
+
+// system.rs:8-24 — boxed systems run in insertion order; the first Err stops the bundle.
+template <class AD>
+class SystemBundle {
+public:
+    using System = std::function<SystemResult(Ecs&, AD&)>;
+    // the four closure shapes IntoSystem accepts (system.rs:32-76)
+    void add_system(System s) { systems_.push_back(std::move(s)); }
+    void add_system(std::function<SystemResult(Ecs&)> s) {
+        systems_.push_back([s](Ecs& e, AD&) { return s(e); });
+    }
+    void add_system(std::function<void(Ecs&, AD&)> s) {
+        systems_.push_back([s](Ecs& e, AD& a) { s(e, a); return Ok(); });
+    }
+    void add_system(std::function<void(Ecs&)> s) {
+        systems_.push_back([s](Ecs& e, AD&) { s(e); return Ok(); });
+    }
+    SystemResult step(Ecs& ecs, AD& additional_data) {
+        for (auto& s : systems_)
+            if (auto err = s(ecs, additional_data)) return err;
+        return Ok();
+    }
+    std::size_t size() const { return systems_.size(); }
+
+private:
+    std::vector<System> systems_;
+};
+
+// [SPEC] the velocity system as a device system: translation += velocity * dt with
+// dt = DeltaTime.0 as f32 (tuber-engine/src/state.rs:81). Queued; fused into the next frame.
+inline SystemResult velocity_system(Ecs& ecs) {
+    DeltaTime* dt = ecs.shared_resource<DeltaTime>();
+    if (!dt) return Err("DeltaTime resource missing");
+    try {
+        ecs.flush();
+        ecs.check(tb_system_integrate(ecs.ctx(), (float)dt->dt), "tb_system_integrate");
+        ecs.device_wrote_transforms();
+    } catch (const Error& e) {
+        return Err(e.what());
+    }
+    return Ok();
+}
+
+// tuber-graphics/src/lib.rs:25-36
+struct GraphicsError {
+    std::string what;
+};
+using GraphicsResult = std::optional<GraphicsError>;  // nullopt == Ok(())
+
+class GraphicsAPI {
+public:
+    virtual ~GraphicsAPI() = default;
+    virtual GraphicsResult render_scene(Ecs& ecs) = 0;
+};
+
+// The batching renderer behind render_scene: leaves instances / vertices / batches on the device
+// in draw order (tb_frame_out) for the presenter.
+class Graphics : public GraphicsAPI {
+public:
+    GraphicsResult render_scene(Ecs& ecs) override {
+        try {
+            ecs.flush();
+            ecs.check(tb_frame_transform_batch(ecs.ctx(), &frame_), "tb_frame_transform_batch");
+        } catch (const Error& e) {
+            return GraphicsError{e.what()};
+        }
+        ecs_ = &ecs;
+        return std::nullopt;
+    }
+    const tb_frame_out& frame() const { return frame_; }
+    std::vector<tb_instance> instances() const {
+        std::vector<tb_instance> v(frame_.num_instances);
+        if (!v.empty()) ecs_->check(tb_download_instances(ecs_->ctx(), 0, v.size(), v.data()), "tb_download_instances");
+        return v;
+    }
+    std::vector<tb_quad_vertex> vertices() const {
+        std::vector<tb_quad_vertex> v(frame_.num_instances * 4);
+        if (!v.empty()) ecs_->check(tb_download_vertices(ecs_->ctx(), 0, frame_.num_instances, v.data()), "tb_download_vertices");
+        return v;
+    }
+    std::vector<tb_batch> batches() const {
+        std::vector<tb_batch> v(frame_.num_batches);
+        if (!v.empty()) ecs_->check(tb_download_batches(ecs_->ctx(), 0, v.size(), v.data()), "tb_download_batches");
+        return v;
+    }
+    std::vector<uint32_t> order() const {
+        std::vector<uint32_t> v(frame_.num_instances);
+        if (!v.empty()) ecs_->check(tb_download_order(ecs_->ctx(), 0, v.size(), v.data()), "tb_download_order");
+        return v;
+    }
+
+private:
+    tb_frame_out frame_{};
+    Ecs* ecs_ = nullptr;
+};
+
+}  // namespace tuber
+
+#endif  // TUBER_HOST_HPP

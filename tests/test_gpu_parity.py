@@ -69,8 +69,7 @@ def test_config3_hierarchy_depth8(random_parents):
     assert g.info.hierarchy_levels == 8
     util.assert_frame_parity(g, r)
     w = ctx.download_world_matrices(0, sc.n)
-    scale = np.abs(r.world).max(axis=1, keepdims=True)
-    util.float_close(w, r.world, scale, "world matrix")
+    util.float_close(w, r.world, np.abs(r.world).max(), "world matrix")  # scale: the scene extent
     ctx.close()
 
 

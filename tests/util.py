@@ -57,7 +57,9 @@ def float_close(g, r, scale, what):
 
 
 def assert_frame_parity(gpu, ref, exact_floats=False):
-    """Integer outputs bit-exact; float outputs within REL_TOL norm-wise per matrix / quad."""
+    """Integer outputs bit-exact; float outputs within REL_TOL norm-wise per matrix / quad.
+    Hierarchy frames: a world translation is a sum of ancestors' terms that can cancel to ~0, so the
+    scale is at least the scene extent (largest entry of any reference world matrix)."""
     assert gpu.info.num_instances == len(ref.order), (gpu.info.num_instances, len(ref.order))
     np.testing.assert_array_equal(gpu.order, ref.order, err_msg="sorted entity order")
     assert gpu.info.num_batches == len(ref.batches), (gpu.info.num_batches, len(ref.batches))
@@ -78,6 +80,8 @@ def assert_frame_parity(gpu, ref, exact_floats=False):
         assert np.array_equal(gv, rv), "vertex positions differ (== comparison)"
         return
     scale = np.abs(rm).max(axis=1, keepdims=True)
+    if getattr(gpu.info, "hierarchy_levels", 0):
+        scale = np.maximum(scale, np.abs(rm).max())
     float_close(gm, rm, scale, "instance model matrix")
     vscale = np.abs(rv).max(axis=(1, 2), keepdims=True)
     float_close(gv, rv, np.maximum(vscale, scale[:, :, None]), "quad vertex position")
