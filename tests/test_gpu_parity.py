@@ -511,3 +511,32 @@ def test_sharded_wide_keys_are_refused_not_wrong():
         c.close()
     for b in bufs:
         capi.device_free(b)
+
+
+# ---- few-bucket frames: the warp-autonomous emit -------------------------------------------------------
+
+@pytest.mark.parametrize("textures,layers,zvals", [(1, 1, 1), (2, 1, 1), (4, 2, 1), (2, 1, 2), (8, 1, 1), (3, 1, 2)])
+def test_few_buckets_all_key_shapes(textures, layers, zvals):
+    """<= 8 buckets made of any mix of layer / texture / z bits, ragged size, sparse sprites"""
+    sc = scenes.config4(n=77_777, seed=50 + textures)
+    i = np.arange(sc.n)
+    sc.sprites["texture"] = i % textures
+    sc.sprites["layer"] = (i // 3) % layers
+    sc.transforms["translation"][:, 2] = (2 + (i // 5) % zvals).astype(np.float32)  # 2.0 / 3.0: one bit apart
+    masks = {capi.TB_SPRITE: util.random_mask(sc.n, 0.85, 21)}
+    for opts in ({}, {"small_emit": 0}, {"interleaved_rows": 1}):
+        ctx, ref, g, r = run_both(sc, masks, ticks=1, **opts)
+        assert g.info.path == capi.TB_PATH_BUCKET
+        util.assert_frame_parity(g, r)
+        ctx.close()
+
+
+def test_few_buckets_hierarchy():
+    sc = scenes.config3(n=50_000, seed=52)
+    sc.sprites["texture"] = np.arange(sc.n) % 3
+    sc.sprites["layer"] = 0
+    sc.transforms["translation"][:, 2] = 0
+    ctx, ref, g, r = run_both(sc)
+    assert g.info.path == capi.TB_PATH_BUCKET and g.info.hierarchy_levels == 8
+    util.assert_frame_parity(g, r)
+    ctx.close()

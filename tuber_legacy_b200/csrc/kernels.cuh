@@ -194,8 +194,9 @@ struct PrepParams {
     uint32_t* hist;        // [kMaxPasses][256]
     uint32_t* lt_hist;     // [1 << ltbits]
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
-    uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per 512-entity emit tile
+    uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per emit tile
     uint32_t emit_tiles;
+    uint32_t emit_tile_shift;  // log2 of the emit tile: 9 (CTA tiles of 512) or 6 (warp tiles of 64)
     uint32_t* key_hist;     // optional [1 << nbits]: histogram over the whole short key (multi-GPU placement)
     FramePlan plan;
 };
@@ -241,6 +242,8 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
             atomicAdd(&sh.hist[0][d], c);
             if (p.tile_counts != nullptr) atomicAdd(&p.tile_counts[(size_t)d * p.emit_tiles + emit_tile], c);
             if (p.key_hist != nullptr) atomicAdd(&p.key_hist[d], c);  // single pass: the digit is the short key
+            if (p.lt_mode == 1) atomicAdd(&sh.lt[d >> p.plan.zbits], c);
+            else if (p.lt_mode == 2) atomicAdd(&p.lt_hist[d >> p.plan.zbits], c);
         }
         return;
     }
@@ -261,7 +264,7 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
 
 // The single-pass few-bucket plan the `small` accounting path serves.
 __device__ __forceinline__ bool prep_small(const PrepParams& p) {
-    return p.have_plan && p.plan.npasses == 1 && p.plan.bits[0] <= 5 && p.lt_mode == 0 && !p.write_keys;
+    return p.have_plan && p.plan.npasses == 1 && p.plan.bits[0] <= 5 && !p.write_keys;
 }
 
 __device__ __forceinline__ void prep_init(const PrepParams& p, PrepShared& sh) {
@@ -376,8 +379,9 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             const uint32_t i = base + k * kThreads;
             uint64_t key = 0;
             if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
-            // this 1024-entity tile is two 512-entity emit tiles
-            prep_account(p, sh, acc, rend[k], key, i, small, tile * 2 + (k >> 1), tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
+            // this 1024-entity tile is two 512-entity emit tiles (shared-memory counts) or
+            // sixteen 64-entity warp tiles (direct global counts of the small path)
+            prep_account(p, sh, acc, rend[k], key, i, small, i >> p.emit_tile_shift, tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
         }
         if (tiles_out) {
             __syncthreads();
@@ -499,19 +503,33 @@ __global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
 
 // First output position of every (digit, tile) of one pass from its per-tile digit counts
 // (reduce-then-scan radix placement: no inter-CTA waiting anywhere). counts and tile_off are
-// digit-major [R][ntiles]; hist is the pass's raw 256-bin digit histogram. Grid (chunks of 1024
-// tiles, R): every block sums the chunks before its own (coalesced, L2-resident) instead of
-// waiting for them.
+// digit-major [R][ntiles]; hist is the pass's raw 256-bin digit histogram. Two launches over a
+// grid of (chunks of 1024 tiles, R): chunk sums, then every block adds the sums of the chunks
+// before its own (a few hundred L2-resident words) and scans its chunk.
+__global__ void __launch_bounds__(1024) tile_chunk_sums_kernel(const uint32_t* __restrict__ counts, uint32_t ntiles,
+                                                                uint32_t nchunks, uint32_t* csum) {
+    __shared__ uint32_t s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    const uint32_t d = blockIdx.y, t = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t v = t < ntiles ? counts[(size_t)d * ntiles + t] : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s, v);
+    __syncthreads();
+    if (threadIdx.x == 0) csum[(size_t)d * nchunks + blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ counts, uint32_t ntiles,
-                                                          const uint32_t* __restrict__ hist, uint32_t* tile_off) {
+                                                          const uint32_t* __restrict__ hist, const uint32_t* __restrict__ csum,
+                                                          uint32_t nchunks, uint32_t* tile_off) {
     __shared__ uint32_t s[1024];
     __shared__ uint32_t s_base;
     const uint32_t d = blockIdx.y, chunk = blockIdx.x;
     const uint32_t* row = counts + (size_t)d * ntiles;
-    // base = all smaller digits (global) + this digit's tiles before the chunk
+    // base = all smaller digits (global) + this digit's chunks before this one
     uint32_t pre = 0;
     for (uint32_t k = threadIdx.x; k < d; k += 1024) pre += hist[k];
-    for (uint32_t t = threadIdx.x; t < chunk * 1024u; t += 1024) pre += row[t];
+    for (uint32_t c = threadIdx.x; c < chunk; c += 1024) pre += csum[(size_t)d * nchunks + c];
     const uint32_t t = chunk * 1024u + threadIdx.x;
     const uint32_t v = t < ntiles ? row[t] : 0u;
     pre = __reduce_add_sync(0xffffffffu, pre);
@@ -913,6 +931,42 @@ __device__ __forceinline__ void make_outputs(const Affine& w, float sw, float sh
     }
 }
 
+// Writes one warp's 32 results (lane i holds the instance and vertices of output position dst)
+// as whole 128-byte lines: staged in the warp's shared buffer, then streamed out 16 bytes per lane.
+// Instances use a 20-word lane stride (conflict-free 128-bit stores; the read-out is linear);
+// vertices a 16-word stride with the chunk index XORed by bits of the lane (conflict-free both ways).
+__device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool live, uint32_t nlive, uint32_t dst,
+                                             const InstanceOut& inst, const float4 (&vtx)[4], float4* instances,
+                                             float4* vertices) {
+    float4* my = stage + lane * kStageF4;
+    if (live) {
+        my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t q = j * 32 + lane;  // 16-byte chunk of the warp's 2560-byte instance stream
+        const uint32_t item = q / 5, part = q - item * 5;
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+        if (item < nlive) st_cs_f4(instances + (size_t)d * 5 + part, stage[q]);
+    }
+    __syncwarp();
+    const uint32_t sw = (lane >> 1) & 3u;
+    if (live) {
+        float4* mv = stage + lane * 4;
+        mv[0 ^ sw] = vtx[0]; mv[1 ^ sw] = vtx[1]; mv[2 ^ sw] = vtx[2]; mv[3 ^ sw] = vtx[3];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t q = j * 32 + lane;
+        const uint32_t item = q >> 2, part = q & 3u;
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+        if (item < nlive) st_cs_f4(vertices + (size_t)d * 4 + part, stage[item * 4 + (part ^ ((item >> 1) & 3u))]);
+    }
+    __syncwarp();
+}
+
 // Final radix pass fused with compose + emit. Persistent CTAs (two per SM) claim 512-position
 // tiles in order from an atomic counter:
 //   1. the tile's rows come into shared memory asynchronously (cp.async, 16-byte chunks into a
@@ -1132,41 +1186,218 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                     st_cs_f4(vp + 3, vtx[3]);
                 }
             } else {
-                const uint32_t nlive = min(32u, cnt - s0);
-                // instances: 32 x 80 B staged lane-major (20-word stride: conflict-free 128-bit
-                // stores), then streamed out as 160 consecutive 16-byte chunks
-                float4* my = stage + lane * kStageF4;
-                if (live) {
-                    my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const uint32_t q = j * 32 + lane;
-                    const uint32_t item = q / 5, part = q - item * 5;
-                    const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
-                    if (item < nlive) st_cs_f4(ep.instances + (size_t)d * 5 + part, stage[q]);
-                }
-                __syncwarp();
-                // vertices: 32 x 64 B in the same buffer (same 20-word stride)
-                if (live) {
-                    my[0] = vtx[0]; my[1] = vtx[1]; my[2] = vtx[2]; my[3] = vtx[3];
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t q = j * 32 + lane;
-                    const uint32_t item = q >> 2, part = q & 3u;
-                    const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
-                    if (item < nlive) st_cs_f4(ep.vertices + (size_t)d * 4 + part, stage[item * kStageF4 + part]);
-                }
-                __syncwarp();
+                staged_store(stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
             }
         }
         rank_reset(rs, ep.pass.bits);
         __syncthreads();  // releases rows[cur], the rank scratch and the tile ring slot for reuse
         cur ^= 1u;
         ring = ring == 2 ? 0 : ring + 1;
+    }
+}
+
+// ---- few-bucket frames: every warp is its own pipeline -----------------------------------------------
+//
+// Single-pass plans with at most 8 buckets (e.g. a particle system with a handful of textures)
+// need no block at all: a warp takes 64 consecutive entities, ranks them with a few ballots in
+// registers, and — because pass A counted the buckets of every 64-entity tile and tile_scan turned
+// the counts into offsets — knows every output position without talking to any other warp. There is
+// not a single block barrier in this kernel; warps drift apart and hide each other's latencies.
+constexpr uint32_t kWarpTile = 64;          // entities per warp step (2 per lane)
+constexpr uint32_t kSmallMaxBits = 3;       // up to 8 buckets: runs of >= 8 instances per warp tile
+
+struct WarpShared {
+    float4 rows[2][kWarpTile * 4];          // 2 x 4 KB: this tile's rows and the prefetched next tile's
+    unsigned long long keys[2][kWarpTile];  // short keys when the pass reads them (hierarchy)
+    float4 stage[32 * kStageF4];            // 2.5 KB staging
+    uint32_t s_dst[kWarpTile];
+    uint8_t s_li[kWarpTile];
+    unsigned long long mbar[2];
+};
+struct SmallShared {
+    WarpShared w[kWarps];
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParams<KeyT> ep) {
+    extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpShared& sm = reinterpret_cast<SmallShared*>(emit_smem_raw)->w[warp];
+    const bool from_world = ep.world != nullptr;
+    const bool keys_given = ep.keys_in != nullptr;
+    const uint32_t n = ep.pass.n;
+    const uint32_t ntiles = ep.pass.ntiles;  // == ceil(n / 64)
+    const uint32_t R = 1u << ep.pass.bits;
+    const bool split = !from_world && ep.rows.stride == 2;
+    const uint32_t sstride = split ? 2u : 4u;
+    const uint32_t boff = split ? 2u * kWarpTile : 2u;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    uint32_t tile = blockIdx.x * kWarps + warp;
+
+    auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0: TMA bulk copies of tile t's rows (and keys)
+        const uint32_t base = t * kWarpTile;
+        const uint32_t cnt = min(kWarpTile, n - base);
+        const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
+        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + kbytes);
+        if (from_world) {
+            bulk_g2s(sm.rows[buf], ep.world + base, cnt * 64u, &sm.mbar[buf]);
+        } else if (split) {
+            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(sm.rows[buf] + 2 * kWarpTile, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+        } else {
+            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+        }
+        if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+    };
+    auto tile_mask = [&](uint32_t t) -> unsigned long long {  // presence of (Transform and Sprite), one word per tile
+        unsigned long long m = ~0ull;
+        if (ep.mask_t) m &= __ldg(ep.mask_t + t);
+        if (ep.mask_s) m &= __ldg(ep.mask_s + t);
+        const uint32_t base = t * kWarpTile;
+        if (n - base < kWarpTile) m &= (1ull << (n - base)) - 1ull;
+        return m;
+    };
+
+    if (lane == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        if (tile < ntiles) fetch(tile, 0);
+    }
+    __syncwarp();
+    unsigned long long pres = tile < ntiles ? tile_mask(tile) : 0ull;
+    uint32_t off = (tile < ntiles && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
+    uint32_t cur = 0, par0 = 0, par1 = 0;
+    for (; tile < ntiles; tile += nwarps) {
+        // prefetch the next tile of this warp: rows by TMA, presence word and bucket offsets in registers
+        const uint32_t next = tile + nwarps;
+        unsigned long long pres_next = 0ull;
+        uint32_t off_next = 0u;
+        if (next < ntiles) {
+            if (lane == 0) fetch(next, cur ^ 1u);
+            pres_next = tile_mask(next);
+            if (lane < R) off_next = __ldg(ep.pass.tile_off + (size_t)lane * ntiles + next);
+        }
+        const float4* rows = sm.rows[cur];
+        const uint32_t base = tile * kWarpTile;
+        mbar_wait(&sm.mbar[cur], cur ? par1 : par0);
+        if (cur) par1 ^= 1u; else par0 ^= 1u;
+        // bucket of this lane's two entities (li = lane and lane + 32)
+        uint32_t digit[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t li = k * 32 + lane;
+            digit[k] = kInvalidDigit;
+            if ((pres >> li) & 1ull) {
+                uint64_t sk;
+                if (keys_given) {
+                    sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
+                } else if (from_world) {
+                    sk = pext_runs(world_key(rows[li * 4 + 2], rows[li * 4 + 3]), ep.plan.pext);
+                } else {
+                    const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
+                    float z;
+                    if (is_planar(a1)) {
+                        z = planar_z(a0, a1);
+                    } else {
+                        Row r;
+                        r.a0 = a0;
+                        r.a1 = a1;
+                        r.b0 = rows[boff + li * sstride];
+                        r.b1 = rows[boff + li * sstride + 1];
+                        z = local_z(r);
+                    }
+                    const uint32_t tl = __float_as_uint(a1.w);
+                    sk = pext_runs(sort_key(tl >> 16, tl & 0xFFFFu, z), ep.plan.pext);
+                }
+                digit[k] = (uint32_t)sk & (R - 1u);
+            }
+        }
+        // stable rank inside the warp tile, in registers: per bucket two ballots
+        uint32_t slot[2] = {0, 0}, dpos[2] = {0, 0};
+        uint32_t run = 0;
+        for (uint32_t d = 0; d < R; ++d) {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, digit[0] == d);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, digit[1] == d);
+            const uint32_t o = __shfl_sync(0xffffffffu, off, d);
+            if (digit[0] == d) {
+                const uint32_t r = __popc(b0 & lt);
+                slot[0] = run + r;
+                dpos[0] = o + r;
+            }
+            if (digit[1] == d) {
+                const uint32_t r = __popc(b0) + __popc(b1 & lt);
+                slot[1] = run + r;
+                dpos[1] = o + r;
+            }
+            run += __popc(b0) + __popc(b1);
+        }
+        const uint32_t cnt = run;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (digit[k] != kInvalidDigit) {
+                sm.s_li[slot[k]] = (uint8_t)(k * 32 + lane);
+                sm.s_dst[slot[k]] = dpos[k] + (ep.remap != nullptr ? __ldg(ep.remap + digit[k]) : 0u);
+            }
+        }
+        __syncwarp();
+        for (uint32_t s0 = 0; s0 < cnt; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            const bool live = s < cnt;
+            uint32_t dst = 0;
+            InstanceOut inst;
+            float4 vtx[4];
+            if (live) {
+                const uint32_t li = sm.s_li[s];
+                dst = sm.s_dst[s];
+                Affine w;
+                float sw, shh;
+                uint32_t tl;
+                if (from_world) {
+                    w.r0 = rows[li * 4];
+                    w.r1 = rows[li * 4 + 1];
+                    w.r2 = rows[li * 4 + 2];
+                    const float4 sv = rows[li * 4 + 3];
+                    sw = sv.x;
+                    shh = sv.y;
+                    tl = __float_as_uint(sv.z);
+                } else {
+                    Row r;
+                    r.a0 = rows[li * sstride];
+                    r.a1 = rows[li * sstride + 1];
+                    r.b0 = rows[boff + li * sstride];
+                    r.b1 = rows[boff + li * sstride + 1];
+                    w = compose_local(r);
+                    sw = r.b1.y;
+                    shh = r.b1.z;
+                    tl = __float_as_uint(r.a1.w);
+                }
+                make_outputs(w, sw, shh, tl, inst, vtx);
+                ep.order[dst] = base + li + ep.global_first;
+                if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
+            }
+            if (!ep.staged) {
+                if (live) {
+                    float4* ip = ep.instances + (size_t)dst * 5;
+                    st_cs_f4(ip, inst.c0);
+                    st_cs_f4(ip + 1, inst.c1);
+                    st_cs_f4(ip + 2, inst.c2);
+                    st_cs_f4(ip + 3, inst.c3);
+                    st_cs_f4(ip + 4, inst.s);
+                    float4* vp = ep.vertices + (size_t)dst * 4;
+                    st_cs_f4(vp, vtx[0]);
+                    st_cs_f4(vp + 1, vtx[1]);
+                    st_cs_f4(vp + 2, vtx[2]);
+                    st_cs_f4(vp + 3, vtx[3]);
+                }
+            } else {
+                staged_store(sm.stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
+            }
+        }
+        __syncwarp();  // every lane is done with rows[cur], s_li, s_dst before they are reused
+        pres = pres_next;
+        off = off_next;
+        cur ^= 1u;
     }
 }
 

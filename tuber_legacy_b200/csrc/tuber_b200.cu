@@ -92,6 +92,7 @@ struct tb_ctx {
     int digit_bits = kMaxDigitBits;
     int staged_emit = 1;
     int tile_offsets = 1;
+    int small_emit = 1;
     int lt_limit = (int)kMaxLtBits;
 
     // hierarchy
@@ -278,18 +279,27 @@ struct ScratchLayout {
     size_t status_off[kMaxPasses];   // look-back words (only with tile_offsets == 0)
     size_t counts_off[kMaxPasses];   // per-tile digit counts  [R][tiles]  (tile_offsets == 1)
     size_t offs_off[kMaxPasses];     // per-tile digit offsets [R][tiles]
+    size_t csum_off[kMaxPasses];     // per-chunk (1024 tiles) sums [R][chunks]
+    uint32_t tile_elems[kMaxPasses];
+    bool small = false;              // last pass runs the warp-autonomous few-bucket emit
     bool tile_offsets = true;
     size_t total_words = 0, alloc_words = 0;
 };
 
-ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets, bool zero_counts0) {
+bool use_small_emit(const tb_ctx* c, const FramePlan& plan) {
+    return c->tile_offsets != 0 && c->small_emit != 0 && plan.npasses == 1 && plan.bits[0] <= kSmallMaxBits;
+}
+
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets, bool zero_counts0,
+                             bool small = false) {
     ScratchLayout L;
     L.tile_offsets = tile_offsets;
+    L.small = small;
     size_t off = kHdrWords;
     L.lt_off = off;
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
     off += L.lt_words;
-    const uint32_t last_tile = kThreads * kEmitItems;
+    const uint32_t last_tile = small ? kWarpTile : kThreads * kEmitItems;
     if (tile_offsets && zero_counts0) {
         // the key pass accumulates pass-0 per-tile counts with REDs: they start from zero
         L.counts_off[0] = off;
@@ -297,7 +307,8 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
     }
     for (uint32_t p = 0; p < plan.npasses; ++p) {
         const bool last = p + 1 == plan.npasses;
-        const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
+        const uint32_t tile = last ? last_tile : kThreads * kScatterItems;
+        L.tile_elems[p] = tile;
         L.tiles[p] = div_up(n, tile);
         L.status_off[p] = off;
         if (!tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
@@ -310,6 +321,8 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
         }
         L.offs_off[p] = off;
         if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        L.csum_off[p] = off;
+        if (tile_offsets) off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
     }
     L.alloc_words = off;
     return L;
@@ -415,12 +428,14 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     const uint32_t tile = kThreads * kScatterItems;
     const uint32_t tiles = div_up(n, tile);
     size_t words = kHdrWords;
-    size_t counts_off[kMaxPasses], offs_off[kMaxPasses];
+    size_t counts_off[kMaxPasses], offs_off[kMaxPasses], csum_off[kMaxPasses];
     for (uint32_t p = 0; p < ds.npasses; ++p) {
         counts_off[p] = words;
         words += (size_t)tiles << ds.bits[p];
         offs_off[p] = words;
         words += (size_t)tiles << ds.bits[p];
+        csum_off[p] = words;
+        words += (size_t)div_up(tiles, 1024) << ds.bits[p];
     }
     s = ensure_scratch(c, words);
     if (s) return s;
@@ -435,8 +450,15 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
         uint32_t* offs = c->scratch + offs_off[p];
         TB_LAUNCH(c, "tile_hist", 0, tile_hist_kernel<uint32_t>, tiles, kThreads, 0, kin, n, (const unsigned long long*)nullptr,
                   (const uint64_t*)nullptr, (const uint64_t*)nullptr, 0u, tile, ds.shift[p], ds.bits[p], tiles, counts);
-        TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(div_up(tiles, 1024), 1u << ds.bits[p]), 1024, 0, counts, tiles,
-                  hist + p * 256, offs);
+        {
+            const uint32_t nchunks = div_up(tiles, 1024);
+            uint32_t* csum = c->scratch + csum_off[p];
+            if (nchunks > 1)
+                TB_LAUNCH(c, "tile_chunk_sums", 0, tile_chunk_sums_kernel, dim3(nchunks, 1u << ds.bits[p]), 1024, 0, counts, tiles,
+                          nchunks, csum);
+            TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(nchunks, 1u << ds.bits[p]), 1024, 0, counts, tiles, hist + p * 256,
+                      (const uint32_t*)csum, nchunks, offs);
+        }
         ScatterParams<uint32_t> sp{};
         sp.pass.n = n;
         sp.pass.count_ptr = nullptr;
@@ -621,6 +643,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
         if (L->tile_offsets && !fm.hier && c->plan.npasses == 1) {
             p.tile_counts = c->scratch + L->counts_off[0];
             p.emit_tiles = L->tiles[0];
+            p.emit_tile_shift = L->small ? 6u : 9u;
         }
     }
     const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 32 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
@@ -670,7 +693,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     int cur = 1;
     for (uint32_t p = 0; p < plan.npasses; ++p) {
         const bool last = p + 1 == plan.npasses;
-        const uint32_t tile = kThreads * (last ? kEmitItems : kScatterItems);
+        const uint32_t tile = L.tile_elems[p];
         PassParams pp{};
         pp.n = n;  // passes after the first only hold the renderables: bounded by the device-side count
         pp.count_ptr = iin ? d_count : nullptr;
@@ -687,8 +710,13 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                 TB_LAUNCH(c, "tile_hist", (uint64_t)n * kb, tile_hist_kernel<KeyT>, L.tiles[p], kThreads, 0, kin, n, pp.count_ptr,
                           mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_SPRITE), iin ? 0u : 1u, tile, pp.shift, pp.bits,
                           L.tiles[p], counts);
-            TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(div_up(L.tiles[p], 1024), 1u << pp.bits), 1024, 0, counts,
-                      L.tiles[p], hist + p * 256, offs);
+            const uint32_t nchunks = div_up(L.tiles[p], 1024);
+            uint32_t* csum = c->scratch + L.csum_off[p];
+            if (nchunks > 1)
+                TB_LAUNCH(c, "tile_chunk_sums", 0, tile_chunk_sums_kernel, dim3(nchunks, 1u << pp.bits), 1024, 0, counts, L.tiles[p],
+                          nchunks, csum);
+            TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(nchunks, 1u << pp.bits), 1024, 0, counts, L.tiles[p], hist + p * 256,
+                      (const uint32_t*)csum, nchunks, offs);
             pp.tile_off = offs;
         }
         if (!last) {
@@ -722,8 +750,13 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             ep.global_first = (uint32_t)c->global_first;
             ep.staged = c->staged_emit;
             ep.remap = c->shard_state == 4 ? c->remap : nullptr;
-            TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
-                      std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared), ep);
+            if (L.small && iin == nullptr) {
+                TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0)), emit_small_kernel<KeyT>,
+                          std::min<uint32_t>(div_up(L.tiles[p], kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
+            } else {
+                TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
+                          std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared), ep);
+            }
         }
     }
     return TB_OK;
@@ -805,6 +838,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->rows.stride = c->interleaved ? 4 : 2;
     cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         tb_ctx_destroy(c);
         return TB_ERR_CUDA;
@@ -875,6 +910,8 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->rows.stride = c->interleaved ? 4 : 2;
     } else if (k == "staged_emit") {
         c->staged_emit = value != 0;
+    } else if (k == "small_emit") {
+        c->small_emit = value != 0;
     } else if (k == "tile_offsets") {
         c->tile_offsets = value != 0;
     } else if (k == "digit_bits") {
@@ -1217,7 +1254,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
         const bool prepare_made_counts = c->tile_offsets != 0 && !fm.hier && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0, prepare_made_counts);
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
         if (fm.lt_generic) {
@@ -1354,7 +1391,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
         const uint64_t n = c->n;
         FrameMode fm{};  // flat; the batch table comes from the global bins, not from pass A
         const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts);
+        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
         TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
@@ -1416,7 +1453,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     if (c->shard_count > 0) {
         FrameMode fm{};
         const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts);
+        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         uint32_t* hist = c->scratch + kHdrHist;
         if (!L.tile_offsets) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
