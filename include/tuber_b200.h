@@ -136,6 +136,9 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
  *   "tile_offsets"     0|1  single-pass flat frames place tiles from per-tile counts made by the
  *                           key pass instead of a decoupled look-back (default 1)
+ *   "static_buckets"   0|1  flat few-bucket scenes whose buckets depend on the Sprite only (no varying z
+ *                           bit) reuse the per-tile offsets of the last full frame until a component is
+ *                           uploaded: the steady-state frame is one kernel, validated every frame (default 1)
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
  *   "lt_limit"         0..16 widest (layer, texture) histogram kept as direct bins (default 16);

@@ -540,3 +540,68 @@ def test_few_buckets_hierarchy():
     assert g.info.path == capi.TB_PATH_BUCKET and g.info.hierarchy_levels == 8
     util.assert_frame_parity(g, r)
     ctx.close()
+
+
+# ---- single-kernel steady-state frames (cached per-tile bucket offsets) -------------------------------
+
+def test_static_bucket_frames_are_one_kernel_and_stay_exact():
+    sc = scenes.config4(n=150_001, seed=60)
+    masks = {capi.TB_VELOCITY: util.random_mask(sc.n, 0.7, 31), capi.TB_SPRITE: util.random_mask(sc.n, 0.9, 32)}
+    ctx = util.make_ctx(sc, masks)
+    ref = util.make_oracle(sc, masks)
+    launches = []
+    for _ in range(4):
+        ctx.system_integrate(sc.dt)
+        ref.step(sc.dt)
+        g = util.GpuFrame(ctx)
+        util.assert_frame_parity(g, ref.frame())
+        launches.append(g.info.kernel_launches)
+    assert launches[0] > 1 and launches[1:] == [1, 1, 1], launches   # full frame once, then one kernel per frame
+    t = ctx.download_transforms(0, sc.n)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
+    # any component upload drops the cached offsets: textures change -> buckets change -> still exact
+    sc.sprites["texture"][::3] = 3 - sc.sprites["texture"][::3]
+    ctx.upload_sprites(0, sc.sprites)
+    ctx.upload_presence(capi.TB_SPRITE, 0, masks[capi.TB_SPRITE])
+    ref2 = oracle.Scene(sc.n, t, sc.sprites, sc.velocities, mask_sprite=masks[capi.TB_SPRITE], mask_velocity=masks[capi.TB_VELOCITY])
+    g = util.GpuFrame(ctx)
+    assert g.info.kernel_launches > 1
+    util.assert_frame_parity(g, ref2.frame())
+    ctx.system_integrate(sc.dt)
+    ref2.step(sc.dt)
+    g = util.GpuFrame(ctx)
+    assert g.info.kernel_launches == 1
+    util.assert_frame_parity(g, ref2.frame())
+    # the option switches it off without changing results
+    ctx.set_option("static_buckets", 0)
+    ctx.system_integrate(sc.dt)
+    ref2.step(sc.dt)
+    g = util.GpuFrame(ctx)
+    assert g.info.kernel_launches > 1
+    util.assert_frame_parity(g, ref2.frame())
+    ctx.close()
+
+
+def test_static_bucket_frame_detects_a_z_change():
+    """the cached plan says z is constant; a tick moves z of some entities: the single-kernel frame's own
+    statistics expose it, the frame is redone the long way, and the tick is still applied exactly once"""
+    sc = scenes.config4(n=60_000, seed=61)
+    ctx = util.make_ctx(sc)
+    ref = util.make_oracle(sc)
+    for _ in range(2):
+        ctx.system_integrate(sc.dt)
+        ref.step(sc.dt)
+        g = util.GpuFrame(ctx)
+    assert g.info.kernel_launches == 1
+    v = sc.velocities.copy()
+    v["v"][::11, 2] = 50.0
+    ctx.upload_velocities(0, v)   # velocities do not touch placement: the cached offsets survive this upload
+    ref3 = oracle.Scene(sc.n, ctx.download_transforms(0, sc.n), sc.sprites, v)
+    ctx.system_integrate(sc.dt)
+    ref3.step(sc.dt)
+    g = util.GpuFrame(ctx)
+    assert g.info.replanned == 1 and g.info.kernel_launches > 1
+    util.assert_frame_parity(g, ref3.frame())
+    t = ctx.download_transforms(0, sc.n)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref3.transforms().view(np.uint32))
+    ctx.close()

@@ -850,6 +850,13 @@ struct EmitParams {
     uint32_t staged;         // stage outputs through shared memory for full-line stores
     const uint32_t* remap;   // optional [1 << nbits]: added to the shard-local position of every element
                              // with that short key -> position in the global (all ranks) draw order
+    // single-kernel frames (emit_small_kernel<KeyT, true>): the velocity system and the key
+    // statistics run inside the emit, placement comes from the cached per-tile offsets
+    const float* vel;
+    const uint64_t* mask_v;
+    float dt;
+    uint32_t integrate;
+    unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
 };
 
 constexpr int kEmitItems = 2;
@@ -1209,6 +1216,7 @@ constexpr uint32_t kSmallMaxBits = 3;       // up to 8 buckets: runs of >= 8 ins
 struct WarpShared {
     float4 rows[2][kWarpTile * 4];          // 2 x 4 KB: this tile's rows and the prefetched next tile's
     unsigned long long keys[2][kWarpTile];  // short keys when the pass reads them (hierarchy)
+    float4 vel[2][kWarpTile * 3 / 4];       // velocities of the tile (single-kernel frames)
     float4 stage[32 * kStageF4];            // 2.5 KB staging
     uint32_t s_dst[kWarpTile];
     uint8_t s_li[kWarpTile];
@@ -1218,11 +1226,18 @@ struct SmallShared {
     WarpShared w[kWarps];
 };
 
-template <typename KeyT>
+// FUSED: the whole frame in this one kernel. When the bucket of an entity depends only on its
+// Sprite (the plan has no varying z bit), per-tile bucket offsets stay valid from frame to frame
+// until a component is uploaded, so the steady-state frame needs no separate key pass: this kernel
+// also runs the velocity system (writing sector A back), and accumulates the key statistics with
+// which the host validates, every frame, that the cached plan and offsets still hold.
+template <typename KeyT, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpShared& sm = reinterpret_cast<SmallShared*>(emit_smem_raw)->w[warp];
+    const bool do_int = FUSED && ep.integrate && ep.vel != nullptr;
+    PrepAcc acc;
     const bool from_world = ep.world != nullptr;
     const bool keys_given = ep.keys_in != nullptr;
     const uint32_t n = ep.pass.n;
@@ -1239,7 +1254,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         const uint32_t base = t * kWarpTile;
         const uint32_t cnt = min(kWarpTile, n - base);
         const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
-        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + kbytes);
+        const uint32_t vbytes = do_int ? ((cnt * 12u + 15u) & ~15u) : 0u;
+        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + kbytes + vbytes);
         if (from_world) {
             bulk_g2s(sm.rows[buf], ep.world + base, cnt * 64u, &sm.mbar[buf]);
         } else if (split) {
@@ -1249,13 +1265,20 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
         }
         if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+        if (do_int) bulk_g2s(sm.vel[buf], ep.vel + (size_t)base * 3, vbytes, &sm.mbar[buf]);
     };
-    auto tile_mask = [&](uint32_t t) -> unsigned long long {  // presence of (Transform and Sprite), one word per tile
-        unsigned long long m = ~0ull;
-        if (ep.mask_t) m &= __ldg(ep.mask_t + t);
+    // presence words of one tile: (Transform and Sprite) = renderable; (Transform and Velocity) = moved by the tick
+    auto tile_mask = [&](uint32_t t, unsigned long long& moving) -> unsigned long long {
+        const unsigned long long mt = ep.mask_t ? __ldg(ep.mask_t + t) : ~0ull;
+        unsigned long long m = mt;
         if (ep.mask_s) m &= __ldg(ep.mask_s + t);
+        moving = 0ull;
+        if (do_int) moving = ep.mask_v ? (mt & __ldg(ep.mask_v + t)) : mt;
         const uint32_t base = t * kWarpTile;
-        if (n - base < kWarpTile) m &= (1ull << (n - base)) - 1ull;
+        if (n - base < kWarpTile) {
+            m &= (1ull << (n - base)) - 1ull;
+            moving &= (1ull << (n - base)) - 1ull;
+        }
         return m;
     };
 
@@ -1265,7 +1288,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         if (tile < ntiles) fetch(tile, 0);
     }
     __syncwarp();
-    unsigned long long pres = tile < ntiles ? tile_mask(tile) : 0ull;
+    unsigned long long moving = 0ull, moving_next = 0ull;
+    unsigned long long pres = tile < ntiles ? tile_mask(tile, moving) : 0ull;
     uint32_t off = (tile < ntiles && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
     uint32_t cur = 0, par0 = 0, par1 = 0;
     for (; tile < ntiles; tile += nwarps) {
@@ -1275,13 +1299,30 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         uint32_t off_next = 0u;
         if (next < ntiles) {
             if (lane == 0) fetch(next, cur ^ 1u);
-            pres_next = tile_mask(next);
+            pres_next = tile_mask(next, moving_next);
             if (lane < R) off_next = __ldg(ep.pass.tile_off + (size_t)lane * ntiles + next);
         }
-        const float4* rows = sm.rows[cur];
+        float4* rows = sm.rows[cur];
         const uint32_t base = tile * kWarpTile;
         mbar_wait(&sm.mbar[cur], cur ? par1 : par0);
         if (cur) par1 ^= 1u; else par0 ^= 1u;
+        if (do_int) {
+            // the velocity system on this tile: translation += velocity * dt, in shared memory (the
+            // compose below reads it) and written back to sector A
+            const float* vel = reinterpret_cast<const float*>(sm.vel[cur]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t li = k * 32 + lane;
+                if ((moving >> li) & 1ull) {
+                    float4 a0 = rows[li * sstride];
+                    a0.x = addr(a0.x, mulr(vel[li * 3], ep.dt));
+                    a0.y = addr(a0.y, mulr(vel[li * 3 + 1], ep.dt));
+                    a0.z = addr(a0.z, mulr(vel[li * 3 + 2], ep.dt));
+                    rows[li * sstride] = a0;
+                    ep.rows.a[(size_t)(base + li) * ep.rows.stride] = a0;
+                }
+            }
+        }
         // bucket of this lane's two entities (li = lane and lane + 32)
         uint32_t digit[2];
 #pragma unroll
@@ -1308,7 +1349,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                         z = local_z(r);
                     }
                     const uint32_t tl = __float_as_uint(a1.w);
-                    sk = pext_runs(sort_key(tl >> 16, tl & 0xFFFFu, z), ep.plan.pext);
+                    const uint64_t key = sort_key(tl >> 16, tl & 0xFFFFu, z);
+                    if (FUSED) {
+                        acc.k_or |= key;
+                        acc.k_and &= key;
+                        acc.count += 1;
+                    }
+                    sk = pext_runs(key, ep.plan.pext);
                 }
                 digit[k] = (uint32_t)sk & (R - 1u);
             }
@@ -1396,8 +1443,22 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         }
         __syncwarp();  // every lane is done with rows[cur], s_li, s_dst before they are reused
         pres = pres_next;
+        moving = moving_next;
         off = off_next;
         cur ^= 1u;
+    }
+    if (FUSED) {
+        // key statistics of everything this warp emitted: the host validates the cached plan with them
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc.k_or);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc.k_or >> 32));
+        const uint32_t nlo = __reduce_or_sync(0xffffffffu, ~(uint32_t)acc.k_and);
+        const uint32_t nhi = __reduce_or_sync(0xffffffffu, ~(uint32_t)(acc.k_and >> 32));
+        const uint32_t c = __reduce_add_sync(0xffffffffu, acc.count);
+        if (lane == 0 && c) {
+            atomicOr(&ep.stats[0], ((unsigned long long)hi << 32) | lo);
+            atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
+            atomicAdd(&ep.stats[2], (unsigned long long)c);
+        }
     }
 }
 

@@ -88,6 +88,12 @@ struct tb_ctx {
     // plan
     FramePlan plan{};
     bool plan_valid = false;
+    // single-kernel steady-state frames: per-tile bucket offsets cached from the last full frame
+    bool static_valid = false;
+    int static_buckets = 1;
+    uint64_t static_count = 0, static_batches = 0;
+    size_t static_offs_off = 0;
+    uint32_t static_tiles = 0;
     uint32_t force_path = TB_PATH_NONE;
     int digit_bits = kMaxDigitBits;
     int staged_emit = 1;
@@ -345,6 +351,7 @@ tb_status ensure_scratch(tb_ctx* c, size_t words) {
     }
     c->scratch = (uint32_t*)q;
     c->scratch_words = want;
+    c->static_valid = false;  // cached tile offsets lived in the old buffer
     return TB_OK;
 }
 
@@ -609,6 +616,7 @@ void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and) {
         }
     }
     c->plan_valid = true;
+    c->static_valid = false;
 }
 
 struct FrameMode {
@@ -751,7 +759,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             ep.staged = c->staged_emit;
             ep.remap = c->shard_state == 4 ? c->remap : nullptr;
             if (L.small && iin == nullptr) {
-                TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0)), emit_small_kernel<KeyT>,
+                TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0)), (emit_small_kernel<KeyT, false>),
                           std::min<uint32_t>(div_up(L.tiles[p], kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
             } else {
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
@@ -759,6 +767,44 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             }
         }
     }
+    return TB_OK;
+}
+
+// The steady-state frame of a flat few-bucket scene whose buckets depend on the Sprite only: one
+// kernel (velocity system + key statistics + rank + compose + emit) placed by the tile offsets the
+// last full frame left in the scratch buffer. Returns true in *ok when the frame's own statistics
+// confirm the cached plan; otherwise the caller falls back to the full frame (the velocity system
+// has already run exactly once either way).
+tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+    *ok = false;
+    const uint32_t n = (uint32_t)c->n;
+    const FramePlan& plan = c->plan;
+    TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrNumBatches * 4, c->stream));
+    EmitParams<uint32_t> ep{};
+    ep.pass.n = n;
+    ep.pass.shift = plan.shift[0];
+    ep.pass.bits = plan.bits[0];
+    ep.pass.tile_off = c->scratch + c->static_offs_off;
+    ep.pass.ntiles = c->static_tiles;
+    ep.mask_t = mask_or_null(c, TB_TRANSFORM);
+    ep.mask_s = mask_or_null(c, TB_SPRITE);
+    ep.rows = c->rows;
+    ep.plan = plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    ep.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
+    ep.mask_v = mask_or_null(c, TB_VELOCITY);
+    ep.dt = c->pending_dt;
+    ep.integrate = integrate && ep.vel != nullptr;
+    ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 32 : 0)), (emit_small_kernel<uint32_t, true>),
+              std::min<uint32_t>(div_up(c->static_tiles, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
+    tb_status s = read_header(c);
+    if (s) return s;
+    *ok = c->h_hdr[2] == c->static_count && plan_covers(plan, c->h_hdr[0], ~c->h_hdr[1]);
     return TB_OK;
 }
 
@@ -838,8 +884,9 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->rows.stride = c->interleaved ? 4 : 2;
     cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
-    cudaFuncSetAttribute(emit_small_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
-    cudaFuncSetAttribute(emit_small_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         tb_ctx_destroy(c);
         return TB_ERR_CUDA;
@@ -910,7 +957,11 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->rows.stride = c->interleaved ? 4 : 2;
     } else if (k == "staged_emit") {
         c->staged_emit = value != 0;
+    } else if (k == "static_buckets") {
+        c->static_buckets = value != 0;
+        c->static_valid = false;
     } else if (k == "small_emit") {
+        c->static_valid = false;
         c->small_emit = value != 0;
     } else if (k == "tile_offsets") {
         c->tile_offsets = value != 0;
@@ -918,10 +969,12 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
         c->digit_bits = (int)value;
         c->plan_valid = false;
+    c->static_valid = false;
     } else if (k == "lt_limit") {
         if (value < 0 || value > (int64_t)kMaxLtBits) return fail(c, TB_ERR_INVALID, "lt_limit must be 0..16");
         c->lt_limit = (int)value;
         c->plan_valid = false;
+    c->static_valid = false;
     } else {
         return fail(c, TB_ERR_INVALID, "unknown option " + k);
     }
@@ -955,6 +1008,7 @@ tb_status tb_set_entity_count(tb_ctx* c, uint64_t n) {
     }
     c->n = n;
     c->plan_valid = false;
+    c->static_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -997,6 +1051,7 @@ tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_t
     c->store[TB_TRANSFORM] = true;
     mark_presence(c, TB_TRANSFORM, first, n, 1);
     c->plan_valid = false;
+    c->static_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1018,6 +1073,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     c->store[TB_SPRITE] = true;
     mark_presence(c, TB_SPRITE, first, n, 1);
     c->plan_valid = false;
+    c->static_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
@@ -1036,8 +1092,9 @@ tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_v
     if (s || n == 0) return s;
     if ((s = flush_integrate(c))) return s;
     if (!c->vel) {
-        TB_CUDA(c, cudaMalloc((void**)&c->vel, c->cap * sizeof(tb_velocity)));
-        TB_CUDA(c, cudaMemsetAsync(c->vel, 0, c->cap * sizeof(tb_velocity), c->stream));
+        // +16 bytes: tiles of velocities are fetched in 16-byte multiples
+        TB_CUDA(c, cudaMalloc((void**)&c->vel, c->cap * sizeof(tb_velocity) + 16));
+        TB_CUDA(c, cudaMemsetAsync(c->vel, 0, c->cap * sizeof(tb_velocity) + 16, c->stream));
     }
     TB_CUDA(c, cudaMemcpyAsync(c->vel + first * 3, src, n * sizeof(tb_velocity), cudaMemcpyHostToDevice, c->stream));
     c->store[TB_VELOCITY] = true;
@@ -1062,6 +1119,7 @@ tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_
     }
     c->levels_dirty = true;
     c->plan_valid = false;
+    c->static_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -1077,6 +1135,7 @@ tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t 
     TB_CUDA(c, cudaMemcpyAsync(c->mask[comp] + first_word, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
     c->store[comp] = true;
     c->plan_valid = false;
+    c->static_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1201,6 +1260,7 @@ tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
     if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
     c->force_path = path;
     c->plan_valid = false;
+    c->static_valid = false;
     return TB_OK;
 }
 
@@ -1236,7 +1296,19 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     c->pending = false;
     uint32_t replanned = 0;
     uint64_t count = 0, num_batches = 0;
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    bool fast_done = false;
+    if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
+        if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
+        integrate = false;
+        if (fast_done) {
+            count = c->static_count;
+            num_batches = c->static_batches;
+        } else {
+            c->static_valid = false;  // e.g. a velocity moved z: fall back to the full frame below
+            replanned = 1;
+        }
+    }
+    for (int attempt = 0; attempt < 4 && !fast_done; ++attempt) {
         if (!c->plan_valid) {
             // discovery: key statistics only (and the velocity system, exactly once)
             TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
@@ -1300,6 +1372,16 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if ((s = read_header(c))) return s;
         }
         num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
+        // buckets that depend on the Sprite only (no varying z bit): the tile offsets stay valid until
+        // a component changes, so the next frames can run as one kernel
+        if (c->static_buckets && L.small && L.tile_offsets && !fm.hier && !fm.lt_generic && plan.zbits == 0 && !plan.key64 &&
+            num_batches <= c->max_batches) {
+            c->static_valid = true;
+            c->static_count = count;
+            c->static_batches = num_batches;
+            c->static_offs_off = L.offs_off[0];
+            c->static_tiles = L.tiles[0];
+        }
         break;
     }
     cudaError_t e = cudaGetLastError();
@@ -1371,7 +1453,8 @@ tb_status tb_shard_plan(tb_ctx* c, const uint64_t g[3], uint64_t* nbins) {
         return TB_OK;
     }
     build_frame_plan(g[0], ~g[1], &c->plan);
-    c->plan_valid = false;  // a later single-GPU frame re-plans for itself
+    c->plan_valid = false;
+    c->static_valid = false;  // a later single-GPU frame re-plans for itself
     if (c->plan.pext.nbits > TB_SHARD_MAX_KEY_BITS)
         return fail(c, TB_ERR_UNSUPPORTED, "sort key too wide for histogram placement across GPUs");
     if ((int)c->plan.ltbits > (int)kMaxLtBits) return fail(c, TB_ERR_UNSUPPORTED, "too many (layer, texture) bins");
