@@ -1267,19 +1267,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
         if (do_int) bulk_g2s(sm.vel[buf], ep.vel + (size_t)base * 3, vbytes, &sm.mbar[buf]);
     };
-    // presence words of one tile: (Transform and Sprite) = renderable; (Transform and Velocity) = moved by the tick
-    auto tile_mask = [&](uint32_t t, unsigned long long& moving) -> unsigned long long {
-        const unsigned long long mt = ep.mask_t ? __ldg(ep.mask_t + t) : ~0ull;
-        unsigned long long m = mt;
-        if (ep.mask_s) m &= __ldg(ep.mask_s + t);
-        moving = 0ull;
-        if (do_int) moving = ep.mask_v ? (mt & __ldg(ep.mask_v + t)) : mt;
-        const uint32_t base = t * kWarpTile;
-        if (n - base < kWarpTile) {
-            m &= (1ull << (n - base)) - 1ull;
-            moving &= (1ull << (n - base)) - 1ull;
-        }
-        return m;
+    // Presence words of a tile, prefetched one tile ahead WITHOUT being consumed: lane 0 holds the
+    // Transform word, lane 1 the Sprite word, lane 2 the Velocity word; they are combined (by shuffle)
+    // only when the tile is processed, so the loads never stall the warp.
+    auto load_raw = [&](uint32_t t) -> unsigned long long {
+        const uint64_t* src = lane == 0 ? ep.mask_t : lane == 1 ? ep.mask_s : (lane == 2 && do_int) ? ep.mask_v : nullptr;
+        return src != nullptr ? __ldg(src + t) : ~0ull;
     };
 
     if (lane == 0) {
@@ -1288,24 +1281,27 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         if (tile < ntiles) fetch(tile, 0);
     }
     __syncwarp();
-    unsigned long long moving = 0ull, moving_next = 0ull;
-    unsigned long long pres = tile < ntiles ? tile_mask(tile, moving) : 0ull;
+    unsigned long long raw = tile < ntiles ? load_raw(tile) : 0ull, raw_next = 0ull;
     uint32_t off = (tile < ntiles && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
     uint32_t cur = 0, par0 = 0, par1 = 0;
     for (; tile < ntiles; tile += nwarps) {
         // prefetch the next tile of this warp: rows by TMA, presence word and bucket offsets in registers
         const uint32_t next = tile + nwarps;
-        unsigned long long pres_next = 0ull;
         uint32_t off_next = 0u;
         if (next < ntiles) {
             if (lane == 0) fetch(next, cur ^ 1u);
-            pres_next = tile_mask(next, moving_next);
+            raw_next = load_raw(next);
             if (lane < R) off_next = __ldg(ep.pass.tile_off + (size_t)lane * ntiles + next);
         }
         float4* rows = sm.rows[cur];
         const uint32_t base = tile * kWarpTile;
         mbar_wait(&sm.mbar[cur], cur ? par1 : par0);
         if (cur) par1 ^= 1u; else par0 ^= 1u;
+        // (Transform and Sprite) = renderable; (Transform and Velocity) = moved by the tick
+        const unsigned long long tail = (n - base < kWarpTile) ? ((1ull << (n - base)) - 1ull) : ~0ull;
+        const unsigned long long mt = __shfl_sync(0xffffffffu, raw, 0);
+        const unsigned long long pres = mt & __shfl_sync(0xffffffffu, raw, 1) & tail;
+        const unsigned long long moving = do_int ? (mt & __shfl_sync(0xffffffffu, raw, 2) & tail) : 0ull;
         if (do_int) {
             // the velocity system on this tile: translation += velocity * dt, in shared memory (the
             // compose below reads it) and written back to sector A
@@ -1442,8 +1438,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             }
         }
         __syncwarp();  // every lane is done with rows[cur], s_li, s_dst before they are reused
-        pres = pres_next;
-        moving = moving_next;
+        raw = raw_next;
         off = off_next;
         cur ^= 1u;
     }
