@@ -1,0 +1,642 @@
+// The last radix pass fused with compose + instance / quad-vertex emission:
+//   emit_kernel        persistent CTAs over 512-position tiles, any plan (multi-pass frames gather rows)
+//   emit_small_kernel  single-pass plans with <= 8 buckets: every warp is its own TMA-fed pipeline,
+//                      no block barrier; the FUSED variant is the whole steady-state frame in one kernel
+#pragma once
+#include "placement.cuh"
+
+namespace tb {
+
+// ---- final pass fused with compose + emit -------------------------------------------------------
+
+struct InstanceOut {
+    float4 c0, c1, c2, c3, s;  // column-major model (matrix.rs:219-251) + {size.w, size.h, texture, layer}
+};
+static_assert(sizeof(InstanceOut) == 80, "instance is 80 bytes");
+
+template <typename KeyT>
+struct EmitParams {
+    PassParams pass;
+    const KeyT* keys_in;     // nullptr when `first` and keys are recomputed from the rows
+    const uint32_t* idx_in;  // nullptr: the entity is the position (single-pass plans)
+    const uint64_t* mask_t;
+    const uint64_t* mask_s;
+    RowView rows;
+    const WorldRow* world;   // non-null: hierarchy path, world rows instead of composing
+    FramePlan plan;
+    float4* instances;       // 5 float4 per position
+    float4* vertices;        // 4 float4 per position
+    uint32_t* order;         // entity per position
+    uint32_t* texlayer;      // optional per-position texture|layer<<16 (generic batch path)
+    uint32_t global_first;   // added to the entity ids written to `order`
+    uint32_t staged;         // stage outputs through shared memory for full-line stores
+    const uint32_t* remap;   // optional [1 << nbits]: added to the shard-local position of every element
+                             // with that short key -> position in the global (all ranks) draw order
+    // single-kernel frames (emit_small_kernel<KeyT, true>): the velocity system and the key
+    // statistics run inside the emit, placement comes from the cached per-tile offsets
+    const float* vel;
+    const uint64_t* mask_v;
+    float dt;
+    uint32_t integrate;
+    unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+};
+
+constexpr int kEmitItems = 2;
+constexpr uint32_t kEmitTile = kThreads * kEmitItems;  // 512 entities per tile
+constexpr int kStageF4 = 5;  // per-lane staging slot: 80 B (one instance, or 64 B of vertices)
+
+// Dynamic shared memory of emit_kernel: ~108 KB, two persistent CTAs per SM.
+struct EmitShared {
+    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's,
+                                        // 16-byte chunks XOR-swizzled (row_slot) against bank conflicts
+    unsigned long long keys[2][kEmitTile];  // short keys of in-order passes that read them (hierarchy)
+    unsigned long long masks[2][2][8];  // presence words (Transform, Sprite) of the tile
+    RankShared rs;
+    uint32_t s_dst[kEmitTile];          // output position per sorted tile slot
+    uint32_t s_ent[kEmitTile];          // entity id per sorted tile slot
+    uint16_t s_li[kEmitTile];           // tile-local item index per sorted tile slot
+    float4 stage[kWarps][32 * kStageF4];  // per-warp staging for full-line stores
+    unsigned long long mbar[2];         // completion barriers of the TMA bulk copies, one per buffer
+    uint32_t s_tile[3];                 // ring of claimed tile ids
+};
+
+// 16-byte chunk c (0..3) of tile-local row li lives at rows[row_slot(li, c)]: the 128-byte
+// swizzle (chunk index XOR line index), so both consecutive rows and the scattered rows of one
+// sort bucket spread over all eight 16-byte bank groups.
+__device__ __forceinline__ uint32_t row_slot(uint32_t li, uint32_t c) { return ((li << 2) | c) ^ ((li >> 1) & 7u); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map): size and both addresses multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void make_outputs(const Affine& w, float sw, float shh, uint32_t tl, InstanceOut& inst,
+                                             float4 (&vtx)[4]) {
+    inst.c0 = make_float4(w.r0.x, w.r1.x, w.r2.x, 0.0f);
+    inst.c1 = make_float4(w.r0.y, w.r1.y, w.r2.y, 0.0f);
+    inst.c2 = make_float4(w.r0.z, w.r1.z, w.r2.z, 0.0f);
+    inst.c3 = make_float4(w.r0.w, w.r1.w, w.r2.w, 1.0f);
+    inst.s = make_float4(sw, shh, __uint_as_float(tl & 0xFFFFu), __uint_as_float(tl >> 16));
+    // corners (0,0) (w,0) (w,h) (0,h), transform_vec3 (matrix.rs:160-171)
+    const float cx[4] = {0.0f, sw, sw, 0.0f};
+    const float cy[4] = {0.0f, 0.0f, shh, shh};
+    const uint32_t uv[4] = {0x00000000u, 0x00000001u, 0x00010001u, 0x00010000u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        vtx[k] = make_float4(corner_coord(w.r0.x, w.r0.y, w.r0.w, cx[k], cy[k]),
+                             corner_coord(w.r1.x, w.r1.y, w.r1.w, cx[k], cy[k]),
+                             corner_coord(w.r2.x, w.r2.y, w.r2.w, cx[k], cy[k]), __uint_as_float(uv[k]));
+    }
+}
+
+// Writes one warp's 32 results (lane i holds the instance and vertices of output position dst)
+// as whole 128-byte lines: staged in the warp's shared buffer, then streamed out 16 bytes per lane.
+// Instances use a 20-word lane stride (conflict-free 128-bit stores; the read-out is linear);
+// vertices a 16-word stride with the chunk index XORed by bits of the lane (conflict-free both ways).
+__device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool live, uint32_t nlive, uint32_t dst,
+                                             const InstanceOut& inst, const float4 (&vtx)[4], float4* instances,
+                                             float4* vertices) {
+    float4* my = stage + lane * kStageF4;
+    if (live) {
+        my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t q = j * 32 + lane;  // 16-byte chunk of the warp's 2560-byte instance stream
+        const uint32_t item = q / 5, part = q - item * 5;
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+        if (item < nlive) st_cs_f4(instances + (size_t)d * 5 + part, stage[q]);
+    }
+    __syncwarp();
+    const uint32_t sw = (lane >> 1) & 3u;
+    if (live) {
+        float4* mv = stage + lane * 4;
+        mv[0 ^ sw] = vtx[0]; mv[1 ^ sw] = vtx[1]; mv[2 ^ sw] = vtx[2]; mv[3 ^ sw] = vtx[3];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t q = j * 32 + lane;
+        const uint32_t item = q >> 2, part = q & 3u;
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+        if (item < nlive) st_cs_f4(vertices + (size_t)d * 4 + part, stage[item * 4 + (part ^ ((item >> 1) & 3u))]);
+    }
+    __syncwarp();
+}
+
+// Final radix pass fused with compose + emit. Persistent CTAs (two per SM) claim 512-position
+// tiles in order from an atomic counter:
+//   1. the tile's rows come into shared memory asynchronously (cp.async, 16-byte chunks into a
+//      bank-swizzled layout), so no register holds a row while the tile is ranked: when the pass
+//      reads positions in entity order (single-pass plans) the NEXT tile's rows, presence words
+//      and keys are prefetched while this tile is processed; otherwise every row is gathered
+//      while the tile is ranked;
+//   2. stable rank of the tile's digits -> final output position per item, from precomputed
+//      per-tile offsets (reduce-then-scan) or by decoupled look-back;
+//   3. warps walk the tile in sorted order (consecutive slots of a digit are consecutive output
+//      positions), compose from shared memory, stage 32 results and write whole 128-byte lines.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT> ep) {
+    constexpr int ITEMS = kEmitItems;
+    constexpr uint32_t TILE = kEmitTile;
+    extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    EmitShared& sm = *reinterpret_cast<EmitShared*>(emit_smem_raw);
+    RankShared& rs = sm.rs;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_order = ep.idx_in == nullptr;  // positions are entity ids: contiguous rows
+    const bool from_world = ep.world != nullptr;
+    const bool keys_given = ep.keys_in != nullptr;
+    const uint32_t n_eff = ep.pass.count_ptr ? min(ep.pass.n, (uint32_t)*ep.pass.count_ptr) : ep.pass.n;
+    const uint32_t ntiles = (ep.pass.n + TILE - 1) / TILE;
+    const uint32_t mask = (1u << ep.pass.bits) - 1u;
+
+    // Shared-memory row layouts. In-order passes land rows with TMA bulk copies, i.e. linearly
+    // (sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]); gathered rows
+    // are placed chunk by chunk with cp.async into the bank-swizzled layout (row_slot).
+    const bool split = in_order && !from_world && ep.rows.stride == 2;
+    const uint32_t sstride = split ? 2u : 4u;
+    const uint32_t boff = split ? 2u * TILE : 2u;
+    auto chunk = [&](uint32_t li, uint32_t c) -> uint32_t {
+        if (!in_order) return row_slot(li, c);
+        return (c < 2 ? 0u : boff - 2u) + li * sstride + c;
+    };
+
+    // in-order passes: TMA bulk copies of one tile's rows / presence words / keys into buffer `buf`
+    // (issued by one thread, completion counted in bytes on the buffer's mbarrier)
+    auto fetch_tile = [&](uint32_t tile, uint32_t buf) {
+        const uint32_t base = tile * TILE;
+        const uint32_t cnt = min(TILE, n_eff - base);
+        const uint32_t mwords = ((cnt + 127u) >> 7) * 2u;  // presence words, padded to 16 bytes
+        const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
+        const uint32_t mbytes = ((ep.mask_t ? 1u : 0u) + (ep.mask_s ? 1u : 0u)) * mwords * 8u;
+        float4* dst = sm.rows[buf];
+        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + mbytes + kbytes);
+        if (from_world) {
+            bulk_g2s(dst, ep.world + base, cnt * 64u, &sm.mbar[buf]);
+        } else if (split) {
+            bulk_g2s(dst, ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(dst + 2 * TILE, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+        } else {
+            bulk_g2s(dst, ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+        }
+        if (ep.mask_t) bulk_g2s(sm.masks[buf][0], ep.mask_t + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+        if (ep.mask_s) bulk_g2s(sm.masks[buf][1], ep.mask_s + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+        if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        const uint32_t t0 = atomicAdd(ep.pass.tile_counter, 1u);
+        sm.s_tile[0] = t0;
+        sm.s_tile[1] = atomicAdd(ep.pass.tile_counter, 1u);
+        if (in_order && t0 < ntiles) fetch_tile(t0, 0);
+    }
+    rank_reset(rs, ep.pass.bits);
+    __syncthreads();
+    uint32_t cur = 0, ring = 0, parity0 = 0, parity1 = 0;
+    for (;;) {
+        const uint32_t tile = sm.s_tile[ring];
+        if (tile >= ntiles) break;
+        const uint32_t next = sm.s_tile[ring == 2 ? 0 : ring + 1];
+        if (threadIdx.x == 0) {
+            sm.s_tile[ring == 0 ? 2 : ring - 1] = atomicAdd(ep.pass.tile_counter, 1u);
+            if (in_order && next < ntiles) fetch_tile(next, cur ^ 1u);  // prefetch; buffer freed by the last barrier
+        }
+        const float4* rows = sm.rows[cur];
+        const uint32_t tile_base = tile * TILE;
+        uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS], shift_g[ITEMS];
+        bool valid[ITEMS];
+        if (in_order) {
+            mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
+            if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+                const uint32_t pos = tile_base + li;
+                ent[k] = pos;
+                valid[k] = pos < n_eff;
+                if (valid[k]) {
+                    const bool t_ok = ep.mask_t == nullptr || ((sm.masks[cur][0][li >> 6] >> (li & 63u)) & 1ull);
+                    const bool s_ok = ep.mask_s == nullptr || ((sm.masks[cur][1][li >> 6] >> (li & 63u)) & 1ull);
+                    valid[k] = t_ok && s_ok;
+                }
+                uint64_t sk = 0;
+                if (valid[k]) {
+                    if (keys_given) {
+                        sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
+                    } else if (from_world) {
+                        sk = pext_runs(world_key(rows[chunk(li, 2)], rows[chunk(li, 3)]), ep.plan.pext);
+                    } else {
+                        const float4 a0 = rows[chunk(li, 0)], a1 = rows[chunk(li, 1)];
+                        float z;
+                        if (is_planar(a1)) {
+                            z = planar_z(a0, a1);
+                        } else {
+                            Row r;
+                            r.a0 = a0;
+                            r.a1 = a1;
+                            r.b0 = rows[chunk(li, 2)];
+                            r.b1 = rows[chunk(li, 3)];
+                            z = local_z(r);
+                        }
+                        const uint32_t tl = __float_as_uint(a1.w);
+                        sk = pext_runs(sort_key(tl >> 16, tl & 0xFFFFu, z), ep.plan.pext);
+                    }
+                }
+                digit[k] = valid[k] ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
+                shift_g[k] = (ep.remap != nullptr && valid[k]) ? __ldg(ep.remap + (uint32_t)sk) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+                const uint32_t pos = tile_base + li;
+                valid[k] = pos < n_eff;
+                ent[k] = pos;
+                digit[k] = kInvalidDigit;
+                shift_g[k] = 0u;
+                if (valid[k]) {
+                    const KeyT key = ep.keys_in[pos];
+                    ent[k] = ep.idx_in[pos];
+                    digit[k] = (uint32_t)(key >> ep.pass.shift) & mask;
+                    if (ep.remap != nullptr) shift_g[k] = __ldg(ep.remap + (uint32_t)key);
+                    // gather this entity's row into the item's shared-memory slot
+                    float4* d = sm.rows[cur];
+                    if (from_world) {
+                        const float4* src = reinterpret_cast<const float4*>(ep.world + ent[k]);
+                        cp_async16(d + row_slot(li, 0), src);
+                        cp_async16(d + row_slot(li, 1), src + 1);
+                        cp_async16(d + row_slot(li, 2), src + 2);
+                        cp_async16(d + row_slot(li, 3), src + 3);
+                    } else {
+                        const size_t o = (size_t)ent[k] * ep.rows.stride;
+                        cp_async16(d + row_slot(li, 0), ep.rows.a + o);
+                        cp_async16(d + row_slot(li, 1), ep.rows.a + o + 1);
+                        cp_async16(d + row_slot(li, 2), ep.rows.b + o);
+                        cp_async16(d + row_slot(li, 3), ep.rows.b + o + 1);
+                    }
+                }
+            }
+        }
+        rank_tile<ITEMS>(rs, ep.pass, tile, digit, slot);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (digit[k] != kInvalidDigit) {
+                sm.s_li[slot[k]] = (uint16_t)(warp * (ITEMS * 32) + k * 32 + lane);
+                sm.s_ent[slot[k]] = ent[k];
+                sm.s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k] + shift_g[k];
+            }
+        }
+        if (!in_order) cp_async_wait_all();
+        __syncthreads();
+        const uint32_t cnt = rs.tile_count;
+        float4* stage = sm.stage[warp];
+        for (uint32_t s0 = warp * 32; s0 < cnt; s0 += kThreads) {
+            const uint32_t s = s0 + lane;
+            const bool live = s < cnt;
+            uint32_t dst = 0;
+            InstanceOut inst;
+            float4 vtx[4];
+            if (live) {
+                const uint32_t li = sm.s_li[s];
+                const uint32_t e = sm.s_ent[s];
+                dst = sm.s_dst[s];
+                Affine w;
+                float sw, shh;
+                uint32_t tl;
+                if (from_world) {
+                    w.r0 = rows[chunk(li, 0)];
+                    w.r1 = rows[chunk(li, 1)];
+                    w.r2 = rows[chunk(li, 2)];
+                    const float4 sv = rows[chunk(li, 3)];
+                    sw = sv.x;
+                    shh = sv.y;
+                    tl = __float_as_uint(sv.z);
+                } else {
+                    Row r;
+                    r.a0 = rows[chunk(li, 0)];
+                    r.a1 = rows[chunk(li, 1)];
+                    r.b0 = rows[chunk(li, 2)];
+                    r.b1 = rows[chunk(li, 3)];
+                    w = compose_local(r);
+                    sw = r.b1.y;
+                    shh = r.b1.z;
+                    tl = __float_as_uint(r.a1.w);
+                }
+                make_outputs(w, sw, shh, tl, inst, vtx);
+                ep.order[dst] = e + ep.global_first;
+                if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
+            }
+            if (!ep.staged) {
+                if (live) {
+                    float4* ip = ep.instances + (size_t)dst * 5;
+                    st_cs_f4(ip, inst.c0);
+                    st_cs_f4(ip + 1, inst.c1);
+                    st_cs_f4(ip + 2, inst.c2);
+                    st_cs_f4(ip + 3, inst.c3);
+                    st_cs_f4(ip + 4, inst.s);
+                    float4* vp = ep.vertices + (size_t)dst * 4;
+                    st_cs_f4(vp, vtx[0]);
+                    st_cs_f4(vp + 1, vtx[1]);
+                    st_cs_f4(vp + 2, vtx[2]);
+                    st_cs_f4(vp + 3, vtx[3]);
+                }
+            } else {
+                staged_store(stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
+            }
+        }
+        rank_reset(rs, ep.pass.bits);
+        __syncthreads();  // releases rows[cur], the rank scratch and the tile ring slot for reuse
+        cur ^= 1u;
+        ring = ring == 2 ? 0 : ring + 1;
+    }
+}
+
+// ---- few-bucket frames: every warp is its own pipeline -----------------------------------------------
+//
+// Single-pass plans with at most 8 buckets (e.g. a particle system with a handful of textures)
+// need no block at all: a warp takes 64 consecutive entities, ranks them with a few ballots in
+// registers, and — because pass A counted the buckets of every 64-entity tile and tile_scan turned
+// the counts into offsets — knows every output position without talking to any other warp. There is
+// not a single block barrier in this kernel; warps drift apart and hide each other's latencies.
+constexpr uint32_t kWarpTile = 64;          // entities per warp step (2 per lane)
+constexpr uint32_t kSmallMaxBits = 3;       // up to 8 buckets: runs of >= 8 instances per warp tile
+
+struct WarpShared {
+    float4 rows[2][kWarpTile * 4];          // 2 x 4 KB: this tile's rows and the prefetched next tile's
+    unsigned long long keys[2][kWarpTile];  // short keys when the pass reads them (hierarchy)
+    float4 vel[2][kWarpTile * 3 / 4];       // velocities of the tile (single-kernel frames)
+    float4 stage[32 * kStageF4];            // 2.5 KB staging
+    uint32_t s_dst[kWarpTile];
+    uint8_t s_li[kWarpTile];
+    unsigned long long mbar[2];
+};
+struct SmallShared {
+    WarpShared w[kWarps];
+};
+
+// FUSED: the whole frame in this one kernel. When the bucket of an entity depends only on its
+// Sprite (the plan has no varying z bit), per-tile bucket offsets stay valid from frame to frame
+// until a component is uploaded, so the steady-state frame needs no separate key pass: this kernel
+// also runs the velocity system (writing sector A back), and accumulates the key statistics with
+// which the host validates, every frame, that the cached plan and offsets still hold.
+template <typename KeyT, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParams<KeyT> ep) {
+    extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpShared& sm = reinterpret_cast<SmallShared*>(emit_smem_raw)->w[warp];
+    const bool do_int = FUSED && ep.integrate && ep.vel != nullptr;
+    PrepAcc acc;
+    const bool from_world = ep.world != nullptr;
+    const bool keys_given = ep.keys_in != nullptr;
+    const uint32_t n = ep.pass.n;
+    const uint32_t ntiles = ep.pass.ntiles;  // == ceil(n / 64)
+    const uint32_t R = 1u << ep.pass.bits;
+    const bool split = !from_world && ep.rows.stride == 2;
+    const uint32_t sstride = split ? 2u : 4u;
+    const uint32_t boff = split ? 2u * kWarpTile : 2u;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    uint32_t tile = blockIdx.x * kWarps + warp;
+
+    auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0: TMA bulk copies of tile t's rows (and keys)
+        const uint32_t base = t * kWarpTile;
+        const uint32_t cnt = min(kWarpTile, n - base);
+        const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
+        const uint32_t vbytes = do_int ? ((cnt * 12u + 15u) & ~15u) : 0u;
+        mbar_expect_tx(&sm.mbar[buf], cnt * 64u + kbytes + vbytes);
+        if (from_world) {
+            bulk_g2s(sm.rows[buf], ep.world + base, cnt * 64u, &sm.mbar[buf]);
+        } else if (split) {
+            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(sm.rows[buf] + 2 * kWarpTile, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+        } else {
+            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+        }
+        if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+        if (do_int) bulk_g2s(sm.vel[buf], ep.vel + (size_t)base * 3, vbytes, &sm.mbar[buf]);
+    };
+    // Presence words of a tile, prefetched one tile ahead WITHOUT being consumed: lane 0 holds the
+    // Transform word, lane 1 the Sprite word, lane 2 the Velocity word; they are combined (by shuffle)
+    // only when the tile is processed, so the loads never stall the warp.
+    auto load_raw = [&](uint32_t t) -> unsigned long long {
+        const uint64_t* src = lane == 0 ? ep.mask_t : lane == 1 ? ep.mask_s : (lane == 2 && do_int) ? ep.mask_v : nullptr;
+        return src != nullptr ? __ldg(src + t) : ~0ull;
+    };
+
+    if (lane == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        if (tile < ntiles) fetch(tile, 0);
+    }
+    __syncwarp();
+    unsigned long long raw = tile < ntiles ? load_raw(tile) : 0ull, raw_next = 0ull;
+    uint32_t off = (tile < ntiles && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
+    uint32_t cur = 0, par0 = 0, par1 = 0;
+    for (; tile < ntiles; tile += nwarps) {
+        // prefetch the next tile of this warp: rows by TMA, presence word and bucket offsets in registers
+        const uint32_t next = tile + nwarps;
+        uint32_t off_next = 0u;
+        if (next < ntiles) {
+            if (lane == 0) fetch(next, cur ^ 1u);
+            raw_next = load_raw(next);
+            if (lane < R) off_next = __ldg(ep.pass.tile_off + (size_t)lane * ntiles + next);
+        }
+        float4* rows = sm.rows[cur];
+        const uint32_t base = tile * kWarpTile;
+        mbar_wait(&sm.mbar[cur], cur ? par1 : par0);
+        if (cur) par1 ^= 1u; else par0 ^= 1u;
+        // (Transform and Sprite) = renderable; (Transform and Velocity) = moved by the tick
+        const unsigned long long tail = (n - base < kWarpTile) ? ((1ull << (n - base)) - 1ull) : ~0ull;
+        const unsigned long long mt = __shfl_sync(0xffffffffu, raw, 0);
+        const unsigned long long pres = mt & __shfl_sync(0xffffffffu, raw, 1) & tail;
+        const unsigned long long moving = do_int ? (mt & __shfl_sync(0xffffffffu, raw, 2) & tail) : 0ull;
+        if (do_int) {
+            // the velocity system on this tile: translation += velocity * dt, in shared memory (the
+            // compose below reads it) and written back to sector A
+            const float* vel = reinterpret_cast<const float*>(sm.vel[cur]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t li = k * 32 + lane;
+                if ((moving >> li) & 1ull) {
+                    float4 a0 = rows[li * sstride];
+                    a0.x = addr(a0.x, mulr(vel[li * 3], ep.dt));
+                    a0.y = addr(a0.y, mulr(vel[li * 3 + 1], ep.dt));
+                    a0.z = addr(a0.z, mulr(vel[li * 3 + 2], ep.dt));
+                    rows[li * sstride] = a0;
+                    ep.rows.a[(size_t)(base + li) * ep.rows.stride] = a0;
+                }
+            }
+        }
+        // bucket of this lane's two entities (li = lane and lane + 32)
+        uint32_t digit[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t li = k * 32 + lane;
+            digit[k] = kInvalidDigit;
+            if ((pres >> li) & 1ull) {
+                uint64_t sk;
+                if (keys_given) {
+                    sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
+                } else if (from_world) {
+                    sk = pext_runs(world_key(rows[li * 4 + 2], rows[li * 4 + 3]), ep.plan.pext);
+                } else {
+                    const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
+                    float z;
+                    if (is_planar(a1)) {
+                        z = planar_z(a0, a1);
+                    } else {
+                        Row r;
+                        r.a0 = a0;
+                        r.a1 = a1;
+                        r.b0 = rows[boff + li * sstride];
+                        r.b1 = rows[boff + li * sstride + 1];
+                        z = local_z(r);
+                    }
+                    const uint32_t tl = __float_as_uint(a1.w);
+                    const uint64_t key = sort_key(tl >> 16, tl & 0xFFFFu, z);
+                    if (FUSED) {
+                        acc.k_or |= key;
+                        acc.k_and &= key;
+                        acc.count += 1;
+                    }
+                    sk = pext_runs(key, ep.plan.pext);
+                }
+                digit[k] = (uint32_t)sk & (R - 1u);
+            }
+        }
+        // stable rank inside the warp tile, in registers: per bucket two ballots
+        uint32_t slot[2] = {0, 0}, dpos[2] = {0, 0};
+        uint32_t run = 0;
+        for (uint32_t d = 0; d < R; ++d) {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, digit[0] == d);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, digit[1] == d);
+            const uint32_t o = __shfl_sync(0xffffffffu, off, d);
+            if (digit[0] == d) {
+                const uint32_t r = __popc(b0 & lt);
+                slot[0] = run + r;
+                dpos[0] = o + r;
+            }
+            if (digit[1] == d) {
+                const uint32_t r = __popc(b0) + __popc(b1 & lt);
+                slot[1] = run + r;
+                dpos[1] = o + r;
+            }
+            run += __popc(b0) + __popc(b1);
+        }
+        const uint32_t cnt = run;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (digit[k] != kInvalidDigit) {
+                sm.s_li[slot[k]] = (uint8_t)(k * 32 + lane);
+                sm.s_dst[slot[k]] = dpos[k] + (ep.remap != nullptr ? __ldg(ep.remap + digit[k]) : 0u);
+            }
+        }
+        __syncwarp();
+        for (uint32_t s0 = 0; s0 < cnt; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            const bool live = s < cnt;
+            uint32_t dst = 0;
+            InstanceOut inst;
+            float4 vtx[4];
+            if (live) {
+                const uint32_t li = sm.s_li[s];
+                dst = sm.s_dst[s];
+                Affine w;
+                float sw, shh;
+                uint32_t tl;
+                if (from_world) {
+                    w.r0 = rows[li * 4];
+                    w.r1 = rows[li * 4 + 1];
+                    w.r2 = rows[li * 4 + 2];
+                    const float4 sv = rows[li * 4 + 3];
+                    sw = sv.x;
+                    shh = sv.y;
+                    tl = __float_as_uint(sv.z);
+                } else {
+                    Row r;
+                    r.a0 = rows[li * sstride];
+                    r.a1 = rows[li * sstride + 1];
+                    r.b0 = rows[boff + li * sstride];
+                    r.b1 = rows[boff + li * sstride + 1];
+                    w = compose_local(r);
+                    sw = r.b1.y;
+                    shh = r.b1.z;
+                    tl = __float_as_uint(r.a1.w);
+                }
+                make_outputs(w, sw, shh, tl, inst, vtx);
+                ep.order[dst] = base + li + ep.global_first;
+                if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
+            }
+            if (!ep.staged) {
+                if (live) {
+                    float4* ip = ep.instances + (size_t)dst * 5;
+                    st_cs_f4(ip, inst.c0);
+                    st_cs_f4(ip + 1, inst.c1);
+                    st_cs_f4(ip + 2, inst.c2);
+                    st_cs_f4(ip + 3, inst.c3);
+                    st_cs_f4(ip + 4, inst.s);
+                    float4* vp = ep.vertices + (size_t)dst * 4;
+                    st_cs_f4(vp, vtx[0]);
+                    st_cs_f4(vp + 1, vtx[1]);
+                    st_cs_f4(vp + 2, vtx[2]);
+                    st_cs_f4(vp + 3, vtx[3]);
+                }
+            } else {
+                staged_store(sm.stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
+            }
+        }
+        __syncwarp();  // every lane is done with rows[cur], s_li, s_dst before they are reused
+        raw = raw_next;
+        off = off_next;
+        cur ^= 1u;
+    }
+    if (FUSED) {
+        // key statistics of everything this warp emitted: the host validates the cached plan with them
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc.k_or);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc.k_or >> 32));
+        const uint32_t nlo = __reduce_or_sync(0xffffffffu, ~(uint32_t)acc.k_and);
+        const uint32_t nhi = __reduce_or_sync(0xffffffffu, ~(uint32_t)(acc.k_and >> 32));
+        const uint32_t c = __reduce_add_sync(0xffffffffu, acc.count);
+        if (lane == 0 && c) {
+            atomicOr(&ep.stats[0], ((unsigned long long)hi << 32) | lo);
+            atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
+            atomicAdd(&ep.stats[2], (unsigned long long)c);
+        }
+    }
+}
+
+}  // namespace tb
