@@ -60,3 +60,7 @@ if __name__ == "__main__":
         run("configs[3] 16M particles", scenes.config4(), 232, integrate=True)
     if "5" in which:
         run("configs[4] 64M flat on one GPU", scenes.config5(), 208)
+    if "5i" in which:
+        run("configs[4] 64M flat on one GPU", scenes.config5(), 208, interleaved_rows=1)
+    if "4s" in which:
+        run("configs[3] 16M particles, nothing cached between frames", scenes.config4(), 232, integrate=True, static_buckets=0)

@@ -45,19 +45,20 @@ constexpr int kEmitItems = 2;
 constexpr uint32_t kEmitTile = kThreads * kEmitItems;  // 512 entities per tile
 constexpr int kStageF4 = 5;  // per-lane staging slot: 80 B (one instance, or 64 B of vertices)
 
-// Dynamic shared memory of emit_kernel: ~108 KB, two persistent CTAs per SM.
+// Dynamic shared memory of emit_kernel: ~110 KB with 32-bit short keys, two persistent CTAs per SM.
+template <typename KeyT>
 struct EmitShared {
-    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's,
-                                        // 16-byte chunks XOR-swizzled (row_slot) against bank conflicts
-    unsigned long long keys[2][kEmitTile];  // short keys of in-order passes that read them (hierarchy)
-    unsigned long long masks[2][2][8];  // presence words (Transform, Sprite) of the tile
+    float4 rows[2][kEmitTile * 4];      // 2 x 32 KB: this tile's rows and the prefetched next tile's
+                                        // (gathered rows: 16-byte chunks XOR-swizzled, see row_slot)
+    KeyT keys[3][kEmitTile];            // ring of short keys: tiles k, k+1, k+2 of a sorted stream
+    uint32_t idx[3][kEmitTile];         // ring of entity ids of the same tiles
+    unsigned long long masks[2][2][8];  // presence words (Transform, Sprite) of an in-order tile
     RankShared rs;
     uint32_t s_dst[kEmitTile];          // output position per sorted tile slot
-    uint32_t s_ent[kEmitTile];          // entity id per sorted tile slot
     uint16_t s_li[kEmitTile];           // tile-local item index per sorted tile slot
     float4 stage[kWarps][32 * kStageF4];  // per-warp staging for full-line stores
-    unsigned long long mbar[2];         // completion barriers of the TMA bulk copies, one per buffer
-    uint32_t s_tile[3];                 // ring of claimed tile ids
+    unsigned long long mbar[2];         // completion barriers of the row copies (in-order passes)
+    unsigned long long kbar[3];         // completion barriers of the (key, entity) ring
 };
 
 // 16-byte chunk c (0..3) of tile-local row li lives at rows[row_slot(li, c)]: the 128-byte
@@ -156,31 +157,33 @@ __device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool 
     __syncwarp();
 }
 
-// Final radix pass fused with compose + emit. Persistent CTAs (two per SM) claim 512-position
-// tiles in order from an atomic counter:
-//   1. the tile's rows come into shared memory asynchronously (cp.async, 16-byte chunks into a
-//      bank-swizzled layout), so no register holds a row while the tile is ranked: when the pass
-//      reads positions in entity order (single-pass plans) the NEXT tile's rows, presence words
-//      and keys are prefetched while this tile is processed; otherwise every row is gathered
-//      while the tile is ranked;
-//   2. stable rank of the tile's digits -> final output position per item, from precomputed
-//      per-tile offsets (reduce-then-scan) or by decoupled look-back;
-//   3. warps walk the tile in sorted order (consecutive slots of a digit are consecutive output
+// Final radix pass fused with compose + emit, any plan. Persistent CTAs (two per SM) walk
+// 512-position tiles (tile = blockIdx.x + k * gridDim.x); every tile's output positions come from
+// the precomputed per-tile digit offsets, so no CTA ever waits for another.
+//   1. The tile's rows reach shared memory asynchronously, one tile ahead of the compute:
+//      - passes that read positions in entity order (single-pass plans): TMA bulk copies of the
+//        next tile's sector blocks, presence words and keys;
+//      - passes over a sorted (key, entity) stream: the (key, entity) pairs of tile k+2 arrive by TMA
+//        while the rows of tile k+1 are gathered by entity id with cp.async (into a 128-byte-swizzled
+//        layout) and tile k is ranked and emitted — a three-deep software pipeline, all in shared memory.
+//   2. Stable rank of the tile's digits (match.any per warp, per-warp counters, one block scan).
+//   3. Warps walk the tile in sorted order (consecutive slots of a digit are consecutive output
 //      positions), compose from shared memory, stage 32 results and write whole 128-byte lines.
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT> ep) {
     constexpr int ITEMS = kEmitItems;
     constexpr uint32_t TILE = kEmitTile;
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
-    EmitShared& sm = *reinterpret_cast<EmitShared*>(emit_smem_raw);
+    EmitShared<KeyT>& sm = *reinterpret_cast<EmitShared<KeyT>*>(emit_smem_raw);
     RankShared& rs = sm.rs;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool in_order = ep.idx_in == nullptr;  // positions are entity ids: contiguous rows
     const bool from_world = ep.world != nullptr;
     const bool keys_given = ep.keys_in != nullptr;
     const uint32_t n_eff = ep.pass.count_ptr ? min(ep.pass.n, (uint32_t)*ep.pass.count_ptr) : ep.pass.n;
-    const uint32_t ntiles = (ep.pass.n + TILE - 1) / TILE;
+    const uint32_t ntiles = ep.pass.ntiles;
     const uint32_t mask = (1u << ep.pass.bits) - 1u;
+    const uint32_t step = gridDim.x;
 
     // Shared-memory row layouts. In-order passes land rows with TMA bulk copies, i.e. linearly
     // (sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]); gathered rows
@@ -192,12 +195,15 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
         if (!in_order) return row_slot(li, c);
         return (c < 2 ? 0u : boff - 2u) + li * sstride + c;
     };
-
-    // in-order passes: TMA bulk copies of one tile's rows / presence words / keys into buffer `buf`
-    // (issued by one thread, completion counted in bytes on the buffer's mbarrier)
-    auto fetch_tile = [&](uint32_t tile, uint32_t buf) {
+    auto tile_count = [&](uint32_t tile) -> uint32_t {
         const uint32_t base = tile * TILE;
-        const uint32_t cnt = min(TILE, n_eff - base);
+        return (tile < ntiles && base < n_eff) ? min(TILE, n_eff - base) : 0u;
+    };
+    // in-order passes (thread 0): TMA bulk copies of one tile's rows / presence words / keys
+    auto fetch_rows = [&](uint32_t tile, uint32_t buf, uint32_t ring) {
+        const uint32_t base = tile * TILE;
+        const uint32_t cnt = tile_count(tile);
+        if (cnt == 0) return;
         const uint32_t mwords = ((cnt + 127u) >> 7) * 2u;  // presence words, padded to 16 bytes
         const uint32_t kbytes = keys_given ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
         const uint32_t mbytes = ((ep.mask_t ? 1u : 0u) + (ep.mask_s ? 1u : 0u)) * mwords * 8u;
@@ -213,41 +219,91 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
         }
         if (ep.mask_t) bulk_g2s(sm.masks[buf][0], ep.mask_t + (base >> 6), mwords * 8u, &sm.mbar[buf]);
         if (ep.mask_s) bulk_g2s(sm.masks[buf][1], ep.mask_s + (base >> 6), mwords * 8u, &sm.mbar[buf]);
-        if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+        if (keys_given) bulk_g2s(sm.keys[ring], ep.keys_in + base, kbytes, &sm.mbar[buf]);
+    };
+    // sorted-stream passes (thread 0): TMA bulk copies of one tile's (key, entity) pairs
+    auto fetch_pairs = [&](uint32_t tile, uint32_t ring) {
+        const uint32_t base = tile * TILE;
+        const uint32_t cnt = tile_count(tile);
+        if (cnt == 0) return;
+        const uint32_t kbytes = (cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u;
+        const uint32_t ibytes = (cnt * 4u + 15u) & ~15u;
+        mbar_expect_tx(&sm.kbar[ring], kbytes + ibytes);
+        bulk_g2s(sm.keys[ring], ep.keys_in + base, kbytes, &sm.kbar[ring]);
+        bulk_g2s(sm.idx[ring], ep.idx_in + base, ibytes, &sm.kbar[ring]);
+    };
+    // sorted-stream passes (all threads): gather the rows of one tile whose pairs are in ring slot `ring`
+    auto gather_rows = [&](uint32_t tile, uint32_t buf, uint32_t ring) {
+        const uint32_t cnt = tile_count(tile);
+        float4* d = sm.rows[buf];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+            if (li < cnt) {
+                const uint32_t e = sm.idx[ring][li];
+                if (from_world) {
+                    const float4* src = reinterpret_cast<const float4*>(ep.world + e);
+                    cp_async16(d + row_slot(li, 0), src);
+                    cp_async16(d + row_slot(li, 1), src + 1);
+                    cp_async16(d + row_slot(li, 2), src + 2);
+                    cp_async16(d + row_slot(li, 3), src + 3);
+                } else {
+                    const size_t o = (size_t)e * ep.rows.stride;
+                    cp_async16(d + row_slot(li, 0), ep.rows.a + o);
+                    cp_async16(d + row_slot(li, 1), ep.rows.a + o + 1);
+                    cp_async16(d + row_slot(li, 2), ep.rows.b + o);
+                    cp_async16(d + row_slot(li, 3), ep.rows.b + o + 1);
+                }
+            }
+        }
     };
 
+    uint32_t tile = blockIdx.x;
+    uint32_t kpar = 0;  // phase parities of the three kbar slots (bit r)
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
-        const uint32_t t0 = atomicAdd(ep.pass.tile_counter, 1u);
-        sm.s_tile[0] = t0;
-        sm.s_tile[1] = atomicAdd(ep.pass.tile_counter, 1u);
-        if (in_order && t0 < ntiles) fetch_tile(t0, 0);
+        mbar_init(&sm.kbar[0], 1);
+        mbar_init(&sm.kbar[1], 1);
+        mbar_init(&sm.kbar[2], 1);
+        if (in_order) {
+            fetch_rows(tile, 0, 0);
+        } else {
+            fetch_pairs(tile, 0);
+            fetch_pairs(tile + step, 1);
+        }
     }
     rank_reset(rs, ep.pass.bits);
     __syncthreads();
-    uint32_t cur = 0, ring = 0, parity0 = 0, parity1 = 0;
-    for (;;) {
-        const uint32_t tile = sm.s_tile[ring];
-        if (tile >= ntiles) break;
-        const uint32_t next = sm.s_tile[ring == 2 ? 0 : ring + 1];
-        if (threadIdx.x == 0) {
-            sm.s_tile[ring == 0 ? 2 : ring - 1] = atomicAdd(ep.pass.tile_counter, 1u);
-            if (in_order && next < ntiles) fetch_tile(next, cur ^ 1u);  // prefetch; buffer freed by the last barrier
+    if (!in_order) {
+        if (tile_count(tile)) {
+            mbar_wait(&sm.kbar[0], 0);
+            kpar ^= 1u;
         }
+        gather_rows(tile, 0, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    uint32_t cur = 0, ring = 0, parity0 = 0, parity1 = 0;
+    for (; tile < ntiles; tile += step) {
+        const uint32_t next = tile + step;
+        const uint32_t ring1 = ring == 2 ? 0 : ring + 1, ring2 = ring == 0 ? 2 : ring - 1;
         const float4* rows = sm.rows[cur];
         const uint32_t tile_base = tile * TILE;
+        const uint32_t tcnt = tile_count(tile);
         uint32_t ent[ITEMS], digit[ITEMS], slot[ITEMS], shift_g[ITEMS];
         bool valid[ITEMS];
         if (in_order) {
-            mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
-            if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+            if (threadIdx.x == 0) fetch_rows(next, cur ^ 1u, ring1);  // prefetch; buffer freed by the last barrier
+            if (tcnt) {
+                mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
+                if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+            }
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
                 const uint32_t pos = tile_base + li;
                 ent[k] = pos;
-                valid[k] = pos < n_eff;
+                valid[k] = li < tcnt;
                 if (valid[k]) {
                     const bool t_ok = ep.mask_t == nullptr || ((sm.masks[cur][0][li >> 6] >> (li & 63u)) & 1ull);
                     const bool s_ok = ep.mask_s == nullptr || ((sm.masks[cur][1][li >> 6] >> (li & 63u)) & 1ull);
@@ -256,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 uint64_t sk = 0;
                 if (valid[k]) {
                     if (keys_given) {
-                        sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
+                        sk = (uint64_t)sm.keys[ring][li];
                     } else if (from_world) {
                         sk = pext_runs(world_key(rows[chunk(li, 2)], rows[chunk(li, 3)]), ep.plan.pext);
                     } else {
@@ -280,34 +336,26 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 shift_g[k] = (ep.remap != nullptr && valid[k]) ? __ldg(ep.remap + (uint32_t)sk) : 0u;
             }
         } else {
+            // pairs of tile k+2 by TMA, rows of tile k+1 by cp.async, then wait for the rows of tile k
+            if (threadIdx.x == 0) fetch_pairs(next + step, ring2);
+            if (tile_count(next)) {
+                mbar_wait(&sm.kbar[ring1], (kpar >> ring1) & 1u);
+                kpar ^= 1u << ring1;
+            }
+            gather_rows(next, cur ^ 1u, ring1);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
-                const uint32_t pos = tile_base + li;
-                valid[k] = pos < n_eff;
-                ent[k] = pos;
+                valid[k] = li < tcnt;
+                ent[k] = 0;
                 digit[k] = kInvalidDigit;
                 shift_g[k] = 0u;
                 if (valid[k]) {
-                    const KeyT key = ep.keys_in[pos];
-                    ent[k] = ep.idx_in[pos];
+                    const KeyT key = sm.keys[ring][li];
+                    ent[k] = sm.idx[ring][li];
                     digit[k] = (uint32_t)(key >> ep.pass.shift) & mask;
                     if (ep.remap != nullptr) shift_g[k] = __ldg(ep.remap + (uint32_t)key);
-                    // gather this entity's row into the item's shared-memory slot
-                    float4* d = sm.rows[cur];
-                    if (from_world) {
-                        const float4* src = reinterpret_cast<const float4*>(ep.world + ent[k]);
-                        cp_async16(d + row_slot(li, 0), src);
-                        cp_async16(d + row_slot(li, 1), src + 1);
-                        cp_async16(d + row_slot(li, 2), src + 2);
-                        cp_async16(d + row_slot(li, 3), src + 3);
-                    } else {
-                        const size_t o = (size_t)ent[k] * ep.rows.stride;
-                        cp_async16(d + row_slot(li, 0), ep.rows.a + o);
-                        cp_async16(d + row_slot(li, 1), ep.rows.a + o + 1);
-                        cp_async16(d + row_slot(li, 2), ep.rows.b + o);
-                        cp_async16(d + row_slot(li, 3), ep.rows.b + o + 1);
-                    }
                 }
             }
         }
@@ -316,12 +364,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
         for (int k = 0; k < ITEMS; ++k) {
             if (digit[k] != kInvalidDigit) {
                 sm.s_li[slot[k]] = (uint16_t)(warp * (ITEMS * 32) + k * 32 + lane);
-                sm.s_ent[slot[k]] = ent[k];
                 sm.s_dst[slot[k]] = rs.dbase[digit[k]] + slot[k] + shift_g[k];
             }
         }
-        if (!in_order) cp_async_wait_all();
-        __syncthreads();
+        __syncthreads();  // also publishes every thread's finished cp.async gathers of this tile
         const uint32_t cnt = rs.tile_count;
         float4* stage = sm.stage[warp];
         for (uint32_t s0 = warp * 32; s0 < cnt; s0 += kThreads) {
@@ -332,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
             float4 vtx[4];
             if (live) {
                 const uint32_t li = sm.s_li[s];
-                const uint32_t e = sm.s_ent[s];
+                const uint32_t e = in_order ? tile_base + li : sm.idx[ring][li];
                 dst = sm.s_dst[s];
                 Affine w;
                 float sw, shh;
@@ -379,10 +425,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
             }
         }
         rank_reset(rs, ep.pass.bits);
-        __syncthreads();  // releases rows[cur], the rank scratch and the tile ring slot for reuse
+        __syncthreads();  // releases rows[cur], the rank scratch and the pair ring slot for reuse
         cur ^= 1u;
-        ring = ring == 2 ? 0 : ring + 1;
+        ring = ring1;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ---- few-bucket frames: every warp is its own pipeline -----------------------------------------------

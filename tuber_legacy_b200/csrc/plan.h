@@ -123,11 +123,15 @@ inline void build_frame_plan(uint64_t key_or, uint64_t key_and, FramePlan* out) 
     uint32_t np = (nbits + kMaxDigitBits - 1) / kMaxDigitBits;
     if (np == 0) np = 1;
     f.npasses = np;
-    uint32_t base = nbits / np, rem = nbits % np, sh = 0;
+    // The scatter passes move 8..12-byte (key, id) pairs and take full 8-bit digits; whatever is
+    // left goes to the LAST pass, the one fused with the emit: the fewer buckets it has, the longer
+    // the runs of consecutive output positions a tile produces and the better its 80/64-byte
+    // payload stores coalesce.
+    uint32_t sh = 0;
     for (uint32_t p = 0; p < (uint32_t)kMaxPasses; ++p) f.shift[p] = f.bits[p] = 0;
     for (uint32_t p = 0; p < np; ++p) {
         f.shift[p] = sh;
-        f.bits[p] = base + (p < rem ? 1u : 0u);
+        f.bits[p] = (p + 1 < np) ? (uint32_t)kMaxDigitBits : nbits - sh;
         sh += f.bits[p];
     }
 }

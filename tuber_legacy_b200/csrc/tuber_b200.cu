@@ -293,7 +293,7 @@ struct ScratchLayout {
 };
 
 bool use_small_emit(const tb_ctx* c, const FramePlan& plan) {
-    return c->tile_offsets != 0 && c->small_emit != 0 && plan.npasses == 1 && plan.bits[0] <= kSmallMaxBits;
+    return c->small_emit != 0 && plan.npasses == 1 && plan.bits[0] <= kSmallMaxBits;
 }
 
 ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets, bool zero_counts0,
@@ -306,7 +306,7 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
     off += L.lt_words;
     const uint32_t last_tile = small ? kWarpTile : kThreads * kEmitItems;
-    if (tile_offsets && zero_counts0) {
+    if (zero_counts0) {
         // the key pass accumulates pass-0 per-tile counts with REDs: they start from zero
         L.counts_off[0] = off;
         off += (size_t)div_up(n, plan.npasses == 1 ? last_tile : kThreads * kScatterItems) << plan.bits[0];
@@ -321,14 +321,15 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
     }
     L.total_words = off;  // everything up to here is zeroed every frame
     for (uint32_t p = 0; p < plan.npasses; ++p) {
-        if (!(p == 0 && tile_offsets && zero_counts0)) {
+        const bool placed = tile_offsets || p + 1 == plan.npasses;  // the emit pass always uses tile offsets
+        if (!(p == 0 && zero_counts0)) {
             L.counts_off[p] = off;
-            if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+            if (placed) off += (size_t)L.tiles[p] << plan.bits[p];
         }
         L.offs_off[p] = off;
-        if (tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        if (placed) off += (size_t)L.tiles[p] << plan.bits[p];
         L.csum_off[p] = off;
-        if (tile_offsets) off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
+        if (placed) off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
     }
     L.alloc_words = off;
     return L;
@@ -648,7 +649,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
         p.keys_out = c->keys[0];
         p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
         p.lt_hist = c->scratch + L->lt_off;
-        if (L->tile_offsets && !fm.hier && c->plan.npasses == 1) {
+        if (!fm.hier && c->plan.npasses == 1) {
             p.tile_counts = c->scratch + L->counts_off[0];
             p.emit_tiles = L->tiles[0];
             p.emit_tile_shift = L->small ? 6u : 9u;
@@ -711,7 +712,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
         pp.status = c->scratch + L.status_off[p];
         pp.tile_counter = c->scratch + kHdrTileCounters + p;
         pp.ntiles = L.tiles[p];
-        if (L.tile_offsets) {
+        if (L.tile_offsets || last) {
             uint32_t* counts = c->scratch + L.counts_off[p];
             uint32_t* offs = c->scratch + L.offs_off[p];
             if (!(p == 0 && prepare_made_counts))
@@ -763,7 +764,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                           std::min<uint32_t>(div_up(L.tiles[p], kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
             } else {
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
-                          std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared), ep);
+                          std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared<KeyT>), ep);
             }
         }
     }
@@ -882,8 +883,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->rows.a = c->rows_mem;
     c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * max_entities;
     c->rows.stride = c->interleaved ? 4 : 2;
-    cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
-    cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
+    cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint32_t>));
+    cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
@@ -1325,7 +1326,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
-        const bool prepare_made_counts = c->tile_offsets != 0 && !fm.hier && plan.npasses == 1;
+        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
@@ -1345,7 +1346,9 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
                       (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
         }
-        if (!L.tile_offsets) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
+        // look-back placement (scatter passes only): bucket bases = exclusive scan of their histograms;
+        // the emit pass is always placed by tile offsets, which start from its raw histogram
+        if (!L.tile_offsets && plan.npasses > 1) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses - 1, 256, 0, hist);
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
@@ -1374,7 +1377,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
         // buckets that depend on the Sprite only (no varying z bit): the tile offsets stay valid until
         // a component changes, so the next frames can run as one kernel
-        if (c->static_buckets && L.small && L.tile_offsets && !fm.hier && !fm.lt_generic && plan.zbits == 0 && !plan.key64 &&
+        if (c->static_buckets && L.small && !fm.hier && !fm.lt_generic && plan.zbits == 0 && !plan.key64 &&
             num_batches <= c->max_batches) {
             c->static_valid = true;
             c->static_count = count;
@@ -1473,7 +1476,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
         tb_status s;
         const uint64_t n = c->n;
         FrameMode fm{};  // flat; the batch table comes from the global bins, not from pass A
-        const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
+        const bool prepare_made_counts = plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
@@ -1535,10 +1538,12 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     }
     if (c->shard_count > 0) {
         FrameMode fm{};
-        const bool prepare_made_counts = c->tile_offsets != 0 && plan.npasses == 1;
+        const bool prepare_made_counts = plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         uint32_t* hist = c->scratch + kHdrHist;
-        if (!L.tile_offsets) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses, 256, 0, hist);
+        // look-back placement (scatter passes only): bucket bases = exclusive scan of their histograms;
+        // the emit pass is always placed by tile offsets, which start from its raw histogram
+        if (!L.tile_offsets && plan.npasses > 1) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses - 1, 256, 0, hist);
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
