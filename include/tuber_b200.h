@@ -247,8 +247,11 @@ TB_API tb_status tb_frame_set_output(tb_ctx* ctx, void* d_instances, void* d_ver
  *                             over NVLink), and builds the global batch table.
  *
  * Exact for short keys up to TB_SHARD_MAX_KEY_BITS bits (tb_shard_plan returns TB_ERR_UNSUPPORTED
- * beyond, e.g. continuous z: such scenes need a merge at the presenting rank). Scenes with Parent
- * links across shards are not supported yet. */
+ * beyond, e.g. continuous z: such scenes need a merge at the presenting rank).
+ * Parent links must resolve inside the context: a shard additionally stores, after its own id
+ * range and WITHOUT a Sprite, the ancestors of its entities that live on other ranks, and uploads
+ * Parent values as global_first + local index. Their world matrices are then recomputed on this
+ * rank (a thin slice of a BFS-ordered tree) and no parent matrix ever crosses the link. */
 #define TB_SHARD_MAX_KEY_BITS 22
 TB_API tb_status tb_shard_key_stats(tb_ctx* ctx, uint64_t stats[3]);
 TB_API tb_status tb_shard_plan(tb_ctx* ctx, const uint64_t global_stats[3], uint64_t* nbins);

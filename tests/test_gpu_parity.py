@@ -605,3 +605,42 @@ def test_static_bucket_frame_detects_a_z_change():
     t = ctx.download_transforms(0, sc.n)
     np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref3.transforms().view(np.uint32))
     ctx.close()
+
+
+def test_sharded_scene_graph_with_ghost_ancestors():
+    """Parent links across shards: every shard also holds its entities' out-of-shard ancestors (no Sprite)
+    and recomputes their chain; the merged result equals the single-process oracle frame."""
+    from tuber_legacy_b200.shard import ancestor_closure, reduce_stats
+    for random_parents in (False, True):
+        sc = scenes.config3(n=60_000, seed=70, random_parents=random_parents)
+        v = np.zeros(sc.n, capi.VELOCITY_DTYPE)
+        v["v"][:, 0] = np.linspace(-30, 30, sc.n, dtype=np.float32)
+        sc.velocities = v
+        ref = util.make_oracle(sc)
+        n, nranks = sc.n, 3
+        bufs = [capi.device_alloc(n * 80), capi.device_alloc(n * 64), capi.device_alloc(n * 4)]
+        ctxs = []
+        for r in range(nranks):
+            first, cnt = scenes.shard_range(n, r, nranks)
+            ghosts, local_parents = ancestor_closure(sc.parents, first, cnt)
+            ids = np.concatenate([np.arange(first, first + cnt), ghosts.astype(np.int64)])
+            m = len(ids)
+            ctx = capi.Context(m)
+            ctx.shard_set(r, nranks, first)
+            ctx.set_entity_count(m)
+            ctx.upload_transforms(0, sc.transforms[ids])
+            ctx.upload_velocities(0, sc.velocities[ids])
+            ctx.upload_sprites(0, sc.sprites[first:first + cnt])     # own entities only: ghosts are never drawn
+            ctx.upload_parents(0, local_parents)
+            ctx.set_output(bufs[0], bufs[1], bufs[2], n)
+            ctxs.append(ctx)
+            if r > 0 and not random_parents:
+                assert 0 < len(ghosts) < cnt // 2   # BFS-ordered tree: a slice of ancestors, not the whole scene
+        ref.step(0.01)
+        g = _run_sharded(ctxs, bufs, ticks=1, dt=0.01)
+        assert g.info.hierarchy_levels == 8
+        util.assert_frame_parity(g, ref.frame())
+        for c in ctxs:
+            c.close()
+        for b in bufs:
+            capi.device_free(b)

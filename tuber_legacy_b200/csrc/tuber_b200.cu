@@ -1418,8 +1418,6 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
     stats[2] = 0;
     c->shard_state = 0;
     c->frame_valid = false;
-    if (c->store[TB_PARENT] && c->nranks > 1)
-        return fail(c, TB_ERR_UNSUPPORTED, "Parent links are not supported in a multi-GPU frame yet");
     tb_status s;
     c->shard_count = 0;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
@@ -1428,9 +1426,13 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
         c->shard_state = 1;
         return TB_OK;
     }
-    c->nlevels = 1;
-    c->levels_dirty = false;
+    // Parent links must resolve inside this context: a shard also holds (as entities without a
+    // Sprite, after its own id range) the ancestors of its entities that live on other ranks, and
+    // recomputes their world matrices itself — see shard.ancestor_closure / DESIGN.md §7.
+    if (c->levels_dirty && (s = plan_levels(c))) return s;
     FrameMode fm{};
+    fm.hier = c->nlevels > 1;
+    if (fm.hier && (s = ensure_world(c, c->n))) return s;
     const bool integrate = c->pending;
     c->pending = false;
     TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
@@ -1475,11 +1477,12 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
     if (c->shard_count > 0) {
         tb_status s;
         const uint64_t n = c->n;
-        FrameMode fm{};  // flat; the batch table comes from the global bins, not from pass A
-        const bool prepare_made_counts = plan.npasses == 1;
+        FrameMode fm{};  // the batch table comes from the global bins, not from pass A
+        fm.hier = c->nlevels > 1;
+        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
-        if (plan.npasses > 1 && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
         TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
         TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (L.total_words - kHdrTileCounters) * 4, c->stream));
         if ((s = run_prepare(c, true, false, fm, &L, (uint32_t*)d_hist))) return s;
@@ -1538,7 +1541,8 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     }
     if (c->shard_count > 0) {
         FrameMode fm{};
-        const bool prepare_made_counts = plan.npasses == 1;
+        fm.hier = c->nlevels > 1;
+        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
         uint32_t* hist = c->scratch + kHdrHist;
         // look-back placement (scatter passes only): bucket bases = exclusive scan of their histograms;
@@ -1568,6 +1572,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     out->key_bits = plan.pext.nbits;
     out->sort_passes = plan.npasses;
     out->kernel_launches = c->frame_launches;
+    out->hierarchy_levels = c->nlevels > 1 ? c->nlevels : 0;
     return TB_OK;
 }
 

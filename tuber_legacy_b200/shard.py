@@ -109,3 +109,41 @@ class ShardedFrame:
         if self.world > 1:
             dist.barrier(group=self.group)  # every rank's stores have landed in the presenter's buffers
         return out, total
+
+
+# ---- scene graphs across shards --------------------------------------------------------------------
+
+NO_PARENT = 0xFFFFFFFF
+
+
+def ancestor_closure(parents, first, count):
+    """Which entities of other shards a shard must also hold so that every Parent link of its own
+    entities resolves locally (the chain's world matrices are then recomputed on this rank: no
+    exchange of parent matrices at all).
+
+    parents: global uint32 array (NO_PARENT for roots). Returns (ghost_ids, local_parents):
+      ghost_ids      ascending global ids of the ancestors outside [first, first+count): the shard
+                     stores them after its own entities, WITHOUT a Sprite (they are never drawn);
+      local_parents  the Parent column to upload for the count + len(ghost_ids) local entities, as
+                     the ids the C ABI expects after tb_shard_set(rank, nranks, first): first + local index.
+    """
+    parents = np.asarray(parents, dtype=np.uint32)
+    own = np.arange(first, first + count, dtype=np.int64)
+    in_own = lambda ids: (ids >= first) & (ids < first + count)  # noqa: E731
+    ghosts = np.zeros(0, dtype=np.int64)
+    frontier = own
+    while True:
+        p = parents[frontier].astype(np.int64)
+        p = p[p != NO_PARENT]
+        p = np.unique(p[~in_own(p)])
+        new = np.setdiff1d(p, ghosts, assume_unique=True)
+        if new.size == 0:
+            break
+        ghosts = np.union1d(ghosts, new)
+        frontier = new
+    local_ids = np.concatenate([own, ghosts])
+    p = parents[local_ids].astype(np.int64)
+    has = p != NO_PARENT
+    local_index = np.where(in_own(p), p - first, count + np.searchsorted(ghosts, p))
+    local_parents = np.where(has, first + local_index, NO_PARENT).astype(np.uint32)
+    return ghosts.astype(np.uint32), local_parents
