@@ -234,6 +234,34 @@ def main():
     ctx.profile_enable(False)
     assert info.num_instances == n
 
+    # ---- the same steps with nothing reused between frames --------------------------------------
+    # (static_buckets=0: key pass + tile offsets + emit every frame; reported beside `value`)
+    full = None
+    if info.kernel_launches == 1:
+        ctx.set_option("static_buckets", 0)
+        for _ in range(3):
+            step()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0.record(stream)
+        for _ in range(args.steps):
+            finfo = step()
+        h1.record(stream)
+        barrier()
+        full_ms = h0.elapsed_time(h1)
+        if world > 1:
+            t_ = torch.tensor([full_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            full_ms = float(t_[0])
+        full = {"value": n * world * args.steps / (full_ms * 1e-3), "unit": UNIT, "ms_per_step": full_ms / args.steps,
+                "kernels_per_frame": int(finfo.kernel_launches),
+                "frame_roofline_frac": n * ALG_BYTES_FRAME / (full_ms / args.steps * 1e-3) / 1e9 / measured_peaks()[0],
+                "what": "static_buckets=0: nothing cached between frames (key pass, bucket counts, tile offsets and "
+                        "emit every frame)"}
+        ctx.set_option("static_buckets", 1)
+        for _ in range(2):
+            step()
+
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     # Every step: H2D of all three component arrays from pinned memory, tick + frame, D2H of instances,
     # vertices, order and the batch table. PCIe is full duplex, so the steps are double-buffered the way a
@@ -434,6 +462,8 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
             except Exception:
                 pass
+        if full is not None:
+            line["full_recompute_every_frame"] = full
         if gather is not None:
             line["gather_to_rank0"] = gather
         if world == 1 and not args.no_cpu:

@@ -134,8 +134,6 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *   "interleaved_rows" 0|1  one 64-byte row per entity instead of two 32-byte sector arrays
  *                           (only before the first upload)
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
- *   "tile_offsets"     0|1  single-pass flat frames place tiles from per-tile counts made by the
- *                           key pass instead of a decoupled look-back (default 1)
  *   "static_buckets"   0|1  flat few-bucket scenes whose buckets depend on the Sprite only (no varying z
  *                           bit) reuse the per-tile offsets of the last full frame until a component is
  *                           uploaded: the steady-state frame is one kernel, validated every frame (default 1)

@@ -41,8 +41,8 @@ def test_config2_1M_flat_full_size():
     sample_matches_oracle(sc, g)
     assert checksum(g) == checksum(util.GpuFrame(ctx))  # idempotent
     ctx.close()
-    # narrower digits / look-back placement / unstaged stores: same bytes
-    for opts in ({"digit_bits": 5}, {"tile_offsets": 0}, {"staged_emit": 0, "lt_limit": 0}):
+    # narrower digits / interleaved rows / unstaged stores + generic batches: same bytes
+    for opts in ({"digit_bits": 5}, {"interleaved_rows": 1}, {"staged_emit": 0, "lt_limit": 0}):
         c2 = util.make_ctx(sc, **opts)
         assert checksum(util.GpuFrame(c2)) == checksum(g), opts
         c2.close()
@@ -102,8 +102,8 @@ def test_config4_16M_particles_full_size():
     np.testing.assert_array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
     sc.transforms["translation"][:] = got
     sample_matches_oracle(sc, g)
-    # the look-back placement gives the same bytes
-    c2 = util.make_ctx(sc, tile_offsets=0)
+    # the CTA-tile emit, with nothing cached, gives the same bytes
+    c2 = util.make_ctx(sc, small_emit=0, static_buckets=0)
     assert checksum(util.GpuFrame(c2)) == checksum(g)
     c2.close()
     ctx.close()

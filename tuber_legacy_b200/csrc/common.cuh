@@ -11,20 +11,9 @@ namespace tb {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
-constexpr uint32_t kFlagLocal = 1u << 30;   // decoupled look-back status words (tile_offsets == 0 only)
-constexpr uint32_t kFlagIncl = 2u << 30;
-constexpr uint32_t kCountMask = (1u << 30) - 1u;
 
 // ---- small helpers ---------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Streaming (evict-first) 128-bit store: emitted buffers are written once and not re-read by
 // this frame, so they should not displace the rows / keys that are.
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) { __stcs(p, v); }
@@ -76,6 +65,44 @@ struct WorldRow {
 __device__ __forceinline__ uint64_t world_key(const float4 r2, const float4 s) {
     const uint32_t tl = __float_as_uint(s.z);
     return sort_key(tl >> 16, tl & 0xFFFFu, r2.w);
+}
+
+// ---- asynchronous copies into shared memory: mbarrier + TMA bulk (cp.async.bulk), cp.async ------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map): size and both addresses multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace tb

@@ -8,24 +8,6 @@ namespace tb {
 
 // ---- histogram -> bucket bases; (layer, texture) histogram -> batch table -----------------------
 
-// One block per radix pass: exclusive scan of its 256-bin digit histogram, in place.
-__global__ void __launch_bounds__(256) scan_hist_kernel(uint32_t* hist) {
-    __shared__ uint32_t wsum[8];
-    uint32_t* h = hist + blockIdx.x * 256;
-    const uint32_t v = h[threadIdx.x];
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
-    __syncthreads();
-    uint32_t add = 0;
-    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) add += wsum[w];
-    h[threadIdx.x] = x + add - v;
-}
-
 // First output position of every (digit, tile) of one pass from its per-tile digit counts
 // (reduce-then-scan radix placement: no inter-CTA waiting anywhere). counts and tile_off are
 // digit-major [R][ntiles]; hist is the pass's raw 256-bin digit histogram. Two launches over a
@@ -85,7 +67,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 }
 
 // Per-tile digit counts of one pass's input (positions in the pass's input order).
-// counts is digit-major [R][ntiles]. One block per tile.
+// counts is digit-major [R][ntiles]. One block per tile; four independent loads in flight per thread.
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) tile_hist_kernel(const KeyT* __restrict__ keys, uint32_t n,
                                                               const unsigned long long* count_ptr,
@@ -98,11 +80,19 @@ __global__ void __launch_bounds__(kThreads) tile_hist_kernel(const KeyT* __restr
     for (uint32_t d = threadIdx.x; d < R; d += kThreads) h[d] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * tile_elems;
-    for (uint32_t k = threadIdx.x; k < tile_elems; k += kThreads) {
-        const uint32_t pos = base + k;
-        bool valid = pos < n_eff;
-        if (valid && first) valid = mask_bit(mask_t, pos) && mask_bit(mask_s, pos);
-        if (valid) atomicAdd(&h[(uint32_t)(keys[pos] >> shift) & mask], 1u);
+    for (uint32_t k0 = threadIdx.x; k0 < tile_elems; k0 += 4 * kThreads) {
+        KeyT key[4];
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k = k0 + j * kThreads, pos = base + k;
+            valid[j] = k < tile_elems && pos < n_eff;
+            key[j] = valid[j] ? keys[pos] : (KeyT)0;
+            if (valid[j] && first) valid[j] = mask_bit(mask_t, pos) && mask_bit(mask_s, pos);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (valid[j]) atomicAdd(&h[(uint32_t)(key[j] >> shift) & mask], 1u);
     }
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < R; d += kThreads) counts[(size_t)d * ntiles + blockIdx.x] = h[d];
@@ -113,8 +103,7 @@ struct BatchOut {
 };
 
 // Every non-empty (layer, texture) bin is one batch: first = exclusive prefix, count = bin.
-// `bins` has 1 << ltbits entries (when it aliases digit pass 0 it must be read BEFORE
-// scan_hist_kernel rewrites it: the host orders the launches). Single block.
+// `bins` has 1 << ltbits entries (it may alias the raw digit histogram of pass 0). Single block.
 __global__ void __launch_bounds__(1024) build_batches_kernel(const uint32_t* __restrict__ bins, uint32_t nbins,
                                                               FramePlan plan, BatchOut* out, uint32_t max_batches,
                                                               uint32_t* num_batches) {
@@ -170,7 +159,6 @@ struct RankShared {
     uint32_t dstart[256];         // first tile slot of each digit
     uint32_t dbase[256];          // destination of digit d's slot s is dbase[d] + s
     uint32_t wsum[kWarps];
-    uint32_t tile;
     uint32_t tile_count;
 };
 
@@ -179,11 +167,8 @@ struct PassParams {
     const unsigned long long* count_ptr;  // when non-null only positions < *count_ptr hold elements
                                           // (passes after the first: the renderable count lives on the device)
     uint32_t shift, bits;    // this pass's digit of the short key
-    const uint32_t* gbase;   // exclusive scan of this pass's digit histogram
-    uint32_t* status;        // [tiles][1 << bits] look-back words, zeroed per frame
-    uint32_t* tile_counter;  // zeroed per frame
-    const uint32_t* tile_off;  // optional [1 << bits][ntiles]: first output position of each (digit, tile),
-                               // precomputed from per-tile counts; replaces the look-back
+    const uint32_t* tile_off;  // [1 << bits][ntiles]: first output position of each (digit, tile), from the
+                               // per-tile digit counts (tile_chunk_sums + tile_scan)
     uint32_t ntiles;           // tiles of this pass (row length of tile_off)
 };
 
@@ -195,11 +180,10 @@ __device__ __forceinline__ void rank_reset(RankShared& rs, uint32_t bits) {
 }
 
 // Ranks ITEMS digits per thread (warp-striped order: item k of lane l in warp w is element
-// w*ITEMS*32 + k*32 + l of the tile) into stable tile slots and leaves dbase[] ready: from the
-// precomputed tile offsets when the pass has them, else by publishing the tile's digit counts
-// and looking back over the preceding tiles (decoupled look-back). Invalid items (kInvalidDigit)
-// get no slot. Needs rank_reset() + __syncthreads() before, and a __syncthreads() before the
-// next rank_reset().
+// w*ITEMS*32 + k*32 + l of the tile) into stable tile slots, and leaves dbase[] ready from the
+// pass's precomputed tile offsets (no CTA ever waits for another). Invalid items (kInvalidDigit)
+// get no slot. Needs rank_reset() + __syncthreads() before, and a __syncthreads() before the next
+// rank_reset().
 template <int ITEMS>
 __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, const uint32_t tile,
                                           const uint32_t (&digit)[ITEMS], uint32_t (&slot)[ITEMS]) {
@@ -222,9 +206,10 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive prefix over warps, tile total
-    uint32_t total = 0;
+    // per digit: exclusive prefix over warps, tile total; the tile offset load overlaps the scan
+    uint32_t total = 0, toff = 0;
     if (threadIdx.x < R) {
+        toff = __ldg(pp.tile_off + (size_t)threadIdx.x * pp.ntiles + tile);
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t c = rs.wcnt[w * R + threadIdx.x];
@@ -232,10 +217,6 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
             total += c;
         }
     }
-    const bool lookback = pp.tile_off == nullptr;
-    // publish the local count as early as possible
-    uint32_t* st = pp.status + (size_t)tile * R + threadIdx.x;
-    if (lookback && threadIdx.x < R) st_relaxed_u32(st, (tile == 0 ? kFlagIncl : kFlagLocal) | total);
     // block exclusive scan of the totals -> dstart (all digits live in warp 0 when R <= 32)
     uint32_t x = total;
 #pragma unroll
@@ -257,23 +238,7 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
     const uint32_t dstart = x + add - total;
     if (threadIdx.x < R) {
         rs.dstart[threadIdx.x] = dstart;
-        if (lookback) {
-            uint32_t excl = 0;
-            if (tile > 0) {
-                for (int t = (int)tile - 1; t >= 0; --t) {
-                    uint32_t v;
-                    do {
-                        v = ld_relaxed_u32(pp.status + (size_t)t * R + threadIdx.x);
-                    } while ((v >> 30) == 0u);
-                    excl += v & kCountMask;
-                    if ((v >> 30) == 2u) break;
-                }
-                st_relaxed_u32(st, kFlagIncl | (excl + total));
-            }
-            rs.dbase[threadIdx.x] = pp.gbase[threadIdx.x] + excl - dstart;
-        } else {
-            rs.dbase[threadIdx.x] = __ldg(pp.tile_off + (size_t)threadIdx.x * pp.ntiles + tile) - dstart;
-        }
+        rs.dbase[threadIdx.x] = toff - dstart;
     }
     __syncthreads();
 #pragma unroll
@@ -281,12 +246,6 @@ __device__ __forceinline__ void rank_tile(RankShared& rs, const PassParams& pp, 
         const uint32_t d = digit[k];
         if (d != kInvalidDigit) slot[k] += rs.dstart[d] + rs.wcnt[warp * R + d];
     }
-}
-
-__device__ __forceinline__ void claim_tile(RankShared& rs, const PassParams& pp) {
-    if (threadIdx.x == 0) rs.tile = atomicAdd(pp.tile_counter, 1u);
-    rank_reset(rs, pp.bits);
-    __syncthreads();
 }
 
 // ---- one LSD scatter pass of (short key, entity) pairs ------------------------------------------
@@ -302,51 +261,107 @@ struct ScatterParams {
     uint32_t* idx_out;
 };
 
-constexpr int kScatterItems = 12;
+constexpr int kScatterItems = 8;
+constexpr uint32_t kScatterTile = kThreads * kScatterItems;  // 2048 pairs per tile
 
+// Dynamic shared memory of radix_scatter_kernel: 58 KB with 32-bit keys, three CTAs per SM.
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const ScatterParams<KeyT> sp) {
+struct ScatterShared {
+    KeyT kin[2][kScatterTile];          // this tile's keys and the prefetched next tile's (TMA bulk copies)
+    uint32_t iin[2][kScatterTile];      // ... entity ids
+    unsigned long long masks[2][2][kScatterTile / 64 + 2];  // ... presence words (first pass)
+    KeyT s_key[kScatterTile];           // the tile in sorted order
+    uint32_t s_idx[kScatterTile];
+    RankShared rs;
+    unsigned long long mbar[2];
+};
+
+// One stable LSD pass. Persistent CTAs walk 2048-pair tiles (tile = blockIdx.x + k * gridDim.x); the
+// next tile's keys / ids / presence words are prefetched by TMA bulk copies while the current tile is
+// ranked, ordered in shared memory and written out in runs of consecutive destinations.
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const ScatterParams<KeyT> sp) {
     constexpr int ITEMS = kScatterItems;
-    constexpr uint32_t TILE = kThreads * ITEMS;
-    __shared__ RankShared rs;
-    __shared__ KeyT s_key[TILE];
-    __shared__ uint32_t s_idx[TILE];
-    claim_tile(rs, sp.pass);
+    constexpr uint32_t TILE = kScatterTile;
+    extern __shared__ __align__(128) unsigned char scatter_smem_raw[];
+    ScatterShared<KeyT>& sm = *reinterpret_cast<ScatterShared<KeyT>*>(scatter_smem_raw);
+    RankShared& rs = sm.rs;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile_base = rs.tile * TILE;
-    const uint32_t mask = (1u << sp.pass.bits) - 1u;
-    KeyT key[ITEMS];
-    uint32_t idx[ITEMS], digit[ITEMS], slot[ITEMS];
+    const bool first = sp.idx_in == nullptr;
     const uint32_t n_eff = sp.pass.count_ptr ? min(sp.pass.n, (uint32_t)*sp.pass.count_ptr) : sp.pass.n;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const uint32_t pos = tile_base + warp * (ITEMS * 32) + k * 32 + lane;
-        bool valid = pos < n_eff;
-        if (valid && sp.idx_in == nullptr) valid = mask_bit(sp.mask_t, pos) && mask_bit(sp.mask_s, pos);
-        key[k] = 0;
-        idx[k] = pos;
-        if (valid) {
-            key[k] = sp.keys_in[pos];
-            if (sp.idx_in != nullptr) idx[k] = sp.idx_in[pos];
-        }
-        digit[k] = valid ? ((uint32_t)(key[k] >> sp.pass.shift) & mask) : kInvalidDigit;
+    const uint32_t ntiles = sp.pass.ntiles;
+    const uint32_t mask = (1u << sp.pass.bits) - 1u;
+    const uint32_t step = gridDim.x;
+    auto tile_count = [&](uint32_t tile) -> uint32_t {
+        const uint32_t base = tile * TILE;
+        return (tile < ntiles && base < n_eff) ? min(TILE, n_eff - base) : 0u;
+    };
+    auto fetch = [&](uint32_t tile, uint32_t buf) {  // thread 0
+        const uint32_t base = tile * TILE;
+        const uint32_t cnt = tile_count(tile);
+        if (cnt == 0) return;
+        const uint32_t kbytes = (cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u;
+        const uint32_t ibytes = first ? 0u : ((cnt * 4u + 15u) & ~15u);
+        const uint32_t mwords = ((cnt + 127u) >> 7) * 2u;
+        const uint32_t mbytes = first ? ((sp.mask_t ? 1u : 0u) + (sp.mask_s ? 1u : 0u)) * mwords * 8u : 0u;
+        mbar_expect_tx(&sm.mbar[buf], kbytes + ibytes + mbytes);
+        bulk_g2s(sm.kin[buf], sp.keys_in + base, kbytes, &sm.mbar[buf]);
+        if (!first) bulk_g2s(sm.iin[buf], sp.idx_in + base, ibytes, &sm.mbar[buf]);
+        if (first && sp.mask_t) bulk_g2s(sm.masks[buf][0], sp.mask_t + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+        if (first && sp.mask_s) bulk_g2s(sm.masks[buf][1], sp.mask_s + (base >> 6), mwords * 8u, &sm.mbar[buf]);
+    };
+    uint32_t tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        fetch(tile, 0);
     }
-    rank_tile<ITEMS>(rs, sp.pass, rs.tile, digit, slot);
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (digit[k] != kInvalidDigit) {
-            s_key[slot[k]] = key[k];
-            s_idx[slot[k]] = idx[k];
-        }
-    }
+    rank_reset(rs, sp.pass.bits);
     __syncthreads();
-    const uint32_t cnt = rs.tile_count;
-    for (uint32_t s = threadIdx.x; s < cnt; s += kThreads) {
-        const KeyT kk = s_key[s];
-        const uint32_t d = (uint32_t)(kk >> sp.pass.shift) & mask;
-        const uint32_t dst = rs.dbase[d] + s;
-        sp.keys_out[dst] = kk;
-        sp.idx_out[dst] = s_idx[s];
+    uint32_t cur = 0, parity0 = 0, parity1 = 0;
+    for (; tile < ntiles; tile += step) {
+        if (threadIdx.x == 0) fetch(tile + step, cur ^ 1u);  // buffer freed by the last barrier
+        const uint32_t tile_base = tile * TILE;
+        const uint32_t tcnt = tile_count(tile);
+        if (tcnt) {
+            mbar_wait(&sm.mbar[cur], cur ? parity1 : parity0);
+            if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+        }
+        KeyT key[ITEMS];
+        uint32_t idx[ITEMS], digit[ITEMS], slot[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
+            bool valid = li < tcnt;
+            if (valid && first) {
+                const bool t_ok = sp.mask_t == nullptr || ((sm.masks[cur][0][li >> 6] >> (li & 63u)) & 1ull);
+                const bool s_ok = sp.mask_s == nullptr || ((sm.masks[cur][1][li >> 6] >> (li & 63u)) & 1ull);
+                valid = t_ok && s_ok;
+            }
+            key[k] = valid ? sm.kin[cur][li] : (KeyT)0;
+            idx[k] = first ? tile_base + li : (valid ? sm.iin[cur][li] : 0u);
+            digit[k] = valid ? ((uint32_t)(key[k] >> sp.pass.shift) & mask) : kInvalidDigit;
+        }
+        rank_tile<ITEMS>(rs, sp.pass, tile, digit, slot);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (digit[k] != kInvalidDigit) {
+                sm.s_key[slot[k]] = key[k];
+                sm.s_idx[slot[k]] = idx[k];
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = rs.tile_count;
+        for (uint32_t s = threadIdx.x; s < cnt; s += kThreads) {
+            const KeyT kk = sm.s_key[s];
+            const uint32_t d = (uint32_t)(kk >> sp.pass.shift) & mask;
+            const uint32_t dst = rs.dbase[d] + s;
+            sp.keys_out[dst] = kk;
+            sp.idx_out[dst] = sm.s_idx[s];
+        }
+        rank_reset(rs, sp.pass.bits);
+        __syncthreads();  // releases the input buffer, the sorted tile and the rank scratch
+        cur ^= 1u;
     }
 }
 

@@ -97,7 +97,6 @@ struct tb_ctx {
     uint32_t force_path = TB_PATH_NONE;
     int digit_bits = kMaxDigitBits;
     int staged_emit = 1;
-    int tile_offsets = 1;
     int small_emit = 1;
     int lt_limit = (int)kMaxLtBits;
 
@@ -282,13 +281,11 @@ tb_status flush_integrate(tb_ctx* c) {
 struct ScratchLayout {
     size_t lt_off = 0, lt_words = 0;
     uint32_t tiles[kMaxPasses];
-    size_t status_off[kMaxPasses];   // look-back words (only with tile_offsets == 0)
-    size_t counts_off[kMaxPasses];   // per-tile digit counts  [R][tiles]  (tile_offsets == 1)
+    uint32_t tile_elems[kMaxPasses];
+    size_t counts_off[kMaxPasses];   // per-tile digit counts  [R][tiles]
     size_t offs_off[kMaxPasses];     // per-tile digit offsets [R][tiles]
     size_t csum_off[kMaxPasses];     // per-chunk (1024 tiles) sums [R][chunks]
-    uint32_t tile_elems[kMaxPasses];
     bool small = false;              // last pass runs the warp-autonomous few-bucket emit
-    bool tile_offsets = true;
     size_t total_words = 0, alloc_words = 0;
 };
 
@@ -296,40 +293,36 @@ bool use_small_emit(const tb_ctx* c, const FramePlan& plan) {
     return c->small_emit != 0 && plan.npasses == 1 && plan.bits[0] <= kSmallMaxBits;
 }
 
-ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool tile_offsets, bool zero_counts0,
-                             bool small = false) {
+// Scratch of one frame under a plan: [header | (layer,texture) bins | pass-0 tile counts when the key
+// pass accumulates them] is zeroed every frame; the tile count / offset tables behind it are fully
+// overwritten by tile_hist / tile_scan.
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool zero_counts0, bool small = false) {
     ScratchLayout L;
-    L.tile_offsets = tile_offsets;
     L.small = small;
     size_t off = kHdrWords;
     L.lt_off = off;
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
     off += L.lt_words;
-    const uint32_t last_tile = small ? kWarpTile : kThreads * kEmitItems;
+    for (uint32_t p = 0; p < plan.npasses; ++p) {
+        const bool last = p + 1 == plan.npasses;
+        L.tile_elems[p] = last ? (small ? kWarpTile : kEmitTile) : kScatterTile;
+        L.tiles[p] = div_up(n, L.tile_elems[p]);
+    }
     if (zero_counts0) {
         // the key pass accumulates pass-0 per-tile counts with REDs: they start from zero
         L.counts_off[0] = off;
-        off += (size_t)div_up(n, plan.npasses == 1 ? last_tile : kThreads * kScatterItems) << plan.bits[0];
-    }
-    for (uint32_t p = 0; p < plan.npasses; ++p) {
-        const bool last = p + 1 == plan.npasses;
-        const uint32_t tile = last ? last_tile : kThreads * kScatterItems;
-        L.tile_elems[p] = tile;
-        L.tiles[p] = div_up(n, tile);
-        L.status_off[p] = off;
-        if (!tile_offsets) off += (size_t)L.tiles[p] << plan.bits[p];
+        off += (size_t)L.tiles[0] << plan.bits[0];
     }
     L.total_words = off;  // everything up to here is zeroed every frame
     for (uint32_t p = 0; p < plan.npasses; ++p) {
-        const bool placed = tile_offsets || p + 1 == plan.npasses;  // the emit pass always uses tile offsets
         if (!(p == 0 && zero_counts0)) {
             L.counts_off[p] = off;
-            if (placed) off += (size_t)L.tiles[p] << plan.bits[p];
+            off += (size_t)L.tiles[p] << plan.bits[p];
         }
         L.offs_off[p] = off;
-        if (placed) off += (size_t)L.tiles[p] << plan.bits[p];
+        off += (size_t)L.tiles[p] << plan.bits[p];
         L.csum_off[p] = off;
-        if (placed) off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
+        off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
     }
     L.alloc_words = off;
     return L;
@@ -433,7 +426,7 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     split_digits(nbits, kMaxDigitBits, &ds);
     tb_status s = ensure_sort_buffers(c, n, 4);
     if (s) return s;
-    const uint32_t tile = kThreads * kScatterItems;
+    const uint32_t tile = kScatterTile;
     const uint32_t tiles = div_up(n, tile);
     size_t words = kHdrWords;
     size_t counts_off[kMaxPasses], offs_off[kMaxPasses], csum_off[kMaxPasses];
@@ -472,9 +465,6 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
         sp.pass.count_ptr = nullptr;
         sp.pass.shift = ds.shift[p];
         sp.pass.bits = ds.bits[p];
-        sp.pass.gbase = nullptr;
-        sp.pass.status = nullptr;
-        sp.pass.tile_counter = c->scratch + kHdrTileCounters + p;
         sp.pass.tile_off = offs;
         sp.pass.ntiles = tiles;
         sp.keys_in = kin;
@@ -483,7 +473,8 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
         sp.mask_s = nullptr;
         sp.keys_out = (uint32_t*)c->keys[cur];
         sp.idx_out = c->idx[cur];
-        TB_LAUNCH(c, "level_sort", 0, radix_scatter_kernel<uint32_t>, tiles, kThreads, 0, sp);
+        TB_LAUNCH(c, "level_sort", 0, radix_scatter_kernel<uint32_t>, std::min<uint32_t>(tiles, 3u * (uint32_t)c->sm_count), kThreads,
+                  sizeof(ScatterShared<uint32_t>), sp);
         kin = (const uint32_t*)c->keys[cur];
         iin = c->idx[cur];
         cur ^= 1;
@@ -510,9 +501,10 @@ tb_status plan_levels(tb_ctx* c) {
         c->level_cap = n;
     }
     uint32_t* tmp = nullptr;
-    TB_CUDA(c, cudaMalloc((void**)&tmp, (size_t)n * 4 * 4));
-    uint32_t* hop[2] = {tmp, tmp + n};
-    uint32_t* dist[2] = {tmp + 2 * (size_t)n, tmp + 3 * (size_t)n};
+    const size_t stride = ((size_t)n + 3) & ~(size_t)3;  // 16-byte aligned columns: the level sort reads them by TMA
+    TB_CUDA(c, cudaMalloc((void**)&tmp, stride * 4 * 4 + 16));
+    uint32_t* hop[2] = {tmp, tmp + stride};
+    uint32_t* dist[2] = {tmp + 2 * stride, tmp + 3 * stride};
     tb_status s = ensure_scratch(c, kHdrWords);
     if (s) {
         cudaFree(tmp);
@@ -708,11 +700,8 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
         pp.count_ptr = iin ? d_count : nullptr;
         pp.shift = plan.shift[p];
         pp.bits = plan.bits[p];
-        pp.gbase = hist + p * 256;
-        pp.status = c->scratch + L.status_off[p];
-        pp.tile_counter = c->scratch + kHdrTileCounters + p;
         pp.ntiles = L.tiles[p];
-        if (L.tile_offsets || last) {
+        {
             uint32_t* counts = c->scratch + L.counts_off[p];
             uint32_t* offs = c->scratch + L.offs_off[p];
             if (!(p == 0 && prepare_made_counts))
@@ -737,8 +726,8 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             sp.mask_s = mask_or_null(c, TB_SPRITE);
             sp.keys_out = (KeyT*)c->keys[cur];
             sp.idx_out = c->idx[cur];
-            TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>, L.tiles[p],
-                      kThreads, 0, sp);
+            TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>,
+                      std::min<uint32_t>(L.tiles[p], 3u * (uint32_t)c->sm_count), kThreads, sizeof(ScatterShared<KeyT>), sp);
             kin = (const KeyT*)c->keys[cur];
             iin = c->idx[cur];
             cur ^= 1;
@@ -885,6 +874,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->rows.stride = c->interleaved ? 4 : 2;
     cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint32_t>));
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
+    cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
+    cudaFuncSetAttribute(radix_scatter_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint64_t>));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
@@ -964,8 +955,6 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     } else if (k == "small_emit") {
         c->static_valid = false;
         c->small_emit = value != 0;
-    } else if (k == "tile_offsets") {
-        c->tile_offsets = value != 0;
     } else if (k == "digit_bits") {
         if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
         c->digit_bits = (int)value;
@@ -1327,7 +1316,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
         const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
         if (fm.lt_generic) {
@@ -1346,9 +1335,6 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
                       (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
         }
-        // look-back placement (scatter passes only): bucket bases = exclusive scan of their histograms;
-        // the emit pass is always placed by tile offsets, which start from its raw histogram
-        if (!L.tile_offsets && plan.npasses > 1) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses - 1, 256, 0, hist);
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
@@ -1480,7 +1466,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
         FrameMode fm{};  // the batch table comes from the global bins, not from pass A
         fm.hier = c->nlevels > 1;
         const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
+        const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
         TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
@@ -1543,11 +1529,8 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
         FrameMode fm{};
         fm.hier = c->nlevels > 1;
         const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
-        const ScratchLayout L = layout_scratch(plan, n, false, c->tile_offsets != 0, prepare_made_counts, use_small_emit(c, plan));
+        const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
         uint32_t* hist = c->scratch + kHdrHist;
-        // look-back placement (scatter passes only): bucket bases = exclusive scan of their histograms;
-        // the emit pass is always placed by tile offsets, which start from its raw histogram
-        if (!L.tile_offsets && plan.npasses > 1) TB_LAUNCH(c, "scan_hist", 0, scan_hist_kernel, plan.npasses - 1, 256, 0, hist);
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
