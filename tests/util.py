@@ -111,7 +111,6 @@ def check_frame_properties(ctx, gpu, n_expected):
     u = z.view(np.uint32).astype(np.uint64)
     u = np.where(u >> np.uint64(31), u ^ np.uint64(0xFFFFFFFF), u ^ np.uint64(0x80000000))
     key = (inst["layer"].astype(np.uint64) << np.uint64(48)) | (inst["texture"].astype(np.uint64) << np.uint64(32)) | u
-    dk = np.diff(key.astype(np.int64)) if False else None
     ks, ke = key[:-1], key[1:]
     assert np.all(ks <= ke), "keys not sorted"
     tie = ks == ke

@@ -17,7 +17,6 @@ constexpr uint32_t kInvalidDigit = 0xFFFFFFFFu;
 // Streaming (evict-first) 128-bit store: emitted buffers are written once and not re-read by
 // this frame, so they should not displace the rows / keys that are.
 __device__ __forceinline__ void st_cs_f4(float4* p, float4 v) { __stcs(p, v); }
-__device__ __forceinline__ float4 ld_nc_f4(const float4* p) { return __ldg(p); }
 
 __device__ __forceinline__ bool mask_bit(const uint64_t* mask, uint32_t i) {
     return mask == nullptr || ((__ldg(mask + (i >> 6)) >> (i & 63u)) & 1ull);

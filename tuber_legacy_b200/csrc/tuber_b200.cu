@@ -137,15 +137,17 @@ struct tb_ctx {
 
 namespace {
 
-// scratch header layout (32-bit words)
-constexpr size_t kHdrStats = 0;        // 3 x u64: OR(key), OR(~key), renderable count
-constexpr size_t kHdrNumBatches = 6;   // u32
-constexpr size_t kHdrRangeErr = 7;     // u32 (sprite range violations since last check)
-constexpr size_t kHdrPending = 8;      // u32 scratch for level planning
-constexpr size_t kHdrLevelStats = 9;   // 2 x u32
-constexpr size_t kHdrTileCounters = 12;  // kMaxPasses + 1 x u32
-constexpr size_t kHdrHist = 32;          // kMaxPasses * 256 u32
-constexpr size_t kHdrWords = kHdrHist + kMaxPasses * 256;  // then lt_hist, then look-back words
+// scratch header layout (32-bit words). Words [0, kHdrFrame) outlive a frame; everything from
+// kHdrFrame up to ScratchLayout::total_words is zeroed by ONE memset at the start of every frame.
+constexpr size_t kHdrRangeErr = 0;     // u32: sprite range violations since the last check
+constexpr size_t kHdrPending = 1;      // u32: scratch of the level planner
+constexpr size_t kHdrLevelStats = 2;   // 2 x u32
+constexpr size_t kHdrFrame = 4;
+constexpr size_t kHdrStats = 4;        // 3 x u64: OR(key), OR(~key), renderable count
+constexpr size_t kHdrNumBatches = 10;  // u32
+constexpr size_t kHdrReadWords = 8;    // what a frame copies back: stats + batch count
+constexpr size_t kHdrHist = 16;        // kMaxPasses * 256 u32: raw digit histograms
+constexpr size_t kHdrWords = kHdrHist + kMaxPasses * 256;  // then (layer,texture) bins, tile tables
 
 tb_status fail(tb_ctx* c, tb_status s, const std::string& msg) {
     if (c) c->err = msg;
@@ -440,7 +442,7 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     }
     s = ensure_scratch(c, words);
     if (s) return s;
-    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (kHdrWords - kHdrTileCounters) * 4, c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrHist, 0, (kHdrWords - kHdrHist) * 4, c->stream));
     uint32_t* hist = c->scratch + kHdrHist;
     TB_LAUNCH(c, "level_key_hist", 0, key_hist_kernel, div_up(n, kThreads), kThreads, 0, d_keys, n, ds, hist);
     const uint32_t* kin = d_keys;
@@ -675,7 +677,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
 }
 
 tb_status read_header(tb_ctx* c) {
-    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
@@ -769,7 +771,7 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     *ok = false;
     const uint32_t n = (uint32_t)c->n;
     const FramePlan& plan = c->plan;
-    TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrNumBatches * 4, c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrStats, 0, 6 * 4, c->stream));
     EmitParams<uint32_t> ep{};
     ep.pass.n = n;
     ep.pass.shift = plan.shift[0];
@@ -1301,7 +1303,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     for (int attempt = 0; attempt < 4 && !fast_done; ++attempt) {
         if (!c->plan_valid) {
             // discovery: key statistics only (and the velocity system, exactly once)
-            TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+            TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
             if ((s = run_prepare(c, false, integrate, fm, nullptr))) return s;
             integrate = false;
             if ((s = read_header(c))) return s;
@@ -1325,8 +1327,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             c->texlayer_cap = cap;
         }
         // zero: stats, num_batches | tile counters, histograms, lt bins, look-back words
-        TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
-        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (L.total_words - kHdrTileCounters) * 4, c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
         if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
         integrate = false;
         uint32_t* hist = c->scratch + kHdrHist;
@@ -1360,7 +1361,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
                       c->scratch + kHdrNumBatches, (uint32_t)c->max_batches, (uint32_t)count);
             if ((s = read_header(c))) return s;
         }
-        num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
+        num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches - kHdrFrame];
         // buckets that depend on the Sprite only (no varying z bit): the tile offsets stay valid until
         // a component changes, so the next frames can run as one kernel
         if (c->static_buckets && L.small && !fm.hier && !fm.lt_generic && plan.zbits == 0 && !plan.key64 &&
@@ -1421,7 +1422,7 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
     if (fm.hier && (s = ensure_world(c, c->n))) return s;
     const bool integrate = c->pending;
     c->pending = false;
-    TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
     if ((s = run_prepare(c, false, integrate, fm, nullptr))) return s;
     if ((s = read_header(c))) return s;
     stats[0] = c->h_hdr[0];
@@ -1469,8 +1470,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
         const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
-        TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
-        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrTileCounters, 0, (L.total_words - kHdrTileCounters) * 4, c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
         if ((s = run_prepare(c, true, false, fm, &L, (uint32_t*)d_hist))) return s;
     }
     TB_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller's collective may run on another stream
@@ -1536,7 +1536,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
         if (s) return s;
     }
     if ((s = read_header(c))) return s;
-    if (c->shard_global_count > 0) num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches];
+    if (c->shard_global_count > 0) num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches - kHdrFrame];
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(c, e, "frame");
     if (c->prof) prof_harvest(c);
@@ -1640,7 +1640,7 @@ tb_status tb_download_world_matrices(tb_ctx* c, uint64_t first, uint64_t n, floa
             FrameMode fm{};
             fm.hier = true;
             if ((s = ensure_scratch(c, kHdrWords))) return s;
-            TB_CUDA(c, cudaMemsetAsync(c->scratch, 0, kHdrRangeErr * 4, c->stream));
+            TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
             if ((s = run_prepare(c, false, false, fm, nullptr))) return s;
         } else {
             TB_LAUNCH(c, "compose_world", c->n * 128, compose_world_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows,
