@@ -56,3 +56,16 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c99():
+    """include/tuber_b200.h compiles as strict C99 and the struct layouts are the documented ones"""
+    src = os.path.join(ROOT, "tests", "helpers", "c_abi_check.c")
+    out = os.path.join(ROOT, "tests", "helpers", "_c_abi_check.o")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-c", src, "-o", out], check=True)
+
+
+def test_cpp_host_header_compiles_standalone():
+    """include/tuber_host.hpp is self-contained C++17 (syntax check; no GPU needed)"""
+    hdr = os.path.join(ROOT, "include", "tuber_host.hpp")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)

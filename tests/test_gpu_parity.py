@@ -644,3 +644,57 @@ def test_sharded_scene_graph_with_ghost_ancestors():
             c.close()
         for b in bufs:
             capi.device_free(b)
+
+
+# ---- misuse of the C ABI is an error status, never a crash -------------------------------------------
+
+def test_c_abi_misuse_returns_statuses():
+    import ctypes as C
+    lib = capi.load()
+    out = capi.FrameOut()
+    assert lib.tb_frame_transform_batch(None, C.byref(out)) == capi.TB_ERR_INVALID
+    assert lib.tb_set_entity_count(None, 3) == capi.TB_ERR_INVALID
+    h = C.c_void_p()
+    assert lib.tb_ctx_create(0, 0, C.byref(h)) == capi.TB_ERR_INVALID            # zero capacity
+    assert lib.tb_ctx_create(0, 1 << 31, C.byref(h)) == capi.TB_ERR_INVALID      # beyond 2^30 entity indices
+    assert lib.tb_ctx_create(999, 16, C.byref(h)) == capi.TB_ERR_NO_DEVICE       # no such GPU
+    with capi.Context(64) as ctx:
+        sc = scenes.config1(n=64)
+        ctx.set_entity_count(64)
+        ctx.upload_transforms(0, sc.transforms)
+        ctx.upload_sprites(0, sc.sprites)
+        # downloads before any frame, and beyond the last frame's output
+        with pytest.raises(capi.TuberError) as e:
+            ctx.download_instances(1)
+        assert e.value.status == capi.TB_ERR_INVALID
+        assert ctx.frame().num_instances == 64
+        with pytest.raises(capi.TuberError):
+            ctx.download_instances(65)
+        # the multi-GPU calls must follow their protocol order
+        with pytest.raises(capi.TuberError) as e:
+            ctx.shard_plan([0, 0, 0])
+        assert e.value.status == capi.TB_ERR_INVALID
+        with pytest.raises(capi.TuberError):
+            ctx.shard_key_histogram(0)
+        with pytest.raises(capi.TuberError):
+            ctx.set_option("no_such_option", 1)
+        with pytest.raises(capi.TuberError):
+            ctx.set_option("interleaved_rows", 1)   # only before the first upload
+        with pytest.raises(capi.TuberError):
+            ctx.upload_presence(7, 0, np.zeros(1, np.uint64))
+        # output buffers smaller than the frame
+        buf = capi.device_alloc(1024)
+        ctx.set_output(buf, buf, buf, 8)
+        with pytest.raises(capi.TuberError) as e:
+            ctx.frame()
+        assert e.value.status == capi.TB_ERR_CAPACITY
+        ctx.set_output(0, 0, 0, 0)
+        assert ctx.frame().num_instances == 64      # and the context is still usable
+        capi.device_free(buf)
+        # more batches than the table holds
+        sc.sprites["texture"] = np.arange(64)
+        ctx.upload_sprites(0, sc.sprites)
+        ctx.set_max_batches(10)
+        with pytest.raises(capi.TuberError) as e:
+            ctx.frame()
+        assert e.value.status == capi.TB_ERR_CAPACITY
