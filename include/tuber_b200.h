@@ -225,10 +225,17 @@ TB_API tb_status tb_launch_count(tb_ctx* ctx, uint64_t* n);
  * are then global indices. */
 TB_API tb_status tb_shard_set(tb_ctx* ctx, int rank, int nranks, uint64_t global_first);
 /* Emit the next frames' instances / vertices / order into caller-provided DEVICE buffers
- * (e.g. a slice of a gather buffer, or memory shared with the presenter). NULL restores
- * the context's own buffers. Capacities are in elements. */
+ * (e.g. a slice of a gather buffer, or memory shared with the presenter). All NULL restores
+ * the context's own buffers. d_vertices alone may be NULL: the context then emits no vertices
+ * (ranks that ship instances to a presenter; see tb_vertices_from_instances). Capacities are in
+ * elements; buffers must be 16-byte aligned. */
 TB_API tb_status tb_frame_set_output(tb_ctx* ctx, void* d_instances, void* d_vertices, void* d_order,
                                      uint64_t capacity_instances);
+/* Quad vertices of instances [first, first+count) of a device instance buffer, written to the same
+ * positions of a device vertex buffer: bit-identical to what the emit kernels write (the vertices
+ * are a pure function of the instance). Lets only instances cross NVLink to the presenting rank. */
+TB_API tb_status tb_vertices_from_instances(tb_ctx* ctx, const void* d_instances, uint64_t first, uint64_t count,
+                                            void* d_vertices);
 
 /* ---- one scene over several GPUs: exact global draw order --------------------
  *

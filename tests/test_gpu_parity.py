@@ -392,7 +392,7 @@ def test_frames_are_idempotent():
 
 # ---- one scene over several contexts: exact global draw order (multi-GPU placement) ---------------
 
-def _sharded_frame(sc, nranks, **options):
+def _sharded_frame(sc, nranks, instances_only=False, **options):
     """Emulates `nranks` ranks as contexts on this GPU (run one after another, no waiting between
     them), all emitting into one set of output buffers; returns the frame read back from them."""
     n = sc.n
@@ -405,12 +405,12 @@ def _sharded_frame(sc, nranks, **options):
         part.velocities = None if sc.velocities is None else sc.velocities[first:first + cnt]
         ctx = util.make_ctx(part, **options)
         ctx.shard_set(r, nranks, first)
-        ctx.set_output(bufs[0], bufs[1], bufs[2], n)
+        ctx.set_output(bufs[0], 0 if instances_only else bufs[1], bufs[2], n)
         ctxs.append(ctx)
     return ctxs, bufs
 
 
-def _run_sharded(ctxs, bufs, ticks=0, dt=0.01):
+def _run_sharded(ctxs, bufs, ticks=0, dt=0.01, regenerate_vertices=False):
     for _ in range(ticks):
         for c in ctxs:
             c.system_integrate(dt)
@@ -427,6 +427,8 @@ def _run_sharded(ctxs, bufs, ticks=0, dt=0.01):
     assert len(set(totals)) == 1 and totals[0] == g[2]
     outs = [c.frame() for c in ctxs]
     m, b = totals[0], outs[0].num_batches
+    if regenerate_vertices:  # the presenter rebuilds every quad from the instances it received
+        ctxs[0].vertices_from_instances(bufs[0], 0, m, bufs[1])
 
     class G:
         pass
@@ -698,3 +700,20 @@ def test_c_abi_misuse_returns_statuses():
         with pytest.raises(capi.TuberError) as e:
             ctx.frame()
         assert e.value.status == capi.TB_ERR_CAPACITY
+
+
+def test_sharded_instances_only_then_vertices_regenerated():
+    """only instances cross to the presenter; its vertices_from_instances gives the very same quads"""
+    sc = scenes.config2(n=70_003, seed=45)
+    ctxs, bufs = _sharded_frame(sc, 4, instances_only=True)
+    g = _run_sharded(ctxs, bufs, regenerate_vertices=True)
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    # bit-identical to the vertices a single context emits itself
+    one = util.make_ctx(sc)
+    ref = util.GpuFrame(one)
+    assert g.vertices.tobytes() == ref.vertices.tobytes() and g.instances.tobytes() == ref.instances.tobytes()
+    one.close()
+    for c in ctxs:
+        c.close()
+    for b in bufs:
+        capi.device_free(b)

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "tb_ipc_open": (C.c_int32, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "tb_ipc_close": (C.c_int32, [C.c_void_p]),
     "tb_device_read": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_vertices_from_instances": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p)]),
     "tb_host_free": (None, [C.c_void_p]),
 }
@@ -334,6 +335,10 @@ class Context:
         total = C.c_uint64()
         self._check(self._lib.tb_shard_place(self._h, C.c_void_p(d_all_hists), C.byref(total)))
         return total.value
+
+    def vertices_from_instances(self, d_instances, first, count, d_vertices):
+        self._check(self._lib.tb_vertices_from_instances(self._h, C.c_void_p(d_instances), int(first), int(count),
+                                                         C.c_void_p(d_vertices)))
 
     def device_read(self, d_ptr, nbytes, dtype=np.uint8):
         out = np.zeros(int(nbytes) // np.dtype(dtype).itemsize, dtype=dtype)

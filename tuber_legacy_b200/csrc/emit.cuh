@@ -25,7 +25,8 @@ struct EmitParams {
     const WorldRow* world;   // non-null: hierarchy path, world rows instead of composing
     FramePlan plan;
     float4* instances;       // 5 float4 per position
-    float4* vertices;        // 4 float4 per position
+    float4* vertices;        // 4 float4 per position; nullptr: do not emit vertices (a presenter that
+                             // receives instances from other GPUs regenerates them: vertices_from_instances)
     uint32_t* order;         // entity per position
     uint32_t* texlayer;      // optional per-position texture|layer<<16 (generic batch path)
     uint32_t global_first;   // added to the entity ids written to `order`
@@ -105,6 +106,7 @@ __device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool 
         if (item < nlive) st_cs_f4(instances + (size_t)d * 5 + part, stage[q]);
     }
     __syncwarp();
+    if (vertices == nullptr) return;  // warp-uniform
     const uint32_t sw = (lane >> 1) & 3u;
     if (live) {
         float4* mv = stage + lane * 4;
@@ -378,11 +380,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                     st_cs_f4(ip + 2, inst.c2);
                     st_cs_f4(ip + 3, inst.c3);
                     st_cs_f4(ip + 4, inst.s);
-                    float4* vp = ep.vertices + (size_t)dst * 4;
-                    st_cs_f4(vp, vtx[0]);
-                    st_cs_f4(vp + 1, vtx[1]);
-                    st_cs_f4(vp + 2, vtx[2]);
-                    st_cs_f4(vp + 3, vtx[3]);
+                    if (ep.vertices != nullptr) {
+                        float4* vp = ep.vertices + (size_t)dst * 4;
+                        st_cs_f4(vp, vtx[0]);
+                        st_cs_f4(vp + 1, vtx[1]);
+                        st_cs_f4(vp + 2, vtx[2]);
+                        st_cs_f4(vp + 3, vtx[3]);
+                    }
                 }
             } else {
                 staged_store(stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
@@ -620,11 +624,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     st_cs_f4(ip + 2, inst.c2);
                     st_cs_f4(ip + 3, inst.c3);
                     st_cs_f4(ip + 4, inst.s);
-                    float4* vp = ep.vertices + (size_t)dst * 4;
-                    st_cs_f4(vp, vtx[0]);
-                    st_cs_f4(vp + 1, vtx[1]);
-                    st_cs_f4(vp + 2, vtx[2]);
-                    st_cs_f4(vp + 3, vtx[3]);
+                    if (ep.vertices != nullptr) {
+                        float4* vp = ep.vertices + (size_t)dst * 4;
+                        st_cs_f4(vp, vtx[0]);
+                        st_cs_f4(vp + 1, vtx[1]);
+                        st_cs_f4(vp + 2, vtx[2]);
+                        st_cs_f4(vp + 3, vtx[3]);
+                    }
                 }
             } else {
                 staged_store(sm.stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
@@ -647,6 +653,54 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
             atomicAdd(&ep.stats[2], (unsigned long long)c);
         }
+    }
+}
+
+// ---- quad vertices from instances ------------------------------------------------------------------
+//
+// The four quad corners are a pure function of an instance (column-major model + size), computed
+// with the same individually rounded operations as in the emit kernels, so regenerating them on the
+// presenting GPU gives bit-identical vertices while only instances cross NVLink. One warp per 32
+// instances: coalesced 16-byte loads of the 2560-byte instance block into shared memory, compute,
+// XOR-swizzled staging, coalesced 16-byte stores.
+__global__ void __launch_bounds__(kThreads) vertices_from_instances_kernel(const float4* __restrict__ instances,
+                                                                            uint32_t first, uint32_t count,
+                                                                            float4* __restrict__ vertices) {
+    __shared__ float4 s_in[kWarps][32 * 5];
+    __shared__ float4 s_out[kWarps][32 * 4];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * kWarps;
+    for (uint32_t blk = blockIdx.x * kWarps + warp; blk * 32u < count; blk += nwarps) {
+        const uint32_t base = blk * 32u, m = min(32u, count - base);
+        const float4* src = instances + (size_t)(first + base) * 5;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t q = j * 32 + lane;
+            if (q < m * 5) s_in[warp][q] = __ldcs(src + q);
+        }
+        __syncwarp();
+        const uint32_t sw = (lane >> 1) & 3u;
+        if (lane < m) {
+            const float4 c0 = s_in[warp][lane * 5], c1 = s_in[warp][lane * 5 + 1], c3 = s_in[warp][lane * 5 + 3];
+            const float4 sz = s_in[warp][lane * 5 + 4];
+            const float cx[4] = {0.0f, sz.x, sz.x, 0.0f};
+            const float cy[4] = {0.0f, 0.0f, sz.y, sz.y};
+            const uint32_t uv[4] = {0x00000000u, 0x00000001u, 0x00010001u, 0x00010000u};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                s_out[warp][lane * 4 + (k ^ sw)] =
+                    make_float4(corner_coord(c0.x, c1.x, c3.x, cx[k], cy[k]), corner_coord(c0.y, c1.y, c3.y, cx[k], cy[k]),
+                                corner_coord(c0.z, c1.z, c3.z, cx[k], cy[k]), __uint_as_float(uv[k]));
+        }
+        __syncwarp();
+        float4* dst = vertices + (size_t)(first + base) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = j * 32 + lane;
+            const uint32_t item = q >> 2, part = q & 3u;
+            if (item < m) st_cs_f4(dst + q, s_out[warp][item * 4 + (part ^ ((item >> 1) & 3u))]);
+        }
+        __syncwarp();
     }
 }
 

@@ -1281,7 +1281,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     if ((s = ensure_outputs(c, n))) return s;
     if (fm.hier && (s = ensure_world(c, n))) return s;
     float4* d_inst = c->ext_inst ? (float4*)c->ext_inst : c->inst;
-    float4* d_vtx = c->ext_vtx ? (float4*)c->ext_vtx : c->vtx;
+    float4* d_vtx = c->ext_inst ? (float4*)c->ext_vtx : c->vtx;
     uint32_t* d_order = c->ext_order ? (uint32_t*)c->ext_order : c->order;
 
     bool integrate = c->pending;
@@ -1518,7 +1518,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     if (c->ext_inst && c->ext_cap < c->shard_global_count)
         return fail(c, TB_ERR_CAPACITY, "output buffers smaller than the global instance count");
     float4* d_inst = c->ext_inst ? (float4*)c->ext_inst : c->inst;
-    float4* d_vtx = c->ext_vtx ? (float4*)c->ext_vtx : c->vtx;
+    float4* d_vtx = c->ext_inst ? (float4*)c->ext_vtx : c->vtx;
     uint32_t* d_order = c->ext_order ? (uint32_t*)c->ext_order : c->order;
     uint64_t num_batches = 0;
     if (c->shard_global_count > 0) {
@@ -1618,7 +1618,8 @@ tb_status tb_download_instances(tb_ctx* c, uint64_t first, uint64_t n, tb_instan
 }
 tb_status tb_download_vertices(tb_ctx* c, uint64_t first, uint64_t n, tb_quad_vertex* dst) {
     if (!c) return TB_ERR_INVALID;
-    return download(c, c->ext_vtx ? c->ext_vtx : (void*)c->vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
+    if (c->ext_inst && !c->ext_vtx) return fail(c, TB_ERR_INVALID, "this context does not emit vertices");
+    return download(c, c->ext_inst ? c->ext_vtx : (void*)c->vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
 }
 tb_status tb_download_batches(tb_ctx* c, uint64_t first, uint64_t n, tb_batch* dst) {
     if (!c) return TB_ERR_INVALID;
@@ -1713,13 +1714,25 @@ tb_status tb_frame_set_output(tb_ctx* c, void* d_instances, void* d_vertices, vo
         c->ext_inst = c->ext_vtx = c->ext_order = nullptr;
         c->ext_cap = 0;
     } else {
-        if (!d_instances || !d_vertices || !d_order) return fail(c, TB_ERR_INVALID, "all three output buffers are required");
+        if (!d_instances || !d_order) return fail(c, TB_ERR_INVALID, "instance and order buffers are required");
         c->ext_inst = d_instances;
-        c->ext_vtx = d_vertices;
+        c->ext_vtx = d_vertices;  // NULL: this context does not emit vertices (see tb_vertices_from_instances)
         c->ext_order = d_order;
         c->ext_cap = capacity;
     }
     c->frame_valid = false;
+    return TB_OK;
+}
+
+tb_status tb_vertices_from_instances(tb_ctx* c, const void* d_instances, uint64_t first, uint64_t count, void* d_vertices) {
+    if (!c) return TB_ERR_INVALID;
+    if (count == 0) return TB_OK;
+    if (!d_instances || !d_vertices) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (first + count >= (1ull << 32)) return fail(c, TB_ERR_INVALID, "range beyond 2^32 instances");
+    const uint32_t grid = std::min<uint32_t>(div_up(count, 32 * kWarps), 8u * (uint32_t)c->sm_count);
+    TB_LAUNCH(c, "vertices_from_instances", count * 144, vertices_from_instances_kernel, grid, kThreads, 0, (const float4*)d_instances,
+              (uint32_t)first, (uint32_t)count, (float4*)d_vertices);
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
 
