@@ -17,8 +17,8 @@ static_assert(sizeof(InstanceOut) == 80, "instance is 80 bytes");
 template <typename KeyT>
 struct EmitParams {
     PassParams pass;
-    const KeyT* keys_in;     // nullptr when `first` and keys are recomputed from the rows
-    const uint32_t* idx_in;  // nullptr: the entity is the position (single-pass plans)
+    const KeyT* keys_in;     // short keys in input order; nullptr: recomputed from the rows (single-pass flat frames)
+    const uint32_t* idx_in;  // entity per input position; nullptr: the entity is the position (single-pass plans)
     const uint64_t* mask_t;
     const uint64_t* mask_s;
     RowView rows;

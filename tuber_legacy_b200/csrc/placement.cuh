@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(1024) build_batches_kernel(const uint32_t* __r
     if (threadIdx.x == 1023) *num_batches = s_cnt[1023];
 }
 
-// ---- stable tile ranking with decoupled look-back (shared by scatter and emit) ------------------
+// ---- stable tile ranking (shared by scatter and emit) ------------------------------------------------
 
 struct RankShared {
     uint32_t wcnt[kWarps * 256];  // [warp][R] per-warp digit counters, then per-warp exclusive prefixes

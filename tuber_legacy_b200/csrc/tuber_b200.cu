@@ -1,9 +1,9 @@
 // libtuber_b200.so — host side of the C ABI in include/tuber_b200.h.
 //
 // One tb_ctx per GPU owns the device-resident ECS columns (two-sector rows, presence bitsets,
-// velocity and parent columns), the frame scratch (key statistics, histograms, look-back
-// words, sort ping-pong buffers) and the emitted buffers. A frame is a short fixed sequence
-// of kernel launches on the context's stream (DESIGN.md §4); the only host round trip is the
+// velocity and parent columns), the frame scratch (key statistics, histograms, tile offset
+// tables, sort ping-pong buffers) and the emitted buffers. A frame is a short fixed sequence
+// of kernel launches on the context's stream (DESIGN.md §3); the only host round trip is the
 // read-back of the counts and key statistics that tb_frame_transform_batch returns.
 //
 // There is no CPU fallback anywhere in this file: without an sm_100 device tb_ctx_create
@@ -1326,7 +1326,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
             c->texlayer_cap = cap;
         }
-        // zero: stats, num_batches | tile counters, histograms, lt bins, look-back words
+        // zero: stats, batch count, histograms, (layer,texture) bins, pass-0 tile counts
         TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
         if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
         integrate = false;
