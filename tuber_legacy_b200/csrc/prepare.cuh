@@ -248,27 +248,40 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
     const uint32_t nchunks = (lp.count + kThreads - 1) / kThreads;
     for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const uint32_t slot = chunk * kThreads + threadIdx.x;
-        bool live = slot < lp.count;
+        const bool inb = slot < lp.count;
         uint32_t e = 0;
-        if (live) {
-            e = lp.list ? __ldg(lp.list + lp.first + slot) : lp.first + slot;
+        if (inb) e = lp.list ? __ldg(lp.list + lp.first + slot) : lp.first + slot;
+        // Every load of the entity is issued before any is consumed: rows, velocities and parent
+        // links exist (zero / none) for every id, so they do not wait for the presence bits.
+        Row r;
+        r.a0 = r.a1 = r.b0 = r.b1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+        uint32_t par = 0xFFFFFFFFu;
+        bool live = false, moves = false;
+        const bool do_int = p.integrate && p.vel != nullptr;
+        if (inb) {
+            r = load_row(p.rows, e);
+            if (do_int) {
+                const float* v = p.vel + (size_t)e * 3;
+                vx = __ldg(v);
+                vy = __ldg(v + 1);
+                vz = __ldg(v + 2);
+                moves = mask_bit(p.mask_v, e);
+            }
+            if (lp.level > 0) par = __ldg(lp.parent + e) - lp.global_first;
             live = mask_bit(p.mask_t, e);  // level 0 also lists entities without a Transform
         }
-        Row r;
         Affine w;
-        uint32_t par = 0xFFFFFFFFu;
         if (live) {
-            r = load_row(p.rows, e);
-            if (p.integrate && p.vel != nullptr && mask_bit(p.mask_v, e)) {
-                const float* v = p.vel + (size_t)e * 3;
-                const float vx = __ldg(v), vy = __ldg(v + 1), vz = __ldg(v + 2);
+            if (do_int && moves) {
                 r.a0.x = addr(r.a0.x, mulr(vx, p.dt));
                 r.a0.y = addr(r.a0.y, mulr(vy, p.dt));
                 r.a0.z = addr(r.a0.z, mulr(vz, p.dt));
                 p.rows.a[(size_t)e * p.rows.stride] = r.a0;
             }
             w = compose_local(r);
-            if (lp.level > 0) par = __ldg(lp.parent + e) - lp.global_first;
+        } else {
+            par = 0xFFFFFFFFu;
         }
         if (lp.level > 0) {
             // warp-shuffle parent broadcast
