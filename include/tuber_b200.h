@@ -131,14 +131,18 @@ TB_API tb_status tb_ctx_synchronize(tb_ctx* ctx);
 /* Cap on the batch table (default 65536 entries). */
 TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
 /* Tuning / test knobs; results never depend on them. Names:
- *   "interleaved_rows" 0|1  one 64-byte row per entity instead of two 32-byte sector arrays
- *                           (only before the first upload)
+ *   "interleaved_rows" 0|1|-1  one 64-byte row per entity (1) or two 32-byte sector arrays (0); -1, the
+ *                           default, starts with the sector arrays and switches to 64-byte rows at the
+ *                           first frame that gathers rows in sorted order (multi-pass, no hierarchy).
+ *                           Changing the layout of uploaded rows costs one conversion pass.
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
  *   "static_buckets"   0|1  flat few-bucket scenes whose buckets depend on the Sprite only (no varying z
  *                           bit) reuse the per-tile offsets of the last full frame until a component is
  *                           uploaded: the steady-state frame is one kernel, validated every frame (default 1)
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
+ *   "z_dictionary"     0|1  scenes with at most 64 distinct depths sort by the rank of z instead of by
+ *                           its varying float bits: fewer sort passes (default 1)
  *   "lt_limit"         0..16 widest (layer, texture) histogram kept as direct bins (default 16);
  *                           wider scenes find batch boundaries by run-head detection */
 TB_API tb_status tb_ctx_set_option(tb_ctx* ctx, const char* name, int64_t value);

@@ -110,14 +110,14 @@ def test_config4_16M_particles_full_size():
 
 
 def test_config5_64M_flat_full_size_one_gpu():
-    """BASELINE configs[4] on one GPU: 2^26 entities, 21 key bits, 3 radix passes. Checked without
+    """BASELINE configs[4] on one GPU: 2^26 entities, 10 + 4 key bits (16 depths by rank), 2 radix passes. Checked without
     downloading the 10 GB of payload: the order is a permutation, the batch table equals the host's
     (layer, texture) histogram, and windows of the output are sorted and match the oracle's compose."""
     n = 1 << 26
     sc = scenes.config5(n=n)
     ctx = util.make_ctx(sc)
     info = ctx.frame()
-    assert info.num_instances == n and info.sort_passes == 3
+    assert info.num_instances == n and info.sort_passes == 2 and info.key_bits == 14
     order = ctx.download_order(n)
     seen = np.zeros(n, np.uint8)
     seen[order] = 1

@@ -681,8 +681,6 @@ def test_c_abi_misuse_returns_statuses():
         with pytest.raises(capi.TuberError):
             ctx.set_option("no_such_option", 1)
         with pytest.raises(capi.TuberError):
-            ctx.set_option("interleaved_rows", 1)   # only before the first upload
-        with pytest.raises(capi.TuberError):
             ctx.upload_presence(7, 0, np.zeros(1, np.uint64))
         # output buffers smaller than the frame
         buf = capi.device_alloc(1024)
@@ -717,3 +715,127 @@ def test_sharded_instances_only_then_vertices_regenerated():
         c.close()
     for b in bufs:
         capi.device_free(b)
+
+
+# ---- z dictionary (few distinct depths sort by rank, not by their varying float bits) ------------------
+
+def test_z_dictionary_saves_a_sort_pass():
+    """64 textures x 16 layers x depths 0.0..15.0: 10 + 11 varying key bits (3 passes) become 10 + 4 (2)"""
+    sc = scenes.config2(n=150_000, seed=61)
+    r = util.make_oracle(sc).frame()
+    ctx = util.make_ctx(sc)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, r)
+    assert g.info.key_bits == 14 and g.info.sort_passes == 2
+    g2 = util.GpuFrame(ctx)  # cached plan, dictionary still valid
+    assert g2.info.replanned == 0
+    util.assert_frame_parity(g2, r)
+    ctx.close()
+    ctx = util.make_ctx(sc, z_dictionary=0)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, r)
+    assert g.info.key_bits > 14 and g.info.sort_passes == 3
+    ctx.close()
+
+
+def test_z_dictionary_follows_uploads():
+    """uploads drop the cached plan: the next frame collects the depths again"""
+    sc = scenes.config2(n=60_000, seed=62)
+    ctx = util.make_ctx(sc)
+    g = util.GpuFrame(ctx)
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    # 2.5 lies inside the bit envelope of {0..15}: a 17th depth, 5 rank bits
+    sc.transforms["translation"][1000:1200, 2] = 2.5
+    ctx.upload_transforms(1000, sc.transforms[1000:1200])
+    g = util.GpuFrame(ctx)
+    assert g.info.key_bits == 10 + 5
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    # a new layer bit: the (layer, texture) half is validated by the key statistics
+    sc.sprites["layer"][5:50] = 40
+    ctx.upload_sprites(5, sc.sprites[5:50])
+    g = util.GpuFrame(ctx)
+    assert g.info.key_bits == 11 + 5
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    # more than 64 depths: no dictionary any more
+    sc.transforms["translation"][:, 2] = (np.arange(sc.n) % 100).astype(np.float32) * np.float32(0.25)
+    ctx.upload_transforms(0, sc.transforms)
+    g = util.GpuFrame(ctx)
+    assert g.info.key_bits > 16
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    ctx.close()
+
+
+def test_z_dictionary_goes_stale_and_replans():
+    """the velocity system moves every depth without an upload: the cached dictionary misses (the
+    varying-bit envelope alone would not notice 1.0 -> 3.0) and the frame re-plans itself"""
+    sc = scenes.config4(n=40_000, seed=63)
+    sc.sprites["texture"] = np.arange(sc.n) % 64
+    sc.sprites["layer"] = np.arange(sc.n) % 5
+    sc.transforms["translation"][:, 2] = (np.arange(sc.n) % 3).astype(np.float32)
+    sc.velocities["v"][:, 2] = 16.0  # every depth moves each tick: the dictionary is rebuilt each frame
+    ctx = util.make_ctx(sc)
+    ref = util.make_oracle(sc)
+    util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+    for _ in range(3):
+        ctx.system_integrate(0.0625)
+        ref.step(0.0625)
+        g = util.GpuFrame(ctx)
+        assert g.info.replanned == 1 and g.info.key_bits == 6 + 3 + 2
+        util.assert_frame_parity(g, ref.frame())
+    t = ctx.download_transforms(0, sc.n)
+    np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
+    ctx.close()
+
+
+@pytest.mark.parametrize("opts", [{}, {"small_emit": 0}, {"interleaved_rows": 1, "staged_emit": 0}])
+def test_z_dictionary_single_pass_and_sparse(opts):
+    """2 textures x depths {0, 1, 5}: 1 + 2 rank bits, one pass, the few-bucket emit with a dictionary"""
+    sc = scenes.config4(n=70_003, seed=64)
+    i = np.arange(sc.n)
+    sc.sprites["texture"] = i % 2
+    sc.sprites["layer"] = 0
+    sc.transforms["translation"][:, 2] = np.array([0.0, 1.0, 5.0], np.float32)[(i // 7) % 3]
+    masks = {capi.TB_SPRITE: util.random_mask(sc.n, 0.8, 31), capi.TB_TRANSFORM: util.random_mask(sc.n, 0.9, 32)}
+    ctx, ref, g, r = run_both(sc, masks, ticks=1, **opts)
+    assert g.info.key_bits == 3 and g.info.path == capi.TB_PATH_BUCKET
+    util.assert_frame_parity(g, r)
+    g = util.GpuFrame(ctx)
+    assert g.info.replanned == 0
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+def test_z_dictionary_hierarchy():
+    """every node 1.0 deep below its parent: world depths 1..8, three rank bits"""
+    sc = scenes.config3(n=60_000, seed=65)
+    sc.transforms["translation"][:, 2] = 1.0
+    ctx, ref, g, r = run_both(sc)
+    assert g.info.hierarchy_levels == 8 and g.info.key_bits == 10 + 3
+    util.assert_frame_parity(g, r)
+    ctx.close()
+
+
+# ---- row layout ------------------------------------------------------------------------------------------
+
+def test_row_layout_switches_keep_the_rows():
+    """sorted frames move the storage to 64-byte rows on their own; an explicit switch converts in place"""
+    sc = scenes.config2(n=70_001, seed=71, z_mode="random")
+    ctx = util.make_ctx(sc)
+    ctx.profile_enable(True)
+    r = util.make_oracle(sc).frame()
+    util.assert_frame_parity(util.GpuFrame(ctx), r)
+    util.assert_frame_parity(util.GpuFrame(ctx), r)
+    assert ctx.profile()["relayout_rows"][2] == 1  # converted once, at the first sorted frame
+    for layout in (0, 1, 0, -1):
+        ctx.set_option("interleaved_rows", layout)
+        util.assert_frame_parity(util.GpuFrame(ctx), r)
+        t = ctx.download_transforms(0, sc.n)
+        np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), sc.transforms.view(np.uint32).reshape(-1, 12))
+    # in-order single-pass frames stay on the sector arrays
+    sc = scenes.config4(n=30_000, seed=72)
+    ctx2 = util.make_ctx(sc)
+    ctx2.profile_enable(True)
+    util.assert_frame_parity(util.GpuFrame(ctx2), util.make_oracle(sc).frame())
+    assert "relayout_rows" not in ctx2.profile()
+    ctx2.close()
+    ctx.close()

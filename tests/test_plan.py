@@ -19,7 +19,7 @@ class PextPlan(C.Structure):
 class FramePlan(C.Structure):
     _fields_ = [("pext", PextPlan), ("varying", C.c_uint64), ("constant", C.c_uint64), ("npasses", C.c_uint32),
                 ("shift", C.c_uint32 * 8), ("bits", C.c_uint32 * 8), ("ltbits", C.c_uint32), ("zbits", C.c_uint32),
-                ("key64", C.c_uint32)]
+                ("key64", C.c_uint32), ("zdict_n", C.c_uint32), ("zdict", C.c_uint32 * 64)]
 
 
 @pytest.fixture(scope="module")
@@ -36,6 +36,9 @@ def lib():
     L.plan_pdep.restype = C.c_uint64
     L.plan_pdep.argtypes = [C.POINTER(FramePlan), C.c_uint64]
     L.plan_covers.argtypes = [C.POINTER(FramePlan), C.c_uint64, C.c_uint64]
+    L.plan_build_dict.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(FramePlan)]
+    L.plan_short_key.restype = C.c_uint64
+    L.plan_short_key.argtypes = [C.POINTER(FramePlan), C.c_uint64, C.POINTER(C.c_int)]
     assert L.plan_sizeof() == C.sizeof(FramePlan)
     return L
 
@@ -129,3 +132,78 @@ def test_plan_covers_detects_stale_plans(lib):
     assert lib.plan_covers(C.byref(f), int(np.bitwise_or.reduce(more)), int(np.bitwise_and.reduce(more))) == 0
     moved = keys | np.uint64(1)
     assert lib.plan_covers(C.byref(f), int(np.bitwise_or.reduce(moved)), int(np.bitwise_and.reduce(moved))) == 0
+
+
+def orderable(zf):
+    u = np.asarray(zf, np.float32).view(np.uint32).astype(np.uint64)
+    return np.where(u >> np.uint64(31), u ^ np.uint64(0xFFFFFFFF), u ^ np.uint64(0x80000000))
+
+
+def build_dict(lib, keys):
+    k_or = int(np.bitwise_or.reduce(keys))
+    k_and = int(np.bitwise_and.reduce(keys))
+    zvals = np.unique((keys & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+    f = FramePlan()
+    lib.plan_build_dict(k_or, k_and, zvals.ctypes.data_as(C.POINTER(C.c_uint32)), len(zvals), C.byref(f))
+    return f, k_or, k_and
+
+
+def short_keys(lib, f, keys):
+    miss = C.c_int(0)
+    out = []
+    for k in keys:
+        out.append(lib.plan_short_key(C.byref(f), int(k), C.byref(miss)))
+        assert miss.value == 0
+    return np.array(out, np.uint64)
+
+
+@pytest.mark.parametrize("nz", [2, 3, 5, 17, 64])
+def test_z_dictionary_ranks_preserve_order(lib, nz):
+    # depths 0.0, 1.0, 2.0 ... differ in many float bits but are few values: the short key holds their rank
+    rng = np.random.default_rng(nz)
+    n = 3000
+    z = orderable(rng.integers(0, nz, n).astype(np.float32) - 1.0)
+    z[:nz] = orderable(np.arange(nz, dtype=np.float32) - 1.0)
+    keys = (rng.integers(0, 3, n).astype(np.uint64) << np.uint64(48)) | (rng.integers(0, 5, n).astype(np.uint64) << np.uint64(32)) | z
+    plain, _, _ = build(lib, keys)
+    f, k_or, k_and = build_dict(lib, keys)
+    rank_bits = int(np.ceil(np.log2(nz)))
+    assert f.zdict_n == nz and f.zbits == rank_bits and f.zbits < plain.zbits
+    assert f.ltbits == plain.ltbits and f.pext.nbits == f.ltbits + f.zbits
+    assert sum(f.bits[p] for p in range(f.npasses)) == f.pext.nbits and f.npasses <= plain.npasses
+    short = short_keys(lib, f, keys)
+    assert int(short.max()) < (1 << f.pext.nbits)
+    o_full = np.argsort(keys, kind="stable")
+    o_short = np.argsort(short, kind="stable")
+    assert np.array_equal(o_full, o_short)
+    assert np.array_equal(np.diff(keys[o_full]) == 0, np.diff(short[o_short]) == 0)
+    # the (layer, texture) bin of a short key expands back to the key's high half
+    for k, s in zip(keys[:50], short[:50]):
+        hi = lib.plan_pdep(C.byref(f), int(s) >> f.zbits) | (f.constant & 0xFFFFFFFF00000000)
+        assert hi == int(k) & 0xFFFFFFFF00000000
+    assert lib.plan_covers(C.byref(f), k_or, k_and) == 1
+
+
+def test_z_dictionary_not_taken_when_it_does_not_help(lib):
+    # two depths one bit apart: the varying-bit key is already 1 bit wide
+    z = orderable(np.array([1.0, np.nextafter(np.float32(1.0), np.float32(2.0))] * 10, np.float32))
+    keys = z | (np.uint64(1) << np.uint64(32))
+    f, _, _ = build_dict(lib, keys)
+    assert f.zdict_n == 0 and f.zbits == 1
+    # more than 64 depths
+    z = orderable(np.arange(65, dtype=np.float32))
+    f, _, _ = build_dict(lib, z)
+    assert f.zdict_n == 0
+
+
+def test_z_dictionary_miss_and_stale_high_half(lib):
+    z = orderable(np.array([0.0, 1.0, 2.0, 3.0], np.float32))
+    keys = np.concatenate([z | (np.uint64(t) << np.uint64(32)) for t in range(4)])
+    f, k_or, k_and = build_dict(lib, keys)
+    assert f.zdict_n == 4 and f.zbits == 2 and f.ltbits == 2
+    miss = C.c_int(0)
+    lib.plan_short_key(C.byref(f), int(orderable(np.float32(1.5))), C.byref(miss))
+    assert miss.value == 1
+    # low-half changes are the dictionary's business; a new texture bit is not covered
+    assert lib.plan_covers(C.byref(f), k_or | 0x7FFFFFFF, k_and & ~0x7FFFFFFF) == 1
+    assert lib.plan_covers(C.byref(f), k_or | (8 << 32), k_and) == 0

@@ -64,3 +64,19 @@ if __name__ == "__main__":
         run("configs[4] 64M flat on one GPU", scenes.config5(), 208, interleaved_rows=1)
     if "4s" in which:
         run("configs[3] 16M particles, nothing cached between frames", scenes.config4(), 232, integrate=True, static_buckets=0)
+    if "2n" in which:
+        run("configs[1] 1M flat, z in {0..15}, no z dictionary", scenes.config2(), 208, z_dictionary=0)
+    if "5n" in which:
+        run("configs[4] 64M flat on one GPU, no z dictionary", scenes.config5(), 208, z_dictionary=0)
+    if "16" in which:
+        run("16M flat, 64 textures x 16 layers, z in {0..15}", scenes.config2(n=1 << 24), 208)
+    if "16n" in which:
+        run("16M flat, 64 textures x 16 layers, z in {0..15}, no z dictionary", scenes.config2(n=1 << 24), 208, z_dictionary=0)
+    if "16i" in which:
+        run("16M flat, 64 textures x 16 layers, z in {0..15}, interleaved rows", scenes.config2(n=1 << 24), 208, interleaved_rows=1)
+    if "2i" in which:
+        run("configs[1] 1M flat, z in {0..15}, interleaved rows", scenes.config2(), 208, interleaved_rows=1)
+    if "4i" in which:
+        run("configs[3] 16M particles, interleaved rows", scenes.config4(), 232, integrate=True, interleaved_rows=1)
+    if "3i" in which:
+        run("configs[2] 4M hierarchy depth 8, interleaved rows", scenes.config3(), 212, interleaved_rows=1)

@@ -60,6 +60,7 @@ struct EmitShared {
     float4 stage[kWarps][32 * kStageF4];  // per-warp staging for full-line stores
     unsigned long long mbar[2];         // completion barriers of the row copies (in-order passes)
     unsigned long long kbar[3];         // completion barriers of the (key, entity) ring
+    uint32_t zdict[kMaxZDict];          // the plan's z dictionary (passes that recompute keys from rows)
 };
 
 // 16-byte chunk c (0..3) of tile-local row li lives at rows[row_slot(li, c)]: the 128-byte
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
 
     uint32_t tile = blockIdx.x;
     uint32_t kpar = 0;  // phase parities of the three kbar slots (bit r)
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) sm.zdict[k] = ep.plan.zdict[k];
     if (threadIdx.x == 0) {
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
@@ -277,10 +279,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 }
                 uint64_t sk = 0;
                 if (valid[k]) {
-                    if (keys_given) {
+                    if (keys_given) {  // hierarchy frames always carry the keys pass A wrote
                         sk = (uint64_t)sm.keys[ring][li];
-                    } else if (from_world) {
-                        sk = pext_runs(world_key(rows[chunk(li, 2)], rows[chunk(li, 3)]), ep.plan.pext);
                     } else {
                         const float4 a0 = rows[chunk(li, 0)], a1 = rows[chunk(li, 1)];
                         float z;
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                             z = local_z(r);
                         }
                         const uint32_t tl = __float_as_uint(a1.w);
-                        sk = pext_runs(sort_key(tl >> 16, tl & 0xFFFFu, z), ep.plan.pext);
+                        bool miss = false;  // pass A of the same frame reports misses
+                        sk = plan_short_key(ep.plan, sm.zdict, sort_key(tl >> 16, tl & 0xFFFFu, z), &miss);
                     }
                 }
                 digit[k] = valid[k] ? ((uint32_t)(sk >> ep.pass.shift) & mask) : kInvalidDigit;
@@ -435,6 +436,9 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
     WarpShared& sm = reinterpret_cast<SmallShared*>(emit_smem_raw)->w[warp];
     const bool do_int = FUSED && ep.integrate && ep.vel != nullptr;
     PrepAcc acc;
+    __shared__ uint32_t s_zdict[kMaxZDict];
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) s_zdict[k] = ep.plan.zdict[k];
+    __syncthreads();  // the only block barrier of the kernel, before the warps go their own ways
     const bool from_world = ep.world != nullptr;
     const bool keys_given = ep.keys_in != nullptr;
     const uint32_t n = ep.pass.n;
@@ -524,10 +528,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             digit[k] = kInvalidDigit;
             if ((pres >> li) & 1ull) {
                 uint64_t sk;
-                if (keys_given) {
+                if (keys_given) {  // hierarchy frames always carry the keys pass A wrote
                     sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
-                } else if (from_world) {
-                    sk = pext_runs(world_key(rows[li * 4 + 2], rows[li * 4 + 3]), ep.plan.pext);
                 } else {
                     const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
                     float z;
@@ -548,7 +550,9 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                         acc.k_and &= key;
                         acc.count += 1;
                     }
-                    sk = pext_runs(key, ep.plan.pext);
+                    bool miss = false;
+                    sk = plan_short_key(ep.plan, s_zdict, key, &miss);
+                    if (FUSED && miss) acc.miss = true;
                 }
                 digit[k] = (uint32_t)sk & (R - 1u);
             }
@@ -653,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
             atomicAdd(&ep.stats[2], (unsigned long long)c);
         }
+        if (__any_sync(0xffffffffu, acc.miss) && lane == 0) atomicOr(&ep.stats[4], 1ull);
     }
 }
 

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(1024) build_batches_kernel(const uint32_t* __r
         const uint32_t c = bins[b];
         if (c) {
             if (slot < max_batches) {
-                const uint64_t key = plan.constant | pdep_runs((uint64_t)b << plan.zbits, plan.pext);
+                // with a z dictionary the pext runs cover the (layer, texture) half only, from bit 0
+                const uint64_t key = plan.constant | pdep_runs(plan.zdict_n ? (uint64_t)b : ((uint64_t)b << plan.zbits), plan.pext);
                 BatchOut o;
                 o.layer = (uint32_t)(key >> 48);
                 o.texture = (uint32_t)(key >> 32) & 0xFFFFu;

@@ -24,11 +24,13 @@ struct PrepParams {
     void* keys_out;
     uint32_t* hist;        // [kMaxPasses][256]
     uint32_t* lt_hist;     // [1 << ltbits]
-    unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+    unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count, [4] z-dictionary misses ([3] holds the batch count)
     uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per emit tile
     uint32_t emit_tiles;
     uint32_t emit_tile_shift;  // log2 of the emit tile: 9 (CTA tiles of 512) or 6 (warp tiles of 64)
     uint32_t* key_hist;     // optional [1 << nbits]: histogram over the whole short key (multi-GPU placement)
+    unsigned long long* zset;  // plan discovery: open-addressing set of the distinct orderable z values
+    uint32_t* zset_overflow;   // ... set when the scene has more distinct depths than the set is meant for
     FramePlan plan;
 };
 
@@ -38,6 +40,7 @@ struct PrepShared {
     uint32_t hist[kMaxPasses][256];
     uint32_t tcnt[2][2][256];  // [iteration parity][half of the 1024-entity tile][pass-0 digit]
     uint32_t lt[2048];
+    uint32_t zdict[kMaxZDict];  // the plan's z dictionary
     unsigned long long k_or, k_and;
     uint32_t count;
 };
@@ -46,7 +49,27 @@ struct PrepShared {
 struct PrepAcc {
     unsigned long long k_or = 0ull, k_and = ~0ull;
     uint32_t count = 0;
+    bool miss = false;  // a depth that the plan's z dictionary does not hold
 };
+
+// Plan discovery: remember this depth (warp-aggregated insert into a small open-addressing set).
+__device__ __forceinline__ void zset_insert(unsigned long long* zset, uint32_t* overflow, bool renderable, uint32_t z) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, renderable ? z : 0xFFFFFFFFu);
+    if (!renderable || (threadIdx.x & 31) != (uint32_t)(__ffs(peers) - 1)) return;
+    if (*reinterpret_cast<volatile uint32_t*>(overflow)) return;
+    const unsigned long long want = (1ull << 32) | z;
+    uint32_t h = (z * 2654435761u) >> 23;
+    for (uint32_t probe = 0; probe < 4u * kMaxZDict; ++probe, ++h) {
+        unsigned long long* slot = zset + (h & (kZSetSlots - 1));
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
+        if (cur == want) return;
+        if (cur == 0ull) {
+            cur = atomicCAS(slot, 0ull, want);
+            if (cur == 0ull || cur == want) return;
+        }
+    }
+    atomicExch(overflow, 1u);  // far more distinct depths than a dictionary can hold
+}
 
 // Accounts one entity: key statistics in registers, digit histograms in shared memory, optional
 // short key write. Must be called by all 32 lanes of a warp (it contains warp collectives).
@@ -62,8 +85,13 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
         acc.k_and &= key;
         acc.count += 1;
     }
-    if (!p.have_plan) return;
-    const uint64_t sk = pext_runs(key, p.plan.pext);
+    if (!p.have_plan) {
+        if (p.zset != nullptr) zset_insert(p.zset, p.zset_overflow, renderable, (uint32_t)key);
+        return;
+    }
+    bool miss = false;
+    const uint64_t sk = plan_short_key(p.plan, sh.zdict, key, &miss);
+    if (renderable && miss) acc.miss = true;
     if (small) {
         const uint32_t d = renderable ? (uint32_t)sk & ((1u << p.plan.bits[0]) - 1u) : kInvalidDigit;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
@@ -100,6 +128,7 @@ __device__ __forceinline__ bool prep_small(const PrepParams& p) {
 __device__ __forceinline__ void prep_init(const PrepParams& p, PrepShared& sh) {
     for (uint32_t k = threadIdx.x; k < kMaxPasses * 256; k += blockDim.x) (&sh.hist[0][0])[k] = 0;
     for (uint32_t k = threadIdx.x; k < 2048; k += blockDim.x) sh.lt[k] = 0;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += blockDim.x) sh.zdict[k] = p.have_plan ? p.plan.zdict[k] : 0u;
     if (threadIdx.x == 0) {
         sh.k_or = 0ull;
         sh.k_and = ~0ull;
@@ -121,6 +150,7 @@ __device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh, 
             atomicAnd(&sh.k_and, ((unsigned long long)nhi << 32) | nlo);
             atomicAdd(&sh.count, cnt);
         }
+        if (__any_sync(0xffffffffu, acc.miss) && (threadIdx.x & 31) == 0) atomicOr(&p.stats[4], 1ull);
     }
     __syncthreads();
     if (p.have_plan) {

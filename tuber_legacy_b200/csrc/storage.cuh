@@ -47,6 +47,18 @@ __global__ void __launch_bounds__(kThreads) convert_sprites_kernel(const uint32_
     b1[3] = 0.0f;
 }
 
+// Copies every row from one layout to the other (two 32-byte sector arrays <-> one 64-byte row per
+// entity): one thread per 16-byte chunk.
+__global__ void __launch_bounds__(kThreads) relayout_rows_kernel(RowView src, RowView dst, uint64_t n) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t i = t >> 2;
+    if (i >= n) return;
+    const uint32_t ch = (uint32_t)t & 3u;
+    const float4* from = ((ch & 2u) ? src.b : src.a) + i * src.stride + (ch & 1u);
+    float4* to = ((ch & 2u) ? dst.b : dst.a) + i * dst.stride + (ch & 1u);
+    *to = *from;
+}
+
 // rows -> tb_transform (download for parity checks of the velocity system)
 __global__ void __launch_bounds__(kThreads) unconvert_transforms_kernel(RowView rv, uint32_t first, uint32_t n,
                                                                          float* __restrict__ dst) {

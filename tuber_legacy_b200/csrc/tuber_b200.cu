@@ -49,6 +49,7 @@ struct tb_ctx {
 
     // storage
     int interleaved = 0;
+    bool layout_auto = true;  // frames that gather rows in sorted order switch to 64-byte rows on their own
     bool rows_touched = false;
     float4* rows_mem = nullptr;
     RowView rows{};
@@ -99,6 +100,12 @@ struct tb_ctx {
     int staged_emit = 1;
     int small_emit = 1;
     int lt_limit = (int)kMaxLtBits;
+    int z_dictionary = 1;
+
+    // plan discovery: the distinct depths of the scene (device set + pinned host copy)
+    unsigned long long* zset = nullptr;  // [kZSetSlots] entries + 1 overflow word
+    unsigned long long* h_zset = nullptr;
+    bool zset_active = false;
 
     // hierarchy
     bool levels_dirty = true;
@@ -145,7 +152,8 @@ constexpr size_t kHdrLevelStats = 2;   // 2 x u32
 constexpr size_t kHdrFrame = 4;
 constexpr size_t kHdrStats = 4;        // 3 x u64: OR(key), OR(~key), renderable count
 constexpr size_t kHdrNumBatches = 10;  // u32
-constexpr size_t kHdrReadWords = 8;    // what a frame copies back: stats + batch count
+constexpr size_t kHdrZMiss = 12;       // u64 (stats[4]): a depth outside the plan's z dictionary was seen
+constexpr size_t kHdrReadWords = 10;   // what a frame copies back: stats + batch count + dictionary misses
 constexpr size_t kHdrHist = 16;        // kMaxPasses * 256 u32: raw digit histograms
 constexpr size_t kHdrWords = kHdrHist + kMaxPasses * 256;  // then (layer,texture) bins, tile tables
 
@@ -592,10 +600,38 @@ tb_status plan_levels(tb_ctx* c) {
     return TB_OK;
 }
 
+// Switches the row layout, converting whatever the rows hold (one pass over the storage, out of place).
+tb_status relayout_rows(tb_ctx* c, bool interleaved) {
+    if ((c->interleaved != 0) == interleaved) return TB_OK;
+    RowView dst;
+    float4* fresh = nullptr;
+    if (c->rows_touched) {
+        cudaError_t e = cudaMalloc((void**)&fresh, c->cap * 64);
+        if (e != cudaSuccess) return cuda_fail(c, e, "relayout_rows");
+    } else {
+        fresh = c->rows_mem;  // nothing uploaded yet: the rows are all zero in either layout
+    }
+    dst.a = fresh;
+    dst.b = interleaved ? fresh + 2 : fresh + 2 * c->cap;
+    dst.stride = interleaved ? 4 : 2;
+    if (c->rows_touched) {
+        TB_LAUNCH(c, "relayout_rows", c->cap * 128, relayout_rows_kernel, (uint32_t)div_up(c->cap * 4, (uint64_t)kThreads), kThreads, 0,
+                  c->rows, dst, (uint64_t)c->cap);
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->rows_mem);
+        c->rows_mem = fresh;
+    }
+    c->rows = dst;
+    c->interleaved = interleaved ? 1 : 0;
+    c->static_valid = false;
+    return TB_OK;
+}
+
 // ---- the frame --------------------------------------------------------------------------------
 
-void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and) {
-    build_frame_plan(key_or, key_and, &c->plan);
+void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and, const uint32_t* zvals = nullptr, uint32_t nz = 0) {
+    if (nz) build_frame_plan_dict(key_or, key_and, zvals, nz, &c->plan);
+    else build_frame_plan(key_or, key_and, &c->plan);
     // optional narrower digits (tests, tb_frame_force_path(TB_PATH_SORT))
     int db = c->digit_bits;
     if (c->force_path == TB_PATH_SORT && c->plan.pext.nbits >= 2) db = std::min<int>(db, (c->plan.pext.nbits + 1) / 2);
@@ -637,6 +673,10 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     p.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     p.hist = c->scratch + kHdrHist;
     p.key_hist = key_hist;
+    if (!have_plan && c->zset_active) {
+        p.zset = c->zset;
+        p.zset_overflow = reinterpret_cast<uint32_t*>(c->zset + kZSetSlots);
+    }
     if (have_plan) {
         p.plan = c->plan;
         p.write_keys = c->plan.npasses > 1 || fm.hier;
@@ -847,7 +887,10 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     c->cap = max_entities;
     const char* env = getenv("TB_INTERLEAVED_ROWS");
-    if (env) c->interleaved = atoi(env);
+    if (env) {
+        c->interleaved = atoi(env);
+        c->layout_auto = false;
+    }
     env = getenv("TB_STAGED_EMIT");
     if (env) c->staged_emit = atoi(env);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
@@ -864,6 +907,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
         if (ok) cudaMemsetAsync(c->mask[k], 0, (words + 2) * 8, c->stream);
     }
     ok = ok && cudaMallocHost((void**)&c->h_hdr, 64) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&c->zset, (kZSetSlots + 1) * 8) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_zset, (kZSetSlots + 1) * 8) == cudaSuccess;
     if (ok) ok = ensure_scratch(c, kHdrWords) == TB_OK;
     if (!ok) {
         cudaGetLastError();
@@ -916,6 +961,8 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->lt_global);
     cudaFree(c->place_tmp);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    cudaFree(c->zset);
+    if (c->h_zset) cudaFreeHost(c->h_zset);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -945,10 +992,11 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return TB_ERR_INVALID;
     std::string k(name);
     if (k == "interleaved_rows") {
-        if (c->rows_touched) return fail(c, TB_ERR_INVALID, "interleaved_rows must be set before the first upload");
-        c->interleaved = value != 0;
-        c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * c->cap;
-        c->rows.stride = c->interleaved ? 4 : 2;
+        c->layout_auto = value < 0;
+        if (value >= 0) {
+            tb_status s = relayout_rows(c, value != 0);
+            if (s) return s;
+        }
     } else if (k == "staged_emit") {
         c->staged_emit = value != 0;
     } else if (k == "static_buckets") {
@@ -962,6 +1010,10 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->digit_bits = (int)value;
         c->plan_valid = false;
     c->static_valid = false;
+    } else if (k == "z_dictionary") {
+        c->z_dictionary = value != 0;
+        c->plan_valid = false;
+        c->static_valid = false;
     } else if (k == "lt_limit") {
         if (value < 0 || value > (int64_t)kMaxLtBits) return fail(c, TB_ERR_INVALID, "lt_limit must be 0..16");
         c->lt_limit = (int)value;
@@ -1304,14 +1356,33 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         if (!c->plan_valid) {
             // discovery: key statistics only (and the velocity system, exactly once)
             TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
-            if ((s = run_prepare(c, false, integrate, fm, nullptr))) return s;
+            c->zset_active = c->z_dictionary != 0;
+            if (c->zset_active) TB_CUDA(c, cudaMemsetAsync(c->zset, 0, (kZSetSlots + 1) * 8, c->stream));
+            s = run_prepare(c, false, integrate, fm, nullptr);
+            const bool have_zset = c->zset_active;
+            c->zset_active = false;
+            if (s) return s;
             integrate = false;
+            if (have_zset)
+                TB_CUDA(c, cudaMemcpyAsync(c->h_zset, c->zset, (kZSetSlots + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
             if ((s = read_header(c))) return s;
             count = c->h_hdr[2];
             if (count == 0) break;
-            make_plan(c, c->h_hdr[0], ~c->h_hdr[1]);
+            // few distinct depths: sort them by rank instead of by their varying float bits
+            uint32_t zvals[kZSetSlots];
+            uint32_t nz = 0;
+            if (have_zset && (uint32_t)c->h_zset[kZSetSlots] == 0) {
+                for (int k = 0; k < kZSetSlots; ++k)
+                    if (c->h_zset[k] >> 32) zvals[nz++] = (uint32_t)c->h_zset[k];
+                if (nz > (uint32_t)kMaxZDict) nz = 0;
+                std::sort(zvals, zvals + nz);
+            }
+            make_plan(c, c->h_hdr[0], ~c->h_hdr[1], zvals, nz);
         }
         const FramePlan& plan = c->plan;
+        // sorted frames gather whole rows in draw order: one 64-byte row per entity reads one DRAM
+        // atom instead of two half-used ones (the in-order single-pass frames prefer the split sectors)
+        if (c->layout_auto && !c->interleaved && plan.npasses > 1 && !fm.hier && (s = relayout_rows(c, true))) return s;
         if (c->force_path == TB_PATH_BUCKET && plan.npasses > 1)
             return fail(c, TB_ERR_UNSUPPORTED, "TB_PATH_BUCKET needs at most 256 distinct key buckets");
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
@@ -1343,9 +1414,11 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         count = c->h_hdr[2];
         const uint64_t k_or = c->h_hdr[0], k_and = ~c->h_hdr[1];
         if (count == 0) break;
-        if (!plan_covers(plan, k_or, k_and)) {
-            // the scene's keys moved outside the cached plan: re-plan from this frame's statistics
-            make_plan(c, k_or, k_and);
+        if (!plan_covers(plan, k_or, k_and) || c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] != 0) {
+            // the scene's keys moved outside the cached plan: re-plan through discovery (which collects
+            // the depths for the z dictionary again), or from this frame's statistics without dictionaries
+            if (c->z_dictionary) c->plan_valid = false;
+            else make_plan(c, k_or, k_and);
             replanned = 1;
             continue;
         }
@@ -1530,7 +1603,6 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
         fm.hier = c->nlevels > 1;
         const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
         const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
-        uint32_t* hist = c->scratch + kHdrHist;
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
