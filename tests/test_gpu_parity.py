@@ -839,3 +839,54 @@ def test_row_layout_switches_keep_the_rows():
     assert "relayout_rows" not in ctx2.profile()
     ctx2.close()
     ctx.close()
+
+
+# ---- steady-state frames replay a CUDA graph ---------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["flat", "hierarchy"])
+def test_graph_replayed_frames_stay_exact(kind):
+    """frame 1 plans, frame 2 runs kernel by kernel, frame 3 captures, frames 4.. replay: all equal the
+    oracle, through velocity ticks, and an upload in between is picked up"""
+    if kind == "flat":
+        sc = scenes.config4(n=60_000, seed=81)
+        sc.sprites["texture"] = np.arange(sc.n) % 64
+        sc.sprites["layer"] = np.arange(sc.n) % 7
+    else:
+        sc = scenes.config3(n=40_000, seed=82)
+    has_vel = sc.velocities is not None
+    ctx = util.make_ctx(sc)
+    ref = util.make_oracle(sc)
+    launches = []
+    for k in range(7):
+        if has_vel:
+            ctx.system_integrate(0.01)
+            ref.step(0.01)
+        g = util.GpuFrame(ctx)
+        util.assert_frame_parity(g, ref.frame())
+        launches.append(g.info.kernel_launches)
+        assert g.info.sort_passes >= 2
+    assert len(set(launches[1:])) == 1  # replayed frames report the launches of the captured frame
+    # same frames without graphs
+    ctx2 = util.make_ctx(sc, cuda_graphs=0)
+    for k in range(7):
+        if has_vel:
+            ctx2.system_integrate(0.01)
+    g2 = util.GpuFrame(ctx2)
+    np.testing.assert_array_equal(g2.order, g.order)
+    np.testing.assert_array_equal(g2.instances.view(np.uint32), g.instances.view(np.uint32))
+    np.testing.assert_array_equal(g2.vertices.view(np.uint32), g.vertices.view(np.uint32))
+    ctx2.close()
+    # an upload changes data (and here the plan): the graph must not serve a stale frame
+    sc.sprites["texture"][: sc.n // 2] = 100
+    sc.sprites["size"][:, 0] += 1.0
+    ctx.upload_sprites(0, sc.sprites)
+    ref.close()
+    if has_vel:
+        sc.transforms = ctx.download_transforms(0, sc.n)
+    ref = util.make_oracle(sc)
+    for k in range(4):
+        if has_vel:
+            ctx.system_integrate(0.02)  # a different dt is a different signature
+            ref.step(0.02)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+    ctx.close()

@@ -116,9 +116,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("TB_REBUILD"):
-        path = _build.build()
+    path = os.environ.get("TB_LIB_PATH")  # a deployed build elsewhere; default: the in-tree library
+    if not path:
+        path = _build.LIB_PATH
+        if not os.path.exists(path) or os.environ.get("TB_REBUILD"):
+            path = _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol

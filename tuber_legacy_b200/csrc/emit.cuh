@@ -23,7 +23,6 @@ struct EmitParams {
     const uint64_t* mask_s;
     RowView rows;
     const WorldRow* world;   // non-null: hierarchy path, world rows instead of composing
-    FramePlan plan;
     float4* instances;       // 5 float4 per position
     float4* vertices;        // 4 float4 per position; nullptr: do not emit vertices (a presenter that
                              // receives instances from other GPUs regenerates them: vertices_from_instances)
@@ -40,6 +39,7 @@ struct EmitParams {
     float dt;
     uint32_t integrate;
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+    FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
 constexpr int kEmitItems = 2;
@@ -436,9 +436,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
     WarpShared& sm = reinterpret_cast<SmallShared*>(emit_smem_raw)->w[warp];
     const bool do_int = FUSED && ep.integrate && ep.vel != nullptr;
     PrepAcc acc;
-    __shared__ uint32_t s_zdict[kMaxZDict];
-    for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) s_zdict[k] = ep.plan.zdict[k];
-    __syncthreads();  // the only block barrier of the kernel, before the warps go their own ways
+    // z dictionary of the plan. The single-kernel frame (FUSED) only runs under plans without z bits.
+    __shared__ uint32_t s_zdict[FUSED ? 1 : kMaxZDict];
+    if (!FUSED) {
+        for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) s_zdict[k] = ep.plan.zdict[k];
+        __syncthreads();  // the only block barrier of the kernel, before the warps go their own ways
+    }
     const bool from_world = ep.world != nullptr;
     const bool keys_given = ep.keys_in != nullptr;
     const uint32_t n = ep.pass.n;
@@ -550,9 +553,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                         acc.k_and &= key;
                         acc.count += 1;
                     }
-                    bool miss = false;
-                    sk = plan_short_key(ep.plan, s_zdict, key, &miss);
-                    if (FUSED && miss) acc.miss = true;
+                    if (FUSED) {
+                        sk = pext_runs(key, ep.plan.pext);
+                    } else {
+                        bool miss = false;  // pass A of the same frame reports misses
+                        sk = plan_short_key(ep.plan, s_zdict, key, &miss);
+                    }
                 }
                 digit[k] = (uint32_t)sk & (R - 1u);
             }
@@ -657,7 +663,6 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
             atomicAdd(&ep.stats[2], (unsigned long long)c);
         }
-        if (__any_sync(0xffffffffu, acc.miss) && lane == 0) atomicOr(&ep.stats[4], 1ull);
     }
 }
 

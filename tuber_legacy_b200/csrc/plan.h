@@ -199,4 +199,21 @@ inline bool plan_covers(const FramePlan& f, uint64_t key_or, uint64_t key_and) {
     return (key_and & ~f.varying & m) == (f.constant & m) && (key_or & ~f.varying & m) == (f.constant & m);
 }
 
+// Field-wise equality (struct padding and unused dictionary slots do not count).
+inline bool plan_equal(const FramePlan& a, const FramePlan& b) {
+    if (a.pext.nruns != b.pext.nruns || a.pext.nbits != b.pext.nbits) return false;
+    for (int r = 0; r < kMaxRuns; ++r)
+        if (a.pext.src_shift[r] != b.pext.src_shift[r] || a.pext.width[r] != b.pext.width[r] ||
+            a.pext.dst_shift[r] != b.pext.dst_shift[r])
+            return false;
+    if (a.varying != b.varying || a.constant != b.constant || a.npasses != b.npasses || a.ltbits != b.ltbits ||
+        a.zbits != b.zbits || a.key64 != b.key64 || a.zdict_n != b.zdict_n)
+        return false;
+    for (int p = 0; p < kMaxPasses; ++p)
+        if (a.shift[p] != b.shift[p] || a.bits[p] != b.bits[p]) return false;
+    for (uint32_t k = 0; k < a.zdict_n; ++k)
+        if (a.zdict[k] != b.zdict[k]) return false;
+    return true;
+}
+
 }  // namespace tb

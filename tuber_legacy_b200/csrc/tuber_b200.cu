@@ -40,6 +40,19 @@ struct ProfTotal {
 
 }  // namespace
 
+// Everything the launches of a full frame read on the host side. Two frames with equal signatures
+// issue identical launches, so the second can replay the first one's graph.
+struct FrameSig {
+    uint64_t n = 0, max_batches = 0, global_first = 0, level_epoch = 0;
+    const void* ptr[24] = {};
+    FramePlan plan{};
+    uint32_t flags[12] = {};
+    bool operator==(const FrameSig& o) const {
+        return n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
+               memcmp(ptr, o.ptr, sizeof(ptr)) == 0 && memcmp(flags, o.flags, sizeof(flags)) == 0 && plan_equal(plan, o.plan);
+    }
+};
+
 struct tb_ctx {
     int device = 0;
     int sm_count = 148;
@@ -106,6 +119,15 @@ struct tb_ctx {
     unsigned long long* zset = nullptr;  // [kZSetSlots] entries + 1 overflow word
     unsigned long long* h_zset = nullptr;
     bool zset_active = false;
+
+    // steady-state full frames replay a captured CUDA graph (memset, every kernel, header copy)
+    int use_graphs = 1;
+    cudaGraphExec_t frame_graph = nullptr;
+    FrameSig frame_sig{};
+    bool frame_graph_valid = false;
+    bool frame_graph_seen = false;  // frame_sig holds the previous steady frame's signature
+    uint32_t frame_graph_launches = 0;
+    uint64_t level_epoch = 0;  // bumped whenever the level structure is rebuilt
 
     // hierarchy
     bool levels_dirty = true;
@@ -495,6 +517,7 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
 
 tb_status plan_levels(tb_ctx* c) {
     c->levels_dirty = false;
+    c->level_epoch++;
     c->nlevels = 1;
     c->level_ranges = true;
     c->level_first.clear();
@@ -802,6 +825,52 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     return TB_OK;
 }
 
+// Every launch of a full frame under the cached plan, in stream order, ending with the header copy.
+// Launch-only (no allocation, no synchronisation), so it can be captured into a graph.
+tb_status record_full_frame(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, bool integrate, bool prepare_made_counts,
+                            float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+    const FramePlan& plan = c->plan;
+    tb_status s;
+    // zero: stats, batch count, histograms, (layer,texture) bins, pass-0 tile counts
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
+    if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
+    uint32_t* hist = c->scratch + kHdrHist;
+    if (!fm.lt_generic) {
+        const uint32_t* bins = fm.lt_alias ? hist : c->scratch + L.lt_off;
+        TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
+                  (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
+    }
+    if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+    else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+    if (s) return s;
+    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return TB_OK;
+}
+
+void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void* d_inst, const void* d_vtx, const void* d_order,
+                     FrameSig* out) {
+    FrameSig& g = *out;
+    g.n = c->n;
+    g.max_batches = c->max_batches;
+    g.global_first = c->global_first;
+    g.level_epoch = c->level_epoch;
+    const void* ptrs[] = {c->rows.a, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
+                          c->mask[0], c->mask[1], c->mask[2], c->mask[3], c->batches, c->texlayer, c->level_list,
+                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr};
+    static_assert(sizeof(ptrs) <= sizeof(g.ptr), "FrameSig::ptr too small");
+    memcpy(g.ptr, ptrs, sizeof(ptrs));
+    g.plan = c->plan;
+    float dt = c->pending_dt;
+    uint32_t dt_bits;
+    memcpy(&dt_bits, &dt, 4);
+    const uint32_t flags[] = {integrate ? 1u : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
+                              fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
+                              c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.stride,
+                              (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0)};
+    static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
+    memcpy(g.flags, flags, sizeof(flags));
+}
+
 // The steady-state frame of a flat few-bucket scene whose buckets depend on the Sprite only: one
 // kernel (velocity system + key statistics + rank + compose + emit) placed by the tile offsets the
 // last full frame left in the scratch buffer. Returns true in *ok when the frame's own statistics
@@ -961,6 +1030,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->lt_global);
     cudaFree(c->place_tmp);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->frame_graph) cudaGraphExecDestroy(c->frame_graph);
     cudaFree(c->zset);
     if (c->h_zset) cudaFreeHost(c->h_zset);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1010,6 +1080,9 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->digit_bits = (int)value;
         c->plan_valid = false;
     c->static_valid = false;
+    } else if (k == "cuda_graphs") {
+        c->use_graphs = value != 0;
+        c->frame_graph_valid = false;
     } else if (k == "z_dictionary") {
         c->z_dictionary = value != 0;
         c->plan_valid = false;
@@ -1353,6 +1426,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         }
     }
     for (int attempt = 0; attempt < 4 && !fast_done; ++attempt) {
+        const bool cached_plan = c->plan_valid;
         if (!c->plan_valid) {
             // discovery: key statistics only (and the velocity system, exactly once)
             TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
@@ -1397,20 +1471,52 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
             c->texlayer_cap = cap;
         }
-        // zero: stats, batch count, histograms, (layer,texture) bins, pass-0 tile counts
-        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
-        if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
-        integrate = false;
-        uint32_t* hist = c->scratch + kHdrHist;
-        if (!fm.lt_generic) {
-            const uint32_t* bins = fm.lt_alias ? hist : c->scratch + L.lt_off;
-            TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
-                      (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
+        // Steady state (cached plan, nothing changed since the last frame): replay the captured graph.
+        // A frame whose launches would differ in any parameter has a different signature.
+        const bool graphable = c->use_graphs && cached_plan && !c->prof && !fm.lt_generic;
+        FrameSig sig;
+        if (graphable) frame_signature(c, fm, integrate, d_inst, d_vtx, d_order, &sig);
+        if (graphable && c->frame_graph_valid && sig == c->frame_sig) {
+            TB_CUDA(c, cudaGraphLaunch(c->frame_graph, c->stream));
+            c->launches += c->frame_graph_launches;
+            c->frame_launches += c->frame_graph_launches;
+            if (fm.hier) c->world_valid = true;
+        } else {
+            bool capture = graphable && !c->frame_graph_valid && c->frame_graph_seen && sig == c->frame_sig;
+            const uint32_t launches_before = c->frame_launches;
+            if (capture && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();  // e.g. the caller handed us the legacy default stream: run eagerly from now on
+                c->use_graphs = 0;
+                capture = false;
+            }
+            s = record_full_frame(c, fm, L, integrate, prepare_made_counts, d_inst, d_vtx, d_order);
+            if (capture) {
+                cudaGraph_t g = nullptr;
+                cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+                if (s == TB_OK && e != cudaSuccess) s = cuda_fail(c, e, "cudaStreamEndCapture");
+                if (s == TB_OK) {
+                    if (c->frame_graph) cudaGraphExecDestroy(c->frame_graph);
+                    c->frame_graph = nullptr;
+                    e = cudaGraphInstantiate(&c->frame_graph, g, 0);
+                    if (e != cudaSuccess) s = cuda_fail(c, e, "cudaGraphInstantiate");
+                }
+                if (g) cudaGraphDestroy(g);
+                if (s == TB_OK) {
+                    c->frame_graph_valid = true;
+                    c->frame_graph_launches = c->frame_launches - launches_before;
+                    TB_CUDA(c, cudaGraphLaunch(c->frame_graph, c->stream));
+                }
+            }
+            if (s) return s;
+            if (graphable && !capture) {
+                // first steady frame with this signature runs eagerly; the next one captures
+                c->frame_sig = sig;
+                c->frame_graph_seen = true;
+                c->frame_graph_valid = false;
+            }
         }
-        if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
-        else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
-        if (s) return s;
-        if ((s = read_header(c))) return s;
+        integrate = false;
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
         count = c->h_hdr[2];
         const uint64_t k_or = c->h_hdr[0], k_and = ~c->h_hdr[1];
         if (count == 0) break;
