@@ -30,11 +30,10 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 __device__ __forceinline__ Row load_row(const RowView& rv, uint32_t i) {
     Row r;
-    const size_t o = (size_t)i * rv.stride;
-    r.a0 = rv.a[o];
-    r.a1 = rv.a[o + 1];
-    r.b0 = rv.b[o];
-    r.b1 = rv.b[o + 1];
+    r.a0 = rv.t[(size_t)i * rv.st];
+    r.a1 = rv.a[(size_t)i * rv.st];
+    r.b0 = rv.b[(size_t)i * rv.sb];
+    r.b1 = rv.b[(size_t)i * rv.sb + 1];
     return r;
 }
 
@@ -48,9 +47,8 @@ __device__ __forceinline__ uint64_t flat_key(const RowView& rv, uint32_t i, cons
         Row r;
         r.a0 = a0;
         r.a1 = a1;
-        const size_t o = (size_t)i * rv.stride;
-        r.b0 = rv.b[o];
-        r.b1 = rv.b[o + 1];
+        r.b0 = rv.b[(size_t)i * rv.sb];
+        r.b1 = rv.b[(size_t)i * rv.sb + 1];
         z = local_z(r);
     }
     return sort_key(tl >> 16, tl & 0xFFFFu, z);

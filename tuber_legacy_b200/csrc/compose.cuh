@@ -9,18 +9,20 @@
 
 namespace tb {
 
-// Device row of the (Transform, Sprite) table: two 32-byte DRAM sectors per entity
-// (DESIGN.md §2). Sector A holds everything the sort key and the velocity system touch,
-// sector B the rest, so the key pass reads 32 B/entity and the integrate write-back dirties
-// one sector only.
+// Device row of the (Transform, Sprite) table: four 16-byte chunks per entity.
 //   A0 = {t.x, t.y, t.z, c.z}        A1 = {s.z, angle.x, angle.y, texture | layer << 16}
 //   B0 = {angle.z, c.x, c.y, s.x}    B1 = {s.y, size.w, size.h, 0}
-// `stride` is in float4 units: 2 when A and B are separate arrays, 4 when they are
-// interleaved into one 64-byte row (b == a + 2).
+// A0 is everything the velocity system writes; A0 + A1 everything the sort key of a planar entity
+// needs. Chunk A0 of entity i is t[i * st], A1 is a[i * st], B0 / B1 are b[i * sb] and b[i * sb + 1]
+// (strides in float4 units). Two layouts:
+//   split (start-up): three dense arrays T (16 B/entity), A (16 B), B (32 B), st = 1, sb = 2 — the
+//     velocity system's write-back is a dense 16 B/entity stream and the key pass reads 32 B/entity
+//   64-byte rows: t = R, a = R + 1, b = R + 2, st = sb = 4 — one DRAM atom per gathered entity
 struct RowView {
+    float4* t;
     float4* a;
     float4* b;
-    uint32_t stride;
+    uint32_t st, sb;
 };
 
 // The four 16-byte quarters of one row, in registers.

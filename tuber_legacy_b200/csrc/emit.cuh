@@ -152,15 +152,14 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
     const uint32_t mask = (1u << ep.pass.bits) - 1u;
     const uint32_t step = gridDim.x;
 
-    // Shared-memory row layouts. In-order passes land rows with TMA bulk copies, i.e. linearly
-    // (sector A of item li at rows[li*sstride], sector B at rows[boff + li*sstride]); gathered rows
-    // are placed chunk by chunk with cp.async into the bank-swizzled layout (row_slot).
-    const bool split = in_order && !from_world && ep.rows.stride == 2;
-    const uint32_t sstride = split ? 2u : 4u;
-    const uint32_t boff = split ? 2u * TILE : 2u;
+    // Shared-memory row layouts. In-order passes land rows with TMA bulk copies, i.e. as they lie in
+    // global memory (split arrays: T block, A block, B block of the tile; else 64-byte rows); gathered
+    // rows are placed chunk by chunk with cp.async into the bank-swizzled layout (row_slot).
+    const bool split = in_order && !from_world && ep.rows.st == 1;
     auto chunk = [&](uint32_t li, uint32_t c) -> uint32_t {
         if (!in_order) return row_slot(li, c);
-        return (c < 2 ? 0u : boff - 2u) + li * sstride + c;
+        if (!split) return li * 4u + c;
+        return c == 0 ? li : c == 1 ? TILE + li : 2u * TILE + li * 2u + (c - 2u);
     };
     auto tile_count = [&](uint32_t tile) -> uint32_t {
         const uint32_t base = tile * TILE;
@@ -179,10 +178,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
         if (from_world) {
             bulk_g2s(dst, ep.world + base, cnt * 64u, &sm.mbar[buf]);
         } else if (split) {
-            bulk_g2s(dst, ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(dst, ep.rows.t + base, cnt * 16u, &sm.mbar[buf]);
+            bulk_g2s(dst + TILE, ep.rows.a + base, cnt * 16u, &sm.mbar[buf]);
             bulk_g2s(dst + 2 * TILE, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
         } else {
-            bulk_g2s(dst, ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+            bulk_g2s(dst, ep.rows.t + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
         }
         if (ep.mask_t) bulk_g2s(sm.masks[buf][0], ep.mask_t + (base >> 6), mwords * 8u, &sm.mbar[buf]);
         if (ep.mask_s) bulk_g2s(sm.masks[buf][1], ep.mask_s + (base >> 6), mwords * 8u, &sm.mbar[buf]);
@@ -215,11 +215,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                     cp_async16(d + row_slot(li, 2), src + 2);
                     cp_async16(d + row_slot(li, 3), src + 3);
                 } else {
-                    const size_t o = (size_t)e * ep.rows.stride;
-                    cp_async16(d + row_slot(li, 0), ep.rows.a + o);
-                    cp_async16(d + row_slot(li, 1), ep.rows.a + o + 1);
-                    cp_async16(d + row_slot(li, 2), ep.rows.b + o);
-                    cp_async16(d + row_slot(li, 3), ep.rows.b + o + 1);
+                    cp_async16(d + row_slot(li, 0), ep.rows.t + (size_t)e * ep.rows.st);
+                    cp_async16(d + row_slot(li, 1), ep.rows.a + (size_t)e * ep.rows.st);
+                    cp_async16(d + row_slot(li, 2), ep.rows.b + (size_t)e * ep.rows.sb);
+                    cp_async16(d + row_slot(li, 3), ep.rows.b + (size_t)e * ep.rows.sb + 1);
                 }
             }
         }
@@ -447,9 +446,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
     const uint32_t n = ep.pass.n;
     const uint32_t ntiles = ep.pass.ntiles;  // == ceil(n / 64)
     const uint32_t R = 1u << ep.pass.bits;
-    const bool split = !from_world && ep.rows.stride == 2;
-    const uint32_t sstride = split ? 2u : 4u;
-    const uint32_t boff = split ? 2u * kWarpTile : 2u;
+    // shared-memory position of chunk c of tile item li: as the TMA bulk copies land it (split
+    // arrays: T block, A block, B block of the tile; else 64-byte rows)
+    const bool split = !from_world && ep.rows.st == 1;
+    const uint32_t s01 = split ? 1u : 4u, sb = split ? 2u : 4u;
+    const uint32_t off1 = split ? kWarpTile : 1u, offb = split ? 2u * kWarpTile : 2u;
     const uint32_t lt = lanemask_lt();
     const uint32_t nwarps = gridDim.x * kWarps;
     uint32_t tile = blockIdx.x * kWarps + warp;
@@ -463,10 +464,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         if (from_world) {
             bulk_g2s(sm.rows[buf], ep.world + base, cnt * 64u, &sm.mbar[buf]);
         } else if (split) {
-            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
+            bulk_g2s(sm.rows[buf], ep.rows.t + base, cnt * 16u, &sm.mbar[buf]);
+            bulk_g2s(sm.rows[buf] + kWarpTile, ep.rows.a + base, cnt * 16u, &sm.mbar[buf]);
             bulk_g2s(sm.rows[buf] + 2 * kWarpTile, ep.rows.b + (size_t)base * 2, cnt * 32u, &sm.mbar[buf]);
         } else {
-            bulk_g2s(sm.rows[buf], ep.rows.a + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
+            bulk_g2s(sm.rows[buf], ep.rows.t + (size_t)base * 4, cnt * 64u, &sm.mbar[buf]);
         }
         if (keys_given) bulk_g2s(sm.keys[buf], ep.keys_in + base, kbytes, &sm.mbar[buf]);
         if (do_int) bulk_g2s(sm.vel[buf], ep.vel + (size_t)base * 3, vbytes, &sm.mbar[buf]);
@@ -514,12 +516,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
             for (int k = 0; k < 2; ++k) {
                 const uint32_t li = k * 32 + lane;
                 if ((moving >> li) & 1ull) {
-                    float4 a0 = rows[li * sstride];
+                    float4 a0 = rows[li * s01];
                     a0.x = addr(a0.x, mulr(vel[li * 3], ep.dt));
                     a0.y = addr(a0.y, mulr(vel[li * 3 + 1], ep.dt));
                     a0.z = addr(a0.z, mulr(vel[li * 3 + 2], ep.dt));
-                    rows[li * sstride] = a0;
-                    ep.rows.a[(size_t)(base + li) * ep.rows.stride] = a0;
+                    rows[li * s01] = a0;
+                    ep.rows.t[(size_t)(base + li) * ep.rows.st] = a0;
                 }
             }
         }
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                 if (keys_given) {  // hierarchy frames always carry the keys pass A wrote
                     sk = (uint64_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li];
                 } else {
-                    const float4 a0 = rows[li * sstride], a1 = rows[li * sstride + 1];
+                    const float4 a0 = rows[li * s01], a1 = rows[off1 + li * s01];
                     float z;
                     if (is_planar(a1)) {
                         z = planar_z(a0, a1);
@@ -542,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                         Row r;
                         r.a0 = a0;
                         r.a1 = a1;
-                        r.b0 = rows[boff + li * sstride];
-                        r.b1 = rows[boff + li * sstride + 1];
+                        r.b0 = rows[offb + li * sb];
+                        r.b1 = rows[offb + li * sb + 1];
                         z = local_z(r);
                     }
                     const uint32_t tl = __float_as_uint(a1.w);
@@ -613,10 +615,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     tl = __float_as_uint(sv.z);
                 } else {
                     Row r;
-                    r.a0 = rows[li * sstride];
-                    r.a1 = rows[li * sstride + 1];
-                    r.b0 = rows[boff + li * sstride];
-                    r.b1 = rows[boff + li * sstride + 1];
+                    r.a0 = rows[li * s01];
+                    r.a1 = rows[off1 + li * s01];
+                    r.b0 = rows[offb + li * sb];
+                    r.b1 = rows[offb + li * sb + 1];
                     w = compose_local(r);
                     sw = r.b1.y;
                     shh = r.b1.z;

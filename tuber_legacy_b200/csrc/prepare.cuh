@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             vx[k] = vy[k] = vz[k] = 0.0f;
             has_t[k] = rend[k] = has_v[k] = false;
             if (inb) {
-                const size_t o = (size_t)i * p.rows.stride;
-                a0[k] = p.rows.a[o];
-                a1[k] = p.rows.a[o + 1];
+                const size_t o = (size_t)i * p.rows.st;
+                a0[k] = p.rows.t[o];
+                a1[k] = p.rows.a[o];
                 if (do_int) {
                     const float* v = p.vel + (size_t)i * 3;
                     vx[k] = __ldg(v);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
                 a0[k].x = addr(a0[k].x, mulr(vx[k], p.dt));
                 a0[k].y = addr(a0[k].y, mulr(vy[k], p.dt));
                 a0[k].z = addr(a0[k].z, mulr(vz[k], p.dt));
-                p.rows.a[(size_t)i * p.rows.stride] = a0[k];
+                p.rows.t[(size_t)i * p.rows.st] = a0[k];
             }
         }
         if (tiles_out) __syncthreads();
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
                 r.a0.x = addr(r.a0.x, mulr(vx, p.dt));
                 r.a0.y = addr(r.a0.y, mulr(vy, p.dt));
                 r.a0.z = addr(r.a0.z, mulr(vz, p.dt));
-                p.rows.a[(size_t)e * p.rows.stride] = r.a0;
+                p.rows.t[(size_t)e * p.rows.st] = r.a0;
             }
             w = compose_local(r);
         } else {

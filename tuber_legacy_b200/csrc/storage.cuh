@@ -17,18 +17,18 @@ __global__ void __launch_bounds__(kThreads) convert_transforms_kernel(const floa
     float v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = __ldg(t + k);
-    const size_t o = (size_t)(first + i) * rv.stride;
+    const size_t e = first + i;
     // A0 = {t.x, t.y, t.z, c.z}
-    rv.a[o] = make_float4(v[0], v[1], v[2], v[8]);
+    rv.t[e * rv.st] = make_float4(v[0], v[1], v[2], v[8]);
     // A1 = {s.z, angle.x, angle.y, texlayer}: keep .w
-    float* a1 = reinterpret_cast<float*>(rv.a + o + 1);
+    float* a1 = reinterpret_cast<float*>(rv.a + e * rv.st);
     a1[0] = v[11];
     a1[1] = v[3];
     a1[2] = v[4];
     // B0 = {angle.z, c.x, c.y, s.x}
-    rv.b[o] = make_float4(v[5], v[6], v[7], v[9]);
+    rv.b[e * rv.sb] = make_float4(v[5], v[6], v[7], v[9]);
     // B1 = {s.y, size.w, size.h, 0}: keep .y .z
-    float* b1 = reinterpret_cast<float*>(rv.b + o + 1);
+    float* b1 = reinterpret_cast<float*>(rv.b + e * rv.sb + 1);
     b1[0] = v[10];
 }
 
@@ -38,24 +38,24 @@ __global__ void __launch_bounds__(kThreads) convert_sprites_kernel(const uint32_
     if (i >= n) return;
     const uint4 s = __ldg(reinterpret_cast<const uint4*>(src) + i);
     if (s.z > 0xFFFFu || s.w > 0xFFFEu) atomicAdd(range_err, 1u);
-    const size_t o = (size_t)(first + i) * rv.stride;
-    float* a1 = reinterpret_cast<float*>(rv.a + o + 1);
+    const size_t e = first + i;
+    float* a1 = reinterpret_cast<float*>(rv.a + e * rv.st);
     a1[3] = __uint_as_float((s.z & 0xFFFFu) | (s.w << 16));
-    float* b1 = reinterpret_cast<float*>(rv.b + o + 1);
+    float* b1 = reinterpret_cast<float*>(rv.b + e * rv.sb + 1);
     b1[1] = __uint_as_float(s.x);
     b1[2] = __uint_as_float(s.y);
     b1[3] = 0.0f;
 }
 
-// Copies every row from one layout to the other (two 32-byte sector arrays <-> one 64-byte row per
-// entity): one thread per 16-byte chunk.
+// Copies every row from one layout to the other (split arrays <-> one 64-byte row per entity): one
+// thread per 16-byte chunk.
 __global__ void __launch_bounds__(kThreads) relayout_rows_kernel(RowView src, RowView dst, uint64_t n) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint64_t i = t >> 2;
     if (i >= n) return;
     const uint32_t ch = (uint32_t)t & 3u;
-    const float4* from = ((ch & 2u) ? src.b : src.a) + i * src.stride + (ch & 1u);
-    float4* to = ((ch & 2u) ? dst.b : dst.a) + i * dst.stride + (ch & 1u);
+    const float4* from = ch == 0 ? src.t + i * src.st : ch == 1 ? src.a + i * src.st : src.b + i * src.sb + (ch & 1u);
+    float4* to = ch == 0 ? dst.t + i * dst.st : ch == 1 ? dst.a + i * dst.st : dst.b + i * dst.sb + (ch & 1u);
     *to = *from;
 }
 
@@ -111,13 +111,13 @@ __global__ void __launch_bounds__(kThreads) integrate_kernel(RowView rows, const
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!mask_bit(mask_t, i) || !mask_bit(mask_v, i)) return;
-    const size_t o = (size_t)i * rows.stride;
-    float4 a0 = rows.a[o];
+    const size_t o = (size_t)i * rows.st;
+    float4 a0 = rows.t[o];
     const float* v = vel + (size_t)i * 3;
     a0.x = addr(a0.x, mulr(__ldg(v), dt));
     a0.y = addr(a0.y, mulr(__ldg(v + 1), dt));
     a0.z = addr(a0.z, mulr(__ldg(v + 2), dt));
-    rows.a[o] = a0;
+    rows.t[o] = a0;
 }
 
 // ---- Ecs::query: presence AND -> packed ascending indices --------------------------------------

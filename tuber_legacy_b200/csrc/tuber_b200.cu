@@ -53,6 +53,17 @@ struct FrameSig {
     }
 };
 
+// View of `cap` rows stored at `mem` (cap x 64 bytes) in either layout (compose.cuh).
+RowView make_row_view(float4* mem, uint64_t cap, bool interleaved) {
+    RowView v;
+    v.t = mem;
+    v.a = interleaved ? mem + 1 : mem + cap;
+    v.b = interleaved ? mem + 2 : mem + 2 * cap;
+    v.st = interleaved ? 4 : 1;
+    v.sb = interleaved ? 4 : 2;
+    return v;
+}
+
 struct tb_ctx {
     int device = 0;
     int sm_count = 148;
@@ -626,7 +637,7 @@ tb_status plan_levels(tb_ctx* c) {
 // Switches the row layout, converting whatever the rows hold (one pass over the storage, out of place).
 tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     if ((c->interleaved != 0) == interleaved) return TB_OK;
-    RowView dst;
+    RowView dst = c->rows;
     float4* fresh = nullptr;
     if (c->rows_touched) {
         cudaError_t e = cudaMalloc((void**)&fresh, c->cap * 64);
@@ -634,9 +645,7 @@ tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     } else {
         fresh = c->rows_mem;  // nothing uploaded yet: the rows are all zero in either layout
     }
-    dst.a = fresh;
-    dst.b = interleaved ? fresh + 2 : fresh + 2 * c->cap;
-    dst.stride = interleaved ? 4 : 2;
+    dst = make_row_view(fresh, c->cap, interleaved);
     if (c->rows_touched) {
         TB_LAUNCH(c, "relayout_rows", c->cap * 128, relayout_rows_kernel, (uint32_t)div_up(c->cap * 4, (uint64_t)kThreads), kThreads, 0,
                   c->rows, dst, (uint64_t)c->cap);
@@ -712,7 +721,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
             p.emit_tile_shift = L->small ? 6u : 9u;
         }
     }
-    const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 32 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
+    const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 16 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
     if (!fm.hier) {
         const uint32_t tiles = div_up(n, kThreads * kPrepItems);
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)c->sm_count * 8u);
@@ -854,7 +863,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     g.max_batches = c->max_batches;
     g.global_first = c->global_first;
     g.level_epoch = c->level_epoch;
-    const void* ptrs[] = {c->rows.a, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
+    const void* ptrs[] = {c->rows.t, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
                           c->mask[0], c->mask[1], c->mask[2], c->mask[3], c->batches, c->texlayer, c->level_list,
                           c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr};
     static_assert(sizeof(ptrs) <= sizeof(g.ptr), "FrameSig::ptr too small");
@@ -865,7 +874,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     memcpy(&dt_bits, &dt, 4);
     const uint32_t flags[] = {integrate ? 1u : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
                               fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
-                              c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.stride,
+                              c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
                               (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0)};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
@@ -901,7 +910,7 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.dt = c->pending_dt;
     ep.integrate = integrate && ep.vel != nullptr;
     ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
-    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 32 : 0)), (emit_small_kernel<uint32_t, true>),
+    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
               std::min<uint32_t>(div_up(c->static_tiles, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
     tb_status s = read_header(c);
     if (s) return s;
@@ -985,9 +994,7 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
         return TB_ERR_OOM;
     }
     cudaMemsetAsync(c->rows_mem, 0, max_entities * 64, c->stream);
-    c->rows.a = c->rows_mem;
-    c->rows.b = c->interleaved ? c->rows_mem + 2 : c->rows_mem + 2 * max_entities;
-    c->rows.stride = c->interleaved ? 4 : 2;
+    c->rows = make_row_view(c->rows_mem, max_entities, c->interleaved != 0);
     cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint32_t>));
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
@@ -1342,7 +1349,7 @@ tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* d
         cudaFree(d_rows); cudaFree(d_world); cudaFree(d_in); cudaFree(d_out);
         return cuda_fail(c, e, "cudaMalloc(as_matrix4)");
     }
-    RowView rv{d_rows, d_rows + 2 * m0, 2};
+    RowView rv = make_row_view(d_rows, m0, false);
     tb_status s = TB_OK;
     for (uint64_t off = 0; off < n && s == TB_OK; off += per) {
         const uint64_t m = std::min<uint64_t>(per, n - off);
