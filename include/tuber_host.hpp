@@ -40,6 +40,17 @@ namespace tuber {
 
 using EntityIndex = std::size_t;  // tuber-ecs/src/lib.rs:16
 
+// Generation-checked entity handle. The reference hands out bare indices and never reuses one
+// (ecs.rs:94-97), so an index cannot come to name ANOTHER entity, but it can outlive its own
+// (delete_by_ids / delete_by_query). A handle pairs the index with the generation it was issued at;
+// deleting an entity bumps its slot's generation, so stale handles stop resolving. Plain indices keep
+// working everywhere, exactly as in the reference.
+struct Entity {
+    EntityIndex index;
+    uint32_t generation;
+    bool operator==(const Entity& o) const { return index == o.index && generation == o.generation; }
+};
+
 struct Vector3f {
     float x = 0, y = 0, z = 0;
 };
@@ -138,6 +149,7 @@ public:
     EntityIndex insert(Cs... components) {
         if (next_ >= cap_) throw Error(TB_ERR_CAPACITY, "entity index beyond the presence bitset (the reference panics)");
         const EntityIndex e = next_++;
+        generation_.push_back(0);
         for (auto& kv : stores_) kv.second.data.push_back(nullptr);  // ecs.rs:194-196
         (put(e, std::move(components)), ...);
         count_dirty_ = true;
@@ -161,9 +173,25 @@ public:
     }
     // ecs.rs:105-112
     void delete_by_ids(const std::vector<EntityIndex>& ids) {
-        for (EntityIndex e : ids)
-            for (auto& kv : stores_)
-                if (e < next_) erase(kv.first, kv.second, e);
+        for (EntityIndex e : ids) {
+            if (e >= next_) continue;
+            for (auto& kv : stores_) erase(kv.first, kv.second, e);
+            generation_[e] += 1;  // handles issued before the delete no longer resolve
+        }
+    }
+
+    // Generation-checked handles over the never-reused indices.
+    Entity handle(EntityIndex e) const {
+        if (e >= next_) throw Error(TB_ERR_INVALID, "handle(): no such entity index");
+        return Entity{e, generation_[e]};
+    }
+    bool alive(Entity h) const { return h.index < next_ && generation_[h.index] == h.generation; }
+    std::optional<EntityIndex> resolve(Entity h) const {
+        return alive(h) ? std::optional<EntityIndex>(h.index) : std::nullopt;
+    }
+    template <class C>
+    const C* get(Entity h) {
+        return alive(h) ? get<C>(h.index) : nullptr;
     }
     // ecs.rs:100-103
     template <class... As>
@@ -356,6 +384,7 @@ private:
     tb_ctx* ctx_ = nullptr;
     uint64_t cap_;
     EntityIndex next_ = 0;
+    std::vector<uint32_t> generation_;  // per entity slot
     std::unordered_map<std::type_index, detail::Store> stores_;             // Components (ecs.rs:11)
     std::unordered_map<std::type_index, std::shared_ptr<void>> resources_;  // Resources (ecs.rs:12)
     std::unique_ptr<std::type_index> device_type_[TB_COMPONENT_COUNT];

@@ -115,7 +115,11 @@ static void source_only_semantics() {
     CHECK(ecs.get<Velocity>(4) == nullptr);
     ecs.remove_component<Sprite>(3);
     CHECK((ecs.query<Transform, Sprite>() == std::vector<EntityIndex>{9, 6, 0}));
+    const tuber::Entity h9 = ecs.handle(9), h6 = ecs.handle(6);
+    CHECK(ecs.alive(h9) && ecs.resolve(h9).value() == 9 && ecs.get<Transform>(h9) != nullptr);
     ecs.delete_by_ids({9});
+    CHECK(!ecs.alive(h9) && !ecs.resolve(h9).has_value() && ecs.get<Transform>(h9) == nullptr);  // stale handle
+    CHECK(ecs.alive(h6) && ecs.handle(9).generation == h9.generation + 1);
     CHECK((ecs.query<Transform, Sprite>() == std::vector<EntityIndex>{6, 0}));
     CHECK(ecs.entity_count() == 10);                            // indices are never reused
     CHECK((ecs.query_by_ids<Transform>({0, 1, 9, 42}) == std::vector<EntityIndex>{1, 0}));
