@@ -27,7 +27,7 @@ struct PrepParams {
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count, [4] z-dictionary misses ([3] holds the batch count)
     uint32_t* tile_counts;  // optional [1 << bits[0]][emit_tiles]: pass-0 digit counts per emit tile
     uint32_t emit_tiles;
-    uint32_t emit_tile_shift;  // log2 of the emit tile: 9 (CTA tiles of 512) or 6 (warp tiles of 64)
+    uint32_t emit_tile_shift;  // log2 of pass 0's tile: 6 (warp tiles of 64), 9 (emit tiles of 512), 11 (scatter tiles of 2048)
     uint32_t* key_hist;     // optional [1 << nbits]: histogram over the whole short key (multi-GPU placement)
     unsigned long long* zset;  // plan discovery: open-addressing set of the distinct orderable z values
     uint32_t* zset_overflow;   // ... set when the scene has more distinct depths than the set is meant for
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
     const bool small = prep_small(p);
     const bool tiles_out = !small && p.have_plan && p.tile_counts != nullptr;  // shared-memory per-tile counts
     const uint32_t R0 = 1u << p.plan.bits[0];
+    const bool wide_tiles = p.emit_tile_shift == 11;  // a 2048-pair scatter tile is two of this kernel's tiles
     PrepAcc acc;
     uint32_t par = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, par ^= 1u) {
@@ -241,14 +242,23 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
             // this 1024-entity tile is two 512-entity emit tiles (shared-memory counts) or
             // sixteen 64-entity warp tiles (direct global counts of the small path)
-            prep_account(p, sh, acc, rend[k], key, i, small, i >> p.emit_tile_shift, tiles_out ? sh.tcnt[par][k >> 1] : nullptr);
+            prep_account(p, sh, acc, rend[k], key, i, small, i >> p.emit_tile_shift,
+                         tiles_out ? sh.tcnt[par][wide_tiles ? 0 : (k >> 1)] : nullptr);
         }
         if (tiles_out) {
             __syncthreads();
-            for (uint32_t d = threadIdx.x; d < 2 * R0; d += kThreads) {
-                const uint32_t h = d / R0, dd = d - h * R0;
-                const uint32_t et = tile * 2 + h;
-                if (et < p.emit_tiles) p.tile_counts[(size_t)dd * p.emit_tiles + et] = sh.tcnt[par][h][dd];
+            if (wide_tiles) {
+                // half of a scatter tile: add to its (zeroed) counts
+                for (uint32_t d = threadIdx.x; d < R0; d += kThreads) {
+                    const uint32_t cnt = sh.tcnt[par][0][d];
+                    if (cnt) atomicAdd(&p.tile_counts[(size_t)d * p.emit_tiles + (tile >> 1)], cnt);
+                }
+            } else {
+                for (uint32_t d = threadIdx.x; d < 2 * R0; d += kThreads) {
+                    const uint32_t h = d / R0, dd = d - h * R0;
+                    const uint32_t et = tile * 2 + h;
+                    if (et < p.emit_tiles) p.tile_counts[(size_t)dd * p.emit_tiles + et] = sh.tcnt[par][h][dd];
+                }
             }
         }
     }

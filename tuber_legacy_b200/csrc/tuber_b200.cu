@@ -715,10 +715,13 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
         p.keys_out = c->keys[0];
         p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
         p.lt_hist = c->scratch + L->lt_off;
-        if (!fm.hier && c->plan.npasses == 1) {
+        if (!fm.hier) {
+            // pass 0 reads the keys in entity order, which is how this pass produces them: it counts
+            // pass 0's per-tile digits on the way (no tile_hist launch for that pass)
+            static_assert(kWarpTile == 64 && kEmitTile == 512 && kScatterTile == 2 * kThreads * kPrepItems, "tile shifts");
             p.tile_counts = c->scratch + L->counts_off[0];
             p.emit_tiles = L->tiles[0];
-            p.emit_tile_shift = L->small ? 6u : 9u;
+            p.emit_tile_shift = L->small ? 6u : (c->plan.npasses == 1 ? 9u : 11u);
         }
     }
     const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 16 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
@@ -1469,7 +1472,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
-        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
+        const bool prepare_made_counts = !fm.hier;  // flat frames: pass A counts pass 0's tile digits
         const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
@@ -1652,7 +1655,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
         const uint64_t n = c->n;
         FrameMode fm{};  // the batch table comes from the global bins, not from pass A
         fm.hier = c->nlevels > 1;
-        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
+        const bool prepare_made_counts = !fm.hier;  // flat frames: pass A counts pass 0's tile digits
         const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
         if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
@@ -1714,7 +1717,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     if (c->shard_count > 0) {
         FrameMode fm{};
         fm.hier = c->nlevels > 1;
-        const bool prepare_made_counts = !fm.hier && plan.npasses == 1;
+        const bool prepare_made_counts = !fm.hier;  // flat frames: pass A counts pass 0's tile digits
         const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
