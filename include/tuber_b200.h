@@ -191,7 +191,9 @@ TB_API tb_status tb_as_matrix4(tb_ctx* ctx, const tb_transform* src, uint64_t n,
 
 /* [SPEC] velocity integration for every entity with Transform and Velocity:
  * translation += velocity * dt, dt = DeltaTime.0 as f32 (state.rs:81). Queued on the
- * context's stream; when a frame follows it is fused into that frame's first pass. */
+ * context's stream; when a frame follows it is fused into that frame's first pass. Several
+ * ticks of the same dt before one frame (the fixed-timestep loop of tuber-winit/src/lib.rs:117-141
+ * runs 1-2 updates per render) run as one pass, each tick rounded as if run alone. */
 TB_API tb_status tb_system_integrate(tb_ctx* ctx, float dt);
 
 /* ---- frame: what a batching render_scene(&Ecs) does (tuber-graphics/src/lib.rs:134-156) -- */

@@ -890,3 +890,29 @@ def test_graph_replayed_frames_stay_exact(kind):
             ref.step(0.02)
         util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
     ctx.close()
+
+
+def test_several_ticks_before_a_frame_run_as_one_pass():
+    """the update loop may tick more than once per render: the ticks fuse into the frame's first pass and
+    give the bits of running them one after the other (also across a dt change and a download)"""
+    for sc, opts in ((scenes.config4(n=50_000, seed=91), {}), (scenes.config4(n=50_000, seed=92), {"static_buckets": 0}),
+                     (scenes.config3(n=30_000, seed=93), {})):
+        if sc.velocities is None:
+            sc.velocities = scenes.config4(n=sc.n, seed=94).velocities
+        ctx = util.make_ctx(sc, **opts)
+        ref = util.make_oracle(sc)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+        for ticks, dt in ((3, 0.01), (1, 0.01), (2, 0.02), (5, 0.01)):
+            for _ in range(ticks):
+                ctx.system_integrate(dt)
+                ref.step(dt)
+            g = util.GpuFrame(ctx)
+            util.assert_frame_parity(g, ref.frame())
+        # mixed dt without a frame in between, then a download (flushes the queue)
+        for dt in (0.01, 0.01, 0.03, 0.01):
+            ctx.system_integrate(dt)
+            ref.step(dt)
+        t = ctx.download_transforms(0, sc.n)
+        np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+        ctx.close()

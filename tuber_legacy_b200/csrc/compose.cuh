@@ -39,6 +39,18 @@ __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
 
+// The velocity system over `ticks` engine ticks of the same dt (the fixed-timestep loop of
+// tuber-winit/src/lib.rs:117-141 runs 1-2 updates per render): translation += velocity * dt, once per
+// tick, every product and sum rounded on its own — the value the ticks give one after the other.
+__device__ __forceinline__ void integrate_ticks(float4& a0, float vx, float vy, float vz, float dt, uint32_t ticks) {
+    const float dx = mulr(vx, dt), dy = mulr(vy, dt), dz = mulr(vz, dt);
+    for (uint32_t k = 0; k < ticks; ++k) {
+        a0.x = addr(a0.x, dx);
+        a0.y = addr(a0.y, dy);
+        a0.z = addr(a0.z, dz);
+    }
+}
+
 // Quaternion::from_euler (quaternion.rs:39-59) followed by rotation_matrix (:63-90),
 // un-normalised, returning the 3x3 block R[j][i].
 // Fast path: angle.x == 0 && angle.y == 0 (every 2-D sprite) needs one sincos instead of

@@ -37,7 +37,7 @@ struct EmitParams {
     const float* vel;
     const uint64_t* mask_v;
     float dt;
-    uint32_t integrate;
+    uint32_t integrate;      // engine ticks of `dt` to run (0: none)
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
@@ -517,9 +517,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                 const uint32_t li = k * 32 + lane;
                 if ((moving >> li) & 1ull) {
                     float4 a0 = rows[li * s01];
-                    a0.x = addr(a0.x, mulr(vel[li * 3], ep.dt));
-                    a0.y = addr(a0.y, mulr(vel[li * 3 + 1], ep.dt));
-                    a0.z = addr(a0.z, mulr(vel[li * 3 + 2], ep.dt));
+                    integrate_ticks(a0, vel[li * 3], vel[li * 3 + 1], vel[li * 3 + 2], ep.dt, ep.integrate);
                     rows[li * s01] = a0;
                     ep.rows.t[(size_t)(base + li) * ep.rows.st] = a0;
                 }

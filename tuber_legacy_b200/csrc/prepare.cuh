@@ -17,7 +17,7 @@ struct PrepParams {
     const uint64_t* mask_v;
     const float* vel;      // tb_velocity AoS (3 f32), nullptr when no Velocity store
     float dt;
-    uint32_t integrate;    // run the velocity system in this pass
+    uint32_t integrate;    // engine ticks of `dt` the velocity system runs in this pass (0: none)
     uint32_t have_plan;    // 0: only masks + count (plan discovery)
     uint32_t write_keys;   // short keys to keys_out (multi-pass plans)
     uint32_t lt_mode;      // 0: none (aliases digit pass 0), 1: shared-memory bins, 2: global bins
@@ -228,9 +228,7 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             const uint32_t i = base + k * kThreads;
             rend[k] = rend[k] && has_t[k];
             if (do_int && has_t[k] && has_v[k]) {
-                a0[k].x = addr(a0[k].x, mulr(vx[k], p.dt));
-                a0[k].y = addr(a0[k].y, mulr(vy[k], p.dt));
-                a0[k].z = addr(a0[k].z, mulr(vz[k], p.dt));
+                integrate_ticks(a0[k], vx[k], vy[k], vz[k], p.dt, p.integrate);
                 p.rows.t[(size_t)i * p.rows.st] = a0[k];
             }
         }
@@ -314,9 +312,7 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
         Affine w;
         if (live) {
             if (do_int && moves) {
-                r.a0.x = addr(r.a0.x, mulr(vx, p.dt));
-                r.a0.y = addr(r.a0.y, mulr(vy, p.dt));
-                r.a0.z = addr(r.a0.z, mulr(vz, p.dt));
+                integrate_ticks(r.a0, vx, vy, vz, p.dt, p.integrate);
                 p.rows.t[(size_t)e * p.rows.st] = r.a0;
             }
             w = compose_local(r);

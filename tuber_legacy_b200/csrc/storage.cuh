@@ -107,16 +107,15 @@ __global__ void __launch_bounds__(kThreads) mark_parent_presence_kernel(uint64_t
 // ---- standalone velocity system (when no frame follows the tick) --------------------------------
 
 __global__ void __launch_bounds__(kThreads) integrate_kernel(RowView rows, const uint64_t* mask_t, const uint64_t* mask_v,
-                                                              const float* __restrict__ vel, float dt, uint32_t n) {
+                                                              const float* __restrict__ vel, float dt, uint32_t ticks,
+                                                              uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!mask_bit(mask_t, i) || !mask_bit(mask_v, i)) return;
     const size_t o = (size_t)i * rows.st;
     float4 a0 = rows.t[o];
     const float* v = vel + (size_t)i * 3;
-    a0.x = addr(a0.x, mulr(__ldg(v), dt));
-    a0.y = addr(a0.y, mulr(__ldg(v + 1), dt));
-    a0.z = addr(a0.z, mulr(__ldg(v + 2), dt));
+    integrate_ticks(a0, __ldg(v), __ldg(v + 1), __ldg(v + 2), dt, ticks);
     rows.t[o] = a0;
 }
 

@@ -152,6 +152,7 @@ struct tb_ctx {
     // velocity system
     bool pending = false;
     float pending_dt = 0.0f;
+    uint32_t pending_ticks = 0;  // consecutive ticks of the same dt no frame has consumed yet: run as one pass
 
     // shard
     int rank = 0, nranks = 1;
@@ -314,7 +315,7 @@ tb_status flush_integrate(tb_ctx* c) {
     c->pending = false;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_VELOCITY]) return TB_OK;
     TB_LAUNCH(c, "integrate", c->n * 36ull, integrate_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows,
-              mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, (uint32_t)c->n);
+              mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, c->pending_ticks, (uint32_t)c->n);
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -700,7 +701,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     p.mask_v = mask_or_null(c, TB_VELOCITY);
     p.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
     p.dt = c->pending_dt;
-    p.integrate = integrate && p.vel != nullptr;
+    p.integrate = (integrate && p.vel != nullptr) ? c->pending_ticks : 0u;
     p.have_plan = have_plan;
     p.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     p.hist = c->scratch + kHdrHist;
@@ -875,7 +876,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     float dt = c->pending_dt;
     uint32_t dt_bits;
     memcpy(&dt_bits, &dt, 4);
-    const uint32_t flags[] = {integrate ? 1u : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
+    const uint32_t flags[] = {integrate ? c->pending_ticks : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
                               fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
                               c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
                               (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0)};
@@ -911,7 +912,7 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
     ep.mask_v = mask_or_null(c, TB_VELOCITY);
     ep.dt = c->pending_dt;
-    ep.integrate = integrate && ep.vel != nullptr;
+    ep.integrate = (integrate && ep.vel != nullptr) ? c->pending_ticks : 0u;
     ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
               std::min<uint32_t>(div_up(c->static_tiles, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
@@ -1372,10 +1373,17 @@ tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* d
 
 tb_status tb_system_integrate(tb_ctx* c, float dt) {
     if (!c) return TB_ERR_INVALID;
-    tb_status s = flush_integrate(c);  // an earlier tick that no frame consumed
+    // several ticks of the same dt between two frames (a 100 Hz update loop under a 60 Hz render loop,
+    // tuber-winit/src/lib.rs:117-141) run as ONE pass over the rows, each tick rounded on its own
+    if (c->pending && memcmp(&dt, &c->pending_dt, sizeof(float)) == 0 && c->pending_ticks < 4096) {
+        c->pending_ticks += 1;
+        return TB_OK;
+    }
+    tb_status s = flush_integrate(c);  // earlier ticks of another dt that no frame consumed
     if (s) return s;
     c->pending = true;
     c->pending_dt = dt;
+    c->pending_ticks = 1;
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
