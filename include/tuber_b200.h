@@ -202,6 +202,14 @@ TB_API tb_status tb_system_integrate(tb_ctx* ctx, float dt);
  * -> sort key (layer, texture, world z, entity) -> instances + quad vertices + batch table.
  * Synchronises the stream before returning (the counts in `out` are host values). */
 TB_API tb_status tb_frame_transform_batch(tb_ctx* ctx, tb_frame_out* out);
+/* [SPEC] camera: a row-major 4x4 view-projection matrix folded into the emitted
+ * geometry: instance model = view_proj * world (Matrix4::mul, matrix.rs:174-194), quad corners
+ * transformed by that product (transform_vec3, matrix.rs:160-171). The draw order stays by world z.
+ * NULL removes the camera (the default). */
+TB_API tb_status tb_frame_set_view_projection(tb_ctx* ctx, const float* view_proj16);
+/* Matrix4::new_orthographic (matrix.rs:41-58) in f32, row-major, into out16. */
+TB_API tb_status tb_orthographic(float left, float right, float bottom, float top, float near_plane, float far_plane,
+                                 float* out16);
 /* Force one path (enum tb_path; TB_PATH_NONE == automatic). Results never depend on it. */
 TB_API tb_status tb_frame_force_path(tb_ctx* ctx, uint32_t path);
 

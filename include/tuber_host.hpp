@@ -455,9 +455,22 @@ public:
 // in draw order (tb_frame_out) for the presenter.
 class Graphics : public GraphicsAPI {
 public:
+    // Camera ([SPEC]): an orthographic view-projection (Matrix4::new_orthographic, matrix.rs:41-58) folded
+    // into the emitted instances and vertices; clear_camera() goes back to world-space output.
+    void set_orthographic(float left, float right, float bottom, float top, float near_plane, float far_plane) {
+        tb_orthographic(left, right, bottom, top, near_plane, far_plane, view_proj_);
+        has_camera_ = true;
+    }
+    void set_view_projection(const float (&row_major)[16]) {
+        std::memcpy(view_proj_, row_major, sizeof(view_proj_));
+        has_camera_ = true;
+    }
+    void clear_camera() { has_camera_ = false; }
+
     GraphicsResult render_scene(Ecs& ecs) override {
         try {
             ecs.flush();
+            ecs.check(tb_frame_set_view_projection(ecs.ctx(), has_camera_ ? view_proj_ : nullptr), "tb_frame_set_view_projection");
             ecs.check(tb_frame_transform_batch(ecs.ctx(), &frame_), "tb_frame_transform_batch");
         } catch (const Error& e) {
             return GraphicsError{e.what()};
@@ -490,6 +503,8 @@ public:
 private:
     tb_frame_out frame_{};
     Ecs* ecs_ = nullptr;
+    float view_proj_[16] = {};
+    bool has_camera_ = false;
 };
 
 }  // namespace tuber

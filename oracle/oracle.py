@@ -51,6 +51,9 @@ def lib():
         L.orc_scene_read_transforms.argtypes = [vp, vp]
         L.orc_frame_run.restype = vp
         L.orc_frame_run.argtypes = [vp]
+        L.orc_frame_run_camera.restype = vp
+        L.orc_frame_run_camera.argtypes = [vp, vp]
+        L.orc_orthographic.argtypes = [C.c_float] * 6 + [vp]
         L.orc_frame_free.argtypes = [vp]
         L.orc_frame_seconds.restype = dbl
         L.orc_frame_seconds.argtypes = [vp]
@@ -195,8 +198,19 @@ class Scene:
         lib().orc_scene_read_transforms(self._h, _p(out))
         return out
 
-    def frame(self):
-        return Frame(lib().orc_frame_run(self._h))
+    def frame(self, view_proj=None):
+        """render_scene; `view_proj` (4x4 row-major f32) folds a camera into instances and vertices."""
+        if view_proj is None:
+            return Frame(lib().orc_frame_run(self._h))
+        m = np.ascontiguousarray(np.asarray(view_proj, np.float32).reshape(16))
+        return Frame(lib().orc_frame_run_camera(self._h, _p(m)))
+
+
+def orthographic(left, right, bottom, top, near, far):
+    """Matrix4::new_orthographic (matrix.rs:41-58), row-major 4x4 f32."""
+    out = np.zeros(16, np.float32)
+    lib().orc_orthographic(left, right, bottom, top, near, far, _p(out))
+    return out.reshape(4, 4)
 
 
 def as_matrix4(transforms):

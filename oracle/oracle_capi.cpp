@@ -364,6 +364,19 @@ void* orc_frame_run(void* h) {
     render_scene(o->ecs, f->r);
     return f;
 }
+// The same with a view-projection matrix (row-major 16 f32) folded into the emitted geometry.
+void* orc_frame_run_camera(void* h, const float* view_proj16) {
+    auto* o = static_cast<OrcEcs*>(h);
+    auto* f = new OrcFrame();
+    Mat4f vp;
+    for (int k = 0; k < 16; ++k) vp.v[k] = view_proj16[k];
+    render_scene(o->ecs, f->r, &vp);
+    return f;
+}
+void orc_orthographic(float l, float r, float b, float t, float n, float fa, float* out16) {
+    const Mat4f m = new_orthographic(l, r, b, t, n, fa);
+    for (int k = 0; k < 16; ++k) out16[k] = m.v[k];
+}
 void orc_frame_free(void* f) { delete static_cast<OrcFrame*>(f); }
 double orc_frame_seconds(void* f) { return static_cast<OrcFrame*>(f)->r.seconds; }
 uint64_t orc_frame_num_instances(void* f) { return static_cast<OrcFrame*>(f)->r.instances.size(); }

@@ -112,7 +112,9 @@ struct FrameResult {
 
 // What a batching `render_scene(&Ecs)` does with the Ecs it is handed
 // (tuber-graphics/src/lib.rs:134-156 is the slot; contents per SPEC).
-inline void render_scene(const Ecs& ecs, FrameResult& out) {
+// `view_proj` ([SPEC]): when given, instances carry view_proj * world and the quad
+// corners are transformed by it (Matrix4::mul then transform_vec3); the draw order stays by world z.
+inline void render_scene(const Ecs& ecs, FrameResult& out, const Mat4f* view_proj = nullptr) {
     auto t0 = std::chrono::steady_clock::now();
     const size_t n = ecs.entity_count();
     out.world.assign(n, identity<float>());
@@ -183,7 +185,7 @@ inline void render_scene(const Ecs& ecs, FrameResult& out) {
     out.batches.clear();
     for (size_t pos = 0; pos < m; ++pos) {
         const Item& it = items[pos];
-        const Mat4f& w = out.world[it.entity];
+        const Mat4f w = view_proj ? mul(*view_proj, out.world[it.entity]) : out.world[it.entity];
         out.order[pos] = it.entity;
         out.keys[pos] = it.key;
         Instance& inst = out.instances[pos];

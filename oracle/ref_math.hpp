@@ -60,6 +60,21 @@ inline Mat4f new_scale(const Vec3& s) {
     return m;
 }
 
+// matrix.rs:41-58 — Matrix4::new_orthographic (unused by the reference itself; the camera a batching
+// render_scene folds into its emit).
+inline Mat4f new_orthographic(float left, float right, float bottom, float top, float near_, float far_) {
+    Mat4f m;
+    for (int k = 0; k < 16; ++k) m.v[k] = 0.0f;
+    m.v[0] = 2.0f / (right - left);
+    m.v[3] = -((right + left) / (right - left));
+    m.v[5] = 2.0f / (top - bottom);
+    m.v[7] = -((top + bottom) / (top - bottom));
+    m.v[10] = -2.0f / (far_ - near_);
+    m.v[11] = -((far_ + near_) / (far_ - near_));
+    m.v[15] = 1.0f;
+    return m;
+}
+
 // matrix.rs:174-194 — out[j][i] = a[j][0]*b[0][i] + a[j][1]*b[1][i] + a[j][2]*b[2][i]
 // + a[j][3]*b[3][i], evaluated left to right.
 template <typename T>

@@ -916,3 +916,32 @@ def test_several_ticks_before_a_frame_run_as_one_pass():
         np.testing.assert_array_equal(t.view(np.uint32).reshape(-1, 12), ref.transforms().view(np.uint32))
         util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
         ctx.close()
+
+
+# ---- camera: view-projection folded into the emitted geometry ------------------------------------------------
+
+def test_camera_view_projection_folded_into_every_emit_path():
+    """instances carry view_proj * world, corners are transformed by it; order and batches are unchanged"""
+    vp = capi.orthographic(-1200.0, 1200.0, -900.0, 900.0, -100.0, 100.0)
+    np.testing.assert_array_equal(vp.view(np.uint32), oracle.orthographic(-1200.0, 1200.0, -900.0, 900.0, -100.0, 100.0).view(np.uint32))
+    general = vp.copy()
+    general[3] = [0.001, -0.002, 0.003, 1.5]  # a non-affine last row is carried through as well
+    cases = [(scenes.config4(n=40_000, seed=101), {}),                    # single-kernel frames
+             (scenes.config4(n=40_000, seed=102), {"small_emit": 0}),     # CTA-tile emit, in order
+             (scenes.config2(n=60_000, seed=103), {}),                    # sorted stream, gathered rows, graph replay
+             (scenes.config3(n=30_000, seed=104), {})]                    # hierarchy: world rows
+    for sc, opts in cases:
+        ctx = util.make_ctx(sc, **opts)
+        ref = util.make_oracle(sc)
+        plain = ref.frame()
+        for m in (vp, None, general, general, general, vp):
+            ctx.set_view_projection(m)
+            if sc.velocities is not None:
+                ctx.system_integrate(0.01)
+                ref.step(0.01)
+            g = util.GpuFrame(ctx)
+            r = ref.frame(m)
+            util.assert_frame_parity(g, r)
+            np.testing.assert_array_equal(r.order, ref.frame().order)
+        assert not np.array_equal(plain.instances["model"], r.instances["model"])
+        ctx.close()

@@ -144,3 +144,23 @@ def test_sort_key_orders_like_floats():
     assert oracle.sort_key(1, 0, 5.0) > oracle.sort_key(0, 65535, 1e30)  # layer dominates
     assert oracle.sort_key(0, 2, -5.0) > oracle.sort_key(0, 1, 5.0)       # then texture
     assert keys[8] >> 32 == (3 << 16 | 7)
+
+
+def test_orthographic_matches_matrix_rs_and_the_library():
+    """Matrix4::new_orthographic (matrix.rs:41-58): entries by hand, and the product library's host helper
+    (tb_orthographic, no GPU needed) is bit-identical to the oracle's restatement."""
+    from tuber_legacy_b200 import capi
+    m = oracle.orthographic(0.0, 800.0, 0.0, 600.0, -1.0, 1.0)
+    f = np.float32
+    expect = np.array([[f(2) / f(800), 0, 0, -(f(800) / f(800))],
+                       [0, f(2) / f(600), 0, -(f(600) / f(600))],
+                       [0, 0, f(-2) / f(2), -(f(0) / f(2))],
+                       [0, 0, 0, 1]], np.float32)
+    np.testing.assert_array_equal(m, expect)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        l, b, n = rng.uniform(-1000, 0, 3)
+        r, t, fa = rng.uniform(1, 1000, 3)
+        a = oracle.orthographic(l, r, b, t, n, fa)
+        g = capi.orthographic(l, r, b, t, n, fa)
+        np.testing.assert_array_equal(a.view(np.uint32), g.view(np.uint32))

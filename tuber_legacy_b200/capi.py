@@ -77,6 +77,8 @@ _SIGNATURES = {
     "tb_system_integrate": (C.c_int32, [C.c_void_p, C.c_float]),
     "tb_frame_transform_batch": (C.c_int32, [C.c_void_p, C.POINTER(FrameOut)]),
     "tb_frame_force_path": (C.c_int32, [C.c_void_p, C.c_uint32]),
+    "tb_frame_set_view_projection": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "tb_orthographic": (C.c_int32, [C.c_float] * 6 + [C.c_void_p]),
     "tb_download_instances": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_vertices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_batches": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -261,6 +263,14 @@ class Context:
         self._check(self._lib.tb_system_integrate(self._h, float(np.float32(dt))))
 
     # -- frame
+    def set_view_projection(self, view_proj):
+        """Row-major 4x4 f32 folded into instances and vertices; None removes the camera."""
+        if view_proj is None:
+            self._check(self._lib.tb_frame_set_view_projection(self._h, None))
+        else:
+            m = np.ascontiguousarray(np.asarray(view_proj, np.float32).reshape(16))
+            self._check(self._lib.tb_frame_set_view_projection(self._h, _ptr(m)))
+
     def force_path(self, path):
         self._check(self._lib.tb_frame_force_path(self._h, int(path)))
 
@@ -398,3 +408,11 @@ def ipc_open(handle, device=0):
 
 def ipc_close(ptr):
     load().tb_ipc_close(C.c_void_p(ptr))
+
+
+def orthographic(left, right, bottom, top, near, far):
+    """Matrix4::new_orthographic (matrix.rs:41-58): row-major 4x4 f32."""
+    out = np.zeros(16, np.float32)
+    if load().tb_orthographic(left, right, bottom, top, near, far, _ptr(out)) != 0:
+        raise TuberError(1, "tb_orthographic")
+    return out.reshape(4, 4)

@@ -39,6 +39,10 @@ struct EmitParams {
     float dt;
     uint32_t integrate;      // engine ticks of `dt` to run (0: none)
     unsigned long long* stats;  // [0] OR of keys, [1] OR of ~keys, [2] renderable count
+    // camera ([SPEC]): rows of a row-major view-projection matrix folded into the
+    // emitted geometry (instance model = vp * world, corners transformed by it); has_vp == 0: none
+    float4 vp[4];
+    uint32_t has_vp;
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -68,12 +72,21 @@ struct EmitShared {
 // sort bucket spread over all eight 16-byte bank groups.
 __device__ __forceinline__ uint32_t row_slot(uint32_t li, uint32_t c) { return ((li << 2) | c) ^ ((li >> 1) & 7u); }
 
-__device__ __forceinline__ void make_outputs(const Affine& w, float sw, float shh, uint32_t tl, InstanceOut& inst,
-                                             float4 (&vtx)[4]) {
-    inst.c0 = make_float4(w.r0.x, w.r1.x, w.r2.x, 0.0f);
-    inst.c1 = make_float4(w.r0.y, w.r1.y, w.r2.y, 0.0f);
-    inst.c2 = make_float4(w.r0.z, w.r1.z, w.r2.z, 0.0f);
-    inst.c3 = make_float4(w.r0.w, w.r1.w, w.r2.w, 1.0f);
+template <typename Params>
+__device__ __forceinline__ void make_outputs(const Params& ep, const Affine& world, float sw, float shh, uint32_t tl,
+                                             InstanceOut& inst, float4 (&vtx)[4]) {
+    Affine w = world;
+    float4 r3 = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    if (ep.has_vp) {  // Matrix4::mul(view_proj, world), matrix.rs:174-194
+        w.r0 = mul_row(ep.vp[0], world);
+        w.r1 = mul_row(ep.vp[1], world);
+        w.r2 = mul_row(ep.vp[2], world);
+        r3 = mul_row(ep.vp[3], world);
+    }
+    inst.c0 = make_float4(w.r0.x, w.r1.x, w.r2.x, r3.x);
+    inst.c1 = make_float4(w.r0.y, w.r1.y, w.r2.y, r3.y);
+    inst.c2 = make_float4(w.r0.z, w.r1.z, w.r2.z, r3.z);
+    inst.c3 = make_float4(w.r0.w, w.r1.w, w.r2.w, r3.w);
     inst.s = make_float4(sw, shh, __uint_as_float(tl & 0xFFFFu), __uint_as_float(tl >> 16));
     // corners (0,0) (w,0) (w,h) (0,h), transform_vec3 (matrix.rs:160-171)
     const float cx[4] = {0.0f, sw, sw, 0.0f};
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
                 }
-                make_outputs(w, sw, shh, tl, inst, vtx);
+                make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = e + ep.global_first;
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
                 }
-                make_outputs(w, sw, shh, tl, inst, vtx);
+                make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = base + li + ep.global_first;
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }

@@ -47,8 +47,9 @@ struct FrameSig {
     const void* ptr[24] = {};
     FramePlan plan{};
     uint32_t flags[12] = {};
+    uint32_t vp_bits[17] = {};  // has_vp, then the 16 matrix entries
     bool operator==(const FrameSig& o) const {
-        return n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
+        return memcmp(vp_bits, o.vp_bits, sizeof(vp_bits)) == 0 && n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
                memcmp(ptr, o.ptr, sizeof(ptr)) == 0 && memcmp(flags, o.flags, sizeof(flags)) == 0 && plan_equal(plan, o.plan);
     }
 };
@@ -109,6 +110,10 @@ struct tb_ctx {
     uint64_t ext_cap = 0;
     uint64_t last_instances = 0, last_batches = 0;
     bool frame_valid = false;
+
+    // camera folded into the emitted geometry (tb_frame_set_view_projection)
+    float vp[16] = {};
+    bool has_vp = false;
 
     // plan
     FramePlan plan{};
@@ -256,6 +261,16 @@ void prof_clear(tb_ctx* c) {
     c->prof_pool.clear();
     c->prof_totals.clear();
 }
+
+// Device scratch that lives for one call.
+struct DeviceTemp {
+    void* p = nullptr;
+    DeviceTemp() = default;
+    DeviceTemp(const DeviceTemp&) = delete;
+    DeviceTemp& operator=(const DeviceTemp&) = delete;
+    ~DeviceTemp() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+};
 
 #define TB_LAUNCH(c, name, bytes, kern, grid, block, smem, ...)        \
     do {                                                               \
@@ -528,14 +543,17 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
 }
 
 tb_status plan_levels(tb_ctx* c) {
-    c->levels_dirty = false;
+    c->levels_dirty = true;  // until this function succeeds
     c->level_epoch++;
     c->nlevels = 1;
     c->level_ranges = true;
     c->level_first.clear();
     c->level_count.clear();
     const uint32_t n = (uint32_t)c->n;
-    if (!c->store[TB_PARENT] || n == 0) return TB_OK;
+    if (!c->store[TB_PARENT] || n == 0) {
+        c->levels_dirty = false;
+        return TB_OK;
+    }
     // hop / dist ping-pong + sane_parent + list
     if (c->level_cap < n) {
         if (c->level_list) cudaFree(c->level_list);
@@ -545,14 +563,14 @@ tb_status plan_levels(tb_ctx* c) {
         TB_CUDA(c, cudaMalloc((void**)&c->sane_parent, (size_t)n * 4));
         c->level_cap = n;
     }
-    uint32_t* tmp = nullptr;
     const size_t stride = ((size_t)n + 3) & ~(size_t)3;  // 16-byte aligned columns: the level sort reads them by TMA
-    TB_CUDA(c, cudaMalloc((void**)&tmp, stride * 4 * 4 + 16));
+    DeviceTemp tmp_owner;  // freed on every return path
+    TB_CUDA(c, tmp_owner.alloc(stride * 4 * 4 + 16));
+    uint32_t* tmp = static_cast<uint32_t*>(tmp_owner.p);
     uint32_t* hop[2] = {tmp, tmp + stride};
     uint32_t* dist[2] = {tmp + 2 * stride, tmp + 3 * stride};
     tb_status s = ensure_scratch(c, kHdrWords);
     if (s) {
-        cudaFree(tmp);
         return s;
     }
     const uint32_t grid = div_up(n, kThreads);
@@ -569,13 +587,11 @@ tb_status plan_levels(tb_ctx* c) {
         cudaMemcpyAsync(&pending, c->scratch + kHdrPending, 4, cudaMemcpyDeviceToHost, c->stream);
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) {
-            cudaFree(tmp);
             return cuda_fail(c, e, "plan_levels");
         }
         done = pending == 0;
     }
     if (!done) {
-        cudaFree(tmp);
         c->levels_dirty = true;
         return fail(c, TB_ERR_CYCLE, "the Parent links contain a cycle");
     }
@@ -587,30 +603,24 @@ tb_status plan_levels(tb_ctx* c) {
     cudaMemcpyAsync(stats, c->scratch + kHdrLevelStats, 8, cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
-        cudaFree(tmp);
         return cuda_fail(c, e, "plan_levels");
     }
     c->nlevels = stats[0] + 1;
     c->level_ranges = stats[1] == 0;
     if (c->nlevels > 1) {
         if (c->nlevels > 65536) {
-            cudaFree(tmp);
-            c->levels_dirty = true;
             return fail(c, TB_ERR_UNSUPPORTED, "hierarchy deeper than 65536 levels");
         }
-        uint32_t* d_hist = nullptr;
-        TB_CUDA(c, cudaMalloc((void**)&d_hist, (size_t)c->nlevels * 4));
+        DeviceTemp hist_owner;
+        TB_CUDA(c, hist_owner.alloc((size_t)c->nlevels * 4));
+        uint32_t* d_hist = static_cast<uint32_t*>(hist_owner.p);
         cudaMemsetAsync(d_hist, 0, (size_t)c->nlevels * 4, c->stream);
         TB_LAUNCH(c, "level_hist", 0, level_hist_kernel, grid, kThreads, 0, level, (const uint64_t*)nullptr, n, d_hist,
                   c->nlevels);
         c->level_count.resize(c->nlevels);
         cudaMemcpyAsync(c->level_count.data(), d_hist, (size_t)c->nlevels * 4, cudaMemcpyDeviceToHost, c->stream);
         e = cudaStreamSynchronize(c->stream);
-        cudaFree(d_hist);
-        if (e != cudaSuccess) {
-            cudaFree(tmp);
-            return cuda_fail(c, e, "plan_levels");
-        }
+        if (e != cudaSuccess) return cuda_fail(c, e, "plan_levels");
         c->level_first.resize(c->nlevels);
         uint32_t run = 0;
         for (uint32_t l = 0; l < c->nlevels; ++l) {
@@ -621,17 +631,12 @@ tb_status plan_levels(tb_ctx* c) {
             uint32_t nbits = 0;
             while ((1u << nbits) < c->nlevels) ++nbits;
             uint32_t* sorted = nullptr;
-            s = sort_ids_by_key(c, level, n, nbits, &sorted);
-            if (s) {
-                cudaFree(tmp);
-                return s;
-            }
-            cudaMemcpyAsync(c->level_list, sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream);
-            cudaStreamSynchronize(c->stream);
+            if ((s = sort_ids_by_key(c, level, n, nbits, &sorted))) return s;
+            TB_CUDA(c, cudaMemcpyAsync(c->level_list, sorted, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
         }
     }
-    cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));  // the temporaries die with this scope
+    c->levels_dirty = false;
     return TB_OK;
 }
 
@@ -650,7 +655,11 @@ tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     if (c->rows_touched) {
         TB_LAUNCH(c, "relayout_rows", c->cap * 128, relayout_rows_kernel, (uint32_t)div_up(c->cap * 4, (uint64_t)kThreads), kThreads, 0,
                   c->rows, dst, (uint64_t)c->cap);
-        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        const cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(fresh);
+            return cuda_fail(c, e, "relayout_rows");
+        }
         cudaFree(c->rows_mem);
         c->rows_mem = fresh;
     }
@@ -758,6 +767,15 @@ tb_status read_header(tb_ctx* c) {
     return TB_OK;
 }
 
+// The context's camera as kernel parameters.
+template <typename Params>
+void set_camera(const tb_ctx* c, Params* ep) {
+    ep->has_vp = c->has_vp ? 1u : 0u;
+    for (int j = 0; j < 4; ++j)
+        ep->vp[j] = c->has_vp ? make_float4(c->vp[4 * j], c->vp[4 * j + 1], c->vp[4 * j + 2], c->vp[4 * j + 3])
+                              : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 template <typename KeyT>
 tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, bool prepare_made_counts,
                             float4* d_inst, float4* d_vtx, uint32_t* d_order) {
@@ -826,6 +844,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             ep.global_first = (uint32_t)c->global_first;
             ep.staged = c->staged_emit;
             ep.remap = c->shard_state == 4 ? c->remap : nullptr;
+            set_camera(c, &ep);
             if (L.small && iin == nullptr) {
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0)), (emit_small_kernel<KeyT, false>),
                           std::min<uint32_t>(div_up(L.tiles[p], kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
@@ -882,7 +901,10 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
                               (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0)};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
+    g.vp_bits[0] = c->has_vp ? 1u : 0u;
+    if (c->has_vp) memcpy(g.vp_bits + 1, c->vp, sizeof(c->vp));
 }
+
 
 // The steady-state frame of a flat few-bucket scene whose buckets depend on the Sprite only: one
 // kernel (velocity system + key statistics + rank + compose + emit) placed by the tile offsets the
@@ -914,6 +936,7 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.dt = c->pending_dt;
     ep.integrate = (integrate && ep.vel != nullptr) ? c->pending_ticks : 0u;
     ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    set_camera(c, &ep);
     TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
               std::min<uint32_t>(div_up(c->static_tiles, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
     tb_status s = read_header(c);
@@ -1340,33 +1363,26 @@ tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* d
     if (!src || !dst16) return fail(c, TB_ERR_INVALID, "null pointer");
     // temporary rows + world rows, chunked
     const uint64_t per = 1u << 20;
-    float4* d_rows = nullptr;
-    WorldRow* d_world = nullptr;
-    float* d_in = nullptr;
-    float* d_out = nullptr;
     const uint64_t m0 = std::min<uint64_t>(n, per);
-    TB_CUDA(c, cudaMalloc((void**)&d_rows, m0 * 64));
-    cudaError_t e = cudaMalloc((void**)&d_world, m0 * 64);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_in, m0 * 48);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, m0 * 64);
-    if (e != cudaSuccess) {
-        cudaFree(d_rows); cudaFree(d_world); cudaFree(d_in); cudaFree(d_out);
-        return cuda_fail(c, e, "cudaMalloc(as_matrix4)");
-    }
-    RowView rv = make_row_view(d_rows, m0, false);
-    tb_status s = TB_OK;
-    for (uint64_t off = 0; off < n && s == TB_OK; off += per) {
+    DeviceTemp rows_mem, world_mem, in_mem, out_mem;  // freed on every return path
+    TB_CUDA(c, rows_mem.alloc(m0 * 64));
+    TB_CUDA(c, world_mem.alloc(m0 * 64));
+    TB_CUDA(c, in_mem.alloc(m0 * 48));
+    TB_CUDA(c, out_mem.alloc(m0 * 64));
+    WorldRow* d_world = static_cast<WorldRow*>(world_mem.p);
+    float* d_in = static_cast<float*>(in_mem.p);
+    float* d_out = static_cast<float*>(out_mem.p);
+    const RowView rv = make_row_view(static_cast<float4*>(rows_mem.p), m0, false);
+    for (uint64_t off = 0; off < n; off += per) {
         const uint64_t m = std::min<uint64_t>(per, n - off);
-        cudaMemcpyAsync(d_in, src + off, m * 48, cudaMemcpyHostToDevice, c->stream);
+        TB_CUDA(c, cudaMemcpyAsync(d_in, src + off, m * 48, cudaMemcpyHostToDevice, c->stream));
         TB_LAUNCH(c, "convert_transforms", m * 96, convert_transforms_kernel, div_up(m, kThreads), kThreads, 0, d_in, rv, 0u, (uint32_t)m);
         TB_LAUNCH(c, "compose_world", m * 128, compose_world_kernel, div_up(m, kThreads), kThreads, 0, rv, (const uint64_t*)nullptr, (uint32_t)m, d_world);
         TB_LAUNCH(c, "world_to_mat4", m * 128, world_to_mat4_kernel, div_up(m, kThreads), kThreads, 0, d_world, (const uint64_t*)nullptr, 0u, (uint32_t)m, d_out);
-        cudaMemcpyAsync(dst16 + off * 16, d_out, m * 64, cudaMemcpyDeviceToHost, c->stream);
-        e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) s = cuda_fail(c, e, "tb_as_matrix4");
+        TB_CUDA(c, cudaMemcpyAsync(dst16 + off * 16, d_out, m * 64, cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    cudaFree(d_rows); cudaFree(d_world); cudaFree(d_in); cudaFree(d_out);
-    return s;
+    return TB_OK;
 }
 
 // ---- systems ------------------------------------------------------------------------------------------
@@ -1390,6 +1406,28 @@ tb_status tb_system_integrate(tb_ctx* c, float dt) {
 }
 
 // ---- frame ----------------------------------------------------------------------------------------------
+
+tb_status tb_frame_set_view_projection(tb_ctx* c, const float* m16) {
+    if (!c) return TB_ERR_INVALID;
+    c->has_vp = m16 != nullptr;
+    if (m16) memcpy(c->vp, m16, sizeof(c->vp));
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+// Matrix4::new_orthographic (matrix.rs:41-58), f32, row-major.
+tb_status tb_orthographic(float left, float right, float bottom, float top, float near_, float far_, float* out16) {
+    if (!out16) return TB_ERR_INVALID;
+    for (int k = 0; k < 16; ++k) out16[k] = 0.0f;
+    out16[0] = 2.0f / (right - left);
+    out16[3] = -((right + left) / (right - left));
+    out16[5] = 2.0f / (top - bottom);
+    out16[7] = -((top + bottom) / (top - bottom));
+    out16[10] = -2.0f / (far_ - near_);
+    out16[11] = -((far_ + near_) / (far_ - near_));
+    out16[15] = 1.0f;
+    return TB_OK;
+}
 
 tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
     if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
