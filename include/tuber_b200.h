@@ -141,6 +141,9 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *                           uploaded: the steady-state frame is one kernel, validated every frame (default 1)
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
+ *   "sorted_cache"     0|1  sorted (multi-pass / hierarchy) frames keep the previous frame's sorted arrays; when the
+ *                           key pass finds every entity's sort key unchanged, the sort passes are skipped on the
+ *                           device (default 1)
  *   "cuda_graphs"      0|1  steady-state multi-kernel frames (same plan, same buffers as the frame before)
  *                           replay a captured CUDA graph instead of launching kernel by kernel (default 1)
  *   "z_dictionary"     0|1  scenes with at most 64 distinct depths sort by the rank of z instead of by

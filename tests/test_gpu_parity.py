@@ -945,3 +945,58 @@ def test_camera_view_projection_folded_into_every_emit_path():
             np.testing.assert_array_equal(r.order, ref.frame().order)
         assert not np.array_equal(plain.instances["model"], r.instances["model"])
         ctx.close()
+
+
+# ---- sorted frames keep the previous frame's sort when no key changed ------------------------------------------
+
+@pytest.mark.parametrize("kind", ["flat", "flat64", "hierarchy"])
+def test_sorted_cache_skips_the_sort_only_when_no_key_changed(kind):
+    """x/y velocities move sprites without touching their (layer, texture, z) keys: the sort passes are skipped
+    on the device and the frame still matches; a z change, a sprite upload or a presence change re-sorts"""
+    if kind == "hierarchy":
+        sc = scenes.config3(n=40_000, seed=111)
+        sc.velocities = scenes.config4(n=sc.n, seed=112).velocities
+    else:
+        sc = scenes.config2(n=60_000, seed=113, z_mode="random" if kind == "flat64" else "steps")
+        sc.velocities = scenes.config4(n=sc.n, seed=114).velocities
+    sc.velocities["v"][:, 2] = 0.0
+    masks = {capi.TB_SPRITE: util.random_mask(sc.n, 0.9, 41)}
+    ctx = util.make_ctx(sc, masks)
+    ref = util.make_oracle(sc, masks)
+    ctx.profile_enable(True)  # per-kernel times: skipped sort passes return at once
+    for k in range(5):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        g = util.GpuFrame(ctx)
+        assert g.info.sort_passes >= 2 and g.info.replanned == 0
+        util.assert_frame_parity(g, ref.frame())
+    ctx.profile_enable(False)
+    # a z velocity on a few entities changes their keys: the same frame re-sorts
+    v = sc.velocities.copy()
+    v["v"][100:140, 2] = 50.0
+    ctx.upload_velocities(0, v)
+    ref.close()
+    sc.transforms = ctx.download_transforms(0, sc.n)
+    sc.velocities = v
+    ref = util.make_oracle(sc, masks)
+    for k in range(4):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+    # presence change and sprite change
+    sc.sprites["texture"][::7] = 3
+    ctx.upload_sprites(0, sc.sprites)  # marks every uploaded sprite present ...
+    masks[capi.TB_SPRITE] = util.random_mask(sc.n, 0.8, 42)
+    ctx.upload_presence(capi.TB_SPRITE, 0, masks[capi.TB_SPRITE])  # ... so the mask goes second
+    ref.close()
+    sc.transforms = ctx.download_transforms(0, sc.n)
+    ref = util.make_oracle(sc, masks)
+    for k in range(3):
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
+    # the cache off gives the same bytes
+    c2 = util.make_ctx(sc, masks, sorted_cache=0)
+    g1, g2 = util.GpuFrame(ctx), util.GpuFrame(c2)
+    np.testing.assert_array_equal(g1.order, g2.order)
+    np.testing.assert_array_equal(g1.instances.view(np.uint32), g2.instances.view(np.uint32))
+    c2.close()
+    ctx.close()

@@ -20,6 +20,8 @@ struct PrepParams {
     uint32_t integrate;    // engine ticks of `dt` the velocity system runs in this pass (0: none)
     uint32_t have_plan;    // 0: only masks + count (plan discovery)
     uint32_t write_keys;   // short keys to keys_out (multi-pass plans)
+    uint32_t check_keys;   // keys_out still holds the previous frame's keys: compare before overwriting
+                           // (stats[5] != 0 afterwards <=> some key changed <=> the cached sort is stale)
     uint32_t lt_mode;      // 0: none (aliases digit pass 0), 1: shared-memory bins, 2: global bins
     void* keys_out;
     uint32_t* hist;        // [kMaxPasses][256]
@@ -50,6 +52,7 @@ struct PrepAcc {
     unsigned long long k_or = 0ull, k_and = ~0ull;
     uint32_t count = 0;
     bool miss = false;  // a depth that the plan's z dictionary does not hold
+    bool changed = false;  // an entity whose short key differs from the previous frame's
 };
 
 // Plan discovery: remember this depth (warp-aggregated insert into a small open-addressing set).
@@ -78,7 +81,8 @@ __device__ __forceinline__ void zset_insert(unsigned long long* zset, uint32_t* 
 //     distinct digit per warp - no block barrier anywhere in the key pass;
 //   small == false: plain shared atomics (many distinct digits, little contention), per-tile counts
 //     through `tcnt` in shared memory when the caller wants them.
-__device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, PrepAcc& acc, bool renderable,
+// `inb`: i is a real entity of this shard (out-of-range lanes take part in the warp collectives only).
+__device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, PrepAcc& acc, bool inb, bool renderable,
                                              uint64_t key, uint32_t i, bool small, uint32_t emit_tile, uint32_t* tcnt) {
     if (renderable) {
         acc.k_or |= key;
@@ -105,6 +109,21 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
         }
         return;
     }
+    if (p.write_keys && inb) {
+        // every entity gets a key slot (all ones: not renderable), so that next frame's pass can tell
+        // whether anything moved in the draw order by comparing slot by slot
+        if (p.plan.key64) {
+            uint64_t* slot = reinterpret_cast<uint64_t*>(p.keys_out) + i;
+            const uint64_t v = renderable ? sk : ~0ull;
+            if (p.check_keys && *slot != v) acc.changed = true;
+            *slot = v;
+        } else {
+            uint32_t* slot = reinterpret_cast<uint32_t*>(p.keys_out) + i;
+            const uint32_t v = renderable ? (uint32_t)sk : 0xFFFFFFFFu;
+            if (p.check_keys && *slot != v) acc.changed = true;
+            *slot = v;
+        }
+    }
     if (!renderable) return;
     if (p.key_hist != nullptr) atomicAdd(&p.key_hist[(uint32_t)sk], 1u);
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
@@ -114,10 +133,6 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
     }
     if (p.lt_mode == 1) atomicAdd(&sh.lt[(uint32_t)(sk >> p.plan.zbits)], 1u);
     else if (p.lt_mode == 2) atomicAdd(&p.lt_hist[(uint32_t)(sk >> p.plan.zbits)], 1u);
-    if (p.write_keys) {
-        if (p.plan.key64) reinterpret_cast<uint64_t*>(p.keys_out)[i] = sk;
-        else reinterpret_cast<uint32_t*>(p.keys_out)[i] = (uint32_t)sk;
-    }
 }
 
 // The single-pass few-bucket plan the `small` accounting path serves.
@@ -151,6 +166,7 @@ __device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh, 
             atomicAdd(&sh.count, cnt);
         }
         if (__any_sync(0xffffffffu, acc.miss) && (threadIdx.x & 31) == 0) atomicOr(&p.stats[4], 1ull);
+        if (__any_sync(0xffffffffu, acc.changed) && (threadIdx.x & 31) == 0) atomicOr(&p.stats[5], 1ull);
     }
     __syncthreads();
     if (p.have_plan) {
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             if (rend[k]) key = flat_key(p.rows, i, a0[k], a1[k]);
             // this 1024-entity tile is two 512-entity emit tiles (shared-memory counts) or
             // sixteen 64-entity warp tiles (direct global counts of the small path)
-            prep_account(p, sh, acc, rend[k], key, i, small, i >> p.emit_tile_shift,
+            prep_account(p, sh, acc, i < p.n, rend[k], key, i, small, i >> p.emit_tile_shift,
                          tiles_out ? sh.tcnt[par][wide_tiles ? 0 : (k >> 1)] : nullptr);
         }
         if (tiles_out) {
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
             rend = mask_bit(p.mask_s, e);
             if (rend) key = world_key(wr.r2, wr.s);
         }
-        prep_account(p, sh, acc, rend, key, e, false, 0u, nullptr);
+        prep_account(p, sh, acc, inb, rend, key, e, false, 0u, nullptr);
     }
     prep_flush(p, sh, acc);
 }

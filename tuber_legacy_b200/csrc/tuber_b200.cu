@@ -46,7 +46,7 @@ struct FrameSig {
     uint64_t n = 0, max_batches = 0, global_first = 0, level_epoch = 0;
     const void* ptr[24] = {};
     FramePlan plan{};
-    uint32_t flags[12] = {};
+    uint32_t flags[13] = {};
     uint32_t vp_bits[17] = {};  // has_vp, then the 16 matrix entries
     bool operator==(const FrameSig& o) const {
         return memcmp(vp_bits, o.vp_bits, sizeof(vp_bits)) == 0 && n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
@@ -89,6 +89,7 @@ struct tb_ctx {
     uint32_t* scratch = nullptr;
     size_t scratch_words = 0;
     void* keys[2] = {nullptr, nullptr};
+    void* ekeys = nullptr;  // short keys in entity order (what the key pass writes; kept from frame to frame)
     uint32_t* idx[2] = {nullptr, nullptr};
     size_t sort_cap = 0, sort_keybytes = 0;
     uint32_t* texlayer = nullptr;
@@ -120,6 +121,10 @@ struct tb_ctx {
     bool plan_valid = false;
     // single-kernel steady-state frames: per-tile bucket offsets cached from the last full frame
     bool static_valid = false;
+    // sorted frames: the previous frame's sorted (key, id) arrays and tile offsets are still in place; a frame
+    // whose key pass finds every entity's key unchanged skips its sort passes (decided on the device)
+    bool sorted_valid = false;
+    int sorted_cache = 1;
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
     size_t static_offs_off = 0;
@@ -192,7 +197,8 @@ constexpr size_t kHdrFrame = 4;
 constexpr size_t kHdrStats = 4;        // 3 x u64: OR(key), OR(~key), renderable count
 constexpr size_t kHdrNumBatches = 10;  // u32
 constexpr size_t kHdrZMiss = 12;       // u64 (stats[4]): a depth outside the plan's z dictionary was seen
-constexpr size_t kHdrReadWords = 10;   // what a frame copies back: stats + batch count + dictionary misses
+constexpr size_t kHdrKeysChanged = 14;  // u64 (stats[5]): an entity's short key differs from the previous frame's
+constexpr size_t kHdrReadWords = 12;   // what a frame copies back: stats, batch count, dictionary misses, key changes
 constexpr size_t kHdrHist = 16;        // kMaxPasses * 256 u32: raw digit histograms
 constexpr size_t kHdrWords = kHdrHist + kMaxPasses * 256;  // then (layer,texture) bins, tile tables
 
@@ -404,7 +410,7 @@ tb_status ensure_scratch(tb_ctx* c, size_t words) {
     }
     c->scratch = (uint32_t*)q;
     c->scratch_words = want;
-    c->static_valid = false;  // cached tile offsets lived in the old buffer
+    c->static_valid = c->sorted_valid = false;  // cached tile offsets lived in the old buffer
     return TB_OK;
 }
 
@@ -443,7 +449,14 @@ tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
         c->keys[k] = nullptr;
         c->idx[k] = nullptr;
     }
+    if (c->ekeys) cudaFree(c->ekeys);
+    c->ekeys = nullptr;
     c->sort_cap = 0;
+    c->sorted_valid = false;
+    {
+        cudaError_t e = cudaMalloc(&c->ekeys, (size_t)n * keybytes + 16);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(entity keys)");
+    }
     for (int k = 0; k < 2; ++k) {
         // +16 bytes: the emit kernel prefetches keys in 16-byte chunks
         cudaError_t e = cudaMalloc(&c->keys[k], (size_t)n * keybytes + 16);
@@ -485,6 +498,7 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     split_digits(nbits, kMaxDigitBits, &ds);
     tb_status s = ensure_sort_buffers(c, n, 4);
     if (s) return s;
+    c->sorted_valid = false;  // this sort reuses the frame's ping-pong buffers and scratch
     const uint32_t tile = kScatterTile;
     const uint32_t tiles = div_up(n, tile);
     size_t words = kHdrWords;
@@ -508,16 +522,18 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     for (uint32_t p = 0; p < ds.npasses; ++p) {
         uint32_t* counts = c->scratch + counts_off[p];
         uint32_t* offs = c->scratch + offs_off[p];
-        TB_LAUNCH(c, "tile_hist", 0, tile_hist_kernel<uint32_t>, tiles, kThreads, 0, kin, n, (const unsigned long long*)nullptr,
-                  (const uint64_t*)nullptr, (const uint64_t*)nullptr, 0u, tile, ds.shift[p], ds.bits[p], tiles, counts);
+        TB_LAUNCH(c, "tile_hist", 0, tile_hist_kernel<uint32_t>, std::min<uint32_t>(tiles, 16u * (uint32_t)c->sm_count), kThreads, 0, kin, n,
+                  (const unsigned long long*)nullptr,
+                  (const uint64_t*)nullptr, (const uint64_t*)nullptr, 0u, tile, ds.shift[p], ds.bits[p], tiles, counts,
+                  (const unsigned long long*)nullptr);
         {
             const uint32_t nchunks = div_up(tiles, 1024);
             uint32_t* csum = c->scratch + csum_off[p];
             if (nchunks > 1)
                 TB_LAUNCH(c, "tile_chunk_sums", 0, tile_chunk_sums_kernel, dim3(nchunks, 1u << ds.bits[p]), 1024, 0, counts, tiles,
-                          nchunks, csum);
+                          nchunks, csum, (const unsigned long long*)nullptr);
             TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(nchunks, 1u << ds.bits[p]), 1024, 0, counts, tiles, hist + p * 256,
-                      (const uint32_t*)csum, nchunks, offs);
+                      (const uint32_t*)csum, nchunks, offs, (const unsigned long long*)nullptr);
         }
         ScatterParams<uint32_t> sp{};
         sp.pass.n = n;
@@ -665,7 +681,7 @@ tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     }
     c->rows = dst;
     c->interleaved = interleaved ? 1 : 0;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     return TB_OK;
 }
 
@@ -689,7 +705,7 @@ void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and, const uint32_t* zva
         }
     }
     c->plan_valid = true;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
 }
 
 struct FrameMode {
@@ -722,7 +738,8 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     if (have_plan) {
         p.plan = c->plan;
         p.write_keys = c->plan.npasses > 1 || fm.hier;
-        p.keys_out = c->keys[0];
+        p.keys_out = c->ekeys;
+        p.check_keys = (c->sorted_valid && p.write_keys) ? 1u : 0u;
         p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
         p.lt_hist = c->scratch + L->lt_off;
         if (!fm.hier) {
@@ -784,7 +801,11 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     uint32_t* hist = c->scratch + kHdrHist;
     const unsigned long long* d_count = reinterpret_cast<const unsigned long long*>(c->scratch + kHdrStats) + 2;
     const bool have_keys = plan.npasses > 1 || fm.hier;  // pass A wrote short keys (entity order)
-    const KeyT* kin = have_keys ? (const KeyT*)c->keys[0] : nullptr;
+    const KeyT* kin = have_keys ? (const KeyT*)c->ekeys : nullptr;
+    // the previous frame's sort is still in place: the sort-pass kernels return at once when the key pass found
+    // no changed key (stats[5] == 0)
+    const unsigned long long* skip =
+        c->sorted_valid ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrKeysChanged) : nullptr;
     const uint32_t* iin = nullptr;
     const uint64_t kb = sizeof(KeyT);
     int cur = 1;
@@ -801,16 +822,17 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             uint32_t* counts = c->scratch + L.counts_off[p];
             uint32_t* offs = c->scratch + L.offs_off[p];
             if (!(p == 0 && prepare_made_counts))
-                TB_LAUNCH(c, "tile_hist", (uint64_t)n * kb, tile_hist_kernel<KeyT>, L.tiles[p], kThreads, 0, kin, n, pp.count_ptr,
+                TB_LAUNCH(c, "tile_hist", (uint64_t)n * kb, tile_hist_kernel<KeyT>,
+                          std::min<uint32_t>(L.tiles[p], 16u * (uint32_t)c->sm_count), kThreads, 0, kin, n, pp.count_ptr,
                           mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_SPRITE), iin ? 0u : 1u, tile, pp.shift, pp.bits,
-                          L.tiles[p], counts);
+                          L.tiles[p], counts, skip);
             const uint32_t nchunks = div_up(L.tiles[p], 1024);
             uint32_t* csum = c->scratch + L.csum_off[p];
             if (nchunks > 1)
                 TB_LAUNCH(c, "tile_chunk_sums", 0, tile_chunk_sums_kernel, dim3(nchunks, 1u << pp.bits), 1024, 0, counts, L.tiles[p],
-                          nchunks, csum);
+                          nchunks, csum, skip);
             TB_LAUNCH(c, "tile_scan", 0, tile_scan_kernel, dim3(nchunks, 1u << pp.bits), 1024, 0, counts, L.tiles[p], hist + p * 256,
-                      (const uint32_t*)csum, nchunks, offs);
+                      (const uint32_t*)csum, nchunks, offs, skip);
             pp.tile_off = offs;
         }
         if (!last) {
@@ -822,6 +844,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
             sp.mask_s = mask_or_null(c, TB_SPRITE);
             sp.keys_out = (KeyT*)c->keys[cur];
             sp.idx_out = c->idx[cur];
+            sp.skip = skip;
             TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (kb + (iin ? 4 : 0) + kb + 4), radix_scatter_kernel<KeyT>,
                       std::min<uint32_t>(L.tiles[p], 3u * (uint32_t)c->sm_count), kThreads, sizeof(ScatterShared<KeyT>), sp);
             kin = (const KeyT*)c->keys[cur];
@@ -888,7 +911,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     g.level_epoch = c->level_epoch;
     const void* ptrs[] = {c->rows.t, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
                           c->mask[0], c->mask[1], c->mask[2], c->mask[3], c->batches, c->texlayer, c->level_list,
-                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr};
+                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr, c->ekeys};
     static_assert(sizeof(ptrs) <= sizeof(g.ptr), "FrameSig::ptr too small");
     memcpy(g.ptr, ptrs, sizeof(ptrs));
     g.plan = c->plan;
@@ -898,7 +921,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     const uint32_t flags[] = {integrate ? c->pending_ticks : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
                               fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
                               c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
-                              (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0)};
+                              (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0), c->sorted_valid ? 1u : 0u};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
     g.vp_bits[0] = c->has_vp ? 1u : 0u;
@@ -1052,6 +1075,7 @@ void tb_ctx_destroy(tb_ctx* c) {
         cudaFree(c->keys[k]);
         cudaFree(c->idx[k]);
     }
+    cudaFree(c->ekeys);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1105,27 +1129,30 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->staged_emit = value != 0;
     } else if (k == "static_buckets") {
         c->static_buckets = value != 0;
-        c->static_valid = false;
+        c->static_valid = c->sorted_valid = false;
     } else if (k == "small_emit") {
-        c->static_valid = false;
+        c->static_valid = c->sorted_valid = false;
         c->small_emit = value != 0;
     } else if (k == "digit_bits") {
         if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
         c->digit_bits = (int)value;
         c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
+    } else if (k == "sorted_cache") {
+        c->sorted_cache = value != 0;
+        c->sorted_valid = false;
     } else if (k == "cuda_graphs") {
         c->use_graphs = value != 0;
         c->frame_graph_valid = false;
     } else if (k == "z_dictionary") {
         c->z_dictionary = value != 0;
         c->plan_valid = false;
-        c->static_valid = false;
+        c->static_valid = c->sorted_valid = false;
     } else if (k == "lt_limit") {
         if (value < 0 || value > (int64_t)kMaxLtBits) return fail(c, TB_ERR_INVALID, "lt_limit must be 0..16");
         c->lt_limit = (int)value;
         c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     } else {
         return fail(c, TB_ERR_INVALID, "unknown option " + k);
     }
@@ -1159,7 +1186,7 @@ tb_status tb_set_entity_count(tb_ctx* c, uint64_t n) {
     }
     c->n = n;
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1202,7 +1229,7 @@ tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_t
     c->store[TB_TRANSFORM] = true;
     mark_presence(c, TB_TRANSFORM, first, n, 1);
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1224,7 +1251,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     c->store[TB_SPRITE] = true;
     mark_presence(c, TB_SPRITE, first, n, 1);
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
@@ -1270,7 +1297,7 @@ tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_
     }
     c->levels_dirty = true;
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -1286,7 +1313,7 @@ tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t 
     TB_CUDA(c, cudaMemcpyAsync(c->mask[comp] + first_word, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
     c->store[comp] = true;
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1433,7 +1460,7 @@ tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
     if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
     c->force_path = path;
     c->plan_valid = false;
-    c->static_valid = false;
+    c->static_valid = c->sorted_valid = false;
     return TB_OK;
 }
 
@@ -1477,7 +1504,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             count = c->static_count;
             num_batches = c->static_batches;
         } else {
-            c->static_valid = false;  // e.g. a velocity moved z: fall back to the full frame below
+            c->static_valid = c->sorted_valid = false;  // e.g. a velocity moved z: fall back to the full frame below
             replanned = 1;
         }
     }
@@ -1607,6 +1634,11 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             c->static_offs_off = L.offs_off[0];
             c->static_tiles = L.tiles[0];
         }
+        // sorted frames: this frame's sorted (key, id) arrays, tile offsets and entity-order keys stay where
+        // they are; the next frame's key pass compares every key with them and its sort passes only run
+        // if one changed (a u32 short key of all ones would collide with the "not renderable" mark)
+        if (c->sorted_cache && (plan.npasses > 1 || fm.hier) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32))
+            c->sorted_valid = true;
         break;
     }
     cudaError_t e = cudaGetLastError();
@@ -1640,6 +1672,7 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
     stats[2] = 0;
     c->shard_state = 0;
     c->frame_valid = false;
+    c->sorted_valid = false;  // the multi-GPU protocol re-plans every frame from the global statistics
     tb_status s;
     c->shard_count = 0;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
@@ -1681,7 +1714,7 @@ tb_status tb_shard_plan(tb_ctx* c, const uint64_t g[3], uint64_t* nbins) {
     }
     build_frame_plan(g[0], ~g[1], &c->plan);
     c->plan_valid = false;
-    c->static_valid = false;  // a later single-GPU frame re-plans for itself
+    c->static_valid = c->sorted_valid = false;  // a later single-GPU frame re-plans for itself
     if (c->plan.pext.nbits > TB_SHARD_MAX_KEY_BITS)
         return fail(c, TB_ERR_UNSUPPORTED, "sort key too wide for histogram placement across GPUs");
     if ((int)c->plan.ltbits > (int)kMaxLtBits) return fail(c, TB_ERR_UNSUPPORTED, "too many (layer, texture) bins");
