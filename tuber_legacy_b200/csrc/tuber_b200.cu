@@ -46,7 +46,7 @@ struct FrameSig {
     uint64_t n = 0, max_batches = 0, global_first = 0, level_epoch = 0;
     const void* ptr[24] = {};
     FramePlan plan{};
-    uint32_t flags[13] = {};
+    uint32_t flags[14] = {};
     uint32_t vp_bits[17] = {};  // has_vp, then the 16 matrix entries
     bool operator==(const FrameSig& o) const {
         return memcmp(vp_bits, o.vp_bits, sizeof(vp_bits)) == 0 && n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
@@ -125,6 +125,11 @@ struct tb_ctx {
     // whose key pass finds every entity's key unchanged skips its sort passes (decided on the device)
     bool sorted_valid = false;
     int sorted_cache = 1;
+    // ... and the draw order itself (a copy of the last re-sorted frame's `order` output): frames that keep
+    // the sort emit straight from it (emit_ordered_kernel)
+    uint32_t* final_idx = nullptr;
+    size_t final_cap = 0;
+    bool final_valid = false;
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
     size_t static_offs_off = 0;
@@ -872,8 +877,25 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0)), (emit_small_kernel<KeyT, false>),
                           std::min<uint32_t>(div_up(L.tiles[p], kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
             } else {
+                // a frame that keeps the previous frame's sort also keeps its draw order: exactly one of the two
+                // emit kernels does the work, chosen on the device by the key pass's "changed" flag
+                const bool ordered = skip != nullptr && c->final_valid && !fm.lt_generic;
+                if (ordered) {
+                    ep.changed = skip;
+                    ep.run_when = 1u;
+                }
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
                           std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared<KeyT>), ep);
+                if (ordered) {
+                    EmitParams<KeyT> eo = ep;
+                    eo.run_when = 2u;
+                    eo.keys_in = nullptr;
+                    eo.idx_in = c->final_idx;
+                    eo.pass.n = n;
+                    eo.pass.count_ptr = d_count;
+                    TB_LAUNCH(c, "emit_ordered", (uint64_t)n * (64 + 80 + 64 + 4 + 4), emit_ordered_kernel<KeyT>,
+                              2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), eo);
+                }
             }
         }
     }
@@ -911,7 +933,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     g.level_epoch = c->level_epoch;
     const void* ptrs[] = {c->rows.t, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
                           c->mask[0], c->mask[1], c->mask[2], c->mask[3], c->batches, c->texlayer, c->level_list,
-                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr, c->ekeys};
+                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr, c->ekeys, c->final_idx};
     static_assert(sizeof(ptrs) <= sizeof(g.ptr), "FrameSig::ptr too small");
     memcpy(g.ptr, ptrs, sizeof(ptrs));
     g.plan = c->plan;
@@ -921,7 +943,8 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     const uint32_t flags[] = {integrate ? c->pending_ticks : 0u, integrate ? dt_bits : 0u, fm.hier ? 1u : 0u, fm.lt_alias ? 1u : 0u,
                               fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
                               c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
-                              (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0), c->sorted_valid ? 1u : 0u};
+                              (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0), c->sorted_valid ? 1u : 0u,
+                              (c->sorted_valid && c->final_valid) ? 1u : 0u};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
     g.vp_bits[0] = c->has_vp ? 1u : 0u;
@@ -1049,6 +1072,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint64_t>));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
@@ -1076,6 +1101,7 @@ void tb_ctx_destroy(tb_ctx* c) {
         cudaFree(c->idx[k]);
     }
     cudaFree(c->ekeys);
+    cudaFree(c->final_idx);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1556,6 +1582,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         }
         // Steady state (cached plan, nothing changed since the last frame): replay the captured graph.
         // A frame whose launches would differ in any parameter has a different signature.
+        const bool armed_at_start = c->sorted_valid;
         const bool graphable = c->use_graphs && cached_plan && !c->prof && !fm.lt_generic;
         FrameSig sig;
         if (graphable) frame_signature(c, fm, integrate, d_inst, d_vtx, d_order, &sig);
@@ -1637,8 +1664,23 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         // sorted frames: this frame's sorted (key, id) arrays, tile offsets and entity-order keys stay where
         // they are; the next frame's key pass compares every key with them and its sort passes only run
         // if one changed (a u32 short key of all ones would collide with the "not renderable" mark)
-        if (c->sorted_cache && (plan.npasses > 1 || fm.hier) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32))
+        if (c->sorted_cache && (plan.npasses > 1 || fm.hier) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32)) {
+            const bool resorted = !armed_at_start || c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] != 0;
             c->sorted_valid = true;
+            if (!armed_at_start) c->final_valid = false;
+            if (resorted && count > 0) {
+                // keep this frame's draw order for the frames that will not need to sort
+                size_t cap = c->final_idx ? c->final_cap : 0;
+                if (grow(c, &c->final_idx, &cap, (size_t)n + 4, 4) == TB_OK) {
+                    c->final_cap = cap;
+                    c->final_valid = cudaMemcpyAsync(c->final_idx, d_order, count * 4, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+                } else {
+                    c->final_cap = 0;
+                    c->final_valid = false;
+                    cudaGetLastError();
+                }
+            }
+        }
         break;
     }
     cudaError_t e = cudaGetLastError();
