@@ -85,3 +85,12 @@ if __name__ == "__main__":
         run("configs[3] 16M particles, interleaved rows", scenes.config4(), 232, integrate=True, interleaved_rows=1)
     if "3i" in which:
         run("configs[2] 4M hierarchy depth 8, interleaved rows", scenes.config3(), 212, interleaved_rows=1)
+    if "2c" in which:
+        run("configs[1] 1M flat, z in {0..15}, keys treated as changed every frame", scenes.config2(), 208, sorted_cache=0)
+    if "3c" in which:
+        run("configs[2] 4M hierarchy depth 8, keys treated as changed every frame", scenes.config3(), 212, sorted_cache=0)
+    if "16c" in which:
+        run("16M flat, 64 textures x 16 layers, z in {0..15}, keys treated as changed every frame", scenes.config2(n=1 << 24), 208,
+            sorted_cache=0)
+    if "5c" in which:
+        run("configs[4] 64M flat on one GPU, keys treated as changed every frame", scenes.config5(), 208, sorted_cache=0)
