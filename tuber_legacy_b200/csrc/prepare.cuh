@@ -81,9 +81,32 @@ __device__ __forceinline__ void zset_insert(unsigned long long* zset, uint32_t* 
 //     distinct digit per warp - no block barrier anywhere in the key pass;
 //   small == false: plain shared atomics (many distinct digits, little contention), per-tile counts
 //     through `tcnt` in shared memory when the caller wants them.
+// Every entity gets a key slot in entity order (all ones: not renderable), so that the next frame's pass can
+// tell whether anything moved in the draw order by comparing slot by slot before it overwrites them.
+// `old32`: the slot's previous 32-bit value when the caller fetched it ahead of time (32-bit keys, key check on).
+__device__ __forceinline__ void store_key(const PrepParams& p, PrepAcc& acc, uint32_t i, uint64_t v, bool have_old, uint32_t old32) {
+    if (p.plan.key64) {
+        uint64_t* slot = reinterpret_cast<uint64_t*>(p.keys_out) + i;
+        if (p.check_keys && *slot != v) acc.changed = true;
+        *slot = v;
+    } else {
+        uint32_t* slot = reinterpret_cast<uint32_t*>(p.keys_out) + i;
+        if (p.check_keys && (have_old ? old32 : *slot) != (uint32_t)v) acc.changed = true;
+        *slot = (uint32_t)v;
+    }
+}
+// The previous frame's 32-bit key of entity i, read through the non-coherent path: only this thread ever touches
+// the slot in this kernel and it reads before it writes, so the load may be issued long before the compare.
+__device__ __forceinline__ bool fetch_old_key(const PrepParams& p, bool inb, uint32_t i, uint32_t* old32) {
+    if (!(p.check_keys && p.write_keys && !p.plan.key64 && inb)) return false;
+    *old32 = __ldg(reinterpret_cast<const uint32_t*>(p.keys_out) + i);
+    return true;
+}
+
 // `inb`: i is a real entity of this shard (out-of-range lanes take part in the warp collectives only).
 __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh, PrepAcc& acc, bool inb, bool renderable,
-                                             uint64_t key, uint32_t i, bool small, uint32_t emit_tile, uint32_t* tcnt) {
+                                             uint64_t key, uint32_t i, bool small, uint32_t emit_tile, uint32_t* tcnt,
+                                             bool have_old = false, uint32_t old32 = 0u) {
     if (renderable) {
         acc.k_or |= key;
         acc.k_and &= key;
@@ -109,22 +132,10 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
         }
         return;
     }
-    if (p.write_keys && inb) {
-        // every entity gets a key slot (all ones: not renderable), so that next frame's pass can tell
-        // whether anything moved in the draw order by comparing slot by slot
-        if (p.plan.key64) {
-            uint64_t* slot = reinterpret_cast<uint64_t*>(p.keys_out) + i;
-            const uint64_t v = renderable ? sk : ~0ull;
-            if (p.check_keys && *slot != v) acc.changed = true;
-            *slot = v;
-        } else {
-            uint32_t* slot = reinterpret_cast<uint32_t*>(p.keys_out) + i;
-            const uint32_t v = renderable ? (uint32_t)sk : 0xFFFFFFFFu;
-            if (p.check_keys && *slot != v) acc.changed = true;
-            *slot = v;
-        }
+    if (!renderable) {
+        if (p.write_keys && inb) store_key(p, acc, i, ~0ull, have_old, old32);  // all ones: not renderable
+        return;
     }
-    if (!renderable) return;
     if (p.key_hist != nullptr) atomicAdd(&p.key_hist[(uint32_t)sk], 1u);
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
         const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
@@ -133,6 +144,7 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
     }
     if (p.lt_mode == 1) atomicAdd(&sh.lt[(uint32_t)(sk >> p.plan.zbits)], 1u);
     else if (p.lt_mode == 2) atomicAdd(&p.lt_hist[(uint32_t)(sk >> p.plan.zbits)], 1u);
+    if (p.write_keys) store_key(p, acc, i, sk, have_old, old32);
 }
 
 // The single-pass few-bucket plan the `small` accounting path serves.
@@ -248,6 +260,13 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
                 p.rows.t[(size_t)i * p.rows.st] = a0[k];
             }
         }
+        uint32_t old32[kPrepItems];
+        bool have_old[kPrepItems];
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {
+            old32[k] = 0u;
+            have_old[k] = fetch_old_key(p, base + k * kThreads < p.n, base + k * kThreads, &old32[k]);
+        }
         if (tiles_out) __syncthreads();
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
@@ -257,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
             // this 1024-entity tile is two 512-entity emit tiles (shared-memory counts) or
             // sixteen 64-entity warp tiles (direct global counts of the small path)
             prep_account(p, sh, acc, i < p.n, rend[k], key, i, small, i >> p.emit_tile_shift,
-                         tiles_out ? sh.tcnt[par][wide_tiles ? 0 : (k >> 1)] : nullptr);
+                         tiles_out ? sh.tcnt[par][wide_tiles ? 0 : (k >> 1)] : nullptr, have_old[k], old32[k]);
         }
         if (tiles_out) {
             __syncthreads();
