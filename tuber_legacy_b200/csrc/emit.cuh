@@ -48,6 +48,10 @@ struct EmitParams {
     // frame), 2: only if it is clear (emit_ordered_kernel over the cached draw order), 0: always.
     const unsigned long long* changed;
     uint32_t run_when;
+    // the ranking emit of a (re)sorted frame also leaves the draw order and its short keys for the frames
+    // that will keep them: final_idx[pos] = entity id (global), final_keys[pos] = short key
+    uint32_t* final_idx;
+    KeyT* final_keys;
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -389,6 +393,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 }
                 make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = e + ep.global_first;
+                if (ep.final_idx != nullptr) {
+                    ep.final_idx[dst] = e + ep.global_first;
+                    ep.final_keys[dst] = sm.keys[ring][li];
+                }
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }
             if (!ep.staged) {
@@ -702,10 +710,21 @@ struct OrderedShared {
     OrderedWarpShared w[kWarps];
 };
 
-template <typename KeyT>
+//
+// VALIDATE: the whole steady-state frame of a flat sorted scene in this one kernel (no key pass at all). Every
+// gathered row's key is recomputed and compared with the kept short key of its position (keys_in); the key
+// statistics, dictionary misses and a "changed" flag go to `stats`, with which the host confirms after the
+// frame that the kept plan, sort and draw order still hold — or redoes the frame the long way.
+template <typename KeyT, bool VALIDATE>
 __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
     if (ep.run_when == 2u && *reinterpret_cast<const volatile unsigned long long*>(ep.changed) != 0ull) return;
+    __shared__ uint32_t s_zdict[VALIDATE ? kMaxZDict : 1];
+    if (VALIDATE) {
+        for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) s_zdict[k] = ep.plan.zdict[k];
+        __syncthreads();  // the only block barrier, before the warps go their own ways
+    }
+    PrepAcc acc;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     OrderedWarpShared& sm = reinterpret_cast<OrderedShared*>(emit_smem_raw)->w[warp];
     const bool from_world = ep.world != nullptr;
@@ -777,6 +796,12 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
         __syncwarp();  // every lane's gathers of this tile have landed
         const float4* rows = sm.rows[cur];
         const uint32_t base = tile * kWarpTile, cnt = tile_cnt(tile);
+        KeyT kept[2] = {(KeyT)0, (KeyT)0};
+        if (VALIDATE) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if ((uint32_t)k * 32u + lane < cnt) kept[k] = __ldg(ep.keys_in + base + k * 32 + lane);
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t li = k * 32 + lane;
@@ -806,6 +831,16 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
                     sw = r.b1.y;
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
+                    if (VALIDATE) {
+                        const float z = is_planar(r.a1) ? planar_z(r.a0, r.a1) : local_z(r);
+                        const uint64_t key = sort_key(tl >> 16, tl & 0xFFFFu, z);
+                        acc.k_or |= key;
+                        acc.k_and &= key;
+                        acc.count += 1;
+                        bool miss = false;
+                        if ((KeyT)plan_short_key(ep.plan, s_zdict, key, &miss) != kept[k]) acc.changed = true;
+                        if (miss) acc.miss = true;
+                    }
                 }
                 make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = sm.idx[ring][li];
@@ -818,6 +853,20 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
         ring = ring1;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    if (VALIDATE) {
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc.k_or);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc.k_or >> 32));
+        const uint32_t nlo = __reduce_or_sync(0xffffffffu, ~(uint32_t)acc.k_and);
+        const uint32_t nhi = __reduce_or_sync(0xffffffffu, ~(uint32_t)(acc.k_and >> 32));
+        const uint32_t c = __reduce_add_sync(0xffffffffu, acc.count);
+        if (lane == 0 && c) {
+            atomicOr(&ep.stats[0], ((unsigned long long)hi << 32) | lo);
+            atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
+            atomicAdd(&ep.stats[2], (unsigned long long)c);
+        }
+        if (__any_sync(0xffffffffu, acc.miss) && lane == 0) atomicOr(&ep.stats[4], 1ull);
+        if (__any_sync(0xffffffffu, acc.changed) && lane == 0) atomicOr(&ep.stats[5], 1ull);
+    }
 }
 
 // ---- quad vertices from instances ------------------------------------------------------------------

@@ -127,9 +127,10 @@ struct tb_ctx {
     int sorted_cache = 1;
     // ... and the draw order itself (a copy of the last re-sorted frame's `order` output): frames that keep
     // the sort emit straight from it (emit_ordered_kernel)
-    uint32_t* final_idx = nullptr;
-    size_t final_cap = 0;
+    uint32_t* final_idx = nullptr;   // [n] entity id (global) per draw position
+    void* final_keys = nullptr;      // [n] short key per draw position
     bool final_valid = false;
+    uint64_t sorted_count = 0, sorted_batches = 0;
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
     size_t static_offs_off = 0;
@@ -455,12 +456,17 @@ tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
         c->idx[k] = nullptr;
     }
     if (c->ekeys) cudaFree(c->ekeys);
-    c->ekeys = nullptr;
+    if (c->final_idx) cudaFree(c->final_idx);
+    if (c->final_keys) cudaFree(c->final_keys);
+    c->ekeys = c->final_keys = nullptr;
+    c->final_idx = nullptr;
     c->sort_cap = 0;
-    c->sorted_valid = false;
+    c->sorted_valid = c->final_valid = false;
     {
         cudaError_t e = cudaMalloc(&c->ekeys, (size_t)n * keybytes + 16);
-        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(entity keys)");
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c->final_idx, (size_t)n * 4 + 16);
+        if (e == cudaSuccess) e = cudaMalloc(&c->final_keys, (size_t)n * keybytes + 16);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(entity keys / draw order)");
     }
     for (int k = 0; k < 2; ++k) {
         // +16 bytes: the emit kernel prefetches keys in 16-byte chunks
@@ -884,6 +890,10 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                     ep.changed = skip;
                     ep.run_when = 1u;
                 }
+                if (c->sorted_cache && iin != nullptr && !fm.lt_generic && c->shard_state != 4) {
+                    ep.final_idx = c->final_idx;  // whenever this kernel ranks, it leaves the draw order behind
+                    ep.final_keys = (KeyT*)c->final_keys;
+                }
                 TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (kin ? kb : 0) + (iin ? 4 : 0)), emit_kernel<KeyT>,
                           std::min<uint32_t>(L.tiles[p], 2u * (uint32_t)c->sm_count), kThreads, sizeof(EmitShared<KeyT>), ep);
                 if (ordered) {
@@ -891,9 +901,11 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                     eo.run_when = 2u;
                     eo.keys_in = nullptr;
                     eo.idx_in = c->final_idx;
+                    eo.final_idx = nullptr;
+                    eo.final_keys = nullptr;
                     eo.pass.n = n;
                     eo.pass.count_ptr = d_count;
-                    TB_LAUNCH(c, "emit_ordered", (uint64_t)n * (64 + 80 + 64 + 4 + 4), emit_ordered_kernel<KeyT>,
+                    TB_LAUNCH(c, "emit_ordered", (uint64_t)n * (64 + 80 + 64 + 4 + 4), (emit_ordered_kernel<KeyT, false>),
                               2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), eo);
                 }
             }
@@ -951,6 +963,41 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     if (c->has_vp) memcpy(g.vp_bits + 1, c->vp, sizeof(c->vp));
 }
 
+
+// The steady-state frame of a flat SORTED scene whose previous sort and draw order are still in place: the
+// velocity system as its own streaming pass (when a tick is pending), then one kernel that gathers, composes
+// and writes in the kept draw order while recomputing every key and comparing it with the kept one. *ok tells
+// whether the frame's own statistics confirm the kept plan, keys and order; if not the caller redoes the
+// frame the long way (the velocity system has run exactly once either way).
+template <typename KeyT>
+tb_status sorted_fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+    *ok = false;
+    const FramePlan& plan = c->plan;
+    if (integrate && c->store[TB_VELOCITY] && c->store[TB_TRANSFORM])
+        TB_LAUNCH(c, "integrate", c->n * 44ull, integrate_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows,
+                  mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, c->pending_ticks, (uint32_t)c->n);
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
+    EmitParams<KeyT> ep{};
+    ep.pass.n = (uint32_t)c->sorted_count;
+    ep.idx_in = c->final_idx;
+    ep.keys_in = (const KeyT*)c->final_keys;
+    ep.rows = c->rows;
+    ep.plan = plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    set_camera(c, &ep);
+    TB_LAUNCH(c, "emit_ordered", c->sorted_count * (64 + 80 + 64 + 4 + 4 + sizeof(KeyT)), (emit_ordered_kernel<KeyT, true>),
+              2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), ep);
+    tb_status s = read_header(c);
+    if (s) return s;
+    *ok = c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] == 0 && c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] == 0 &&
+          c->h_hdr[2] == c->sorted_count && plan_covers(plan, c->h_hdr[0], ~c->h_hdr[1]);
+    return TB_OK;
+}
 
 // The steady-state frame of a flat few-bucket scene whose buckets depend on the Sprite only: one
 // kernel (velocity system + key statistics + rank + compose + emit) placed by the tile offsets the
@@ -1072,8 +1119,10 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint64_t>));
-    cudaFuncSetAttribute(emit_ordered_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
-    cudaFuncSetAttribute(emit_ordered_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
@@ -1102,6 +1151,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     }
     cudaFree(c->ekeys);
     cudaFree(c->final_idx);
+    cudaFree(c->final_keys);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1523,6 +1573,19 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     uint32_t replanned = 0;
     uint64_t count = 0, num_batches = 0;
     bool fast_done = false;
+    if (!c->static_valid && c->sorted_valid && c->final_valid && c->static_buckets && c->sorted_cache && c->plan_valid &&
+        !fm.hier && c->shard_state != 4) {
+        // flat sorted scene with its sort and draw order kept: one kernel emits and validates
+        if (c->plan.key64) s = sorted_fast_frame<uint64_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+        else s = sorted_fast_frame<uint32_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+        if (s) return s;
+        integrate = false;  // the velocity system has run (as its own pass)
+        if (fast_done) {
+            count = c->sorted_count;
+            num_batches = c->sorted_batches;
+        }
+        // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
+    }
     if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
         if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
         integrate = false;
@@ -1667,19 +1730,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         if (c->sorted_cache && (plan.npasses > 1 || fm.hier) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32)) {
             const bool resorted = !armed_at_start || c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] != 0;
             c->sorted_valid = true;
-            if (!armed_at_start) c->final_valid = false;
-            if (resorted && count > 0) {
-                // keep this frame's draw order for the frames that will not need to sort
-                size_t cap = c->final_idx ? c->final_cap : 0;
-                if (grow(c, &c->final_idx, &cap, (size_t)n + 4, 4) == TB_OK) {
-                    c->final_cap = cap;
-                    c->final_valid = cudaMemcpyAsync(c->final_idx, d_order, count * 4, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
-                } else {
-                    c->final_cap = 0;
-                    c->final_valid = false;
-                    cudaGetLastError();
-                }
-            }
+            // a frame that ranked has left its draw order and short keys in final_idx / final_keys
+            if (resorted) c->final_valid = plan.npasses > 1;  // multi-pass frames rank in emit_kernel, which wrote them
+            c->sorted_count = count;
+            c->sorted_batches = num_batches;
         }
         break;
     }
