@@ -136,9 +136,10 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *                           first frame that gathers rows in sorted order (multi-pass, no hierarchy).
  *                           Changing the layout of uploaded rows costs one conversion pass.
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
- *   "static_buckets"   0|1  flat few-bucket scenes whose buckets depend on the Sprite only (no varying z
- *                           bit) reuse the per-tile offsets of the last full frame until a component is
- *                           uploaded: the steady-state frame is one kernel, validated every frame (default 1)
+ *   "static_buckets"   0|1  single-kernel steady-state frames (default 1): flat few-bucket scenes whose buckets
+ *                           depend on the Sprite only reuse the per-tile offsets of the last full frame, flat
+ *                           sorted scenes reuse its draw order; both are validated every frame and dropped
+ *                           when a component is uploaded
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
  *   "sorted_cache"     0|1  sorted (multi-pass / hierarchy) frames keep the previous frame's sorted arrays; when the
