@@ -94,3 +94,13 @@ if __name__ == "__main__":
             sorted_cache=0)
     if "5c" in which:
         run("configs[4] 64M flat on one GPU, keys treated as changed every frame", scenes.config5(), 208, sorted_cache=0)
+    if "3v" in which:
+        sc = scenes.config3()
+        sc.velocities = scenes.config4(n=sc.n, seed=33).velocities  # x / y motion: world rows change every frame, keys do not
+        sc.dt = 0.01
+        run("configs[2] 4M hierarchy depth 8, every entity moving (propagation every frame, sort kept)", sc, 224, integrate=True)
+    if "16v" in which:
+        sc = scenes.config2(n=1 << 24)
+        sc.velocities = scenes.config4(n=sc.n, seed=34).velocities
+        sc.dt = 0.01
+        run("16M flat, 64 textures x 16 layers, z in {0..15}, every entity moving (sort kept)", sc, 232, integrate=True)

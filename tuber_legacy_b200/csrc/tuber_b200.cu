@@ -999,6 +999,28 @@ tb_status sorted_fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d
     return TB_OK;
 }
 
+// A hierarchy frame whose inputs are those of the previous frame: world rows, sort and draw order are all
+// in place, so the frame is emit_ordered_kernel over the world rows.
+template <typename KeyT>
+tb_status replay_hierarchy_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+    EmitParams<KeyT> ep{};
+    ep.pass.n = (uint32_t)c->sorted_count;
+    ep.idx_in = c->final_idx;
+    ep.rows = c->rows;
+    ep.world = c->world;
+    ep.plan = c->plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    set_camera(c, &ep);
+    TB_LAUNCH(c, "emit_ordered", c->sorted_count * (64 + 80 + 64 + 4 + 4), (emit_ordered_kernel<KeyT, false>),
+              2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), ep);
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
 // The steady-state frame of a flat few-bucket scene whose buckets depend on the Sprite only: one
 // kernel (velocity system + key statistics + rank + compose + emit) placed by the tile offsets the
 // last full frame left in the scratch buffer. Returns true in *ok when the frame's own statistics
@@ -1585,6 +1607,17 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             num_batches = c->sorted_batches;
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
+    }
+    if (fm.hier && !integrate && c->world_valid && c->sorted_valid && c->final_valid && c->static_buckets && c->sorted_cache &&
+        c->plan_valid && c->shard_state != 4) {
+        // a scene graph nothing has touched since the frame that left its world rows, sort and draw order (no
+        // upload, no tick): the frame is the emit over those, e.g. under a new camera
+        if (c->plan.key64) s = replay_hierarchy_frame<uint64_t>(c, d_inst, d_vtx, d_order);
+        else s = replay_hierarchy_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+        if (s) return s;
+        fast_done = true;
+        count = c->sorted_count;
+        num_batches = c->sorted_batches;
     }
     if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
         if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
