@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <vector>
 
@@ -30,7 +31,18 @@ __global__ void gather_kernel(const float4* __restrict__ rows, const uint32_t* _
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1) {  // optional: L2 fetch granularity in bytes (32, 64, 128)
+        size_t g = (size_t)atoi(argv[1]);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("{\"l2_fetch_granularity_requested\": %zu, \"status\": \"%s\", \"now\": %zu}\n", g, cudaGetErrorString(e), got);
+    } else {
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        printf("{\"l2_fetch_granularity_default\": %zu}\n", got);
+    }
     const uint32_t n = 1u << 24;  // 1 GiB of 64-byte rows
     float4 *rows, *out;
     uint32_t* idx;
