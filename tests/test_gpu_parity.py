@@ -1000,3 +1000,34 @@ def test_sorted_cache_skips_the_sort_only_when_no_key_changed(kind):
     np.testing.assert_array_equal(g1.instances.view(np.uint32), g2.instances.view(np.uint32))
     c2.close()
     ctx.close()
+
+
+def test_kept_frames_survive_output_and_batch_table_changes():
+    """caller-side changes between steady frames: a larger batch table (re-allocated), other output buffers, a
+    smaller batch cap (error, then recovery)"""
+    for sc in (scenes.config4(n=30_000, seed=121), scenes.config2(n=30_000, seed=122)):
+        ctx = util.make_ctx(sc)
+        ref = util.make_oracle(sc)
+        r = ref.frame()
+        for _ in range(3):
+            util.assert_frame_parity(util.GpuFrame(ctx), r)
+        ctx.set_max_batches(200_000)  # the table moves to a bigger buffer
+        util.assert_frame_parity(util.GpuFrame(ctx), r)
+        util.assert_frame_parity(util.GpuFrame(ctx), r)
+        bufs = [capi.device_alloc(sc.n * b) for b in (80, 64, 4)]
+        ctx.set_output(bufs[0], bufs[1], bufs[2], sc.n)
+        info = ctx.frame()
+        assert info.num_instances == len(r.order) and info.num_batches == len(r.batches)
+        order = ctx.device_read(bufs[2], len(r.order) * 4, np.uint32)
+        np.testing.assert_array_equal(order, r.order)
+        ctx.set_output(None, None, None, 0)
+        if len(r.batches) > 1:
+            ctx.set_max_batches(1)
+            with pytest.raises(capi.TuberError) as e:
+                ctx.frame()
+            assert e.value.status == capi.TB_ERR_CAPACITY
+            ctx.set_max_batches(65536)
+        util.assert_frame_parity(util.GpuFrame(ctx), r)
+        for b in bufs:
+            capi.device_free(b)
+        ctx.close()

@@ -441,6 +441,7 @@ tb_status ensure_outputs(tb_ctx* c, uint64_t n) {
     }
     if (!c->batches || c->batches_cap < c->max_batches) {
         c->batches_cap = 0;
+        c->static_valid = c->sorted_valid = false;  // the single-kernel frames reuse the table that lived in the old buffer
         if ((s = realloc_dev(c, (void**)&c->batches, (size_t)c->max_batches * sizeof(BatchOut)))) return s;
         c->batches_cap = c->max_batches;
     }
