@@ -1031,3 +1031,34 @@ def test_kept_frames_survive_output_and_batch_table_changes():
         for b in bufs:
             capi.device_free(b)
         ctx.close()
+
+
+def test_per_frame_uploads_keep_plan_and_sort_when_keys_do_not_change():
+    """a host system rewrites some transforms every frame (dirty-range upload): the plan is not rediscovered and
+    the sort is kept as long as no key moves; a changed depth re-sorts; a texture outside the plan re-plans"""
+    sc = scenes.config2(n=50_000, seed=131)
+    ctx = util.make_ctx(sc)
+    util.assert_frame_parity(util.GpuFrame(ctx), util.make_oracle(sc).frame())
+    rng = np.random.default_rng(7)
+    for k in range(4):
+        lo = int(rng.integers(0, sc.n - 5000))
+        sc.transforms["translation"][lo:lo + 5000, 0] += np.float32(1.5)  # x only: keys unchanged
+        ctx.upload_transforms(lo, sc.transforms[lo:lo + 5000])
+        g = util.GpuFrame(ctx)
+        assert g.info.replanned == 0
+        util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    sc.transforms["translation"][100:200, 2] = 7.0  # a depth of the dictionary: same plan, new order
+    ctx.upload_transforms(100, sc.transforms[100:200])
+    g = util.GpuFrame(ctx)
+    assert g.info.replanned == 0
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    sc.sprites["texture"][300:310] = 500  # bits the plan does not cover
+    ctx.upload_sprites(300, sc.sprites[300:310])
+    g = util.GpuFrame(ctx)
+    assert g.info.replanned == 1
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    for _ in range(3):  # and back to steady single-kernel frames
+        g = util.GpuFrame(ctx)
+        util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    assert g.info.kernel_launches == 1
+    ctx.close()

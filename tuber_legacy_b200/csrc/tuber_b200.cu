@@ -124,6 +124,7 @@ struct tb_ctx {
     // sorted frames: the previous frame's sorted (key, id) arrays and tile offsets are still in place; a frame
     // whose key pass finds every entity's key unchanged skips its sort passes (decided on the device)
     bool sorted_valid = false;
+    bool fast_clean = false;  // no component was uploaded since the last frame that ran a key pass
     int sorted_cache = 1;
     // ... and the draw order itself (a copy of the last re-sorted frame's `order` output): frames that keep
     // the sort emit straight from it (emit_ordered_kernel)
@@ -1327,8 +1328,11 @@ tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_t
     if (s) return s;
     c->store[TB_TRANSFORM] = true;
     mark_presence(c, TB_TRANSFORM, first, n, 1);
-    c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    // Component values changed. The cached plan stays (every frame validates it against its own statistics) and
+    // so does the kept sort (the key pass compares every entity's key with the kept one); the frames that run
+    // WITHOUT a key pass need one clean prepare-based frame first.
+    c->static_valid = false;
+    c->fast_clean = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1349,8 +1353,8 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     if (s) return s;
     c->store[TB_SPRITE] = true;
     mark_presence(c, TB_SPRITE, first, n, 1);
-    c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    c->static_valid = false;  // as for transforms: plan and kept sort are validated by the next frame's key pass
+    c->fast_clean = false;
     c->world_valid = false;
     c->frame_valid = false;
     // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
@@ -1596,8 +1600,8 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     uint32_t replanned = 0;
     uint64_t count = 0, num_batches = 0;
     bool fast_done = false;
-    if (!c->static_valid && c->sorted_valid && c->final_valid && c->static_buckets && c->sorted_cache && c->plan_valid &&
-        !fm.hier && c->shard_state != 4) {
+    if (!c->static_valid && c->sorted_valid && c->final_valid && c->fast_clean && c->static_buckets && c->sorted_cache &&
+        c->plan_valid && !fm.hier && c->shard_state != 4) {
         // flat sorted scene with its sort and draw order kept: one kernel emits and validates
         if (c->plan.key64) s = sorted_fast_frame<uint64_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
         else s = sorted_fast_frame<uint32_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
@@ -1609,8 +1613,8 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
     }
-    if (fm.hier && !integrate && c->world_valid && c->sorted_valid && c->final_valid && c->static_buckets && c->sorted_cache &&
-        c->plan_valid && c->shard_state != 4) {
+    if (fm.hier && !integrate && c->world_valid && c->sorted_valid && c->final_valid && c->fast_clean && c->static_buckets &&
+        c->sorted_cache && c->plan_valid && c->shard_state != 4) {
         // a scene graph nothing has touched since the frame that left its world rows, sort and draw order (no
         // upload, no tick): the frame is the emit over those, e.g. under a new camera
         if (c->plan.key64) s = replay_hierarchy_frame<uint64_t>(c, d_inst, d_vtx, d_order);
@@ -1768,6 +1772,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if (resorted) c->final_valid = plan.npasses > 1;  // multi-pass frames rank in emit_kernel, which wrote them
             c->sorted_count = count;
             c->sorted_batches = num_batches;
+            c->fast_clean = true;
         }
         break;
     }
