@@ -254,11 +254,21 @@ def test_3d_rotation():
     {"digit_bits": 3},
     {"lt_limit": 0},
     {"lt_limit": 0, "digit_bits": 5, "staged_emit": 0, "interleaved_rows": 1},
+    {"sorted_cache": 0},
+    {"static_buckets": 0},
+    {"cuda_graphs": 0},
+    {"z_dictionary": 0},
+    {"sorted_cache": 0, "static_buckets": 0, "cuda_graphs": 0, "z_dictionary": 0, "small_emit": 0},
 ])
 def test_options_do_not_change_results(options):
     for sc in (scenes.config2(n=50_000, seed=14), scenes.config4(n=50_000, seed=15), scenes.config3(n=30_000, seed=16)):
         ctx, ref, g, r = run_both(sc, ticks=1 if sc.velocities is not None else 0, **options)
         util.assert_frame_parity(g, r)
+        for _ in range(3):  # steady-state frames under the same options
+            if sc.velocities is not None:
+                ctx.system_integrate(0.01)
+                ref.step(0.01)
+            util.assert_frame_parity(util.GpuFrame(ctx), ref.frame())
         ctx.close()
 
 
