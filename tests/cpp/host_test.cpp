@@ -246,6 +246,23 @@ static void frame_parity(bool hierarchy) {
     bool same = true;
     while (it.next(row)) same = same && std::memcmp(ecs2.get<Transform>(it.index), row[0].get<ref::Transform>(), 48) == 0;
     CHECK(same);
+    // camera: Graphics::set_orthographic folds Matrix4::new_orthographic (matrix.rs:41-58) into the next frame
+    {
+        gfx.set_orthographic(-1200.0f, 1200.0f, -900.0f, 900.0f, -100.0f, 100.0f);
+        CHECK(!gfx.render_scene(ecs2).has_value());
+        const ref::Mat4f vp = ref::new_orthographic(-1200.0f, 1200.0f, -900.0f, 900.0f, -100.0f, 100.0f);
+        ref::FrameResult cam;
+        ref::render_scene(oracle2, cam, &vp);
+        auto order2 = gfx.order();
+        auto inst2 = gfx.instances();
+        bool ok = order2.size() == cam.order.size();
+        for (size_t p = 0; ok && p < order2.size(); ++p) {
+            ok = order2[p] == cam.order[p];
+            for (int k = 0; ok && k < 16; ++k) ok = close(inst2[p].model[k], cam.instances[p].model[k], 1.0f);  // clip space: the matrix holds a 1
+        }
+        CHECK(ok);
+        gfx.clear_camera();
+    }
     std::printf("ok frame_parity(%s): %zu instances, %zu batches\n", hierarchy ? "hierarchy" : "flat", order.size(), batches.size());
 }
 
