@@ -863,6 +863,7 @@ def test_graph_replayed_frames_stay_exact(kind):
         sc.sprites["layer"] = np.arange(sc.n) % 7
     else:
         sc = scenes.config3(n=40_000, seed=82)
+        sc.velocities = scenes.config4(n=sc.n, seed=83).velocities  # every node moves in x / y: propagation every frame
     has_vel = sc.velocities is not None
     ctx = util.make_ctx(sc)
     ref = util.make_oracle(sc)

@@ -52,6 +52,7 @@ struct EmitParams {
     // that will keep them: final_idx[pos] = entity id (global), final_keys[pos] = short key
     uint32_t* final_idx;
     KeyT* final_keys;
+    const float4* seq_rows;  // emit_sequential_kernel: the rows (or world rows) in draw order, 64 bytes each
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -866,6 +867,97 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
         }
         if (__any_sync(0xffffffffu, acc.miss) && lane == 0) atomicOr(&ep.stats[4], 1ull);
         if (__any_sync(0xffffffffu, acc.changed) && lane == 0) atomicOr(&ep.stats[5], 1ull);
+    }
+}
+
+// ---- static scenes: rows kept in draw order ---------------------------------------------------------------
+//
+// A scene nothing has touched for two frames (no upload, no tick) gets a copy of its rows in draw order
+// (gather_rows_kernel, once). From then on a frame — e.g. under a moving camera — streams: a warp takes 64
+// consecutive output positions, TMA bulk copies bring the next tile's 4 KB of rows and its entity ids, the
+// current tile is composed and written out in whole lines. Sequential reads instead of one random 64-byte row
+// per entity (which costs about 128 bytes of DRAM traffic each).
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(RowView rows, const WorldRow* world, const uint32_t* __restrict__ idx,
+                                                                uint32_t global_first, uint32_t count, float4* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte chunk: a row's four are adjacent lanes
+    const uint32_t pos = t >> 2, ch = t & 3u;
+    if (pos >= count) return;
+    const uint32_t e = __ldg(idx + pos) - global_first;
+    float4 v;
+    if (world != nullptr) v = reinterpret_cast<const float4*>(world + e)[ch];
+    else v = ch == 0 ? rows.t[(size_t)e * rows.st] : ch == 1 ? rows.a[(size_t)e * rows.st] : rows.b[(size_t)e * rows.sb + (ch & 1u)];
+    out[(size_t)pos * 4 + ch] = v;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const EmitParams<KeyT> ep) {
+    extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    OrderedWarpShared& sm = reinterpret_cast<OrderedShared*>(emit_smem_raw)->w[warp];
+    const bool from_world = ep.world != nullptr;
+    const uint32_t count = ep.pass.n;
+    const uint32_t ntiles = (count + kWarpTile - 1) / kWarpTile;
+    const uint32_t nwarps = gridDim.x * kWarps;
+    auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0
+        const uint32_t cnt = min(kWarpTile, count - t * kWarpTile);
+        const uint32_t ibytes = (cnt * 4u + 15u) & ~15u;
+        mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes);
+        bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile * 4, cnt * 64u, &sm.kbar[buf]);
+        bulk_g2s(sm.idx[buf], ep.idx_in + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
+    };
+    uint32_t tile = blockIdx.x * kWarps + warp;
+    if (lane == 0) {
+        mbar_init(&sm.kbar[0], 1);
+        mbar_init(&sm.kbar[1], 1);
+        if (tile < ntiles) fetch(tile, 0);
+    }
+    __syncwarp();
+    uint32_t cur = 0, par0 = 0, par1 = 0;
+    for (; tile < ntiles; tile += nwarps) {
+        const uint32_t next = tile + nwarps;
+        if (lane == 0 && next < ntiles) fetch(next, cur ^ 1u);
+        mbar_wait(&sm.kbar[cur], cur ? par1 : par0);
+        if (cur) par1 ^= 1u; else par0 ^= 1u;
+        const float4* rows = sm.rows[cur];
+        const uint32_t base = tile * kWarpTile, cnt = min(kWarpTile, count - base);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t li = k * 32 + lane;
+            const bool live = li < cnt;
+            const uint32_t dst = base + li;
+            InstanceOut inst;
+            float4 vtx[4];
+            if (live) {
+                Affine w;
+                float sw, shh;
+                uint32_t tl;
+                if (from_world) {
+                    w.r0 = rows[li * 4];
+                    w.r1 = rows[li * 4 + 1];
+                    w.r2 = rows[li * 4 + 2];
+                    const float4 sv = rows[li * 4 + 3];
+                    sw = sv.x;
+                    shh = sv.y;
+                    tl = __float_as_uint(sv.z);
+                } else {
+                    Row r;
+                    r.a0 = rows[li * 4];
+                    r.a1 = rows[li * 4 + 1];
+                    r.b0 = rows[li * 4 + 2];
+                    r.b1 = rows[li * 4 + 3];
+                    w = compose_local(r);
+                    sw = r.b1.y;
+                    shh = r.b1.z;
+                    tl = __float_as_uint(r.a1.w);
+                }
+                make_outputs(ep, w, sw, shh, tl, inst, vtx);
+                ep.order[dst] = sm.idx[cur][li];
+            }
+            const uint32_t nlive = cnt > (uint32_t)k * 32u ? min(32u, cnt - k * 32u) : 0u;
+            staged_store(sm.stage, lane, live, nlive, dst, inst, vtx, ep.instances, ep.vertices);
+        }
+        __syncwarp();  // the buffers are free for the fetch of the tile after next
+        cur ^= 1u;
     }
 }
 

@@ -132,6 +132,12 @@ struct tb_ctx {
     void* final_keys = nullptr;      // [n] short key per draw position
     bool final_valid = false;
     uint64_t sorted_count = 0, sorted_batches = 0;
+    // static scenes (no upload, no tick for a few frames): a copy of the rows (hierarchy: world rows) in draw order,
+    // from which frames stream instead of gathering
+    float4* seq_rows = nullptr;
+    size_t seq_cap = 0;
+    bool seq_valid = false, seq_world = false;
+    uint32_t clean_streak = 0;  // consecutive frames served by a kept draw order with nothing touched
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
     size_t static_offs_off = 0;
@@ -966,6 +972,45 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
 }
 
 
+// Static scenes: emit from the draw-ordered copy of the rows (see emit_sequential_kernel).
+template <typename KeyT>
+tb_status sequential_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+    EmitParams<KeyT> ep{};
+    ep.pass.n = (uint32_t)c->sorted_count;
+    ep.idx_in = c->final_idx;
+    ep.seq_rows = c->seq_rows;
+    ep.world = c->seq_world ? c->world : nullptr;  // only tells the kernel which kind of row it reads
+    ep.plan = c->plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    set_camera(c, &ep);
+    TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4), emit_sequential_kernel<KeyT>,
+              2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), ep);
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+// Third untouched frame in a row: copy the rows (world rows for a hierarchy) into draw order, once.
+tb_status build_sequential_rows(tb_ctx* c, bool world) {
+    c->seq_valid = false;
+    size_t cap = c->seq_rows ? c->seq_cap : 0;
+    if (grow(c, &c->seq_rows, &cap, (size_t)c->sorted_count * 4 + 4, sizeof(float4)) != TB_OK) {
+        c->seq_cap = 0;
+        cudaGetLastError();
+        return TB_OK;  // no memory for the copy: keep gathering
+    }
+    c->seq_cap = cap;
+    TB_LAUNCH(c, "gather_rows", c->sorted_count * (64 + 64 + 4), gather_rows_kernel, div_up(c->sorted_count * 4, kThreads), kThreads, 0,
+              c->rows, world ? c->world : (const WorldRow*)nullptr, (const uint32_t*)c->final_idx, (uint32_t)c->global_first,
+              (uint32_t)c->sorted_count, c->seq_rows);
+    c->seq_valid = true;
+    c->seq_world = world;
+    return TB_OK;
+}
+
 // The steady-state frame of a flat SORTED scene whose previous sort and draw order are still in place: the
 // velocity system as its own streaming pass (when a tick is pending), then one kernel that gathers, composes
 // and writes in the kept draw order while recomputing every key and comparing it with the kept one. *ok tells
@@ -1143,6 +1188,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint64_t>));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
@@ -1176,6 +1223,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->ekeys);
     cudaFree(c->final_idx);
     cudaFree(c->final_keys);
+    cudaFree(c->seq_rows);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1332,7 +1380,7 @@ tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_t
     // so does the kept sort (the key pass compares every entity's key with the kept one); the frames that run
     // WITHOUT a key pass need one clean prepare-based frame first.
     c->static_valid = false;
-    c->fast_clean = false;
+    c->fast_clean = c->seq_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1354,7 +1402,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     c->store[TB_SPRITE] = true;
     mark_presence(c, TB_SPRITE, first, n, 1);
     c->static_valid = false;  // as for transforms: plan and kept sort are validated by the next frame's key pass
-    c->fast_clean = false;
+    c->fast_clean = c->seq_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
@@ -1523,6 +1571,7 @@ tb_status tb_system_integrate(tb_ctx* c, float dt) {
     // tuber-winit/src/lib.rs:117-141) run as ONE pass over the rows, each tick rounded on its own
     if (c->pending && memcmp(&dt, &c->pending_dt, sizeof(float)) == 0 && c->pending_ticks < 4096) {
         c->pending_ticks += 1;
+        c->seq_valid = false;
         return TB_OK;
     }
     tb_status s = flush_integrate(c);  // earlier ticks of another dt that no frame consumed
@@ -1530,6 +1579,7 @@ tb_status tb_system_integrate(tb_ctx* c, float dt) {
     c->pending = true;
     c->pending_dt = dt;
     c->pending_ticks = 1;
+    c->seq_valid = false;  // rows are about to move
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -1602,14 +1652,24 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     bool fast_done = false;
     if (!c->static_valid && c->sorted_valid && c->final_valid && c->fast_clean && c->static_buckets && c->sorted_cache &&
         c->plan_valid && !fm.hier && c->shard_state != 4) {
-        // flat sorted scene with its sort and draw order kept: one kernel emits and validates
-        if (c->plan.key64) s = sorted_fast_frame<uint64_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
-        else s = sorted_fast_frame<uint32_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+        // flat sorted scene with its sort and draw order kept: one kernel emits and validates — or, when nothing at
+        // all has been touched for a few frames, streams from the draw-ordered copy of the rows
+        const bool untouched = !integrate;
+        if (untouched && c->seq_valid && !c->seq_world) {
+            if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
+            else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+            fast_done = true;
+        } else {
+            if (c->plan.key64) s = sorted_fast_frame<uint64_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+            else s = sorted_fast_frame<uint32_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+        }
         if (s) return s;
         integrate = false;  // the velocity system has run (as its own pass)
         if (fast_done) {
             count = c->sorted_count;
             num_batches = c->sorted_batches;
+            c->clean_streak = untouched ? c->clean_streak + 1 : 0;
+            if (untouched && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, false))) return s;
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
     }
@@ -1617,12 +1677,19 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         c->sorted_cache && c->plan_valid && c->shard_state != 4) {
         // a scene graph nothing has touched since the frame that left its world rows, sort and draw order (no
         // upload, no tick): the frame is the emit over those, e.g. under a new camera
-        if (c->plan.key64) s = replay_hierarchy_frame<uint64_t>(c, d_inst, d_vtx, d_order);
-        else s = replay_hierarchy_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+        if (c->seq_valid && c->seq_world) {
+            if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
+            else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+        } else {
+            if (c->plan.key64) s = replay_hierarchy_frame<uint64_t>(c, d_inst, d_vtx, d_order);
+            else s = replay_hierarchy_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+        }
         if (s) return s;
         fast_done = true;
         count = c->sorted_count;
         num_batches = c->sorted_batches;
+        c->clean_streak += 1;
+        if (!c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, true))) return s;
     }
     if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
         if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
@@ -1770,6 +1837,8 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             c->sorted_valid = true;
             // a frame that ranked has left its draw order and short keys in final_idx / final_keys
             if (resorted) c->final_valid = plan.npasses > 1;  // multi-pass frames rank in emit_kernel, which wrote them
+            if (resorted) c->seq_valid = false;
+            c->clean_streak = 0;
             c->sorted_count = count;
             c->sorted_batches = num_batches;
             c->fast_clean = true;
