@@ -199,6 +199,11 @@ struct tb_ctx {
     uint32_t frame_launches = 0;
 };
 
+// Everything a later frame would reuse without a key pass of its own (per-tile offsets of few-bucket scenes, the
+// kept sort of sorted scenes) is dropped; the next frame computes all of it again.
+inline void drop_kept_frames(tb_ctx* c) { c->static_valid = c->sorted_valid = false; }
+
+
 namespace {
 
 // scratch header layout (32-bit words). Words [0, kHdrFrame) outlive a frame; everything from
@@ -423,7 +428,7 @@ tb_status ensure_scratch(tb_ctx* c, size_t words) {
     }
     c->scratch = (uint32_t*)q;
     c->scratch_words = want;
-    c->static_valid = c->sorted_valid = false;  // cached tile offsets lived in the old buffer
+    drop_kept_frames(c);  // cached tile offsets lived in the old buffer
     return TB_OK;
 }
 
@@ -448,7 +453,7 @@ tb_status ensure_outputs(tb_ctx* c, uint64_t n) {
     }
     if (!c->batches || c->batches_cap < c->max_batches) {
         c->batches_cap = 0;
-        c->static_valid = c->sorted_valid = false;  // the single-kernel frames reuse the table that lived in the old buffer
+        drop_kept_frames(c);  // the single-kernel frames reuse the table that lived in the old buffer
         if ((s = realloc_dev(c, (void**)&c->batches, (size_t)c->max_batches * sizeof(BatchOut)))) return s;
         c->batches_cap = c->max_batches;
     }
@@ -700,7 +705,7 @@ tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     }
     c->rows = dst;
     c->interleaved = interleaved ? 1 : 0;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
     return TB_OK;
 }
 
@@ -724,7 +729,7 @@ void make_plan(tb_ctx* c, uint64_t key_or, uint64_t key_and, const uint32_t* zva
         }
     }
     c->plan_valid = true;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
 }
 
 struct FrameMode {
@@ -1277,15 +1282,15 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->staged_emit = value != 0;
     } else if (k == "static_buckets") {
         c->static_buckets = value != 0;
-        c->static_valid = c->sorted_valid = false;
+        drop_kept_frames(c);
     } else if (k == "small_emit") {
-        c->static_valid = c->sorted_valid = false;
+        drop_kept_frames(c);
         c->small_emit = value != 0;
     } else if (k == "digit_bits") {
         if (value < 1 || value > kMaxDigitBits) return fail(c, TB_ERR_INVALID, "digit_bits must be 1..8");
         c->digit_bits = (int)value;
         c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+        drop_kept_frames(c);
     } else if (k == "sorted_cache") {
         c->sorted_cache = value != 0;
         c->sorted_valid = false;
@@ -1295,12 +1300,12 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     } else if (k == "z_dictionary") {
         c->z_dictionary = value != 0;
         c->plan_valid = false;
-        c->static_valid = c->sorted_valid = false;
+        drop_kept_frames(c);
     } else if (k == "lt_limit") {
         if (value < 0 || value > (int64_t)kMaxLtBits) return fail(c, TB_ERR_INVALID, "lt_limit must be 0..16");
         c->lt_limit = (int)value;
         c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+        drop_kept_frames(c);
     } else {
         return fail(c, TB_ERR_INVALID, "unknown option " + k);
     }
@@ -1334,7 +1339,7 @@ tb_status tb_set_entity_count(tb_ctx* c, uint64_t n) {
     }
     c->n = n;
     c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1448,7 +1453,7 @@ tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_
     }
     c->levels_dirty = true;
     c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -1464,7 +1469,7 @@ tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t 
     TB_CUDA(c, cudaMemcpyAsync(c->mask[comp] + first_word, words, nwords * 8, cudaMemcpyHostToDevice, c->stream));
     c->store[comp] = true;
     c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -1613,7 +1618,7 @@ tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
     if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
     c->force_path = path;
     c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;
+    drop_kept_frames(c);
     return TB_OK;
 }
 
@@ -1698,7 +1703,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             count = c->static_count;
             num_batches = c->static_batches;
         } else {
-            c->static_valid = c->sorted_valid = false;  // e.g. a velocity moved z: fall back to the full frame below
+            drop_kept_frames(c);  // e.g. a velocity moved z: fall back to the full frame below
             replanned = 1;
         }
     }
@@ -1918,7 +1923,7 @@ tb_status tb_shard_plan(tb_ctx* c, const uint64_t g[3], uint64_t* nbins) {
     }
     build_frame_plan(g[0], ~g[1], &c->plan);
     c->plan_valid = false;
-    c->static_valid = c->sorted_valid = false;  // a later single-GPU frame re-plans for itself
+    drop_kept_frames(c);  // a later single-GPU frame re-plans for itself
     if (c->plan.pext.nbits > TB_SHARD_MAX_KEY_BITS)
         return fail(c, TB_ERR_UNSUPPORTED, "sort key too wide for histogram placement across GPUs");
     if ((int)c->plan.ltbits > (int)kMaxLtBits) return fail(c, TB_ERR_UNSUPPORTED, "too many (layer, texture) bins");
