@@ -131,15 +131,16 @@ TB_API tb_status tb_ctx_synchronize(tb_ctx* ctx);
 /* Cap on the batch table (default 65536 entries). */
 TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
 /* Tuning / test knobs; results never depend on them. Names:
- *   "interleaved_rows" 0|1|-1  one 64-byte row per entity (1) or two 32-byte sector arrays (0); -1, the
- *                           default, starts with the sector arrays and switches to 64-byte rows at the
- *                           first frame that gathers rows in sorted order (multi-pass, no hierarchy).
- *                           Changing the layout of uploaded rows costs one conversion pass.
+ *   "interleaved_rows" 0|1|-1  one 64-byte row per entity (1) or three dense arrays (0: translation chunk,
+ *                           key chunk, rest); -1, the default, starts with the arrays and switches to 64-byte
+ *                           rows at the first frame that gathers rows in sorted order (multi-pass, no
+ *                           hierarchy). Changing the layout of uploaded rows costs one conversion pass.
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
  *   "static_buckets"   0|1  single-kernel steady-state frames (default 1): flat few-bucket scenes whose buckets
  *                           depend on the Sprite only reuse the per-tile offsets of the last full frame, flat
- *                           sorted scenes reuse its draw order; both are validated every frame and dropped
- *                           when a component is uploaded
+ *                           sorted scenes reuse its draw order (every key re-checked while emitting), scenes
+ *                           nothing has touched for two frames stream from a draw-ordered copy of their rows;
+ *                           all of it is dropped when a component is uploaded
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
  *   "sorted_cache"     0|1  sorted (multi-pass / hierarchy) frames keep the previous frame's sorted arrays; when the
