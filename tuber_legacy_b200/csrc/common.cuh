@@ -37,7 +37,7 @@ __device__ __forceinline__ Row load_row(const RowView& rv, uint32_t i) {
     return r;
 }
 
-// Full 64-bit sort key of a flat row (sector A only when planar).
+// Full 64-bit sort key of a flat row (chunks A0 A1 only when planar).
 __device__ __forceinline__ uint64_t flat_key(const RowView& rv, uint32_t i, const float4 a0, const float4 a1) {
     const uint32_t tl = __float_as_uint(a1.w);
     float z;

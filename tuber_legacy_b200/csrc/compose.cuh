@@ -122,10 +122,10 @@ __device__ __forceinline__ Affine compose_local(const Row& r) {
 }
 
 // True when the row's rotation is about z only (every 2-D sprite): then M[2][3] needs no
-// trigonometry and nothing from sector B.
+// trigonometry and nothing from chunks B0 B1.
 __device__ __forceinline__ bool is_planar(const float4 a1) { return a1.y == 0.0f && a1.z == 0.0f; }
 
-// M[2][3] (the world z of a flat entity) from sector A alone, valid when is_planar(a1):
+// M[2][3] (the world z of a flat entity) from chunks A0 A1 alone, valid when is_planar(a1):
 // R[2] = (0, 0, 1), so with finite c.x, c.y the row-2 sum is
 //   ((+-0 + +-0) + s.z*(-c.z)) + (s.z*c.z + s.z*t.z).
 __device__ __forceinline__ float planar_z(const float4 a0, const float4 a1) {
@@ -135,7 +135,7 @@ __device__ __forceinline__ float planar_z(const float4 a0, const float4 a1) {
     return addr(acc, trj);
 }
 
-// M[2][3] of any row (general 3-D rotation needs sector B too).
+// M[2][3] of any row (general 3-D rotation needs chunks B0 B1 too).
 __device__ __forceinline__ float local_z(const Row& r) {
     const float tz = r.a0.z, cz = r.a0.w, sz = r.a1.x, ax = r.a1.y, ay = r.a1.z;
     const float az = r.b0.x, cx = r.b0.y, cy = r.b0.z;

@@ -454,7 +454,7 @@ struct SmallShared {
 // FUSED: the whole frame in this one kernel. When the bucket of an entity depends only on its
 // Sprite (the plan has no varying z bit), per-tile bucket offsets stay valid from frame to frame
 // until a component is uploaded, so the steady-state frame needs no separate key pass: this kernel
-// also runs the velocity system (writing sector A back), and accumulates the key statistics with
+// also runs the velocity system (writing the translation chunk back), and accumulates the key statistics with
 // which the host validates, every frame, that the cached plan and offsets still hold.
 template <typename KeyT, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParams<KeyT> ep) {
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
         const unsigned long long moving = do_int ? (mt & __shfl_sync(0xffffffffu, raw, 2) & tail) : 0ull;
         if (do_int) {
             // the velocity system on this tile: translation += velocity * dt, in shared memory (the
-            // compose below reads it) and written back to sector A
+            // compose below reads it) and written back to the translation array
             const float* vel = reinterpret_cast<const float*>(sm.vel[cur]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
