@@ -18,5 +18,6 @@ uint64_t plan_short_key(const tb::FramePlan* f, uint64_t key, int* miss) {
     *miss = m ? 1 : 0;
     return sk;
 }
+int plan_equal(const tb::FramePlan* a, const tb::FramePlan* b) { return tb::plan_equal(*a, *b) ? 1 : 0; }
 uint32_t plan_sizeof() { return (uint32_t)sizeof(tb::FramePlan); }
 }

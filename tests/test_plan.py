@@ -37,6 +37,7 @@ def lib():
     L.plan_pdep.argtypes = [C.POINTER(FramePlan), C.c_uint64]
     L.plan_covers.argtypes = [C.POINTER(FramePlan), C.c_uint64, C.c_uint64]
     L.plan_build_dict.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(FramePlan)]
+    L.plan_equal.argtypes = [C.POINTER(FramePlan), C.POINTER(FramePlan)]
     L.plan_short_key.restype = C.c_uint64
     L.plan_short_key.argtypes = [C.POINTER(FramePlan), C.c_uint64, C.POINTER(C.c_int)]
     assert L.plan_sizeof() == C.sizeof(FramePlan)
@@ -207,3 +208,22 @@ def test_z_dictionary_miss_and_stale_high_half(lib):
     # low-half changes are the dictionary's business; a new texture bit is not covered
     assert lib.plan_covers(C.byref(f), k_or | 0x7FFFFFFF, k_and & ~0x7FFFFFFF) == 1
     assert lib.plan_covers(C.byref(f), k_or | (8 << 32), k_and) == 0
+
+
+def test_plan_equal_ignores_padding_and_unused_dictionary_slots(lib):
+    """the frame signature (which steady frames may replay a captured graph) compares plans field by field"""
+    z = orderable(np.array([0.0, 1.0, 2.0, 3.0], np.float32))
+    keys = np.concatenate([z | (np.uint64(t) << np.uint64(32)) for t in range(4)])
+    a, _, _ = build_dict(lib, keys)
+    b, _, _ = build_dict(lib, keys)
+    for k in range(a.zdict_n, 64):
+        b.zdict[k] = 0xDEADBEEF  # slots beyond zdict_n do not count
+    assert lib.plan_equal(C.byref(a), C.byref(b)) == 1
+    b.zdict[1] += 1
+    assert lib.plan_equal(C.byref(a), C.byref(b)) == 0
+    c, _, _ = build(lib, keys)  # the same keys without a dictionary: another plan
+    assert lib.plan_equal(C.byref(a), C.byref(c)) == 0
+    d, _, _ = build(lib, keys)
+    assert lib.plan_equal(C.byref(c), C.byref(d)) == 1
+    d.bits[0] += 1
+    assert lib.plan_equal(C.byref(c), C.byref(d)) == 0
