@@ -120,7 +120,9 @@ typedef struct tb_frame_out {
 TB_API const char* tb_version(void);
 TB_API const char* tb_status_string(tb_status s);
 /* Creates a context on CUDA device `device` with room for `max_entities` entity indices.
- * Fails with TB_ERR_NO_DEVICE when there is no sm_100 GPU. */
+ * Fails with TB_ERR_NO_DEVICE when there is no sm_100 GPU. Every entry point makes the context's
+ * device current for the duration of the call and restores the calling thread's current device on
+ * return, so one process may hold a context per GPU. */
 TB_API tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out);
 TB_API void tb_ctx_destroy(tb_ctx* ctx);
 TB_API const char* tb_last_error(tb_ctx* ctx);
@@ -165,7 +167,12 @@ TB_API void tb_host_free(void* p);
 TB_API tb_status tb_set_entity_count(tb_ctx* ctx, uint64_t n);
 TB_API tb_status tb_entity_count(tb_ctx* ctx, uint64_t* n);
 /* Column uploads for entity indices [first, first + n). Uploading a column marks the
- * component present on that range (ComponentStore::add_to_entity, ecs.rs:40-43). */
+ * component present on that range (ComponentStore::add_to_entity, ecs.rs:40-43).
+ * SOURCE LIFETIME: uploads are enqueued on the context's stream and may return before the copy has
+ * read `src` (always so for page-locked memory from tb_host_alloc; pageable memory is staged by the
+ * driver before the call returns). The caller must not modify or free `src` until the next call that
+ * synchronises the context: tb_ctx_synchronize, tb_frame_transform_batch, any tb_download_*, tb_query,
+ * tb_upload_sprites (it reads back the range check). The same holds for tb_upload_presence. */
 TB_API tb_status tb_upload_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_transform* src);
 TB_API tb_status tb_upload_sprites(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_sprite* src);
 TB_API tb_status tb_upload_velocities(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_velocity* src);
@@ -191,6 +198,30 @@ TB_API tb_status tb_query(tb_ctx* ctx, uint32_t required_components, uint32_t* o
 
 /* n host Transforms -> n row-major Matrix4f (16 f32 each, matrix.rs:9-12) on the host. */
 TB_API tb_status tb_as_matrix4(tb_ctx* ctx, const tb_transform* src, uint64_t n, float* dst16);
+
+/* ---- the rest of tuber-math on the device, batched -------------------------------
+ *
+ * Host arrays in, host arrays out, n elements each; every operation individually rounded in the
+ * reference's own order, so the results are the reference's bit for bit (sin / cos: the host libm's
+ * sinf / cosf reproduced on the device). Quaternions are (w, x, y, z); matrices row-major 16 f32
+ * (matrix.rs:9-12). */
+/* Quaternion::from_euler (quaternion.rs:39-59): (roll, pitch, yaw) per element. */
+TB_API tb_status tb_quat_from_euler(tb_ctx* ctx, const float* euler_xyz, uint64_t n, float* wxyz);
+/* Quaternion::from_axis_angle (quaternion.rs:28-37): (axis.x, axis.y, axis.z, angle) per element. */
+TB_API tb_status tb_quat_from_axis_angle(tb_ctx* ctx, const float* axis_angle4, uint64_t n, float* wxyz);
+/* Quaternion::rotation_matrix (quaternion.rs:63-90); the quaternion is not normalised first. */
+TB_API tb_status tb_quat_rotation_matrix(tb_ctx* ctx, const float* wxyz, uint64_t n, float* m16);
+/* impl Mul for Quaternion (quaternion.rs:132-158). */
+TB_API tb_status tb_quat_mul(tb_ctx* ctx, const float* a_wxyz, const float* b_wxyz, uint64_t n, float* out_wxyz);
+/* Quaternion::normalized (quaternion.rs:92-120). */
+TB_API tb_status tb_quat_normalize(tb_ctx* ctx, const float* wxyz, uint64_t n, float* out_wxyz);
+/* impl Mul for Matrix4 (matrix.rs:174-194). */
+TB_API tb_status tb_mat4_mul(tb_ctx* ctx, const float* a16, const float* b16, uint64_t n, float* out16);
+/* Matrix4::transform_vec3 (matrix.rs:160-171): one point (3 f32) per matrix. */
+TB_API tb_status tb_mat4_transform_vec3(tb_ctx* ctx, const float* m16, const float* v3, uint64_t n, float* out3);
+/* Matrix4::try_inverse (matrix.rs:98-149): some[i] = 1 and out16[i] = inverse, or some[i] = 0 (None:
+ * |det| < 1e-8, number_traits.rs:80-84) and out16[i] all zero. */
+TB_API tb_status tb_mat4_try_inverse(tb_ctx* ctx, const float* m16, uint64_t n, float* out16, uint8_t* some);
 
 /* ---- systems: what SystemBundle::step (system.rs:17-23) runs per tick -------------------- */
 

@@ -55,6 +55,7 @@ def lib():
         L.orc_frame_run_camera.argtypes = [vp, vp]
         L.orc_orthographic.argtypes = [C.c_float] * 6 + [vp]
         L.orc_frame_free.argtypes = [vp]
+        L.orc_frame_bounds.argtypes = [vp, vp, vp, vp]
         L.orc_frame_seconds.restype = dbl
         L.orc_frame_seconds.argtypes = [vp]
         for f in ("orc_frame_num_instances", "orc_frame_num_batches", "orc_frame_num_entities"):
@@ -104,6 +105,12 @@ def lib():
         for f in ("orc_words_set_bit", "orc_words_unset_bit", "orc_words_bit"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [vp, u64, u64]
+        for f in ("orc_batch_quat_from_euler", "orc_batch_quat_from_axis_angle", "orc_batch_quat_rotation_matrix",
+                  "orc_batch_quat_normalize"):
+            getattr(L, f).argtypes = [vp, u64, vp]
+        for f in ("orc_batch_quat_mul", "orc_batch_mat4_mul", "orc_batch_mat4_transform_vec3"):
+            getattr(L, f).argtypes = [vp, vp, u64, vp]
+        L.orc_batch_mat4_try_inverse.argtypes = [vp, u64, vp, vp]
         _lib = L
     return _lib
 
@@ -133,7 +140,7 @@ def _u32(a, cols):
 class Frame:
     """Result of ref::render_scene over a restated-reference Ecs."""
 
-    def __init__(self, h):
+    def __init__(self, h, scene_handle=None, view_proj=None):
         L = lib()
         n = L.orc_frame_num_entities(h)
         m = L.orc_frame_num_instances(h)
@@ -154,6 +161,10 @@ class Frame:
             L.orc_frame_read_vertices(h, _p(self.vertices))
         if b:
             L.orc_frame_read_batches(h, _p(self.batches))
+        # forward bounds of the model matrices (row-major, per instance): the denominator of the parity metric
+        self.bounds = np.zeros((m, 16), np.float64)
+        if m and scene_handle:
+            L.orc_frame_bounds(scene_handle, h, _p(view_proj), _p(self.bounds))
         L.orc_frame_free(h)
 
 
@@ -198,12 +209,12 @@ class Scene:
         lib().orc_scene_read_transforms(self._h, _p(out))
         return out
 
-    def frame(self, view_proj=None):
+    def frame(self, view_proj=None, bounds=True):
         """render_scene; `view_proj` (4x4 row-major f32) folds a camera into instances and vertices."""
         if view_proj is None:
-            return Frame(lib().orc_frame_run(self._h))
+            return Frame(lib().orc_frame_run(self._h), self._h if bounds else None)
         m = np.ascontiguousarray(np.asarray(view_proj, np.float32).reshape(16))
-        return Frame(lib().orc_frame_run_camera(self._h, _p(m)))
+        return Frame(lib().orc_frame_run_camera(self._h, _p(m)), self._h if bounds else None, m)
 
 
 def orthographic(left, right, bottom, top, near, far):
@@ -229,3 +240,49 @@ def as_matrix4_closed(transforms):
 
 def sort_key(layer, texture, z):
     return lib().orc_sort_key(int(layer), int(texture), float(np.float32(z)))
+
+
+# ---- batched tuber-math (matrix.rs / quaternion.rs restatements), for the device-vs-oracle tests ----
+
+def _batch(fn, ins, cols_out, dtype=np.float32):
+    ins = [np.ascontiguousarray(a, dtype=np.float32) for a in ins]
+    n = ins[0].shape[0]
+    out = np.zeros((n, cols_out), dtype) if cols_out else np.zeros(n, dtype)
+    getattr(lib(), fn)(*[_p(a) for a in ins], n, _p(out))
+    return out
+
+
+def quat_from_euler(e):
+    return _batch("orc_batch_quat_from_euler", [np.reshape(e, (-1, 3))], 4)
+
+
+def quat_from_axis_angle(aa):
+    return _batch("orc_batch_quat_from_axis_angle", [np.reshape(aa, (-1, 4))], 4)
+
+
+def quat_rotation_matrix(q):
+    return _batch("orc_batch_quat_rotation_matrix", [np.reshape(q, (-1, 4))], 16)
+
+
+def quat_mul(a, b):
+    return _batch("orc_batch_quat_mul", [np.reshape(a, (-1, 4)), np.reshape(b, (-1, 4))], 4)
+
+
+def quat_normalize(q):
+    return _batch("orc_batch_quat_normalize", [np.reshape(q, (-1, 4))], 4)
+
+
+def mat4_mul(a, b):
+    return _batch("orc_batch_mat4_mul", [np.reshape(a, (-1, 16)), np.reshape(b, (-1, 16))], 16)
+
+
+def mat4_transform_vec3(m, v):
+    return _batch("orc_batch_mat4_transform_vec3", [np.reshape(m, (-1, 16)), np.reshape(v, (-1, 3))], 3)
+
+
+def mat4_try_inverse(m):
+    m = np.ascontiguousarray(np.reshape(m, (-1, 16)), dtype=np.float32)
+    out = np.zeros_like(m)
+    some = np.zeros(m.shape[0], np.uint8)
+    lib().orc_batch_mat4_try_inverse(_p(m), m.shape[0], _p(out), _p(some))
+    return out, some

@@ -92,6 +92,44 @@ void orc_transform_vec3(const float* m16, const float* p3, float* out3) {
     Vec3 r = transform_vec3(m, Vec3{p3[0], p3[1], p3[2]});
     out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
 }
+// ---- batched forms (n elements) for the device-vs-oracle tests of the tuber-math entry points ----
+void orc_batch_quat_from_euler(const float* e3, uint64_t n, float* wxyz) {
+    for (uint64_t i = 0; i < n; ++i) orc_quat_from_euler(e3 + 3 * i, wxyz + 4 * i);
+}
+void orc_batch_quat_from_axis_angle(const float* aa4, uint64_t n, float* wxyz) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* a = aa4 + 4 * i;
+        Quat q = from_axis_angle(Vec3{a[0], a[1], a[2]}, a[3]);
+        float* o = wxyz + 4 * i;
+        o[0] = q.w; o[1] = q.x; o[2] = q.y; o[3] = q.z;
+    }
+}
+void orc_batch_quat_rotation_matrix(const float* wxyz, uint64_t n, float* out16) {
+    for (uint64_t i = 0; i < n; ++i) orc_quat_rotation_matrix(wxyz + 4 * i, out16 + 16 * i);
+}
+void orc_batch_quat_mul(const float* a, const float* b, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) orc_quat_mul(a + 4 * i, b + 4 * i, out + 4 * i);
+}
+void orc_batch_quat_normalize(const float* q, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* a = q + 4 * i;
+        Quat r = quat_normalized(Quat{a[0], a[1], a[2], a[3]});
+        float* o = out + 4 * i;
+        o[0] = r.w; o[1] = r.x; o[2] = r.y; o[3] = r.z;
+    }
+}
+void orc_batch_mat4_mul(const float* a, const float* b, uint64_t n, float* out) {
+    for (uint64_t i = 0; i < n; ++i) orc_mat4_mul_f32(a + 16 * i, b + 16 * i, out + 16 * i);
+}
+void orc_batch_mat4_try_inverse(const float* a, uint64_t n, float* out, uint8_t* some) {
+    for (uint64_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 16; ++k) out[16 * i + k] = 0.0f;
+        some[i] = (uint8_t)orc_mat4_try_inverse(a + 16 * i, out + 16 * i);
+    }
+}
+void orc_batch_mat4_transform_vec3(const float* m16, const float* p3, uint64_t n, float* out3) {
+    for (uint64_t i = 0; i < n; ++i) orc_transform_vec3(m16 + 16 * i, p3 + 3 * i, out3 + 3 * i);
+}
 void orc_to_column_major(const float* m16, float* out16) {
     Mat4f m;
     std::memcpy(m.v, m16, 64);
@@ -376,6 +414,14 @@ void* orc_frame_run_camera(void* h, const float* view_proj16) {
 void orc_orthographic(float l, float r, float b, float t, float n, float fa, float* out16) {
     const Mat4f m = new_orthographic(l, r, b, t, n, fa);
     for (int k = 0; k < 16; ++k) out16[k] = m.v[k];
+}
+// Forward bounds of the frame's model matrices (ref_frame.hpp forward_bounds): 16 doubles per instance.
+void orc_frame_bounds(void* h, void* f, const float* view_proj16, double* out) {
+    auto* o = static_cast<OrcEcs*>(h);
+    auto* fr = static_cast<OrcFrame*>(f);
+    Mat4f vp;
+    if (view_proj16) for (int k = 0; k < 16; ++k) vp.v[k] = view_proj16[k];
+    forward_bounds(o->ecs, fr->r.order, view_proj16 ? &vp : nullptr, out);
 }
 void orc_frame_free(void* f) { delete static_cast<OrcFrame*>(f); }
 double orc_frame_seconds(void* f) { return static_cast<OrcFrame*>(f)->r.seconds; }

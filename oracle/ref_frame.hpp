@@ -209,4 +209,72 @@ inline void render_scene(const Ecs& ecs, FrameResult& out, const Mat4f* view_pro
     out.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- forward error bounds (the parity metric's denominator; not part of the frame) ----------------------
+//
+// For every emitted instance, the entry-wise forward bound of its model matrix: the same chain of products
+// as render_scene, evaluated on ABSOLUTE values in double — i.e. for every entry the sum of the magnitudes of
+// all the terms that are added up to produce it (an entry that is a cancelling sum, such as a
+// world translation near 0, is judged against the size of its terms, not against its own tiny value).
+// out: 16 doubles per instance, row-major, in draw order (`order`).
+struct AbsMat {
+    double v[16];
+};
+inline AbsMat abs_of(const Mat4f& m) {
+    AbsMat r;
+    for (int k = 0; k < 16; ++k) r.v[k] = std::fabs(double(m.v[k]));
+    return r;
+}
+inline AbsMat abs_mul(const AbsMat& a, const AbsMat& b) {
+    AbsMat r;
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += a.v[j * 4 + k] * b.v[k * 4 + i];
+            r.v[j * 4 + i] = s;
+        }
+    return r;
+}
+inline void forward_bounds(const Ecs& ecs, const std::vector<uint32_t>& order, const Mat4f* view_proj, double* out) {
+    const size_t n = ecs.entity_count();
+    std::vector<AbsMat> bound(n);
+    std::vector<uint8_t> has(n, 0), done(n, 0);
+    std::vector<size_t> parent(n, SIZE_MAX);
+    {
+        QueryIterator it = ecs.query({{TY_TRANSFORM, true, false}, {TY_PARENT, false, false}});
+        std::vector<Guard> row;
+        while (it.next(row)) {
+            const size_t e = it.index;
+            const Transform& t = *row[0].get<Transform>();
+            AbsMat m = abs_mul(abs_of(new_scale(t.scale)), abs_of(new_translation(t.translation)));
+            m = abs_mul(m, abs_of(new_translation(t.rotation_center)));
+            m = abs_mul(m, abs_of(rotation_matrix(from_euler(t.angle))));
+            m = abs_mul(m, abs_of(new_translation(neg(t.rotation_center))));
+            bound[e] = m;
+            has[e] = 1;
+            if (row[1].some()) parent[e] = row[1].get<Parent>()->index;
+        }
+    }
+    std::vector<size_t> chain;
+    for (size_t e = 0; e < n; ++e) {
+        if (!has[e] || done[e]) continue;
+        chain.clear();
+        size_t cur = e;
+        while (true) {
+            chain.push_back(cur);
+            const size_t p = parent[cur];
+            if (p == SIZE_MAX || p >= n || !has[p] || done[p] || chain.size() > n) break;
+            cur = p;
+        }
+        for (size_t k = chain.size(); k-- > 0;) {
+            const size_t c = chain[k], p = parent[c];
+            if (p != SIZE_MAX && p < n && has[p] && done[p]) bound[c] = abs_mul(bound[p], bound[c]);
+            done[c] = 1;
+        }
+    }
+    for (size_t pos = 0; pos < order.size(); ++pos) {
+        const AbsMat b = view_proj ? abs_mul(abs_of(*view_proj), bound[order[pos]]) : bound[order[pos]];
+        for (int k = 0; k < 16; ++k) out[16 * pos + k] = b.v[k];
+    }
+}
+
 }  // namespace ref

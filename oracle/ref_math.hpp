@@ -220,15 +220,40 @@ inline Mat4f rotation_matrix(const Quat& q) {
     return m;
 }
 
-// quaternion.rs:132-158 — Hamilton product; off the per-frame path, restated for the
-// reference's own test (quaternion.rs:167-177).
+// quaternion.rs:132-158 — Hamilton product, every component summed in the reference's own term order
+// (x1*w2 + y1*z2 - z1*y2 + w1*x2, ...); off the per-frame path, pinned by the reference's test (quaternion.rs:167-177).
 inline Quat quat_mul(const Quat& a, const Quat& b) {
+    const float x1 = a.x, y1 = a.y, z1 = a.z, w1 = a.w;
+    const float x2 = b.x, y2 = b.y, z2 = b.z, w2 = b.w;
     Quat r;
-    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
-    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+    r.w = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+    r.x = x1 * w2 + y1 * z2 - z1 * y2 + w1 * x2;
+    r.y = y1 * w2 + z1 * x2 + w1 * y2 - x1 * z2;
+    r.z = z1 * w2 + w1 * z2 + x1 * y2 - y1 * x2;
     return r;
+}
+
+// quaternion.rs:28-37
+inline Quat from_axis_angle(const Vec3& axis, float angle) {
+    const float half_angle = angle * 0.5f;
+    const float s = sinf(half_angle);
+    Quat q;
+    q.x = axis.x * s;
+    q.y = axis.y * s;
+    q.z = axis.z * s;
+    q.w = cosf(half_angle);
+    return q;
+}
+
+// quaternion.rs:106-117 (norm) and :92-96 (normalize): vector part and scalar part divided by the norm
+// (vector.rs:132-140: component / rhs).
+inline float quat_norm(const Quat& q) {
+    const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, ww = q.w * q.w;
+    return std::sqrt(ww + xx + yy + zz);
+}
+inline Quat quat_normalized(const Quat& q) {
+    const float norm = quat_norm(q);
+    return Quat{q.w / norm, q.x / norm, q.y / norm, q.z / norm};
 }
 
 // tuber-core/src/transform.rs:5-11 — 4 × Vector3<f32> = 48 bytes, this field order.

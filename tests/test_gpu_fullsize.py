@@ -28,7 +28,7 @@ def sample_matches_oracle(sc, g, k=4096, seed=0):
     ent = g.order[pos]
     want = oracle.as_matrix4(sc.transforms[ent].view(np.float32).reshape(-1, 12))
     got = g.instances["model"][pos].reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1, 16)  # column-major -> row-major
-    util.float_close(got, want, np.abs(want).max(axis=1, keepdims=True), "sampled instance matrix")
+    util.assert_floats_match(got, want, "sampled instance matrix")
     np.testing.assert_array_equal(g.instances["texture"][pos], sc.sprites["texture"][ent])
     np.testing.assert_array_equal(g.instances["layer"][pos], sc.sprites["layer"][ent])
 
@@ -80,7 +80,7 @@ def test_config3_4M_hierarchy_full_size():
             out = np.zeros(16, np.float32)
             L.orc_mat4_mul_f32(C.c_void_p(m.ctypes.data), C.c_void_p(local[k].ctypes.data), C.c_void_p(out.ctypes.data))
             m = out
-        util.float_close(w[e], m, np.abs(m).max(), "world matrix of a depth-%d chain" % len(chain))
+        util.assert_floats_match(w[e], m, "world matrix of a depth-%d chain" % len(chain))
     ctx.close()
 
 
@@ -144,7 +144,7 @@ def test_config5_64M_flat_full_size_one_gpu():
         assert np.all(ent[:-1][tie] < ent[1:][tie])
         want = oracle.as_matrix4(sc.transforms[ent].view(np.float32).reshape(-1, 12))
         got = inst["model"].reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1, 16)
-        util.float_close(got, want, np.abs(want).max(axis=1, keepdims=True), "instance matrix")
+        util.assert_floats_match(got, want, "instance matrix")
         np.testing.assert_array_equal(inst["texture"], sc.sprites["texture"][ent])
         vtx = ctx.download_vertices(m, first=first)
         assert np.array_equal(vtx["x"][:, 0], inst["model"][:, 12]) and np.array_equal(vtx["y"][:, 0], inst["model"][:, 13])

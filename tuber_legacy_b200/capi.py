@@ -74,6 +74,14 @@ _SIGNATURES = {
     "tb_download_transforms": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_query": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tb_as_matrix4": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_quat_from_euler": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_quat_from_axis_angle": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_quat_rotation_matrix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_quat_mul": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_quat_normalize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_mat4_mul": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_mat4_transform_vec3": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_mat4_try_inverse": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "tb_system_integrate": (C.c_int32, [C.c_void_p, C.c_float]),
     "tb_frame_transform_batch": (C.c_int32, [C.c_void_p, C.POINTER(FrameOut)]),
     "tb_frame_force_path": (C.c_int32, [C.c_void_p, C.c_uint32]),
@@ -258,6 +266,39 @@ class Context:
         out = np.zeros((a.shape[0], 16), dtype=np.float32)
         self._check(self._lib.tb_as_matrix4(self._h, _ptr(a), a.shape[0], _ptr(out)))
         return out
+
+    # -- the rest of tuber-math, batched (f32 arrays; quaternions (w, x, y, z), matrices row-major)
+    def _math(self, fn, ins, out_shapes):
+        ins = [np.ascontiguousarray(a, dtype=np.float32) for a in ins]
+        n = ins[0].shape[0]
+        outs = [np.zeros((n,) + tuple(sh), dtype=dt) for sh, dt in out_shapes]
+        self._check(fn(self._h, *[_ptr(a) for a in ins], n, *[_ptr(o) for o in outs]))
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def quat_from_euler(self, euler_xyz):
+        return self._math(self._lib.tb_quat_from_euler, [np.reshape(euler_xyz, (-1, 3))], [((4,), np.float32)])
+
+    def quat_from_axis_angle(self, axis_angle):
+        return self._math(self._lib.tb_quat_from_axis_angle, [np.reshape(axis_angle, (-1, 4))], [((4,), np.float32)])
+
+    def quat_rotation_matrix(self, q):
+        return self._math(self._lib.tb_quat_rotation_matrix, [np.reshape(q, (-1, 4))], [((16,), np.float32)])
+
+    def quat_mul(self, a, b):
+        return self._math(self._lib.tb_quat_mul, [np.reshape(a, (-1, 4)), np.reshape(b, (-1, 4))], [((4,), np.float32)])
+
+    def quat_normalize(self, q):
+        return self._math(self._lib.tb_quat_normalize, [np.reshape(q, (-1, 4))], [((4,), np.float32)])
+
+    def mat4_mul(self, a, b):
+        return self._math(self._lib.tb_mat4_mul, [np.reshape(a, (-1, 16)), np.reshape(b, (-1, 16))], [((16,), np.float32)])
+
+    def mat4_transform_vec3(self, m, v):
+        return self._math(self._lib.tb_mat4_transform_vec3, [np.reshape(m, (-1, 16)), np.reshape(v, (-1, 3))], [((3,), np.float32)])
+
+    def mat4_try_inverse(self, m):
+        """-> (inverse (n, 16), some (n,) uint8); some == 0 is the reference's None."""
+        return self._math(self._lib.tb_mat4_try_inverse, [np.reshape(m, (-1, 16))], [((16,), np.float32), ((), np.uint8)])
 
     def system_integrate(self, dt):
         self._check(self._lib.tb_system_integrate(self._h, float(np.float32(dt))))

@@ -7,7 +7,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "libm_sincosf.h"
+
 namespace tb {
+
+// Which build of glibc's sinf / cosf the HOST's libm uses (1: the FMA + AVX2 build, 0: the generic one); set per
+// device by tb_ctx_create from the same CPU-feature test as glibc's own selector. See libm_sincosf.h.
+__constant__ int c_libm_fma = 1;
+
+// f32::sin / f32::cos of the reference (number_traits.rs:137-143 -> the platform libm), bit for bit.
+__device__ __forceinline__ void ref_sincosf(float a, float* s, float* c) {
+    if (c_libm_fma) tbm::sincosf_ref<true>(a, s, c);
+    else tbm::sincosf_ref<false>(a, s, c);
+}
 
 // Device row of the (Transform, Sprite) table: four 16-byte chunks per entity.
 //   A0 = {t.x, t.y, t.z, c.z}        A1 = {s.z, angle.x, angle.y, texture | layer << 16}
@@ -59,7 +71,7 @@ __device__ __forceinline__ void integrate_ticks(float4& a0, float vx, float vy, 
 __device__ __forceinline__ void rotation3x3(float ax, float ay, float az, float R[9]) {
     float w, x, y, z;
     float sy_, cy_;
-    sincosf(mulr(az, 0.5f), &sy_, &cy_);
+    ref_sincosf(mulr(az, 0.5f), &sy_, &cy_);
     if (ax == 0.0f && ay == 0.0f) {
         // 2-D: R = [[1-zz2, -wz2, 0], [wz2, 1-zz2, 0], [0, 0, 1]]
         float z2 = addr(sy_, sy_);
@@ -73,8 +85,8 @@ __device__ __forceinline__ void rotation3x3(float ax, float ay, float az, float 
         return;
     }
     float sp, cp, sr, cr;
-    sincosf(mulr(ay, 0.5f), &sp, &cp);
-    sincosf(mulr(ax, 0.5f), &sr, &cr);
+    ref_sincosf(mulr(ay, 0.5f), &sp, &cp);
+    ref_sincosf(mulr(ax, 0.5f), &sr, &cr);
     w = addr(mulr(mulr(cr, cp), cy_), mulr(mulr(sr, sp), sy_));
     x = subr(mulr(mulr(sr, cp), cy_), mulr(mulr(cr, sp), sy_));
     y = addr(mulr(mulr(cr, sp), cy_), mulr(mulr(sr, cp), sy_));

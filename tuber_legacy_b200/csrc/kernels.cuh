@@ -9,6 +9,7 @@
 //                  rank_tile, radix_scatter, build_batches, batch_*     batch table
 //   emit.cuh       emit_kernel, emit_small_kernel                       last pass fused with compose + emit
 //   shard.cuh      place_sums, place_write                              multi-GPU global draw order
+//   mathops.cuh    quat_*, mat4_*                                       the rest of tuber-math, batched
 #pragma once
 #include "common.cuh"
 #include "storage.cuh"
@@ -16,3 +17,4 @@
 #include "placement.cuh"
 #include "emit.cuh"
 #include "shard.cuh"
+#include "mathops.cuh"

@@ -46,7 +46,7 @@ struct FrameSig {
     uint64_t n = 0, max_batches = 0, global_first = 0, level_epoch = 0;
     const void* ptr[24] = {};
     FramePlan plan{};
-    uint32_t flags[14] = {};
+    uint32_t flags[16] = {};
     uint32_t vp_bits[17] = {};  // has_vp, then the 16 matrix entries
     bool operator==(const FrameSig& o) const {
         return memcmp(vp_bits, o.vp_bits, sizeof(vp_bits)) == 0 && n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
@@ -68,6 +68,7 @@ RowView make_row_view(float4* mem, uint64_t cap, bool interleaved) {
 struct tb_ctx {
     int device = 0;
     int sm_count = 148;
+    int libm_fma = 1;  // which build of sinf / cosf the host libm uses (mirrored in the device's c_libm_fma)
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t cap = 0, n = 0;
     std::string err;
@@ -286,6 +287,27 @@ void prof_clear(tb_ctx* c) {
     c->prof_totals.clear();
 }
 
+// Makes the context's device current for the duration of one C-ABI call and restores the caller's afterwards: a
+// process may hold one context per GPU, or call from a thread whose current device is another one.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (device < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define TB_ENTER(c) DeviceGuard device_guard__((c) ? (c)->device : -1)
+
 // Device scratch that lives for one call.
 struct DeviceTemp {
     void* p = nullptr;
@@ -357,6 +379,10 @@ tb_status flush_integrate(tb_ctx* c) {
               mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, c->pending_ticks, (uint32_t)c->n);
     c->world_valid = false;
     c->frame_valid = false;
+    // the rows moved outside a frame: every frame kind that runs WITHOUT a key pass of its own (hierarchy replay,
+    // draw-ordered copy, single-kernel frames placed by cached tile offsets) needs one clean key pass first
+    c->fast_clean = c->seq_valid = false;
+    c->static_valid = false;
     return TB_OK;
 }
 
@@ -969,7 +995,8 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
                               fm.lt_hist ? 1u : 0u, (uint32_t)c->staged_emit, (uint32_t)c->small_emit, c->nlevels,
                               c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
                               (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0), c->sorted_valid ? 1u : 0u,
-                              (c->sorted_valid && c->final_valid) ? 1u : 0u};
+                              (c->sorted_valid && c->final_valid) ? 1u : 0u, (uint32_t)c->sorted_cache,
+                              (uint32_t)c->static_buckets};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
     g.vp_bits[0] = c->has_vp ? 1u : 0u;
@@ -1112,6 +1139,42 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     return TB_OK;
 }
 
+struct MathArg {
+    const void* in;   // host input (nullptr: this slot is an output)
+    void* out;        // host output
+    size_t elem;      // bytes per element
+};
+// Runs `launch(device pointers, first element, count)` over n elements in chunks: inputs host -> device, outputs
+// device -> host, all on the context's stream.
+template <typename Launch>
+tb_status math_batch(tb_ctx* c, uint64_t n, const MathArg* args, int nargs, Launch launch) {
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    for (int k = 0; k < nargs; ++k)
+        if (!args[k].in && !args[k].out) return fail(c, TB_ERR_INVALID, "null pointer");
+    const uint64_t per = 1u << 20;
+    const uint64_t m0 = std::min<uint64_t>(n, per);
+    DeviceTemp mem[8];
+    void* d[8] = {};
+    for (int k = 0; k < nargs; ++k) {
+        TB_CUDA(c, mem[k].alloc(m0 * args[k].elem));
+        d[k] = mem[k].p;
+    }
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint64_t m = std::min<uint64_t>(per, n - off);
+        for (int k = 0; k < nargs; ++k)
+            if (args[k].in)
+                TB_CUDA(c, cudaMemcpyAsync(d[k], (const char*)args[k].in + off * args[k].elem, m * args[k].elem, cudaMemcpyHostToDevice, c->stream));
+        launch(d, (uint32_t)m);
+        for (int k = 0; k < nargs; ++k)
+            if (!args[k].in)
+                TB_CUDA(c, cudaMemcpyAsync((char*)args[k].out + off * args[k].elem, d[k], m * args[k].elem, cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(c, e, "tuber-math batch");
+    return TB_OK;
+}
 }  // namespace
 
 // =================================================================================================
@@ -1152,7 +1215,11 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TB_ERR_NO_DEVICE;
     if (prop.major != 10) return TB_ERR_NO_DEVICE;  // the only code in this library is sm_100a
-    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    DeviceGuard device_guard__(device);  // the caller's current device is restored on return
+    {
+        int now = -1;
+        if (cudaGetDevice(&now) != cudaSuccess || now != device) return TB_ERR_NO_DEVICE;
+    }
     tb_ctx* c = new (std::nothrow) tb_ctx();
     if (!c) return TB_ERR_OOM;
     c->device = device;
@@ -1171,6 +1238,18 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
         return TB_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    {
+        // the reference's sin / cos are the host libm's; glibc picks its FMA build exactly when the CPU has FMA and
+        // AVX2 (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h) and the device evaluates the same build (libm_sincosf.h)
+        __builtin_cpu_init();
+        int fma = (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
+        if (const char* v = getenv("TB_LIBM_FMA")) fma = atoi(v) != 0;
+        c->libm_fma = fma;
+        if (cudaMemcpyToSymbol(c_libm_fma, &fma, sizeof(int)) != cudaSuccess) {
+            tb_ctx_destroy(c);
+            return TB_ERR_CUDA;
+        }
+    }
     const size_t words = (max_entities + 63) / 64;
     bool ok = cudaMalloc((void**)&c->rows_mem, max_entities * 64) == cudaSuccess;
     for (int k = 0; ok && k < TB_COMPONENT_COUNT; ++k) {
@@ -1212,7 +1291,7 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
 
 void tb_ctx_destroy(tb_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    TB_ENTER(c);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     prof_clear(c);
     cudaFree(c->rows_mem);
@@ -1251,6 +1330,7 @@ void tb_ctx_destroy(tb_ctx* c) {
 const char* tb_last_error(tb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
 tb_status tb_ctx_set_stream(tb_ctx* c, void* cuda_stream) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     cudaStreamSynchronize(c->stream);
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
@@ -1258,6 +1338,7 @@ tb_status tb_ctx_set_stream(tb_ctx* c, void* cuda_stream) {
 }
 
 tb_status tb_ctx_synchronize(tb_ctx* c) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
@@ -1270,6 +1351,7 @@ tb_status tb_ctx_set_max_batches(tb_ctx* c, uint64_t max_batches) {
 }
 
 tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
+    TB_ENTER(c);
     if (!c || !name) return TB_ERR_INVALID;
     std::string k(name);
     if (k == "interleaved_rows") {
@@ -1293,7 +1375,7 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         drop_kept_frames(c);
     } else if (k == "sorted_cache") {
         c->sorted_cache = value != 0;
-        c->sorted_valid = false;
+        c->sorted_valid = c->final_valid = c->seq_valid = false;
     } else if (k == "cuda_graphs") {
         c->use_graphs = value != 0;
         c->frame_graph_valid = false;
@@ -1309,6 +1391,8 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     } else {
         return fail(c, TB_ERR_INVALID, "unknown option " + k);
     }
+    // a captured frame graph bakes in what the options selected (which kernels, which optional outputs)
+    c->frame_graph_valid = c->frame_graph_seen = false;
     return TB_OK;
 }
 
@@ -1329,6 +1413,7 @@ void tb_host_free(void* p) {
 // ---- storage ------------------------------------------------------------------------------------
 
 tb_status tb_set_entity_count(tb_ctx* c, uint64_t n) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     if (n > c->cap) return fail(c, TB_ERR_CAPACITY, "entity_count beyond max_entities");
     tb_status s = flush_integrate(c);
@@ -1367,6 +1452,7 @@ static tb_status upload_chunks(tb_ctx* c, const void* src, uint64_t n, size_t el
 }
 
 tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_transform* src) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, src);
     if (s || n == 0) return s;
     if ((s = flush_integrate(c))) return s;
@@ -1393,6 +1479,7 @@ tb_status tb_upload_transforms(tb_ctx* c, uint64_t first, uint64_t n, const tb_t
 }
 
 tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_sprite* src) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, src);
     if (s || n == 0) return s;
     c->rows_touched = true;
@@ -1422,6 +1509,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
 }
 
 tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_velocity* src) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, src);
     if (s || n == 0) return s;
     if ((s = flush_integrate(c))) return s;
@@ -1437,6 +1525,7 @@ tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_v
 }
 
 tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_t* src) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, src);
     if (s || n == 0) return s;
     if (!c->parent) {
@@ -1460,6 +1549,7 @@ tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_
 }
 
 tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t nwords, const uint64_t* words) {
+    TB_ENTER(c);
     if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
     if (nwords == 0) return TB_OK;
     if (!words) return fail(c, TB_ERR_INVALID, "null pointer");
@@ -1477,6 +1567,7 @@ tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t 
 }
 
 tb_status tb_download_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t nwords, uint64_t* words) {
+    TB_ENTER(c);
     if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
     if (nwords == 0) return TB_OK;
     if (!words) return fail(c, TB_ERR_INVALID, "null pointer");
@@ -1487,6 +1578,7 @@ tb_status tb_download_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_
 }
 
 tb_status tb_download_transforms(tb_ctx* c, uint64_t first, uint64_t n, tb_transform* dst) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, dst);
     if (s || n == 0) return s;
     if ((s = flush_integrate(c))) return s;
@@ -1505,6 +1597,7 @@ tb_status tb_download_transforms(tb_ctx* c, uint64_t first, uint64_t n, tb_trans
 // ---- query ----------------------------------------------------------------------------------------
 
 tb_status tb_query(tb_ctx* c, uint32_t required, uint32_t* out_indices, uint64_t cap, uint64_t* count) {
+    TB_ENTER(c);
     if (!c || !count) return TB_ERR_INVALID;
     *count = 0;
     if (required >> TB_COMPONENT_COUNT) return fail(c, TB_ERR_INVALID, "unknown component bit");
@@ -1541,6 +1634,7 @@ tb_status tb_query(tb_ctx* c, uint32_t required, uint32_t* out_indices, uint64_t
 // ---- compose ----------------------------------------------------------------------------------------
 
 tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* dst16) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     if (n == 0) return TB_OK;
     if (!src || !dst16) return fail(c, TB_ERR_INVALID, "null pointer");
@@ -1568,9 +1662,77 @@ tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* d
     return TB_OK;
 }
 
+// ---- the rest of tuber-math, batched (mathops.cuh) -------------------------------------------------------
+
+tb_status tb_quat_from_euler(tb_ctx* c, const float* euler_xyz, uint64_t n, float* wxyz) {
+    TB_ENTER(c);
+    const MathArg a[] = {{euler_xyz, nullptr, 12}, {nullptr, wxyz, 16}};
+    return math_batch(c, n, a, 2, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "quat_from_euler", m * 28ull, quat_from_euler_kernel, div_up(m, kThreads), kThreads, 0, (const float*)d[0], m, (float4*)d[1]);
+    });
+}
+
+tb_status tb_quat_from_axis_angle(tb_ctx* c, const float* axis_angle4, uint64_t n, float* wxyz) {
+    TB_ENTER(c);
+    const MathArg a[] = {{axis_angle4, nullptr, 16}, {nullptr, wxyz, 16}};
+    return math_batch(c, n, a, 2, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "quat_from_axis_angle", m * 32ull, quat_from_axis_angle_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], m, (float4*)d[1]);
+    });
+}
+
+tb_status tb_quat_rotation_matrix(tb_ctx* c, const float* wxyz, uint64_t n, float* m16) {
+    TB_ENTER(c);
+    const MathArg a[] = {{wxyz, nullptr, 16}, {nullptr, m16, 64}};
+    return math_batch(c, n, a, 2, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "quat_rotation_matrix", m * 80ull, quat_rotation_matrix_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], m, (float4*)d[1]);
+    });
+}
+
+tb_status tb_quat_mul(tb_ctx* c, const float* a_wxyz, const float* b_wxyz, uint64_t n, float* out_wxyz) {
+    TB_ENTER(c);
+    const MathArg a[] = {{a_wxyz, nullptr, 16}, {b_wxyz, nullptr, 16}, {nullptr, out_wxyz, 16}};
+    return math_batch(c, n, a, 3, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "quat_mul", m * 48ull, quat_mul_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], (const float4*)d[1], m, (float4*)d[2]);
+    });
+}
+
+tb_status tb_quat_normalize(tb_ctx* c, const float* wxyz, uint64_t n, float* out_wxyz) {
+    TB_ENTER(c);
+    const MathArg a[] = {{wxyz, nullptr, 16}, {nullptr, out_wxyz, 16}};
+    return math_batch(c, n, a, 2, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "quat_normalize", m * 32ull, quat_normalize_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], m, (float4*)d[1]);
+    });
+}
+
+tb_status tb_mat4_mul(tb_ctx* c, const float* a16, const float* b16, uint64_t n, float* out16) {
+    TB_ENTER(c);
+    const MathArg a[] = {{a16, nullptr, 64}, {b16, nullptr, 64}, {nullptr, out16, 64}};
+    return math_batch(c, n, a, 3, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "mat4_mul", m * 192ull, mat4_mul_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], (const float4*)d[1], m, (float4*)d[2]);
+    });
+}
+
+tb_status tb_mat4_transform_vec3(tb_ctx* c, const float* m16, const float* v3, uint64_t n, float* out3) {
+    TB_ENTER(c);
+    const MathArg a[] = {{m16, nullptr, 64}, {v3, nullptr, 12}, {nullptr, out3, 12}};
+    return math_batch(c, n, a, 3, [&](void** d, uint32_t m) {
+        TB_LAUNCH(c, "mat4_transform_vec3", m * 88ull, mat4_transform_vec3_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], (const float*)d[1], m, (float*)d[2]);
+    });
+}
+
+tb_status tb_mat4_try_inverse(tb_ctx* c, const float* m16, uint64_t n, float* out16, uint8_t* some) {
+    TB_ENTER(c);
+    const MathArg a[] = {{m16, nullptr, 64}, {nullptr, out16, 64}, {nullptr, some, 1}};
+    return math_batch(c, n, a, 3, [&](void** d, uint32_t m) {
+        cudaMemsetAsync(d[1], 0, (size_t)m * 64, c->stream);  // None: the output matrix reads as zeros
+        TB_LAUNCH(c, "mat4_try_inverse", m * 129ull, mat4_try_inverse_kernel, div_up(m, kThreads), kThreads, 0, (const float4*)d[0], m, (float4*)d[1], (uint8_t*)d[2]);
+    });
+}
+
 // ---- systems ------------------------------------------------------------------------------------------
 
 tb_status tb_system_integrate(tb_ctx* c, float dt) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     // several ticks of the same dt between two frames (a 100 Hz update loop under a 60 Hz render loop,
     // tuber-winit/src/lib.rs:117-141) run as ONE pass over the rows, each tick rounded on its own
@@ -1623,6 +1785,7 @@ tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
 }
 
 tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
+    TB_ENTER(c);
     if (!c || !out) return TB_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     c->frame_launches = 0;
@@ -1875,6 +2038,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
 // ---- multi-GPU frame -------------------------------------------------------------------------------------
 
 tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
+    TB_ENTER(c);
     if (!c || !stats) return TB_ERR_INVALID;
     stats[0] = 0;
     stats[1] = ~0ull;
@@ -1933,6 +2097,7 @@ tb_status tb_shard_plan(tb_ctx* c, const uint64_t g[3], uint64_t* nbins) {
 }
 
 tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
+    TB_ENTER(c);
     if (!c || !d_hist) return TB_ERR_INVALID;
     if (c->shard_state != 2) return fail(c, TB_ERR_INVALID, "tb_shard_key_histogram follows tb_shard_plan");
     const FramePlan& plan = c->plan;
@@ -1956,6 +2121,7 @@ tb_status tb_shard_key_histogram(tb_ctx* c, void* d_hist) {
 }
 
 tb_status tb_shard_place(tb_ctx* c, const void* d_all_hists, uint64_t* global_instances) {
+    TB_ENTER(c);
     if (!c || !d_all_hists) return TB_ERR_INVALID;
     if (c->shard_state != 3) return fail(c, TB_ERR_INVALID, "tb_shard_place follows tb_shard_key_histogram");
     const FramePlan& plan = c->plan;
@@ -2038,7 +2204,7 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
 tb_status tb_device_alloc(int device, uint64_t bytes, void** d_ptr) {
     if (!d_ptr || bytes == 0) return TB_ERR_INVALID;
     *d_ptr = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    DeviceGuard device_guard__(device);
     if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
         cudaGetLastError();
         return TB_ERR_OOM;
@@ -2060,7 +2226,7 @@ tb_status tb_ipc_export(void* d_ptr, uint8_t handle[TB_IPC_HANDLE_BYTES]) {
 tb_status tb_ipc_open(int device, const uint8_t handle[TB_IPC_HANDLE_BYTES], void** d_ptr) {
     if (!d_ptr || !handle) return TB_ERR_INVALID;
     *d_ptr = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess) return TB_ERR_NO_DEVICE;
+    DeviceGuard device_guard__(device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof(h));
     if (cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -2071,6 +2237,7 @@ tb_status tb_ipc_open(int device, const uint8_t handle[TB_IPC_HANDLE_BYTES], voi
 }
 tb_status tb_ipc_close(void* d_ptr) { return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? TB_OK : TB_ERR_COMM; }
 tb_status tb_device_read(tb_ctx* c, const void* d_src, uint64_t bytes, void* dst) {
+    TB_ENTER(c);
     if (!c || !d_src || !dst) return TB_ERR_INVALID;
     TB_CUDA(c, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -2089,24 +2256,29 @@ static tb_status download(tb_ctx* c, const void* d_src, uint64_t first, uint64_t
 }
 
 tb_status tb_download_instances(tb_ctx* c, uint64_t first, uint64_t n, tb_instance* dst) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     return download(c, c->ext_inst ? c->ext_inst : (void*)c->inst, first, n, c->last_instances, sizeof(tb_instance), dst);
 }
 tb_status tb_download_vertices(tb_ctx* c, uint64_t first, uint64_t n, tb_quad_vertex* dst) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     if (c->ext_inst && !c->ext_vtx) return fail(c, TB_ERR_INVALID, "this context does not emit vertices");
     return download(c, c->ext_inst ? c->ext_vtx : (void*)c->vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
 }
 tb_status tb_download_batches(tb_ctx* c, uint64_t first, uint64_t n, tb_batch* dst) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     return download(c, c->batches, first, n, c->last_batches, sizeof(tb_batch), dst);
 }
 tb_status tb_download_order(tb_ctx* c, uint64_t first, uint64_t n, uint32_t* dst) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     return download(c, c->ext_order ? c->ext_order : (void*)c->order, first, n, c->last_instances, 4, dst);
 }
 
 tb_status tb_download_world_matrices(tb_ctx* c, uint64_t first, uint64_t n, float* dst16) {
+    TB_ENTER(c);
     tb_status s = check_range(c, first, n, dst16);
     if (s || n == 0) return s;
     if ((s = flush_integrate(c))) return s;
@@ -2141,6 +2313,7 @@ tb_status tb_download_world_matrices(tb_ctx* c, uint64_t first, uint64_t n, floa
 // ---- instrumentation ----------------------------------------------------------------------------------------
 
 tb_status tb_profile_enable(tb_ctx* c, int on) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     cudaStreamSynchronize(c->stream);
     prof_clear(c);
@@ -2149,6 +2322,7 @@ tb_status tb_profile_enable(tb_ctx* c, int on) {
 }
 
 tb_status tb_profile_count(tb_ctx* c, uint32_t* n) {
+    TB_ENTER(c);
     if (!c || !n) return TB_ERR_INVALID;
     cudaStreamSynchronize(c->stream);
     prof_harvest(c);
@@ -2178,6 +2352,14 @@ tb_status tb_shard_set(tb_ctx* c, int rank, int nranks, uint64_t global_first) {
     if (global_first + c->cap > (1ull << 32)) return fail(c, TB_ERR_INVALID, "global entity ids must fit 32 bits");
     c->rank = rank;
     c->nranks = nranks;
+    if (global_first != c->global_first) {
+        // final_idx / level lists / captured launches hold ids relative to the old range
+        drop_kept_frames(c);
+        c->final_valid = c->seq_valid = c->fast_clean = false;
+        c->plan_valid = false;
+        c->frame_graph_valid = c->frame_graph_seen = false;
+        c->world_valid = false;
+    }
     c->global_first = global_first;
     c->levels_dirty = true;
     c->frame_valid = false;
@@ -2201,6 +2383,7 @@ tb_status tb_frame_set_output(tb_ctx* c, void* d_instances, void* d_vertices, vo
 }
 
 tb_status tb_vertices_from_instances(tb_ctx* c, const void* d_instances, uint64_t first, uint64_t count, void* d_vertices) {
+    TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     if (count == 0) return TB_OK;
     if (!d_instances || !d_vertices) return fail(c, TB_ERR_INVALID, "null pointer");
