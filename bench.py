@@ -125,6 +125,80 @@ def cpu_reference(steps, warmup, n_sample):
                       f"(velocity system + render_scene), {total:.1f} s of CPU time"}, total / len(times)
 
 
+def config_table(capi, scenes, torch, device, peak, steps, which=None):
+    """Every BASELINE config on ONE GPU x what happens between frames, device-resident, CUDA events around `steps`
+    frames after 4 warm-up frames (every pass streams far more than the L2 holds, except configs[0]):
+      static       nothing touched since the previous frame (e.g. only the camera moves)
+      all_moving   every entity has a velocity in x / y and a tick runs before every frame: all matrices change,
+                   no sort key does (+12 B velocity read, +12 B translation write-back per entity)
+      keys_change  the frame recomputes everything (key pass, sort, emit: sorted_cache = static_buckets = 0), which is
+                   what a frame whose sort keys changed costs; configs[3] also ticks, as its workload says
+    frac = entities x algorithmic bytes / frame time / measured HBM peak."""
+    stream = torch.cuda.current_stream()
+    specs = [
+        ("configs[0]", "10k flat sprites, 1 texture, no hierarchy", scenes.config1, 208),
+        ("configs[1]", "1M flat sprites, 64 textures x 16 layers x 16 depths", scenes.config2, 208),
+        ("configs[2]", "4M-entity scene graph, depth 8: propagation + batching", scenes.config3, 212),
+        ("configs[3]", "16M particles: velocity system + transform + batching", scenes.config4, 232),
+        ("configs[4]", "64M flat sprites (64 textures x 16 layers x 16 depths) on ONE GPU", scenes.config5, 208),
+    ]
+    table = []
+    for name, what, make, alg in specs:
+        if which is not None and name not in which:
+            continue
+        sc = make()
+        native_tick = sc.velocities is not None
+        ctx = capi.Context(sc.n, device=device)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_entity_count(sc.n)
+        ctx.upload_transforms(0, sc.transforms)
+        ctx.upload_sprites(0, sc.sprites)
+        if sc.parents is not None:
+            ctx.upload_parents(0, sc.parents)
+        vel = sc.velocities if native_tick else scenes.config4(n=sc.n_total, first=sc.first, count=sc.n, seed=77).velocities
+        dt = 0.01
+        if native_tick:
+            ctx.upload_velocities(0, vel)
+
+        def run(tick, k):
+            for _ in range(k):
+                if tick:
+                    ctx.system_integrate(dt)
+                info = ctx.frame()
+            return info
+
+        def timed(tick, bytes_per_entity):
+            run(tick, 4)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            info = run(tick, steps)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            assert info.num_instances == sc.n
+            return {"ms_per_frame": ms, "entities_per_s": sc.n / (ms * 1e-3), "algorithmic_bytes_per_entity": bytes_per_entity,
+                    "frac": sc.n * bytes_per_entity / (ms * 1e-3) / 1e9 / peak, "kernels_per_frame": int(info.kernel_launches),
+                    "key_bits": int(info.key_bits), "sort_passes": int(info.sort_passes)}
+
+        base = alg - 24 if native_tick else alg
+        modes = {"static": timed(False, base)}
+        ctx.set_option("sorted_cache", 0)
+        ctx.set_option("static_buckets", 0)
+        modes["keys_change"] = timed(native_tick, alg if native_tick else base)
+        ctx.set_option("sorted_cache", 1)
+        ctx.set_option("static_buckets", 1)
+        if not native_tick:
+            ctx.upload_velocities(0, vel)
+        modes["all_moving"] = timed(True, base + 24)
+        info = ctx.frame()
+        table.append({"config": name, "workload": what, "entities": sc.n, "batches": int(info.num_batches),
+                      "hierarchy_levels": int(info.hierarchy_levels), "modes": modes})
+        ctx.close()
+        del sc, vel
+    return table
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -157,6 +231,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--option", action="append", default=[], help="tb_ctx_set_option name=value")
+    ap.add_argument("--configs", default="all", help="the per-config table at N=1: all | none | comma list, e.g. configs[1],configs[2]")
+    ap.add_argument("--only-configs", action="store_true", help="print just the per-config table (tuning runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -182,6 +258,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.only_configs:
+        which = None if args.configs == "all" else set(args.configs.split(","))
+        print(json.dumps({"configs": config_table(capi, scenes, torch, local_rank, measured_peaks()[0], args.steps, which)}))
+        return 0
     n = args.entities
     first = rank * n
     sc = scenes.config4(n=world * n, first=first, count=n)
@@ -492,10 +572,14 @@ def main():
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_reference(3, 1, CPU_SAMPLE)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
     ctx.close()
     for p in (p_t, p_s, p_v):
         capi.host_free(p)
+    if rank == 0:
+        if world == 1 and args.configs != "none":
+            which = None if args.configs == "all" else set(args.configs.split(","))
+            line["configs"] = config_table(capi, scenes, torch, local_rank, peak, min(args.steps, 20), which)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -22,10 +22,14 @@ __device__ __forceinline__ void ref_sincosf(float a, float* s, float* c) {
 }
 
 // Device row of the (Transform, Sprite) table: four 16-byte chunks per entity.
-//   A0 = {t.x, t.y, t.z, c.z}        A1 = {s.z, angle.x, angle.y, texture | layer << 16}
-//   B0 = {angle.z, c.x, c.y, s.x}    B1 = {s.y, size.w, size.h, 0}
+//   A0 = {t.x, t.y, t.z, c.z}                A1 = {s.z, angle.x, angle.y, texture | layer << 16}
+//   B0 = {sin(angle.z/2), c.x, c.y, s.x}     B1 = {s.y, size.w, size.h, cos(angle.z/2)}
 // A0 is everything the velocity system writes; A0 + A1 everything the sort key of a planar entity
-// needs. Chunk A0 of entity i is t[i * st], A1 is a[i * st], B0 / B1 are b[i * sb] and b[i * sb + 1]
+// needs. The yaw enters Transform::as_matrix4 only through sin / cos of its half (quaternion.rs:39-59), so the row
+// keeps those two values — evaluated ONCE, when the Transform is uploaded (or an angular system changes it), with
+// the host libm's sinf / cosf reproduced bit for bit (libm_sincosf.h) — and the per-frame kernels do no
+// trigonometry at all for entities that rotate about z only (every 2-D sprite). angle.z itself lives in the cold
+// `yaw` array (4 B/entity, read only by downloads and angular systems). Chunk A0 of entity i is t[i * st], A1 is a[i * st], B0 / B1 are b[i * sb] and b[i * sb + 1]
 // (strides in float4 units). Two layouts:
 //   split (start-up): three dense arrays T (16 B/entity), A (16 B), B (32 B), st = 1, sb = 2 — the
 //     velocity system's write-back is a dense 16 B/entity stream and the key pass reads 32 B/entity
@@ -35,6 +39,7 @@ struct RowView {
     float4* a;
     float4* b;
     uint32_t st, sb;
+    float* yaw;  // angle.z per entity (cold)
 };
 
 // The four 16-byte quarters of one row, in registers.
@@ -68,10 +73,9 @@ __device__ __forceinline__ void integrate_ticks(float4& a0, float vx, float vy, 
 // Fast path: angle.x == 0 && angle.y == 0 (every 2-D sprite) needs one sincos instead of
 // three and is value-identical, because x1, x0 and +0 are exact:
 //   w = 1*1*cy + 0*0*sy = cy,  x = 0,  y = 0,  z = 1*1*sy - 0*0*cy = sy.
-__device__ __forceinline__ void rotation3x3(float ax, float ay, float az, float R[9]) {
+// `sy_`, `cy_`: sin / cos of yaw / 2 as the row caches them.
+__device__ __forceinline__ void rotation3x3_yaw(float ax, float ay, float sy_, float cy_, float R[9]) {
     float w, x, y, z;
-    float sy_, cy_;
-    ref_sincosf(mulr(az, 0.5f), &sy_, &cy_);
     if (ax == 0.0f && ay == 0.0f) {
         // 2-D: R = [[1-zz2, -wz2, 0], [wz2, 1-zz2, 0], [0, 0, 1]]
         float z2 = addr(sy_, sy_);
@@ -99,6 +103,17 @@ __device__ __forceinline__ void rotation3x3(float ax, float ay, float az, float 
     R[3] = addr(xy2, wz2);              R[4] = subr(subr(1.0f, xx2), zz2);  R[5] = subr(yz2, wx2);
     R[6] = subr(xz2, wy2);              R[7] = addr(yz2, wx2);              R[8] = subr(subr(1.0f, xx2), yy2);
 }
+__device__ __forceinline__ void rotation3x3(float ax, float ay, float az, float R[9]) {
+    float sy_, cy_;
+    ref_sincosf(mulr(az, 0.5f), &sy_, &cy_);
+    rotation3x3_yaw(ax, ay, sy_, cy_, R);
+}
+// sin / cos of yaw / 2 for the row's B0.x / B1.w slots (upload conversion, angular systems)
+__device__ __forceinline__ float2 yaw_sincos(const float yaw) {
+    float2 sc;
+    ref_sincosf(mulr(yaw, 0.5f), &sc.x, &sc.y);
+    return sc;
+}
 
 // One row j of Transform::as_matrix4 (transform.rs:28-38) in closed form
 // (equivalence with the 4-multiply chain is proven on the CPU in
@@ -122,10 +137,10 @@ __device__ __forceinline__ float4 compose_row(const float* Rj, float sj, float c
 __device__ __forceinline__ Affine compose_local(const Row& r) {
     const float tx = r.a0.x, ty = r.a0.y, tz = r.a0.z, cz = r.a0.w;
     const float sz = r.a1.x, ax = r.a1.y, ay = r.a1.z;
-    const float az = r.b0.x, cx = r.b0.y, cy = r.b0.z, sx = r.b0.w;
+    const float cx = r.b0.y, cy = r.b0.z, sx = r.b0.w;
     const float sy = r.b1.x;
     float R[9];
-    rotation3x3(ax, ay, az, R);
+    rotation3x3_yaw(ax, ay, r.b0.x, r.b1.w, R);
     Affine m;
     m.r0 = compose_row(R + 0, sx, cx, tx, cx, cy, cz);
     m.r1 = compose_row(R + 3, sy, cy, ty, cx, cy, cz);
@@ -150,9 +165,9 @@ __device__ __forceinline__ float planar_z(const float4 a0, const float4 a1) {
 // M[2][3] of any row (general 3-D rotation needs chunks B0 B1 too).
 __device__ __forceinline__ float local_z(const Row& r) {
     const float tz = r.a0.z, cz = r.a0.w, sz = r.a1.x, ax = r.a1.y, ay = r.a1.z;
-    const float az = r.b0.x, cx = r.b0.y, cy = r.b0.z;
+    const float cx = r.b0.y, cy = r.b0.z;
     float R[9];
-    rotation3x3(ax, ay, az, R);
+    rotation3x3_yaw(ax, ay, r.b0.x, r.b1.w, R);
     return compose_row(R + 6, sz, cz, tz, cx, cy, cz).w;
 }
 

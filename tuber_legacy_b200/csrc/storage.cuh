@@ -25,11 +25,13 @@ __global__ void __launch_bounds__(kThreads) convert_transforms_kernel(const floa
     a1[0] = v[11];
     a1[1] = v[3];
     a1[2] = v[4];
-    // B0 = {angle.z, c.x, c.y, s.x}
-    rv.b[e * rv.sb] = make_float4(v[5], v[6], v[7], v[9]);
-    // B1 = {s.y, size.w, size.h, 0}: keep .y .z
+    // B0 = {sin(angle.z / 2), c.x, c.y, s.x}, B1 = {s.y, size.w, size.h, cos(angle.z / 2)}: keep B1 .y .z
+    const float2 sc = yaw_sincos(v[5]);
+    rv.b[e * rv.sb] = make_float4(sc.x, v[6], v[7], v[9]);
     float* b1 = reinterpret_cast<float*>(rv.b + e * rv.sb + 1);
     b1[0] = v[10];
+    b1[3] = sc.y;
+    rv.yaw[e] = v[5];
 }
 
 __global__ void __launch_bounds__(kThreads) convert_sprites_kernel(const uint32_t* __restrict__ src, RowView rv,
@@ -44,7 +46,6 @@ __global__ void __launch_bounds__(kThreads) convert_sprites_kernel(const uint32_
     float* b1 = reinterpret_cast<float*>(rv.b + e * rv.sb + 1);
     b1[1] = __uint_as_float(s.x);
     b1[2] = __uint_as_float(s.y);
-    b1[3] = 0.0f;
 }
 
 // Copies every row from one layout to the other (split arrays <-> one 64-byte row per entity): one
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) unconvert_transforms_kernel(RowView 
     Row r = load_row(rv, first + i);
     float* t = dst + (size_t)i * 12;
     t[0] = r.a0.x; t[1] = r.a0.y; t[2] = r.a0.z;
-    t[3] = r.a1.y; t[4] = r.a1.z; t[5] = r.b0.x;
+    t[3] = r.a1.y; t[4] = r.a1.z; t[5] = rv.yaw[first + i];
     t[6] = r.b0.y; t[7] = r.b0.z; t[8] = r.a0.w;
     t[9] = r.b0.w; t[10] = r.b1.x; t[11] = r.a1.x;
 }

@@ -55,8 +55,9 @@ struct FrameSig {
 };
 
 // View of `cap` rows stored at `mem` (cap x 64 bytes) in either layout (compose.cuh).
-RowView make_row_view(float4* mem, uint64_t cap, bool interleaved) {
+RowView make_row_view(float4* mem, uint64_t cap, bool interleaved, float* yaw) {
     RowView v;
+    v.yaw = yaw;
     v.t = mem;
     v.a = interleaved ? mem + 1 : mem + cap;
     v.b = interleaved ? mem + 2 : mem + 2 * cap;
@@ -78,6 +79,7 @@ struct tb_ctx {
     bool layout_auto = true;  // frames that gather rows in sorted order switch to 64-byte rows on their own
     bool rows_touched = false;
     float4* rows_mem = nullptr;
+    float* yaw_mem = nullptr;  // angle.z per entity (the rows keep sin / cos of its half)
     RowView rows{};
     uint64_t* mask[TB_COMPONENT_COUNT] = {nullptr, nullptr, nullptr, nullptr};
     bool store[TB_COMPONENT_COUNT] = {false, false, false, false};
@@ -717,7 +719,7 @@ tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     } else {
         fresh = c->rows_mem;  // nothing uploaded yet: the rows are all zero in either layout
     }
-    dst = make_row_view(fresh, c->cap, interleaved);
+    dst = make_row_view(fresh, c->cap, interleaved, c->yaw_mem);
     if (c->rows_touched) {
         TB_LAUNCH(c, "relayout_rows", c->cap * 128, relayout_rows_kernel, (uint32_t)div_up(c->cap * 4, (uint64_t)kThreads), kThreads, 0,
                   c->rows, dst, (uint64_t)c->cap);
@@ -1252,6 +1254,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     }
     const size_t words = (max_entities + 63) / 64;
     bool ok = cudaMalloc((void**)&c->rows_mem, max_entities * 64) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&c->yaw_mem, max_entities * 4) == cudaSuccess;
+    if (ok) cudaMemsetAsync(c->yaw_mem, 0, max_entities * 4, c->stream);
     for (int k = 0; ok && k < TB_COMPONENT_COUNT; ++k) {
         // +2 words: the emit kernel copies presence words two at a time (16-byte cp.async)
         ok = cudaMalloc((void**)&c->mask[k], (words + 2) * 8) == cudaSuccess;
@@ -1267,7 +1271,7 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
         return TB_ERR_OOM;
     }
     cudaMemsetAsync(c->rows_mem, 0, max_entities * 64, c->stream);
-    c->rows = make_row_view(c->rows_mem, max_entities, c->interleaved != 0);
+    c->rows = make_row_view(c->rows_mem, max_entities, c->interleaved != 0, c->yaw_mem);
     cudaFuncSetAttribute(emit_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint32_t>));
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
@@ -1295,6 +1299,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     prof_clear(c);
     cudaFree(c->rows_mem);
+    cudaFree(c->yaw_mem);
     for (int k = 0; k < TB_COMPONENT_COUNT; ++k) cudaFree(c->mask[k]);
     cudaFree(c->vel);
     cudaFree(c->parent);
@@ -1641,15 +1646,16 @@ tb_status tb_as_matrix4(tb_ctx* c, const tb_transform* src, uint64_t n, float* d
     // temporary rows + world rows, chunked
     const uint64_t per = 1u << 20;
     const uint64_t m0 = std::min<uint64_t>(n, per);
-    DeviceTemp rows_mem, world_mem, in_mem, out_mem;  // freed on every return path
+    DeviceTemp rows_mem, yaw_mem, world_mem, in_mem, out_mem;  // freed on every return path
     TB_CUDA(c, rows_mem.alloc(m0 * 64));
+    TB_CUDA(c, yaw_mem.alloc(m0 * 4));
     TB_CUDA(c, world_mem.alloc(m0 * 64));
     TB_CUDA(c, in_mem.alloc(m0 * 48));
     TB_CUDA(c, out_mem.alloc(m0 * 64));
     WorldRow* d_world = static_cast<WorldRow*>(world_mem.p);
     float* d_in = static_cast<float*>(in_mem.p);
     float* d_out = static_cast<float*>(out_mem.p);
-    const RowView rv = make_row_view(static_cast<float4*>(rows_mem.p), m0, false);
+    const RowView rv = make_row_view(static_cast<float4*>(rows_mem.p), m0, false, static_cast<float*>(yaw_mem.p));
     for (uint64_t off = 0; off < n; off += per) {
         const uint64_t m = std::min<uint64_t>(per, n - off);
         TB_CUDA(c, cudaMemcpyAsync(d_in, src + off, m * 48, cudaMemcpyHostToDevice, c->stream));
