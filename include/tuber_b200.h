@@ -316,6 +316,30 @@ TB_API tb_status tb_shard_key_histogram(tb_ctx* ctx, void* d_hist /* nbins x u32
 TB_API tb_status tb_shard_place(tb_ctx* ctx, const void* d_all_hists /* nranks x nbins x u32, device */,
                                 uint64_t* global_instances);
 
+/* ---- the same, with the exchanges inside the library ------------------------------
+ *
+ * A host binds two calls: tb_shard_init once, tb_frame_sharded per frame. The collectives run inside the
+ * library on the context's stream, over one of two transports chosen by the id:
+ *   tb_shard_unique_id  NCCL (libnccl.so.2 is opened at run time; a copy the process already loaded is
+ *                       shared): one process per GPU. Rank 0 creates the id and hands the 128 bytes to
+ *                       the other ranks by any means (it is an ncclUniqueId).
+ *   tb_shard_local_id   several contexts of ONE process, one host thread per context (one or several
+ *                       GPUs): rendezvous in host memory, peer copies.
+ * tb_shard_init is collective: every rank calls it with the same id, nranks and root. It also does what
+ * tb_shard_set does, allocates the global draw list on `root` (sum of the ranks' max_entities) and maps it
+ * into every other rank (CUDA IPC between processes). tb_frame_sharded is collective too: every rank's
+ * emit kernel stores its instances and order at their positions of the exact global draw order straight
+ * into root's list; on root `out` describes the whole list (instances, regenerated quad vertices, global
+ * batch table, global order), elsewhere only the counts are meaningful. A rank that fails before an
+ * exchange leaves the others waiting, as with any collective. tb_download_* on root read the global list. */
+#define TB_SHARD_ID_BYTES 128
+TB_API tb_status tb_shard_unique_id(uint8_t id[TB_SHARD_ID_BYTES]);
+TB_API tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]);
+TB_API tb_status tb_shard_init(tb_ctx* ctx, int rank, int nranks, const uint8_t id[TB_SHARD_ID_BYTES],
+                               uint64_t global_first, int root);
+TB_API tb_status tb_frame_sharded(tb_ctx* ctx, tb_frame_out* out);
+TB_API tb_status tb_shard_finalize(tb_ctx* ctx);
+
 /* Raw device buffers that can be shared with other processes of the node (CUDA IPC). */
 #define TB_IPC_HANDLE_BYTES 64
 TB_API tb_status tb_device_alloc(int device, uint64_t bytes, void** d_ptr);

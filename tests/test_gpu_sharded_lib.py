@@ -1,0 +1,125 @@
+"""The library-owned multi-GPU frame (tb_shard_init / tb_frame_sharded): exchanges inside the library.
+
+* local transport: N contexts of this process, one thread each, all on cuda:0 — the whole protocol (statistics and
+  histogram all-gathers, list mapping, barrier, direct stores into the presenting rank's list, vertex regeneration)
+  against the single-process oracle frame. Runs on a single-GPU box.
+* NCCL transport: one process per GPU (tests/helpers/shard_worker.py), world = min(4, device_count); the presenting
+  rank's global order / instances / vertices / batch table are compared byte for byte with a single-context frame of
+  the whole scene. Needs >= 2 GPUs (NCCL refuses two ranks on one device); with one GPU the same code path still runs
+  with world = 1."""
+import json
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from tuber_legacy_b200 import capi, scenes
+
+import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_local(full, nranks, ticks=0, frames=1, root=0, devices=None):
+    """`full`: the whole scene. Returns the presenting rank's frame of the last of `frames` frames."""
+    sid = capi.shard_local_id()
+    results, errors = [None] * nranks, []
+
+    def worker(rank):
+        try:
+            first, count = scenes.shard_range(full.n, rank, nranks)
+            ctx = capi.Context(max(count, 1), device=(devices[rank] if devices else 0))
+            ctx.shard_init(rank, nranks, sid, first, root)
+            ctx.set_entity_count(count)
+            if count:
+                ctx.upload_transforms(0, full.transforms[first:first + count])
+                ctx.upload_sprites(0, full.sprites[first:first + count])
+                if full.velocities is not None:
+                    ctx.upload_velocities(0, full.velocities[first:first + count])
+            for _ in range(frames):
+                for _ in range(ticks):
+                    ctx.system_integrate(0.01)
+                info = ctx.frame_sharded()
+            if rank == root:
+                class G:
+                    pass
+                g = G()
+                g.info = info
+                m, b = info.num_instances, info.num_batches
+                g.order = ctx.download_order(m)
+                g.instances = ctx.download_instances(m)
+                g.vertices = ctx.download_vertices(m)
+                g.batches = ctx.download_batches(b)
+                results[rank] = g
+            ctx.shard_finalize()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    return results[root]
+
+
+@pytest.mark.parametrize("nranks,root", [(1, 0), (2, 0), (3, 2), (8, 0)])
+def test_sharded_frame_over_the_local_transport_matches_the_oracle(nranks, root):
+    sc = scenes.config2(n=90_001, seed=51)
+    g = run_local(sc, nranks, root=root)
+    r = util.make_oracle(sc).frame()
+    util.assert_frame_parity(g, r, what=f"tb_frame_sharded, local transport, {nranks} ranks")
+
+
+def test_sharded_particles_tick_and_steady_frames():
+    sc = scenes.config4(n=70_000, seed=52)
+    ref = util.make_oracle(sc)
+    for _ in range(3):
+        ref.step(0.01)
+    g = run_local(sc, 4, ticks=1, frames=3)
+    util.assert_frame_parity(g, ref.frame(), what="tb_frame_sharded, particles, third frame")
+
+
+def test_sharded_empty_ranks_and_wide_keys():
+    sc = scenes.config2(n=5, seed=53)          # fewer entities than ranks: some shards are empty
+    g = run_local(sc, 8)
+    util.assert_frame_parity(g, util.make_oracle(sc).frame())
+    wide = scenes.config2(n=20_000, seed=54, z_mode="random")
+    sid = capi.shard_local_id()
+    with capi.Context(wide.n) as ctx:
+        ctx.shard_init(0, 1, sid, 0, 0)
+        ctx.set_entity_count(wide.n)
+        ctx.upload_transforms(0, wide.transforms)
+        ctx.upload_sprites(0, wide.sprites)
+        with pytest.raises(capi.TuberError) as e:
+            ctx.frame_sharded()
+        assert e.value.status == capi.TB_ERR_UNSUPPORTED  # refused, never approximated
+
+
+@pytest.mark.parametrize("kind", ["config2", "config4"])
+def test_nccl_multiprocess_list_equals_single_context_frame(kind):
+    import torch
+    world = min(4, torch.cuda.device_count())
+    n = 300_000
+    out = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp"
+    id_file = os.path.join("/tmp", f"shard_id_{os.getpid()}_{kind}.bin")
+    if os.path.exists(id_file):
+        os.remove(id_file)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "helpers", "shard_worker.py"), str(r), str(world),
+                               str(n), id_file, kind], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert res["world"] == world and res["instances"] == n
+    assert res["order_equal"] and res["instances_equal"] and res["vertices_equal"] and res["batches_equal"], res
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", f"nccl_parity_world{world}_{kind}.json"), "w") as f:
+            json.dump(res, f)

@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtuber_b200.so")
 
 SOURCES = ["tuber_b200.cu"]
-HEADERS = ["kernels.cuh", "common.cuh", "storage.cuh", "prepare.cuh", "placement.cuh", "emit.cuh", "shard.cuh", "mathops.cuh",
+HEADERS = ["kernels.cuh", "common.cuh", "storage.cuh", "prepare.cuh", "placement.cuh", "emit.cuh", "shard.cuh", "mathops.cuh", "comm.h",
            "compose.cuh", "libm_sincosf.h", "plan.h", os.path.join("..", "..", "include", "tuber_b200.h")]
 
 NVCC_FLAGS = [
@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "--fmad=false",          # parity: rustc never contracts a*b+c; the kernels also use __fmul_rn/__fadd_rn
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall",
     "-shared", "-cudart", "static",
+    "-ldl",                  # NCCL is opened at run time (comm.h), not linked
 ]
 
 

@@ -103,6 +103,11 @@ _SIGNATURES = {
     "tb_shard_plan": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tb_shard_key_histogram": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "tb_shard_place": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_shard_unique_id": (C.c_int32, [C.c_void_p]),
+    "tb_shard_local_id": (C.c_int32, [C.c_void_p]),
+    "tb_shard_init": (C.c_int32, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_int]),
+    "tb_frame_sharded": (C.c_int32, [C.c_void_p, C.POINTER(FrameOut)]),
+    "tb_shard_finalize": (C.c_int32, [C.c_void_p]),
     "tb_device_alloc": (C.c_int32, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "tb_device_free": (C.c_int32, [C.c_void_p]),
     "tb_ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
@@ -389,6 +394,20 @@ class Context:
         self._check(self._lib.tb_shard_place(self._h, C.c_void_p(d_all_hists), C.byref(total)))
         return total.value
 
+    def shard_init(self, rank, nranks, shard_id, global_first, root=0):
+        """Collective: joins the exchange group `shard_id` (bytes from shard_unique_id / shard_local_id)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(shard_id))
+        self._check(self._lib.tb_shard_init(self._h, int(rank), int(nranks), buf, int(global_first), int(root)))
+
+    def frame_sharded(self):
+        """Collective: one frame of the sharded scene as one draw list on the presenting rank."""
+        out = FrameOut()
+        self._check(self._lib.tb_frame_sharded(self._h, C.byref(out)))
+        return out
+
+    def shard_finalize(self):
+        self._check(self._lib.tb_shard_finalize(self._h))
+
     def vertices_from_instances(self, d_instances, first, count, d_vertices):
         self._check(self._lib.tb_vertices_from_instances(self._h, C.c_void_p(d_instances), int(first), int(count),
                                                          C.c_void_p(d_vertices)))
@@ -457,3 +476,21 @@ def orthographic(left, right, bottom, top, near, far):
     if load().tb_orthographic(left, right, bottom, top, near, far, _ptr(out)) != 0:
         raise TuberError(1, "tb_orthographic")
     return out.reshape(4, 4)
+
+
+def shard_unique_id():
+    """A new NCCL exchange group id (128 bytes): rank 0 creates it and passes it to the other ranks."""
+    buf = (C.c_uint8 * 128)()
+    st = load().tb_shard_unique_id(buf)
+    if st != TB_OK:
+        raise TuberError(st, "tb_shard_unique_id (is libnccl.so.2 loadable?)")
+    return bytes(buf)
+
+
+def shard_local_id():
+    """A new process-local exchange group id (several contexts of this process, one thread each)."""
+    buf = (C.c_uint8 * 128)()
+    st = load().tb_shard_local_id(buf)
+    if st != TB_OK:
+        raise TuberError(st, "tb_shard_local_id")
+    return bytes(buf)

@@ -13,11 +13,13 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/tuber_b200.h"
+#include "comm.h"
 #include "kernels.cuh"
 
 using namespace tb;
@@ -189,6 +191,21 @@ struct tb_ctx {
     uint32_t* lt_global = nullptr;  // [1 << ltbits]
     uint32_t* place_tmp = nullptr;  // block sums of the placement scans
     size_t remap_cap = 0, lt_global_cap = 0, place_tmp_cap = 0;
+
+    // library-owned multi-GPU frame (tb_shard_init / tb_frame_sharded): the exchange transport, the presenting
+    // rank's draw-list buffers (owned by the root, peer-mapped by everyone else) and small exchange buffers
+    std::unique_ptr<Comm> comm;
+    int list_root = -1;
+    void* list_inst = nullptr;   // [list_cap] tb_instance
+    void* list_vtx = nullptr;    // [list_cap] 4 x tb_quad_vertex (root only)
+    void* list_order = nullptr;  // [list_cap] u32
+    uint64_t list_cap = 0;
+    bool list_ipc = false;       // list_inst / list_order were opened with cudaIpcOpenMemHandle
+    uint64_t* d_xchg = nullptr;  // device: [4] send + [4 * nranks] receive words
+    uint64_t* h_xchg = nullptr;  // pinned mirror
+    uint32_t* shard_hist = nullptr;      // [nbins] this rank's short-key histogram
+    uint32_t* shard_all_hists = nullptr; // [nranks * nbins]
+    size_t shard_hist_cap = 0, shard_all_cap = 0;
 
     // pinned host mirror of the scratch header
     uint64_t* h_hdr = nullptr;
@@ -1186,6 +1203,7 @@ tb_status math_batch(tb_ctx* c, uint64_t n, const MathArg* args, int nargs, Laun
 extern "C" {
 
 static tb_status shard_frame(tb_ctx* c, tb_frame_out* out);
+static tb_status shard_finalize_impl(tb_ctx* c, bool collective);
 
 const char* tb_version(void) { return "tuber_b200 0.1 (sm_100a)"; }
 
@@ -1297,6 +1315,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (!c) return;
     TB_ENTER(c);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    shard_finalize_impl(c, false);
     prof_clear(c);
     cudaFree(c->rows_mem);
     cudaFree(c->yaw_mem);
@@ -2207,6 +2226,193 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     return TB_OK;
 }
 
+// ---- library-owned multi-GPU frame ---------------------------------------------------------------------------------------
+
+tb_status tb_shard_unique_id(uint8_t id[TB_SHARD_ID_BYTES]) {
+    static_assert(TB_SHARD_ID_BYTES == kCommIdBytes, "id size");
+    if (!id) return TB_ERR_INVALID;
+    NcclApi& api = NcclApi::get();
+    if (!api.ok()) return TB_ERR_COMM;
+    ncclUniqueId uid;
+    if (api.GetUniqueId(&uid) != ncclSuccess) return TB_ERR_COMM;
+    memcpy(id, &uid, sizeof(uid));
+    return TB_OK;
+}
+
+tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]) {
+    if (!id) return TB_ERR_INVALID;
+    static std::mutex m;
+    static uint64_t counter = 0;
+    std::lock_guard<std::mutex> lk(m);
+    memset(id, 0, TB_SHARD_ID_BYTES);
+    memcpy(id, kLocalIdMagic, sizeof(kLocalIdMagic));
+    const uint64_t v[2] = {(uint64_t)getpid(), ++counter};
+    memcpy(id + 8, v, sizeof(v));
+    return TB_OK;
+}
+
+namespace {
+struct ListHandles {
+    cudaIpcMemHandle_t inst, order;
+    void* p_inst;
+    void* p_order;
+    uint64_t cap;
+};
+}  // namespace
+
+tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHARD_ID_BYTES], uint64_t global_first, int root) {
+    TB_ENTER(c);
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks || root < 0 || root >= nranks) return TB_ERR_INVALID;
+    tb_status s = tb_shard_finalize(c);
+    if (s) return s;
+    if ((s = tb_shard_set(c, rank, nranks, global_first))) return s;
+    if (memcmp(id, kLocalIdMagic, sizeof(kLocalIdMagic)) == 0) {
+        std::unique_ptr<LocalComm> lc(new LocalComm());
+        if (!lc->init(rank, nranks, id, c->device)) return fail(c, TB_ERR_COMM, lc->err);
+        c->comm = std::move(lc);
+    } else {
+        std::unique_ptr<NcclComm> nc(new NcclComm());
+        if (!nc->init(rank, nranks, id)) return fail(c, TB_ERR_COMM, nc->err);
+        c->comm = std::move(nc);
+    }
+    c->list_root = root;
+    TB_CUDA(c, cudaMalloc((void**)&c->d_xchg, (size_t)(4 + 4 * nranks) * 8 + sizeof(ListHandles)));
+    TB_CUDA(c, cudaMallocHost((void**)&c->h_xchg, (size_t)(4 + 4 * nranks) * 8 + sizeof(ListHandles)));
+    // capacity of the global draw list = sum of the ranks' capacities
+    c->h_xchg[0] = c->cap;
+    TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 8, cudaMemcpyHostToDevice, c->stream));
+    if (!c->comm->all_gather(c->d_xchg, c->d_xchg + 4, 8, c->stream)) return fail(c, TB_ERR_COMM, c->comm->err);
+    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    for (int r = 0; r < nranks; ++r) total += c->h_xchg[4 + r];
+    if (total >= (1ull << 32)) return fail(c, TB_ERR_CAPACITY, "the global draw list must stay below 2^32 instances");
+    // the presenting rank owns the list; everyone else maps it
+    ListHandles* hh = reinterpret_cast<ListHandles*>(c->h_xchg + 4 + 4 * nranks);
+    ListHandles* dh = reinterpret_cast<ListHandles*>(c->d_xchg + 4 + 4 * nranks);
+    memset(hh, 0, sizeof(*hh));
+    if (rank == root) {
+        TB_CUDA(c, cudaMalloc(&c->list_inst, total * 80));
+        TB_CUDA(c, cudaMalloc(&c->list_vtx, total * 64));
+        TB_CUDA(c, cudaMalloc(&c->list_order, total * 4));
+        hh->p_inst = c->list_inst;
+        hh->p_order = c->list_order;
+        hh->cap = total;
+        if (!c->comm->same_process() && nranks > 1) {
+            TB_CUDA(c, cudaIpcGetMemHandle(&hh->inst, c->list_inst));
+            TB_CUDA(c, cudaIpcGetMemHandle(&hh->order, c->list_order));
+        }
+        TB_CUDA(c, cudaMemcpyAsync(dh, hh, sizeof(*hh), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!c->comm->broadcast(dh, sizeof(ListHandles), root, c->stream)) return fail(c, TB_ERR_COMM, c->comm->err);
+    if (rank != root) {
+        TB_CUDA(c, cudaMemcpyAsync(hh, dh, sizeof(*hh), cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->comm->same_process()) {
+            c->list_inst = hh->p_inst;
+            c->list_order = hh->p_order;
+        } else {
+            if (cudaIpcOpenMemHandle(&c->list_inst, hh->inst, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&c->list_order, hh->order, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                c->list_inst = c->list_order = nullptr;
+                return fail(c, TB_ERR_COMM, "cannot map the presenting rank's draw list (CUDA IPC)");
+            }
+            c->list_ipc = true;
+        }
+    }
+    c->list_cap = total;
+    // every rank has mapped the list before the owner could ever free it
+    if (!c->comm->barrier(c->stream)) return fail(c, TB_ERR_COMM, c->comm->err);
+    return TB_OK;
+}
+
+tb_status tb_shard_finalize(tb_ctx* c) { return shard_finalize_impl(c, true); }
+// collective == false (tb_ctx_destroy): no exchange with the other ranks, which may be gone already
+static tb_status shard_finalize_impl(tb_ctx* c, bool collective) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (!c->comm) return TB_OK;
+    cudaStreamSynchronize(c->stream);
+    if (c->ext_inst == c->list_inst) {
+        c->ext_inst = c->ext_vtx = c->ext_order = nullptr;
+        c->ext_cap = 0;
+    }
+    const bool owner = c->rank == c->list_root;
+    if (!owner && c->list_ipc) {
+        if (c->list_inst) cudaIpcCloseMemHandle(c->list_inst);
+        if (c->list_order) cudaIpcCloseMemHandle(c->list_order);
+    }
+    if (collective) c->comm->barrier(c->stream);  // nobody stores into the list any more
+    if (owner) {
+        cudaFree(c->list_inst);
+        cudaFree(c->list_vtx);
+        cudaFree(c->list_order);
+    }
+    c->list_inst = c->list_vtx = c->list_order = nullptr;
+    c->list_cap = 0;
+    c->list_ipc = false;
+    c->list_root = -1;
+    cudaFree(c->d_xchg);
+    if (c->h_xchg) cudaFreeHost(c->h_xchg);
+    c->d_xchg = c->h_xchg = nullptr;
+    cudaFree(c->shard_hist);
+    cudaFree(c->shard_all_hists);
+    c->shard_hist = c->shard_all_hists = nullptr;
+    c->shard_hist_cap = c->shard_all_cap = 0;
+    c->comm.reset();
+    c->frame_valid = false;
+    return TB_OK;
+}
+
+// One frame of a scene sharded over the ranks of tb_shard_init, as ONE draw list in the exact global order on the
+// presenting rank: key statistics -> (all-gather) -> common plan -> short-key histogram -> (all-gather) -> placement
+// -> every rank's emit kernel stores its instances and order at their global positions in the presenter's list ->
+// (barrier) -> the presenter regenerates the quad vertices of the whole list.
+tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
+    TB_ENTER(c);
+    if (!c || !out) return TB_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    if (!c->comm) return fail(c, TB_ERR_INVALID, "tb_frame_sharded follows tb_shard_init");
+    Comm& comm = *c->comm;
+    const int nranks = comm.nranks;
+    tb_status s;
+    uint64_t st[3];
+    if ((s = tb_shard_key_stats(c, st))) return s;
+    memcpy(c->h_xchg, st, sizeof(st));
+    TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 24, cudaMemcpyHostToDevice, c->stream));
+    if (!comm.all_gather(c->d_xchg, c->d_xchg + 4, 24, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 24, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t g[3] = {0, 0, 0};
+    for (int r = 0; r < nranks; ++r) {
+        g[0] |= c->h_xchg[4 + 3 * r];
+        g[1] |= c->h_xchg[4 + 3 * r + 1];
+        g[2] += c->h_xchg[4 + 3 * r + 2];
+    }
+    uint64_t nbins = 0;
+    if ((s = tb_shard_plan(c, g, &nbins))) return s;  // identical inputs on every rank: they fail or pass together
+    if ((s = grow(c, &c->shard_hist, &c->shard_hist_cap, (size_t)nbins, 4))) return s;
+    if ((s = grow(c, &c->shard_all_hists, &c->shard_all_cap, (size_t)nbins * nranks, 4))) return s;
+    if ((s = tb_shard_key_histogram(c, c->shard_hist))) return s;
+    if (!comm.all_gather(c->shard_hist, c->shard_all_hists, (size_t)nbins * 4, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    uint64_t total = 0;
+    if ((s = tb_shard_place(c, c->shard_all_hists, &total))) return s;
+    if (total > c->list_cap) return fail(c, TB_ERR_CAPACITY, "more instances than the draw list was sized for");
+    c->ext_inst = c->list_inst;
+    c->ext_vtx = nullptr;  // instances and order cross the link; the presenter regenerates the vertices
+    c->ext_order = c->list_order;
+    c->ext_cap = c->list_cap;
+    if ((s = tb_frame_transform_batch(c, out))) return s;
+    if (!comm.barrier(c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    if (c->rank == c->list_root && total > 0) {
+        if ((s = tb_vertices_from_instances(c, c->list_inst, 0, total, c->list_vtx))) return s;
+        out->d_vertices = (const tb_quad_vertex*)c->list_vtx;
+        out->kernel_launches += 1;
+    }
+    return TB_OK;
+}
+
 tb_status tb_device_alloc(int device, uint64_t bytes, void** d_ptr) {
     if (!d_ptr || bytes == 0) return TB_ERR_INVALID;
     *d_ptr = nullptr;
@@ -2269,6 +2475,8 @@ tb_status tb_download_instances(tb_ctx* c, uint64_t first, uint64_t n, tb_instan
 tb_status tb_download_vertices(tb_ctx* c, uint64_t first, uint64_t n, tb_quad_vertex* dst) {
     TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
+    if (c->comm && c->list_vtx && c->ext_inst == c->list_inst)  // the presenting rank of tb_frame_sharded
+        return download(c, c->list_vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
     if (c->ext_inst && !c->ext_vtx) return fail(c, TB_ERR_INVALID, "this context does not emit vertices");
     return download(c, c->ext_inst ? c->ext_vtx : (void*)c->vtx, first, n, c->last_instances, 4 * sizeof(tb_quad_vertex), dst);
 }
