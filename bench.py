@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--option", action="append", default=[], help="tb_ctx_set_option name=value")
     ap.add_argument("--configs", default="all", help="the per-config table at N=1: all | none | comma list, e.g. configs[1],configs[2]")
+    ap.add_argument("--strong-entities", type=int, default=1 << 26, help="N > 1: total entities of the strong-scaled configs[4] leg")
     ap.add_argument("--only-configs", action="store_true", help="print just the per-config table (tuning runs)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -438,67 +439,127 @@ def main():
     # every rank's emit kernel storing its instances straight into rank 0's buffers over NVLink
     # (CUDA IPC peer mapping): the payload never goes through a collective. Reported next to `value`.
     gather = None
+    strong = None
     if world > 1:
-        from tuber_legacy_b200.shard import CudaShard, ShardedFrame
+        def dev_tensor(ptr, nbytes):
+            class _Dev:
+                pass
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (int(nbytes) // 8,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+            return torch.as_tensor(d, device=torch.device("cuda", local_rank))
+
+        def share_id():
+            box = [capi.shard_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        def timed_sharded(c, tick, steps_):
+            for _ in range(2):
+                if tick:
+                    c.system_integrate(dt)
+                o = c.frame_sharded()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t_ = time.perf_counter()
+            a0.record(stream)
+            for _ in range(steps_):
+                if tick:
+                    c.system_integrate(dt)
+                o = c.frame_sharded()
+            a1.record(stream)
+            barrier()
+            ms_ = max(a0.elapsed_time(a1), (time.perf_counter() - t_) * 1e3) / steps_
+            tt = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0]), o
+
+        method = ("tb_shard_init + tb_frame_sharded: the exchanges run inside the library (NCCL opened by the library: 3-word and "
+                  "short-key-histogram all-gathers, one barrier); every rank's emit kernel stores instances and order at their "
+                  "positions of the exact global draw order straight into rank 0's list over NVLink (CUDA IPC mapping); rank 0 "
+                  "regenerates the quad vertices of the whole list")
+        # (1) weak: the headline workload, 2^24 entities per rank, as ONE draw list on rank 0
         n_total = n * world
-        ptrs = [0, 0, 0]
-        handles = [None]
-        if rank == 0:
-            ptrs = [capi.device_alloc(n_total * 80, local_rank), capi.device_alloc(n_total * 64, local_rank),
-                    capi.device_alloc(n_total * 4, local_rank)]
-            handles = [[capi.ipc_export(p) for p in ptrs]]
-        dist.broadcast_object_list(handles, src=0)
-        if rank != 0:
-            ptrs = [capi.ipc_open(h, local_rank) for h in handles[0]]
-        # only instances + order cross NVLink; the presenter regenerates the quads of the whole list
-        ctx.set_output(ptrs[0], 0, ptrs[2], n_total)
-        drv = ShardedFrame(CudaShard(ctx, torch.device("cuda", local_rank)), rank, world)
-
-        def gather_step():
-            ctx.system_integrate(dt)
-            o, t = drv.step()          # ends with a barrier: every rank's instances are in rank 0's buffer
-            if rank == 0:
-                ctx.vertices_from_instances(ptrs[0], 0, t, ptrs[1])
-            return o, t
-
-        for _ in range(2):
-            gout, gtotal = gather_step()
-        assert gtotal == n_total
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.shard_init(rank, world, share_id(), first, 0)
         gsteps = max(5, args.steps // 2)
-        barrier()
-        tg = time.perf_counter()
-        g0.record(stream)
-        for _ in range(gsteps):
-            gout, gtotal = gather_step()
-        g1.record(stream)
-        barrier()
-        gather_ms = max(g0.elapsed_time(g1), (time.perf_counter() - tg) * 1e3) / gsteps
-        gcheck = None
-        if rank == 0:
-            b = ctx.download_batches(gout.num_batches)
-            assert int(b["count"].sum()) == n_total
-            sample = ctx.device_read(ptrs[2], 4 * 65536, np.uint32)  # head of the global order: texture 0 bucket
-            gcheck = {"batches": int(gout.num_batches), "order_head_sorted_by_id": bool(np.all(np.diff(sample.astype(np.int64)) > 0))}
-        gt = torch.tensor([gather_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gather_ms = float(gt[0])
+        gather_ms, gout = timed_sharded(ctx, True, gsteps)
+        assert gout.num_instances == n_total
         remote_bytes = (world - 1) * n * (80 + 4)
         gather = {"value": n_total / (gather_ms * 1e-3), "unit": UNIT, "ms_per_step": gather_ms, "steps": gsteps,
                   "global_instances": n_total, "bytes_into_rank0_per_step": remote_bytes,
-                  "rank0_ingress_GBps": remote_bytes / (gather_ms * 1e-3) / 1e9,
-                  "method": "histogram placement + P2P stores of instances and order from the emit kernel into rank 0 "
-                            "(CUDA IPC), 2 small NCCL all-gathers per frame (3 words, 1<<key_bits counters); rank 0 "
-                            "regenerates the quad vertices of the whole list from the instances", "check": gcheck}
-        ctx.set_output(0, 0, 0, 0)
-        dist.barrier()
-        if rank != 0:
-            for p_ in ptrs:
-                capi.ipc_close(p_)
-        dist.barrier()
+                  "rank0_ingress_GBps": remote_bytes / (gather_ms * 1e-3) / 1e9, "scaling": "weak", "method": method}
+        ctx.shard_finalize()
+
+        # (2) strong: configs[4] as BASELINE names it — 2^26 entities in total, id-range-partitioned over the ranks
+        n5 = args.strong_entities
+        f5, c5 = scenes.shard_range(n5, rank, world)
+        s5 = scenes.config5(n=n5, first=f5, count=c5)
+        c5x = capi.Context(c5, device=local_rank)
+        c5x.set_stream(stream.cuda_stream)
+        c5x.shard_init(rank, world, share_id(), f5, 0)
+        c5x.set_entity_count(c5)
+        c5x.upload_transforms(0, s5.transforms)
+        c5x.upload_sprites(0, s5.sprites)
+        del s5
+
+        def timed_local(k):
+            for _ in range(3):
+                o = c5x.frame()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a0.record(stream)
+            for _ in range(k):
+                o = c5x.frame()
+            a1.record(stream)
+            barrier()
+            tt = torch.tensor([a0.elapsed_time(a1) / k], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0]), o
+
+        c5x.set_output(0, 0, 0, 0)
+        static_ms, _ = timed_local(gsteps)                      # every rank frames its own shard, nothing exchanged
+        c5x.set_option("sorted_cache", 0)
+        c5x.set_option("static_buckets", 0)
+        full_ms, _ = timed_local(gsteps)
+        c5x.set_option("sorted_cache", 1)
+        c5x.set_option("static_buckets", 1)
+        list_ms, lout = timed_sharded(c5x, False, gsteps)       # one draw list on rank 0
+        assert lout.num_instances == n5
+        check = None
         if rank == 0:
-            for p_ in ptrs:
-                capi.device_free(p_)
+            # the presenting rank's global list against a single-context frame of the whole scene, byte for byte
+            full = scenes.config5(n=n5)
+            one = capi.Context(n5, device=local_rank)
+            one.set_stream(stream.cuda_stream)
+            one.set_entity_count(n5)
+            one.upload_transforms(0, full.transforms)
+            one.upload_sprites(0, full.sprites)
+            del full
+            oo = one.frame()
+            m5 = int(lout.num_instances)
+            eq = {"order": bool(torch.equal(dev_tensor(lout.d_order, m5 * 4), dev_tensor(oo.d_order, m5 * 4))),
+                  "instances": bool(torch.equal(dev_tensor(lout.d_instances, m5 * 80), dev_tensor(oo.d_instances, m5 * 80))),
+                  "vertices": bool(torch.equal(dev_tensor(lout.d_vertices, m5 * 64), dev_tensor(oo.d_vertices, m5 * 64))),
+                  "batches": bool(int(oo.num_batches) == int(lout.num_batches) and
+                                  c5x.download_batches(lout.num_batches).tobytes() == one.download_batches(oo.num_batches).tobytes())}
+            check = {"equal_to_single_gpu_frame": all(eq.values()), **eq, "compared_on": "device (torch.equal over the raw buffers)"}
+            one.close()
+        dist.barrier()
+        rb5 = (n5 - c5 if rank == 0 else 0)
+        rb5t = torch.tensor([float(rb5)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(rb5t, op=dist.ReduceOp.MAX)
+        remote5 = float(rb5t[0]) * (80 + 4)
+        strong = {"workload": f"configs[4]: {n5} flat sprites in total (64 textures x 16 layers x 16 depths), contiguous id ranges over "
+                              f"{world} GPUs, instance list gathered on rank 0", "scaling": "strong", "entities_total": n5,
+                  "compute_only": {"static": {"ms_per_frame": static_ms, "entities_per_s": n5 / (static_ms * 1e-3)},
+                                   "keys_change": {"ms_per_frame": full_ms, "entities_per_s": n5 / (full_ms * 1e-3)},
+                                   "what": "every rank frames its own shard into its own buffers; max over ranks"},
+                  "list_on_rank0": {"ms_per_frame": list_ms, "entities_per_s": n5 / (list_ms * 1e-3),
+                                    "bytes_into_rank0_per_frame": remote5, "rank0_ingress_GBps": remote5 / (list_ms * 1e-3) / 1e9,
+                                    "what": "end to end, transfer overlapped with the emit: the remote stores ARE the emit kernels' stores; "
+                                            "includes both exchanges, the barrier and the vertex regeneration on rank 0"},
+                  "check": check, "method": method}
+        c5x.shard_finalize()
+        c5x.close()
 
     # ---- reduce over ranks: max time, summed work -------------------------------------------------
     vals = torch.tensor([ms_total, e2e_ms, float(gpu_launches), serial_ms], dtype=torch.float64, device="cuda")
@@ -569,6 +630,8 @@ def main():
             line["full_recompute_every_frame"] = full
         if gather is not None:
             line["gather_to_rank0"] = gather
+        if strong is not None:
+            line["strong_scaling_configs4"] = strong
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_reference(3, 1, CPU_SAMPLE)
             line["cpu_baseline"] = cb

@@ -372,6 +372,10 @@ def test_resharding_and_option_toggles_drop_kept_draw_orders():
     {"cuda_graphs": 0},
     {"z_dictionary": 0},
     {"sorted_cache": 0, "static_buckets": 0, "cuda_graphs": 0, "z_dictionary": 0, "small_emit": 0},
+    {"chunked_sort": 0},
+    {"chunk_shift": 11},
+    {"chunk_shift": 13, "sorted_cache": 0},
+    {"chunk_shift": 12, "cuda_graphs": 0, "z_dictionary": 0},
 ])
 def test_options_do_not_change_results(options):
     for sc in (scenes.config2(n=50_000, seed=14), scenes.config4(n=50_000, seed=15), scenes.config3(n=30_000, seed=16)):
@@ -1186,3 +1190,72 @@ def test_per_frame_uploads_keep_plan_and_sort_when_keys_do_not_change():
         util.assert_frame_parity(g, util.make_oracle(sc).frame())
     assert g.info.kernel_launches == 1
     ctx.close()
+
+
+# ---- chunked sort (csrc/chunked.cuh): many small chunks at test sizes ----------------------------------------------
+
+@pytest.mark.parametrize("shift", [11, 12, 14])
+@pytest.mark.parametrize("kind", ["flat", "flat_sparse", "hierarchy", "hierarchy_random", "textures_only"])
+def test_chunked_sort_matches_the_oracle(kind, shift):
+    masks = None
+    if kind == "flat":
+        sc = scenes.config2(n=70_001, seed=71)
+    elif kind == "flat_sparse":
+        sc = scenes.config2(n=50_000, seed=72)
+        masks = {capi.TB_TRANSFORM: util.random_mask(sc.n, 0.7, 1), capi.TB_SPRITE: util.random_mask(sc.n, 0.5, 2)}
+    elif kind == "hierarchy":
+        sc = scenes.config3(n=60_000, seed=73)
+    elif kind == "hierarchy_random":
+        sc = scenes.config3(n=60_000, seed=74, random_parents=True)
+    else:  # one pass of 6 bits: 64 textures, nothing else varies
+        sc = scenes.config2(n=66_000, seed=75)
+        sc.sprites["layer"][:] = 3
+        sc.transforms["translation"][:, 2] = 2.0
+    ctx, ref, g, r = run_both(sc, masks=masks, chunk_shift=shift)
+    assert g.info.path in (capi.TB_PATH_SORT, capi.TB_PATH_BUCKET)
+    util.assert_frame_parity(g, r, what=f"chunked sort {kind} shift {shift}")
+    for k in range(4):  # kept list: validated single-kernel frames (flat) / key-compare frames (scene graph)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame(), what=f"chunked sort {kind} steady {k}")
+    ctx.close()
+
+
+@pytest.mark.parametrize("shift", [11, 13])
+def test_chunked_sort_moving_entities_and_key_changes(shift):
+    """x / y motion keeps the list (the velocity system runs inside the list emit); a z velocity changes keys: the
+    validation catches it and the frame re-sorts."""
+    sc = scenes.config2(n=60_000, seed=76)
+    v = np.zeros(sc.n, capi.VELOCITY_DTYPE)
+    rng = np.random.default_rng(9)
+    v["v"][:, 0] = rng.uniform(-100, 100, sc.n)
+    v["v"][:, 1] = rng.uniform(-100, 100, sc.n)
+    sc.velocities = v
+    ctx, ref, g, r = run_both(sc, ticks=1, chunk_shift=shift)
+    util.assert_frame_parity(g, r)
+    for k in range(4):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        gf = util.GpuFrame(ctx)
+        util.assert_frame_parity(gf, ref.frame(), what=f"chunked, moving, frame {k}")
+    assert gf.info.kernel_launches == 1  # the steady frame is the list emit alone
+    # now some entities move in z by whole depth steps: keys change
+    v["v"][: sc.n // 3, 2] = 100.0
+    ctx.upload_velocities(0, v)
+    ref.close()
+    ref = util.make_oracle(sc)
+    ctx.upload_transforms(0, sc.transforms)
+    for k in range(3):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame(), what=f"chunked, z velocity, frame {k}")
+    ctx.close()
+
+
+def test_chunked_and_global_sort_emit_the_same_bytes():
+    sc = scenes.config2(n=200_000, seed=77)
+    a = util.make_ctx(sc, chunk_shift=14)
+    b = util.make_ctx(sc, chunked_sort=0)
+    ga, gb = util.GpuFrame(a), util.GpuFrame(b)
+    for f in ("order", "instances", "vertices", "batches"):
+        assert getattr(ga, f).tobytes() == getattr(gb, f).tobytes(), f
+    a.close()
+    b.close()

@@ -8,6 +8,7 @@
 //   placement.cuh  scan_hist, tile_hist, tile_chunk_sums, tile_scan,    reduce-then-scan radix placement,
 //                  rank_tile, radix_scatter, build_batches, batch_*     batch table
 //   emit.cuh       emit_kernel, emit_small_kernel                       last pass fused with compose + emit
+//   chunked.cuh    chunk_place, chunk_tile_scan, emit_list                 sorted frames whose row reads stay in L2
 //   shard.cuh      place_sums, place_write                              multi-GPU global draw order
 //   mathops.cuh    quat_*, mat4_*                                       the rest of tuber-math, batched
 #pragma once
@@ -16,5 +17,6 @@
 #include "prepare.cuh"
 #include "placement.cuh"
 #include "emit.cuh"
+#include "chunked.cuh"
 #include "shard.cuh"
 #include "mathops.cuh"

@@ -89,15 +89,21 @@ __global__ void __launch_bounds__(kThreads) tile_hist_kernel(const KeyT* __restr
                                                               const unsigned long long* count_ptr,
                                                               const uint64_t* mask_t, const uint64_t* mask_s, uint32_t first,
                                                               uint32_t tile_elems, uint32_t shift, uint32_t bits,
-                                                              uint32_t ntiles, uint32_t* counts, const unsigned long long* skip) {
+                                                              uint32_t ntiles, uint32_t* counts, const unsigned long long* skip,
+                                                              const uint32_t* chunk_cnt = nullptr, uint32_t chunk_shift = 0) {
     if (sort_is_cached(skip)) return;
     __shared__ uint32_t h[256];
     const uint32_t R = 1u << bits, mask = R - 1u;
-    const uint32_t n_eff = count_ptr ? min(n, (uint32_t)*count_ptr) : n;
+    uint32_t n_eff = count_ptr ? min(n, (uint32_t)*count_ptr) : n;
+    const uint32_t n_all = n_eff;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {  // persistent blocks: a skipped launch costs ~1000 exits
         for (uint32_t d = threadIdx.x; d < R; d += kThreads) h[d] = 0;
         __syncthreads();
         const uint32_t base = t * tile_elems;
+        if (chunk_cnt != nullptr) {  // chunk-padded list: positions of this tile below the chunk's count hold data
+            const uint32_t c0 = (base >> chunk_shift) << chunk_shift;
+            n_eff = min(n_all, c0 + __ldg(chunk_cnt + (base >> chunk_shift)));
+        }
         for (uint32_t k0 = threadIdx.x; k0 < tile_elems; k0 += 4 * kThreads) {
             KeyT key[4];
             bool valid[4];
@@ -191,7 +197,23 @@ struct PassParams {
     const uint32_t* tile_off;  // [1 << bits][ntiles]: first output position of each (digit, tile), from the
                                // per-tile digit counts (tile_chunk_sums + tile_scan)
     uint32_t ntiles;           // tiles of this pass (row length of tile_off)
+    // chunked sort (chunked.cuh): the pass's input is a list padded per chunk of 1 << chunk_shift entities — chunk c
+    // occupies positions [c << chunk_shift, (c << chunk_shift) + chunk_cnt[c]); nullptr: one dense list
+    const uint32_t* chunk_cnt;
+    uint32_t chunk_shift;
 };
+
+// Elements of tile `tile` (tile_elems positions each) that hold data.
+__device__ __forceinline__ uint32_t pass_tile_count(const PassParams& pp, uint32_t tile, uint32_t tile_elems, uint32_t n_eff) {
+    if (tile >= pp.ntiles) return 0u;
+    const uint32_t base = tile * tile_elems;
+    if (pp.chunk_cnt != nullptr) {
+        const uint32_t local = base & ((1u << pp.chunk_shift) - 1u);
+        const uint32_t cnt = __ldg(pp.chunk_cnt + (base >> pp.chunk_shift));
+        return cnt > local ? min(tile_elems, cnt - local) : 0u;
+    }
+    return base < n_eff ? min(tile_elems, n_eff - base) : 0u;
+}
 
 // Zeroes the per-warp digit counters of the next rank_tile call; a __syncthreads() must
 // separate it from that call.
@@ -281,6 +303,12 @@ struct ScatterParams {
     KeyT* keys_out;
     uint32_t* idx_out;
     const unsigned long long* skip;  // see sort_is_cached
+    // last pass of a chunked sort: idx_out receives GLOBAL entity ids (+ id_offset) and dst_out the position of every
+    // element in the global draw order: (position inside its chunk's sorted list) + remap[chunk][short key]
+    uint32_t* dst_out;
+    const uint32_t* remap;
+    uint32_t key_bits;
+    uint32_t id_offset;
 };
 
 constexpr int kScatterItems = 8;
@@ -316,8 +344,12 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const Scatte
     const uint32_t mask = (1u << sp.pass.bits) - 1u;
     const uint32_t step = gridDim.x;
     auto tile_count = [&](uint32_t tile) -> uint32_t {
-        const uint32_t base = tile * TILE;
-        return (tile < ntiles && base < n_eff) ? min(TILE, n_eff - base) : 0u;
+        // the first pass of a chunked sort reads keys in entity order (dense); later passes the chunk-padded list
+        if (first) {
+            const uint32_t base = tile * TILE;
+            return (tile < ntiles && base < n_eff) ? min(TILE, n_eff - base) : 0u;
+        }
+        return pass_tile_count(sp.pass, tile, TILE, n_eff);
     };
     auto fetch = [&](uint32_t tile, uint32_t buf) {  // thread 0
         const uint32_t base = tile * TILE;
@@ -380,7 +412,13 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const Scatte
             const uint32_t d = (uint32_t)(kk >> sp.pass.shift) & mask;
             const uint32_t dst = rs.dbase[d] + s;
             sp.keys_out[dst] = kk;
-            sp.idx_out[dst] = sm.s_idx[s];
+            if (sp.dst_out != nullptr) {
+                const uint32_t chunk = dst >> sp.pass.chunk_shift;
+                sp.idx_out[dst] = sm.s_idx[s] + sp.id_offset;
+                sp.dst_out[dst] = (dst - (chunk << sp.pass.chunk_shift)) + __ldg(sp.remap + ((size_t)chunk << sp.key_bits) + (uint32_t)kk);
+            } else {
+                sp.idx_out[dst] = sm.s_idx[s];
+            }
         }
         rank_reset(rs, sp.pass.bits);
         __syncthreads();  // releases the input buffer, the sorted tile and the rank scratch

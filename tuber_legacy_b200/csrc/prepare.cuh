@@ -31,6 +31,8 @@ struct PrepParams {
     uint32_t emit_tiles;
     uint32_t emit_tile_shift;  // log2 of pass 0's tile: 6 (warp tiles of 64), 9 (emit tiles of 512), 11 (scatter tiles of 2048)
     uint32_t* key_hist;     // optional [1 << nbits]: histogram over the whole short key (multi-GPU placement)
+    uint32_t* chunk_hist;   // optional [nchunks][1 << nbits]: the same per chunk of 1 << chunk_shift entity ids (chunked.cuh)
+    uint32_t chunk_shift;
     unsigned long long* zset;  // plan discovery: open-addressing set of the distinct orderable z values
     uint32_t* zset_overflow;   // ... set when the scene has more distinct depths than the set is meant for
     FramePlan plan;
@@ -137,6 +139,7 @@ __device__ __forceinline__ void prep_account(const PrepParams& p, PrepShared& sh
         return;
     }
     if (p.key_hist != nullptr) atomicAdd(&p.key_hist[(uint32_t)sk], 1u);
+    if (p.chunk_hist != nullptr) atomicAdd(&p.chunk_hist[((size_t)(i >> p.chunk_shift) << p.plan.pext.nbits) + (uint32_t)sk], 1u);
     for (uint32_t q = 0; q < p.plan.npasses; ++q) {
         const uint32_t d = (uint32_t)(sk >> p.plan.shift[q]) & ((1u << p.plan.bits[q]) - 1u);
         atomicAdd(&sh.hist[q][d], 1u);

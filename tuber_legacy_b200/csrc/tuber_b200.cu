@@ -46,9 +46,9 @@ struct ProfTotal {
 // issue identical launches, so the second can replay the first one's graph.
 struct FrameSig {
     uint64_t n = 0, max_batches = 0, global_first = 0, level_epoch = 0;
-    const void* ptr[24] = {};
+    const void* ptr[26] = {};
     FramePlan plan{};
-    uint32_t flags[16] = {};
+    uint32_t flags[18] = {};
     uint32_t vp_bits[17] = {};  // has_vp, then the 16 matrix entries
     bool operator==(const FrameSig& o) const {
         return memcmp(vp_bits, o.vp_bits, sizeof(vp_bits)) == 0 && n == o.n && max_batches == o.max_batches && global_first == o.global_first && level_epoch == o.level_epoch &&
@@ -136,6 +136,14 @@ struct tb_ctx {
     uint32_t* final_idx = nullptr;   // [n] entity id (global) per draw position
     void* final_keys = nullptr;      // [n] short key per draw position
     bool final_valid = false;
+    // chunked sort (chunked.cuh): final_idx / final_keys are then the chunk-major list (padded per chunk) and final_dst
+    // the destination of every list position in the global draw order
+    uint32_t* final_dst = nullptr;
+    int chunked_sort = 1;            // option
+    int chunk_shift_opt = 0;         // option: log2 of the chunk size (0: chosen from the key width)
+    bool chunked = false;            // the current plan runs as a chunked sort
+    ChunkGeom cg{};
+    size_t chunk_cnt_off = 0, chunk_remap_off = 0;  // where the kept chunk tables live in the scratch buffer
     uint64_t sorted_count = 0, sorted_batches = 0;
     // static scenes (no upload, no tick for a few frames): a copy of the rows (hierarchy: world rows) in draw order,
     // from which frames stream instead of gathering
@@ -415,6 +423,9 @@ struct ScratchLayout {
     size_t csum_off[kMaxPasses];     // per-chunk (1024 tiles) sums [R][chunks]
     bool small = false;              // last pass runs the warp-autonomous few-bucket emit
     size_t total_words = 0, alloc_words = 0;
+    // chunked sort: H[nchunks][K] (zeroed every frame), keytot[K], remap[nchunks][K], chunk_cnt[nchunks]
+    bool chunked = false;
+    size_t H_off = 0, keytot_off = 0, remap_off = 0, cnt_off = 0;
 };
 
 bool use_small_emit(const tb_ctx* c, const FramePlan& plan) {
@@ -424,17 +435,23 @@ bool use_small_emit(const tb_ctx* c, const FramePlan& plan) {
 // Scratch of one frame under a plan: [header | (layer,texture) bins | pass-0 tile counts when the key
 // pass accumulates them] is zeroed every frame; the tile count / offset tables behind it are fully
 // overwritten by tile_hist / tile_scan.
-ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool zero_counts0, bool small = false) {
+ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, bool zero_counts0, bool small = false,
+                             const ChunkGeom* cg = nullptr) {
     ScratchLayout L;
     L.small = small;
+    L.chunked = cg != nullptr;
     size_t off = kHdrWords;
     L.lt_off = off;
     L.lt_words = use_lt ? ((size_t)1 << plan.ltbits) : 0;
     off += L.lt_words;
     for (uint32_t p = 0; p < plan.npasses; ++p) {
         const bool last = p + 1 == plan.npasses;
-        L.tile_elems[p] = last ? (small ? kWarpTile : kEmitTile) : kScatterTile;
-        L.tiles[p] = div_up(n, L.tile_elems[p]);
+        L.tile_elems[p] = cg ? kScatterTile : last ? (small ? kWarpTile : kEmitTile) : kScatterTile;
+        L.tiles[p] = cg ? (uint32_t)(((uint64_t)cg->nchunks << cg->shift) / kScatterTile) : div_up(n, L.tile_elems[p]);
+    }
+    if (cg) {
+        L.H_off = off;
+        off += (size_t)cg->nchunks << cg->nbits;
     }
     if (zero_counts0) {
         // the key pass accumulates pass-0 per-tile counts with REDs: they start from zero
@@ -451,6 +468,14 @@ ScratchLayout layout_scratch(const FramePlan& plan, uint64_t n, bool use_lt, boo
         off += (size_t)L.tiles[p] << plan.bits[p];
         L.csum_off[p] = off;
         off += (size_t)div_up(L.tiles[p], 1024) << plan.bits[p];
+    }
+    if (cg) {
+        L.keytot_off = off;
+        off += (size_t)1 << cg->nbits;
+        L.remap_off = off;
+        off += (size_t)cg->nchunks << cg->nbits;
+        L.cnt_off = off;
+        off += cg->nchunks;
     }
     L.alloc_words = off;
     return L;
@@ -516,14 +541,16 @@ tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
     if (c->ekeys) cudaFree(c->ekeys);
     if (c->final_idx) cudaFree(c->final_idx);
     if (c->final_keys) cudaFree(c->final_keys);
+    if (c->final_dst) cudaFree(c->final_dst);
     c->ekeys = c->final_keys = nullptr;
-    c->final_idx = nullptr;
+    c->final_idx = c->final_dst = nullptr;
     c->sort_cap = 0;
     c->sorted_valid = c->final_valid = false;
     {
         cudaError_t e = cudaMalloc(&c->ekeys, (size_t)n * keybytes + 16);
         if (e == cudaSuccess) e = cudaMalloc((void**)&c->final_idx, (size_t)n * 4 + 16);
         if (e == cudaSuccess) e = cudaMalloc(&c->final_keys, (size_t)n * keybytes + 16);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c->final_dst, (size_t)n * 4 + 16);
         if (e != cudaSuccess) return cuda_fail(c, e, "cudaMalloc(entity keys / draw order)");
     }
     for (int k = 0; k < 2; ++k) {
@@ -806,18 +833,23 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
     }
     if (have_plan) {
         p.plan = c->plan;
-        p.write_keys = c->plan.npasses > 1 || fm.hier;
+        p.write_keys = c->plan.npasses > 1 || fm.hier || L->chunked;
         p.keys_out = c->ekeys;
         p.check_keys = (c->sorted_valid && p.write_keys) ? 1u : 0u;
-        p.lt_mode = fm.lt_hist ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;
+        p.lt_mode = (fm.lt_hist && !L->chunked) ? (c->plan.ltbits <= 11 ? 1u : 2u) : 0u;  // chunked: bins come from H
         p.lt_hist = c->scratch + L->lt_off;
+        if (L->chunked) {
+            p.write_keys = 1u;
+            p.chunk_hist = c->scratch + L->H_off;
+            p.chunk_shift = c->cg.shift;
+        }
         if (!fm.hier) {
             // pass 0 reads the keys in entity order, which is how this pass produces them: it counts
             // pass 0's per-tile digits on the way (no tile_hist launch for that pass)
             static_assert(kWarpTile == 64 && kEmitTile == 512 && kScatterTile == 2 * kThreads * kPrepItems, "tile shifts");
             p.tile_counts = c->scratch + L->counts_off[0];
             p.emit_tiles = L->tiles[0];
-            p.emit_tile_shift = L->small ? 6u : (c->plan.npasses == 1 ? 9u : 11u);
+            p.emit_tile_shift = L->small ? 6u : ((c->plan.npasses == 1 && !L->chunked) ? 9u : 11u);
         }
     }
     const uint64_t bytes_in = (uint64_t)n * (32 + (p.integrate ? 12 + 16 : 0) + (p.write_keys ? (c->plan.key64 ? 8 : 4) : 0));
@@ -972,6 +1004,138 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     return TB_OK;
 }
 
+// The emit over the kept chunk-major list (chunked.cuh). VALIDATE: flat frames without a key pass.
+void fill_list_params(tb_ctx* c, const FrameMode& fm, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, ListParams* out) {
+    ListParams& lp = *out;
+    lp = ListParams{};
+    lp.ids = c->final_idx;
+    lp.dst = c->final_dst;
+    lp.keys = (const uint32_t*)c->final_keys;
+    lp.chunk_cnt = c->scratch + c->chunk_cnt_off;
+    lp.chunk_shift = c->cg.shift;
+    lp.npad = c->cg.nchunks << c->cg.shift;
+    lp.rows = c->rows;
+    lp.world = fm.hier ? c->world : nullptr;
+    lp.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
+    lp.mask_v = mask_or_null(c, TB_VELOCITY);
+    lp.dt = c->pending_dt;
+    lp.integrate = (integrate && lp.vel != nullptr && c->store[TB_TRANSFORM]) ? c->pending_ticks : 0u;
+    lp.instances = d_inst;
+    lp.vertices = d_vtx;
+    lp.order = d_order;
+    lp.global_first = (uint32_t)c->global_first;
+    lp.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    lp.plan = c->plan;
+    set_camera(c, &lp);
+}
+
+// Steps 2-4 of a chunked sorted frame (chunked.cuh) after the key pass: batch bins and run starts from H, the
+// per-chunk LSD passes (all chunks in one launch; every sort kernel returns at once when the key pass found no changed
+// key), then the emit over the chunk-major list.
+tb_status run_chunked_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, bool prepare_made_counts,
+                                    float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+    const uint32_t n = (uint32_t)c->n;
+    const FramePlan& plan = c->plan;
+    const ChunkGeom g = c->cg;
+    const uint32_t K = 1u << g.nbits;
+    const uint32_t npad = g.nchunks << g.shift;
+    const uint32_t tpc = (1u << g.shift) / kScatterTile;
+    const unsigned long long* skip =
+        c->sorted_valid ? reinterpret_cast<const unsigned long long*>(c->scratch + kHdrKeysChanged) : nullptr;
+    uint32_t* H = c->scratch + L.H_off;
+    uint32_t* keytot = c->scratch + L.keytot_off;
+    uint32_t* remap = c->scratch + L.remap_off;
+    uint32_t* chunk_cnt = c->scratch + L.cnt_off;
+    // batch table bins + key starts: recomputed every frame (H is), cheap
+    TB_LAUNCH(c, "chunk_key_totals", (uint64_t)g.nchunks * K * 4, chunk_key_totals_kernel, div_up(K, kThreads), kThreads, 0, (const uint32_t*)H, g,
+              plan.zbits, keytot, c->scratch + L.lt_off);
+    TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, (const uint32_t*)(c->scratch + L.lt_off), 1u << plan.ltbits, plan,
+              c->batches, (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
+    TB_LAUNCH(c, "chunk_key_scan", 0, scan_blocks_kernel, 1, 1024, 0, keytot, K, c->scratch + kHdrPending);
+    TB_LAUNCH(c, "chunk_place", (uint64_t)g.nchunks * K * 8, chunk_place_kernel, div_up(K, kThreads), kThreads, 0, (const uint32_t*)H,
+              (const uint32_t*)keytot, g, remap, skip);
+    TB_LAUNCH(c, "chunk_local", (uint64_t)g.nchunks * K * 12, chunk_local_kernel, g.nchunks, 1024, 0, (const uint32_t*)H, g, remap, chunk_cnt, skip);
+    const uint32_t* kin = (const uint32_t*)c->ekeys;
+    const uint32_t* iin = nullptr;
+    int cur = 1;
+    for (uint32_t p = 0; p < plan.npasses; ++p) {
+        const bool last = p + 1 == plan.npasses;
+        const uint32_t ntiles = L.tiles[p];
+        uint32_t* counts = c->scratch + L.counts_off[p];
+        uint32_t* offs = c->scratch + L.offs_off[p];
+        if (!(p == 0 && prepare_made_counts))
+            TB_LAUNCH(c, "tile_hist", (uint64_t)n * 4, tile_hist_kernel<uint32_t>, std::min<uint32_t>(ntiles, 16u * (uint32_t)c->sm_count), kThreads, 0,
+                      kin, iin ? npad : n, (const unsigned long long*)nullptr, mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_SPRITE),
+                      iin ? 0u : 1u, kScatterTile, plan.shift[p], plan.bits[p], ntiles, counts, skip,
+                      iin ? (const uint32_t*)chunk_cnt : (const uint32_t*)nullptr, g.shift);
+        TB_LAUNCH(c, "chunk_tile_scan", 0, chunk_tile_scan_kernel, g.nchunks, 1024, 0, (const uint32_t*)counts, ntiles, tpc, plan.bits[p], g.shift, offs,
+                  skip);
+        ScatterParams<uint32_t> sp{};
+        sp.pass.n = iin ? npad : n;
+        sp.pass.count_ptr = nullptr;
+        sp.pass.shift = plan.shift[p];
+        sp.pass.bits = plan.bits[p];
+        sp.pass.tile_off = offs;
+        sp.pass.ntiles = ntiles;
+        sp.pass.chunk_cnt = chunk_cnt;
+        sp.pass.chunk_shift = g.shift;
+        sp.keys_in = kin;
+        sp.idx_in = iin;
+        sp.mask_t = mask_or_null(c, TB_TRANSFORM);
+        sp.mask_s = mask_or_null(c, TB_SPRITE);
+        sp.skip = skip;
+        if (last) {
+            sp.keys_out = (uint32_t*)c->final_keys;
+            sp.idx_out = c->final_idx;
+            sp.dst_out = c->final_dst;
+            sp.remap = remap;
+            sp.key_bits = g.nbits;
+            sp.id_offset = (uint32_t)c->global_first;
+        } else {
+            sp.keys_out = (uint32_t*)c->keys[cur];
+            sp.idx_out = c->idx[cur];
+        }
+        TB_LAUNCH(c, "radix_scatter", (uint64_t)n * (last ? 20 : 16), radix_scatter_kernel<uint32_t>,
+                  std::min<uint32_t>(ntiles, 3u * (uint32_t)c->sm_count), kThreads, sizeof(ScatterShared<uint32_t>), sp);
+        kin = (const uint32_t*)c->keys[cur];
+        iin = c->idx[cur];
+        cur ^= 1;
+    }
+    ListParams lp;
+    fill_list_params(c, fm, false, d_inst, d_vtx, d_order, &lp);
+    TB_LAUNCH(c, "emit_list", (uint64_t)n * (64 + 80 + 64 + 4 + 8), emit_list_kernel<false>, 2u * (uint32_t)c->sm_count, kThreads, sizeof(ListShared), lp);
+    return TB_OK;
+}
+
+// The steady-state frame of a flat scene under a chunked sort whose list is kept: one kernel — the velocity system on
+// the gathered rows, every key re-checked against the kept one, compose, emit. *ok as in sorted_fast_frame.
+tb_status chunk_fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+    *ok = false;
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
+    FrameMode fm{};
+    ListParams lp;
+    fill_list_params(c, fm, integrate, d_inst, d_vtx, d_order, &lp);
+    TB_LAUNCH(c, "emit_list", c->sorted_count * (64 + 80 + 64 + 4 + 12 + (lp.integrate ? 28 : 0)), emit_list_kernel<true>,
+              2u * (uint32_t)c->sm_count, kThreads, sizeof(ListShared), lp);
+    tb_status s = read_header(c);
+    if (s) return s;
+    *ok = c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] == 0 && c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] == 0 &&
+          c->h_hdr[2] == c->sorted_count && plan_covers(c->plan, c->h_hdr[0], ~c->h_hdr[1]);
+    return TB_OK;
+}
+
+// A scene graph nothing has touched since the frame that left its world rows and list: the emit over those.
+tb_status chunk_replay_hierarchy(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+    FrameMode fm{};
+    fm.hier = true;
+    ListParams lp;
+    fill_list_params(c, fm, false, d_inst, d_vtx, d_order, &lp);
+    TB_LAUNCH(c, "emit_list", c->sorted_count * (64 + 80 + 64 + 4 + 8), emit_list_kernel<false>, 2u * (uint32_t)c->sm_count, kThreads,
+              sizeof(ListShared), lp);
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
 // Every launch of a full frame under the cached plan, in stream order, ending with the header copy.
 // Launch-only (no allocation, no synchronisation), so it can be captured into a graph.
 tb_status record_full_frame(tb_ctx* c, const FrameMode& fm, const ScratchLayout& L, bool integrate, bool prepare_made_counts,
@@ -982,12 +1146,13 @@ tb_status record_full_frame(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
     if ((s = run_prepare(c, true, integrate, fm, &L))) return s;
     uint32_t* hist = c->scratch + kHdrHist;
-    if (!fm.lt_generic) {
+    if (!fm.lt_generic && !L.chunked) {
         const uint32_t* bins = fm.lt_alias ? hist : c->scratch + L.lt_off;
         TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, bins, 1u << plan.ltbits, plan, c->batches,
                   (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
     }
-    if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+    if (L.chunked) s = run_chunked_sort_and_emit(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
+    else if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
     else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
     if (s) return s;
     TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1003,7 +1168,8 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
     g.level_epoch = c->level_epoch;
     const void* ptrs[] = {c->rows.t, c->rows.b, c->scratch, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->world, c->vel,
                           c->mask[0], c->mask[1], c->mask[2], c->mask[3], c->batches, c->texlayer, c->level_list,
-                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr, c->ekeys, c->final_idx};
+                          c->sane_parent, c->remap, d_inst, d_vtx, d_order, c->h_hdr, c->ekeys, c->final_idx, c->final_dst,
+                          c->final_keys};
     static_assert(sizeof(ptrs) <= sizeof(g.ptr), "FrameSig::ptr too small");
     memcpy(g.ptr, ptrs, sizeof(ptrs));
     g.plan = c->plan;
@@ -1015,7 +1181,7 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
                               c->level_ranges ? 1u : 0u, (uint32_t)c->shard_state, (uint32_t)c->rows.st,
                               (uint32_t)(c->store[TB_VELOCITY] ? 1 : 0), c->sorted_valid ? 1u : 0u,
                               (c->sorted_valid && c->final_valid) ? 1u : 0u, (uint32_t)c->sorted_cache,
-                              (uint32_t)c->static_buckets};
+                              (uint32_t)c->static_buckets, c->chunked ? 1u + c->cg.shift : 0u, c->cg.nchunks};
     static_assert(sizeof(flags) == sizeof(g.flags), "FrameSig::flags size");
     memcpy(g.flags, flags, sizeof(flags));
     g.vp_bits[0] = c->has_vp ? 1u : 0u;
@@ -1303,6 +1469,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ListShared));
+    cudaFuncSetAttribute(emit_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ListShared));
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
         tb_ctx_destroy(c);
         return TB_ERR_CUDA;
@@ -1331,6 +1499,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->ekeys);
     cudaFree(c->final_idx);
     cudaFree(c->final_keys);
+    cudaFree(c->final_dst);
     cudaFree(c->seq_rows);
     cudaFree(c->texlayer);
     cudaFree(c->world);
@@ -1400,6 +1569,17 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     } else if (k == "sorted_cache") {
         c->sorted_cache = value != 0;
         c->sorted_valid = c->final_valid = c->seq_valid = false;
+    } else if (k == "chunked_sort") {
+        c->chunked_sort = value != 0;
+        c->plan_valid = false;
+        drop_kept_frames(c);
+        c->final_valid = c->seq_valid = false;
+    } else if (k == "chunk_shift") {
+        if (value != 0 && (value < 11 || value > 24)) return fail(c, TB_ERR_INVALID, "chunk_shift must be 0 (automatic) or 11..24");
+        c->chunk_shift_opt = (int)value;
+        c->plan_valid = false;
+        drop_kept_frames(c);
+        c->final_valid = c->seq_valid = false;
     } else if (k == "cuda_graphs") {
         c->use_graphs = value != 0;
         c->frame_graph_valid = false;
@@ -1848,7 +2028,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         // flat sorted scene with its sort and draw order kept: one kernel emits and validates — or, when nothing at
         // all has been touched for a few frames, streams from the draw-ordered copy of the rows
         const bool untouched = !integrate;
-        if (untouched && c->seq_valid && !c->seq_world) {
+        if (c->chunked) {
+            // chunked sort: the kept chunk-major list serves moving and static frames alike (window-local gathers)
+            s = chunk_fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done);
+        } else if (untouched && c->seq_valid && !c->seq_world) {
             if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
             else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
             fast_done = true;
@@ -1862,7 +2045,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             count = c->sorted_count;
             num_batches = c->sorted_batches;
             c->clean_streak = untouched ? c->clean_streak + 1 : 0;
-            if (untouched && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, false))) return s;
+            if (!c->chunked && untouched && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, false))) return s;
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
     }
@@ -1870,7 +2053,9 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         c->sorted_cache && c->plan_valid && c->shard_state != 4) {
         // a scene graph nothing has touched since the frame that left its world rows, sort and draw order (no
         // upload, no tick): the frame is the emit over those, e.g. under a new camera
-        if (c->seq_valid && c->seq_world) {
+        if (c->chunked) {
+            s = chunk_replay_hierarchy(c, d_inst, d_vtx, d_order);
+        } else if (c->seq_valid && c->seq_world) {
             if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
             else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
         } else {
@@ -1882,7 +2067,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         count = c->sorted_count;
         num_batches = c->sorted_batches;
         c->clean_streak += 1;
-        if (!c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, true))) return s;
+        if (!c->chunked && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, true))) return s;
     }
     if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
         if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
@@ -1924,18 +2109,44 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             make_plan(c, c->h_hdr[0], ~c->h_hdr[1], zvals, nz);
         }
         const FramePlan& plan = c->plan;
-        // sorted frames gather whole rows in draw order: one 64-byte row per entity reads one DRAM
-        // atom instead of two half-used ones (the in-order single-pass frames prefer the split sectors)
-        if (c->layout_auto && !c->interleaved && plan.npasses > 1 && !fm.hier && (s = relayout_rows(c, true))) return s;
         if (c->force_path == TB_PATH_BUCKET && plan.npasses > 1)
             return fail(c, TB_ERR_UNSUPPORTED, "TB_PATH_BUCKET needs at most 256 distinct key buckets");
         fm.lt_alias = plan.npasses == 1 && plan.zbits == 0 && (int)plan.ltbits <= c->lt_limit;
         fm.lt_hist = !fm.lt_alias && (int)plan.ltbits <= c->lt_limit;
         fm.lt_generic = !fm.lt_alias && !fm.lt_hist;
+        // Chunked sort (chunked.cuh): short keys of 4..16 bits. The id range is cut into chunks whose rows fit the L2
+        // several times over; a (chunk, key) run then holds 2^shift / 2^bits entities on average, so wider keys take
+        // bigger chunks (32 entities per run: whole-line stores), within 2^17..2^20 entities (8..64 MB of rows).
+        const bool was_chunked = c->chunked;
+        c->chunked = c->chunked_sort != 0 && !plan.key64 && plan.pext.nbits > kSmallMaxBits && plan.pext.nbits <= 16 &&
+                     !fm.lt_generic && c->shard_state != 4 && n < (1ull << 31);
+        if (c->chunked) {
+            uint32_t shift = c->chunk_shift_opt ? (uint32_t)c->chunk_shift_opt : std::min(20u, std::max(17u, plan.pext.nbits + 5u));
+            while (shift > 11 && (1ull << (shift - 1)) >= n) --shift;  // small scenes: one chunk
+            const ChunkGeom cg{shift, div_up(n, 1ull << shift), plan.pext.nbits};
+            if (!was_chunked || cg.shift != c->cg.shift || cg.nchunks != c->cg.nchunks || cg.nbits != c->cg.nbits)
+                c->sorted_valid = c->final_valid = false;  // the kept list has another geometry
+            c->cg = cg;
+            fm.lt_alias = false;  // the batch bins come from the per-chunk histogram
+            fm.lt_hist = true;
+        } else if (was_chunked) {
+            c->sorted_valid = c->final_valid = false;
+        }
+        // Frames that gather rows in draw order from anywhere in the storage read whole 64-byte rows: one DRAM atom
+        // per entity instead of three partial ones. Chunked frames gather inside an L2-sized window, where every
+        // sector of the split arrays gets used, and keep the split layout (dense key pass and write-back).
+        if (c->layout_auto && !c->interleaved && plan.npasses > 1 && !fm.hier && !c->chunked && (s = relayout_rows(c, true))) return s;
         const bool prepare_made_counts = !fm.hier;  // flat frames: pass A counts pass 0's tile digits
-        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, prepare_made_counts, use_small_emit(c, plan));
+        const ScratchLayout L = layout_scratch(plan, n, fm.lt_hist, prepare_made_counts, use_small_emit(c, plan),
+                                               c->chunked ? &c->cg : nullptr);
         if ((s = ensure_scratch(c, L.alloc_words))) return s;
-        if ((plan.npasses > 1 || fm.hier) && (s = ensure_sort_buffers(c, n, plan.key64 ? 8 : 4))) return s;
+        if (c->chunked) {
+            c->chunk_cnt_off = L.cnt_off;
+            c->chunk_remap_off = L.remap_off;
+        }
+        if ((plan.npasses > 1 || fm.hier || c->chunked) &&
+            (s = ensure_sort_buffers(c, c->chunked ? ((uint64_t)c->cg.nchunks << c->cg.shift) : n, plan.key64 ? 8 : 4)))
+            return s;
         if (fm.lt_generic) {
             size_t cap = c->texlayer ? c->texlayer_cap : 0;
             if ((s = grow(c, &c->texlayer, &cap, (size_t)n, 4))) return s;
@@ -2025,11 +2236,11 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         // sorted frames: this frame's sorted (key, id) arrays, tile offsets and entity-order keys stay where
         // they are; the next frame's key pass compares every key with them and its sort passes only run
         // if one changed (a u32 short key of all ones would collide with the "not renderable" mark)
-        if (c->sorted_cache && (plan.npasses > 1 || fm.hier) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32)) {
+        if (c->sorted_cache && (plan.npasses > 1 || fm.hier || c->chunked) && !fm.lt_generic && (plan.key64 || plan.pext.nbits < 32)) {
             const bool resorted = !armed_at_start || c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] != 0;
             c->sorted_valid = true;
             // a frame that ranked has left its draw order and short keys in final_idx / final_keys
-            if (resorted) c->final_valid = plan.npasses > 1;  // multi-pass frames rank in emit_kernel, which wrote them
+            if (resorted) c->final_valid = plan.npasses > 1 || c->chunked;  // written by emit_kernel / the last chunk scatter
             if (resorted) c->seq_valid = false;
             c->clean_streak = 0;
             c->sorted_count = count;
