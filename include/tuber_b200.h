@@ -91,7 +91,8 @@ typedef struct tb_batch {
     uint32_t count;
 } tb_batch;                   /* 16 bytes: one per maximal run of equal (layer, texture) */
 
-enum tb_component { TB_TRANSFORM = 0, TB_SPRITE = 1, TB_VELOCITY = 2, TB_PARENT = 3, TB_COMPONENT_COUNT = 4 };
+/* [SPEC] angular velocity about z in radians per second (one f32): the component of the second device system. */
+enum tb_component { TB_TRANSFORM = 0, TB_SPRITE = 1, TB_VELOCITY = 2, TB_PARENT = 3, TB_SPIN = 4, TB_COMPONENT_COUNT = 5 };
 
 /* Which batching path a frame took (both give identical results). */
 enum tb_path {
@@ -177,6 +178,7 @@ TB_API tb_status tb_upload_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, c
 TB_API tb_status tb_upload_sprites(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_sprite* src);
 TB_API tb_status tb_upload_velocities(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_velocity* src);
 TB_API tb_status tb_upload_parents(tb_ctx* ctx, uint64_t first, uint64_t n, const uint32_t* src);
+TB_API tb_status tb_upload_spins(tb_ctx* ctx, uint64_t first, uint64_t n, const float* src);
 /* Presence bitset words of one component, same bit layout as bitset.rs:15-36
  * (entity e -> word e/64, bit e%64). Clearing a bit is remove_from_entity (ecs.rs:35-38). */
 TB_API tb_status tb_upload_presence(tb_ctx* ctx, int component, uint64_t first_word, uint64_t nwords,
@@ -184,6 +186,29 @@ TB_API tb_status tb_upload_presence(tb_ctx* ctx, int component, uint64_t first_w
 TB_API tb_status tb_download_presence(tb_ctx* ctx, int component, uint64_t first_word, uint64_t nwords,
                                       uint64_t* words);
 TB_API tb_status tb_download_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, tb_transform* dst);
+
+/* ---- structural changes on the device (ecs.rs:93-124) -------------------------------------------
+ *
+ * Incremental: a few presence words and rows change, nothing is re-uploaded. Entity indices are never
+ * reused (ecs.rs:94-97), so an index stays valid for ever; what a delete invalidates is a HANDLE: every
+ * slot has a generation on the device, bumped by tb_delete_*, and tb_entities_alive resolves
+ * (index, generation) pairs against it (the north star's generation-checked entity indices). */
+/* Ecs::insert (ecs.rs:93-98): one new entity with the given components (NULL = not part of the entity);
+ * *index receives its EntityIndex (the old entity_count). */
+TB_API tb_status tb_insert(tb_ctx* ctx, const tb_transform* t, const tb_sprite* s, const tb_velocity* v, const uint32_t* parent,
+                           uint64_t* index);
+/* Ecs::delete_by_ids (ecs.rs:106-112): every component of the listed entities is removed. An id outside
+ * [0, entity_count) is TB_ERR_INVALID (the reference panics) and nothing is changed for it. */
+TB_API tb_status tb_delete_by_ids(tb_ctx* ctx, const uint32_t* ids, uint64_t n);
+/* Ecs::delete_by_query (ecs.rs:100-104): the same for every entity that has all `required_components`
+ * (bit c == enum tb_component c); a required component without a store matches nothing. */
+TB_API tb_status tb_delete_by_query(tb_ctx* ctx, uint32_t required_components, uint64_t* deleted);
+/* Ecs::add_component / remove_component (ecs.rs:114-124): as in the reference, a component type that has no store
+ * yet is left alone (no-op). `value`: tb_transform / tb_sprite / tb_velocity / uint32_t parent / float spin. */
+TB_API tb_status tb_add_component(tb_ctx* ctx, int component, uint64_t index, const void* value);
+TB_API tb_status tb_remove_component(tb_ctx* ctx, int component, uint64_t index);
+TB_API tb_status tb_entity_generations(tb_ctx* ctx, uint64_t first, uint64_t n, uint32_t* generations);
+TB_API tb_status tb_entities_alive(tb_ctx* ctx, const uint32_t* ids, const uint32_t* generations, uint64_t n, uint8_t* alive);
 
 /* ---- query: replaces QueryIterator::new (query.rs:94-129) -------------------------------- */
 
@@ -232,6 +257,25 @@ TB_API tb_status tb_mat4_try_inverse(tb_ctx* ctx, const float* m16, uint64_t n, 
  * runs 1-2 updates per render) run as one pass, each tick rounded as if run alone. */
 TB_API tb_status tb_system_integrate(tb_ctx* ctx, float dt);
 
+/* [SPEC] a second device system: angle.z += spin * dt for every entity with Transform and Spin,
+ * then sin / cos of the new half angle (bit-exact host libm values) into the row. Runs at once on the
+ * context's stream. */
+TB_API tb_status tb_system_spin(tb_ctx* ctx, float dt);
+
+/* What a device system reads and writes, as bit sets over enum tb_column: the declared access sets a
+ * scheduler needs. Two systems may run concurrently iff neither writes a column the other reads or writes. */
+enum tb_system_id { TB_SYSTEM_VELOCITY = 0, TB_SYSTEM_SPIN = 1, TB_SYSTEM_COUNT = 2 };
+enum tb_column { TB_COL_TRANSLATION = 0, TB_COL_YAW = 1, TB_COL_VELOCITY = 2, TB_COL_SPIN = 3, TB_COL_PRESENCE = 4 };
+TB_API tb_status tb_system_access(int system, uint32_t* reads, uint32_t* writes);
+/* SystemBundle::step (system.rs:17-23) for device systems: the state afterwards is the one running
+ * systems[0], systems[1], ... one after the other leaves (insertion order, as the reference runs them).
+ * Systems are list-scheduled into stages by their access sets; the systems of one stage touch disjoint
+ * columns and run concurrently on separate streams, forked from and joined to the context's stream by
+ * events (capturable into a CUDA graph by a caller that captures the context's stream). stages[k], when
+ * not NULL, receives the stage system k was placed in. A bundle that is just the velocity system is
+ * queued like tb_system_integrate (fused into the next frame). */
+TB_API tb_status tb_bundle_step(tb_ctx* ctx, const int* systems, uint32_t n, float dt, uint32_t* stages);
+
 /* ---- frame: what a batching render_scene(&Ecs) does (tuber-graphics/src/lib.rs:134-156) -- */
 
 /* query (&Transform, &Sprite, Opt<&Parent>) -> world matrices (with parent propagation)
@@ -257,6 +301,21 @@ TB_API tb_status tb_download_order(tb_ctx* ctx, uint64_t first, uint64_t n, uint
 /* World matrices (row-major 4x4) of entities [first, first+n) as of the last frame; entities
  * without a Transform get the identity. Runs the compose/propagate kernels if needed. */
 TB_API tb_status tb_download_world_matrices(tb_ctx* ctx, uint64_t first, uint64_t n, float* dst16);
+
+/* ---- headless presenter ([SPEC]) ------------------------------------------------------
+ *
+ * What sits behind render_scene after the frame (tuber-graphics/src/lib.rs:134-156 submits an empty encoder
+ * and presents): consumes the last frame's draw list on the device. The quad vertices, taken as clip-space
+ * coordinates (set a camera with tb_frame_set_view_projection, e.g. tb_orthographic), are rasterised in draw
+ * order with the painter's rule into a width x height buffer, row 0 at clip y = -1:
+ *   ids[p]  = 1 + draw position of the quad on top of pixel p, 0 where nothing was drawn
+ *   rgba[p] = an opaque colour derived from that instance's (texture, layer), 0 for the background
+ * Either host buffer may be NULL. Quads entirely outside the clip square are culled here (per quad, on the
+ * presenter side: the frame itself never culls, so what it keeps between frames survives camera moves);
+ * `drawn` / `culled` count them. Coverage is decided at pixel centres by edge functions in individually
+ * rounded f32, so a CPU rasterisation of the same list reproduces the id buffer exactly. */
+TB_API tb_status tb_present_headless(tb_ctx* ctx, uint32_t width, uint32_t height, uint32_t* ids, uint32_t* rgba,
+                                     uint64_t* drawn, uint64_t* culled);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 

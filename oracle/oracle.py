@@ -38,7 +38,9 @@ def lib():
         L = C.CDLL(build())
         vp, u64, u32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_double
         L.orc_scene_create.restype = vp
-        L.orc_scene_create.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, u64]
+        L.orc_scene_create.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, u64, vp, vp]
+        L.orc_scene_step_systems.restype = C.c_int
+        L.orc_scene_step_systems.argtypes = [vp, dbl, vp, u32]
         L.orc_ecs_free.argtypes = [vp]
         L.orc_ecs_new.restype = vp
         L.orc_ecs_new.argtypes = [u64]
@@ -172,7 +174,7 @@ class Scene:
     """A restated-reference Ecs filled from component arrays (NULL array == no such store)."""
 
     def __init__(self, n, transforms=None, sprites=None, velocities=None, parents=None,
-                 mask_transform=None, mask_sprite=None, mask_velocity=None, bitset_words=0):
+                 mask_transform=None, mask_sprite=None, mask_velocity=None, bitset_words=0, spins=None, mask_spin=None):
         L = lib()
         self.n = int(n)
         t = _f32(transforms, 12)
@@ -181,8 +183,10 @@ class Scene:
         p = None if parents is None else np.ascontiguousarray(parents, dtype=np.uint32)
         masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint64)
                  for m in (mask_transform, mask_sprite, mask_velocity)]
+        w = None if spins is None else np.ascontiguousarray(spins, dtype=np.float32)
+        mw = None if mask_spin is None else np.ascontiguousarray(mask_spin, dtype=np.uint64)
         self._h = L.orc_scene_create(self.n, _p(t), _p(masks[0]), _p(s), _p(masks[1]), _p(v), _p(masks[2]), _p(p),
-                                     int(bitset_words))
+                                     int(bitset_words), _p(w), _p(mw))
         if not self._h:
             raise OverflowError("entity index beyond the presence bitset (the reference panics)")
 
@@ -203,6 +207,12 @@ class Scene:
         if r < 0:
             raise RuntimeError(lib().orc_ecs_last_error(self._h).decode())
         return r
+
+    def step_systems(self, dt, systems):
+        """One tick running the built-in systems (0: velocity, 1: spin) in this order, like SystemBundle::step."""
+        a = np.ascontiguousarray(systems, dtype=np.int32)
+        if lib().orc_scene_step_systems(self._h, float(dt), _p(a), len(a)) != 0:
+            raise RuntimeError(lib().orc_ecs_last_error(self._h).decode())
 
     def transforms(self):
         out = np.zeros((self.n, 12), np.float32)
@@ -286,3 +296,41 @@ def mat4_try_inverse(m):
     some = np.zeros(m.shape[0], np.uint8)
     lib().orc_batch_mat4_try_inverse(_p(m), m.shape[0], _p(out), _p(some))
     return out, some
+
+
+# ---- CPU rasterisation of a draw list (checker of the headless presenter, tb_present_headless) ----
+
+def rasterize(vertices, width, height):
+    """Painter's-rule rasterisation of quads (n, 4) VERTEX_DTYPE in draw order, clip space, pixel centres, four edge
+    functions in float32 with every operation rounded on its own (numpy float32 arithmetic): ids[j, i] = 1 + position of
+    the last quad covering pixel (i, j), 0 for none. Row 0 is clip y = -1."""
+    f = np.float32
+    ids = np.zeros((height, width), np.uint32)
+    sx, sy = f(2.0) / f(width), f(2.0) / f(height)
+    cx = (np.arange(width, dtype=np.float32) + f(0.5)) * sx - f(1.0)
+    cy = (np.arange(height, dtype=np.float32) + f(0.5)) * sy - f(1.0)
+    vx = np.asarray(vertices["x"], np.float32)
+    vy = np.asarray(vertices["y"], np.float32)
+    for q in range(vx.shape[0]):
+        x, y = vx[q], vy[q]
+        if not (x.max() >= -1 and x.min() <= 1 and y.max() >= -1 and y.min() <= 1):
+            continue
+        i0 = max(0, int(np.floor((float(x.min()) + 1) * 0.5 * width)) - 2)
+        i1 = min(width - 1, int(np.floor((float(x.max()) + 1) * 0.5 * width)) + 2)
+        j0 = max(0, int(np.floor((float(y.min()) + 1) * 0.5 * height)) - 2)
+        j1 = min(height - 1, int(np.floor((float(y.max()) + 1) * 0.5 * height)) + 2)
+        if i1 < i0 or j1 < j0:
+            continue
+        px = cx[i0:i1 + 1][None, :]
+        py = cy[j0:j1 + 1][:, None]
+        pos = np.ones((j1 - j0 + 1, i1 - i0 + 1), bool)
+        neg = pos.copy()
+        for k in range(4):
+            ax, ay, bx, by = x[k], y[k], x[(k + 1) % 4], y[(k + 1) % 4]
+            e = (bx - ax) * (py - ay) - (by - ay) * (px - ax)   # float32 throughout, no fused operations
+            pos &= e >= 0
+            neg &= e <= 0
+        inside = pos | neg
+        view = ids[j0:j1 + 1, i0:i1 + 1]
+        view[inside] = q + 1
+    return ids

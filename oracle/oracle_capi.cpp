@@ -342,7 +342,7 @@ static inline bool mask_bit(const uint64_t* mask, uint64_t i) {
 // parents[i] == 0xFFFFFFFF means entity i has no Parent component.
 void* orc_scene_create(uint64_t n, const float* transforms, const uint64_t* mask_transform, const uint32_t* sprites,
                        const uint64_t* mask_sprite, const float* velocities, const uint64_t* mask_velocity,
-                       const uint32_t* parents, uint64_t bitset_words) {
+                       const uint32_t* parents, uint64_t bitset_words, const float* spins, const uint64_t* mask_spin) {
     uint64_t need = (n + 63) / 64;
     if (bitset_words == 0) bitset_words = need > 1024 ? need : 1024;
     auto* o = new OrcEcs(bitset_words);
@@ -358,6 +358,7 @@ void* orc_scene_create(uint64_t n, const float* transforms, const uint64_t* mask
                 p.index = parents[i];
                 def.push_back({TY_PARENT, &p, sizeof(Parent)});
             }
+            if (spins && mask_bit(mask_spin, i)) def.push_back({TY_SPIN, spins + i, sizeof(Spin)});
             o->ecs.insert(def, /*faithful_insert_cost=*/n <= 4096);
         }
     } catch (const std::out_of_range&) {
@@ -380,6 +381,23 @@ double orc_scene_step(void* h, double dt) {
     std::string err = bundle.step(o->ecs, ad);
     if (!err.empty()) { o->last_error = err; return -1.0; }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// One engine tick running a bundle of the built-in systems in the given order (0: velocity, 1: spin) — sequentially,
+// in insertion order, as SystemBundle::step does (system.rs:17-23). Returns 0, or -1 on a system error.
+int orc_scene_step_systems(void* h, double dt, const int* systems, uint32_t n) {
+    auto* o = static_cast<OrcEcs*>(h);
+    DeltaTime d{dt};
+    o->ecs.insert_shared_resource(TY_DELTA_TIME, &d, sizeof(d));
+    SystemBundle<int> bundle;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (systems[k] == 0) bundle.add_system([](Ecs& ecs, int&) { return velocity_system(ecs); });
+        else bundle.add_system([](Ecs& ecs, int&) { return spin_system(ecs); });
+    }
+    int ad = 0;
+    std::string err = bundle.step(o->ecs, ad);
+    if (!err.empty()) { o->last_error = err; return -1; }
+    return 0;
 }
 
 // Copies every entity's Transform out (zeros where absent).

@@ -28,7 +28,7 @@ namespace ref {
 // Component type ids of the built-in device-visible components.
 enum : TypeId { TY_TRANSFORM = 0x7472616e73666f72ull, TY_SPRITE = 0x7370726974650000ull,
                 TY_VELOCITY = 0x76656c6f63697479ull, TY_PARENT = 0x706172656e740000ull,
-                TY_DELTA_TIME = 0x64656c746174696dull };
+                TY_DELTA_TIME = 0x64656c746174696dull, TY_SPIN = 0x7370696e00000000ull };
 
 // SPEC §3.1 component layouts.
 struct Sprite {
@@ -42,6 +42,9 @@ struct Velocity {
 };
 struct Parent {
     size_t index;  // tuber-ecs/src/lib.rs:18-19: Parent(pub EntityIndex)
+};
+struct Spin {
+    float w;  // [SPEC] angular velocity about z, radians per second
 };
 struct DeltaTime {
     double dt;  // tuber-core/src/lib.rs:13
@@ -95,6 +98,24 @@ inline std::string velocity_system(Ecs& ecs) {
         t->translation.x = t->translation.x + v->v[0] * dt;
         t->translation.y = t->translation.y + v->v[1] * dt;
         t->translation.z = t->translation.z + v->v[2] * dt;
+    }
+    return std::string();
+}
+
+// [SPEC] the spin system, a second user system of the same shape: angle.z += spin * dt.
+inline std::string spin_system(Ecs& ecs) {
+    float dt;
+    {
+        Guard g = ecs.shared_resource(TY_DELTA_TIME, false);
+        if (!g.some()) return "DeltaTime resource missing";
+        dt = float(g.get<DeltaTime>()->dt);
+    }
+    QueryIterator it = ecs.query({{TY_TRANSFORM, true, true}, {TY_SPIN, true, false}});
+    std::vector<Guard> row;
+    while (it.next(row)) {
+        Transform* t = row[0].get<Transform>();
+        const Spin* s = row[1].get<Spin>();
+        t->angle.z = t->angle.z + s->w * dt;
     }
     return std::string();
 }

@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtuber_b200.so")
 
 SOURCES = ["tuber_b200.cu"]
-HEADERS = ["kernels.cuh", "common.cuh", "storage.cuh", "prepare.cuh", "placement.cuh", "emit.cuh", "chunked.cuh", "shard.cuh", "mathops.cuh", "comm.h",
+HEADERS = ["kernels.cuh", "common.cuh", "storage.cuh", "prepare.cuh", "placement.cuh", "emit.cuh", "chunked.cuh", "shard.cuh", "mathops.cuh", "present.cuh", "comm.h",
            "compose.cuh", "libm_sincosf.h", "plan.h", os.path.join("..", "..", "include", "tuber_b200.h")]
 
 NVCC_FLAGS = [

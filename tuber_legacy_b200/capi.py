@@ -14,7 +14,8 @@ from . import build as _build
 TB_OK = 0
 TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_OOM, TB_ERR_RANGE, TB_ERR_NO_DEVICE = 1, 2, 3, 4, 5
 TB_ERR_CAPACITY, TB_ERR_CYCLE, TB_ERR_COMM, TB_ERR_UNSUPPORTED = 6, 7, 8, 9
-TB_TRANSFORM, TB_SPRITE, TB_VELOCITY, TB_PARENT = 0, 1, 2, 3
+TB_TRANSFORM, TB_SPRITE, TB_VELOCITY, TB_PARENT, TB_SPIN = 0, 1, 2, 3, 4
+TB_SYSTEM_VELOCITY, TB_SYSTEM_SPIN = 0, 1
 TB_PATH_NONE, TB_PATH_BUCKET, TB_PATH_SORT = 0, 1, 2
 TB_NO_PARENT = 0xFFFFFFFF
 
@@ -69,6 +70,17 @@ _SIGNATURES = {
     "tb_upload_sprites": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_upload_velocities": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_upload_parents": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_upload_spins": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_insert": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "tb_delete_by_ids": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "tb_delete_by_query": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "tb_add_component": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
+    "tb_remove_component": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64]),
+    "tb_entity_generations": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_entities_alive": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_system_spin": (C.c_int32, [C.c_void_p, C.c_float]),
+    "tb_system_access": (C.c_int32, [C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "tb_bundle_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_void_p]),
     "tb_upload_presence": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_presence": (C.c_int32, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_transforms": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -92,6 +104,8 @@ _SIGNATURES = {
     "tb_download_batches": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_order": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "tb_download_world_matrices": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tb_present_headless": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]),
     "tb_profile_enable": (C.c_int32, [C.c_void_p, C.c_int]),
     "tb_profile_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "tb_profile_get": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -305,6 +319,70 @@ class Context:
         """-> (inverse (n, 16), some (n,) uint8); some == 0 is the reference's None."""
         return self._math(self._lib.tb_mat4_try_inverse, [np.reshape(m, (-1, 16))], [((16,), np.float32), ((), np.uint8)])
 
+    # -- structural changes on the device (ecs.rs:93-124)
+    def upload_spins(self, first, spins):
+        a = np.ascontiguousarray(spins, dtype=np.float32).reshape(-1)
+        self._check(self._lib.tb_upload_spins(self._h, int(first), a.shape[0], _ptr(a)))
+
+    def insert(self, transform=None, sprite=None, velocity=None, parent=None):
+        def one(v, dt):
+            return None if v is None else np.ascontiguousarray(np.asarray(v, dtype=dt).reshape(1))
+        t, s, v = one(transform, TRANSFORM_DTYPE), one(sprite, SPRITE_DTYPE), one(velocity, VELOCITY_DTYPE)
+        p = None if parent is None else np.array([parent], np.uint32)
+        idx = C.c_uint64()
+        self._check(self._lib.tb_insert(self._h, _ptr(t), _ptr(s), _ptr(v), _ptr(p), C.byref(idx)))
+        return idx.value
+
+    def delete_by_ids(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self._lib.tb_delete_by_ids(self._h, _ptr(a), a.shape[0]))
+
+    def delete_by_query(self, required_mask):
+        n = C.c_uint64()
+        self._check(self._lib.tb_delete_by_query(self._h, int(required_mask), C.byref(n)))
+        return n.value
+
+    def add_component(self, component, index, value):
+        dt = {TB_TRANSFORM: TRANSFORM_DTYPE, TB_SPRITE: SPRITE_DTYPE, TB_VELOCITY: VELOCITY_DTYPE, TB_PARENT: np.uint32,
+              TB_SPIN: np.float32}[component]
+        a = np.ascontiguousarray(np.asarray(value, dtype=dt).reshape(1))
+        self._check(self._lib.tb_add_component(self._h, int(component), int(index), _ptr(a)))
+
+    def remove_component(self, component, index):
+        self._check(self._lib.tb_remove_component(self._h, int(component), int(index)))
+
+    def entity_generations(self, first, n):
+        out = np.zeros(int(n), np.uint32)
+        self._check(self._lib.tb_entity_generations(self._h, int(first), int(n), _ptr(out)))
+        return out
+
+    def entities_alive(self, ids, generations):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        g = np.ascontiguousarray(generations, dtype=np.uint32)
+        out = np.zeros(a.shape[0], np.uint8)
+        self._check(self._lib.tb_entities_alive(self._h, _ptr(a), _ptr(g), a.shape[0], _ptr(out)))
+        return out
+
+    # -- systems beyond the velocity system
+    def system_spin(self, dt):
+        self._check(self._lib.tb_system_spin(self._h, float(np.float32(dt))))
+
+    def bundle_step(self, systems, dt):
+        """SystemBundle::step for device systems; returns the stage every system was scheduled in."""
+        a = np.ascontiguousarray(systems, dtype=np.int32)
+        stages = np.zeros(a.shape[0], np.uint32)
+        self._check(self._lib.tb_bundle_step(self._h, _ptr(a), a.shape[0], float(np.float32(dt)), _ptr(stages)))
+        return stages
+
+    def present_headless(self, width, height):
+        """Rasterises the last frame's draw list: -> (ids (h, w) u32, rgba (h, w) u32, drawn, culled)."""
+        ids = np.zeros((height, width), np.uint32)
+        rgba = np.zeros((height, width), np.uint32)
+        drawn, culled = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.tb_present_headless(self._h, int(width), int(height), _ptr(ids), _ptr(rgba), C.byref(drawn),
+                                                  C.byref(culled)))
+        return ids, rgba, drawn.value, culled.value
+
     def system_integrate(self, dt):
         self._check(self._lib.tb_system_integrate(self._h, float(np.float32(dt))))
 
@@ -494,3 +572,11 @@ def shard_local_id():
     if st != TB_OK:
         raise TuberError(st, "tb_shard_local_id")
     return bytes(buf)
+
+
+def system_access(system):
+    """(reads, writes) column bit sets of a built-in device system (enum tb_column)."""
+    r, w = C.c_uint32(), C.c_uint32()
+    if load().tb_system_access(int(system), C.byref(r), C.byref(w)) != TB_OK:
+        raise TuberError(TB_ERR_INVALID, "tb_system_access")
+    return r.value, w.value

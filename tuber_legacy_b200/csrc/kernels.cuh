@@ -10,6 +10,7 @@
 //   emit.cuh       emit_kernel, emit_small_kernel                       last pass fused with compose + emit
 //   chunked.cuh    chunk_place, chunk_tile_scan, emit_list                 sorted frames whose row reads stay in L2
 //   shard.cuh      place_sums, place_write                              multi-GPU global draw order
+//   present.cuh    raster_quads, raster_resolve                         headless presenter of the draw list
 //   mathops.cuh    quat_*, mat4_*                                       the rest of tuber-math, batched
 #pragma once
 #include "common.cuh"
@@ -20,3 +21,4 @@
 #include "chunked.cuh"
 #include "shard.cuh"
 #include "mathops.cuh"
+#include "present.cuh"

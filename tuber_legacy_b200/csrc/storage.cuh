@@ -120,10 +120,29 @@ __global__ void __launch_bounds__(kThreads) integrate_kernel(RowView rows, const
     rows.t[o] = a0;
 }
 
+// ---- [SPEC] the spin system: a second device system next to the velocity system --------------------
+//
+// angle.z += angular_velocity * dt for every entity with Transform and Spin (idiom of system.rs:132-137), multiply and
+// add individually rounded. The row keeps sin / cos of the half yaw (compose.cuh), so the system re-evaluates them —
+// with the host libm's sinf / cosf, bit for bit — for exactly the entities it turns.
+// Access sets (tb_system_access): reads Spin, writes Transform.angle.z — disjoint from the velocity system's
+// (reads Velocity, writes Transform.translation), so the two may run concurrently.
+__global__ void __launch_bounds__(kThreads) spin_kernel(RowView rows, const uint64_t* mask_t, const uint64_t* mask_w,
+                                                         const float* __restrict__ spin, float dt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!mask_bit(mask_t, i) || !mask_bit(mask_w, i)) return;
+    const float yaw = addr(rows.yaw[i], mulr(__ldg(spin + i), dt));
+    rows.yaw[i] = yaw;
+    const float2 sc = yaw_sincos(yaw);
+    reinterpret_cast<float*>(rows.b + (size_t)i * rows.sb)[0] = sc.x;      // B0.x
+    reinterpret_cast<float*>(rows.b + (size_t)i * rows.sb + 1)[3] = sc.y;  // B1.w
+}
+
 // ---- Ecs::query: presence AND -> packed ascending indices --------------------------------------
 
 struct QueryParams {
-    const uint64_t* masks[4];
+    const uint64_t* masks[8];
     uint32_t nmasks;
     uint32_t nwords;
     uint32_t n;  // entity_count
@@ -187,6 +206,62 @@ __global__ void __launch_bounds__(kThreads) query_write_kernel(const QueryParams
         }
         __syncthreads();
     }
+}
+
+// ---- structural changes on the device (crates/tuber-ecs/src/ecs.rs:100-112) ----------------------------
+
+struct AllMasks {
+    uint64_t* m[8];
+    uint32_t count;
+};
+
+// Ecs::delete_by_ids: every component of the listed entities is removed (presence bit cleared in every store); the
+// slot's generation is bumped so that handles issued before the delete stop resolving. Ids outside [0, entity_count)
+// are counted in *bad (the reference would panic on the out-of-range index).
+__global__ void __launch_bounds__(kThreads) delete_ids_kernel(const uint32_t* __restrict__ ids, uint32_t n, uint32_t entity_count,
+                                                               AllMasks masks, uint32_t* gen, uint32_t* bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = ids[i];
+    if (e >= entity_count) {
+        atomicAdd(bad, 1u);
+        return;
+    }
+    const unsigned long long bit = 1ull << (e & 63u);
+    for (uint32_t k = 0; k < masks.count; ++k)
+        atomicAnd(reinterpret_cast<unsigned long long*>(masks.m[k] + (e >> 6)), ~bit);
+    atomicAdd(gen + e, 1u);
+}
+
+// Ecs::delete_by_query: the same for every entity matching the presence AND of `q` (one thread per bitset word).
+__global__ void __launch_bounds__(kThreads) delete_query_kernel(const QueryParams q, AllMasks masks, uint32_t* gen,
+                                                                 unsigned long long* deleted) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0;
+    if (w < q.nwords) {
+        uint64_t m = query_word(q, w);
+        if (m) {
+            for (uint32_t k = 0; k < masks.count; ++k) masks.m[k][w] &= ~m;
+            cnt = __popcll(m);
+            while (m) {
+                const uint32_t b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                gen[w * 64u + b] += 1u;
+            }
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(deleted, (unsigned long long)cnt);
+}
+
+// Generation-checked handles resolved on the device: alive = the slot's generation is still the handle's.
+__global__ void __launch_bounds__(kThreads) handles_alive_kernel(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ gens,
+                                                                  uint32_t n, uint32_t entity_count, const uint32_t* __restrict__ gen,
+                                                                  uint8_t* alive) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = ids[i];
+    alive[i] = (e < entity_count && gen[e] == gens[i]) ? 1 : 0;
 }
 
 }  // namespace tb

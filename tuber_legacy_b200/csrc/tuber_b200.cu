@@ -83,9 +83,13 @@ struct tb_ctx {
     float4* rows_mem = nullptr;
     float* yaw_mem = nullptr;  // angle.z per entity (the rows keep sin / cos of its half)
     RowView rows{};
-    uint64_t* mask[TB_COMPONENT_COUNT] = {nullptr, nullptr, nullptr, nullptr};
-    bool store[TB_COMPONENT_COUNT] = {false, false, false, false};
+    uint64_t* mask[TB_COMPONENT_COUNT] = {};
+    bool store[TB_COMPONENT_COUNT] = {};
     float* vel = nullptr;
+    float* spin = nullptr;       // [cap] angular velocity about z
+    uint32_t* gen = nullptr;     // [cap] generation of every entity slot (bumped by deletes)
+    cudaStream_t side_stream[TB_SYSTEM_COUNT] = {};  // stages of tb_bundle_step: one stream per concurrent system
+    cudaEvent_t fork_event = nullptr, join_event[TB_SYSTEM_COUNT] = {};
     uint32_t* parent = nullptr;
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -1445,6 +1449,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
         ok = cudaMalloc((void**)&c->mask[k], (words + 2) * 8) == cudaSuccess;
         if (ok) cudaMemsetAsync(c->mask[k], 0, (words + 2) * 8, c->stream);
     }
+    ok = ok && cudaMalloc((void**)&c->gen, max_entities * 4) == cudaSuccess;
+    if (ok) cudaMemsetAsync(c->gen, 0, max_entities * 4, c->stream);
     ok = ok && cudaMallocHost((void**)&c->h_hdr, 64) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&c->zset, (kZSetSlots + 1) * 8) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_zset, (kZSetSlots + 1) * 8) == cudaSuccess;
@@ -1489,6 +1495,13 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->yaw_mem);
     for (int k = 0; k < TB_COMPONENT_COUNT; ++k) cudaFree(c->mask[k]);
     cudaFree(c->vel);
+    cudaFree(c->spin);
+    cudaFree(c->gen);
+    for (int k = 0; k < TB_SYSTEM_COUNT; ++k) {
+        if (c->side_stream[k]) cudaStreamDestroy(c->side_stream[k]);
+        if (c->join_event[k]) cudaEventDestroy(c->join_event[k]);
+    }
+    if (c->fork_event) cudaEventDestroy(c->fork_event);
     cudaFree(c->parent);
     cudaFree(c->stage);
     cudaFree(c->scratch);
@@ -1798,6 +1811,163 @@ tb_status tb_download_transforms(tb_ctx* c, uint64_t first, uint64_t n, tb_trans
     return TB_OK;
 }
 
+// ---- structural changes on the device ---------------------------------------------------------------------
+
+namespace {
+// what every change of the renderable set invalidates (as tb_upload_presence)
+void structure_changed(tb_ctx* c) {
+    c->plan_valid = false;
+    drop_kept_frames(c);
+    c->final_valid = c->seq_valid = c->fast_clean = false;
+    c->levels_dirty = true;
+    c->world_valid = false;
+    c->frame_valid = false;
+}
+AllMasks all_masks(tb_ctx* c) {
+    AllMasks m{};
+    m.count = TB_COMPONENT_COUNT;
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k) m.m[k] = c->mask[k];
+    return m;
+}
+}  // namespace
+
+tb_status tb_upload_spins(tb_ctx* c, uint64_t first, uint64_t n, const float* src) {
+    TB_ENTER(c);
+    tb_status s = check_range(c, first, n, src);
+    if (s || n == 0) return s;
+    if (!c->spin) {
+        TB_CUDA(c, cudaMalloc((void**)&c->spin, c->cap * 4));
+        TB_CUDA(c, cudaMemsetAsync(c->spin, 0, c->cap * 4, c->stream));
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->spin + first, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+    c->store[TB_SPIN] = true;
+    mark_presence(c, TB_SPIN, first, n, 1);
+    return TB_OK;
+}
+
+tb_status tb_insert(tb_ctx* c, const tb_transform* t, const tb_sprite* sp, const tb_velocity* v, const uint32_t* parent, uint64_t* index) {
+    TB_ENTER(c);
+    if (!c || !index) return TB_ERR_INVALID;
+    const uint64_t e = c->n;
+    tb_status s = tb_set_entity_count(c, e + 1);
+    if (s) return s;
+    if (t && (s = tb_upload_transforms(c, e, 1, t))) return s;
+    if (sp && (s = tb_upload_sprites(c, e, 1, sp))) return s;
+    if (v && (s = tb_upload_velocities(c, e, 1, v))) return s;
+    if (parent && (s = tb_upload_parents(c, e, 1, parent))) return s;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));  // the sources may be temporaries of the caller
+    *index = e;
+    return TB_OK;
+}
+
+tb_status tb_delete_by_ids(tb_ctx* c, const uint32_t* ids, uint64_t n) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!ids) return fail(c, TB_ERR_INVALID, "null pointer");
+    tb_status s = flush_integrate(c);
+    if (s) return s;
+    if ((s = ensure_stage(c, n * 4))) return s;
+    TB_CUDA(c, cudaMemcpyAsync(c->stage, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrPending, 0, 4, c->stream));
+    TB_LAUNCH(c, "delete_ids", n * 4, delete_ids_kernel, div_up(n, kThreads), kThreads, 0, (const uint32_t*)c->stage, (uint32_t)n, (uint32_t)c->n,
+              all_masks(c), c->gen, c->scratch + kHdrPending);
+    uint32_t bad = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&bad, c->scratch + kHdrPending, 4, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    structure_changed(c);
+    if (bad) return fail(c, TB_ERR_INVALID, "delete_by_ids: an entity index outside entity_count");
+    return TB_OK;
+}
+
+tb_status tb_delete_by_query(tb_ctx* c, uint32_t required, uint64_t* deleted) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (deleted) *deleted = 0;
+    if (required >> TB_COMPONENT_COUNT) return fail(c, TB_ERR_INVALID, "unknown component bit");
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k)
+        if (((required >> k) & 1u) && !c->store[k]) return TB_OK;  // query.rs:110
+    if (c->n == 0) return TB_OK;
+    tb_status s = flush_integrate(c);
+    if (s) return s;
+    QueryParams q{};
+    for (int k = 0; k < TB_COMPONENT_COUNT; ++k)
+        if ((required >> k) & 1u) q.masks[q.nmasks++] = c->mask[k];
+    q.nwords = div_up(c->n, 64);
+    q.n = (uint32_t)c->n;
+    if ((s = ensure_stage(c, 16))) return s;
+    unsigned long long* d_cnt = static_cast<unsigned long long*>(c->stage);
+    TB_CUDA(c, cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+    TB_LAUNCH(c, "delete_query", q.nwords * 8ull * (q.nmasks + TB_COMPONENT_COUNT), delete_query_kernel, div_up(q.nwords, kThreads), kThreads, 0, q,
+              all_masks(c), c->gen, d_cnt);
+    unsigned long long cnt = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (cnt) structure_changed(c);
+    if (deleted) *deleted = cnt;
+    return TB_OK;
+}
+
+tb_status tb_add_component(tb_ctx* c, int comp, uint64_t index, const void* value) {
+    TB_ENTER(c);
+    if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
+    if (!value) return fail(c, TB_ERR_INVALID, "null pointer");
+    if (index >= c->n) return fail(c, TB_ERR_INVALID, "add_component: no such entity index");
+    if (!c->store[comp]) return TB_OK;  // ecs.rs:114-118: no store of that type yet -> nothing happens
+    tb_status s = TB_OK;
+    switch (comp) {
+        case TB_TRANSFORM: s = tb_upload_transforms(c, index, 1, static_cast<const tb_transform*>(value)); break;
+        case TB_SPRITE: s = tb_upload_sprites(c, index, 1, static_cast<const tb_sprite*>(value)); break;
+        case TB_VELOCITY: s = tb_upload_velocities(c, index, 1, static_cast<const tb_velocity*>(value)); break;
+        case TB_PARENT: s = tb_upload_parents(c, index, 1, static_cast<const uint32_t*>(value)); break;
+        case TB_SPIN: s = tb_upload_spins(c, index, 1, static_cast<const float*>(value)); break;
+    }
+    if (s) return s;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    structure_changed(c);
+    return TB_OK;
+}
+
+tb_status tb_remove_component(tb_ctx* c, int comp, uint64_t index) {
+    TB_ENTER(c);
+    if (!c || comp < 0 || comp >= TB_COMPONENT_COUNT) return TB_ERR_INVALID;
+    if (index >= c->n) return fail(c, TB_ERR_INVALID, "remove_component: no such entity index");
+    if (!c->store[comp]) return TB_OK;  // ecs.rs:120-124
+    tb_status s = flush_integrate(c);
+    if (s) return s;
+    mark_presence(c, comp, index, 1, 0);
+    structure_changed(c);
+    return TB_OK;
+}
+
+tb_status tb_entity_generations(tb_ctx* c, uint64_t first, uint64_t n, uint32_t* generations) {
+    TB_ENTER(c);
+    tb_status s = check_range(c, first, n, generations);
+    if (s || n == 0) return s;
+    TB_CUDA(c, cudaMemcpyAsync(generations, c->gen + first, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+tb_status tb_entities_alive(tb_ctx* c, const uint32_t* ids, const uint32_t* generations, uint64_t n, uint8_t* alive) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!ids || !generations || !alive) return fail(c, TB_ERR_INVALID, "null pointer");
+    tb_status s = ensure_stage(c, n * 9 + 16);
+    if (s) return s;
+    uint32_t* d_ids = static_cast<uint32_t*>(c->stage);
+    uint32_t* d_gens = d_ids + n;
+    uint8_t* d_alive = reinterpret_cast<uint8_t*>(d_gens + n);
+    TB_CUDA(c, cudaMemcpyAsync(d_ids, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_gens, generations, n * 4, cudaMemcpyHostToDevice, c->stream));
+    TB_LAUNCH(c, "handles_alive", n * 13, handles_alive_kernel, div_up(n, kThreads), kThreads, 0, (const uint32_t*)d_ids, (const uint32_t*)d_gens,
+              (uint32_t)n, (uint32_t)c->n, (const uint32_t*)c->gen, d_alive);
+    TB_CUDA(c, cudaMemcpyAsync(alive, d_alive, n, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
 // ---- query ----------------------------------------------------------------------------------------
 
 tb_status tb_query(tb_ctx* c, uint32_t required, uint32_t* out_indices, uint64_t cap, uint64_t* count) {
@@ -1954,6 +2124,111 @@ tb_status tb_system_integrate(tb_ctx* c, float dt) {
     c->seq_valid = false;  // rows are about to move
     c->world_valid = false;
     c->frame_valid = false;
+    return TB_OK;
+}
+
+namespace {
+// The spin system as a launch on `stream` (the rows' sin / cos slots and the yaw array change).
+void launch_spin(tb_ctx* c, float dt, cudaStream_t stream) {
+    prof_begin(c, "spin", c->n * 24ull);
+    spin_kernel<<<div_up(c->n, kThreads), kThreads, 0, stream>>>(c->rows, mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_SPIN), c->spin, dt,
+                                                               (uint32_t)c->n);
+    prof_end(c);
+    c->launches++;
+    c->frame_launches++;
+}
+void rows_changed_outside_a_frame(tb_ctx* c) {
+    c->world_valid = false;
+    c->frame_valid = false;
+    c->fast_clean = c->seq_valid = false;  // frames without a key pass of their own need one first
+}
+struct SystemAccess {
+    uint32_t reads, writes;
+};
+constexpr SystemAccess kSystemAccess[TB_SYSTEM_COUNT] = {
+    {(1u << TB_COL_VELOCITY) | (1u << TB_COL_TRANSLATION) | (1u << TB_COL_PRESENCE), 1u << TB_COL_TRANSLATION},
+    {(1u << TB_COL_SPIN) | (1u << TB_COL_YAW) | (1u << TB_COL_PRESENCE), 1u << TB_COL_YAW},
+};
+bool systems_conflict(int a, int b) {
+    const SystemAccess &x = kSystemAccess[a], &y = kSystemAccess[b];
+    return (x.writes & (y.reads | y.writes)) != 0 || (y.writes & (x.reads | x.writes)) != 0;
+}
+}  // namespace
+
+tb_status tb_system_spin(tb_ctx* c, float dt) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPIN]) return TB_OK;
+    launch_spin(c, dt, c->stream);
+    rows_changed_outside_a_frame(c);
+    return TB_OK;
+}
+
+tb_status tb_system_access(int system, uint32_t* reads, uint32_t* writes) {
+    if (system < 0 || system >= TB_SYSTEM_COUNT || !reads || !writes) return TB_ERR_INVALID;
+    *reads = kSystemAccess[system].reads;
+    *writes = kSystemAccess[system].writes;
+    return TB_OK;
+}
+
+tb_status tb_bundle_step(tb_ctx* c, const int* systems, uint32_t n, float dt, uint32_t* stages) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (n == 0) return TB_OK;
+    if (!systems) return fail(c, TB_ERR_INVALID, "null pointer");
+    for (uint32_t k = 0; k < n; ++k)
+        if (systems[k] < 0 || systems[k] >= TB_SYSTEM_COUNT) return fail(c, TB_ERR_INVALID, "unknown system id");
+    // list scheduling: a system goes one stage after the latest earlier system it conflicts with
+    std::vector<uint32_t> stage(n, 0);
+    uint32_t nstages = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        for (uint32_t j = 0; j < k; ++j)
+            if (systems_conflict(systems[j], systems[k])) stage[k] = std::max(stage[k], stage[j] + 1);
+        nstages = std::max(nstages, stage[k] + 1);
+        if (stages) stages[k] = stage[k];
+    }
+    if (n == 1 && systems[0] == TB_SYSTEM_VELOCITY) return tb_system_integrate(c, dt);  // fused into the next frame
+    tb_status s = flush_integrate(c);  // ticks queued earlier come first
+    if (s) return s;
+    if (!c->fork_event) {
+        TB_CUDA(c, cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming));
+        for (int k = 0; k < TB_SYSTEM_COUNT; ++k) {
+            TB_CUDA(c, cudaStreamCreateWithFlags(&c->side_stream[k], cudaStreamNonBlocking));
+            TB_CUDA(c, cudaEventCreateWithFlags(&c->join_event[k], cudaEventDisableTiming));
+        }
+    }
+    for (uint32_t st = 0; st < nstages; ++st) {
+        std::vector<uint32_t> members;
+        for (uint32_t k = 0; k < n; ++k)
+            if (stage[k] == st) members.push_back(k);
+        // the first member runs on the context's stream, the others on side streams forked from it
+        if (members.size() > 1) TB_CUDA(c, cudaEventRecord(c->fork_event, c->stream));
+        for (size_t m = 0; m < members.size(); ++m) {
+            const int sys = systems[members[m]];
+            cudaStream_t stream = c->stream;
+            if (m > 0) {
+                stream = c->side_stream[m % TB_SYSTEM_COUNT];
+                TB_CUDA(c, cudaStreamWaitEvent(stream, c->fork_event, 0));
+            }
+            if (sys == TB_SYSTEM_VELOCITY) {
+                if (c->n && c->store[TB_TRANSFORM] && c->store[TB_VELOCITY]) {
+                    prof_begin(c, "integrate", c->n * 36ull);
+                    integrate_kernel<<<div_up(c->n, kThreads), kThreads, 0, stream>>>(c->rows, mask_or_null(c, TB_TRANSFORM),
+                                                                                    mask_or_null(c, TB_VELOCITY), c->vel, dt, 1u, (uint32_t)c->n);
+                    prof_end(c);
+                    c->launches++;
+                }
+            } else if (sys == TB_SYSTEM_SPIN) {
+                if (c->n && c->store[TB_TRANSFORM] && c->store[TB_SPIN]) launch_spin(c, dt, stream);
+            }
+            if (m > 0) {
+                TB_CUDA(c, cudaEventRecord(c->join_event[m % TB_SYSTEM_COUNT], stream));
+                TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_event[m % TB_SYSTEM_COUNT], 0));
+            }
+        }
+    }
+    rows_changed_outside_a_frame(c);
+    c->static_valid = false;
     return TB_OK;
 }
 
@@ -2732,6 +3007,50 @@ tb_status tb_download_world_matrices(tb_ctx* c, uint64_t first, uint64_t n, floa
         TB_CUDA(c, cudaMemcpyAsync(dst16 + off * 16, c->stage, m * 64, cudaMemcpyDeviceToHost, c->stream));
     }
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+// ---- headless presenter ----------------------------------------------------------------------------------------------
+
+tb_status tb_present_headless(tb_ctx* c, uint32_t width, uint32_t height, uint32_t* ids, uint32_t* rgba, uint64_t* drawn,
+                              uint64_t* culled) {
+    TB_ENTER(c);
+    if (!c) return TB_ERR_INVALID;
+    if (drawn) *drawn = 0;
+    if (culled) *culled = 0;
+    if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 28)) return fail(c, TB_ERR_INVALID, "framebuffer size");
+    if (!c->frame_valid) return fail(c, TB_ERR_INVALID, "no frame has been run since the last change");
+    const bool list_root = c->comm && c->list_vtx && c->ext_inst == c->list_inst;
+    const float4* vtx = list_root ? (const float4*)c->list_vtx : c->ext_inst ? (const float4*)c->ext_vtx : c->vtx;
+    const float4* inst = c->ext_inst ? (const float4*)c->ext_inst : c->inst;
+    if (c->last_instances > 0 && vtx == nullptr) return fail(c, TB_ERR_INVALID, "this context does not emit vertices");
+    const uint32_t npix = width * height;
+    DeviceTemp fb;  // ids | rgba | 2 counters
+    TB_CUDA(c, fb.alloc((size_t)npix * 8 + 16));
+    uint32_t* d_ids = static_cast<uint32_t*>(fb.p);
+    uint32_t* d_rgba = d_ids + npix;
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_rgba + npix);
+    TB_CUDA(c, cudaMemsetAsync(fb.p, 0, (size_t)npix * 8 + 16, c->stream));
+    if (c->last_instances > 0) {
+        RasterParams rp{};
+        rp.vertices = vtx;
+        rp.count = (uint32_t)c->last_instances;
+        rp.width = width;
+        rp.height = height;
+        rp.ids = d_ids;
+        rp.counters = d_cnt;
+        const uint32_t grid = std::min<uint32_t>(div_up(rp.count, kWarps), 16u * (uint32_t)c->sm_count);
+        TB_LAUNCH(c, "raster_quads", c->last_instances * 64, raster_quads_kernel, grid, kThreads, 0, rp);
+        TB_LAUNCH(c, "raster_resolve", (uint64_t)npix * 8, raster_resolve_kernel, div_up(npix, kThreads), kThreads, 0, (const uint32_t*)d_ids, inst,
+                  npix, d_rgba);
+    }
+    unsigned long long h_cnt[2] = {0, 0};
+    if (ids) TB_CUDA(c, cudaMemcpyAsync(ids, d_ids, (size_t)npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rgba) TB_CUDA(c, cudaMemcpyAsync(rgba, d_rgba, (size_t)npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (drawn) *drawn = h_cnt[0];
+    if (culled) *culled = h_cnt[1];
     return TB_OK;
 }
 
