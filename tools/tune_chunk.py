@@ -13,10 +13,14 @@ import util
 
 n = int(os.environ.get("TB_TUNE_N", 1 << 24))
 sc = scenes.config2(n=n)
-settings = [dict(chunked_sort=0)] + [dict(chunk_shift=s) for s in (int(x) for x in os.environ.get("TB_TUNE_SHIFTS", "14,15,16,17,18,19,20").split(","))]
+shifts = [int(x) for x in os.environ.get("TB_TUNE_SHIFTS", "16,17,18,19,20").split(",")]
+settings = [dict(chunked_sort=0)]
+for extra in ({}, {"chunk_l2_hint": 0}, {"interleaved_rows": 1}):
+    settings += [dict(chunked_sort=1, chunk_shift=s, **extra) for s in shifts]
+modes = os.environ.get("TB_TUNE_MODES", "static").split(",")
 steps = 10
 for opts in settings:
-    for mode in ("static", "keys_change"):
+    for mode in modes:
         o = dict(opts)
         if mode == "keys_change":
             o.update(sorted_cache=0, static_buckets=0)

@@ -16,7 +16,9 @@ namespace tb {
 __constant__ int c_libm_fma = 1;
 
 // f32::sin / f32::cos of the reference (number_traits.rs:137-143 -> the platform libm), bit for bit.
-__device__ __forceinline__ void ref_sincosf(float a, float* s, float* c) {
+// Not inlined: per-frame kernels only reach it for entities with pitch or roll (yaw's sin / cos are cached in the
+// row), and one shared copy of the double-precision code keeps those kernels' hot paths small.
+__device__ __noinline__ void ref_sincosf(float a, float* s, float* c) {
     if (c_libm_fma) tbm::sincosf_ref<true>(a, s, c);
     else tbm::sincosf_ref<false>(a, s, c);
 }

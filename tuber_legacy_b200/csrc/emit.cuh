@@ -53,6 +53,8 @@ struct EmitParams {
     uint32_t* final_idx;
     KeyT* final_keys;
     const float4* seq_rows;  // emit_sequential_kernel: the rows (or world rows) in draw order, 64 bytes each
+    float4* seq_rows_rw;     // ... the same storage, writable: the velocity system's translation write-back
+    const float* seq_vel;    // ... velocities in draw order (zero where the entity has none)
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -878,32 +880,64 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
 // current tile is composed and written out in whole lines. Sequential reads instead of one random 64-byte row
 // per entity (which costs about 128 bytes of DRAM traffic each).
 __global__ void __launch_bounds__(kThreads) gather_rows_kernel(RowView rows, const WorldRow* world, const uint32_t* __restrict__ idx,
-                                                                uint32_t global_first, uint32_t count, float4* __restrict__ out) {
+                                                                uint32_t global_first, uint32_t count, float4* __restrict__ out,
+                                                                const float* __restrict__ vel, const uint64_t* mask_v,
+                                                                float* __restrict__ vel_out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte chunk: a row's four are adjacent lanes
     const uint32_t pos = t >> 2, ch = t & 3u;
     if (pos >= count) return;
     const uint32_t e = __ldg(idx + pos) - global_first;
+    if (vel_out != nullptr && ch < 3u)  // velocities in draw order; zero where the entity has no Velocity
+        vel_out[(size_t)pos * 3 + ch] = (vel != nullptr && mask_bit(mask_v, e)) ? __ldg(vel + (size_t)e * 3 + ch) : 0.0f;
     float4 v;
     if (world != nullptr) v = reinterpret_cast<const float4*>(world + e)[ch];
     else v = ch == 0 ? rows.t[(size_t)e * rows.st] : ch == 1 ? rows.a[(size_t)e * rows.st] : rows.b[(size_t)e * rows.sb + (ch & 1u)];
     out[(size_t)pos * 4 + ch] = v;
 }
 
-template <typename KeyT>
+// Rows of tile-local item li of a draw-ordered tile: plain 64-byte rows as the TMA bulk copy lands them.
+struct SeqWarpShared {
+    float4 rows[2][kWarpTile * 4];
+    float4 stage[32 * kStageF4];
+    float vel[2][kWarpTile * 3];
+    unsigned long long keys[2][kWarpTile];  // kept short keys (KeyT)
+    uint32_t idx[2][kWarpTile];
+    unsigned long long kbar[2];
+};
+struct SeqShared {
+    SeqWarpShared w[kWarps];
+};
+
+// VALIDATE: the steady-state frame of a flat sorted scene whose rows LIVE in draw order (the copy is the working
+// storage): the velocity system runs on the streamed rows (ep.integrate ticks; translation chunk written back in
+// place, sequentially), every key is recomputed and compared with the kept one, statistics go to `stats` for the host
+// to confirm — all of it on sequential reads. Entity-order rows are brought up to date lazily (sync_rows_kernel).
+template <typename KeyT, bool VALIDATE>
 __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
+    __shared__ uint32_t s_zdict[VALIDATE ? kMaxZDict : 1];
+    if (VALIDATE) {
+        for (uint32_t k = threadIdx.x; k < (uint32_t)kMaxZDict; k += kThreads) s_zdict[k] = ep.plan.zdict[k];
+        __syncthreads();  // the only block barrier, before the warps go their own ways
+    }
+    PrepAcc acc;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    OrderedWarpShared& sm = reinterpret_cast<OrderedShared*>(emit_smem_raw)->w[warp];
+    SeqWarpShared& sm = reinterpret_cast<SeqShared*>(emit_smem_raw)->w[warp];
     const bool from_world = ep.world != nullptr;
+    const bool do_int = VALIDATE && ep.integrate != 0 && ep.seq_vel != nullptr && !from_world;
     const uint32_t count = ep.pass.n;
     const uint32_t ntiles = (count + kWarpTile - 1) / kWarpTile;
     const uint32_t nwarps = gridDim.x * kWarps;
     auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0
         const uint32_t cnt = min(kWarpTile, count - t * kWarpTile);
         const uint32_t ibytes = (cnt * 4u + 15u) & ~15u;
-        mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes);
+        const uint32_t kbytes = VALIDATE ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
+        const uint32_t vbytes = do_int ? ((cnt * 12u + 15u) & ~15u) : 0u;
+        mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes + kbytes + vbytes);
         bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile * 4, cnt * 64u, &sm.kbar[buf]);
         bulk_g2s(sm.idx[buf], ep.idx_in + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
+        if (VALIDATE) bulk_g2s(sm.keys[buf], ep.keys_in + (size_t)t * kWarpTile, kbytes, &sm.kbar[buf]);
+        if (do_int) bulk_g2s(sm.vel[buf], ep.seq_vel + (size_t)t * kWarpTile * 3, vbytes, &sm.kbar[buf]);
     };
     uint32_t tile = blockIdx.x * kWarps + warp;
     if (lane == 0) {
@@ -918,8 +952,24 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         if (lane == 0 && next < ntiles) fetch(next, cur ^ 1u);
         mbar_wait(&sm.kbar[cur], cur ? par1 : par0);
         if (cur) par1 ^= 1u; else par0 ^= 1u;
-        const float4* rows = sm.rows[cur];
+        float4* rows = sm.rows[cur];
         const uint32_t base = tile * kWarpTile, cnt = min(kWarpTile, count - base);
+        if (do_int) {
+            const float* vel = sm.vel[cur];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t li = k * 32 + lane;
+                if (li < cnt) {
+                    const float vx = vel[li * 3], vy = vel[li * 3 + 1], vz = vel[li * 3 + 2];
+                    if (vx != 0.0f || vy != 0.0f || vz != 0.0f) {  // no Velocity (or a zero one): the value stays
+                        float4 a0 = rows[li * 4];
+                        integrate_ticks(a0, vx, vy, vz, ep.dt, ep.integrate);
+                        rows[li * 4] = a0;
+                        ep.seq_rows_rw[(size_t)(base + li) * 4] = a0;
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const uint32_t li = k * 32 + lane;
@@ -949,6 +999,16 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                     sw = r.b1.y;
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
+                    if (VALIDATE) {
+                        const float z = is_planar(r.a1) ? planar_z(r.a0, r.a1) : local_z(r);
+                        const uint64_t key = sort_key(tl >> 16, tl & 0xFFFFu, z);
+                        acc.k_or |= key;
+                        acc.k_and &= key;
+                        acc.count += 1;
+                        bool miss = false;
+                        if ((KeyT)plan_short_key(ep.plan, s_zdict, key, &miss) != reinterpret_cast<const KeyT*>(sm.keys[cur])[li]) acc.changed = true;
+                        if (miss) acc.miss = true;
+                    }
                 }
                 make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = sm.idx[cur][li];
@@ -959,6 +1019,30 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         __syncwarp();  // the buffers are free for the fetch of the tile after next
         cur ^= 1u;
     }
+    if (VALIDATE) {
+        const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc.k_or);
+        const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc.k_or >> 32));
+        const uint32_t nlo = __reduce_or_sync(0xffffffffu, ~(uint32_t)acc.k_and);
+        const uint32_t nhi = __reduce_or_sync(0xffffffffu, ~(uint32_t)(acc.k_and >> 32));
+        const uint32_t c = __reduce_add_sync(0xffffffffu, acc.count);
+        if (lane == 0 && c) {
+            atomicOr(&ep.stats[0], ((unsigned long long)hi << 32) | lo);
+            atomicOr(&ep.stats[1], ((unsigned long long)nhi << 32) | nlo);
+            atomicAdd(&ep.stats[2], (unsigned long long)c);
+        }
+        if (__any_sync(0xffffffffu, acc.miss) && lane == 0) atomicOr(&ep.stats[4], 1ull);
+        if (__any_sync(0xffffffffu, acc.changed) && lane == 0) atomicOr(&ep.stats[5], 1ull);
+    }
+}
+
+// The translation chunks of the draw-ordered working storage back into the entity-order rows (lazily: before anything
+// reads or replaces those rows).
+__global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __restrict__ seq_rows, const uint32_t* __restrict__ idx,
+                                                              uint32_t global_first, uint32_t count, RowView rows) {
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= count) return;
+    const uint32_t e = __ldg(idx + pos) - global_first;
+    rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos * 4);
 }
 
 // ---- quad vertices from instances ------------------------------------------------------------------

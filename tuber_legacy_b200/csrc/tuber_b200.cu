@@ -143,8 +143,9 @@ struct tb_ctx {
     // chunked sort (chunked.cuh): final_idx / final_keys are then the chunk-major list (padded per chunk) and final_dst
     // the destination of every list position in the global draw order
     uint32_t* final_dst = nullptr;
-    int chunked_sort = 1;            // option
+    int chunked_sort = 0;            // option; off by default: measured slower than the kept-order paths on B200 (profiles/README.md)
     int chunk_shift_opt = 0;         // option: log2 of the chunk size (0: chosen from the key width)
+    int chunk_l2_hint = 1;           // option: row gathers of the list emit carry the L2 evict_last policy
     bool chunked = false;            // the current plan runs as a chunked sort
     ChunkGeom cg{};
     size_t chunk_cnt_off = 0, chunk_remap_off = 0;  // where the kept chunk tables live in the scratch buffer
@@ -154,6 +155,12 @@ struct tb_ctx {
     float4* seq_rows = nullptr;
     size_t seq_cap = 0;
     bool seq_valid = false, seq_world = false;
+    // ... which is the WORKING storage of moving flat scenes: velocities are kept in draw order too and the velocity
+    // system runs on the copy (emit_sequential_kernel<VALIDATE>); seq_live: the copy holds newer translations than the
+    // entity-order rows, which are brought up to date lazily (ensure_rows_current)
+    float* seq_vel = nullptr;
+    size_t seq_vel_cap = 0;
+    bool seq_has_vel = false, seq_live = false;
     uint32_t clean_streak = 0;  // consecutive frames served by a kept draw order with nothing touched
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
@@ -402,7 +409,19 @@ tb_status mark_presence(tb_ctx* c, int comp, uint64_t first, uint64_t n, int set
     return TB_OK;
 }
 
+// The entity-order rows hold what every tick so far has produced: when the draw-ordered copy is the working storage
+// (seq_live), its translation chunks are written back first.
+tb_status ensure_rows_current(tb_ctx* c) {
+    if (!c->seq_live) return TB_OK;
+    c->seq_live = false;
+    TB_LAUNCH(c, "sync_rows", c->sorted_count * 36ull, sync_rows_kernel, div_up(c->sorted_count, kThreads), kThreads, 0,
+              (const float4*)c->seq_rows, (const uint32_t*)c->final_idx, (uint32_t)c->global_first, (uint32_t)c->sorted_count, c->rows);
+    return TB_OK;
+}
+
 tb_status flush_integrate(tb_ctx* c) {
+    tb_status sync = ensure_rows_current(c);
+    if (sync) return sync;
     if (!c->pending) return TB_OK;
     c->pending = false;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_VELOCITY]) return TB_OK;
@@ -759,6 +778,7 @@ tb_status plan_levels(tb_ctx* c) {
 // Switches the row layout, converting whatever the rows hold (one pass over the storage, out of place).
 tb_status relayout_rows(tb_ctx* c, bool interleaved) {
     if ((c->interleaved != 0) == interleaved) return TB_OK;
+    if (tb_status sy = ensure_rows_current(c)) return sy;
     RowView dst = c->rows;
     float4* fresh = nullptr;
     if (c->rows_touched) {
@@ -1030,6 +1050,7 @@ void fill_list_params(tb_ctx* c, const FrameMode& fm, bool integrate, float4* d_
     lp.global_first = (uint32_t)c->global_first;
     lp.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     lp.plan = c->plan;
+    lp.l2_hint = (uint32_t)c->chunk_l2_hint;
     set_camera(c, &lp);
 }
 
@@ -1193,13 +1214,19 @@ void frame_signature(tb_ctx* c, const FrameMode& fm, bool integrate, const void*
 }
 
 
-// Static scenes: emit from the draw-ordered copy of the rows (see emit_sequential_kernel).
+// Frames served by the draw-ordered copy of the rows (emit_sequential_kernel). validate == false: nothing has touched
+// the scene since the frame that validated it (camera moves). validate == true: the copy is the working storage of a
+// flat sorted scene — a pending tick runs on it, every key is re-checked; *ok as in sorted_fast_frame.
 template <typename KeyT>
-tb_status sequential_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d_order) {
+tb_status sequential_frame(tb_ctx* c, bool validate, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+    *ok = false;
     EmitParams<KeyT> ep{};
     ep.pass.n = (uint32_t)c->sorted_count;
     ep.idx_in = c->final_idx;
+    ep.keys_in = (const KeyT*)c->final_keys;
     ep.seq_rows = c->seq_rows;
+    ep.seq_rows_rw = c->seq_rows;
+    ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
     ep.world = c->seq_world ? c->world : nullptr;  // only tells the kernel which kind of row it reads
     ep.plan = c->plan;
     ep.instances = d_inst;
@@ -1207,14 +1234,30 @@ tb_status sequential_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d
     ep.order = d_order;
     ep.global_first = (uint32_t)c->global_first;
     ep.staged = c->staged_emit;
+    ep.dt = c->pending_dt;
+    ep.integrate = (validate && integrate && c->seq_has_vel) ? c->pending_ticks : 0u;
+    ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     set_camera(c, &ep);
-    TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4), emit_sequential_kernel<KeyT>,
-              2u * (uint32_t)c->sm_count, kThreads, sizeof(OrderedShared), ep);
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!validate) {
+        TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4), (emit_sequential_kernel<KeyT, false>),
+                  2u * (uint32_t)c->sm_count, kThreads, sizeof(SeqShared), ep);
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        *ok = true;
+        return TB_OK;
+    }
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
+    if (ep.integrate) c->seq_live = true;  // the copy now holds newer translations than the entity-order rows
+    TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4 + sizeof(KeyT) + (ep.integrate ? 28 : 0)),
+              (emit_sequential_kernel<KeyT, true>), 2u * (uint32_t)c->sm_count, kThreads, sizeof(SeqShared), ep);
+    tb_status s = read_header(c);
+    if (s) return s;
+    *ok = c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] == 0 && c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] == 0 &&
+          c->h_hdr[2] == c->sorted_count && plan_covers(c->plan, c->h_hdr[0], ~c->h_hdr[1]);
     return TB_OK;
 }
 
-// Third untouched frame in a row: copy the rows (world rows for a hierarchy) into draw order, once.
+// After two validated frames in the kept draw order: copy the rows (world rows for a scene graph) — and, for flat
+// scenes, the velocities — into draw order, once.
 tb_status build_sequential_rows(tb_ctx* c, bool world) {
     c->seq_valid = false;
     size_t cap = c->seq_rows ? c->seq_cap : 0;
@@ -1224,11 +1267,24 @@ tb_status build_sequential_rows(tb_ctx* c, bool world) {
         return TB_OK;  // no memory for the copy: keep gathering
     }
     c->seq_cap = cap;
-    TB_LAUNCH(c, "gather_rows", c->sorted_count * (64 + 64 + 4), gather_rows_kernel, div_up(c->sorted_count * 4, kThreads), kThreads, 0,
-              c->rows, world ? c->world : (const WorldRow*)nullptr, (const uint32_t*)c->final_idx, (uint32_t)c->global_first,
-              (uint32_t)c->sorted_count, c->seq_rows);
+    const bool with_vel = !world && c->store[TB_VELOCITY] && c->vel != nullptr;
+    if (with_vel) {
+        size_t vcap = c->seq_vel ? c->seq_vel_cap : 0;
+        if (grow(c, &c->seq_vel, &vcap, (size_t)c->sorted_count * 3 + 4, sizeof(float)) != TB_OK) {
+            c->seq_vel_cap = 0;
+            cudaGetLastError();
+            return TB_OK;
+        }
+        c->seq_vel_cap = vcap;
+    }
+    TB_LAUNCH(c, "gather_rows", c->sorted_count * (64 + 64 + 4 + (with_vel ? 24 : 0)), gather_rows_kernel, div_up(c->sorted_count * 4, kThreads),
+              kThreads, 0, c->rows, world ? c->world : (const WorldRow*)nullptr, (const uint32_t*)c->final_idx, (uint32_t)c->global_first,
+              (uint32_t)c->sorted_count, c->seq_rows, with_vel ? (const float*)c->vel : (const float*)nullptr, mask_or_null(c, TB_VELOCITY),
+              with_vel ? c->seq_vel : (float*)nullptr);
     c->seq_valid = true;
     c->seq_world = world;
+    c->seq_has_vel = with_vel;
+    c->seq_live = false;
     return TB_OK;
 }
 
@@ -1466,8 +1522,10 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared<uint64_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint32_t>));
     cudaFuncSetAttribute(radix_scatter_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterShared<uint64_t>));
-    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
-    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
@@ -1514,6 +1572,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->final_keys);
     cudaFree(c->final_dst);
     cudaFree(c->seq_rows);
+    cudaFree(c->seq_vel);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1559,6 +1618,7 @@ tb_status tb_ctx_set_max_batches(tb_ctx* c, uint64_t max_batches) {
 tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
     TB_ENTER(c);
     if (!c || !name) return TB_ERR_INVALID;
+    if (tb_status sy = ensure_rows_current(c)) return sy;
     std::string k(name);
     if (k == "interleaved_rows") {
         c->layout_auto = value < 0;
@@ -1587,6 +1647,8 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->plan_valid = false;
         drop_kept_frames(c);
         c->final_valid = c->seq_valid = false;
+    } else if (k == "chunk_l2_hint") {
+        c->chunk_l2_hint = value != 0;
     } else if (k == "chunk_shift") {
         if (value != 0 && (value < 11 || value > 24)) return fail(c, TB_ERR_INVALID, "chunk_shift must be 0 (automatic) or 11..24");
         c->chunk_shift_opt = (int)value;
@@ -1699,6 +1761,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     TB_ENTER(c);
     tb_status s = check_range(c, first, n, src);
     if (s || n == 0) return s;
+    if ((s = ensure_rows_current(c))) return s;
     c->rows_touched = true;
     s = upload_chunks(
         c, src, n, sizeof(tb_sprite),
@@ -1738,6 +1801,7 @@ tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_v
     TB_CUDA(c, cudaMemcpyAsync(c->vel + first * 3, src, n * sizeof(tb_velocity), cudaMemcpyHostToDevice, c->stream));
     c->store[TB_VELOCITY] = true;
     mark_presence(c, TB_VELOCITY, first, n, 1);
+    c->seq_valid = false;  // the draw-ordered copy carries the velocities
     return TB_OK;
 }
 
@@ -1777,6 +1841,7 @@ tb_status tb_upload_presence(tb_ctx* c, int comp, uint64_t first_word, uint64_t 
     c->store[comp] = true;
     c->plan_valid = false;
     drop_kept_frames(c);
+    c->seq_valid = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -2113,15 +2178,19 @@ tb_status tb_system_integrate(tb_ctx* c, float dt) {
     // tuber-winit/src/lib.rs:117-141) run as ONE pass over the rows, each tick rounded on its own
     if (c->pending && memcmp(&dt, &c->pending_dt, sizeof(float)) == 0 && c->pending_ticks < 4096) {
         c->pending_ticks += 1;
-        c->seq_valid = false;
+        if (c->seq_world) c->seq_valid = false;
         return TB_OK;
     }
-    tb_status s = flush_integrate(c);  // earlier ticks of another dt that no frame consumed
-    if (s) return s;
+    if (c->pending) {  // earlier ticks of another dt that no frame consumed
+        tb_status s = flush_integrate(c);
+        if (s) return s;
+    }
     c->pending = true;
     c->pending_dt = dt;
     c->pending_ticks = 1;
-    c->seq_valid = false;  // rows are about to move
+    // a flat scene's draw-ordered copy is working storage: the next frame runs this tick on it; a scene graph's copy
+    // holds world rows, which the tick invalidates
+    if (c->seq_world || !c->seq_has_vel) c->seq_valid = false;
     c->world_valid = false;
     c->frame_valid = false;
     return TB_OK;
@@ -2159,6 +2228,8 @@ tb_status tb_system_spin(tb_ctx* c, float dt) {
     TB_ENTER(c);
     if (!c) return TB_ERR_INVALID;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPIN]) return TB_OK;
+    tb_status s = ensure_rows_current(c);
+    if (s) return s;
     launch_spin(c, dt, c->stream);
     rows_changed_outside_a_frame(c);
     return TB_OK;
@@ -2257,7 +2328,9 @@ tb_status tb_orthographic(float left, float right, float bottom, float top, floa
 }
 
 tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
+    TB_ENTER(c);
     if (!c || path > TB_PATH_SORT) return TB_ERR_INVALID;
+    if (tb_status sy = ensure_rows_current(c)) return sy;
     c->force_path = path;
     c->plan_valid = false;
     drop_kept_frames(c);
@@ -2306,10 +2379,11 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         if (c->chunked) {
             // chunked sort: the kept chunk-major list serves moving and static frames alike (window-local gathers)
             s = chunk_fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done);
-        } else if (untouched && c->seq_valid && !c->seq_world) {
-            if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
-            else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
-            fast_done = true;
+        } else if (c->seq_valid && !c->seq_world) {
+            // rows live in draw order: stream them (a pending tick runs on the copy, with every key re-checked)
+            const bool validate = !untouched;
+            if (c->plan.key64) s = sequential_frame<uint64_t>(c, validate, integrate, d_inst, d_vtx, d_order, &fast_done);
+            else s = sequential_frame<uint32_t>(c, validate, integrate, d_inst, d_vtx, d_order, &fast_done);
         } else {
             if (c->plan.key64) s = sorted_fast_frame<uint64_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
             else s = sorted_fast_frame<uint32_t>(c, integrate, d_inst, d_vtx, d_order, &fast_done);
@@ -2319,8 +2393,13 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         if (fast_done) {
             count = c->sorted_count;
             num_batches = c->sorted_batches;
-            c->clean_streak = untouched ? c->clean_streak + 1 : 0;
-            if (!c->chunked && untouched && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, false))) return s;
+            c->clean_streak += 1;
+            if (!c->chunked && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, false))) return s;
+        } else {
+            // some key changed: the entity-order rows take over again and the full frame below re-sorts
+            if ((s = ensure_rows_current(c))) return s;
+            c->seq_valid = false;
+            c->clean_streak = 0;
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
     }
@@ -2328,11 +2407,12 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         c->sorted_cache && c->plan_valid && c->shard_state != 4) {
         // a scene graph nothing has touched since the frame that left its world rows, sort and draw order (no
         // upload, no tick): the frame is the emit over those, e.g. under a new camera
+        bool seq_ok = false;
         if (c->chunked) {
             s = chunk_replay_hierarchy(c, d_inst, d_vtx, d_order);
         } else if (c->seq_valid && c->seq_world) {
-            if (c->plan.key64) s = sequential_frame<uint64_t>(c, d_inst, d_vtx, d_order);
-            else s = sequential_frame<uint32_t>(c, d_inst, d_vtx, d_order);
+            if (c->plan.key64) s = sequential_frame<uint64_t>(c, false, false, d_inst, d_vtx, d_order, &seq_ok);
+            else s = sequential_frame<uint32_t>(c, false, false, d_inst, d_vtx, d_order, &seq_ok);
         } else {
             if (c->plan.key64) s = replay_hierarchy_frame<uint64_t>(c, d_inst, d_vtx, d_order);
             else s = replay_hierarchy_frame<uint32_t>(c, d_inst, d_vtx, d_order);
@@ -2343,6 +2423,11 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         num_batches = c->sorted_batches;
         c->clean_streak += 1;
         if (!c->chunked && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, true))) return s;
+    }
+    if (!fast_done && c->seq_live) {
+        // whatever kept this frame off the draw-ordered working storage: the entity-order rows take over again
+        if ((s = ensure_rows_current(c))) return s;
+        c->seq_valid = false;
     }
     if (c->static_valid && c->static_buckets && c->plan_valid && !fm.hier) {
         if ((s = fast_frame(c, integrate, d_inst, d_vtx, d_order, &fast_done))) return s;
@@ -2554,6 +2639,8 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
     stats[0] = 0;
     stats[1] = ~0ull;
     stats[2] = 0;
+    if (tb_status sy = ensure_rows_current(c)) return sy;
+    c->seq_valid = false;
     c->shard_state = 0;
     c->frame_valid = false;
     c->sorted_valid = false;  // the multi-GPU protocol re-plans every frame from the global statistics
@@ -3096,6 +3183,7 @@ tb_status tb_shard_set(tb_ctx* c, int rank, int nranks, uint64_t global_first) {
     if (global_first + c->cap > (1ull << 32)) return fail(c, TB_ERR_INVALID, "global entity ids must fit 32 bits");
     c->rank = rank;
     c->nranks = nranks;
+    if (tb_status sy = ensure_rows_current(c)) return sy;
     if (global_first != c->global_first) {
         // final_idx / level lists / captured launches hold ids relative to the old range
         drop_kept_frames(c);
