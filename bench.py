@@ -527,13 +527,13 @@ def main():
         check = None
         if rank == 0:
             # the presenting rank's global list against a single-context frame of the whole scene, byte for byte
-            full = scenes.config5(n=n5)
+            whole = scenes.config5(n=n5)
             one = capi.Context(n5, device=local_rank)
             one.set_stream(stream.cuda_stream)
             one.set_entity_count(n5)
-            one.upload_transforms(0, full.transforms)
-            one.upload_sprites(0, full.sprites)
-            del full
+            one.upload_transforms(0, whole.transforms)
+            one.upload_sprites(0, whole.sprites)
+            del whole
             oo = one.frame()
             m5 = int(lout.num_instances)
             eq = {"order": bool(torch.equal(dev_tensor(lout.d_order, m5 * 4), dev_tensor(oo.d_order, m5 * 4))),

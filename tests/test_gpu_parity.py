@@ -372,6 +372,7 @@ def test_resharding_and_option_toggles_drop_kept_draw_orders():
     {"cuda_graphs": 0},
     {"z_dictionary": 0},
     {"sorted_cache": 0, "static_buckets": 0, "cuda_graphs": 0, "z_dictionary": 0, "small_emit": 0},
+    {"hier_fused": 0},
     {"chunked_sort": 1},
     {"chunked_sort": 1, "chunk_shift": 11},
     {"chunked_sort": 1, "chunk_shift": 13, "sorted_cache": 0},
@@ -993,9 +994,9 @@ def test_graph_replayed_frames_stay_exact(kind):
         util.assert_frame_parity(g, ref.frame())
         launches.append(g.info.kernel_launches)
         assert g.info.sort_passes >= 2
-    # hierarchy: replayed frames report the launches of the captured frame; flat: after two validated frames the rows
-    # move into draw order (one extra copy launch) and every later frame is the streaming emit alone
-    assert len(set(launches[3:] if kind == "flat" else launches[1:])) == 1, launches
+    # after two frames that kept their sort the rows (scene graph: the drawn entities' local rows) move into draw order
+    # (one extra copy launch) and every later frame streams: flat one kernel, scene graph inner level passes + one emit
+    assert len(set(launches[3:])) == 1, launches
     # same frames without graphs
     ctx2 = util.make_ctx(sc, cuda_graphs=0)
     for k in range(7):
@@ -1343,4 +1344,60 @@ def test_working_storage_survives_downloads_and_is_dropped_by_uploads():
         ctx.system_integrate(0.01)
         ref2.step(0.01)
         util.assert_frame_parity(util.GpuFrame(ctx), ref2.frame(), what=f"after partial upload, frame {k}")
+    ctx.close()
+
+
+# ---- scene graphs: the last level composed inside the kept-order emit -------------------------------------------------
+
+@pytest.mark.parametrize("random_parents", [False, True])
+def test_moving_scene_graph_composes_its_leaves_inside_the_emit(random_parents):
+    """Every node moves in x / y. Once the draw order is kept, the level pass runs for the inner levels only and the emit
+    computes world = parent * local for the leaves; leaves without a Sprite are ticked by a side pass. Entity-order
+    transforms, world matrices and frames must stay the oracle's through ticks, a camera-only frame and a z velocity."""
+    sc = scenes.config3(n=50_000, seed=111, random_parents=random_parents)
+    rng = np.random.default_rng(13)
+    v = np.zeros(sc.n, capi.VELOCITY_DTYPE)
+    v["v"][:, 0] = rng.uniform(-30, 30, sc.n)
+    v["v"][:, 1] = rng.uniform(-30, 30, sc.n)
+    sc.velocities = v
+    masks = {capi.TB_SPRITE: util.random_mask(sc.n, 0.8, 3), capi.TB_VELOCITY: util.random_mask(sc.n, 0.9, 4)}
+    ctx, ref, g, r = run_both(sc, masks=masks, ticks=1)
+    util.assert_frame_parity(g, r)
+    launches = []
+    for k in range(6):
+        ticks = 2 if k == 3 else 1
+        for _ in range(ticks):
+            ctx.system_integrate(0.01)
+            ref.step(0.01)
+        gf = util.GpuFrame(ctx)
+        launches.append(gf.info.kernel_launches)
+        util.assert_frame_parity(gf, ref.frame(), what=f"moving scene graph, frame {k}")
+    # inner levels + (side tick) + emit: fewer launches than the full frame, which also runs tile_hist / scans / scatters
+    assert launches[-1] <= 10, launches
+    got = ctx.download_transforms(0, sc.n)
+    want = ref.transforms().view(capi.TRANSFORM_DTYPE).reshape(-1)
+    assert np.array_equal(got["translation"], want["translation"])  # non-renderable leaves were ticked too
+    rf = ref.frame()
+    w = ctx.download_world_matrices(0, sc.n)
+    if util.libm_pinned():
+        assert np.array_equal(w[rf.has_world.astype(bool)], rf.world[rf.has_world.astype(bool)])
+    # camera-only frames after the download (world rows valid again), then ticks again
+    vp = capi.orthographic(-500, 500, -400, 400, -100, 100)
+    ctx.set_view_projection(vp)
+    for k in range(3):
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame(view_proj=vp), what=f"scene graph, camera frame {k}")
+    ctx.set_view_projection(None)
+    # a z velocity on some leaves and inner nodes: keys change, the fused frame detects it and the frame re-sorts
+    v["v"][::5, 2] = 100.0
+    ctx.upload_velocities(0, v)
+    ctx.upload_presence(capi.TB_VELOCITY, 0, masks[capi.TB_VELOCITY])
+    sc2 = scenes.config3(n=50_000, seed=111, random_parents=random_parents)
+    sc2.transforms = ctx.download_transforms(0, sc.n)
+    sc2.velocities = v
+    ref.close()
+    ref = util.make_oracle(sc2, masks)
+    for k in range(4):
+        ctx.system_integrate(0.01)
+        ref.step(0.01)
+        util.assert_frame_parity(util.GpuFrame(ctx), ref.frame(), what=f"scene graph, z velocity, frame {k}")
     ctx.close()

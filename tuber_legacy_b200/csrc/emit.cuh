@@ -52,6 +52,14 @@ struct EmitParams {
     // that will keep them: final_idx[pos] = entity id (global), final_keys[pos] = short key
     uint32_t* final_idx;
     KeyT* final_keys;
+    // scene graphs on the draw-ordered working storage (emit_sequential_kernel<KeyT, true> with world != nullptr): draw
+    // positions whose entity has a local id >= leaf_first belong to the LAST level (leaves: nobody's parent). Their LOCAL
+    // rows, velocities and parent ids live in draw order (sequential streams); the kernel ticks them, composes
+    // world = world[parent] * local from the parent's world row (the parents are a small, L2-resident set, written by
+    // the level pass of the inner levels just before) and re-checks their keys. The other positions (inner levels, a
+    // small minority) read the world row the level pass wrote for them.
+    const uint32_t* seq_par;  // parent (global id) per draw position
+    uint32_t leaf_first;
     const float4* seq_rows;  // emit_sequential_kernel: the rows (or world rows) in draw order, 64 bytes each
     float4* seq_rows_rw;     // ... the same storage, writable: the velocity system's translation write-back
     const float* seq_vel;    // ... velocities in draw order (zero where the entity has none)
@@ -882,13 +890,15 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
 __global__ void __launch_bounds__(kThreads) gather_rows_kernel(RowView rows, const WorldRow* world, const uint32_t* __restrict__ idx,
                                                                 uint32_t global_first, uint32_t count, float4* __restrict__ out,
                                                                 const float* __restrict__ vel, const uint64_t* mask_v,
-                                                                float* __restrict__ vel_out) {
+                                                                float* __restrict__ vel_out, const uint32_t* __restrict__ parent = nullptr,
+                                                                uint32_t* __restrict__ par_out = nullptr) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte chunk: a row's four are adjacent lanes
     const uint32_t pos = t >> 2, ch = t & 3u;
     if (pos >= count) return;
     const uint32_t e = __ldg(idx + pos) - global_first;
     if (vel_out != nullptr && ch < 3u)  // velocities in draw order; zero where the entity has no Velocity
         vel_out[(size_t)pos * 3 + ch] = (vel != nullptr && mask_bit(mask_v, e)) ? __ldg(vel + (size_t)e * 3 + ch) : 0.0f;
+    if (par_out != nullptr && ch == 3u) par_out[pos] = __ldg(parent + e);
     float4 v;
     if (world != nullptr) v = reinterpret_cast<const float4*>(world + e)[ch];
     else v = ch == 0 ? rows.t[(size_t)e * rows.st] : ch == 1 ? rows.a[(size_t)e * rows.st] : rows.b[(size_t)e * rows.sb + (ch & 1u)];
@@ -902,6 +912,7 @@ struct SeqWarpShared {
     float vel[2][kWarpTile * 3];
     unsigned long long keys[2][kWarpTile];  // kept short keys (KeyT)
     uint32_t idx[2][kWarpTile];
+    uint32_t par[2][kWarpTile];             // parent ids (scene graphs)
     unsigned long long kbar[2];
 };
 struct SeqShared {
@@ -912,7 +923,7 @@ struct SeqShared {
 // storage): the velocity system runs on the streamed rows (ep.integrate ticks; translation chunk written back in
 // place, sequentially), every key is recomputed and compared with the kept one, statistics go to `stats` for the host
 // to confirm — all of it on sequential reads. Entity-order rows are brought up to date lazily (sync_rows_kernel).
-template <typename KeyT, bool VALIDATE>
+template <typename KeyT, bool VALIDATE, bool GRAPH = false>
 __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
     __shared__ uint32_t s_zdict[VALIDATE ? kMaxZDict : 1];
@@ -923,7 +934,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
     PrepAcc acc;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SeqWarpShared& sm = reinterpret_cast<SeqShared*>(emit_smem_raw)->w[warp];
-    const bool from_world = ep.world != nullptr;
+    constexpr bool graph = VALIDATE && GRAPH;  // scene graph on the working storage (see EmitParams::seq_par)
+    const bool from_world = ep.world != nullptr && !graph;
     const bool do_int = VALIDATE && ep.integrate != 0 && ep.seq_vel != nullptr && !from_world;
     const uint32_t count = ep.pass.n;
     const uint32_t ntiles = (count + kWarpTile - 1) / kWarpTile;
@@ -933,9 +945,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         const uint32_t ibytes = (cnt * 4u + 15u) & ~15u;
         const uint32_t kbytes = VALIDATE ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
         const uint32_t vbytes = do_int ? ((cnt * 12u + 15u) & ~15u) : 0u;
-        mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes + kbytes + vbytes);
+        mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes + kbytes + vbytes + (graph ? ibytes : 0u));
         bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile * 4, cnt * 64u, &sm.kbar[buf]);
         bulk_g2s(sm.idx[buf], ep.idx_in + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
+        if (graph) bulk_g2s(sm.par[buf], ep.seq_par + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
         if (VALIDATE) bulk_g2s(sm.keys[buf], ep.keys_in + (size_t)t * kWarpTile, kbytes, &sm.kbar[buf]);
         if (do_int) bulk_g2s(sm.vel[buf], ep.seq_vel + (size_t)t * kWarpTile * 3, vbytes, &sm.kbar[buf]);
     };
@@ -954,12 +967,31 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         if (cur) par1 ^= 1u; else par0 ^= 1u;
         float4* rows = sm.rows[cur];
         const uint32_t base = tile * kWarpTile, cnt = min(kWarpTile, count - base);
+        // scene graphs: the world rows this lane's two positions need (a leaf's parent, or an inner node's own) are
+        // requested before anything else of the tile is consumed
+        float4 wr[2][4];
+        bool leaf[2] = {false, false};
+        if (graph) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t li = k * 32 + lane;
+                if (li < cnt) {
+                    const uint32_t e = sm.idx[cur][li] - ep.global_first;
+                    leaf[k] = e >= ep.leaf_first;
+                    const float4* p = reinterpret_cast<const float4*>(ep.world + (leaf[k] ? sm.par[cur][li] - ep.global_first : e));
+                    wr[k][0] = __ldg(p);
+                    wr[k][1] = __ldg(p + 1);
+                    wr[k][2] = __ldg(p + 2);
+                    if (!leaf[k]) wr[k][3] = __ldg(p + 3);
+                }
+            }
+        }
         if (do_int) {
             const float* vel = sm.vel[cur];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const uint32_t li = k * 32 + lane;
-                if (li < cnt) {
+                if (li < cnt && (!graph || leaf[k])) {
                     const float vx = vel[li * 3], vy = vel[li * 3 + 1], vz = vel[li * 3 + 2];
                     if (vx != 0.0f || vy != 0.0f || vz != 0.0f) {  // no Velocity (or a zero one): the value stays
                         float4 a0 = rows[li * 4];
@@ -981,7 +1013,14 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                 Affine w;
                 float sw, shh;
                 uint32_t tl;
-                if (from_world) {
+                if (graph && !leaf[k]) {  // an inner node: the level pass wrote (and key-checked) its world row
+                    w.r0 = wr[k][0];
+                    w.r1 = wr[k][1];
+                    w.r2 = wr[k][2];
+                    sw = wr[k][3].x;
+                    shh = wr[k][3].y;
+                    tl = __float_as_uint(wr[k][3].z);
+                } else if (from_world) {
                     w.r0 = rows[li * 4];
                     w.r1 = rows[li * 4 + 1];
                     w.r2 = rows[li * 4 + 2];
@@ -999,8 +1038,15 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                     sw = r.b1.y;
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
+                    if (graph) {  // a leaf: world = world[parent] * local
+                        Affine P;
+                        P.r0 = wr[k][0];
+                        P.r1 = wr[k][1];
+                        P.r2 = wr[k][2];
+                        w = mul_affine(P, w);
+                    }
                     if (VALIDATE) {
-                        const float z = is_planar(r.a1) ? planar_z(r.a0, r.a1) : local_z(r);
+                        const float z = graph ? w.r2.w : (is_planar(r.a1) ? planar_z(r.a0, r.a1) : local_z(r));
                         const uint64_t key = sort_key(tl >> 16, tl & 0xFFFFu, z);
                         acc.k_or |= key;
                         acc.k_and &= key;
@@ -1037,11 +1083,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
 
 // The translation chunks of the draw-ordered working storage back into the entity-order rows (lazily: before anything
 // reads or replaces those rows).
+// `first`: only entities with a local id >= first own their copy (scene graphs: the leaves).
 __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __restrict__ seq_rows, const uint32_t* __restrict__ idx,
-                                                              uint32_t global_first, uint32_t count, RowView rows) {
+                                                              uint32_t global_first, uint32_t count, RowView rows, uint32_t first) {
     const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= count) return;
     const uint32_t e = __ldg(idx + pos) - global_first;
+    if (e < first) return;
     rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos * 4);
 }
 

@@ -107,12 +107,15 @@ __global__ void __launch_bounds__(kThreads) mark_parent_presence_kernel(uint64_t
 
 // ---- standalone velocity system (when no frame follows the tick) --------------------------------
 
+// `first`, `skip_mask`: only entities [first, n) that are NOT in skip_mask (the scene-graph frames that run the velocity
+// system of the renderable leaves inside the emit tick the remaining leaves here).
 __global__ void __launch_bounds__(kThreads) integrate_kernel(RowView rows, const uint64_t* mask_t, const uint64_t* mask_v,
                                                               const float* __restrict__ vel, float dt, uint32_t ticks,
-                                                              uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                              uint32_t n, uint32_t first = 0, const uint64_t* skip_mask = nullptr) {
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!mask_bit(mask_t, i) || !mask_bit(mask_v, i)) return;
+    if (skip_mask != nullptr && mask_bit(skip_mask, i)) return;
     const size_t o = (size_t)i * rows.st;
     float4 a0 = rows.t[o];
     const float* v = vel + (size_t)i * 3;

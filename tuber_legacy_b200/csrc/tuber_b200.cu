@@ -146,6 +146,7 @@ struct tb_ctx {
     int chunked_sort = 0;            // option; off by default: measured slower than the kept-order paths on B200 (profiles/README.md)
     int chunk_shift_opt = 0;         // option: log2 of the chunk size (0: chosen from the key width)
     int chunk_l2_hint = 1;           // option: row gathers of the list emit carry the L2 evict_last policy
+    int hier_fused = 1;              // option: kept-order scene-graph frames compose the last level inside the emit
     bool chunked = false;            // the current plan runs as a chunked sort
     ChunkGeom cg{};
     size_t chunk_cnt_off = 0, chunk_remap_off = 0;  // where the kept chunk tables live in the scratch buffer
@@ -161,6 +162,13 @@ struct tb_ctx {
     float* seq_vel = nullptr;
     size_t seq_vel_cap = 0;
     bool seq_has_vel = false, seq_live = false;
+    // scene graphs: the copy holds the LOCAL rows (+ velocities + parent ids) of the drawn entities; the last level's
+    // (the leaves') are the working storage, the inner levels stay in the entity-order rows (hierarchy_seq_frame)
+    uint32_t* seq_par = nullptr;
+    size_t seq_par_cap = 0;
+    bool seq_graph = false;
+    uint32_t seq_leaf_first = 0;
+    uint32_t hier_streak = 0;  // consecutive scene-graph frames that kept their sort
     uint32_t clean_streak = 0;  // consecutive frames served by a kept draw order with nothing touched
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
@@ -415,7 +423,8 @@ tb_status ensure_rows_current(tb_ctx* c) {
     if (!c->seq_live) return TB_OK;
     c->seq_live = false;
     TB_LAUNCH(c, "sync_rows", c->sorted_count * 36ull, sync_rows_kernel, div_up(c->sorted_count, kThreads), kThreads, 0,
-              (const float4*)c->seq_rows, (const uint32_t*)c->final_idx, (uint32_t)c->global_first, (uint32_t)c->sorted_count, c->rows);
+              (const float4*)c->seq_rows, (const uint32_t*)c->final_idx, (uint32_t)c->global_first, (uint32_t)c->sorted_count, c->rows,
+              c->seq_graph ? c->seq_leaf_first : 0u);
     return TB_OK;
 }
 
@@ -836,7 +845,7 @@ struct FrameMode {
 };
 
 tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode& fm, const ScratchLayout* L,
-                      uint32_t* key_hist = nullptr) {
+                      uint32_t* key_hist = nullptr, uint32_t max_levels = 0xFFFFFFFFu) {
     const uint32_t n = (uint32_t)c->n;
     PrepParams p{};
     p.n = n;
@@ -882,7 +891,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)c->sm_count * 8u);
         TB_LAUNCH(c, have_plan ? "prepare_flat" : "discover_flat", bytes_in, prepare_flat_kernel, grid, kThreads, 0, p);
     } else {
-        for (uint32_t l = 0; l < c->nlevels; ++l) {
+        for (uint32_t l = 0; l < std::min(c->nlevels, max_levels); ++l) {
             LevelParams lp{};
             lp.prep = p;
             lp.parent = c->sane_parent;
@@ -898,7 +907,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
             TB_LAUNCH(c, have_plan ? "prepare_level" : "discover_level", (uint64_t)lp.count * (64 + 4 + 64 + (p.integrate ? 44 : 0)),
                       prepare_level_kernel, grid, kThreads, 0, lp);
         }
-        c->world_valid = true;
+        c->world_valid = max_levels >= c->nlevels;
     }
     return TB_OK;
 }
@@ -1149,6 +1158,59 @@ tb_status chunk_fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_
     return TB_OK;
 }
 
+// The steady-state frame of a scene graph whose draw order is kept and whose entities move: the level pass runs for
+// every level but the last (velocity system, world rows, key comparison: sequential in entity order), then ONE streaming
+// kernel serves the frame from the draw-ordered working storage — the leaves (typically ~90 % of the entities) are ticked
+// there, composed as world[parent] * local from the parents' L2-resident world rows, and key-checked; their world rows
+// are never written and never re-read. *ok as in sorted_fast_frame.
+template <typename KeyT>
+tb_status hierarchy_seq_frame(tb_ctx* c, bool integrate, const ScratchLayout& L, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+    *ok = false;
+    tb_status s;
+    FrameMode fm{};
+    fm.hier = true;
+    fm.lt_hist = true;
+    const uint32_t last = c->nlevels - 1;
+    TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
+    if ((s = run_prepare(c, true, integrate, fm, &L, nullptr, last))) return s;
+    const bool tick = integrate && c->store[TB_VELOCITY] && c->store[TB_TRANSFORM];
+    if (tick && c->level_count[last] > 0) {
+        // leaves that are not drawn (no Sprite) are not in the working storage: their tick runs on the entity-order rows
+        const uint32_t first = c->level_first[last], end = first + c->level_count[last];
+        TB_LAUNCH(c, "integrate", (uint64_t)c->level_count[last], integrate_kernel, div_up(end - first, kThreads), kThreads, 0, c->rows,
+                  mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, c->pending_ticks, end, first,
+                  mask_or_null(c, TB_SPRITE));
+    }
+    EmitParams<KeyT> ep{};
+    ep.pass.n = (uint32_t)c->sorted_count;
+    ep.idx_in = c->final_idx;
+    ep.keys_in = (const KeyT*)c->final_keys;
+    ep.seq_rows = c->seq_rows;
+    ep.seq_rows_rw = c->seq_rows;
+    ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
+    ep.seq_par = c->seq_par;
+    ep.leaf_first = c->seq_leaf_first;
+    ep.world = c->world;
+    ep.dt = c->pending_dt;
+    ep.integrate = (tick && c->seq_has_vel) ? c->pending_ticks : 0u;
+    ep.plan = c->plan;
+    ep.instances = d_inst;
+    ep.vertices = d_vtx;
+    ep.order = d_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    set_camera(c, &ep);
+    if (ep.integrate) c->seq_live = true;
+    TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4 + 4 + sizeof(KeyT) + (tick ? 28 : 0)),
+              (emit_sequential_kernel<KeyT, true, true>), 2u * (uint32_t)c->sm_count, kThreads, sizeof(SeqShared), ep);
+    if ((s = read_header(c))) return s;
+    *ok = c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] == 0 && c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] == 0 &&
+          c->h_hdr[2] == c->sorted_count && plan_covers(c->plan, c->h_hdr[0], ~c->h_hdr[1]);
+    c->world_valid = false;  // the leaves' world rows were not written
+    return TB_OK;
+}
+
 // A scene graph nothing has touched since the frame that left its world rows and list: the emit over those.
 tb_status chunk_replay_hierarchy(tb_ctx* c, float4* d_inst, float4* d_vtx, uint32_t* d_order) {
     FrameMode fm{};
@@ -1258,8 +1320,9 @@ tb_status sequential_frame(tb_ctx* c, bool validate, bool integrate, float4* d_i
 
 // After two validated frames in the kept draw order: copy the rows (world rows for a scene graph) — and, for flat
 // scenes, the velocities — into draw order, once.
-tb_status build_sequential_rows(tb_ctx* c, bool world) {
+tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
     c->seq_valid = false;
+    c->seq_graph = false;
     size_t cap = c->seq_rows ? c->seq_cap : 0;
     if (grow(c, &c->seq_rows, &cap, (size_t)c->sorted_count * 4 + 4, sizeof(float4)) != TB_OK) {
         c->seq_cap = 0;
@@ -1268,6 +1331,15 @@ tb_status build_sequential_rows(tb_ctx* c, bool world) {
     }
     c->seq_cap = cap;
     const bool with_vel = !world && c->store[TB_VELOCITY] && c->vel != nullptr;
+    if (graph) {
+        size_t pcap = c->seq_par ? c->seq_par_cap : 0;
+        if (grow(c, &c->seq_par, &pcap, (size_t)c->sorted_count + 4, sizeof(uint32_t)) != TB_OK) {
+            c->seq_par_cap = 0;
+            cudaGetLastError();
+            return TB_OK;
+        }
+        c->seq_par_cap = pcap;
+    }
     if (with_vel) {
         size_t vcap = c->seq_vel ? c->seq_vel_cap : 0;
         if (grow(c, &c->seq_vel, &vcap, (size_t)c->sorted_count * 3 + 4, sizeof(float)) != TB_OK) {
@@ -1280,8 +1352,11 @@ tb_status build_sequential_rows(tb_ctx* c, bool world) {
     TB_LAUNCH(c, "gather_rows", c->sorted_count * (64 + 64 + 4 + (with_vel ? 24 : 0)), gather_rows_kernel, div_up(c->sorted_count * 4, kThreads),
               kThreads, 0, c->rows, world ? c->world : (const WorldRow*)nullptr, (const uint32_t*)c->final_idx, (uint32_t)c->global_first,
               (uint32_t)c->sorted_count, c->seq_rows, with_vel ? (const float*)c->vel : (const float*)nullptr, mask_or_null(c, TB_VELOCITY),
-              with_vel ? c->seq_vel : (float*)nullptr);
+              with_vel ? c->seq_vel : (float*)nullptr, graph ? (const uint32_t*)c->sane_parent : (const uint32_t*)nullptr,
+              graph ? c->seq_par : (uint32_t*)nullptr);
     c->seq_valid = true;
+    c->seq_graph = graph;
+    if (graph) c->seq_leaf_first = c->level_first[c->nlevels - 1];
     c->seq_world = world;
     c->seq_has_vel = with_vel;
     c->seq_live = false;
@@ -1526,6 +1601,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
@@ -1573,6 +1650,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->final_dst);
     cudaFree(c->seq_rows);
     cudaFree(c->seq_vel);
+    cudaFree(c->seq_par);
     cudaFree(c->texlayer);
     cudaFree(c->world);
     cudaFree(c->inst);
@@ -1647,6 +1725,8 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->plan_valid = false;
         drop_kept_frames(c);
         c->final_valid = c->seq_valid = false;
+    } else if (k == "hier_fused") {
+        c->hier_fused = value != 0;
     } else if (k == "chunk_l2_hint") {
         c->chunk_l2_hint = value != 0;
     } else if (k == "chunk_shift") {
@@ -2424,6 +2504,26 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         c->clean_streak += 1;
         if (!c->chunked && !c->seq_valid && c->clean_streak >= 2 && (s = build_sequential_rows(c, true))) return s;
     }
+    if (fm.hier && !fast_done && c->hier_fused && c->seq_valid && c->seq_graph && c->level_ranges && c->nlevels > 1 && c->sorted_valid &&
+        c->final_valid && c->fast_clean && c->static_buckets && c->sorted_cache && c->plan_valid && !c->chunked && c->shard_state != 4 &&
+        !c->levels_dirty && c->seq_leaf_first == c->level_first[c->nlevels - 1]) {
+        // scene graph with a kept draw order on the draw-ordered working storage (see hierarchy_seq_frame)
+        const ScratchLayout HL = layout_scratch(c->plan, n, true, false, false);
+        if (HL.alloc_words <= c->scratch_words) {
+            if (c->plan.key64) s = hierarchy_seq_frame<uint64_t>(c, integrate, HL, d_inst, d_vtx, d_order, &fast_done);
+            else s = hierarchy_seq_frame<uint32_t>(c, integrate, HL, d_inst, d_vtx, d_order, &fast_done);
+            if (s) return s;
+            integrate = false;  // the velocity system has run
+            if (fast_done) {
+                count = c->sorted_count;
+                num_batches = c->sorted_batches;
+            } else {
+                if ((s = ensure_rows_current(c))) return s;
+                c->seq_valid = false;
+                c->hier_streak = 0;
+            }
+        }
+    }
     if (!fast_done && c->seq_live) {
         // whatever kept this frame off the draw-ordered working storage: the entity-order rows take over again
         if ((s = ensure_rows_current(c))) return s;
@@ -2606,6 +2706,16 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             c->sorted_count = count;
             c->sorted_batches = num_batches;
             c->fast_clean = true;
+            // scene graphs whose entities move keep coming through here (level passes every frame): after two frames that
+            // kept their sort, the drawn entities' local rows, velocities and parent ids are copied into draw order and
+            // the next frames stream (hierarchy_seq_frame)
+            c->hier_streak = (fm.hier && !resorted) ? c->hier_streak + 1 : 0;
+            if (fm.hier && c->hier_fused && c->static_buckets && c->hier_streak >= 2 && !(c->seq_valid && c->seq_graph) && c->final_valid &&
+                c->level_ranges && c->nlevels > 1 && !c->chunked && (int)plan.ltbits <= c->lt_limit &&
+                c->level_first[c->nlevels - 1] + c->level_count[c->nlevels - 1] == n && c->store[TB_VELOCITY]) {
+                if ((s = build_sequential_rows(c, false, true))) return s;
+                TB_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
         }
         break;
     }
