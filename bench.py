@@ -620,10 +620,18 @@ def main():
                                "note": "whole step (all kernels + the per-frame host sync) against the same peak"},
             "kernels": kernels,
         }
+        # DRAM bytes per launch of the dominant kernel from an `ncu --set full` capture — reported only when that capture
+        # was taken from THIS build (same source hash), otherwise null
         traffic_file = os.path.join(ROOT, "profiles", "emit_traffic.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                from tuber_legacy_b200 import build as tb_build
+                tr = json.load(open(traffic_file))
+                if tr.get("source_sha256") == tb_build.source_hash() and tr.get("entities") == n:
+                    line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                    line["roofline"]["traffic_source"] = tr.get("source")
+                else:
+                    line["roofline"]["traffic_source"] = "profiles/emit_traffic.json is from another build: not reported"
             except Exception:
                 pass
         if full is not None:

@@ -27,6 +27,17 @@ NVCC_FLAGS = [
 ]
 
 
+def source_hash():
+    """sha256 over the CUDA / C++ sources the library is built from: ties committed ncu evidence (profiles/emit_traffic.json)
+    to the build that produced it."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(SOURCES + [x for x in HEADERS if not x.startswith("..")]):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
