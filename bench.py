@@ -105,6 +105,35 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Runs this process on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated (first
+    touch then places the pages there): with several ranks per box the host copies of the e2e leg otherwise all cross
+    the socket interconnect from node 0. Returns what was done, for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for this GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"numa_node": node, "note": "none of the node's CPUs is available to this process"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "note": f"not bound: {type(e).__name__}"}
+
+
 def cpu_reference(steps, warmup, n_sample):
     """The CPU oracle (oracle/: restated tuber-ecs query + tuber-math compose + SPEC batching), single
     thread like the reference, on the first n_sample entities of the same scene."""
@@ -251,6 +280,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -598,7 +628,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": total_entities * e2e_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_total,
-                    "steps": e2e_total, "steps_in_flight": 2, "host_buffers": "pinned (tb_host_alloc)",
+                    "steps": e2e_total, "steps_in_flight": 2, "host_buffers": "pinned (tb_host_alloc)", "rank0_numa": numa,
+                    "h2d_GBps_per_rank": h2d / (e2e_ms / e2e_total * 1e-3) / 1e9, "d2h_GBps_per_rank": d2h / (e2e_ms / e2e_total * 1e-3) / 1e9,
                     "how": "two contexts / streams / host threads take alternate steps so one step's D2H overlaps the "
                            "next step's H2D (PCIe full duplex); every step still copies all inputs in and all outputs out",
                     "order_checksum": checksum},

@@ -29,6 +29,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <typeindex>
 #include <unordered_map>
 #include <unordered_set>
@@ -86,6 +87,66 @@ struct DeltaTime {  // tuber-core/src/lib.rs:13
 // Opt<T> accessor marker (query.rs:226-245): never filters.
 template <class T>
 struct Opt {};
+// `&mut T` accessor marker (query.rs:181-208); a bare T is `&T` (query.rs:159-179).
+template <class T>
+struct Mut {};
+
+struct Spin {  // [SPEC] angular velocity about z, radians per second
+    float w = 0;
+};
+
+// The reference keeps every component in a RefCell (ecs.rs:17): a second exclusive borrow, or a shared one while an
+// exclusive one is alive, PANICS ("already borrowed", query.rs:170-199). Here it throws.
+struct BorrowError : std::logic_error {
+    using std::logic_error::logic_error;
+};
+
+// Ref<T> / RefMut<T>: what the accessors of a query hand out (query.rs:27, 166-208). They hold the slot's borrow flag
+// like std::cell::Ref / RefMut and release it when they go out of scope.
+template <class T>
+class Ref {
+public:
+    Ref(const T* p, int32_t* flag) : p_(p), flag_(flag) {
+        if (*flag_ < 0) throw BorrowError("already mutably borrowed");
+        ++*flag_;
+    }
+    Ref(Ref&& o) noexcept : p_(o.p_), flag_(o.flag_) { o.flag_ = nullptr; }
+    Ref(const Ref&) = delete;
+    Ref& operator=(const Ref&) = delete;
+    ~Ref() {
+        if (flag_) --*flag_;
+    }
+    const T& operator*() const { return *p_; }
+    const T* operator->() const { return p_; }
+
+private:
+    const T* p_;
+    int32_t* flag_;
+};
+template <class T>
+class RefMut {
+public:
+    RefMut(T* p, int32_t* flag, std::function<void()> on_drop) : p_(p), flag_(flag), on_drop_(std::move(on_drop)) {
+        if (*flag_ != 0) throw BorrowError("already borrowed");
+        *flag_ = -1;
+    }
+    RefMut(RefMut&& o) noexcept : p_(o.p_), flag_(o.flag_), on_drop_(std::move(o.on_drop_)) { o.flag_ = nullptr; }
+    RefMut(const RefMut&) = delete;
+    RefMut& operator=(const RefMut&) = delete;
+    ~RefMut() {
+        if (flag_) {
+            *flag_ = 0;
+            if (on_drop_) on_drop_();  // a written device-visible component is pushed by the next device call
+        }
+    }
+    T& operator*() const { return *p_; }
+    T* operator->() const { return p_; }
+
+private:
+    T* p_;
+    int32_t* flag_;
+    std::function<void()> on_drop_;
+};
 
 struct Error : std::runtime_error {
     tb_status status;
@@ -99,14 +160,22 @@ template <> struct device_component<Transform> { static constexpr int id = TB_TR
 template <> struct device_component<Sprite> { static constexpr int id = TB_SPRITE; };
 template <> struct device_component<Velocity> { static constexpr int id = TB_VELOCITY; };
 template <> struct device_component<Parent> { static constexpr int id = TB_PARENT; };
+template <> struct device_component<Spin> { static constexpr int id = TB_SPIN; };
 
-template <class T> struct accessor { using type = T; static constexpr bool required = true; };
-template <class T> struct accessor<Opt<T>> { using type = T; static constexpr bool required = false; };
+template <class T> struct accessor { using type = T; static constexpr bool required = true; static constexpr bool mut = false; using guard = Ref<T>; };
+template <class T> struct accessor<Mut<T>> { using type = T; static constexpr bool required = true; static constexpr bool mut = true; using guard = RefMut<T>; };
+template <class T> struct accessor<Opt<T>> { using type = T; static constexpr bool required = false; static constexpr bool mut = false; using guard = std::optional<Ref<T>>; };
+template <class T> struct accessor<Opt<Mut<T>>> { using type = T; static constexpr bool required = false; static constexpr bool mut = true; using guard = std::optional<RefMut<T>>; };
 
 // One type-erased component column: ComponentStore (ecs.rs:16-53).
 struct Store {
     std::vector<std::shared_ptr<void>> data;  // nullptr == None
     std::vector<uint64_t> bits;               // entities_bitset, bit layout of bitset.rs:15-36
+    mutable std::vector<int32_t> borrow;      // RefCell flag per slot: n > 0 shared borrows, -1 one exclusive borrow
+    int32_t* flag(EntityIndex e) const {
+        if (e >= borrow.size()) borrow.resize(e + 1, 0);
+        return &borrow[e];
+    }
     bool test(EntityIndex e) const { return e / 64 < bits.size() && ((bits[e / 64] >> (e % 64)) & 1u); }
     void set(EntityIndex e) {
         if (e / 64 >= bits.size()) bits.resize(e / 64 + 1, 0);
@@ -241,6 +310,58 @@ public:
         return out;
     }
 
+    // The query as the reference yields it (query.rs:27, 131-141): items `(EntityIndex, (A::RefType, ...))` in descending
+    // index order, every accessor a Ref / RefMut / optional guard with RefCell borrow semantics:
+    //     for (auto it = ecs.query_items<Mut<Transform>, Velocity, Opt<Sprite>>(); auto item = it.next();) {
+    //         auto& [e, row] = *item;  auto& [t, v, s] = row;  t->translation.x += v->x; ...
+    // The guards must not outlive the iterator's Ecs; slots of a column must not be added while guards of it are alive.
+    template <class... As>
+    class QueryIterator {
+    public:
+        using Item = std::tuple<EntityIndex, std::tuple<typename detail::accessor<As>::guard...>>;
+        QueryIterator(Ecs* ecs, std::vector<EntityIndex> matches) : ecs_(ecs), matches_(std::move(matches)) {}
+        std::optional<Item> next() {  // query.rs:131-141
+            if (pos_ >= matches_.size()) return std::nullopt;
+            const EntityIndex e = matches_[pos_++];
+            return Item(e, std::tuple<typename detail::accessor<As>::guard...>(ecs_->template fetch<As>(e)...));
+        }
+
+    private:
+        Ecs* ecs_;
+        std::vector<EntityIndex> matches_;  // already in iteration (descending) order
+        std::size_t pos_ = 0;
+    };
+    template <class... As>
+    QueryIterator<As...> query_items() {
+        return QueryIterator<As...>(this, query<As...>());
+    }
+    // ecs.rs:172-174
+    template <class... As>
+    std::optional<typename QueryIterator<As...>::Item> query_one_by_id(EntityIndex id) {
+        for (EntityIndex e : query<As...>())
+            if (e == id) return typename QueryIterator<As...>::Item(e, std::tuple<typename detail::accessor<As>::guard...>(fetch<As>(e)...));
+        return std::nullopt;
+    }
+    // Accessor::fetch (query.rs:170-177, 192-199, 230-232)
+    template <class A>
+    typename detail::accessor<A>::guard fetch(EntityIndex e) {
+        using Acc = detail::accessor<A>;
+        using T = typename Acc::type;
+        if constexpr (std::is_same_v<T, Transform>) refresh_transforms();
+        auto it = stores_.find(std::type_index(typeid(T)));
+        T* p = nullptr;
+        if (it != stores_.end() && e < it->second.data.size()) p = static_cast<T*>(it->second.data[e].get());
+        if constexpr (!Acc::required) {
+            if (!p) return std::nullopt;
+            if constexpr (Acc::mut) return RefMut<T>(p, it->second.flag(e), [this, e] { mark_dirty<T>(e); });
+            else return Ref<T>(p, it->second.flag(e));
+        } else {
+            if (!p) throw Error(TB_ERR_INVALID, "fetch: required component missing");  // cannot happen for matches
+            if constexpr (Acc::mut) return RefMut<T>(p, it->second.flag(e), [this, e] { mark_dirty<T>(e); });
+            else return Ref<T>(p, it->second.flag(e));
+        }
+    }
+
     // Component access (what the Ref / RefMut guards of query.rs:166-208 give). nullptr == None.
     template <class C>
     const C* get(EntityIndex e) {
@@ -266,10 +387,11 @@ public:
     }
 
     // ---- device side -------------------------------------------------------------------------
-    tb_ctx* ctx() { return ctx_; }
+    tb_ctx* ctx() const { return ctx_; }
 
-    // Pushes every dirty range of the device-visible columns.
-    void flush() {
+    // Pushes every dirty range of the device-visible columns. const: render_scene takes `&Ecs`
+    // (tuber-graphics/src/lib.rs:34-36); what changes is the device mirror's bookkeeping, not the Ecs.
+    void flush() const {
         if (count_dirty_) {
             check(tb_set_entity_count(ctx_, next_), "tb_set_entity_count");
             count_dirty_ = false;
@@ -278,6 +400,7 @@ public:
         push<Sprite>();
         push<Velocity>();
         push<Parent>();
+        push<Spin>();
     }
     // A device system has written Transforms: host copies are stale until read again.
     void device_wrote_transforms() { transforms_stale_ = true; }
@@ -334,11 +457,11 @@ private:
         else all_device = false;
     }
     template <class C>
-    void push() {
+    void push() const {
         constexpr int id = detail::device_component<C>::id;
         auto it = stores_.find(std::type_index(typeid(C)));
         if (it == stores_.end()) return;
-        detail::Store& s = it->second;
+        const detail::Store& s = it->second;
         if (value_dirty_[id].any()) {
             const EntityIndex lo = value_dirty_[id].lo, hi = std::min<EntityIndex>(value_dirty_[id].hi, next_);
             if constexpr (std::is_same_v<C, Parent>) {
@@ -354,6 +477,8 @@ private:
                     check(tb_upload_transforms(ctx_, lo, hi - lo, reinterpret_cast<const tb_transform*>(buf.data())), "tb_upload_transforms");
                 else if constexpr (std::is_same_v<C, Sprite>)
                     check(tb_upload_sprites(ctx_, lo, hi - lo, reinterpret_cast<const tb_sprite*>(buf.data())), "tb_upload_sprites");
+                else if constexpr (std::is_same_v<C, Spin>)
+                    check(tb_upload_spins(ctx_, lo, hi - lo, reinterpret_cast<const float*>(buf.data())), "tb_upload_spins");
                 else
                     check(tb_upload_velocities(ctx_, lo, hi - lo, reinterpret_cast<const tb_velocity*>(buf.data())), "tb_upload_velocities");
             }
@@ -388,8 +513,10 @@ private:
     std::unordered_map<std::type_index, detail::Store> stores_;             // Components (ecs.rs:11)
     std::unordered_map<std::type_index, std::shared_ptr<void>> resources_;  // Resources (ecs.rs:12)
     std::unique_ptr<std::type_index> device_type_[TB_COMPONENT_COUNT];
-    detail::DirtyRange value_dirty_[TB_COMPONENT_COUNT], presence_dirty_[TB_COMPONENT_COUNT];
-    bool count_dirty_ = false, transforms_stale_ = false;
+    // the device mirror's bookkeeping (changed by const calls: flush() from render_scene(&Ecs))
+    mutable detail::DirtyRange value_dirty_[TB_COMPONENT_COUNT], presence_dirty_[TB_COMPONENT_COUNT];
+    mutable bool count_dirty_ = false;
+    bool transforms_stale_ = false;
 };
 
 // system.rs:5-6 — Ok(()) is an empty optional, Err(e) carries the message.
@@ -439,6 +566,37 @@ inline SystemResult velocity_system(Ecs& ecs) {
     return Ok();
 }
 
+// [SPEC] the spin system as a device system: angle.z += spin * dt.
+inline SystemResult spin_system(Ecs& ecs) {
+    DeltaTime* dt = ecs.shared_resource<DeltaTime>();
+    if (!dt) return Err("DeltaTime resource missing");
+    try {
+        ecs.flush();
+        ecs.check(tb_system_spin(ecs.ctx(), (float)dt->dt), "tb_system_spin");
+        ecs.device_wrote_transforms();
+    } catch (const Error& e) {
+        return Err(e.what());
+    }
+    return Ok();
+}
+
+// A bundle of built-in device systems stepped with ONE library call (SystemBundle::step order, system.rs:17-23):
+// systems with disjoint access sets run concurrently on forked streams, the state afterwards is the sequential one.
+inline SystemResult device_bundle_step(Ecs& ecs, const std::vector<int>& systems, std::vector<uint32_t>* stages = nullptr) {
+    DeltaTime* dt = ecs.shared_resource<DeltaTime>();
+    if (!dt) return Err("DeltaTime resource missing");
+    try {
+        ecs.flush();
+        std::vector<uint32_t> st(systems.size());
+        ecs.check(tb_bundle_step(ecs.ctx(), systems.data(), (uint32_t)systems.size(), (float)dt->dt, st.data()), "tb_bundle_step");
+        if (stages) *stages = st;
+        ecs.device_wrote_transforms();
+    } catch (const Error& e) {
+        return Err(e.what());
+    }
+    return Ok();
+}
+
 // tuber-graphics/src/lib.rs:25-36
 struct GraphicsError {
     std::string what;
@@ -448,7 +606,7 @@ using GraphicsResult = std::optional<GraphicsError>;  // nullopt == Ok(())
 class GraphicsAPI {
 public:
     virtual ~GraphicsAPI() = default;
-    virtual GraphicsResult render_scene(Ecs& ecs) = 0;
+    virtual GraphicsResult render_scene(const Ecs& ecs) = 0;  // tuber-graphics/src/lib.rs:34-36: `&Ecs`
 };
 
 // The batching renderer behind render_scene: leaves instances / vertices / batches on the device
@@ -467,7 +625,7 @@ public:
     }
     void clear_camera() { has_camera_ = false; }
 
-    GraphicsResult render_scene(Ecs& ecs) override {
+    GraphicsResult render_scene(const Ecs& ecs) override {
         try {
             ecs.flush();
             ecs.check(tb_frame_set_view_projection(ecs.ctx(), has_camera_ ? view_proj_ : nullptr), "tb_frame_set_view_projection");
@@ -502,7 +660,7 @@ public:
 
 private:
     tb_frame_out frame_{};
-    Ecs* ecs_ = nullptr;
+    const Ecs* ecs_ = nullptr;
     float view_proj_[16] = {};
     bool has_camera_ = false;
 };

@@ -134,6 +134,85 @@ static void source_only_semantics() {
     std::puts("ok source_only_semantics");
 }
 
+// Query items as the reference yields them (query.rs:27, 131-141) and the RefCell borrow rules (query.rs:170-199).
+static void query_items_and_borrows() {
+    Ecs ecs(64);
+    for (int k = 0; k < 6; ++k) {
+        Transform t;
+        t.translation = {float(k), 0, 0};
+        if (k % 2) ecs.insert(t, Velocity{1, 2, 0});
+        else ecs.insert(t, Velocity{1, 2, 0}, Sprite{4, 4, 0, 0});
+    }
+    // (EntityIndex, (RefMut<Transform>, Ref<Velocity>, Option<Ref<Sprite>>)), descending
+    std::vector<EntityIndex> seen;
+    int with_sprite = 0;
+    for (auto it = ecs.query_items<tuber::Mut<Transform>, Velocity, tuber::Opt<Sprite>>(); auto item = it.next();) {
+        auto& [e, row] = *item;
+        auto& [t, v, s] = row;
+        t->translation.x += v->x;  // the idiom of system.rs:132-137
+        t->translation.y += v->y;
+        with_sprite += s.has_value();
+        seen.push_back(e);
+    }
+    CHECK((seen == std::vector<EntityIndex>{5, 4, 3, 2, 1, 0}) && with_sprite == 3);
+    CHECK(ecs.get<Transform>(2)->translation.x == 3.0f && ecs.get<Transform>(2)->translation.y == 2.0f);
+    // the written Transforms reach the device with the next device call: a frame sees them
+    tuber::Graphics gfx;
+    CHECK(!gfx.render_scene(ecs).has_value());
+    auto inst = gfx.instances();
+    auto order = gfx.order();
+    for (size_t p = 0; p < order.size(); ++p) CHECK(inst[p].model[12] == float(order[p]) + 1.0f);  // column-major translation.x
+    // two shared borrows coexist; an exclusive one conflicts with either kind (RefCell: "already borrowed")
+    {
+        auto a = ecs.query_one_by_id<Transform>(3);
+        auto b = ecs.query_one_by_id<Transform>(3);
+        CHECK(a.has_value() && b.has_value());
+        bool threw = false;
+        try {
+            auto c = ecs.query_one_by_id<tuber::Mut<Transform>>(3);
+        } catch (const tuber::BorrowError&) { threw = true; }
+        CHECK(threw);
+    }
+    {
+        auto a = ecs.query_one_by_id<tuber::Mut<Transform>>(3);  // released guards: exclusive borrow succeeds
+        CHECK(a.has_value());
+        bool threw = false;
+        try {
+            auto b = ecs.query_one_by_id<Transform>(3);
+        } catch (const tuber::BorrowError&) { threw = true; }
+        CHECK(threw);
+        auto other = ecs.query_one_by_id<tuber::Mut<Transform>>(4);  // another entity's slot is another RefCell
+        CHECK(other.has_value());
+    }
+    CHECK(!ecs.query_one_by_id<Sprite>(1).has_value());  // entity 1 has no Sprite
+    std::puts("ok query_items_and_borrows");
+}
+
+// A second device system and the bundle scheduler through the host API.
+static void device_bundle() {
+    Ecs ecs(64);
+    for (int k = 0; k < 8; ++k) {
+        Transform t;
+        t.angle = {0, 0, 0.25f * k};
+        ecs.insert(t, Sprite{4, 4, 0, 0}, Velocity{1, 0, 0}, tuber::Spin{2.0f});
+    }
+    ecs.insert_shared_resource(tuber::DeltaTime{0.5});
+    std::vector<uint32_t> stages;
+    CHECK(!tuber::device_bundle_step(ecs, {TB_SYSTEM_VELOCITY, TB_SYSTEM_SPIN}, &stages).has_value());
+    CHECK((stages == std::vector<uint32_t>{0, 0}));  // disjoint access sets: one stage
+    CHECK(ecs.get<Transform>(3)->translation.x == 0.5f);
+    CHECK(ecs.get<Transform>(3)->angle.z == 0.25f * 3 + 2.0f * 0.5f);
+    tuber::SystemBundle<int> bundle;
+    bundle.add_system(std::function<tuber::SystemResult(Ecs&)>(tuber::spin_system));
+    bundle.add_system(std::function<tuber::SystemResult(Ecs&)>(tuber::velocity_system));
+    int ad = 0;
+    CHECK(!bundle.step(ecs, ad).has_value());
+    tuber::Graphics gfx;
+    CHECK(!gfx.render_scene(ecs).has_value());  // the queued velocity tick is consumed by the frame
+    CHECK(ecs.get<Transform>(3)->translation.x == 1.0f && ecs.get<Transform>(3)->angle.z == 0.25f * 3 + 2.0f);
+    std::puts("ok device_bundle");
+}
+
 static bool close(float g, float r, float scale) { return std::fabs(g - r) <= 1e-5f * std::max(std::fabs(r), scale); }
 
 struct Gen {
@@ -273,6 +352,8 @@ int main() {
         ecs_query_one_and_optional();
         systems();
         source_only_semantics();
+        query_items_and_borrows();
+        device_bundle();
         frame_parity(false);
         frame_parity(true);
     } catch (const std::exception& e) {

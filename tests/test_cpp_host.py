@@ -37,7 +37,7 @@ def test_cpp_host_replays_reference_tests_and_matches_oracle():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
-    for name in ("ecs_new_and_insert", "ecs_query", "ecs_query_one_and_optional", "systems", "source_only_semantics",
+    for name in ("ecs_new_and_insert", "ecs_query", "ecs_query_one_and_optional", "systems", "source_only_semantics", "query_items_and_borrows", "device_bundle",
                  "frame_parity(flat)", "frame_parity(hierarchy)"):
         assert "ok " + name in r.stdout
     assert "ALL OK" in r.stdout
