@@ -362,8 +362,9 @@ TB_API tb_status tb_vertices_from_instances(tb_ctx* ctx, const void* d_instances
  *                             buffers mapped with tb_ipc_open: the emit kernel then stores straight
  *                             over NVLink), and builds the global batch table.
  *
- * Exact for short keys up to TB_SHARD_MAX_KEY_BITS bits (tb_shard_plan returns TB_ERR_UNSUPPORTED
- * beyond, e.g. continuous z: such scenes need a merge at the presenting rank).
+ * Histogram placement is exact for short keys up to TB_SHARD_MAX_KEY_BITS bits; tb_shard_plan returns
+ * TB_ERR_UNSUPPORTED beyond (e.g. continuous z). tb_frame_sharded (below) serves such scenes too: the
+ * ranks all-gather their sorted full keys and co-rank them.
  * Parent links must resolve inside the context: a shard additionally stores, after its own id
  * range and WITHOUT a Sprite, the ancestors of its entities that live on other ranks, and uploads
  * Parent values as global_first + local index. Their world matrices are then recomputed on this

@@ -31,7 +31,8 @@ def main():
                 raise SystemExit("no exchange id from rank 0")
             time.sleep(0.05)
         sid = open(id_file, "rb").read()
-    make = {"config2": lambda **kw: scenes.config2(n=n, seed=61, **kw), "config4": lambda **kw: scenes.config4(n=n, seed=62, **kw)}[kind]
+    make = {"config2": lambda **kw: scenes.config2(n=n, seed=61, **kw), "config4": lambda **kw: scenes.config4(n=n, seed=62, **kw),
+            "config2_random_z": lambda **kw: scenes.config2(n=n, seed=63, z_mode="random", **kw)}[kind]
     first, count = scenes.shard_range(n, rank, world)
     sc = make(first=first, count=count)
     ctx = capi.Context(max(count, 1), device=rank)

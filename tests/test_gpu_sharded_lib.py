@@ -86,23 +86,36 @@ def test_sharded_particles_tick_and_steady_frames():
     util.assert_frame_parity(g, ref.frame(), what="tb_frame_sharded, particles, third frame")
 
 
-def test_sharded_empty_ranks_and_wide_keys():
+def test_sharded_empty_ranks():
     sc = scenes.config2(n=5, seed=53)          # fewer entities than ranks: some shards are empty
     g = run_local(sc, 8)
     util.assert_frame_parity(g, util.make_oracle(sc).frame())
-    wide = scenes.config2(n=20_000, seed=54, z_mode="random")
-    sid = capi.shard_local_id()
-    with capi.Context(wide.n) as ctx:
-        ctx.shard_init(0, 1, sid, 0, 0)
-        ctx.set_entity_count(wide.n)
-        ctx.upload_transforms(0, wide.transforms)
-        ctx.upload_sprites(0, wide.sprites)
-        with pytest.raises(capi.TuberError) as e:
-            ctx.frame_sharded()
-        assert e.value.status == capi.TB_ERR_UNSUPPORTED  # refused, never approximated
 
 
-@pytest.mark.parametrize("kind", ["config2", "config4"])
+@pytest.mark.parametrize("nranks", [1, 3, 8])
+def test_sharded_wide_keys_are_served_by_co_ranking(nranks):
+    """continuous z: 40+ key bits, far beyond histogram placement. tb_frame_sharded all-gathers the ranks' sorted full keys
+    and co-ranks; the list must be the oracle's, ties between ranks in entity order included."""
+    sc = scenes.config2(n=60_000, seed=54, z_mode="random")
+    sc.transforms["translation"][::7, 2] = 0.25  # many equal keys across ranks: the tie-break matters
+    g = run_local(sc, nranks, frames=2)
+    assert g.info.key_bits > 22
+    util.assert_frame_parity(g, util.make_oracle(sc).frame(), what=f"sharded wide keys, {nranks} ranks")
+
+
+def test_sharded_wide_keys_with_ticks():
+    sc = scenes.config4(n=40_000, seed=55)
+    rng = np.random.default_rng(5)
+    sc.transforms["translation"][:, 2] = rng.uniform(-1, 1, sc.n).astype(np.float32)
+    sc.velocities["v"][:, 2] = rng.uniform(-1, 1, sc.n).astype(np.float32)
+    ref = util.make_oracle(sc)
+    for _ in range(2):
+        ref.step(0.01)
+    g = run_local(sc, 4, ticks=1, frames=2)
+    util.assert_frame_parity(g, ref.frame(), what="sharded wide keys, z velocities")
+
+
+@pytest.mark.parametrize("kind", ["config2", "config4", "config2_random_z"])
 def test_nccl_multiprocess_list_equals_single_context_frame(kind):
     import torch
     world = min(4, torch.cuda.device_count())

@@ -92,3 +92,60 @@ __global__ void __launch_bounds__(kThreads) place_write_kernel(const uint32_t* _
 }
 
 }  // namespace tb
+
+// ---- wide keys: exact global order by co-ranking sorted key arrays ------------------------------------
+//
+// Short keys wider than TB_SHARD_MAX_KEY_BITS (continuous z) cannot be placed from a histogram. Every rank then sorts
+// its shard as usual, the ranks all-gather their sorted FULL 64-bit keys (8 B per element, to every rank), and an
+// element's global position is its local position plus, for every other rank, the number of that rank's elements that
+// come before it: keys <= k on lower ranks (their ids are smaller: the entity-id tie-break), keys < k on higher ranks.
+namespace tb {
+
+// Full sort key of every local draw position: from the world row (scene graphs) or the row.
+__global__ void __launch_bounds__(kThreads) draw_keys_kernel(const uint32_t* __restrict__ order, uint32_t global_first, uint32_t count,
+                                                              RowView rows, const WorldRow* world, unsigned long long* keys, uint32_t padded) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= padded) return;
+    if (p >= count) {
+        keys[p] = ~0ull;  // padding up to the longest rank's count
+        return;
+    }
+    const uint32_t e = __ldg(order + p) - global_first;
+    if (world != nullptr) {
+        const float4* w = reinterpret_cast<const float4*>(world + e);
+        keys[p] = world_key(w[2], w[3]);
+    } else {
+        const float4 a0 = rows.t[(size_t)e * rows.st], a1 = rows.a[(size_t)e * rows.st];
+        keys[p] = flat_key(rows, e, a0, a1);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) corank_kernel(const unsigned long long* __restrict__ all_keys, const unsigned long long* __restrict__ counts,
+                                                           uint32_t stride, uint32_t nranks, uint32_t rank, uint32_t count, uint32_t* dst) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    const unsigned long long k = all_keys[(size_t)rank * stride + p];
+    uint32_t pos = p;
+    for (uint32_t r = 0; r < nranks; ++r) {
+        if (r == rank) continue;
+        const unsigned long long* a = all_keys + (size_t)r * stride;
+        uint32_t lo = 0, hi = (uint32_t)counts[r];
+        if (r < rank) {  // upper bound: elements with key <= k come first
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(a + mid) <= k) lo = mid + 1;
+                else hi = mid;
+            }
+        } else {         // lower bound: only elements with key < k come first
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(a + mid) < k) lo = mid + 1;
+                else hi = mid;
+            }
+        }
+        pos += lo;
+    }
+    dst[p] = pos;
+}
+
+}  // namespace tb

@@ -230,6 +230,11 @@ struct tb_ctx {
     bool list_ipc = false;       // list_inst / list_order were opened with cudaIpcOpenMemHandle
     uint64_t* d_xchg = nullptr;  // device: [4] send + [4 * nranks] receive words
     uint64_t* h_xchg = nullptr;  // pinned mirror
+    unsigned long long* merge_keys = nullptr;  // wide keys: this rank's sorted full keys, padded to the longest rank
+    unsigned long long* merge_all = nullptr;   // ... and every rank's
+    size_t merge_keys_cap = 0, merge_all_cap = 0;
+    BatchOut* merge_batches = nullptr;         // every rank's local batch table
+    size_t merge_batches_cap = 0;
     uint32_t* shard_hist = nullptr;      // [nbins] this rank's short-key histogram
     uint32_t* shard_all_hists = nullptr; // [nranks * nbins]
     size_t shard_hist_cap = 0, shard_all_cap = 0;
@@ -3041,10 +3046,139 @@ static tb_status shard_finalize_impl(tb_ctx* c, bool collective) {
     c->d_xchg = c->h_xchg = nullptr;
     cudaFree(c->shard_hist);
     cudaFree(c->shard_all_hists);
+    cudaFree(c->merge_keys);
+    cudaFree(c->merge_all);
+    cudaFree(c->merge_batches);
+    c->merge_keys = c->merge_all = nullptr;
+    c->merge_batches = nullptr;
+    c->merge_keys_cap = c->merge_all_cap = c->merge_batches_cap = 0;
     c->shard_hist = c->shard_all_hists = nullptr;
     c->shard_hist_cap = c->shard_all_cap = 0;
     c->comm.reset();
     c->frame_valid = false;
+    return TB_OK;
+}
+
+// tb_frame_sharded for short keys wider than TB_SHARD_MAX_KEY_BITS (continuous z): every rank sorts and frames its own
+// shard, the ranks all-gather their sorted full keys and co-rank (shard.cuh), and a second emit over (entity,
+// destination) pairs stores the instances at their global positions in the presenter's list. Slower than histogram
+// placement (an extra all-gather of 8 B per element to every rank, binary searches, two emits) but exact.
+static tb_status sharded_merge_frame(tb_ctx* c, tb_frame_out* out) {
+    Comm& comm = *c->comm;
+    const uint32_t nranks = (uint32_t)comm.nranks;
+    tb_status s;
+    // 1. the shard's own frame into its own buffers (the tick was consumed by tb_shard_key_stats)
+    c->shard_state = 0;
+    c->ext_inst = c->ext_vtx = c->ext_order = nullptr;
+    c->ext_cap = 0;
+    tb_frame_out local{};
+    if ((s = tb_frame_transform_batch(c, &local))) return s;
+    const uint64_t count = local.num_instances, nb = local.num_batches;
+    // 2. counts and batch-table sizes of every rank
+    uint64_t counts[64], nbs[64];
+    if (nranks > 64) return fail(c, TB_ERR_UNSUPPORTED, "more than 64 ranks");
+    for (int round = 0; round < 2; ++round) {
+        c->h_xchg[0] = round == 0 ? count : nb;
+        TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 8, cudaMemcpyHostToDevice, c->stream));
+        if (!comm.all_gather(c->d_xchg, c->d_xchg + 4 + (round ? nranks : 0), 8, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 16, cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint64_t total = 0, maxcount = 1, maxnb = 1;
+    for (uint32_t r = 0; r < nranks; ++r) {
+        counts[r] = c->h_xchg[4 + r];
+        nbs[r] = c->h_xchg[4 + nranks + r];
+        total += counts[r];
+        maxcount = std::max(maxcount, counts[r]);
+        maxnb = std::max(maxnb, nbs[r]);
+    }
+    if (total > c->list_cap) return fail(c, TB_ERR_CAPACITY, "more instances than the draw list was sized for");
+    // 3. sorted full keys of every rank
+    if ((s = grow(c, &c->merge_keys, &c->merge_keys_cap, (size_t)maxcount, 8))) return s;
+    if ((s = grow(c, &c->merge_all, &c->merge_all_cap, (size_t)maxcount * nranks, 8))) return s;
+    const bool hier = c->nlevels > 1;
+    TB_LAUNCH(c, "draw_keys", maxcount * 8 + count * 68, draw_keys_kernel, div_up(maxcount, kThreads), kThreads, 0, (const uint32_t*)c->order,
+              (uint32_t)c->global_first, (uint32_t)count, c->rows, hier ? (const WorldRow*)c->world : (const WorldRow*)nullptr, c->merge_keys,
+              (uint32_t)maxcount);
+    if (!comm.all_gather(c->merge_keys, c->merge_all, (size_t)maxcount * 8, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    // 4. global position of every local draw position
+    if ((s = ensure_sort_buffers(c, std::max<uint64_t>(c->n, 1), c->sort_keybytes ? c->sort_keybytes : 4))) return s;
+    c->sorted_valid = c->final_valid = c->seq_valid = false;  // final_idx / final_dst are reused below
+    if (count) {
+        TB_CUDA(c, cudaMemcpyAsync(c->final_idx, c->order, count * 4, cudaMemcpyDeviceToDevice, c->stream));
+        TB_LAUNCH(c, "corank", count * 8ull * nranks, corank_kernel, div_up(count, kThreads), kThreads, 0, (const unsigned long long*)c->merge_all,
+                  (const unsigned long long*)(c->d_xchg + 4), (uint32_t)maxcount, nranks, (uint32_t)c->rank, (uint32_t)count, c->final_dst);
+    }
+    // 5. the global batch table: the ranks' tables merged by (layer, texture) on the host (a few thousand entries)
+    if ((s = grow(c, &c->merge_batches, &c->merge_batches_cap, (size_t)maxnb * (nranks + 1), sizeof(BatchOut)))) return s;
+    BatchOut* send = c->merge_batches + (size_t)maxnb * nranks;
+    TB_CUDA(c, cudaMemsetAsync(send, 0, maxnb * sizeof(BatchOut), c->stream));
+    if (nb) TB_CUDA(c, cudaMemcpyAsync(send, c->batches, nb * sizeof(BatchOut), cudaMemcpyDeviceToDevice, c->stream));
+    if (!comm.all_gather(send, c->merge_batches, (size_t)maxnb * sizeof(BatchOut), c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    std::vector<BatchOut> tables((size_t)maxnb * nranks);
+    TB_CUDA(c, cudaMemcpyAsync(tables.data(), c->merge_batches, tables.size() * sizeof(BatchOut), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<std::pair<uint64_t, uint64_t>> lt;  // ((layer << 32) | texture, count)
+    for (uint32_t r = 0; r < nranks; ++r)
+        for (uint64_t k = 0; k < nbs[r]; ++k) {
+            const BatchOut& b = tables[(size_t)r * maxnb + k];
+            lt.emplace_back(((uint64_t)b.layer << 32) | b.texture, b.count);
+        }
+    std::sort(lt.begin(), lt.end());
+    std::vector<BatchOut> merged;
+    uint64_t first = 0;
+    for (size_t k = 0; k < lt.size(); ++k) {
+        if (merged.empty() || (((uint64_t)merged.back().layer << 32) | merged.back().texture) != lt[k].first)
+            merged.push_back(BatchOut{(uint32_t)(lt[k].first >> 32), (uint32_t)lt[k].first, (uint32_t)first, 0});
+        merged.back().count += (uint32_t)lt[k].second;
+        first += lt[k].second;
+    }
+    if (merged.size() > c->max_batches) return fail(c, TB_ERR_CAPACITY, "more batches than tb_ctx_set_max_batches allows");
+    if (!merged.empty())
+        TB_CUDA(c, cudaMemcpyAsync(c->batches, merged.data(), merged.size() * sizeof(BatchOut), cudaMemcpyHostToDevice, c->stream));
+    // 6. emit at the global positions into the presenter's list
+    if (count) {
+        uint32_t shift = 6;
+        while ((1ull << shift) < count) ++shift;
+        c->h_xchg[0] = count;  // low word: the single chunk's element count
+        TB_CUDA(c, cudaMemcpyAsync(c->scratch + kHdrPending, c->h_xchg, 4, cudaMemcpyHostToDevice, c->stream));
+        ListParams lp{};
+        lp.ids = c->final_idx;
+        lp.dst = c->final_dst;
+        lp.chunk_cnt = c->scratch + kHdrPending;
+        lp.chunk_shift = shift;
+        lp.npad = 1u << shift;
+        lp.rows = c->rows;
+        lp.world = hier ? c->world : nullptr;
+        lp.instances = (float4*)c->list_inst;
+        lp.vertices = nullptr;
+        lp.order = (uint32_t*)c->list_order;
+        lp.global_first = (uint32_t)c->global_first;
+        lp.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+        lp.plan = c->plan;
+        set_camera(c, &lp);
+        TB_LAUNCH(c, "emit_list", count * (64 + 80 + 4 + 8), emit_list_kernel<false>, 2u * (uint32_t)c->sm_count, kThreads, sizeof(ListShared), lp);
+    }
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));  // `merged` (pageable) and the chunk count have been consumed
+    if (!comm.barrier(c->stream)) return fail(c, TB_ERR_COMM, comm.err);
+    c->ext_inst = c->list_inst;
+    c->ext_vtx = nullptr;
+    c->ext_order = c->list_order;
+    c->ext_cap = c->list_cap;
+    *out = local;
+    out->num_instances = total;
+    out->num_batches = merged.size();
+    out->d_instances = (const tb_instance*)c->list_inst;
+    out->d_order = (const uint32_t*)c->list_order;
+    out->d_vertices = nullptr;
+    out->kernel_launches = c->frame_launches;
+    if (c->rank == c->list_root && total > 0) {
+        if ((s = tb_vertices_from_instances(c, c->list_inst, 0, total, c->list_vtx))) return s;
+        out->d_vertices = (const tb_quad_vertex*)c->list_vtx;
+    }
+    c->last_instances = total;
+    c->last_batches = merged.size();
+    c->frame_valid = true;
     return TB_OK;
 }
 
@@ -3073,8 +3207,15 @@ tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
         g[1] |= c->h_xchg[4 + 3 * r + 1];
         g[2] += c->h_xchg[4 + 3 * r + 2];
     }
+    {
+        // identical inputs on every rank: they take the same branch. Wide keys (continuous z): co-ranking instead of
+        // histogram placement
+        FramePlan gp;
+        build_frame_plan(g[0], ~g[1], &gp);
+        if (g[2] > 0 && (gp.pext.nbits > TB_SHARD_MAX_KEY_BITS || (int)gp.ltbits > (int)kMaxLtBits)) return sharded_merge_frame(c, out);
+    }
     uint64_t nbins = 0;
-    if ((s = tb_shard_plan(c, g, &nbins))) return s;  // identical inputs on every rank: they fail or pass together
+    if ((s = tb_shard_plan(c, g, &nbins))) return s;
     if ((s = grow(c, &c->shard_hist, &c->shard_hist_cap, (size_t)nbins, 4))) return s;
     if ((s = grow(c, &c->shard_all_hists, &c->shard_all_cap, (size_t)nbins * nranks, 4))) return s;
     if ((s = tb_shard_key_histogram(c, c->shard_hist))) return s;
