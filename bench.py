@@ -35,6 +35,12 @@ ALG_BYTES_EMIT = 208    # the emit kernel's share: Transform+Sprite read, Instan
 CPU_SAMPLE = 1 << 22
 
 
+def bench_config(n, world):
+    """The `config` object of the bench line: the same in both arms (this build and --impl reference)."""
+    return {"workload": workload_name(n), "entities_per_gpu": n, "sharding": f"contiguous id range x{world}",
+            "l2": "no flush needed: each pass streams >= 0.5 GB per GPU, far larger than the 126 MB L2"}
+
+
 def workload_name(n):
     return (f"configs[3]: {n} particle-style entities per GPU (Transform+Velocity+Sprite, 4 textures, 1 layer, "
             "dt=0.01): velocity system + transform + sprite batching per frame")
@@ -239,10 +245,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(N_PER_GPU),
-                   "note": "reference arm: the Rust reference cannot be built here (no cargo/rustc); this is the CPU "
-                           "oracle port of its path, single thread like the reference (RefCell storage, "
-                           "sequential systems), each step a bounded sample"},
+        "config": bench_config(N_PER_GPU, args.gpus),
+        "note": "reference arm: the Rust reference cannot be built here (no cargo/rustc); this is the CPU oracle port of its "
+                "path, single thread like the reference (RefCell storage, sequential systems). Each step times a bounded "
+                f"sample — the first {n_sample} entities of the workload scene — and `value` is entities of the sample per "
+                "second of CPU time (the path is linear in the entity count)",
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -257,7 +264,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--entities", type=int, default=N_PER_GPU, help="entities per GPU (default: the named workload)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="steps in flight in the e2e leg (one context + stream + host thread each)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--option", action="append", default=[], help="tb_ctx_set_option name=value")
     ap.add_argument("--configs", default="all", help="the per-config table at N=1: all | none | comma list, e.g. configs[1],configs[2]")
@@ -420,10 +428,14 @@ def main():
                 capi.host_free(p_)
 
     ctx.set_stream(0)  # e2e contexts run on their own streams
-    ctx_b = capi.Context(n, device=local_rank, **{k: int(v) for k, v in options.items()})
-    ctx_b.shard_set(rank, world, first)
-    ctx_b.set_entity_count(n)
-    lanes = [E2E(ctx), E2E(ctx_b)]
+    nlanes = max(2, args.e2e_lanes)
+    extra = []
+    for _ in range(nlanes - 1):
+        cx = capi.Context(n, device=local_rank, **{k: int(v) for k, v in options.items()})
+        cx.shard_set(rank, world, first)
+        cx.set_entity_count(n)
+        extra.append(cx)
+    lanes = [E2E(ctx)] + [E2E(cx) for cx in extra]
     for ln in lanes:
         ln.step()
     # serial: one context, nothing overlapped
@@ -433,8 +445,9 @@ def main():
         lanes[0].step()
     torch.cuda.synchronize()
     serial_ms = (time.perf_counter() - t0) * 1e3 / max(2, args.e2e_steps // 2)
-    # pipelined: two steps in flight
-    e2e_total = 2 * max(1, args.e2e_steps // 2 + args.e2e_steps % 2)
+    # pipelined: one step in flight per lane
+    per_lane = max(1, -(-args.e2e_steps // nlanes))
+    e2e_total = nlanes * per_lane
 
     def lane_loop(ln, k, delay):
         torch.cuda.set_device(local_rank)
@@ -444,7 +457,7 @@ def main():
 
     barrier()
     t0 = time.perf_counter()
-    threads = [threading.Thread(target=lane_loop, args=(ln, e2e_total // 2, i * 0.4 * serial_ms * 1e-3))
+    threads = [threading.Thread(target=lane_loop, args=(ln, per_lane, i * serial_ms * 1e-3 / nlanes))
                for i, ln in enumerate(lanes)]
     for t in threads:
         t.start()
@@ -459,7 +472,8 @@ def main():
     h2d = h_t.nbytes + h_s.nbytes + h_v.nbytes
     d2h = int(out.num_instances) * (80 + 64 + 4) + int(out.num_batches) * 16
     checksum = int(order[:: max(1, n // 4096)].astype(np.uint64).sum())
-    ctx_b.close()
+    for cx in extra:
+        cx.close()
     for ln in lanes:
         ln.free()
     ctx.set_stream(stream.cuda_stream)
@@ -618,20 +632,19 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n), "entities_per_gpu": n, "sharding": f"contiguous id range x{world}",
-                       "l2": "no flush needed: each pass streams >= 0.5 GB per GPU, far larger than the 126 MB L2",
-                       "path": {1: "bucket (one fused rank+compose+emit pass)", 2: "sort"}.get(info.path),
-                       "key_bits": info.key_bits, "sort_passes": info.sort_passes, "kernels_per_frame": info.kernel_launches,
-                       "placement": "per-tile bucket offsets cached from the last full frame, validated every frame "
-                                    "(buckets depend on the Sprite only)" if info.kernel_launches == 1 else "recomputed every frame",
-                       "options": options},
+            "config": bench_config(n, world),
+            "frame": {"path": {1: "bucket (one fused rank+compose+emit pass)", 2: "sort"}.get(info.path),
+                      "key_bits": info.key_bits, "sort_passes": info.sort_passes, "kernels_per_frame": info.kernel_launches,
+                      "placement": "per-tile bucket offsets cached from the last full frame, validated every frame "
+                                   "(buckets depend on the Sprite only)" if info.kernel_launches == 1 else "recomputed every frame",
+                      "options": options},
             "clocks": clocks,
             "e2e": {"value": total_entities * e2e_total / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_total,
-                    "steps": e2e_total, "steps_in_flight": 2, "host_buffers": "pinned (tb_host_alloc)", "rank0_numa": numa,
+                    "steps": e2e_total, "steps_in_flight": nlanes, "host_buffers": "pinned (tb_host_alloc)", "rank0_numa": numa,
                     "h2d_GBps_per_rank": h2d / (e2e_ms / e2e_total * 1e-3) / 1e9, "d2h_GBps_per_rank": d2h / (e2e_ms / e2e_total * 1e-3) / 1e9,
-                    "how": "two contexts / streams / host threads take alternate steps so one step's D2H overlaps the "
-                           "next step's H2D (PCIe full duplex); every step still copies all inputs in and all outputs out",
+                    "how": "contexts / streams / host threads take alternate steps so one step's D2H overlaps the next steps' "
+                           "H2D (PCIe full duplex); every step still copies all inputs in and all outputs out",
                     "order_checksum": checksum},
             "e2e_serial": {"value": total_entities / (serial_ms * 1e-3), "unit": UNIT, "ms_per_step": serial_ms,
                            "steps_in_flight": 1},
