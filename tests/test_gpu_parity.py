@@ -1239,7 +1239,7 @@ def test_chunked_sort_moving_entities_and_key_changes(shift):
         ref.step(0.01)
         gf = util.GpuFrame(ctx)
         util.assert_frame_parity(gf, ref.frame(), what=f"chunked, moving, frame {k}")
-    assert gf.info.kernel_launches == 1  # the steady frame is the list emit alone
+    assert gf.info.kernel_launches == 2  # the steady frame: the list emit + the tick of entities that move undrawn
     # now some entities move in z by whole depth steps: keys change
     v["v"][: sc.n // 3, 2] = 100.0
     ctx.upload_velocities(0, v)
@@ -1277,7 +1277,9 @@ def test_moving_sorted_scene_lives_in_draw_order(z_mode):
     v["v"][:, 0] = rng.uniform(-100, 100, sc.n)
     v["v"][:, 1] = rng.uniform(-100, 100, sc.n)
     sc.velocities = v
-    masks = {capi.TB_VELOCITY: util.random_mask(sc.n, 0.7, 7)}
+    # some entities move without being drawn (Velocity, no Sprite): they are not in the draw-ordered copy and are ticked
+    # by a side pass on the entity-order rows
+    masks = {capi.TB_VELOCITY: util.random_mask(sc.n, 0.7, 7), capi.TB_SPRITE: util.random_mask(sc.n, 0.85, 8)}
     ctx, ref, g, r = run_both(sc, masks=masks, ticks=1)
     util.assert_frame_parity(g, r)
     launches = []
@@ -1293,7 +1295,7 @@ def test_moving_sorted_scene_lives_in_draw_order(z_mode):
             got = ctx.download_transforms(0, sc.n)
             want = ref.transforms().view(capi.TRANSFORM_DTYPE).reshape(-1)
             assert np.array_equal(got["translation"], want["translation"])
-    assert launches[-1] == 1 and launches[4] == 1, launches  # the steady frame is the streaming emit alone
+    assert launches[-1] == 2 and launches[4] == 2, launches  # the steady frame: the streaming emit + the undrawn movers' tick
     # a camera-only frame (nothing pending) and a tick after it
     vp = capi.orthographic(-1200, 1200, -900, 900, -100, 100)
     ctx.set_view_projection(vp)
@@ -1304,6 +1306,8 @@ def test_moving_sorted_scene_lives_in_draw_order(z_mode):
     ctx.upload_velocities(0, v)
     ctx.upload_presence(capi.TB_VELOCITY, 0, masks[capi.TB_VELOCITY])
     moved = ctx.download_transforms(0, sc.n)
+    want = ref.transforms().view(capi.TRANSFORM_DTYPE).reshape(-1)
+    assert np.array_equal(moved["translation"], want["translation"])  # undrawn movers included
     ref.close()
     sc2 = scenes.config2(n=70_000, seed=101, z_mode=z_mode)
     sc2.transforms = moved

@@ -136,7 +136,7 @@ def assert_frame_parity(gpu, ref, exact_floats=None, what=""):
     """Integer outputs bit-exact; float outputs `==` when the libm restatement is pinned on this box (or when
     exact_floats=True), else within the split 1e-5 metric. Records the element-wise relative errors."""
     assert gpu.info.num_instances == len(ref.order), (gpu.info.num_instances, len(ref.order))
-    np.testing.assert_array_equal(gpu.order, ref.order, err_msg="sorted entity order")
+    np.testing.assert_array_equal(gpu.order, ref.order, err_msg=f"{what}: sorted entity order")
     assert gpu.info.num_batches == len(ref.batches), (gpu.info.num_batches, len(ref.batches))
     for f in ("layer", "texture", "first_instance", "count"):
         np.testing.assert_array_equal(gpu.batches[f], ref.batches[f], err_msg=f"batch table {f}")
@@ -162,7 +162,7 @@ def assert_frame_parity(gpu, ref, exact_floats=None, what=""):
     if exact_floats:
         bad = np.argwhere(gm != rm)
         where = f"model {tuple(bad[0])}: gpu {gm[tuple(bad[0])]!r} ref {rm[tuple(bad[0])]!r}" if len(bad) else "vertices"
-        raise AssertionError(f"floats differ from the oracle (== comparison; libm restatement pinned): {where}; "
+        raise AssertionError(f"{what}: floats differ from the oracle (== comparison; libm restatement pinned): {where}; "
                              f"{len(bad)} model entries, max rel {mmax:.3g}")
     # split 1e-5 metric
     blk = [0, 1, 2, 4, 5, 6, 8, 9, 10]          # the 3x3 block (either storage order: the index set is symmetric)

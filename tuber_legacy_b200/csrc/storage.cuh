@@ -142,6 +142,22 @@ __global__ void __launch_bounds__(kThreads) spin_kernel(RowView rows, const uint
     reinterpret_cast<float*>(rows.b + (size_t)i * rows.sb + 1)[3] = sc.y;  // B1.w
 }
 
+// Entities the velocity system moves but no frame draws (Transform and Velocity, no Sprite): the frames that run the
+// velocity system inside the emit only visit drawn entities, so these are ticked by a side pass — when there are any.
+__global__ void __launch_bounds__(kThreads) count_hidden_movers_kernel(const uint64_t* mask_t, const uint64_t* mask_v, const uint64_t* mask_s,
+                                                                        uint32_t nwords, uint32_t n, unsigned long long* out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    if (w < nwords) {
+        uint64_t m = mask_t[w] & mask_v[w] & ~mask_s[w];
+        const uint32_t lo = w * 64u;
+        if (lo + 64u > n) m &= (n > lo) ? ((1ull << (n - lo)) - 1ull) : 0ull;
+        c = __popcll(m);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 // ---- Ecs::query: presence AND -> packed ascending indices --------------------------------------
 
 struct QueryParams {

@@ -162,6 +162,7 @@ struct tb_ctx {
     float* seq_vel = nullptr;
     size_t seq_vel_cap = 0;
     bool seq_has_vel = false, seq_live = false;
+    uint64_t hidden_movers = 0;  // entities with Transform and Velocity but no Sprite, counted when the copy is made
     // scene graphs: the copy holds the LOCAL rows (+ velocities + parent ids) of the drawn entities; the last level's
     // (the leaves') are the working storage, the inner levels stay in the entity-order rows (hierarchy_seq_frame)
     uint32_t* seq_par = nullptr;
@@ -448,6 +449,13 @@ tb_status flush_integrate(tb_ctx* c) {
     c->fast_clean = c->seq_valid = false;
     c->static_valid = false;
     return TB_OK;
+}
+
+// The velocity system for the entities no frame draws (Transform and Velocity, no Sprite), on the entity-order rows: the
+// frames that tick inside their emit only visit drawn entities.
+void tick_hidden_movers(tb_ctx* c) {
+    TB_LAUNCH(c, "integrate", c->n, integrate_kernel, div_up(c->n, kThreads), kThreads, 0, c->rows, mask_or_null(c, TB_TRANSFORM),
+              mask_or_null(c, TB_VELOCITY), c->vel, c->pending_dt, c->pending_ticks, (uint32_t)c->n, 0u, mask_or_null(c, TB_SPRITE));
 }
 
 // Scratch layout for one frame under a plan.
@@ -1154,6 +1162,7 @@ tb_status chunk_fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_
     FrameMode fm{};
     ListParams lp;
     fill_list_params(c, fm, integrate, d_inst, d_vtx, d_order, &lp);
+    if (lp.integrate) tick_hidden_movers(c);  // the list only holds drawn entities
     TB_LAUNCH(c, "emit_list", c->sorted_count * (64 + 80 + 64 + 4 + 12 + (lp.integrate ? 28 : 0)), emit_list_kernel<true>,
               2u * (uint32_t)c->sm_count, kThreads, sizeof(ListShared), lp);
     tb_status s = read_header(c);
@@ -1313,6 +1322,7 @@ tb_status sequential_frame(tb_ctx* c, bool validate, bool integrate, float4* d_i
         return TB_OK;
     }
     TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
+    if (ep.integrate && c->hidden_movers > 0) tick_hidden_movers(c);
     if (ep.integrate) c->seq_live = true;  // the copy now holds newer translations than the entity-order rows
     TB_LAUNCH(c, "emit_sequential", c->sorted_count * (64 + 80 + 64 + 4 + 4 + sizeof(KeyT) + (ep.integrate ? 28 : 0)),
               (emit_sequential_kernel<KeyT, true>), 2u * (uint32_t)c->sm_count, kThreads, sizeof(SeqShared), ep);
@@ -1359,6 +1369,18 @@ tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
               (uint32_t)c->sorted_count, c->seq_rows, with_vel ? (const float*)c->vel : (const float*)nullptr, mask_or_null(c, TB_VELOCITY),
               with_vel ? c->seq_vel : (float*)nullptr, graph ? (const uint32_t*)c->sane_parent : (const uint32_t*)nullptr,
               graph ? c->seq_par : (uint32_t*)nullptr);
+    c->hidden_movers = 0;
+    if (with_vel && !graph) {
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(c->scratch + kHdrLevelStats);
+        TB_CUDA(c, cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+        const uint32_t nwords = div_up(c->n, 64);
+        TB_LAUNCH(c, "count_hidden_movers", nwords * 24ull, count_hidden_movers_kernel, div_up(nwords, kThreads), kThreads, 0,
+                  mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), mask_or_null(c, TB_SPRITE), nwords, (uint32_t)c->n, d_cnt);
+        unsigned long long h = 0;
+        TB_CUDA(c, cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->hidden_movers = h;
+    }
     c->seq_valid = true;
     c->seq_graph = graph;
     if (graph) c->seq_leaf_first = c->level_first[c->nlevels - 1];
