@@ -90,6 +90,11 @@ struct tb_ctx {
     uint32_t* gen = nullptr;     // [cap] generation of every entity slot (bumped by deletes)
     cudaStream_t side_stream[TB_SYSTEM_COUNT] = {};  // stages of tb_bundle_step: one stream per concurrent system
     cudaEvent_t fork_event = nullptr, join_event[TB_SYSTEM_COUNT] = {};
+    // a bundle stepped again with the same systems, dt and storage replays its captured graph (fork / join included)
+    cudaGraphExec_t bundle_graph = nullptr;
+    std::vector<int> bundle_sig_systems;
+    uint64_t bundle_sig[8] = {};
+    bool bundle_graph_valid = false;
     uint32_t* parent = nullptr;
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -1664,6 +1669,7 @@ void tb_ctx_destroy(tb_ctx* c) {
         if (c->join_event[k]) cudaEventDestroy(c->join_event[k]);
     }
     if (c->fork_event) cudaEventDestroy(c->fork_event);
+    if (c->bundle_graph) cudaGraphExecDestroy(c->bundle_graph);
     cudaFree(c->parent);
     cudaFree(c->stage);
     cudaFree(c->scratch);
@@ -2375,6 +2381,33 @@ tb_status tb_bundle_step(tb_ctx* c, const int* systems, uint32_t n, float dt, ui
             TB_CUDA(c, cudaEventCreateWithFlags(&c->join_event[k], cudaEventDisableTiming));
         }
     }
+    // the same bundle as last time over the same storage: replay the captured graph
+    uint32_t dt_bits;
+    memcpy(&dt_bits, &dt, 4);
+    const uint64_t sig[8] = {c->n, dt_bits, (uint64_t)(uintptr_t)c->rows.t, (uint64_t)(uintptr_t)c->rows.b, (uint64_t)(uintptr_t)c->vel,
+                             (uint64_t)(uintptr_t)c->spin, (uint64_t)(uintptr_t)c->stream,
+                             (uint64_t)((c->store[TB_VELOCITY] ? 1 : 0) | (c->store[TB_SPIN] ? 2 : 0) | (c->store[TB_TRANSFORM] ? 4 : 0) | (c->rows.st << 8))};
+    const std::vector<int> sys_list(systems, systems + n);
+    if (c->use_graphs && !c->prof && c->bundle_graph_valid && sys_list == c->bundle_sig_systems && memcmp(sig, c->bundle_sig, sizeof(sig)) == 0) {
+        TB_CUDA(c, cudaGraphLaunch(c->bundle_graph, c->stream));
+        c->launches += n;
+        rows_changed_outside_a_frame(c);
+        c->static_valid = false;
+        return TB_OK;
+    }
+    const bool capture = c->use_graphs && !c->prof && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!capture) cudaGetLastError();
+    struct CaptureGuard {  // an early error return must not leave the stream capturing
+        cudaStream_t stream;
+        bool active;
+        ~CaptureGuard() {
+            if (!active) return;
+            cudaGraph_t g = nullptr;
+            cudaStreamEndCapture(stream, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+    } capture_guard{c->stream, capture};
     for (uint32_t st = 0; st < nstages; ++st) {
         std::vector<uint32_t> members;
         for (uint32_t k = 0; k < n; ++k)
@@ -2404,6 +2437,22 @@ tb_status tb_bundle_step(tb_ctx* c, const int* systems, uint32_t n, float dt, ui
                 TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->join_event[m % TB_SYSTEM_COUNT], 0));
             }
         }
+    }
+    if (capture) {
+        capture_guard.active = false;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaStreamEndCapture(bundle)");
+        if (c->bundle_graph) cudaGraphExecDestroy(c->bundle_graph);
+        c->bundle_graph = nullptr;
+        c->bundle_graph_valid = false;
+        e = cudaGraphInstantiate(&c->bundle_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return cuda_fail(c, e, "cudaGraphInstantiate(bundle)");
+        c->bundle_graph_valid = true;
+        c->bundle_sig_systems = sys_list;
+        memcpy(c->bundle_sig, sig, sizeof(sig));
+        TB_CUDA(c, cudaGraphLaunch(c->bundle_graph, c->stream));  // the capture recorded the work: this runs it
     }
     rows_changed_outside_a_frame(c);
     c->static_valid = false;
