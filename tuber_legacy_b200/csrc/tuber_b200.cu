@@ -175,6 +175,11 @@ struct tb_ctx {
     bool seq_graph = false;
     uint32_t seq_leaf_first = 0;
     uint32_t hier_streak = 0;  // consecutive scene-graph frames that kept their sort
+    // A single-kernel frame whose validation fails costs its own time plus the full frame's. After a failure the next
+    // frames go straight to the full path (whose key pass skips the sort on the device when nothing changed) and the
+    // single-kernel attempts resume once this many full frames have passed: keys that change every frame cost one
+    // full frame per frame, not a failed attempt on top.
+    uint32_t fast_backoff = 0;
     uint32_t clean_streak = 0;  // consecutive frames served by a kept draw order with nothing touched
     int static_buckets = 1;
     uint64_t static_count = 0, static_batches = 0;
@@ -1193,7 +1198,7 @@ tb_status hierarchy_seq_frame(tb_ctx* c, bool integrate, const ScratchLayout& L,
     TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, (L.total_words - kHdrFrame) * 4, c->stream));
     if ((s = run_prepare(c, true, integrate, fm, &L, nullptr, last))) return s;
     const bool tick = integrate && c->store[TB_VELOCITY] && c->store[TB_TRANSFORM];
-    if (tick && c->level_count[last] > 0) {
+    if (tick && c->level_count[last] > 0 && c->hidden_movers > 0) {
         // leaves that are not drawn (no Sprite) are not in the working storage: their tick runs on the entity-order rows
         const uint32_t first = c->level_first[last], end = first + c->level_count[last];
         TB_LAUNCH(c, "integrate", (uint64_t)c->level_count[last], integrate_kernel, div_up(end - first, kThreads), kThreads, 0, c->rows,
@@ -1375,7 +1380,7 @@ tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
               with_vel ? c->seq_vel : (float*)nullptr, graph ? (const uint32_t*)c->sane_parent : (const uint32_t*)nullptr,
               graph ? c->seq_par : (uint32_t*)nullptr);
     c->hidden_movers = 0;
-    if (with_vel && !graph) {
+    if (with_vel) {  // scene graphs: counted over the whole scene (a superset of the undrawn leaves)
         unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(c->scratch + kHdrLevelStats);
         TB_CUDA(c, cudaMemsetAsync(d_cnt, 0, 8, c->stream));
         const uint32_t nwords = div_up(c->n, 64);
@@ -2556,6 +2561,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if ((s = ensure_rows_current(c))) return s;
             c->seq_valid = false;
             c->clean_streak = 0;
+            c->fast_backoff = 2;
         }
         // else: some key changed; the full frame below re-sorts (its key pass finds the same difference)
     }
@@ -2597,6 +2603,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
                 if ((s = ensure_rows_current(c))) return s;
                 c->seq_valid = false;
                 c->hier_streak = 0;
+                c->fast_backoff = 2;
             }
         }
     }
@@ -2614,8 +2621,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         } else {
             drop_kept_frames(c);  // e.g. a velocity moved z: fall back to the full frame below
             replanned = 1;
+            c->fast_backoff = 2;
         }
     }
+    if (!fast_done && integrate) c->seq_valid = false;  // the full frame ticks the entity-order rows: a draw-ordered copy goes stale
     for (int attempt = 0; attempt < 4 && !fast_done; ++attempt) {
         const bool cached_plan = c->plan_valid;
         if (!c->plan_valid) {
@@ -2761,8 +2770,10 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
         num_batches = ((uint32_t*)c->h_hdr)[kHdrNumBatches - kHdrFrame];
         // buckets that depend on the Sprite only (no varying z bit): the tile offsets stay valid until
         // a component changes, so the next frames can run as one kernel
+        const bool backing_off = c->fast_backoff > 0;
+        if (backing_off) c->fast_backoff -= 1;
         if (c->static_buckets && L.small && !fm.hier && !fm.lt_generic && plan.zbits == 0 && !plan.key64 &&
-            num_batches <= c->max_batches) {
+            num_batches <= c->max_batches && !backing_off) {
             c->static_valid = true;
             c->static_count = count;
             c->static_batches = num_batches;
@@ -2781,7 +2792,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             c->clean_streak = 0;
             c->sorted_count = count;
             c->sorted_batches = num_batches;
-            c->fast_clean = true;
+            c->fast_clean = !backing_off;
             // scene graphs whose entities move keep coming through here (level passes every frame): after two frames that
             // kept their sort, the drawn entities' local rows, velocities and parent ids are copied into draw order and
             // the next frames stream (hierarchy_seq_frame)
