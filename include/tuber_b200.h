@@ -141,9 +141,12 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *   "staged_emit"      0|1  stage emitted instances/vertices through shared memory (default 1)
  *   "static_buckets"   0|1  single-kernel steady-state frames (default 1): flat few-bucket scenes whose buckets
  *                           depend on the Sprite only reuse the per-tile offsets of the last full frame, flat
- *                           sorted scenes reuse its draw order (every key re-checked while emitting), scenes
- *                           nothing has touched for two frames stream from a draw-ordered copy of their rows;
- *                           all of it is dropped when a component is uploaded
+ *                           sorted scenes reuse its draw order (every key re-checked while emitting) and, once
+ *                           that order has held for two frames, LIVE in draw order (rows and velocities copied
+ *                           once; the velocity system runs on the copy; entity-order rows are brought up to date
+ *                           lazily before any call that reads or replaces them); all of it is dropped when a
+ *                           component is uploaded. A frame whose validation fails is redone the long way and the
+ *                           next two frames skip the single-kernel attempt
  *   "small_emit"       0|1  single-pass frames with <= 8 buckets use the warp-autonomous emit (default 1)
  *   "digit_bits"       1..8 widest radix digit (default 8)
  *   "sorted_cache"     0|1  sorted (multi-pass / hierarchy) frames keep the previous frame's sorted arrays; when the
@@ -154,7 +157,14 @@ TB_API tb_status tb_ctx_set_max_batches(tb_ctx* ctx, uint64_t max_batches);
  *   "z_dictionary"     0|1  scenes with at most 64 distinct depths sort by the rank of z instead of by
  *                           its varying float bits: fewer sort passes (default 1)
  *   "lt_limit"         0..16 widest (layer, texture) histogram kept as direct bins (default 16);
- *                           wider scenes find batch boundaries by run-head detection */
+ *                           wider scenes find batch boundaries by run-head detection
+ *   "hier_fused"       0|1  scene graphs whose entities move and whose draw order is kept run on the draw-ordered
+ *                           working storage: level passes for the inner levels only, the leaves are ticked, composed
+ *                           (world[parent] * local) and key-checked inside one streaming emit (default 1)
+ *   "chunked_sort"     0|1  sorted frames with 4..16 key bits sort per chunk of entity ids and emit chunk by chunk
+ *                           (window-local row gathers; default 0: measured slower than the kept-order paths on B200)
+ *   "chunk_shift"      0|11..24  log2 of the chunk size in entities (0: chosen from the key width)
+ *   "chunk_l2_hint"    0|1  the chunked emit's row gathers carry an L2 evict_last policy (default 1) */
 TB_API tb_status tb_ctx_set_option(tb_ctx* ctx, const char* name, int64_t value);
 
 /* Page-locked host memory for the caller's component / output arrays (uploads and downloads
