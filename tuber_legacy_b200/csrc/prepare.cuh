@@ -45,6 +45,7 @@ struct PrepShared {
     uint32_t tcnt[2][2][256];  // [iteration parity][half of the 1024-entity tile][pass-0 digit]
     uint32_t lt[2048];
     uint32_t zdict[kMaxZDict];  // the plan's z dictionary
+    unsigned long long mwords[2][3][16];  // [iteration parity][Transform, Sprite, Velocity][word]: presence words of a 1024-entity tile
     unsigned long long k_or, k_and;
     uint32_t count;
 };
@@ -210,7 +211,7 @@ __device__ __forceinline__ void prep_flush(const PrepParams& p, PrepShared& sh, 
 // Flat scenes (no Parent anywhere): per entity, the velocity system
 // (translation += velocity * dt, [SPEC]; idiom of system.rs:132-137) then the sort key of
 // (&Transform, &Sprite) matches (query.rs:109-120 presence AND).
-__global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepParams p) {
+__global__ void __launch_bounds__(kThreads, 3) prepare_flat_kernel(const PrepParams p) {
     __shared__ PrepShared sh;
     prep_init(p, sh);
     const uint32_t tile_elems = kThreads * kPrepItems;
@@ -230,16 +231,16 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
         float4 a0[kPrepItems], a1[kPrepItems];
         float vx[kPrepItems], vy[kPrepItems], vz[kPrepItems];
         bool has_t[kPrepItems], rend[kPrepItems], has_v[kPrepItems];
-        // Every load of the tile is issued before anything is consumed: rows and velocities exist
-        // (zero-filled) for every id below max_entities, so they do not wait for the presence bits.
+        // Every load of the tile is issued before anything is consumed: rows and velocities exist (zero-filled) for
+        // every id below max_entities, so they do not wait for the presence bits. The tile's presence words (16 per
+        // mask) are fetched once by 48 threads and shared: a presence test consumed inside the load loop would stall
+        // on its own load before the next item's loads are even issued (ncu: the top stall of the round-1 kernel).
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
             const uint32_t i = base + k * kThreads;
-            const bool inb = i < p.n;
             a0[k] = a1[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             vx[k] = vy[k] = vz[k] = 0.0f;
-            has_t[k] = rend[k] = has_v[k] = false;
-            if (inb) {
+            if (i < p.n) {
                 const size_t o = (size_t)i * p.rows.st;
                 a0[k] = p.rows.t[o];
                 a1[k] = p.rows.a[o];
@@ -248,11 +249,33 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
                     vx[k] = __ldg(v);
                     vy[k] = __ldg(v + 1);
                     vz[k] = __ldg(v + 2);
-                    has_v[k] = mask_bit(p.mask_v, i);
                 }
-                has_t[k] = mask_bit(p.mask_t, i);
-                rend[k] = mask_bit(p.mask_s, i);
             }
+        }
+        uint32_t old32[kPrepItems];
+        bool have_old[kPrepItems];
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {  // the previous frame's keys come with the tile's other loads
+            old32[k] = 0u;
+            have_old[k] = fetch_old_key(p, base + k * kThreads < p.n, base + k * kThreads, &old32[k]);
+        }
+        if (threadIdx.x < 48) {
+            const uint32_t m = threadIdx.x >> 4, w = threadIdx.x & 15u;
+            const uint64_t* mask = m == 0 ? p.mask_t : m == 1 ? p.mask_s : (do_int ? p.mask_v : nullptr);
+            const uint32_t gw = tile * 16u + w;
+            unsigned long long word = ~0ull;  // no mask: present on every entity
+            if (m == 2 && !do_int) word = 0ull;
+            else if (mask != nullptr) word = gw < ((p.n + 63u) >> 6) ? __ldg(mask + gw) : 0ull;
+            sh.mwords[par][m][w] = word;
+        }
+        __syncthreads();  // also orders the zeroing of tcnt[par] above before this tile's counting
+#pragma unroll
+        for (int k = 0; k < kPrepItems; ++k) {
+            const uint32_t li = k * kThreads + threadIdx.x;
+            const bool inb = base + k * kThreads < p.n;
+            has_t[k] = inb && ((sh.mwords[par][0][li >> 6] >> (li & 63u)) & 1ull);
+            rend[k] = inb && ((sh.mwords[par][1][li >> 6] >> (li & 63u)) & 1ull);
+            has_v[k] = inb && ((sh.mwords[par][2][li >> 6] >> (li & 63u)) & 1ull);
         }
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
@@ -263,14 +286,6 @@ __global__ void __launch_bounds__(kThreads, 4) prepare_flat_kernel(const PrepPar
                 p.rows.t[(size_t)i * p.rows.st] = a0[k];
             }
         }
-        uint32_t old32[kPrepItems];
-        bool have_old[kPrepItems];
-#pragma unroll
-        for (int k = 0; k < kPrepItems; ++k) {
-            old32[k] = 0u;
-            have_old[k] = fetch_old_key(p, base + k * kThreads < p.n, base + k * kThreads, &old32[k]);
-        }
-        if (tiles_out) __syncthreads();
 #pragma unroll
         for (int k = 0; k < kPrepItems; ++k) {
             const uint32_t i = base + k * kThreads;
