@@ -60,8 +60,13 @@ struct EmitParams {
     // small minority) read the world row the level pass wrote for them.
     const uint32_t* seq_par;  // parent (global id) per draw position
     uint32_t leaf_first;
-    const float4* seq_rows;  // emit_sequential_kernel: the rows (or world rows) in draw order, 64 bytes each
-    float4* seq_rows_rw;     // ... the same storage, writable: the velocity system's translation write-back
+    // emit_sequential_kernel: the draw-ordered copy. World rows (static scene graphs): 64 bytes per position. Local rows
+    // (flat scenes, scene-graph leaves; seq_split != 0): a dense block of translation chunks A0 (16 B per position: what
+    // the velocity system writes back, as a dense stream) followed, from float4 index seq_split, by A1 B0 B1 (48 B per
+    // position: a 3-float4 stride is bank-conflict-free in shared memory)
+    const float4* seq_rows;
+    float4* seq_rows_rw;     // ... the same storage, writable
+    uint32_t seq_split;
     const float* seq_vel;    // ... velocities in draw order (zero where the entity has none)
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
@@ -891,7 +896,7 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(RowView rows, con
                                                                 uint32_t global_first, uint32_t count, float4* __restrict__ out,
                                                                 const float* __restrict__ vel, const uint64_t* mask_v,
                                                                 float* __restrict__ vel_out, const uint32_t* __restrict__ parent = nullptr,
-                                                                uint32_t* __restrict__ par_out = nullptr) {
+                                                                uint32_t* __restrict__ par_out = nullptr, uint32_t split = 0u) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte chunk: a row's four are adjacent lanes
     const uint32_t pos = t >> 2, ch = t & 3u;
     if (pos >= count) return;
@@ -899,6 +904,11 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(RowView rows, con
     if (vel_out != nullptr && ch < 3u)  // velocities in draw order; zero where the entity has no Velocity
         vel_out[(size_t)pos * 3 + ch] = (vel != nullptr && mask_bit(mask_v, e)) ? __ldg(vel + (size_t)e * 3 + ch) : 0.0f;
     if (par_out != nullptr && ch == 3u) par_out[pos] = __ldg(parent + e);
+    if (split != 0u) {  // local rows: dense A0 block, then A1 B0 B1 per position
+        const float4 v = ch == 0 ? rows.t[(size_t)e * rows.st] : ch == 1 ? rows.a[(size_t)e * rows.st] : rows.b[(size_t)e * rows.sb + (ch & 1u)];
+        out[ch == 0 ? (size_t)pos : (size_t)split + (size_t)pos * 3 + (ch - 1u)] = v;
+        return;
+    }
     float4 v;
     if (world != nullptr) v = reinterpret_cast<const float4*>(world + e)[ch];
     else v = ch == 0 ? rows.t[(size_t)e * rows.st] : ch == 1 ? rows.a[(size_t)e * rows.st] : rows.b[(size_t)e * rows.sb + (ch & 1u)];
@@ -937,16 +947,24 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
     constexpr bool graph = VALIDATE && GRAPH;  // scene graph on the working storage (see EmitParams::seq_par)
     const bool from_world = ep.world != nullptr && !graph;
     const bool do_int = VALIDATE && ep.integrate != 0 && ep.seq_vel != nullptr && !from_world;
+    const bool split = ep.seq_split != 0;
     const uint32_t count = ep.pass.n;
     const uint32_t ntiles = (count + kWarpTile - 1) / kWarpTile;
     const uint32_t nwarps = gridDim.x * kWarps;
+    // shared-memory slot of chunk c of tile item li
+    auto slot = [&](uint32_t li, uint32_t c) -> uint32_t { return split ? (c == 0 ? li : kWarpTile + li * 3u + (c - 1u)) : li * 4u + c; };
     auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0
         const uint32_t cnt = min(kWarpTile, count - t * kWarpTile);
         const uint32_t ibytes = (cnt * 4u + 15u) & ~15u;
         const uint32_t kbytes = VALIDATE ? ((cnt * (uint32_t)sizeof(KeyT) + 15u) & ~15u) : 0u;
         const uint32_t vbytes = do_int ? ((cnt * 12u + 15u) & ~15u) : 0u;
         mbar_expect_tx(&sm.kbar[buf], cnt * 64u + ibytes + kbytes + vbytes + (graph ? ibytes : 0u));
-        bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile * 4, cnt * 64u, &sm.kbar[buf]);
+        if (split) {
+            bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile, cnt * 16u, &sm.kbar[buf]);
+            bulk_g2s(sm.rows[buf] + kWarpTile, ep.seq_rows + ep.seq_split + (size_t)t * kWarpTile * 3, cnt * 48u, &sm.kbar[buf]);
+        } else {
+            bulk_g2s(sm.rows[buf], ep.seq_rows + (size_t)t * kWarpTile * 4, cnt * 64u, &sm.kbar[buf]);
+        }
         bulk_g2s(sm.idx[buf], ep.idx_in + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
         if (graph) bulk_g2s(sm.par[buf], ep.seq_par + (size_t)t * kWarpTile, ibytes, &sm.kbar[buf]);
         if (VALIDATE) bulk_g2s(sm.keys[buf], ep.keys_in + (size_t)t * kWarpTile, kbytes, &sm.kbar[buf]);
@@ -994,10 +1012,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                 if (li < cnt && (!graph || leaf[k])) {
                     const float vx = vel[li * 3], vy = vel[li * 3 + 1], vz = vel[li * 3 + 2];
                     if (vx != 0.0f || vy != 0.0f || vz != 0.0f) {  // no Velocity (or a zero one): the value stays
-                        float4 a0 = rows[li * 4];
+                        float4 a0 = rows[slot(li, 0)];
                         integrate_ticks(a0, vx, vy, vz, ep.dt, ep.integrate);
-                        rows[li * 4] = a0;
-                        ep.seq_rows_rw[(size_t)(base + li) * 4] = a0;
+                        rows[slot(li, 0)] = a0;
+                        ep.seq_rows_rw[split ? (size_t)(base + li) : (size_t)(base + li) * 4] = a0;
                     }
                 }
             }
@@ -1030,10 +1048,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                     tl = __float_as_uint(sv.z);
                 } else {
                     Row r;
-                    r.a0 = rows[li * 4];
-                    r.a1 = rows[li * 4 + 1];
-                    r.b0 = rows[li * 4 + 2];
-                    r.b1 = rows[li * 4 + 3];
+                    r.a0 = rows[slot(li, 0)];
+                    r.a1 = rows[slot(li, 1)];
+                    r.b0 = rows[slot(li, 2)];
+                    r.b1 = rows[slot(li, 3)];
                     w = compose_local(r);
                     sw = r.b1.y;
                     shh = r.b1.z;
@@ -1090,7 +1108,7 @@ __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __res
     if (pos >= count) return;
     const uint32_t e = __ldg(idx + pos) - global_first;
     if (e < first) return;
-    rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos * 4);
+    rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos);  // the copy's dense translation block
 }
 
 // ---- quad vertices from instances ------------------------------------------------------------------

@@ -174,6 +174,7 @@ struct tb_ctx {
     size_t seq_par_cap = 0;
     bool seq_graph = false;
     uint32_t seq_leaf_first = 0;
+    uint32_t seq_split = 0;  // float4 index where the A1 B0 B1 block of a local-row copy starts (0: 64-byte world rows)
     uint32_t hier_streak = 0;  // consecutive scene-graph frames that kept their sort
     // A single-kernel frame whose validation fails costs its own time plus the full frame's. After a failure the next
     // frames go straight to the full path (whose key pass skips the sort on the device when nothing changed) and the
@@ -1211,6 +1212,7 @@ tb_status hierarchy_seq_frame(tb_ctx* c, bool integrate, const ScratchLayout& L,
     ep.keys_in = (const KeyT*)c->final_keys;
     ep.seq_rows = c->seq_rows;
     ep.seq_rows_rw = c->seq_rows;
+    ep.seq_split = c->seq_split;
     ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
     ep.seq_par = c->seq_par;
     ep.leaf_first = c->seq_leaf_first;
@@ -1312,6 +1314,7 @@ tb_status sequential_frame(tb_ctx* c, bool validate, bool integrate, float4* d_i
     ep.keys_in = (const KeyT*)c->final_keys;
     ep.seq_rows = c->seq_rows;
     ep.seq_rows_rw = c->seq_rows;
+    ep.seq_split = c->seq_split;
     ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
     ep.world = c->seq_world ? c->world : nullptr;  // only tells the kernel which kind of row it reads
     ep.plan = c->plan;
@@ -1349,13 +1352,16 @@ tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
     c->seq_valid = false;
     c->seq_graph = false;
     size_t cap = c->seq_rows ? c->seq_cap : 0;
-    if (grow(c, &c->seq_rows, &cap, (size_t)c->sorted_count * 4 + 4, sizeof(float4)) != TB_OK) {
+    if (grow(c, &c->seq_rows, &cap, (size_t)c->sorted_count * 4 + 80, sizeof(float4)) != TB_OK) {
         c->seq_cap = 0;
         cudaGetLastError();
         return TB_OK;  // no memory for the copy: keep gathering
     }
     c->seq_cap = cap;
     const bool with_vel = !world && c->store[TB_VELOCITY] && c->vel != nullptr;
+    // local rows are kept as a dense translation block + the rest (see EmitParams::seq_split); 16-byte TMA alignment of
+    // every tile of both blocks holds for any float4 index
+    const uint32_t split = world ? 0u : (uint32_t)((c->sorted_count + 63) & ~(uint64_t)63);
     if (graph) {
         size_t pcap = c->seq_par ? c->seq_par_cap : 0;
         if (grow(c, &c->seq_par, &pcap, (size_t)c->sorted_count + 4, sizeof(uint32_t)) != TB_OK) {
@@ -1378,7 +1384,8 @@ tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
               kThreads, 0, c->rows, world ? c->world : (const WorldRow*)nullptr, (const uint32_t*)c->final_idx, (uint32_t)c->global_first,
               (uint32_t)c->sorted_count, c->seq_rows, with_vel ? (const float*)c->vel : (const float*)nullptr, mask_or_null(c, TB_VELOCITY),
               with_vel ? c->seq_vel : (float*)nullptr, graph ? (const uint32_t*)c->sane_parent : (const uint32_t*)nullptr,
-              graph ? c->seq_par : (uint32_t*)nullptr);
+              graph ? c->seq_par : (uint32_t*)nullptr, split);
+    c->seq_split = split;
     c->hidden_movers = 0;
     if (with_vel) {  // scene graphs: counted over the whole scene (a superset of the undrawn leaves)
         unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(c->scratch + kHdrLevelStats);
