@@ -1103,12 +1103,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
 // reads or replaces those rows).
 // `first`: only entities with a local id >= first own their copy (scene graphs: the leaves).
 __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __restrict__ seq_rows, const uint32_t* __restrict__ idx,
-                                                              uint32_t global_first, uint32_t count, RowView rows, uint32_t first) {
+                                                              uint32_t global_first, uint32_t count, RowView rows, uint32_t first,
+                                                              uint32_t stride) {
     const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= count) return;
     const uint32_t e = __ldg(idx + pos) - global_first;
     if (e < first) return;
-    rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos);  // the copy's dense translation block
+    rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos * stride);  // stride 1: the copy's dense translation block
 }
 
 // ---- quad vertices from instances ------------------------------------------------------------------
