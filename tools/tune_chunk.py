@@ -13,7 +13,7 @@ import util
 
 n = int(os.environ.get("TB_TUNE_N", 1 << 24))
 sc = scenes.config2(n=n)
-shifts = [int(x) for x in os.environ.get("TB_TUNE_SHIFTS", "16,17,18,19,20").split(",")]
+shifts = [int(x) for x in os.environ.get("TB_TUNE_SHIFTS", "16,17,18,19,20").split(",") if x]
 settings = [dict(chunked_sort=0)]
 for extra in ({}, {"chunk_l2_hint": 0}, {"interleaved_rows": 1}):
     settings += [dict(chunked_sort=1, chunk_shift=s, **extra) for s in shifts]

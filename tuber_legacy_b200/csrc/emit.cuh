@@ -97,6 +97,15 @@ struct EmitShared {
 // sort bucket spread over all eight 16-byte bank groups.
 __device__ __forceinline__ uint32_t row_slot(uint32_t li, uint32_t c) { return ((li << 2) | c) ^ ((li >> 1) & 7u); }
 
+// address of 16-byte chunk c (0..3 = A0 A1 B0 B1) of entity e's row, in the row storage or the world-row array
+template <typename KeyT>
+__device__ __forceinline__ const float4* row_chunk(const EmitParams<KeyT>& ep, bool from_world, uint32_t e, uint32_t c) {
+    if (from_world) return reinterpret_cast<const float4*>(ep.world + e) + c;
+    return c == 0   ? ep.rows.t + (size_t)e * ep.rows.st
+           : c == 1 ? ep.rows.a + (size_t)e * ep.rows.st
+                    : ep.rows.b + (size_t)e * ep.rows.sb + (c - 2u);
+}
+
 template <typename Params>
 __device__ __forceinline__ void make_outputs(const Params& ep, const Affine& world, float sw, float shh, uint32_t tl,
                                              InstanceOut& inst, float4 (&vtx)[4]) {
@@ -242,24 +251,13 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
     auto gather_rows = [&](uint32_t tile, uint32_t buf, uint32_t ring) {
         const uint32_t cnt = tile_count(tile);
         float4* d = sm.rows[buf];
+        // the four lanes of a quad fetch the four 16-byte chunks of one row: an interleaved (or world) row is ONE
+        // 64-byte request, not four 16-byte ones (random rows over 1 GiB: 39 vs 23 G rows/s, tools/microbench_pages.cu)
+        const uint32_t c = lane & 3u;
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t li = warp * (ITEMS * 32) + k * 32 + lane;
-            if (li < cnt) {
-                const uint32_t e = sm.idx[ring][li];
-                if (from_world) {
-                    const float4* src = reinterpret_cast<const float4*>(ep.world + e);
-                    cp_async16(d + row_slot(li, 0), src);
-                    cp_async16(d + row_slot(li, 1), src + 1);
-                    cp_async16(d + row_slot(li, 2), src + 2);
-                    cp_async16(d + row_slot(li, 3), src + 3);
-                } else {
-                    cp_async16(d + row_slot(li, 0), ep.rows.t + (size_t)e * ep.rows.st);
-                    cp_async16(d + row_slot(li, 1), ep.rows.a + (size_t)e * ep.rows.st);
-                    cp_async16(d + row_slot(li, 2), ep.rows.b + (size_t)e * ep.rows.sb);
-                    cp_async16(d + row_slot(li, 3), ep.rows.b + (size_t)e * ep.rows.sb + 1);
-                }
-            }
+        for (int k = 0; k < ITEMS * 4; ++k) {
+            const uint32_t li = warp * (ITEMS * 32) + k * 8 + (lane >> 2);
+            if (li < cnt) cp_async16(d + row_slot(li, c), row_chunk(ep, from_world, sm.idx[ring][li], c));
         }
     };
 
@@ -760,24 +758,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_ordered_kernel(const EmitPar
     auto gather = [&](uint32_t t, uint32_t buf, uint32_t ring) {  // all lanes: two rows each
         const uint32_t cnt = tile_cnt(t);
         float4* d = sm.rows[buf];
+        const uint32_t c = lane & 3u;  // one 64-byte request per row: a quad of lanes takes its four chunks
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t li = k * 32 + lane;
-            if (li < cnt) {
-                const uint32_t e = sm.idx[ring][li] - ep.global_first;
-                if (from_world) {
-                    const float4* src = reinterpret_cast<const float4*>(ep.world + e);
-                    cp_async16(d + row_slot(li, 0), src);
-                    cp_async16(d + row_slot(li, 1), src + 1);
-                    cp_async16(d + row_slot(li, 2), src + 2);
-                    cp_async16(d + row_slot(li, 3), src + 3);
-                } else {
-                    cp_async16(d + row_slot(li, 0), ep.rows.t + (size_t)e * ep.rows.st);
-                    cp_async16(d + row_slot(li, 1), ep.rows.a + (size_t)e * ep.rows.st);
-                    cp_async16(d + row_slot(li, 2), ep.rows.b + (size_t)e * ep.rows.sb);
-                    cp_async16(d + row_slot(li, 3), ep.rows.b + (size_t)e * ep.rows.sb + 1);
-                }
-            }
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t li = k * 8 + (lane >> 2);
+            if (li < cnt) cp_async16(d + row_slot(li, c), row_chunk(ep, from_world, sm.idx[ring][li] - ep.global_first, c));
         }
     };
 

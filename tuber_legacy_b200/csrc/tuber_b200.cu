@@ -253,6 +253,8 @@ struct tb_ctx {
 
     // pinned host mirror of the scratch header
     uint64_t* h_hdr = nullptr;
+    void* h_peek = nullptr;  // pinned, kPeekBytes: small device -> host reads land here (peek_async)
+    cudaEvent_t copied = nullptr;  // marks the last copy of a bulk upload (LinkTurn)
 
     // instrumentation
     bool prof = false;
@@ -391,6 +393,53 @@ struct DeviceTemp {
     } while (0)
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// Small device -> host reads (the frame's result header, counters, a batch table) do not go through a copy engine:
+// a cudaMemcpyAsync queues on the device's D2H engine behind whatever bulk download ANOTHER context has in flight
+// (measured: a 64-byte read waiting 25 ms behind a 1.3 GB copy, tools/profile_e2e.py). One warp stores the words
+// into pinned host memory instead (cudaMallocHost memory is device-addressable under unified addressing).
+__global__ void peek_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t nwords) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+constexpr size_t kPeekBytes = 64u << 10;
+// pinned_dst: pinned host memory; bytes: a multiple of 4. Counted as a launch of the context, not as a kernel of the frame
+// (it stands where a memcpy node stood).
+inline void peek_async(tb_ctx* c, void* pinned_dst, const void* d_src, size_t bytes) {
+    const uint32_t nwords = (uint32_t)(bytes / 4);
+    peek_kernel<<<nwords > 1024 ? 8 : 1, nwords > 32 ? 256 : 32, 0, c->stream>>>((uint32_t*)pinned_dst, (const uint32_t*)d_src, nwords);
+    c->launches++;
+}
+// One BULK host transfer per direction per device at a time, process-wide. Several contexts (a streaming user keeps
+// two or three in flight so that one step's download overlaps the next step's upload) otherwise put their copies on the
+// link together, and same-direction copies sharing PCIe measured worse than taking turns: 59.8 ms per 3.76 GB step
+// against 50.8 ms (tools/profile_e2e.py; the link's duplex bound is 49 ms). A turn lasts until the copy has finished.
+constexpr size_t kBulkTransferBytes = 8u << 20;
+inline std::mutex& link_mutex(int device, int direction) {
+    static std::mutex m[64][2];
+    return m[(unsigned)device & 63u][direction];
+}
+struct LinkTurn {
+    enum { kUp = 0, kDown = 1 };
+    std::unique_lock<std::mutex> lk;
+    LinkTurn(const tb_ctx* c, int direction, size_t bytes) {
+        if (bytes >= kBulkTransferBytes) lk = std::unique_lock<std::mutex>(link_mutex(c->device, direction));
+    }
+    bool held() const { return lk.owns_lock(); }
+};
+// end of an upload's turn: wait for the copies enqueued so far (not for the kernels that follow them)
+inline cudaError_t finish_upload_turn(tb_ctx* c, const LinkTurn& turn) {
+    if (!turn.held()) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(c->copied, c->stream);
+    return e == cudaSuccess ? cudaEventSynchronize(c->copied) : e;
+}
+
+// ... and the blocking form for a few words into any host memory
+inline cudaError_t peek_sync(tb_ctx* c, void* dst, const void* d_src, size_t bytes) {
+    peek_async(c, c->h_peek, d_src, bytes);
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) memcpy(dst, c->h_peek, bytes);
+    return e;
+}
 
 template <typename T>
 tb_status grow(tb_ctx* c, T** p, size_t* cap, size_t need, size_t elem) {
@@ -752,8 +801,7 @@ tb_status plan_levels(tb_ctx* c) {
                   dist[cur ^ 1], c->scratch + kHdrPending);
         cur ^= 1;
         uint32_t pending = 0;
-        cudaMemcpyAsync(&pending, c->scratch + kHdrPending, 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaError_t e = cudaStreamSynchronize(c->stream);
+        cudaError_t e = peek_sync(c, &pending, c->scratch + kHdrPending, 4);
         if (e != cudaSuccess) {
             return cuda_fail(c, e, "plan_levels");
         }
@@ -768,8 +816,7 @@ tb_status plan_levels(tb_ctx* c) {
     TB_LAUNCH(c, "level_stats", 0, level_stats_kernel, grid, kThreads, 0, level, mask_or_null(c, TB_TRANSFORM), n,
               c->scratch + kHdrLevelStats);
     uint32_t stats[2] = {0, 0};
-    cudaMemcpyAsync(stats, c->scratch + kHdrLevelStats, 8, cudaMemcpyDeviceToHost, c->stream);
-    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaError_t e = peek_sync(c, stats, c->scratch + kHdrLevelStats, 8);
     if (e != cudaSuccess) {
         return cuda_fail(c, e, "plan_levels");
     }
@@ -937,7 +984,7 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
 }
 
 tb_status read_header(tb_ctx* c) {
-    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    peek_async(c, c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
@@ -1268,7 +1315,7 @@ tb_status record_full_frame(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
     else if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
     else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
     if (s) return s;
-    TB_CUDA(c, cudaMemcpyAsync(c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    peek_async(c, c->h_hdr, c->scratch + kHdrFrame, kHdrReadWords * sizeof(uint32_t));
     return TB_OK;
 }
 
@@ -1398,8 +1445,7 @@ tb_status build_sequential_rows(tb_ctx* c, bool world, bool graph = false) {
         TB_LAUNCH(c, "count_hidden_movers", nwords * 24ull, count_hidden_movers_kernel, div_up(nwords, kThreads), kThreads, 0,
                   mask_or_null(c, TB_TRANSFORM), mask_or_null(c, TB_VELOCITY), mask_or_null(c, TB_SPRITE), nwords, (uint32_t)c->n, d_cnt);
         unsigned long long h = 0;
-        TB_CUDA(c, cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
-        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        TB_CUDA(c, peek_sync(c, &h, d_cnt, 8));
         c->hidden_movers = h;
     }
     c->seq_valid = true;
@@ -1631,6 +1677,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     ok = ok && cudaMalloc((void**)&c->gen, max_entities * 4) == cudaSuccess;
     if (ok) cudaMemsetAsync(c->gen, 0, max_entities * 4, c->stream);
     ok = ok && cudaMallocHost((void**)&c->h_hdr, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_peek, kPeekBytes) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&c->zset, (kZSetSlots + 1) * 8) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_zset, (kZSetSlots + 1) * 8) == cudaSuccess;
     if (ok) ok = ensure_scratch(c, kHdrWords) == TB_OK;
@@ -1712,6 +1760,8 @@ void tb_ctx_destroy(tb_ctx* c) {
     cudaFree(c->lt_global);
     cudaFree(c->place_tmp);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
+    if (c->h_peek) cudaFreeHost(c->h_peek);
+    if (c->copied) cudaEventDestroy(c->copied);
     if (c->frame_graph) cudaGraphExecDestroy(c->frame_graph);
     cudaFree(c->zset);
     if (c->h_zset) cudaFreeHost(c->h_zset);
@@ -1850,9 +1900,11 @@ static tb_status upload_chunks(tb_ctx* c, const void* src, uint64_t n, size_t el
     const uint64_t per = kStageChunk / elem;
     tb_status s = ensure_stage(c, (size_t)std::min<uint64_t>(n, per) * elem);
     if (s) return s;
+    LinkTurn turn(c, LinkTurn::kUp, n * elem);
     for (uint64_t off = 0; off < n; off += per) {
         const uint64_t m = std::min<uint64_t>(per, n - off);
         TB_CUDA(c, cudaMemcpyAsync(c->stage, (const char*)src + off * elem, m * elem, cudaMemcpyHostToDevice, c->stream));
+        if (off + per >= n) TB_CUDA(c, finish_upload_turn(c, turn));
         launch(c, c->stage, first + off, m, user);
         // the staging buffer is reused by the next chunk: same stream, so ordering is implicit
     }
@@ -1908,8 +1960,7 @@ tb_status tb_upload_sprites(tb_ctx* c, uint64_t first, uint64_t n, const tb_spri
     c->frame_valid = false;
     // range check of layer / texture (SPEC: layer <= 65534, texture <= 65535)
     uint32_t bad = 0;
-    TB_CUDA(c, cudaMemcpyAsync(&bad, c->scratch + kHdrRangeErr, 4, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TB_CUDA(c, peek_sync(c, &bad, c->scratch + kHdrRangeErr, 4));
     if (bad) {
         cudaMemsetAsync(c->scratch + kHdrRangeErr, 0, 4, c->stream);
         return fail(c, TB_ERR_RANGE, "sprite layer > 65534 or texture > 65535");
@@ -1927,7 +1978,11 @@ tb_status tb_upload_velocities(tb_ctx* c, uint64_t first, uint64_t n, const tb_v
         TB_CUDA(c, cudaMalloc((void**)&c->vel, c->cap * sizeof(tb_velocity) + 16));
         TB_CUDA(c, cudaMemsetAsync(c->vel, 0, c->cap * sizeof(tb_velocity) + 16, c->stream));
     }
-    TB_CUDA(c, cudaMemcpyAsync(c->vel + first * 3, src, n * sizeof(tb_velocity), cudaMemcpyHostToDevice, c->stream));
+    {
+        LinkTurn turn(c, LinkTurn::kUp, n * sizeof(tb_velocity));
+        TB_CUDA(c, cudaMemcpyAsync(c->vel + first * 3, src, n * sizeof(tb_velocity), cudaMemcpyHostToDevice, c->stream));
+        TB_CUDA(c, finish_upload_turn(c, turn));
+    }
     c->store[TB_VELOCITY] = true;
     mark_presence(c, TB_VELOCITY, first, n, 1);
     c->seq_valid = false;  // the draw-ordered copy carries the velocities
@@ -1942,7 +1997,11 @@ tb_status tb_upload_parents(tb_ctx* c, uint64_t first, uint64_t n, const uint32_
         TB_CUDA(c, cudaMalloc((void**)&c->parent, c->cap * 4));
         TB_CUDA(c, cudaMemsetAsync(c->parent, 0xFF, c->cap * 4, c->stream));
     }
-    TB_CUDA(c, cudaMemcpyAsync(c->parent + first, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+    {
+        LinkTurn turn(c, LinkTurn::kUp, n * 4);
+        TB_CUDA(c, cudaMemcpyAsync(c->parent + first, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+        TB_CUDA(c, finish_upload_turn(c, turn));
+    }
     c->store[TB_PARENT] = true;
     // presence == "has a Parent component": every uploaded index whose value is not TB_NO_PARENT
     {
@@ -2067,8 +2126,7 @@ tb_status tb_delete_by_ids(tb_ctx* c, const uint32_t* ids, uint64_t n) {
     TB_LAUNCH(c, "delete_ids", n * 4, delete_ids_kernel, div_up(n, kThreads), kThreads, 0, (const uint32_t*)c->stage, (uint32_t)n, (uint32_t)c->n,
               all_masks(c), c->gen, c->scratch + kHdrPending);
     uint32_t bad = 0;
-    TB_CUDA(c, cudaMemcpyAsync(&bad, c->scratch + kHdrPending, 4, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TB_CUDA(c, peek_sync(c, &bad, c->scratch + kHdrPending, 4));
     structure_changed(c);
     if (bad) return fail(c, TB_ERR_INVALID, "delete_by_ids: an entity index outside entity_count");
     return TB_OK;
@@ -2095,8 +2153,7 @@ tb_status tb_delete_by_query(tb_ctx* c, uint32_t required, uint64_t* deleted) {
     TB_LAUNCH(c, "delete_query", q.nwords * 8ull * (q.nmasks + TB_COMPONENT_COUNT), delete_query_kernel, div_up(q.nwords, kThreads), kThreads, 0, q,
               all_masks(c), c->gen, d_cnt);
     unsigned long long cnt = 0;
-    TB_CUDA(c, cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TB_CUDA(c, peek_sync(c, &cnt, d_cnt, 8));
     if (cnt) structure_changed(c);
     if (deleted) *deleted = cnt;
     return TB_OK;
@@ -2189,8 +2246,7 @@ tb_status tb_query(tb_ctx* c, uint32_t required, uint32_t* out_indices, uint64_t
     const uint64_t wcap = out_indices ? std::min<uint64_t>(cap, c->n) : 0;
     if (wcap) TB_LAUNCH(c, "query_write", q.nwords * 8ull * q.nmasks, query_write_kernel, nblocks, kThreads, 0, q, d_counts, d_out, (uint32_t)wcap);
     uint32_t total = 0;
-    TB_CUDA(c, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TB_CUDA(c, peek_sync(c, &total, d_total, 4));
     if (wcap) {
         TB_CUDA(c, cudaMemcpyAsync(out_indices, d_out, std::min<uint64_t>(wcap, total) * 4, cudaMemcpyDeviceToHost, c->stream));
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -2649,7 +2705,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             if (s) return s;
             integrate = false;
             if (have_zset)
-                TB_CUDA(c, cudaMemcpyAsync(c->h_zset, c->zset, (kZSetSlots + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+                peek_async(c, c->h_zset, c->zset, (kZSetSlots + 1) * 8);
             if ((s = read_header(c))) return s;
             count = c->h_hdr[2];
             if (count == 0) break;
@@ -2948,8 +3004,7 @@ tb_status tb_shard_place(tb_ctx* c, const void* d_all_hists, uint64_t* global_in
     TB_LAUNCH(c, "place_write", 0, place_write_kernel, nblocks, kThreads, 0, H, (uint32_t)c->nranks, (uint32_t)c->rank, nbins,
               (const uint32_t*)bt, (const uint32_t*)bl, plan.zbits, c->remap, c->lt_global);
     uint32_t h[2] = {0, 0};
-    TB_CUDA(c, cudaMemcpyAsync(h, totals, 8, cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TB_CUDA(c, peek_sync(c, h, totals, 8));
     if (h[1] != c->shard_count) return fail(c, TB_ERR_INVALID, "histograms do not match this shard's renderable count");
     c->shard_global_count = h[0];
     if (global_instances) *global_instances = h[0];
@@ -3063,7 +3118,7 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
     c->h_xchg[0] = c->cap;
     TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 8, cudaMemcpyHostToDevice, c->stream));
     if (!c->comm->all_gather(c->d_xchg, c->d_xchg + 4, 8, c->stream)) return fail(c, TB_ERR_COMM, c->comm->err);
-    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 8, cudaMemcpyDeviceToHost, c->stream));
+    peek_async(c, c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 8);
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     uint64_t total = 0;
     for (int r = 0; r < nranks; ++r) total += c->h_xchg[4 + r];
@@ -3175,7 +3230,7 @@ static tb_status sharded_merge_frame(tb_ctx* c, tb_frame_out* out) {
         TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 8, cudaMemcpyHostToDevice, c->stream));
         if (!comm.all_gather(c->d_xchg, c->d_xchg + 4 + (round ? nranks : 0), 8, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
     }
-    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 16, cudaMemcpyDeviceToHost, c->stream));
+    peek_async(c, c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 16);
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     uint64_t total = 0, maxcount = 1, maxnb = 1;
     for (uint32_t r = 0; r < nranks; ++r) {
@@ -3292,7 +3347,7 @@ tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
     memcpy(c->h_xchg, st, sizeof(st));
     TB_CUDA(c, cudaMemcpyAsync(c->d_xchg, c->h_xchg, 24, cudaMemcpyHostToDevice, c->stream));
     if (!comm.all_gather(c->d_xchg, c->d_xchg + 4, 24, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
-    TB_CUDA(c, cudaMemcpyAsync(c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 24, cudaMemcpyDeviceToHost, c->stream));
+    peek_async(c, c->h_xchg + 4, c->d_xchg + 4, (size_t)nranks * 24);
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     uint64_t g[3] = {0, 0, 0};
     for (int r = 0; r < nranks; ++r) {
@@ -3379,6 +3434,14 @@ static tb_status download(tb_ctx* c, const void* d_src, uint64_t first, uint64_t
     if (!dst) return fail(c, TB_ERR_INVALID, "null pointer");
     if (!c->frame_valid) return fail(c, TB_ERR_INVALID, "no frame has been run since the last change");
     if (first + n > limit) return fail(c, TB_ERR_INVALID, "range outside the last frame's output");
+    if (n * elem <= kPeekBytes && (n * elem) % 4 == 0 && (first * elem) % 4 == 0) {  // e.g. the batch table
+        peek_async(c, c->h_peek, (const char*)d_src + first * elem, n * elem);
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(dst, c->h_peek, n * elem);
+        return TB_OK;
+    }
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));  // the frame's kernels are not part of the link turn
+    LinkTurn turn(c, LinkTurn::kDown, n * elem);
     TB_CUDA(c, cudaMemcpyAsync(dst, (const char*)d_src + first * elem, n * elem, cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
