@@ -183,7 +183,11 @@ TB_API tb_status tb_entity_count(tb_ctx* ctx, uint64_t* n);
  * read `src` (always so for page-locked memory from tb_host_alloc; pageable memory is staged by the
  * driver before the call returns). The caller must not modify or free `src` until the next call that
  * synchronises the context: tb_ctx_synchronize, tb_frame_transform_batch, any tb_download_*, tb_query,
- * tb_upload_sprites (it reads back the range check). The same holds for tb_upload_presence. */
+ * tb_upload_sprites (it reads back the range check). The same holds for tb_upload_presence.
+ * LINK TURNS: host transfers of 8 MB or more take turns per device and direction across all contexts of the
+ * process (a streaming host keeps two or three contexts in flight so that one step's download overlaps the next
+ * step's upload; same-direction copies sharing PCIe are slower than copies taking turns). Such an upload returns
+ * once its copy has finished, a download always did. Calls never nest turns, so there is no ordering to respect. */
 TB_API tb_status tb_upload_transforms(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_transform* src);
 TB_API tb_status tb_upload_sprites(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_sprite* src);
 TB_API tb_status tb_upload_velocities(tb_ctx* ctx, uint64_t first, uint64_t n, const tb_velocity* src);
