@@ -568,6 +568,17 @@ def main():
         c5x.set_option("static_buckets", 1)
         list_ms, lout = timed_sharded(c5x, False, gsteps)       # one draw list on rank 0
         assert lout.num_instances == n5
+        # where a list frame's time goes on every rank: per-kernel CUDA-event times (a second pass, not the timed one)
+        c5x.profile_enable(True)
+        t_wall = time.perf_counter()
+        for _ in range(3):
+            c5x.frame_sharded()
+        wall_ms = (time.perf_counter() - t_wall) * 1e3 / 3
+        mine = {"rank": rank, "wall_ms_per_frame": round(wall_ms, 3),
+                "kernels_ms_per_frame": {k_: round(v_[0] / 3, 4) for k_, v_ in c5x.profile().items()}}
+        c5x.profile_enable(False)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         check = None
         if rank == 0:
             # the presenting rank's global list against a single-context frame of the whole scene, byte for byte
@@ -600,7 +611,8 @@ def main():
                   "list_on_rank0": {"ms_per_frame": list_ms, "entities_per_s": n5 / (list_ms * 1e-3),
                                     "bytes_into_rank0_per_frame": remote5, "rank0_ingress_GBps": remote5 / (list_ms * 1e-3) / 1e9,
                                     "what": "end to end, transfer overlapped with the emit: the remote stores ARE the emit kernels' stores; "
-                                            "includes both exchanges, the barrier and the vertex regeneration on rank 0"},
+                                            "includes both exchanges, the barrier and the vertex regeneration on rank 0",
+                                    "per_rank": per_rank},
                   "check": check, "method": method}
         c5x.shard_finalize()
         c5x.close()

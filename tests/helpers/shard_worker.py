@@ -31,8 +31,15 @@ def main():
                 raise SystemExit("no exchange id from rank 0")
             time.sleep(0.05)
         sid = open(id_file, "rb").read()
+    def moving(**kw):  # sorted sprites, all moving in x / y: the steady list frames (kept order, chunked completion flags)
+        sc = scenes.config2(n=n, seed=64, **kw)
+        sc.velocities = scenes.config4(n=n, seed=65, **kw).velocities
+        sc.velocities["v"][:, 2] = 0.0
+        return sc
+
     make = {"config2": lambda **kw: scenes.config2(n=n, seed=61, **kw), "config4": lambda **kw: scenes.config4(n=n, seed=62, **kw),
-            "config2_random_z": lambda **kw: scenes.config2(n=n, seed=63, z_mode="random", **kw)}[kind]
+            "config2_random_z": lambda **kw: scenes.config2(n=n, seed=63, z_mode="random", **kw), "config2_moving": moving}[kind]
+    frames = 5
     first, count = scenes.shard_range(n, rank, world)
     sc = make(first=first, count=count)
     ctx = capi.Context(max(count, 1), device=rank)
@@ -44,10 +51,12 @@ def main():
     if sc.velocities is not None:
         ctx.upload_velocities(0, sc.velocities)
         ticks = 1
-    for _ in range(3):
+    passes = []
+    for _ in range(frames):
         for _ in range(ticks):
             ctx.system_integrate(0.01)
         info = ctx.frame_sharded()
+        passes.append(int(info.sort_passes))
     res = None
     if rank == 0:
         m, b = info.num_instances, info.num_batches
@@ -59,7 +68,7 @@ def main():
         one.upload_sprites(0, full.sprites)
         if full.velocities is not None:
             one.upload_velocities(0, full.velocities)
-        for _ in range(3):
+        for _ in range(frames):
             for _ in range(ticks):
                 one.system_integrate(0.01)
             oi = one.frame()
@@ -67,7 +76,7 @@ def main():
                 one.download_vertices(oi.num_instances), one.download_batches(oi.num_batches))
         eq = [g.shape == w.shape and g.tobytes() == w.tobytes() for g, w in zip(got, want)]
         res = {"world": world, "instances": int(m), "batches": int(b), "order_equal": eq[0], "instances_equal": eq[1],
-               "vertices_equal": eq[2], "batches_equal": eq[3], "crc_order": zlib.crc32(got[0].tobytes()),
+               "vertices_equal": eq[2], "batches_equal": eq[3], "sort_passes_per_frame": passes, "crc_order": zlib.crc32(got[0].tobytes()),
                "crc_instances": zlib.crc32(got[1].tobytes()), "transport": "NCCL (libnccl.so.2 opened by the library)"}
         one.close()
     ctx.shard_finalize()

@@ -24,8 +24,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_local(full, nranks, ticks=0, frames=1, root=0, devices=None):
-    """`full`: the whole scene. Returns the presenting rank's frame of the last of `frames` frames."""
+def run_local(full, nranks, ticks=0, frames=1, root=0, devices=None, hook=None):
+    """`full`: the whole scene. Returns the presenting rank's frame of the last of `frames` frames (`g.infos`: every
+    frame's info on that rank). `hook(rank, ctx, frame_index, first, count)` runs before every frame."""
     sid = capi.shard_local_id()
     results, errors = [None] * nranks, []
 
@@ -40,15 +41,20 @@ def run_local(full, nranks, ticks=0, frames=1, root=0, devices=None):
                 ctx.upload_sprites(0, full.sprites[first:first + count])
                 if full.velocities is not None:
                     ctx.upload_velocities(0, full.velocities[first:first + count])
-            for _ in range(frames):
+            infos = []
+            for f in range(frames):
+                if hook is not None:
+                    hook(rank, ctx, f, first, count)
                 for _ in range(ticks):
                     ctx.system_integrate(0.01)
                 info = ctx.frame_sharded()
+                infos.append(info)
             if rank == root:
                 class G:
                     pass
                 g = G()
                 g.info = info
+                g.infos = infos
                 m, b = info.num_instances, info.num_batches
                 g.order = ctx.download_order(m)
                 g.instances = ctx.download_instances(m)
@@ -86,6 +92,59 @@ def test_sharded_particles_tick_and_steady_frames():
     util.assert_frame_parity(g, ref.frame(), what="tb_frame_sharded, particles, third frame")
 
 
+def moving_sorted_scene(n, seed):
+    """Sorted sprites (64 textures x 16 layers x 16 depths) that all move in x / y: the keys stay, the matrices change."""
+    sc = scenes.config2(n=n, seed=seed)
+    sc.velocities = scenes.config4(n=n, seed=seed + 1000).velocities
+    sc.velocities["v"][:, 2] = 0.0
+    return sc
+
+
+@pytest.mark.parametrize("nranks,root", [(1, 0), (2, 1), (4, 0), (8, 0)])
+def test_sharded_steady_frames_stream_the_kept_list(nranks, root):
+    """From the second frame on nobody re-sorts: every rank streams its draw-ordered working storage (velocity system
+    fused) to its kept positions of the global list; one word of agreement before, one after."""
+    sc = moving_sorted_scene(70_003, 56)
+    ref = util.make_oracle(sc)
+    for _ in range(5):
+        ref.step(0.01)
+    g = run_local(sc, nranks, ticks=1, frames=5, root=root)
+    assert g.infos[0].sort_passes > 1
+    assert [i.sort_passes for i in g.infos[1:]] == [0, 0, 0, 0], "steady frames must not sort"
+    util.assert_frame_parity(g, ref.frame(), what=f"kept list frames, {nranks} ranks")
+
+
+def test_sharded_kept_list_gives_way_when_keys_move():
+    """A few entities drift in z: their keys change every frame, every steady attempt is voided by some rank's key check
+    and the frame is redone in full by all of them; the ticks run exactly once either way."""
+    sc = moving_sorted_scene(50_000, 57)
+    sc.velocities["v"][::5000, 2] = 0.37
+    ref = util.make_oracle(sc)
+    for _ in range(6):
+        ref.step(0.01)
+    g = run_local(sc, 3, ticks=1, frames=6)
+    assert all(i.sort_passes >= 1 for i in g.infos), "no frame of this scene can keep the list"
+    util.assert_frame_parity(g, ref.frame(), what="kept list voided by moving keys")
+
+
+def test_sharded_kept_list_after_an_upload_on_one_rank():
+    """One rank replaces its sprites between steady frames: it votes against the kept list, everybody re-sorts once,
+    and the steady frames resume."""
+    sc = scenes.config2(n=60_000, seed=58)
+    changed = sc.sprites.copy()
+    first1, count1 = scenes.shard_range(sc.n, 1, 4)
+    changed["layer"][first1:first1 + count1] = (changed["layer"][first1:first1 + count1] + 3) % 16
+
+    def hook(rank, ctx, f, first, count):
+        if rank == 1 and f == 3:
+            ctx.upload_sprites(0, changed[first:first + count])
+
+    g = run_local(sc, 4, frames=6, hook=hook)
+    assert [i.sort_passes > 0 for i in g.infos] == [True, False, False, True, False, False]
+    sc.sprites = changed
+    util.assert_frame_parity(g, util.make_oracle(sc).frame(), what="kept list after one rank's upload")
+
+
 def test_sharded_empty_ranks():
     sc = scenes.config2(n=5, seed=53)          # fewer entities than ranks: some shards are empty
     g = run_local(sc, 8)
@@ -115,7 +174,7 @@ def test_sharded_wide_keys_with_ticks():
     util.assert_frame_parity(g, ref.frame(), what="sharded wide keys, z velocities")
 
 
-@pytest.mark.parametrize("kind", ["config2", "config4", "config2_random_z"])
+@pytest.mark.parametrize("kind", ["config2", "config4", "config2_random_z", "config2_moving"])
 def test_nccl_multiprocess_list_equals_single_context_frame(kind):
     import torch
     world = min(4, torch.cuda.device_count())
@@ -133,6 +192,8 @@ def test_nccl_multiprocess_list_equals_single_context_frame(kind):
     res = json.loads(outs[0][0].strip().splitlines()[-1])
     assert res["world"] == world and res["instances"] == n
     assert res["order_equal"] and res["instances_equal"] and res["vertices_equal"] and res["batches_equal"], res
+    if kind in ("config2", "config2_moving"):  # sorted in two passes: every frame after the first keeps the list
+        assert res["sort_passes_per_frame"][0] > 1 and not any(res["sort_passes_per_frame"][1:]), res
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", f"nccl_parity_world{world}_{kind}.json"), "w") as f:
             json.dump(res, f)

@@ -1,5 +1,5 @@
 // The small exchanges of a multi-GPU frame: two all-gathers of a few words / one histogram per
-// rank, one broadcast of buffer handles, one barrier. Two transports behind one interface:
+// rank, one broadcast of buffer handles, one integer sum (which is also the barrier). Two transports behind one interface:
 //
 //   NcclComm   one process per GPU (or any mix): NCCL over NVLink / NVSwitch. libnccl.so.2 is opened at run time
 //              (dlopen) rather than linked, so a host that already carries an NCCL (e.g. the one bundled with
@@ -37,10 +37,19 @@ struct Comm {
     // every rank contributes `bytes` from d_send; d_recv (nranks * bytes) holds them rank-major afterwards
     virtual bool all_gather(const void* d_send, void* d_recv, size_t bytes, cudaStream_t s) = 0;
     virtual bool broadcast(void* d_buf, size_t bytes, int root, cudaStream_t s) = 0;
-    // everything every rank enqueued on its stream before the barrier is complete (and visible) after it
-    virtual bool barrier(cudaStream_t s) = 0;
+    // *total (if given) = sum of every rank's `value`. Also THE barrier: everything every rank enqueued on its stream before
+    // the call is complete (and visible) after it
+    virtual bool sum(cudaStream_t s, int value, int* total) = 0;
+    bool barrier(cudaStream_t s) { return sum(s, 0, nullptr); }
     virtual bool same_process() const = 0;
+    // true if another rank of the group computes on this rank's GPU (only the process-local transport allows that): kernels
+    // of different ranks may then queue behind each other, so no kernel of one rank may WAIT for a kernel of another
+    virtual bool shares_device() const { return false; }
 };
+
+// one word in and out of the reduction without a copy engine (see peek_async in tuber_b200.cu)
+__global__ void comm_put_kernel(int* d, int v) { *d = v; }
+__global__ void comm_get_kernel(int* pinned, const int* d) { *pinned = *d; }
 
 // ---- NCCL, loaded at run time --------------------------------------------------------------------------------------
 
@@ -98,6 +107,7 @@ struct NcclApi {
 struct NcclComm : Comm {
     ncclComm_t comm = nullptr;
     int* d_token = nullptr;
+    int* h_token = nullptr;  // pinned
     bool init(int rank_, int nranks_, const uint8_t id[kCommIdBytes]) {
         NcclApi& api = NcclApi::get();
         if (!api.ok()) {
@@ -119,11 +129,16 @@ struct NcclComm : Comm {
             return false;
         }
         cudaMemset(d_token, 0, 2 * sizeof(int));
+        if (cudaMallocHost((void**)&h_token, sizeof(int)) != cudaSuccess) {
+            err = "cudaMallocHost(barrier token)";
+            return false;
+        }
         return true;
     }
     ~NcclComm() override {
         if (comm) NcclApi::get().CommDestroy(comm);
         cudaFree(d_token);
+        if (h_token) cudaFreeHost(h_token);
     }
     bool check(ncclResult_t r, const char* what) {
         if (r == ncclSuccess) return true;
@@ -136,14 +151,17 @@ struct NcclComm : Comm {
     bool broadcast(void* d_buf, size_t bytes, int root, cudaStream_t s) override {
         return check(NcclApi::get().Broadcast(d_buf, d_buf, bytes, ncclUint8, root, comm, s), "ncclBroadcast");
     }
-    bool barrier(cudaStream_t s) override {
+    bool sum(cudaStream_t s, int value, int* total) override {
         // stream order: every kernel enqueued before has finished (its peer stores are visible system-wide at kernel
         // end) before this rank enters the all-reduce, and the all-reduce finishes only when every rank has entered it
+        comm_put_kernel<<<1, 1, 0, s>>>(d_token, value);
         if (!check(NcclApi::get().AllReduce(d_token, d_token + 1, 1, ncclInt32, ncclSum, comm, s), "ncclAllReduce")) return false;
+        comm_get_kernel<<<1, 1, 0, s>>>(h_token, d_token + 1);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
             err = "barrier: stream synchronisation failed";
             return false;
         }
+        if (total) *total = *h_token;
         return true;
     }
     bool same_process() const override { return false; }
@@ -157,7 +175,7 @@ struct LocalGroup {
     int nranks = 0, arrived = 0;
     uint64_t generation = 0;
     std::vector<const void*> send;
-    std::vector<int> device;
+    std::vector<int> device, value;
     void wait_all() {  // host barrier of the group's threads
         std::unique_lock<std::mutex> lk(m);
         const uint64_t gen = generation;
@@ -185,6 +203,7 @@ struct LocalComm : Comm {
             p->nranks = nranks;
             p->send.assign(nranks, nullptr);
             p->device.assign(nranks, 0);
+            p->value.assign(nranks, 0);
             reg[key] = p;
         }
         return p;
@@ -233,12 +252,22 @@ struct LocalComm : Comm {
         if (!ok && err.empty()) err = "local transport: broadcast failed";
         return ok;
     }
-    bool barrier(cudaStream_t s) override {
+    bool sum(cudaStream_t s, int v, int* total) override {
         const bool ok = sync(s);
+        g->value[rank] = v;
         g->wait_all();
+        int t = 0;
+        for (int r = 0; r < nranks; ++r) t += g->value[r];
+        g->wait_all();  // every rank has read every value: they may be overwritten
+        if (total) *total = t;
         return ok;
     }
     bool same_process() const override { return true; }
+    bool shares_device() const override {
+        for (int r = 0; r < nranks; ++r)
+            if (r != rank && g->device[r] == device) return true;
+        return false;
+    }
 };
 
 }  // namespace tb

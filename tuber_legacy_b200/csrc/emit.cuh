@@ -68,6 +68,9 @@ struct EmitParams {
     float4* seq_rows_rw;     // ... the same storage, writable
     uint32_t seq_split;
     const float* seq_vel;    // ... velocities in draw order (zero where the entity has none)
+    // ... one launch may serve a range of the copy's 64-position tiles only (list frames: one launch per chunk of the
+    // shard's draw order, each followed by a completion signal to the presenting rank); tile_end == 0: all tiles
+    uint32_t tile_first, tile_end;
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -408,8 +411,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_kernel(const EmitParams<KeyT
                 make_outputs(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = e + ep.global_first;
                 if (ep.final_idx != nullptr) {
-                    ep.final_idx[dst] = e + ep.global_first;
-                    ep.final_keys[dst] = sm.keys[ring][li];
+                    // the kept order is the SHARD's: local position = global position - the bucket's shift
+                    const uint32_t lpos = dst - (ep.remap != nullptr ? __ldg(ep.remap + (uint32_t)sm.keys[ring][li]) : 0u);
+                    ep.final_idx[lpos] = e + ep.global_first;
+                    ep.final_keys[lpos] = sm.keys[ring][li];
                 }
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }
@@ -934,7 +939,8 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
     const bool do_int = VALIDATE && ep.integrate != 0 && ep.seq_vel != nullptr && !from_world;
     const bool split = ep.seq_split != 0;
     const uint32_t count = ep.pass.n;
-    const uint32_t ntiles = (count + kWarpTile - 1) / kWarpTile;
+    const uint32_t all_tiles = (count + kWarpTile - 1) / kWarpTile;
+    const uint32_t ntiles = ep.tile_end != 0 ? min(ep.tile_end, all_tiles) : all_tiles;
     const uint32_t nwarps = gridDim.x * kWarps;
     // shared-memory slot of chunk c of tile item li
     auto slot = [&](uint32_t li, uint32_t c) -> uint32_t { return split ? (c == 0 ? li : kWarpTile + li * 3u + (c - 1u)) : li * 4u + c; };
@@ -955,7 +961,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         if (VALIDATE) bulk_g2s(sm.keys[buf], ep.keys_in + (size_t)t * kWarpTile, kbytes, &sm.kbar[buf]);
         if (do_int) bulk_g2s(sm.vel[buf], ep.seq_vel + (size_t)t * kWarpTile * 3, vbytes, &sm.kbar[buf]);
     };
-    uint32_t tile = blockIdx.x * kWarps + warp;
+    uint32_t tile = ep.tile_first + blockIdx.x * kWarps + warp;
     if (lane == 0) {
         mbar_init(&sm.kbar[0], 1);
         mbar_init(&sm.kbar[1], 1);
@@ -1009,7 +1015,10 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
         for (int k = 0; k < 2; ++k) {
             const uint32_t li = k * 32 + lane;
             const bool live = li < cnt;
-            const uint32_t dst = base + li;
+            uint32_t dst = base + li;
+            // list frames: the shard-local position becomes the position in the global draw order (the kept short key
+            // names the bucket; should the key have changed, the whole frame is redone anyway)
+            if (VALIDATE && ep.remap != nullptr && live) dst += __ldg(ep.remap + (uint32_t) reinterpret_cast<const KeyT*>(sm.keys[cur])[li]);
             InstanceOut inst;
             float4 vtx[4];
             if (live) {
@@ -1097,6 +1106,47 @@ __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __res
     rows.t[(size_t)e * rows.st] = __ldcs(seq_rows + (size_t)pos * stride);  // stride 1: the copy's dense translation block
 }
 
+// ---- list frames: completion per chunk of the draw order ------------------------------
+//
+// A shard's steady-state list frame is emitted as kListChunks launches over consecutive ranges of ITS draw order; local
+// draw order is monotone in the global one, so after launch k everything this rank owns below the global position of its
+// next element is in place. One thread says so to the presenting rank: flag = frame sequence number << 32 | that position.
+// The kernel boundary orders the flag after the (peer) stores of the launches before it.
+template <typename KeyT>
+__global__ void list_signal_kernel(unsigned long long* flag, uint32_t seq, const KeyT* __restrict__ keys,
+                                   const uint32_t* __restrict__ remap, uint32_t next_pos, uint32_t count, uint32_t total) {
+    const uint32_t g = next_pos >= count ? total : next_pos + remap[(uint32_t)keys[next_pos]];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(flag) = ((unsigned long long)seq << 32) | g;
+}
+
+// The presenting rank, before regenerating the vertices of chunk k: wait until every rank has signalled chunk k of frame
+// `seq`; range = {where the previous chunk ended, the lowest position some rank has not passed yet}. range[2] is set
+// (and the range left empty) if a rank stays silent for `patience` clock cycles, so a failed peer cannot hang the device.
+__global__ void list_wait_kernel(const unsigned long long* flags, uint32_t nranks, uint32_t nchunks, uint32_t k, uint32_t seq,
+                                 uint32_t* range, long long patience) {
+    const uint32_t lo = k == 0 ? 0u : range[1];
+    uint32_t hi = 0xFFFFFFFFu;
+    const long long t0 = clock64();
+    for (uint32_t r = 0; r < nranks; ++r) {
+        const volatile unsigned long long* f = flags + (size_t)r * nchunks + k;
+        unsigned long long v = *f;
+        while ((uint32_t)(v >> 32) != seq) {
+            if (clock64() - t0 > patience) {
+                range[0] = range[1] = lo;
+                range[2] = 1u;
+                return;
+            }
+            __nanosleep(200);
+            v = *f;
+        }
+        hi = min(hi, (uint32_t)v);
+    }
+    __threadfence_system();
+    range[0] = lo;
+    range[1] = max(hi, lo);
+}
+
 // ---- quad vertices from instances ------------------------------------------------------------------
 //
 // The four quad corners are a pure function of an instance (column-major model + size), computed
@@ -1104,11 +1154,18 @@ __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __res
 // presenting GPU gives bit-identical vertices while only instances cross NVLink. One warp per 32
 // instances: coalesced 16-byte loads of the 2560-byte instance block into shared memory, compute,
 // XOR-swizzled staging, coalesced 16-byte stores.
+// `range` (optional, device memory): {first, end} read at run time instead of the two arguments — a list frame's presenter
+// learns on the device how far every rank's stores have come (list_wait_kernel).
 __global__ void __launch_bounds__(kThreads) vertices_from_instances_kernel(const float4* __restrict__ instances,
                                                                             uint32_t first, uint32_t count,
-                                                                            float4* __restrict__ vertices) {
+                                                                            float4* __restrict__ vertices,
+                                                                            const uint32_t* __restrict__ range) {
     __shared__ float4 s_in[kWarps][32 * 5];
     __shared__ float4 s_out[kWarps][32 * 4];
+    if (range != nullptr) {
+        first = range[0];
+        count = range[1] - range[0];
+    }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nwarps = gridDim.x * kWarps;
     for (uint32_t blk = blockIdx.x * kWarps + warp; blk * 32u < count; blk += nwarps) {

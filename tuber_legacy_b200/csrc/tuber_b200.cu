@@ -242,6 +242,13 @@ struct tb_ctx {
     bool list_ipc = false;       // list_inst / list_order were opened with cudaIpcOpenMemHandle
     uint64_t* d_xchg = nullptr;  // device: [4] send + [4 * nranks] receive words
     uint64_t* h_xchg = nullptr;  // pinned mirror
+    // list frames that keep the previous frame's order (tb_frame_sharded)
+    bool list_kept = false;    // final_idx / final_keys / remap still describe this shard's part of the global list
+    int list_backoff = 0;      // full frames to run before the kept order is tried again (the same on every rank)
+    uint32_t list_seq = 0;     // sequence number carried by the completion flags (the same on every rank)
+    uint64_t list_batches = 0;
+    unsigned long long* list_flags = nullptr;  // in the presenting rank's memory, mapped by all: [nranks][kListChunks]
+    uint32_t* list_range = nullptr;            // presenting rank: {first, end, timed out} of the chunk being expanded
     unsigned long long* merge_keys = nullptr;  // wide keys: this rank's sorted full keys, padded to the longest rank
     unsigned long long* merge_all = nullptr;   // ... and every rank's
     size_t merge_keys_cap = 0, merge_all_cap = 0;
@@ -267,7 +274,7 @@ struct tb_ctx {
 
 // Everything a later frame would reuse without a key pass of its own (per-tile offsets of few-bucket scenes, the
 // kept sort of sorted scenes) is dropped; the next frame computes all of it again.
-inline void drop_kept_frames(tb_ctx* c) { c->static_valid = c->sorted_valid = false; }
+inline void drop_kept_frames(tb_ctx* c) { c->static_valid = c->sorted_valid = c->list_kept = false; }
 
 
 namespace {
@@ -650,7 +657,7 @@ tb_status ensure_sort_buffers(tb_ctx* c, uint64_t n, size_t keybytes) {
     c->ekeys = c->final_keys = nullptr;
     c->final_idx = c->final_dst = nullptr;
     c->sort_cap = 0;
-    c->sorted_valid = c->final_valid = false;
+    c->sorted_valid = c->list_kept = c->final_valid = false;
     {
         cudaError_t e = cudaMalloc(&c->ekeys, (size_t)n * keybytes + 16);
         if (e == cudaSuccess) e = cudaMalloc((void**)&c->final_idx, (size_t)n * 4 + 16);
@@ -699,7 +706,7 @@ tb_status sort_ids_by_key(tb_ctx* c, uint32_t* d_keys, uint32_t n, uint32_t nbit
     split_digits(nbits, kMaxDigitBits, &ds);
     tb_status s = ensure_sort_buffers(c, n, 4);
     if (s) return s;
-    c->sorted_valid = false;  // this sort reuses the frame's ping-pong buffers and scratch
+    c->list_kept = c->sorted_valid = false;  // this sort reuses the frame's ping-pong buffers and scratch
     const uint32_t tile = kScatterTile;
     const uint32_t tiles = div_up(n, tile);
     size_t words = kHdrWords;
@@ -1084,7 +1091,7 @@ tb_status run_sort_and_emit(tb_ctx* c, const FrameMode& fm, const ScratchLayout&
                     ep.changed = skip;
                     ep.run_when = 1u;
                 }
-                if (c->sorted_cache && iin != nullptr && !fm.lt_generic && c->shard_state != 4) {
+                if (c->sorted_cache && iin != nullptr && !fm.lt_generic) {
                     ep.final_idx = c->final_idx;  // whenever this kernel ranks, it leaves the draw order behind
                     ep.final_keys = (KeyT*)c->final_keys;
                 }
@@ -1818,12 +1825,12 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         drop_kept_frames(c);
     } else if (k == "sorted_cache") {
         c->sorted_cache = value != 0;
-        c->sorted_valid = c->final_valid = c->seq_valid = false;
+        c->sorted_valid = c->list_kept = c->final_valid = c->seq_valid = false;
     } else if (k == "chunked_sort") {
         c->chunked_sort = value != 0;
         c->plan_valid = false;
         drop_kept_frames(c);
-        c->final_valid = c->seq_valid = false;
+        c->list_kept = c->final_valid = c->seq_valid = false;
     } else if (k == "hier_fused") {
         c->hier_fused = value != 0;
     } else if (k == "chunk_l2_hint") {
@@ -1833,7 +1840,7 @@ tb_status tb_ctx_set_option(tb_ctx* c, const char* name, int64_t value) {
         c->chunk_shift_opt = (int)value;
         c->plan_valid = false;
         drop_kept_frames(c);
-        c->final_valid = c->seq_valid = false;
+        c->list_kept = c->final_valid = c->seq_valid = false;
     } else if (k == "cuda_graphs") {
         c->use_graphs = value != 0;
         c->frame_graph_valid = false;
@@ -2071,7 +2078,7 @@ namespace {
 void structure_changed(tb_ctx* c) {
     c->plan_valid = false;
     drop_kept_frames(c);
-    c->final_valid = c->seq_valid = c->fast_clean = false;
+    c->list_kept = c->final_valid = c->seq_valid = c->fast_clean = false;
     c->levels_dirty = true;
     c->world_valid = false;
     c->frame_valid = false;
@@ -2574,6 +2581,7 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     c->last_instances = c->last_batches = 0;
     if (c->shard_state == 4) return shard_frame(c, out);
     c->shard_state = 0;
+    c->list_kept = false;  // this frame reuses the kept-order buffers for the shard's own list
     const uint64_t n = c->n;
     // query::<(&Transform, &Sprite)>: no store for either => no matches (query.rs:110)
     if (n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
@@ -2737,12 +2745,12 @@ tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
             while (shift > 11 && (1ull << (shift - 1)) >= n) --shift;  // small scenes: one chunk
             const ChunkGeom cg{shift, div_up(n, 1ull << shift), plan.pext.nbits};
             if (!was_chunked || cg.shift != c->cg.shift || cg.nchunks != c->cg.nchunks || cg.nbits != c->cg.nbits)
-                c->sorted_valid = c->final_valid = false;  // the kept list has another geometry
+                c->sorted_valid = c->list_kept = c->final_valid = false;  // the kept list has another geometry
             c->cg = cg;
             fm.lt_alias = false;  // the batch bins come from the per-chunk histogram
             fm.lt_hist = true;
         } else if (was_chunked) {
-            c->sorted_valid = c->final_valid = false;
+            c->sorted_valid = c->list_kept = c->final_valid = false;
         }
         // Frames that gather rows in draw order from anywhere in the storage read whole 64-byte rows: one DRAM atom
         // per entity instead of three partial ones. Chunked frames gather inside an L2-sized window, where every
@@ -2907,7 +2915,7 @@ tb_status tb_shard_key_stats(tb_ctx* c, uint64_t stats[3]) {
     c->seq_valid = false;
     c->shard_state = 0;
     c->frame_valid = false;
-    c->sorted_valid = false;  // the multi-GPU protocol re-plans every frame from the global statistics
+    c->list_kept = c->sorted_valid = false;  // the multi-GPU protocol re-plans every frame from the global statistics
     tb_status s;
     c->shard_count = 0;
     if (c->n == 0 || !c->store[TB_TRANSFORM] || !c->store[TB_SPRITE]) {
@@ -3048,6 +3056,14 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     c->last_instances = c->shard_global_count;  // the output buffers hold the global order
     c->last_batches = num_batches;
     c->frame_valid = true;
+    // The ranking emit left this shard's draw order and short keys behind (final_idx / final_keys, shard-local positions):
+    // with `remap` they are this rank's part of the global list, which tb_frame_sharded's steady frames keep.
+    c->list_kept = c->sorted_cache && plan.npasses > 1 && c->nlevels <= 1 && c->shard_global_count > 0;
+    if (c->list_kept) {
+        c->sorted_count = c->shard_count;
+        c->list_batches = num_batches;
+        c->fast_clean = true;  // a complete key pass has just seen every entity
+    }
     out->num_instances = c->shard_global_count;
     out->num_batches = num_batches;
     out->d_instances = (const tb_instance*)d_inst;
@@ -3088,6 +3104,10 @@ tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]) {
 }
 
 namespace {
+// A steady list frame goes out as this many launches per rank, each followed by a completion flag (list_signal_kernel).
+constexpr uint32_t kListChunks = 16;
+// the completion flags live behind the order array of the list (one allocation, one IPC mapping)
+inline size_t list_flags_offset(uint64_t total) { return ((size_t)total * 4 + 255) & ~(size_t)255; }
 struct ListHandles {
     cudaIpcMemHandle_t inst, order;
     void* p_inst;
@@ -3130,7 +3150,10 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
     if (rank == root) {
         TB_CUDA(c, cudaMalloc(&c->list_inst, total * 80));
         TB_CUDA(c, cudaMalloc(&c->list_vtx, total * 64));
-        TB_CUDA(c, cudaMalloc(&c->list_order, total * 4));
+        TB_CUDA(c, cudaMalloc(&c->list_order, list_flags_offset(total) + (size_t)nranks * kListChunks * 8));
+        TB_CUDA(c, cudaMemsetAsync((char*)c->list_order + list_flags_offset(total), 0, (size_t)nranks * kListChunks * 8, c->stream));
+        TB_CUDA(c, cudaMalloc((void**)&c->list_range, 4 * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMemsetAsync(c->list_range, 0, 4 * sizeof(uint32_t), c->stream));
         hh->p_inst = c->list_inst;
         hh->p_order = c->list_order;
         hh->cap = total;
@@ -3158,6 +3181,10 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
         }
     }
     c->list_cap = total;
+    c->list_flags = reinterpret_cast<unsigned long long*>((char*)c->list_order + list_flags_offset(total));
+    c->list_kept = false;
+    c->list_backoff = 0;
+    c->list_seq = 0;
     // every rank has mapped the list before the owner could ever free it
     if (!c->comm->barrier(c->stream)) return fail(c, TB_ERR_COMM, c->comm->err);
     return TB_OK;
@@ -3184,8 +3211,12 @@ static tb_status shard_finalize_impl(tb_ctx* c, bool collective) {
         cudaFree(c->list_inst);
         cudaFree(c->list_vtx);
         cudaFree(c->list_order);
+        cudaFree(c->list_range);
     }
     c->list_inst = c->list_vtx = c->list_order = nullptr;
+    c->list_flags = nullptr;
+    c->list_range = nullptr;
+    c->list_kept = false;
     c->list_cap = 0;
     c->list_ipc = false;
     c->list_root = -1;
@@ -3251,7 +3282,7 @@ static tb_status sharded_merge_frame(tb_ctx* c, tb_frame_out* out) {
     if (!comm.all_gather(c->merge_keys, c->merge_all, (size_t)maxcount * 8, c->stream)) return fail(c, TB_ERR_COMM, comm.err);
     // 4. global position of every local draw position
     if ((s = ensure_sort_buffers(c, std::max<uint64_t>(c->n, 1), c->sort_keybytes ? c->sort_keybytes : 4))) return s;
-    c->sorted_valid = c->final_valid = c->seq_valid = false;  // final_idx / final_dst are reused below
+    c->sorted_valid = c->list_kept = c->final_valid = c->seq_valid = false;  // final_idx / final_dst are reused below
     if (count) {
         TB_CUDA(c, cudaMemcpyAsync(c->final_idx, c->order, count * 4, cudaMemcpyDeviceToDevice, c->stream));
         TB_LAUNCH(c, "corank", count * 8ull * nranks, corank_kernel, div_up(count, kThreads), kThreads, 0, (const unsigned long long*)c->merge_all,
@@ -3334,6 +3365,128 @@ static tb_status sharded_merge_frame(tb_ctx* c, tb_frame_out* out) {
 // presenting rank: key statistics -> (all-gather) -> common plan -> short-key histogram -> (all-gather) -> placement
 // -> every rank's emit kernel stores its instances and order at their global positions in the presenter's list ->
 // (barrier) -> the presenter regenerates the quad vertices of the whole list.
+}  // extern "C"
+
+namespace {
+// The steady-state list frame: every rank's keys, order and placement are the previous frame's (`list_kept` everywhere, agreed
+// by the caller). No exchange before the emit: each rank streams its draw-ordered working storage (velocity system fused,
+// every key recomputed and compared with the kept one) and stores instances and order at position + remap[key] in the
+// presenting rank's list — kListChunks launches over consecutive ranges of its draw order, each followed by a completion
+// flag. The presenting rank expands chunk k of the LIST into quad vertices as soon as every rank has passed it
+// (list_wait_kernel), so the expansion overlaps the ingress instead of following the barrier. The closing sum carries
+// every rank's verdict: *ok_all only if all of them confirmed their keys; otherwise the caller redoes the frame in full.
+template <typename KeyT>
+tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
+    *ok_all = false;
+    Comm& comm = *c->comm;
+    tb_status s;
+    const bool root = c->rank == c->list_root;
+    const uint32_t count = (uint32_t)c->sorted_count, total = (uint32_t)c->shard_global_count;
+    c->frame_launches = 0;
+    // this rank can serve the frame from its kept order (the caller built the working storage; no memory for it: this
+    // rank votes for the full frame below)
+    const bool mine = count == 0 || c->seq_valid;
+    const bool integrate = mine && c->pending;
+    if (mine) c->pending = false;
+    EmitParams<KeyT> ep{};
+    ep.pass.n = count;
+    ep.idx_in = c->final_idx;
+    ep.keys_in = (const KeyT*)c->final_keys;
+    ep.seq_rows = c->seq_rows;
+    ep.seq_rows_rw = c->seq_rows;
+    ep.seq_split = c->seq_split;
+    ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
+    ep.plan = c->plan;
+    ep.remap = c->remap;
+    ep.instances = (float4*)c->list_inst;
+    ep.vertices = nullptr;
+    ep.order = (uint32_t*)c->list_order;
+    ep.global_first = (uint32_t)c->global_first;
+    ep.staged = c->staged_emit;
+    ep.dt = c->pending_dt;
+    ep.integrate = (integrate && c->seq_has_vel) ? c->pending_ticks : 0u;
+    ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
+    set_camera(c, &ep);
+    const bool emit = mine && count > 0;
+    if (emit) {
+        TB_CUDA(c, cudaMemsetAsync(c->scratch + kHdrFrame, 0, kHdrReadWords * 4, c->stream));
+        if (ep.integrate && c->hidden_movers > 0) tick_hidden_movers(c);
+        if (ep.integrate) c->seq_live = true;
+    }
+    const uint32_t seq = ++c->list_seq;
+    const uint32_t ntiles = div_up(count, 64), per = std::max<uint32_t>(div_up(ntiles, kListChunks), 1u);
+    unsigned long long* my_flags = c->list_flags + (size_t)c->rank * kListChunks;
+    for (uint32_t k = 0; k < kListChunks; ++k) {
+        const uint32_t t0 = std::min(ntiles, k * per), t1 = k + 1 == kListChunks ? ntiles : std::min(ntiles, (k + 1) * per);
+        if (emit && t0 < t1) {
+            ep.tile_first = t0;
+            ep.tile_end = t1;
+            TB_LAUNCH(c, "emit_sequential", (uint64_t)(t1 - t0) * 64 * (64 + 80 + 4 + 4 + sizeof(KeyT) + (ep.integrate ? 28 : 0)),
+                      (emit_sequential_kernel<KeyT, true>), std::min<uint32_t>(2u * (uint32_t)c->sm_count, div_up(t1 - t0, kWarps)), kThreads,
+                      sizeof(SeqShared), ep);
+        }
+        // a rank that emits nothing still reports, so that the presenter's waits end; its vote below voids the frame
+        TB_LAUNCH(c, "list_signal", 8, list_signal_kernel<KeyT>, 1, 1, 0, my_flags + k, seq, (const KeyT*)c->final_keys, (const uint32_t*)c->remap,
+                  (uint32_t)std::min<uint64_t>((uint64_t)t1 * 64, count), count, total);
+    }
+    bool confirmed = mine;
+    // ranks that share a GPU: none of their kernels may wait for another rank's (see Comm::shares_device); the presenter
+    // then expands the whole list after the closing barrier
+    const bool overlap = !comm.shares_device();
+    if (root && total > 0 && overlap) {
+        const long long patience = 4000000000ll;  // about two seconds of SM clocks
+        TB_CUDA(c, cudaMemsetAsync(c->list_range, 0, 4 * sizeof(uint32_t), c->stream));
+        for (uint32_t k = 0; k < kListChunks; ++k) {
+            TB_LAUNCH(c, "list_wait", (uint64_t)comm.nranks * 8, list_wait_kernel, 1, 1, 0, (const unsigned long long*)c->list_flags,
+                      (uint32_t)comm.nranks, kListChunks, k, seq, c->list_range, patience);
+            TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total / kListChunks * 144, vertices_from_instances_kernel, 8u * (uint32_t)c->sm_count,
+                      kThreads, 0, (const float4*)c->list_inst, 0u, 0u, (float4*)c->list_vtx, (const uint32_t*)c->list_range);
+        }
+        uint32_t range[4] = {0, 0, 0, 0};
+        TB_CUDA(c, peek_sync(c, range, c->list_range, sizeof(range)));
+        if (range[2] != 0) return fail(c, TB_ERR_COMM, "a rank did not report its part of the draw list in time");
+        if (range[1] != total) confirmed = false;
+    }
+    if (emit) {
+        if ((s = read_header(c))) return s;
+        confirmed = confirmed && c->h_hdr[(kHdrKeysChanged - kHdrFrame) / 2] == 0 && c->h_hdr[(kHdrZMiss - kHdrFrame) / 2] == 0 &&
+                    c->h_hdr[2] == c->sorted_count && plan_covers(c->plan, c->h_hdr[0], ~c->h_hdr[1]);
+    }
+    int unconfirmed = 0;
+    if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
+    if (unconfirmed == 0 && root && total > 0 && !overlap) {
+        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total * 144, vertices_from_instances_kernel,
+                  std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count), kThreads, 0, (const float4*)c->list_inst, 0u, total,
+                  (float4*)c->list_vtx, (const uint32_t*)nullptr);
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (c->prof) prof_harvest(c);
+    if (unconfirmed != 0) return TB_OK;
+    *ok_all = true;
+    c->ext_inst = c->list_inst;
+    c->ext_vtx = nullptr;
+    c->ext_order = c->list_order;
+    c->ext_cap = c->list_cap;
+    c->last_instances = total;
+    c->last_batches = c->list_batches;
+    c->frame_valid = true;
+    c->shard_state = 0;
+    out->num_instances = total;
+    out->num_batches = c->list_batches;
+    out->d_instances = (const tb_instance*)c->list_inst;
+    out->d_vertices = root ? (const tb_quad_vertex*)c->list_vtx : nullptr;
+    out->d_batches = (const tb_batch*)c->batches;
+    out->d_order = (const uint32_t*)c->list_order;
+    out->path = count == 0 ? TB_PATH_NONE : TB_PATH_SORT;
+    out->key_bits = c->plan.pext.nbits;
+    out->sort_passes = 0;
+    out->kernel_launches = c->frame_launches;
+    return TB_OK;
+}
+}  // namespace
+
+extern "C" {
+
 tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
     TB_ENTER(c);
     if (!c || !out) return TB_ERR_INVALID;
@@ -3342,6 +3495,35 @@ tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
     Comm& comm = *c->comm;
     const int nranks = comm.nranks;
     tb_status s;
+    {
+        // Steady frames: one word of agreement (does EVERY rank still hold last frame's order, untouched by uploads or
+        // structural changes?), then the frame without any further exchange before its closing barrier.
+        const bool want = c->list_kept && c->fast_clean && c->sorted_cache && c->list_backoff == 0 && c->nlevels <= 1 && !c->levels_dirty;
+        // the draw-ordered working storage is (re)built BEFORE the agreement: allocation synchronises the device, which must
+        // not happen once some rank's kernels may be waiting for this one's
+        if (want && c->sorted_count > 0 && !c->seq_valid) {
+            if ((s = ensure_rows_current(c))) return s;
+            if ((s = build_sequential_rows(c, false))) return s;
+        }
+        int cannot = 0;
+        if (!comm.sum(c->stream, want ? 0 : 1, &cannot)) return fail(c, TB_ERR_COMM, comm.err);
+        if (cannot == 0) {
+            bool done = false;
+            if (c->plan.key64) s = list_fast_frame<uint64_t>(c, out, &done);
+            else s = list_fast_frame<uint32_t>(c, out, &done);
+            if (s) return s;
+            if (done) return TB_OK;
+            // some rank's keys moved: the frame is redone in full by everyone (this rank's tick, if it ran, is in the
+            // working storage and goes back to the entity-order rows first)
+            if ((s = ensure_rows_current(c))) return s;
+            c->seq_valid = false;
+            c->list_kept = false;
+            c->list_backoff = 2;
+            memset(out, 0, sizeof(*out));
+        } else if (c->list_backoff > 0) {
+            c->list_backoff -= 1;
+        }
+    }
     uint64_t st[3];
     if ((s = tb_shard_key_stats(c, st))) return s;
     memcpy(c->h_xchg, st, sizeof(st));
@@ -3594,7 +3776,7 @@ tb_status tb_shard_set(tb_ctx* c, int rank, int nranks, uint64_t global_first) {
     if (global_first != c->global_first) {
         // final_idx / level lists / captured launches hold ids relative to the old range
         drop_kept_frames(c);
-        c->final_valid = c->seq_valid = c->fast_clean = false;
+        c->list_kept = c->final_valid = c->seq_valid = c->fast_clean = false;
         c->plan_valid = false;
         c->frame_graph_valid = c->frame_graph_seen = false;
         c->world_valid = false;
@@ -3629,7 +3811,7 @@ tb_status tb_vertices_from_instances(tb_ctx* c, const void* d_instances, uint64_
     if (first + count >= (1ull << 32)) return fail(c, TB_ERR_INVALID, "range beyond 2^32 instances");
     const uint32_t grid = std::min<uint32_t>(div_up(count, 32 * kWarps), 8u * (uint32_t)c->sm_count);
     TB_LAUNCH(c, "vertices_from_instances", count * 144, vertices_from_instances_kernel, grid, kThreads, 0, (const float4*)d_instances,
-              (uint32_t)first, (uint32_t)count, (float4*)d_vertices);
+              (uint32_t)first, (uint32_t)count, (float4*)d_vertices, (const uint32_t*)nullptr);
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
