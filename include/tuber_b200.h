@@ -405,7 +405,15 @@ TB_API tb_status tb_shard_place(tb_ctx* ctx, const void* d_all_hists /* nranks x
  * emit kernel stores its instances and order at their positions of the exact global draw order straight
  * into root's list; on root `out` describes the whole list (instances, regenerated quad vertices, global
  * batch table, global order), elsewhere only the counts are meaningful. A rank that fails before an
- * exchange leaves the others waiting, as with any collective. tb_download_* on root read the global list. */
+ * exchange leaves the others waiting, as with any collective. tb_download_* on root read the global list.
+ * STEADY FRAMES keep the list: once a frame has been placed (keys sorted in more than one pass, no scene graph) and no
+ * rank has uploaded or changed structure since, the next frame costs one word of agreement, then every rank streams its
+ * shard in its kept draw order (queued tb_system_integrate ticks fused, every key recomputed and compared) straight to
+ * its kept positions of root's list, in 16 launches each followed by a completion flag; root expands chunk after chunk of
+ * the list into quad vertices as soon as every rank has passed it, and a closing sum carries every rank's verdict. If
+ * any rank saw a key change, all of them redo the frame in full inside the same call (out->sort_passes == 0 tells a
+ * steady frame from a placed one). A rank whose flags stay away for about two seconds makes root fail with TB_ERR_COMM
+ * instead of waiting on the device forever. */
 #define TB_SHARD_ID_BYTES 128
 TB_API tb_status tb_shard_unique_id(uint8_t id[TB_SHARD_ID_BYTES]);
 TB_API tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]);

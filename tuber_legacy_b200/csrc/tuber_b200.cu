@@ -3105,7 +3105,8 @@ tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]) {
 
 namespace {
 // A steady list frame goes out as this many launches per rank, each followed by a completion flag (list_signal_kernel).
-constexpr uint32_t kListChunks = 16;
+constexpr uint32_t kListChunks = 16;      // flag slots per rank
+constexpr uint32_t kListChunksUsed = 16;  // launches per rank and frame
 // the completion flags live behind the order array of the list (one allocation, one IPC mapping)
 inline size_t list_flags_offset(uint64_t total) { return ((size_t)total * 4 + 255) & ~(size_t)255; }
 struct ListHandles {
@@ -3414,10 +3415,14 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
         if (ep.integrate) c->seq_live = true;
     }
     const uint32_t seq = ++c->list_seq;
-    const uint32_t ntiles = div_up(count, 64), per = std::max<uint32_t>(div_up(ntiles, kListChunks), 1u);
+    static const uint32_t nchunks = [] {  // experiments: TB_LIST_CHUNKS (the same on every rank)
+        const char* v = getenv("TB_LIST_CHUNKS");
+        return v ? std::min<uint32_t>(std::max(atoi(v), 1), kListChunks) : kListChunksUsed;
+    }();
+    const uint32_t ntiles = div_up(count, 64), per = std::max<uint32_t>(div_up(ntiles, nchunks), 1u);
     unsigned long long* my_flags = c->list_flags + (size_t)c->rank * kListChunks;
-    for (uint32_t k = 0; k < kListChunks; ++k) {
-        const uint32_t t0 = std::min(ntiles, k * per), t1 = k + 1 == kListChunks ? ntiles : std::min(ntiles, (k + 1) * per);
+    for (uint32_t k = 0; k < nchunks; ++k) {
+        const uint32_t t0 = std::min(ntiles, k * per), t1 = k + 1 == nchunks ? ntiles : std::min(ntiles, (k + 1) * per);
         if (emit && t0 < t1) {
             ep.tile_first = t0;
             ep.tile_end = t1;
@@ -3436,7 +3441,7 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     if (root && total > 0 && overlap) {
         const long long patience = 4000000000ll;  // about two seconds of SM clocks
         TB_CUDA(c, cudaMemsetAsync(c->list_range, 0, 4 * sizeof(uint32_t), c->stream));
-        for (uint32_t k = 0; k < kListChunks; ++k) {
+        for (uint32_t k = 0; k < nchunks; ++k) {
             TB_LAUNCH(c, "list_wait", (uint64_t)comm.nranks * 8, list_wait_kernel, 1, 1, 0, (const unsigned long long*)c->list_flags,
                       (uint32_t)comm.nranks, kListChunks, k, seq, c->list_range, patience);
             TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total / kListChunks * 144, vertices_from_instances_kernel, 8u * (uint32_t)c->sm_count,
