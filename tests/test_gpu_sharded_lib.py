@@ -89,6 +89,8 @@ def test_sharded_particles_tick_and_steady_frames():
     for _ in range(3):
         ref.step(0.01)
     g = run_local(sc, 4, ticks=1, frames=3)
+    # a plan of one pass: placed once, then the single-kernel frame with the kept placement on every rank
+    assert [i.sort_passes for i in g.infos] == [1, 0, 0]
     util.assert_frame_parity(g, ref.frame(), what="tb_frame_sharded, particles, third frame")
 
 

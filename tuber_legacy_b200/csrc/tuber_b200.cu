@@ -1526,7 +1526,7 @@ tb_status replay_hierarchy_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint3
 // last full frame left in the scratch buffer. Returns true in *ok when the frame's own statistics
 // confirm the cached plan; otherwise the caller falls back to the full frame (the velocity system
 // has already run exactly once either way).
-tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok) {
+tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok, const uint32_t* remap = nullptr) {
     *ok = false;
     const uint32_t n = (uint32_t)c->n;
     const FramePlan& plan = c->plan;
@@ -1546,6 +1546,7 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.order = d_order;
     ep.global_first = (uint32_t)c->global_first;
     ep.staged = c->staged_emit;
+    ep.remap = remap;  // list frames: shard-local bucket positions -> positions of the global list
     ep.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
     ep.mask_v = mask_or_null(c, TB_VELOCITY);
     ep.dt = c->pending_dt;
@@ -3037,11 +3038,15 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
         TB_LAUNCH(c, "build_batches", 0, build_batches_kernel, 1, 1024, 0, (const uint32_t*)c->lt_global, 1u << plan.ltbits, plan,
                   c->batches, (uint32_t)c->max_batches, c->scratch + kHdrNumBatches);
     }
+    bool small_plan = false;
     if (c->shard_count > 0) {
         FrameMode fm{};
         fm.hier = c->nlevels > 1;
         const bool prepare_made_counts = !fm.hier;  // flat frames: pass A counts pass 0's tile digits
         const ScratchLayout L = layout_scratch(plan, n, false, prepare_made_counts, use_small_emit(c, plan));
+        small_plan = L.small && plan.npasses == 1 && plan.zbits == 0 && !plan.key64 && !fm.hier;
+        c->static_offs_off = L.offs_off[0];
+        c->static_tiles = L.tiles[0];
         if (plan.key64) s = run_sort_and_emit<uint64_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         else s = run_sort_and_emit<uint32_t>(c, fm, L, prepare_made_counts, d_inst, d_vtx, d_order);
         if (s) return s;
@@ -3058,9 +3063,12 @@ static tb_status shard_frame(tb_ctx* c, tb_frame_out* out) {
     c->frame_valid = true;
     // The ranking emit left this shard's draw order and short keys behind (final_idx / final_keys, shard-local positions):
     // with `remap` they are this rank's part of the global list, which tb_frame_sharded's steady frames keep.
-    c->list_kept = c->sorted_cache && plan.npasses > 1 && c->nlevels <= 1 && c->shard_global_count > 0;
+    // Plans of one pass (a few buckets that depend on the Sprite only): what stays is the per-tile bucket offsets of the
+    // single-kernel frame (fast_frame) — the shard's steady frame is that kernel with `remap` added.
+    if (plan.npasses > 1) c->list_kept = c->sorted_cache && c->nlevels <= 1 && c->shard_global_count > 0;
+    else c->list_kept = c->static_buckets && (small_plan || c->shard_count == 0) && c->nlevels <= 1 && c->shard_global_count > 0;
     if (c->list_kept) {
-        c->sorted_count = c->shard_count;
+        c->sorted_count = c->static_count = c->shard_count;
         c->list_batches = num_batches;
         c->fast_clean = true;  // a complete key pass has just seen every entity
     }
@@ -3488,6 +3496,54 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     out->kernel_launches = c->frame_launches;
     return TB_OK;
 }
+
+// ... and for plans of one pass: the single-kernel frame (velocity system + key statistics + rank + emit from the cached
+// per-tile bucket offsets) storing at bucket position + remap[bucket]. It walks the shard in entity order, so there is no
+// per-chunk progress to report: the presenter expands the list after the closing barrier.
+tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
+    *ok_all = false;
+    Comm& comm = *c->comm;
+    tb_status s;
+    const bool root = c->rank == c->list_root;
+    const uint32_t total = (uint32_t)c->shard_global_count;
+    c->frame_launches = 0;
+    bool confirmed = true;
+    if (c->static_count > 0) {
+        const bool integrate = c->pending;
+        c->pending = false;
+        if ((s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap))) return s;
+    }
+    int unconfirmed = 0;
+    if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
+    if (unconfirmed == 0 && root && total > 0) {
+        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total * 144, vertices_from_instances_kernel,
+                  std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count), kThreads, 0, (const float4*)c->list_inst, 0u, total,
+                  (float4*)c->list_vtx, (const uint32_t*)nullptr);
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (c->prof) prof_harvest(c);
+    if (unconfirmed != 0) return TB_OK;
+    *ok_all = true;
+    c->ext_inst = c->list_inst;
+    c->ext_vtx = nullptr;
+    c->ext_order = c->list_order;
+    c->ext_cap = c->list_cap;
+    c->last_instances = total;
+    c->last_batches = c->list_batches;
+    c->frame_valid = true;
+    c->shard_state = 0;
+    out->num_instances = total;
+    out->num_batches = c->list_batches;
+    out->d_instances = (const tb_instance*)c->list_inst;
+    out->d_vertices = root ? (const tb_quad_vertex*)c->list_vtx : nullptr;
+    out->d_batches = (const tb_batch*)c->batches;
+    out->d_order = (const uint32_t*)c->list_order;
+    out->path = c->static_count == 0 ? TB_PATH_NONE : TB_PATH_BUCKET;
+    out->key_bits = c->plan.pext.nbits;
+    out->sort_passes = 0;
+    out->kernel_launches = c->frame_launches;
+    return TB_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -3503,10 +3559,11 @@ tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
     {
         // Steady frames: one word of agreement (does EVERY rank still hold last frame's order, untouched by uploads or
         // structural changes?), then the frame without any further exchange before its closing barrier.
-        const bool want = c->list_kept && c->fast_clean && c->sorted_cache && c->list_backoff == 0 && c->nlevels <= 1 && !c->levels_dirty;
+        const bool want = c->list_kept && c->fast_clean && c->list_backoff == 0 && c->nlevels <= 1 && !c->levels_dirty;
+        const bool one_pass = c->plan.npasses == 1;  // the plan is the global one: the same kind of steady frame on every rank
         // the draw-ordered working storage is (re)built BEFORE the agreement: allocation synchronises the device, which must
         // not happen once some rank's kernels may be waiting for this one's
-        if (want && c->sorted_count > 0 && !c->seq_valid) {
+        if (want && !one_pass && c->sorted_count > 0 && !c->seq_valid) {
             if ((s = ensure_rows_current(c))) return s;
             if ((s = build_sequential_rows(c, false))) return s;
         }
@@ -3514,7 +3571,8 @@ tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
         if (!comm.sum(c->stream, want ? 0 : 1, &cannot)) return fail(c, TB_ERR_COMM, comm.err);
         if (cannot == 0) {
             bool done = false;
-            if (c->plan.key64) s = list_fast_frame<uint64_t>(c, out, &done);
+            if (one_pass) s = list_static_frame(c, out, &done);
+            else if (c->plan.key64) s = list_fast_frame<uint64_t>(c, out, &done);
             else s = list_fast_frame<uint32_t>(c, out, &done);
             if (s) return s;
             if (done) return TB_OK;
