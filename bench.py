@@ -517,10 +517,12 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt[0]), o
 
-        method = ("tb_shard_init + tb_frame_sharded: the exchanges run inside the library (NCCL opened by the library: 3-word and "
-                  "short-key-histogram all-gathers, one barrier); every rank's emit kernel stores instances and order at their "
-                  "positions of the exact global draw order straight into rank 0's list over NVLink (CUDA IPC mapping); rank 0 "
-                  "regenerates the quad vertices of the whole list")
+        method = ("tb_shard_init + tb_frame_sharded: the exchanges run inside the library (NCCL opened by the library). The first "
+                  "frame places the list (3-word and short-key-histogram all-gathers, one barrier); the timed frames are steady "
+                  "ones: one integer all-reduce of agreement, then every rank's emit kernels (velocity system fused, keys "
+                  "re-checked) store instances and order at their kept positions of the exact global draw order straight into "
+                  "rank 0's list over NVLink (CUDA IPC mapping) in 16 launches, each followed by completion flags; rank 0 "
+                  "regenerates the quad vertices of the list behind those flags; a closing all-reduce carries every rank's verdict")
         # (1) weak: the headline workload, 2^24 entities per rank, as ONE draw list on rank 0
         n_total = n * world
         ctx.shard_init(rank, world, share_id(), first, 0)
@@ -528,9 +530,23 @@ def main():
         gather_ms, gout = timed_sharded(ctx, True, gsteps)
         assert gout.num_instances == n_total
         remote_bytes = (world - 1) * n * (80 + 4)
+        gcheck = None
+        if rank == 0:
+            # integrity of the list the timed frames left on rank 0 (a steady frame: kept placement, vertices expanded behind
+            # the other ranks' completion flags): every entity appears exactly once, and the list's vertices are exactly
+            # what a fresh expansion of the list's instances gives
+            od = dev_tensor(gout.d_order, n_total * 4).view(torch.int32)
+            perm = bool(torch.equal(torch.sort(od).values, torch.arange(n_total, dtype=torch.int32, device=od.device)))
+            del od
+            scratch = capi.device_alloc(n_total * 64, local_rank)
+            ctx.vertices_from_instances(gout.d_instances, 0, n_total, scratch)
+            vsame = bool(torch.equal(dev_tensor(scratch, n_total * 64), dev_tensor(gout.d_vertices, n_total * 64)))
+            capi.device_free(scratch)
+            gcheck = {"order_is_a_permutation_of_all_entities": perm, "vertices_equal_a_fresh_expansion_of_the_instances": vsame,
+                      "steady_frame": int(gout.sort_passes) == 0}
         gather = {"value": n_total / (gather_ms * 1e-3), "unit": UNIT, "ms_per_step": gather_ms, "steps": gsteps,
                   "global_instances": n_total, "bytes_into_rank0_per_step": remote_bytes,
-                  "rank0_ingress_GBps": remote_bytes / (gather_ms * 1e-3) / 1e9, "scaling": "weak", "method": method}
+                  "rank0_ingress_GBps": remote_bytes / (gather_ms * 1e-3) / 1e9, "scaling": "weak", "check": gcheck, "method": method}
         ctx.shard_finalize()
 
         # (2) strong: configs[4] as BASELINE names it — 2^26 entities in total, id-range-partitioned over the ranks
@@ -611,7 +627,7 @@ def main():
                   "list_on_rank0": {"ms_per_frame": list_ms, "entities_per_s": n5 / (list_ms * 1e-3),
                                     "bytes_into_rank0_per_frame": remote5, "rank0_ingress_GBps": remote5 / (list_ms * 1e-3) / 1e9,
                                     "what": "end to end, transfer overlapped with the emit: the remote stores ARE the emit kernels' stores; "
-                                            "includes both exchanges, the barrier and the vertex regeneration on rank 0",
+                                            "includes the agreement, the closing all-reduce and the vertex regeneration on rank 0",
                                     "per_rank": per_rank},
                   "check": check, "method": method}
         c5x.shard_finalize()

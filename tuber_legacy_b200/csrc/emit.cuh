@@ -499,7 +499,9 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
     const uint32_t off1 = split ? kWarpTile : 1u, offb = split ? 2u * kWarpTile : 2u;
     const uint32_t lt = lanemask_lt();
     const uint32_t nwarps = gridDim.x * kWarps;
-    uint32_t tile = blockIdx.x * kWarps + warp;
+    // a launch may serve a range of the tiles only (list frames in chunks, see EmitParams::tile_first)
+    const uint32_t tend = ep.tile_end != 0 ? min(ep.tile_end, ntiles) : ntiles;
+    uint32_t tile = ep.tile_first + blockIdx.x * kWarps + warp;
 
     auto fetch = [&](uint32_t t, uint32_t buf) {  // lane 0: TMA bulk copies of tile t's rows (and keys)
         const uint32_t base = t * kWarpTile;
@@ -530,17 +532,17 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
     if (lane == 0) {
         mbar_init(&sm.mbar[0], 1);
         mbar_init(&sm.mbar[1], 1);
-        if (tile < ntiles) fetch(tile, 0);
+        if (tile < tend) fetch(tile, 0);
     }
     __syncwarp();
-    unsigned long long raw = tile < ntiles ? load_raw(tile) : 0ull, raw_next = 0ull;
-    uint32_t off = (tile < ntiles && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
+    unsigned long long raw = tile < tend ? load_raw(tile) : 0ull, raw_next = 0ull;
+    uint32_t off = (tile < tend && lane < R) ? __ldg(ep.pass.tile_off + (size_t)lane * ntiles + tile) : 0u;
     uint32_t cur = 0, par0 = 0, par1 = 0;
-    for (; tile < ntiles; tile += nwarps) {
+    for (; tile < tend; tile += nwarps) {
         // prefetch the next tile of this warp: rows by TMA, presence word and bucket offsets in registers
         const uint32_t next = tile + nwarps;
         uint32_t off_next = 0u;
-        if (next < ntiles) {
+        if (next < tend) {
             if (lane == 0) fetch(next, cur ^ 1u);
             raw_next = load_raw(next);
             if (lane < R) off_next = __ldg(ep.pass.tile_off + (size_t)lane * ntiles + next);
@@ -1119,32 +1121,83 @@ __global__ void list_signal_kernel(unsigned long long* flag, uint32_t seq, const
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(flag) = ((unsigned long long)seq << 32) | g;
 }
+// Plans of one pass emit in ENTITY order (emit_small_kernel): after the tiles before `next_tile`, this rank's part of
+// bucket b is complete up to the position where that tile's bucket-b elements start — the cached per-tile offsets say
+// where. One flag per bucket (thread b).
+__global__ void list_signal_buckets_kernel(unsigned long long* flags, uint32_t seq, const uint32_t* __restrict__ tile_off, uint32_t ntiles,
+                                           uint32_t next_tile, const uint32_t* __restrict__ remap, const uint32_t* __restrict__ hist) {
+    const uint32_t b = threadIdx.x;
+    uint32_t g = 0;
+    if (ntiles != 0) g = remap[b] + (next_tile < ntiles ? tile_off[(size_t)b * ntiles + next_tile] : tile_off[(size_t)b * ntiles] + hist[b]);
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(flags + b) = ((unsigned long long)seq << 32) | g;
+}
+
+// State of the presenting rank's expansion (device memory, kListStateWords words): [0] a rank stayed silent,
+// [1 ...] the range table vertices_from_instances_kernel reads {n, first_0, end_0, ...}, [kListDone ...] where each
+// (rank, bucket) stream had come to before this chunk.
+constexpr uint32_t kListSlots = 8;      // flags per (rank, chunk): buckets of a one-pass plan (sorted plans use slot 0)
+constexpr uint32_t kListMaxStreams = 64;  // ranks x buckets the range table holds
+constexpr uint32_t kListTable = 1, kListDone = 2 + 2 * kListMaxStreams + 1, kListStateWords = kListDone + kListMaxStreams + 1;
 
 // The presenting rank, before regenerating the vertices of chunk k: wait until every rank has signalled chunk k of frame
-// `seq`; range = {where the previous chunk ended, the lowest position some rank has not passed yet}. range[2] is set
-// (and the range left empty) if a rank stays silent for `patience` clock cycles, so a failed peer cannot hang the device.
+// `seq` (flags[(r * nchunks + k) * kListSlots + b], b < nslots); the table then lists, per (rank, slot) stream, what has
+// arrived since the previous chunk. Sorted plans (nslots == 1): every rank's stream is the whole list in order, so the
+// single range is [previous end, the lowest position some rank has not passed yet). Plans of one pass: stream (r, b) is
+// rank r's segment of bucket b, which starts at starts[r * nslots + b]. state[0] is set (and the table left empty) if a
+// rank stays silent for `patience` clock cycles, so a failed peer cannot hang the device.
 __global__ void list_wait_kernel(const unsigned long long* flags, uint32_t nranks, uint32_t nchunks, uint32_t k, uint32_t seq,
-                                 uint32_t* range, long long patience) {
-    const uint32_t lo = k == 0 ? 0u : range[1];
-    uint32_t hi = 0xFFFFFFFFu;
+                                 uint32_t nslots, const uint32_t* __restrict__ starts, uint32_t* state, long long patience) {
+    uint32_t* table = state + kListTable;
+    uint32_t* done = state + kListDone;
     const long long t0 = clock64();
+    table[0] = 0;
+    uint32_t lowest = 0xFFFFFFFFu;
     for (uint32_t r = 0; r < nranks; ++r) {
-        const volatile unsigned long long* f = flags + (size_t)r * nchunks + k;
-        unsigned long long v = *f;
-        while ((uint32_t)(v >> 32) != seq) {
-            if (clock64() - t0 > patience) {
-                range[0] = range[1] = lo;
-                range[2] = 1u;
-                return;
+        for (uint32_t b = 0; b < nslots; ++b) {
+            const volatile unsigned long long* f = flags + ((size_t)r * nchunks + k) * kListSlots + b;
+            unsigned long long v = *f;
+            while ((uint32_t)(v >> 32) != seq) {
+                if (clock64() - t0 > patience) {
+                    table[0] = 0;
+                    state[0] = 1u;
+                    return;
+                }
+                __nanosleep(200);
+                v = *f;
             }
-            __nanosleep(200);
-            v = *f;
+            if (starts == nullptr) {
+                lowest = min(lowest, (uint32_t)v);
+            } else {
+                const uint32_t j = r * nslots + b;
+                const uint32_t lo = k == 0 ? starts[j] : done[j], hi = max((uint32_t)v, lo);
+                table[1 + 2 * j] = lo;
+                table[2 + 2 * j] = hi;
+                done[j] = hi;
+            }
         }
-        hi = min(hi, (uint32_t)v);
     }
     __threadfence_system();
-    range[0] = lo;
-    range[1] = max(hi, lo);
+    if (starts == nullptr) {
+        const uint32_t lo = k == 0 ? 0u : done[0], hi = max(lowest, lo);
+        table[1] = lo;
+        table[2] = hi;
+        done[0] = hi;
+        table[0] = 1;
+    } else {
+        table[0] = nranks * nslots;
+    }
+}
+
+// Where every (rank, bucket) stream of a one-pass plan starts in the global list, from the ranks' histograms
+// (hists[r * nbins + b], the all-gather of the placed frame): buckets in key order, ranks in order inside a bucket.
+__global__ void list_starts_kernel(const uint32_t* __restrict__ hists, uint32_t nranks, uint32_t nbins, uint32_t* starts) {
+    uint32_t pos = 0;
+    for (uint32_t b = 0; b < nbins; ++b)
+        for (uint32_t r = 0; r < nranks; ++r) {
+            starts[r * nbins + b] = pos;
+            pos += hists[(size_t)r * nbins + b];
+        }
 }
 
 // ---- quad vertices from instances ------------------------------------------------------------------
@@ -1154,23 +1207,41 @@ __global__ void list_wait_kernel(const unsigned long long* flags, uint32_t nrank
 // presenting GPU gives bit-identical vertices while only instances cross NVLink. One warp per 32
 // instances: coalesced 16-byte loads of the 2560-byte instance block into shared memory, compute,
 // XOR-swizzled staging, coalesced 16-byte stores.
-// `range` (optional, device memory): {first, end} read at run time instead of the two arguments — a list frame's presenter
-// learns on the device how far every rank's stores have come (list_wait_kernel).
+// `ranges` (optional, device memory): {n, first_0, end_0, first_1, end_1, ...} read at run time instead of the two arguments
+// — a list frame's presenter learns on the device how far every rank's stores have come (list_wait_kernel): one range of
+// the list for sorted plans, one per (rank, bucket) for plans of one pass.
 __global__ void __launch_bounds__(kThreads) vertices_from_instances_kernel(const float4* __restrict__ instances,
                                                                             uint32_t first, uint32_t count,
                                                                             float4* __restrict__ vertices,
-                                                                            const uint32_t* __restrict__ range) {
+                                                                            const uint32_t* __restrict__ ranges) {
     __shared__ float4 s_in[kWarps][32 * 5];
     __shared__ float4 s_out[kWarps][32 * 4];
-    if (range != nullptr) {
-        first = range[0];
-        count = range[1] - range[0];
-    }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nwarps = gridDim.x * kWarps;
-    for (uint32_t blk = blockIdx.x * kWarps + warp; blk * 32u < count; blk += nwarps) {
-        const uint32_t base = blk * 32u, m = min(32u, count - base);
-        const float4* src = instances + (size_t)(first + base) * 5;
+    const uint32_t nranges = ranges != nullptr ? ranges[0] : 1u;
+    for (uint32_t blk = blockIdx.x * kWarps + warp;; blk += nwarps) {
+        // 32-instance block number blk of the ranges laid end to end
+        uint32_t base = 0, m = 0;
+        if (ranges == nullptr) {
+            if (blk * 32u < count) {
+                base = first + blk * 32u;
+                m = min(32u, count - blk * 32u);
+            }
+        } else {
+            uint32_t skipped = 0;
+            for (uint32_t j = 0; j < nranges; ++j) {
+                const uint32_t lo = ranges[1 + 2 * j], hi = ranges[2 + 2 * j];
+                const uint32_t nb = hi > lo ? (hi - lo + 31u) / 32u : 0u;
+                if (blk - skipped < nb) {
+                    base = lo + (blk - skipped) * 32u;
+                    m = min(32u, hi - base);
+                    break;
+                }
+                skipped += nb;
+            }
+        }
+        if (m == 0) break;
+        const float4* src = instances + (size_t)base * 5;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const uint32_t q = j * 32 + lane;
@@ -1191,7 +1262,7 @@ __global__ void __launch_bounds__(kThreads) vertices_from_instances_kernel(const
                                 corner_coord(c0.z, c1.z, c3.z, cx[k], cy[k]), __uint_as_float(uv[k]));
         }
         __syncwarp();
-        float4* dst = vertices + (size_t)(first + base) * 4;
+        float4* dst = vertices + (size_t)base * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t q = j * 32 + lane;

@@ -248,7 +248,7 @@ struct tb_ctx {
     uint32_t list_seq = 0;     // sequence number carried by the completion flags (the same on every rank)
     uint64_t list_batches = 0;
     unsigned long long* list_flags = nullptr;  // in the presenting rank's memory, mapped by all: [nranks][kListChunks]
-    uint32_t* list_range = nullptr;            // presenting rank: {first, end, timed out} of the chunk being expanded
+    uint32_t* list_state = nullptr;            // presenting rank: expansion state (kListStateWords) + stream starts (kListMaxStreams)
     unsigned long long* merge_keys = nullptr;  // wide keys: this rank's sorted full keys, padded to the longest rank
     unsigned long long* merge_all = nullptr;   // ... and every rank's
     size_t merge_keys_cap = 0, merge_all_cap = 0;
@@ -1526,7 +1526,10 @@ tb_status replay_hierarchy_frame(tb_ctx* c, float4* d_inst, float4* d_vtx, uint3
 // last full frame left in the scratch buffer. Returns true in *ok when the frame's own statistics
 // confirm the cached plan; otherwise the caller falls back to the full frame (the velocity system
 // has already run exactly once either way).
-tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok, const uint32_t* remap = nullptr) {
+// List frames (tb_frame_sharded): `remap` shifts the shard's bucket positions to the global list's; with `flags` the
+// tiles go out in `nchunks` launches, each followed by this rank's per-bucket completion flags (list_signal_buckets_kernel).
+tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, uint32_t* d_order, bool* ok, const uint32_t* remap = nullptr,
+                     uint32_t nchunks = 1, unsigned long long* flags = nullptr, uint32_t seq = 0, uint32_t nslots = 0) {
     *ok = false;
     const uint32_t n = (uint32_t)c->n;
     const FramePlan& plan = c->plan;
@@ -1553,8 +1556,19 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.integrate = (integrate && ep.vel != nullptr) ? c->pending_ticks : 0u;
     ep.stats = reinterpret_cast<unsigned long long*>(c->scratch + kHdrStats);
     set_camera(c, &ep);
-    TB_LAUNCH(c, "emit", (uint64_t)n * (64 + 80 + 64 + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
-              std::min<uint32_t>(div_up(c->static_tiles, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
+    const uint32_t per = std::max<uint32_t>(div_up(c->static_tiles, nchunks), 1u);
+    for (uint32_t k = 0; k < nchunks; ++k) {
+        const uint32_t t0 = std::min(c->static_tiles, k * per), t1 = k + 1 == nchunks ? c->static_tiles : std::min(c->static_tiles, (k + 1) * per);
+        if (t0 < t1) {
+            ep.tile_first = t0;
+            ep.tile_end = nchunks == 1 ? 0u : t1;
+            TB_LAUNCH(c, "emit", (uint64_t)(t1 - t0) * 64 * (64 + 80 + (d_vtx ? 64 : 0) + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
+                      std::min<uint32_t>(div_up(t1 - t0, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
+        }
+        if (flags != nullptr)
+            TB_LAUNCH(c, "list_signal", 8ull * nslots, list_signal_buckets_kernel, 1, nslots, 0, flags + (size_t)k * kListSlots, seq,
+                      (const uint32_t*)ep.pass.tile_off, c->static_tiles, t1, remap, (const uint32_t*)c->shard_hist);
+    }
     tb_status s = read_header(c);
     if (s) return s;
     *ok = c->h_hdr[2] == c->static_count && plan_covers(plan, c->h_hdr[0], ~c->h_hdr[1]);
@@ -3159,10 +3173,11 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
     if (rank == root) {
         TB_CUDA(c, cudaMalloc(&c->list_inst, total * 80));
         TB_CUDA(c, cudaMalloc(&c->list_vtx, total * 64));
-        TB_CUDA(c, cudaMalloc(&c->list_order, list_flags_offset(total) + (size_t)nranks * kListChunks * 8));
-        TB_CUDA(c, cudaMemsetAsync((char*)c->list_order + list_flags_offset(total), 0, (size_t)nranks * kListChunks * 8, c->stream));
-        TB_CUDA(c, cudaMalloc((void**)&c->list_range, 4 * sizeof(uint32_t)));
-        TB_CUDA(c, cudaMemsetAsync(c->list_range, 0, 4 * sizeof(uint32_t), c->stream));
+        const size_t flag_bytes = (size_t)nranks * kListChunks * kListSlots * 8;
+        TB_CUDA(c, cudaMalloc(&c->list_order, list_flags_offset(total) + flag_bytes));
+        TB_CUDA(c, cudaMemsetAsync((char*)c->list_order + list_flags_offset(total), 0, flag_bytes, c->stream));
+        TB_CUDA(c, cudaMalloc((void**)&c->list_state, (kListStateWords + kListMaxStreams) * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMemsetAsync(c->list_state, 0, (kListStateWords + kListMaxStreams) * sizeof(uint32_t), c->stream));
         hh->p_inst = c->list_inst;
         hh->p_order = c->list_order;
         hh->cap = total;
@@ -3220,11 +3235,11 @@ static tb_status shard_finalize_impl(tb_ctx* c, bool collective) {
         cudaFree(c->list_inst);
         cudaFree(c->list_vtx);
         cudaFree(c->list_order);
-        cudaFree(c->list_range);
+        cudaFree(c->list_state);
     }
     c->list_inst = c->list_vtx = c->list_order = nullptr;
     c->list_flags = nullptr;
-    c->list_range = nullptr;
+    c->list_state = nullptr;
     c->list_kept = false;
     c->list_cap = 0;
     c->list_ipc = false;
@@ -3384,6 +3399,24 @@ namespace {
 // flag. The presenting rank expands chunk k of the LIST into quad vertices as soon as every rank has passed it
 // (list_wait_kernel), so the expansion overlaps the ingress instead of following the barrier. The closing sum carries
 // every rank's verdict: *ok_all only if all of them confirmed their keys; otherwise the caller redoes the frame in full.
+// The presenting rank's side of the completion flags: per chunk, wait for every rank's flag(s) and regenerate the quad
+// vertices of what has arrived since the previous chunk (list_wait_kernel writes the range table on the device).
+tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq, uint32_t nslots, const uint32_t* d_starts) {
+    const long long patience = 4000000000ll;  // about two seconds of SM clocks
+    const uint32_t total = (uint32_t)c->shard_global_count;
+    TB_CUDA(c, cudaMemsetAsync(c->list_state, 0, 4, c->stream));
+    for (uint32_t k = 0; k < nchunks; ++k) {
+        TB_LAUNCH(c, "list_wait", (uint64_t)c->comm->nranks * nslots * 8, list_wait_kernel, 1, 1, 0, (const unsigned long long*)c->list_flags,
+                  (uint32_t)c->comm->nranks, kListChunks, k, seq, nslots, d_starts, c->list_state, patience);
+        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total / nchunks * 144, vertices_from_instances_kernel, 8u * (uint32_t)c->sm_count, kThreads,
+                  0, (const float4*)c->list_inst, 0u, 0u, (float4*)c->list_vtx, (const uint32_t*)(c->list_state + kListTable));
+    }
+    uint32_t silent = 0;
+    TB_CUDA(c, peek_sync(c, &silent, c->list_state, 4));
+    if (silent != 0) return fail(c, TB_ERR_COMM, "a rank did not report its part of the draw list in time");
+    return TB_OK;
+}
+
 template <typename KeyT>
 tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     *ok_all = false;
@@ -3428,7 +3461,7 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
         return v ? std::min<uint32_t>(std::max(atoi(v), 1), kListChunks) : kListChunksUsed;
     }();
     const uint32_t ntiles = div_up(count, 64), per = std::max<uint32_t>(div_up(ntiles, nchunks), 1u);
-    unsigned long long* my_flags = c->list_flags + (size_t)c->rank * kListChunks;
+    unsigned long long* my_flags = c->list_flags + (size_t)c->rank * kListChunks * kListSlots;
     for (uint32_t k = 0; k < nchunks; ++k) {
         const uint32_t t0 = std::min(ntiles, k * per), t1 = k + 1 == nchunks ? ntiles : std::min(ntiles, (k + 1) * per);
         if (emit && t0 < t1) {
@@ -3439,7 +3472,7 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
                       sizeof(SeqShared), ep);
         }
         // a rank that emits nothing still reports, so that the presenter's waits end; its vote below voids the frame
-        TB_LAUNCH(c, "list_signal", 8, list_signal_kernel<KeyT>, 1, 1, 0, my_flags + k, seq, (const KeyT*)c->final_keys, (const uint32_t*)c->remap,
+        TB_LAUNCH(c, "list_signal", 8, list_signal_kernel<KeyT>, 1, 1, 0, my_flags + (size_t)k * kListSlots, seq, (const KeyT*)c->final_keys, (const uint32_t*)c->remap,
                   (uint32_t)std::min<uint64_t>((uint64_t)t1 * 64, count), count, total);
     }
     bool confirmed = mine;
@@ -3447,18 +3480,10 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     // then expands the whole list after the closing barrier
     const bool overlap = !comm.shares_device();
     if (root && total > 0 && overlap) {
-        const long long patience = 4000000000ll;  // about two seconds of SM clocks
-        TB_CUDA(c, cudaMemsetAsync(c->list_range, 0, 4 * sizeof(uint32_t), c->stream));
-        for (uint32_t k = 0; k < nchunks; ++k) {
-            TB_LAUNCH(c, "list_wait", (uint64_t)comm.nranks * 8, list_wait_kernel, 1, 1, 0, (const unsigned long long*)c->list_flags,
-                      (uint32_t)comm.nranks, kListChunks, k, seq, c->list_range, patience);
-            TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total / kListChunks * 144, vertices_from_instances_kernel, 8u * (uint32_t)c->sm_count,
-                      kThreads, 0, (const float4*)c->list_inst, 0u, 0u, (float4*)c->list_vtx, (const uint32_t*)c->list_range);
-        }
-        uint32_t range[4] = {0, 0, 0, 0};
-        TB_CUDA(c, peek_sync(c, range, c->list_range, sizeof(range)));
-        if (range[2] != 0) return fail(c, TB_ERR_COMM, "a rank did not report its part of the draw list in time");
-        if (range[1] != total) confirmed = false;
+        if ((s = expand_list_behind_the_ranks(c, nchunks, seq, 1, nullptr))) return s;
+        uint32_t reached = 0;
+        TB_CUDA(c, peek_sync(c, &reached, c->list_state + kListDone, 4));
+        if (reached != total) confirmed = false;
     }
     if (emit) {
         if ((s = read_header(c))) return s;
@@ -3508,14 +3533,33 @@ tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     const uint32_t total = (uint32_t)c->shard_global_count;
     c->frame_launches = 0;
     bool confirmed = true;
+    // few buckets: every rank reports, per chunk of its tiles, how far each of its bucket segments has come, and the
+    // presenter expands the vertices behind them (ranks x buckets streams); otherwise after the closing barrier
+    const uint32_t nb = 1u << c->plan.pext.nbits;
+    const bool flagged = nb <= kListSlots && (uint32_t)comm.nranks * nb <= kListMaxStreams;
+    const bool overlap = flagged && !comm.shares_device();
+    const uint32_t seq = ++c->list_seq;
+    unsigned long long* my_flags = c->list_flags + (size_t)c->rank * kListChunks * kListSlots;
     if (c->static_count > 0) {
         const bool integrate = c->pending;
         c->pending = false;
-        if ((s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap))) return s;
+        if (flagged) s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap, kListChunksUsed, my_flags, seq, nb);
+        else s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap);
+        if (s) return s;
+    } else if (flagged) {
+        for (uint32_t k = 0; k < kListChunksUsed; ++k)  // nothing to emit, but the presenter's waits must end
+            TB_LAUNCH(c, "list_signal", 8ull * nb, list_signal_buckets_kernel, 1, nb, 0, my_flags + (size_t)k * kListSlots, seq,
+                      (const uint32_t*)nullptr, 0u, 0u, (const uint32_t*)c->remap, (const uint32_t*)c->shard_hist);
+    }
+    if (root && total > 0 && overlap) {
+        uint32_t* d_starts = c->list_state + kListStateWords;
+        TB_LAUNCH(c, "list_starts", (uint64_t)comm.nranks * nb * 4, list_starts_kernel, 1, 1, 0, (const uint32_t*)c->shard_all_hists, (uint32_t)comm.nranks, nb,
+                  d_starts);
+        if ((s = expand_list_behind_the_ranks(c, kListChunksUsed, seq, nb, d_starts))) return s;
     }
     int unconfirmed = 0;
     if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
-    if (unconfirmed == 0 && root && total > 0) {
+    if (unconfirmed == 0 && root && total > 0 && !overlap) {
         TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total * 144, vertices_from_instances_kernel,
                   std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count), kThreads, 0, (const float4*)c->list_inst, 0u, total,
                   (float4*)c->list_vtx, (const uint32_t*)nullptr);
