@@ -199,3 +199,170 @@ def test_nccl_multiprocess_list_equals_single_context_frame(kind):
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", f"nccl_parity_world{world}_{kind}.json"), "w") as f:
             json.dump(res, f)
+
+
+def _shard_fuzz_ops(rng, n, nranks, steps):
+    """A deterministic operation list every rank executes in lockstep (frames are collective)."""
+    names = ["frame", "tick", "upload", "delete", "sprites", "zvel", "option", "camera"]
+    weights = np.array([10, 7, 1, 1, 1, 0.5, 1, 0.5])
+    ops = []
+    for _ in range(steps):
+        op = str(rng.choice(names, p=weights / weights.sum()))
+        rank = int(rng.integers(0, nranks))
+        first, count = scenes.shard_range(n, rank, nranks)
+        if op == "upload":
+            f = first + int(rng.integers(0, max(count - 40, 1)))
+            ops.append((op, rank, f, int(rng.integers(1, 40))))
+        elif op == "delete":
+            ops.append((op, rank, (first + rng.choice(count, 10, replace=False)).astype(np.uint32)))
+        elif op == "sprites":
+            f = first + int(rng.integers(0, max(count - 60, 1)))
+            ops.append((op, rank, f, int(rng.integers(1, 60)), int(rng.integers(1, 15))))
+        elif op == "zvel":
+            ops.append((op, rank, (first + rng.choice(count, 30, replace=False)).astype(np.int64)))
+        elif op == "option":
+            ops.append((op, rank, str(rng.choice(["sorted_cache", "static_buckets"])), int(rng.integers(0, 2))))
+        else:
+            ops.append((op,))
+    ops.append(("frame",))
+    return ops
+
+
+@pytest.mark.parametrize("kind", ["flat", "particles"])
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_sharded_random_operation_sequences(kind, seed):
+    """The kept list, its working storage and the completion flags survive any interleaving of ticks, partial uploads,
+    deletions, sprite changes, key-changing velocities and per-rank option changes: every frame is the oracle's."""
+    import ctypes as C
+
+    from oracle import oracle
+
+    nranks, root = 3, seed % 3
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.integers(5_000, 9_000))
+    sc = scenes.config2(n=n, seed=70 + seed) if kind == "flat" else scenes.config4(n=n, seed=70 + seed)
+    v = np.zeros(n, capi.VELOCITY_DTYPE)
+    v["v"][:, 0] = rng.uniform(-50, 50, n)
+    v["v"][:, 1] = rng.uniform(-50, 50, n)
+    sc.velocities = v
+    ops = _shard_fuzz_ops(rng, n, nranks, 70)
+    vp = capi.orthographic(-800, 800, -600, 600, -100, 100)
+
+    # the oracle's run: the expected frame at every "frame" op
+    ref = util.make_oracle(sc)
+    want, cam = [], None
+    tr, sp, ve = sc.transforms.copy(), sc.sprites.copy(), sc.velocities.copy()
+    alive = np.ones(n, bool)
+    TY = {"t": 0x7472616e73666f72, "s": 0x7370726974650000, "v": 0x76656c6f63697479}
+
+    def ref_add(ty, rec, size, e):
+        one = np.ascontiguousarray(rec)
+        oracle.lib().orc_ecs_add_component(ref._h, C.c_uint64(TY[ty]), C.c_void_p(one.ctypes.data), C.c_uint64(size), C.c_uint64(int(e)))
+
+    for op in ops:
+        if op[0] == "frame":
+            want.append(ref.frame(view_proj=cam))
+        elif op[0] == "tick":
+            ref.step(0.01)
+        elif op[0] == "camera":
+            cam = None if cam is not None else vp
+        elif op[0] == "upload":
+            _, _, f, cnt = op
+            cur = ref.transforms().view(capi.TRANSFORM_DTYPE).reshape(-1)[f:f + cnt].copy()
+            cur["translation"][:, 0] += np.float32(2.5)
+            for k in range(cnt):
+                if alive[f + k]:
+                    ref_add("t", cur[k:k + 1], 48, f + k)
+        elif op[0] == "delete":
+            a = op[2].astype(np.uint64)
+            alive[op[2]] = False
+            oracle.lib().orc_ecs_delete_by_ids(ref._h, C.c_void_p(a.ctypes.data), len(a))
+        elif op[0] == "sprites":
+            _, _, f, cnt, add = op
+            sp["layer"][f:f + cnt] = (sp["layer"][f:f + cnt] + add) % 16
+            for k in range(cnt):
+                if alive[f + k]:
+                    ref_add("s", sp[f + k:f + k + 1], 16, f + k)
+        elif op[0] == "zvel":
+            ve["v"][op[2], 2] = np.float32(100.0)
+            for e in op[2]:
+                if alive[e]:
+                    ref_add("v", ve[e:e + 1], 12, e)
+
+    sid = capi.shard_local_id()
+    got, errors = [], []
+
+    def worker(rank):
+        try:
+            first, count = scenes.shard_range(n, rank, nranks)
+            ctx = capi.Context(count, device=0)
+            ctx.shard_init(rank, nranks, sid, first, root)
+            ctx.set_entity_count(count)
+            ctx.upload_transforms(0, sc.transforms[first:first + count])
+            ctx.upload_sprites(0, sc.sprites[first:first + count])
+            ctx.upload_velocities(0, sc.velocities[first:first + count])
+            my_sp, my_ve = sc.sprites[first:first + count].copy(), sc.velocities[first:first + count].copy()
+            my_alive = np.ones(count, bool)
+            on = None
+            for op in ops:
+                mine = len(op) > 1 and op[1] == rank
+                if op[0] == "frame":
+                    info = ctx.frame_sharded()
+                    if rank == root:
+                        class G:
+                            pass
+                        g = G()
+                        g.info = info
+                        g.order = ctx.download_order(info.num_instances)
+                        g.instances = ctx.download_instances(info.num_instances)
+                        g.vertices = ctx.download_vertices(info.num_instances)
+                        g.batches = ctx.download_batches(info.num_batches)
+                        got.append(g)
+                elif op[0] == "tick":
+                    ctx.system_integrate(0.01)
+                elif op[0] == "camera":
+                    on = None if on is not None else vp
+                    ctx.set_view_projection(on)
+                elif op[0] == "upload" and mine:
+                    _, _, f, cnt = op
+                    for k in range(cnt):  # entity by entity: deleted ones stay deleted (add_component on a dead index is a no-op in the oracle)
+                        if my_alive[f - first + k]:
+                            t = ctx.download_transforms(f - first + k, 1)
+                            t["translation"][:, 0] += np.float32(2.5)
+                            ctx.upload_transforms(f - first + k, t)
+                elif op[0] == "delete" and mine:
+                    my_alive[op[2] - first] = False
+                    ctx.delete_by_ids((op[2] - first).astype(np.uint32))
+                elif op[0] == "sprites" and mine:
+                    _, _, f, cnt, add = op
+                    lo = f - first
+                    my_sp["layer"][lo:lo + cnt] = (my_sp["layer"][lo:lo + cnt] + add) % 16
+                    for k in range(cnt):
+                        if my_alive[lo + k]:
+                            ctx.upload_sprites(lo + k, my_sp[lo + k:lo + k + 1])
+                elif op[0] == "zvel" and mine:
+                    for e in op[2] - first:
+                        my_ve["v"][e, 2] = np.float32(100.0)
+                        if my_alive[e]:
+                            ctx.upload_velocities(int(e), my_ve[e:e + 1])
+                elif op[0] == "option" and mine:
+                    ctx.set_option(op[2], op[3])
+            ctx.shard_finalize()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            errors.append((rank, repr(e), traceback.format_exc()[-800:]))
+
+    threads = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert len(got) == len(want)
+    frames = [i for i, op in enumerate(ops) if op[0] == "frame"]
+    kept = 0
+    for k, (g, r) in enumerate(zip(got, want)):
+        kept += int(g.info.sort_passes == 0 and g.info.num_instances > 0)
+        util.assert_frame_parity(g, r, what=f"sharded {kind} seed {seed} frame {k} (op {frames[k]}): {[o[0] for o in ops[max(0, frames[k] - 8):frames[k]]]}")
+    assert kept > 0, "no frame of the sequence kept the list"
