@@ -330,14 +330,12 @@ struct LevelParams {
 };
 
 // Level L of the scene graph. Siblings are usually contiguous, so lanes with the same parent
-// elect one loader and share the parent's world row by warp shuffle.
-__global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelParams lp) {
-    __shared__ PrepShared sh;
+// elect one loader and share the parent's world row by warp shuffle. One CTA's share of the level: chunks
+// first_chunk, first_chunk + chunk_stride, ...
+__device__ __forceinline__ void level_pass(const LevelParams& lp, PrepShared& sh, PrepAcc& acc, uint32_t first_chunk, uint32_t chunk_stride) {
     const PrepParams& p = lp.prep;
-    prep_init(p, sh);
-    PrepAcc acc;
     const uint32_t nchunks = (lp.count + kThreads - 1) / kThreads;
-    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (uint32_t chunk = first_chunk; chunk < nchunks; chunk += chunk_stride) {
         const uint32_t slot = chunk * kThreads + threadIdx.x;
         const bool inb = slot < lp.count;
         uint32_t e = 0;
@@ -410,7 +408,39 @@ __global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelPara
         }
         prep_account(p, sh, acc, inb, rend, key, e, false, 0u, nullptr);
     }
-    prep_flush(p, sh, acc);
+}
+
+__global__ void __launch_bounds__(kThreads) prepare_level_kernel(const LevelParams lp) {
+    __shared__ PrepShared sh;
+    prep_init(lp.prep, sh);
+    PrepAcc acc;
+    level_pass(lp, sh, acc, blockIdx.x, gridDim.x);
+    prep_flush(lp.prep, sh, acc);
+}
+
+// The top of a scene graph is a handful of tiny levels (1, 8, 74, ... entities), each waiting for the one above: as
+// separate launches they cost a launch plus a chain of dependent loads apiece. ONE CTA walks a span of consecutive small
+// levels instead; a block barrier (the world rows a level wrote are read by the next through plain loads) stands where
+// the kernel boundary stood.
+constexpr int kMaxSpanLevels = 8;
+constexpr uint32_t kSpanLevelEntities = 1024;  // levels up to this size join a span
+struct LevelSpan {
+    uint32_t n;
+    uint32_t first[kMaxSpanLevels], count[kMaxSpanLevels], level[kMaxSpanLevels];
+};
+__global__ void __launch_bounds__(kThreads) prepare_level_span_kernel(LevelParams lp, const LevelSpan span) {
+    __shared__ PrepShared sh;
+    prep_init(lp.prep, sh);
+    PrepAcc acc;
+    for (uint32_t i = 0; i < span.n; ++i) {
+        lp.first = span.first[i];
+        lp.count = span.count[i];
+        lp.level = span.level[i];
+        level_pass(lp, sh, acc, 0u, 1u);
+        __threadfence();
+        __syncthreads();
+    }
+    prep_flush(lp.prep, sh, acc);
 }
 
 // ---- hierarchy planning (on upload of parents, not per frame) -----------------------------------

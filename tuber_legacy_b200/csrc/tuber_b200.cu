@@ -969,7 +969,8 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)c->sm_count * 8u);
         TB_LAUNCH(c, have_plan ? "prepare_flat" : "discover_flat", bytes_in, prepare_flat_kernel, grid, kThreads, 0, p);
     } else {
-        for (uint32_t l = 0; l < std::min(c->nlevels, max_levels); ++l) {
+        const uint32_t nl = std::min(c->nlevels, max_levels);
+        for (uint32_t l = 0; l < nl; ++l) {
             LevelParams lp{};
             lp.prep = p;
             lp.parent = c->sane_parent;
@@ -980,6 +981,26 @@ tb_status run_prepare(tb_ctx* c, bool have_plan, bool integrate, const FrameMode
             lp.global_first = (uint32_t)c->global_first;
             lp.world = c->world;
             if (lp.count == 0) continue;
+            // consecutive small levels (the top of the tree): one launch of one CTA walks them in order
+            LevelSpan span{};
+            uint32_t l2 = l;
+            while (l2 < nl && span.n < (uint32_t)kMaxSpanLevels && c->level_count[l2] <= kSpanLevelEntities) {
+                if (c->level_count[l2] > 0) {
+                    span.first[span.n] = c->level_first[l2];
+                    span.count[span.n] = c->level_count[l2];
+                    span.level[span.n] = l2;
+                    span.n += 1;
+                }
+                l2 += 1;
+            }
+            if (span.n >= 2) {
+                uint64_t ents = 0;
+                for (uint32_t i = 0; i < span.n; ++i) ents += span.count[i];
+                TB_LAUNCH(c, have_plan ? "prepare_level" : "discover_level", ents * (64 + 4 + 64 + (p.integrate ? 44 : 0)), prepare_level_span_kernel, 1,
+                          kThreads, 0, lp, span);
+                l = l2 - 1;
+                continue;
+            }
             const uint32_t chunks = div_up(lp.count, kThreads);
             const uint32_t grid = std::min<uint32_t>(chunks, (uint32_t)c->sm_count * 8u);
             TB_LAUNCH(c, have_plan ? "prepare_level" : "discover_level", (uint64_t)lp.count * (64 + 4 + 64 + (p.integrate ? 44 : 0)),
