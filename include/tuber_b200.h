@@ -111,7 +111,7 @@ typedef struct tb_frame_out {
     uint32_t path;                     /* enum tb_path */
     uint32_t key_bits;                 /* sort-key bits that actually vary this frame */
     uint32_t sort_passes;              /* radix passes run (TB_PATH_SORT) */
-    uint32_t kernel_launches;          /* kernels this frame launched */
+    uint32_t kernel_launches;          /* kernels this frame launched (its result read-back, a one-warp store, not counted) */
     uint32_t hierarchy_levels;         /* 0 when no entity has a Parent */
     uint32_t replanned;                /* 1 when the cached plan was stale and the frame re-ran batching */
 } tb_frame_out;
@@ -340,7 +340,9 @@ TB_API tb_status tb_profile_enable(tb_ctx* ctx, int on);
 TB_API tb_status tb_profile_count(tb_ctx* ctx, uint32_t* n);
 TB_API tb_status tb_profile_get(tb_ctx* ctx, uint32_t i, const char** name, double* total_ms, uint64_t* total_bytes,
                                 uint32_t* launches);
-/* Total kernels launched by this context since creation. */
+/* Total kernels launched by this context since creation. Small device -> host reads (a frame's result header, counters,
+ * a batch table) are one-warp kernels storing into pinned memory rather than copy-engine transfers (which would queue
+ * behind another context's bulk download): they count here, not in tb_frame_out.kernel_launches. */
 TB_API tb_status tb_launch_count(tb_ctx* ctx, uint64_t* n);
 
 /* ---- sharding across GPUs ------------------------------------------------- */
