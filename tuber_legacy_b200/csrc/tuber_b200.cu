@@ -9,6 +9,7 @@
 // There is no CPU fallback anywhere in this file: without an sm_100 device tb_ctx_create
 // fails with TB_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -390,8 +391,19 @@ struct DeviceTemp {
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
 };
 
+// NVTX range (header-only NVTX3: a call through an empty function table unless a tool such as nsys / ncu is attached).
+// Every frame entry point and every kernel launch carries one, named like the profiler's rows (tb_profile_*); the
+// reference's only tracing is `trace!("Starting scene render")` / `"Render finished"` (tuber-graphics/src/lib.rs:136,152).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define TB_LAUNCH(c, name, bytes, kern, grid, block, smem, ...)        \
     do {                                                               \
+        NvtxRange nvtx_range__(name);                                  \
         prof_begin((c), (name), (bytes));                              \
         kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);   \
         prof_end((c));                                                 \
@@ -2472,6 +2484,7 @@ tb_status tb_system_access(int system, uint32_t* reads, uint32_t* writes) {
 
 tb_status tb_bundle_step(tb_ctx* c, const int* systems, uint32_t n, float dt, uint32_t* stages) {
     TB_ENTER(c);
+    NvtxRange nvtx_call__("tb_bundle_step");
     if (!c) return TB_ERR_INVALID;
     if (n == 0) return TB_OK;
     if (!systems) return fail(c, TB_ERR_INVALID, "null pointer");
@@ -2610,6 +2623,7 @@ tb_status tb_frame_force_path(tb_ctx* c, uint32_t path) {
 
 tb_status tb_frame_transform_batch(tb_ctx* c, tb_frame_out* out) {
     TB_ENTER(c);
+    NvtxRange nvtx_call__("tb_frame_transform_batch");
     if (!c || !out) return TB_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     c->frame_launches = 0;
@@ -3615,6 +3629,7 @@ extern "C" {
 
 tb_status tb_frame_sharded(tb_ctx* c, tb_frame_out* out) {
     TB_ENTER(c);
+    NvtxRange nvtx_call__("tb_frame_sharded");
     if (!c || !out) return TB_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     if (!c->comm) return fail(c, TB_ERR_INVALID, "tb_frame_sharded follows tb_shard_init");
