@@ -520,16 +520,17 @@ def main():
         method = ("tb_shard_init + tb_frame_sharded: the exchanges run inside the library (NCCL opened by the library). The first "
                   "frame places the list (3-word and short-key-histogram all-gathers, one barrier); the timed frames are steady "
                   "ones: one integer all-reduce of agreement, then every rank's emit kernels (velocity system fused, keys "
-                  "re-checked) store instances and order at their kept positions of the exact global draw order straight into "
-                  "rank 0's list over NVLink (CUDA IPC mapping) in 16 launches, each followed by completion flags; rank 0 "
-                  "regenerates the quad vertices of the list behind those flags; a closing all-reduce carries every rank's verdict")
+                  "re-checked) store a 64-byte world row and the entity id per element (68 B instead of the 84 B of an instance) at "
+                  "their kept positions of the exact global draw order straight into rank 0's memory over NVLink (CUDA IPC "
+                  "mapping) in 16 launches, each followed by completion flags; rank 0 expands the rows into instances and quad "
+                  "vertices behind those flags (same arithmetic: bit-identical); a closing all-reduce carries every rank's verdict")
         # (1) weak: the headline workload, 2^24 entities per rank, as ONE draw list on rank 0
         n_total = n * world
         ctx.shard_init(rank, world, share_id(), first, 0)
         gsteps = max(5, args.steps // 2)
         gather_ms, gout = timed_sharded(ctx, True, gsteps)
         assert gout.num_instances == n_total
-        remote_bytes = (world - 1) * n * (80 + 4)
+        remote_bytes = (world - 1) * n * (64 + 4)  # steady frames ship a 64-byte world row + the entity id per element
         gcheck = None
         if rank == 0:
             # integrity of the list the timed frames left on rank 0 (a steady frame: kept placement, vertices expanded behind
@@ -618,7 +619,7 @@ def main():
         rb5 = (n5 - c5 if rank == 0 else 0)
         rb5t = torch.tensor([float(rb5)], dtype=torch.float64, device="cuda")
         dist.all_reduce(rb5t, op=dist.ReduceOp.MAX)
-        remote5 = float(rb5t[0]) * (80 + 4)
+        remote5 = float(rb5t[0]) * (64 + 4)
         strong = {"workload": f"configs[4]: {n5} flat sprites in total (64 textures x 16 layers x 16 depths), contiguous id ranges over "
                               f"{world} GPUs, instance list gathered on rank 0", "scaling": "strong", "entities_total": n5,
                   "compute_only": {"static": {"ms_per_frame": static_ms, "entities_per_s": n5 / (static_ms * 1e-3)},

@@ -71,6 +71,11 @@ struct EmitParams {
     // ... one launch may serve a range of the copy's 64-position tiles only (list frames: one launch per chunk of the
     // shard's draw order, each followed by a completion signal to the presenting rank); tile_end == 0: all tiles
     uint32_t tile_first, tile_end;
+    // ... and may write, instead of instance + quad vertices, the WORLD ROW of every position (3x4 affine, then size /
+    // texture|layer: a WorldRow, 64 bytes) into `vertices` (`instances` == nullptr): what a shard ships to the presenting
+    // rank in steady list frames — 68 instead of 84 bytes per element cross the link, and the presenter expands the rows
+    // (expand_world_rows_kernel: the same make_outputs, bit-identical)
+    uint32_t world_rows_out;
     FramePlan plan;             // last: its z dictionary is the cold tail of the parameter block
 };
 
@@ -137,6 +142,20 @@ __device__ __forceinline__ void make_outputs(const Params& ep, const Affine& wor
     }
 }
 
+// make_outputs, or the world row itself in its place (EmitParams::world_rows_out)
+template <typename Params>
+__device__ __forceinline__ void make_outputs_or_row(const Params& ep, const Affine& world, float sw, float shh, uint32_t tl,
+                                                    InstanceOut& inst, float4 (&vtx)[4]) {
+    if (ep.world_rows_out) {
+        vtx[0] = world.r0;
+        vtx[1] = world.r1;
+        vtx[2] = world.r2;
+        vtx[3] = make_float4(sw, shh, __uint_as_float(tl), 0.0f);
+        return;
+    }
+    make_outputs(ep, world, sw, shh, tl, inst, vtx);
+}
+
 // Writes one warp's 32 results (lane i holds the instance and vertices of output position dst)
 // as whole 128-byte lines: staged in the warp's shared buffer, then streamed out 16 bytes per lane.
 // Instances use a 20-word lane stride (conflict-free 128-bit stores; the read-out is linear);
@@ -144,19 +163,21 @@ __device__ __forceinline__ void make_outputs(const Params& ep, const Affine& wor
 __device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool live, uint32_t nlive, uint32_t dst,
                                              const InstanceOut& inst, const float4 (&vtx)[4], float4* instances,
                                              float4* vertices) {
-    float4* my = stage + lane * kStageF4;
-    if (live) {
-        my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
-    }
-    __syncwarp();
+    if (instances != nullptr) {  // warp-uniform (nullptr: world rows only, see EmitParams::world_rows_out)
+        float4* my = stage + lane * kStageF4;
+        if (live) {
+            my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
+        }
+        __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const uint32_t q = j * 32 + lane;  // 16-byte chunk of the warp's 2560-byte instance stream
-        const uint32_t item = q / 5, part = q - item * 5;
-        const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
-        if (item < nlive) st_cs_f4(instances + (size_t)d * 5 + part, stage[q]);
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t q = j * 32 + lane;  // 16-byte chunk of the warp's 2560-byte instance stream
+            const uint32_t item = q / 5, part = q - item * 5;
+            const uint32_t d = __shfl_sync(0xffffffffu, dst, item & 31);
+            if (item < nlive) st_cs_f4(instances + (size_t)d * 5 + part, stage[q]);
+        }
+        __syncwarp();
     }
-    __syncwarp();
     if (vertices == nullptr) return;  // warp-uniform
     const uint32_t sw = (lane >> 1) & 3u;
     if (live) {
@@ -670,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
                 }
-                make_outputs(ep, w, sw, shh, tl, inst, vtx);
+                make_outputs_or_row(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = base + li + ep.global_first;
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }
@@ -1070,7 +1091,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                         if (miss) acc.miss = true;
                     }
                 }
-                make_outputs(ep, w, sw, shh, tl, inst, vtx);
+                make_outputs_or_row(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = sm.idx[cur][li];
             }
             const uint32_t nlive = cnt > (uint32_t)k * 32u ? min(32u, cnt - k * 32u) : 0u;
@@ -1270,6 +1291,68 @@ __global__ void __launch_bounds__(kThreads) vertices_from_instances_kernel(const
             if (item < m) st_cs_f4(dst + q, s_out[warp][item * 4 + (part ^ ((item >> 1) & 3u))]);
         }
         __syncwarp();
+    }
+}
+
+// ---- instances and quad vertices from world rows -------------------------------------------------------
+//
+// The presenting rank of a steady list frame receives WORLD ROWS (EmitParams::world_rows_out) and turns them into
+// instances and quad vertices with the same make_outputs the emit kernels use (camera included), so the list is
+// bit-identical to one emitted directly. Ranges as in vertices_from_instances_kernel.
+struct CameraParams {
+    float4 vp[4];
+    uint32_t has_vp;
+};
+__global__ void __launch_bounds__(kThreads) expand_world_rows_kernel(const float4* __restrict__ rows, uint32_t first, uint32_t count,
+                                                                      float4* __restrict__ instances, float4* __restrict__ vertices,
+                                                                      const uint32_t* __restrict__ ranges, const CameraParams cam) {
+    __shared__ float4 s_stage[kWarps][32 * kStageF4];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * kWarps;
+    const uint32_t nranges = ranges != nullptr ? ranges[0] : 1u;
+    for (uint32_t blk = blockIdx.x * kWarps + warp;; blk += nwarps) {
+        uint32_t base = 0, m = 0;
+        if (ranges == nullptr) {
+            if (blk * 32u < count) {
+                base = first + blk * 32u;
+                m = min(32u, count - blk * 32u);
+            }
+        } else {
+            uint32_t skipped = 0;
+            for (uint32_t j = 0; j < nranges; ++j) {
+                const uint32_t lo = ranges[1 + 2 * j], hi = ranges[2 + 2 * j];
+                const uint32_t nb = hi > lo ? (hi - lo + 31u) / 32u : 0u;
+                if (blk - skipped < nb) {
+                    base = lo + (blk - skipped) * 32u;
+                    m = min(32u, hi - base);
+                    break;
+                }
+                skipped += nb;
+            }
+        }
+        if (m == 0) break;
+        // the block's 2 KB of rows through shared memory: coalesced 16-byte loads, then each lane reads its own row
+        float4* st = s_stage[warp];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = j * 32 + lane;
+            if (q < m * 4) st[q ^ ((q >> 3) & 3u)] = __ldcs(rows + (size_t)base * 4 + q);
+        }
+        __syncwarp();
+        const bool live = lane < m;
+        InstanceOut inst;
+        float4 vtx[4];
+        if (live) {
+            const uint32_t q0 = lane * 4, sw4 = (q0 >> 3) & 3u;  // the four chunks of a row share one swizzle term
+            Affine w;
+            w.r0 = st[(q0 + 0) ^ sw4];
+            w.r1 = st[(q0 + 1) ^ sw4];
+            w.r2 = st[(q0 + 2) ^ sw4];
+            const float4 sv = st[(q0 + 3) ^ sw4];
+            make_outputs(cam, w, sv.x, sv.y, __float_as_uint(sv.z), inst, vtx);
+        }
+        __syncwarp();
+        staged_store(st, lane, live, m, base + lane, inst, vtx, instances, vertices);
     }
 }
 

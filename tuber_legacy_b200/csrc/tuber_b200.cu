@@ -249,6 +249,7 @@ struct tb_ctx {
     uint32_t list_seq = 0;     // sequence number carried by the completion flags (the same on every rank)
     uint64_t list_batches = 0;
     unsigned long long* list_flags = nullptr;  // in the presenting rank's memory, mapped by all: [nranks][kListChunks]
+    void* list_rows = nullptr;                 // in the presenting rank's memory, mapped by all: a WorldRow per list position
     uint32_t* list_state = nullptr;            // presenting rank: expansion state (kListStateWords) + stream starts (kListMaxStreams)
     unsigned long long* merge_keys = nullptr;  // wide keys: this rank's sorted full keys, padded to the longest rank
     unsigned long long* merge_all = nullptr;   // ... and every rank's
@@ -1583,6 +1584,10 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
     ep.global_first = (uint32_t)c->global_first;
     ep.staged = c->staged_emit;
     ep.remap = remap;  // list frames: shard-local bucket positions -> positions of the global list
+    if (d_inst == nullptr) {
+        ep.world_rows_out = 1u;
+        ep.staged = 1u;
+    }
     ep.vel = c->store[TB_VELOCITY] ? c->vel : nullptr;
     ep.mask_v = mask_or_null(c, TB_VELOCITY);
     ep.dt = c->pending_dt;
@@ -3167,9 +3172,10 @@ constexpr uint32_t kListChunksUsed = 16;  // launches per rank and frame
 // the completion flags live behind the order array of the list (one allocation, one IPC mapping)
 inline size_t list_flags_offset(uint64_t total) { return ((size_t)total * 4 + 255) & ~(size_t)255; }
 struct ListHandles {
-    cudaIpcMemHandle_t inst, order;
+    cudaIpcMemHandle_t inst, order, rows;
     void* p_inst;
     void* p_order;
+    void* p_rows;
     uint64_t cap;
 };
 }  // namespace
@@ -3213,12 +3219,15 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
         TB_CUDA(c, cudaMemsetAsync((char*)c->list_order + list_flags_offset(total), 0, flag_bytes, c->stream));
         TB_CUDA(c, cudaMalloc((void**)&c->list_state, (kListStateWords + kListMaxStreams) * sizeof(uint32_t)));
         TB_CUDA(c, cudaMemsetAsync(c->list_state, 0, (kListStateWords + kListMaxStreams) * sizeof(uint32_t), c->stream));
+        TB_CUDA(c, cudaMalloc(&c->list_rows, total * 64));
         hh->p_inst = c->list_inst;
         hh->p_order = c->list_order;
+        hh->p_rows = c->list_rows;
         hh->cap = total;
         if (!c->comm->same_process() && nranks > 1) {
             TB_CUDA(c, cudaIpcGetMemHandle(&hh->inst, c->list_inst));
             TB_CUDA(c, cudaIpcGetMemHandle(&hh->order, c->list_order));
+            TB_CUDA(c, cudaIpcGetMemHandle(&hh->rows, c->list_rows));
         }
         TB_CUDA(c, cudaMemcpyAsync(dh, hh, sizeof(*hh), cudaMemcpyHostToDevice, c->stream));
     }
@@ -3229,11 +3238,13 @@ tb_status tb_shard_init(tb_ctx* c, int rank, int nranks, const uint8_t id[TB_SHA
         if (c->comm->same_process()) {
             c->list_inst = hh->p_inst;
             c->list_order = hh->p_order;
+            c->list_rows = hh->p_rows;
         } else {
             if (cudaIpcOpenMemHandle(&c->list_inst, hh->inst, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-                cudaIpcOpenMemHandle(&c->list_order, hh->order, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaIpcOpenMemHandle(&c->list_order, hh->order, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&c->list_rows, hh->rows, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
-                c->list_inst = c->list_order = nullptr;
+                c->list_inst = c->list_order = c->list_rows = nullptr;
                 return fail(c, TB_ERR_COMM, "cannot map the presenting rank's draw list (CUDA IPC)");
             }
             c->list_ipc = true;
@@ -3264,15 +3275,17 @@ static tb_status shard_finalize_impl(tb_ctx* c, bool collective) {
     if (!owner && c->list_ipc) {
         if (c->list_inst) cudaIpcCloseMemHandle(c->list_inst);
         if (c->list_order) cudaIpcCloseMemHandle(c->list_order);
+        if (c->list_rows) cudaIpcCloseMemHandle(c->list_rows);
     }
     if (collective) c->comm->barrier(c->stream);  // nobody stores into the list any more
     if (owner) {
         cudaFree(c->list_inst);
         cudaFree(c->list_vtx);
         cudaFree(c->list_order);
+        cudaFree(c->list_rows);
         cudaFree(c->list_state);
     }
-    c->list_inst = c->list_vtx = c->list_order = nullptr;
+    c->list_inst = c->list_vtx = c->list_order = c->list_rows = nullptr;
     c->list_flags = nullptr;
     c->list_state = nullptr;
     c->list_kept = false;
@@ -3429,11 +3442,23 @@ static tb_status sharded_merge_frame(tb_ctx* c, tb_frame_out* out) {
 namespace {
 // The steady-state list frame: every rank's keys, order and placement are the previous frame's (`list_kept` everywhere, agreed
 // by the caller). No exchange before the emit: each rank streams its draw-ordered working storage (velocity system fused,
-// every key recomputed and compared with the kept one) and stores instances and order at position + remap[key] in the
-// presenting rank's list — kListChunks launches over consecutive ranges of its draw order, each followed by a completion
-// flag. The presenting rank expands chunk k of the LIST into quad vertices as soon as every rank has passed it
-// (list_wait_kernel), so the expansion overlaps the ingress instead of following the barrier. The closing sum carries
+// every key recomputed and compared with the kept one) and stores a WORLD ROW (64 bytes, not the 80-byte instance) and the
+// entity id at position + remap[key] in the presenting rank's memory — kListChunks launches over consecutive ranges of its
+// draw order, each followed by a completion flag. The presenting rank expands chunk k of the rows into instances and quad
+// vertices as soon as every rank has passed it (list_wait_kernel + expand_world_rows_kernel), so the expansion overlaps
+// the ingress instead of following the barrier. The closing sum carries
 // every rank's verdict: *ok_all only if all of them confirmed their keys; otherwise the caller redoes the frame in full.
+CameraParams list_camera(const tb_ctx* c) {
+    CameraParams cam{};
+    set_camera(c, &cam);
+    return cam;
+}
+// the whole list at once (ranks that share a GPU: after the closing barrier)
+void expand_whole_list(tb_ctx* c, uint32_t total) {
+    TB_LAUNCH(c, "expand_world_rows", (uint64_t)total * 208, expand_world_rows_kernel, std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count),
+              kThreads, 0, (const float4*)c->list_rows, 0u, total, (float4*)c->list_inst, (float4*)c->list_vtx, (const uint32_t*)nullptr, list_camera(c));
+}
+
 // The presenting rank's side of the completion flags: per chunk, wait for every rank's flag(s) and regenerate the quad
 // vertices of what has arrived since the previous chunk (list_wait_kernel writes the range table on the device).
 tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq, uint32_t nslots, const uint32_t* d_starts) {
@@ -3443,8 +3468,9 @@ tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq
     for (uint32_t k = 0; k < nchunks; ++k) {
         TB_LAUNCH(c, "list_wait", (uint64_t)c->comm->nranks * nslots * 8, list_wait_kernel, 1, 1, 0, (const unsigned long long*)c->list_flags,
                   (uint32_t)c->comm->nranks, kListChunks, k, seq, nslots, d_starts, c->list_state, patience);
-        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total / nchunks * 144, vertices_from_instances_kernel, 8u * (uint32_t)c->sm_count, kThreads,
-                  0, (const float4*)c->list_inst, 0u, 0u, (float4*)c->list_vtx, (const uint32_t*)(c->list_state + kListTable));
+        TB_LAUNCH(c, "expand_world_rows", (uint64_t)total / nchunks * 208, expand_world_rows_kernel, 8u * (uint32_t)c->sm_count, kThreads, 0,
+                  (const float4*)c->list_rows, 0u, 0u, (float4*)c->list_inst, (float4*)c->list_vtx, (const uint32_t*)(c->list_state + kListTable),
+                  list_camera(c));
     }
     uint32_t silent = 0;
     TB_CUDA(c, peek_sync(c, &silent, c->list_state, 4));
@@ -3475,8 +3501,9 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     ep.seq_vel = c->seq_has_vel ? c->seq_vel : nullptr;
     ep.plan = c->plan;
     ep.remap = c->remap;
-    ep.instances = (float4*)c->list_inst;
-    ep.vertices = nullptr;
+    ep.instances = nullptr;  // world rows cross the link (68 instead of 84 bytes per element); the presenter expands them
+    ep.vertices = (float4*)c->list_rows;
+    ep.world_rows_out = 1u;
     ep.order = (uint32_t*)c->list_order;
     ep.global_first = (uint32_t)c->global_first;
     ep.staged = c->staged_emit;
@@ -3528,9 +3555,7 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     int unconfirmed = 0;
     if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
     if (unconfirmed == 0 && root && total > 0 && !overlap) {
-        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total * 144, vertices_from_instances_kernel,
-                  std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count), kThreads, 0, (const float4*)c->list_inst, 0u, total,
-                  (float4*)c->list_vtx, (const uint32_t*)nullptr);
+        expand_whole_list(c, total);
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     if (c->prof) prof_harvest(c);
@@ -3578,8 +3603,9 @@ tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     if (c->static_count > 0) {
         const bool integrate = c->pending;
         c->pending = false;
-        if (flagged) s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap, kListChunksUsed, my_flags, seq, nb);
-        else s = fast_frame(c, integrate, (float4*)c->list_inst, nullptr, (uint32_t*)c->list_order, &confirmed, c->remap);
+        // (nullptr, list_rows): world rows out, see EmitParams::world_rows_out
+        if (flagged) s = fast_frame(c, integrate, nullptr, (float4*)c->list_rows, (uint32_t*)c->list_order, &confirmed, c->remap, kListChunksUsed, my_flags, seq, nb);
+        else s = fast_frame(c, integrate, nullptr, (float4*)c->list_rows, (uint32_t*)c->list_order, &confirmed, c->remap);
         if (s) return s;
     } else if (flagged) {
         for (uint32_t k = 0; k < kListChunksUsed; ++k)  // nothing to emit, but the presenter's waits must end
@@ -3595,9 +3621,7 @@ tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     int unconfirmed = 0;
     if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
     if (unconfirmed == 0 && root && total > 0 && !overlap) {
-        TB_LAUNCH(c, "vertices_from_instances", (uint64_t)total * 144, vertices_from_instances_kernel,
-                  std::min<uint32_t>(div_up(total, 32 * kWarps), 8u * (uint32_t)c->sm_count), kThreads, 0, (const float4*)c->list_inst, 0u, total,
-                  (float4*)c->list_vtx, (const uint32_t*)nullptr);
+        expand_whole_list(c, total);
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     if (c->prof) prof_harvest(c);
