@@ -411,8 +411,9 @@ TB_API tb_status tb_shard_place(tb_ctx* ctx, const void* d_all_hists /* nranks x
  * STEADY FRAMES keep the list: once a frame has been placed (keys sorted in more than one pass, no scene graph) and no
  * rank has uploaded or changed structure since, the next frame costs one word of agreement, then every rank streams its
  * shard in its kept draw order (queued tb_system_integrate ticks fused, every key recomputed and compared) straight to
- * its kept positions of root's list, in 16 launches each followed by a completion flag; root expands chunk after chunk of
- * the list into quad vertices as soon as every rank has passed it, and a closing sum carries every rank's verdict. If
+ * its kept positions in root's memory — as 64-byte world rows, not 80-byte instances —, in 16 launches each followed by a
+ * completion flag; root expands chunk after chunk of the rows into instances and quad vertices (same arithmetic, same
+ * bits) as soon as every rank has passed it, and a closing sum carries every rank's verdict. If
  * any rank saw a key change, all of them redo the frame in full inside the same call (out->sort_passes == 0 tells a
  * steady frame from a placed one). A rank whose flags stay away for about two seconds makes root fail with TB_ERR_COMM
  * instead of waiting on the device forever. */
