@@ -1131,7 +1131,7 @@ __global__ void __launch_bounds__(kThreads) sync_rows_kernel(const float4* __res
 
 // ---- list frames: completion per chunk of the draw order ------------------------------
 //
-// A shard's steady-state list frame is emitted as kListChunks launches over consecutive ranges of ITS draw order; local
+// A shard's steady-state list frame is emitted as several launches over consecutive ranges of ITS draw order; local
 // draw order is monotone in the global one, so after launch k everything this rank owns below the global position of its
 // next element is in place. One thread says so to the presenting rank: flag = frame sequence number << 32 | that position.
 // The kernel boundary orders the flag after the (peer) stores of the launches before it.

@@ -3583,8 +3583,9 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
 }
 
 // ... and for plans of one pass: the single-kernel frame (velocity system + key statistics + rank + emit from the cached
-// per-tile bucket offsets) storing at bucket position + remap[bucket]. It walks the shard in entity order, so there is no
-// per-chunk progress to report: the presenter expands the list after the closing barrier.
+// per-tile bucket offsets) storing world rows at bucket position + remap[bucket]. It walks the shard in ENTITY order, so
+// progress is monotone per bucket, not per list: with few buckets every chunk of tiles is followed by one flag per bucket
+// and the presenter expands ranks x buckets ranges behind them; otherwise it expands the list after the closing barrier.
 tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     *ok_all = false;
     Comm& comm = *c->comm;
