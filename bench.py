@@ -699,15 +699,25 @@ def main():
             "kernels": kernels,
         }
         # DRAM bytes per launch of the dominant kernel from an `ncu --set full` capture — reported only when that capture
-        # was taken from THIS build (same source hash), otherwise null
+        # was taken from THIS build (same source hash) or from a build with the very same dominant kernel (same SASS hash),
+        # otherwise null
         traffic_file = os.path.join(ROOT, "profiles", "emit_traffic.json")
         if os.path.exists(traffic_file):
             try:
                 from tuber_legacy_b200 import build as tb_build
                 tr = json.load(open(traffic_file))
-                if tr.get("source_sha256") == tb_build.source_hash() and tr.get("entities") == n:
+                same_sources = tr.get("source_sha256") == tb_build.source_hash()
+                same_kernel = False
+                if not same_sources and tr.get("kernel_sass_sha256"):
+                    try:  # another build, but is the dominant kernel instruction for instruction the profiled one?
+                        same_kernel = tr["kernel_sass_sha256"] == tb_build.kernel_sass_hash()
+                    except Exception:
+                        same_kernel = False
+                if (same_sources or same_kernel) and tr.get("entities") == n:
                     line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
-                    line["roofline"]["traffic_source"] = tr.get("source")
+                    line["roofline"]["traffic_source"] = tr.get("source") + ("; same sources as this build" if same_sources else
+                                                                              "; taken from another build whose dominant kernel has the same SASS as this "
+                                                                              "build's (sha256 over the instruction text, constant-bank offsets normalised)")
                 else:
                     line["roofline"]["traffic_source"] = "profiles/emit_traffic.json is from another build: not reported"
             except Exception:

@@ -1,5 +1,6 @@
 """Writes profiles/emit_traffic.json from an `ncu --set full` capture of the headline kernel, tagged with the hash of the
-sources the library was built from (bench.py reports roofline.traffic only when the hashes agree).
+sources the library was built from and with the hash of the kernel's own SASS (bench.py reports roofline.traffic only when
+the running build matches one of them: the same sources, or instruction for instruction the same kernel).
     python tools/ncu_traffic.py gpurun_out/<report>.ncu-rep 16777216"""
 import csv
 import json
@@ -29,7 +30,7 @@ def main(path, entities):
                 "dram_bytes_write": wr, "algorithmic_bytes_per_launch": entities * 232,
                 "traffic_over_algorithmic": (rd + wr) / (entities * 232), "gpu_time_us_under_ncu": d.get("gpu__time_duration.sum"),
                 "source": "ncu --set full --clock-control none (" + os.path.basename(path) + "), dram__bytes_read.sum + dram__bytes_write.sum",
-                "source_sha256": build.source_hash()}
+                "source_sha256": build.source_hash(), "kernel_sass_sha256": build.kernel_sass_hash()}
     if best is None:
         raise SystemExit("no emit_small_kernel launch in the report")
     with open(os.path.join(ROOT, "profiles", "emit_traffic.json"), "w") as f:

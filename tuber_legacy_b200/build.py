@@ -38,6 +38,41 @@ def source_hash():
     return h.hexdigest()
 
 
+def kernel_sass(path, mangled_regex):
+    """Instruction text of the kernel whose mangled name matches `mangled_regex` in a cubin / shared library (cuobjdump
+    -sass), without addresses and encodings and with constant-bank OFFSETS normalised: the offset of a kernel parameter
+    moves when an unrelated field is added to the parameter struct, the code does not."""
+    import re
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    cur, text = None, {}
+    for line in out.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1) if re.search(mangled_regex, m.group(1)) else None
+            if cur:
+                text[cur] = []
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if m and cur:
+            t = re.sub(r"c\[0x0\]\[((?:U?R\d+)\+)?0x[0-9a-f]+\]", "c[0][X]", m.group(1).strip())
+            if re.match(r"(@!?U?P\d+ )?(MOV|UMOV|IMAD\.MOV\.U32|HFMA2) ", t):  # immediates that carry such offsets
+                t = re.sub(r"(0x[0-9a-f]+|-?[0-9.]+(e[-+]?\d+)?)$", "IMM", t)
+            text[cur].append(t)
+    if len(text) != 1:
+        raise RuntimeError(f"{len(text)} kernels match {mangled_regex!r}")
+    return next(iter(text.values()))
+
+
+HEADLINE_KERNEL = r"emit_small_kernelIjLb1E(Lb0E)?EEv"  # emit_small_kernel<u32, true> (not the list-frame instantiation)
+
+
+def kernel_sass_hash(path=None, mangled_regex=HEADLINE_KERNEL):
+    """sha256 over kernel_sass(): ties the ncu capture of the headline kernel to the kernel BINARY that runs."""
+    import hashlib
+    return hashlib.sha256("\n".join(kernel_sass(path or LIB_PATH, mangled_regex)).encode()).hexdigest()
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True

@@ -142,28 +142,30 @@ __device__ __forceinline__ void make_outputs(const Params& ep, const Affine& wor
     }
 }
 
-// make_outputs, or the world row itself in its place (EmitParams::world_rows_out)
-template <typename Params>
+// make_outputs, or (ROWS: the list-frame instantiations, EmitParams::world_rows_out) the world row itself in its place. A
+// compile-time choice: as a run-time branch it cost the single-GPU headline kernel 2 % (0.656 -> 0.669 ms at 2^24 entities).
+template <bool ROWS, typename Params>
 __device__ __forceinline__ void make_outputs_or_row(const Params& ep, const Affine& world, float sw, float shh, uint32_t tl,
                                                     InstanceOut& inst, float4 (&vtx)[4]) {
-    if (ep.world_rows_out) {
+    if (ROWS) {
         vtx[0] = world.r0;
         vtx[1] = world.r1;
         vtx[2] = world.r2;
         vtx[3] = make_float4(sw, shh, __uint_as_float(tl), 0.0f);
-        return;
+    } else {
+        make_outputs(ep, world, sw, shh, tl, inst, vtx);
     }
-    make_outputs(ep, world, sw, shh, tl, inst, vtx);
 }
 
 // Writes one warp's 32 results (lane i holds the instance and vertices of output position dst)
 // as whole 128-byte lines: staged in the warp's shared buffer, then streamed out 16 bytes per lane.
 // Instances use a 20-word lane stride (conflict-free 128-bit stores; the read-out is linear);
 // vertices a 16-word stride with the chunk index XORed by bits of the lane (conflict-free both ways).
+template <bool INST = true>
 __device__ __forceinline__ void staged_store(float4* stage, uint32_t lane, bool live, uint32_t nlive, uint32_t dst,
                                              const InstanceOut& inst, const float4 (&vtx)[4], float4* instances,
                                              float4* vertices) {
-    if (instances != nullptr) {  // warp-uniform (nullptr: world rows only, see EmitParams::world_rows_out)
+    if (INST) {  // false: world rows only (through the 64-byte path below), see EmitParams::world_rows_out
         float4* my = stage + lane * kStageF4;
         if (live) {
             my[0] = inst.c0; my[1] = inst.c1; my[2] = inst.c2; my[3] = inst.c3; my[4] = inst.s;
@@ -495,7 +497,7 @@ struct SmallShared {
 // until a component is uploaded, so the steady-state frame needs no separate key pass: this kernel
 // also runs the velocity system (writing the translation chunk back), and accumulates the key statistics with
 // which the host validates, every frame, that the cached plan and offsets still hold.
-template <typename KeyT, bool FUSED>
+template <typename KeyT, bool FUSED, bool ROWS = false>
 __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -691,11 +693,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     shh = r.b1.z;
                     tl = __float_as_uint(r.a1.w);
                 }
-                make_outputs_or_row(ep, w, sw, shh, tl, inst, vtx);
+                make_outputs_or_row<ROWS>(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = base + li + ep.global_first;
                 if (ep.texlayer != nullptr) ep.texlayer[dst] = tl;
             }
-            if (!ep.staged) {
+            if (!ROWS && !ep.staged) {
                 if (live) {
                     float4* ip = ep.instances + (size_t)dst * 5;
                     st_cs_f4(ip, inst.c0);
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 2) emit_small_kernel(const EmitParam
                     }
                 }
             } else {
-                staged_store(sm.stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
+                staged_store<!ROWS>(sm.stage, lane, live, min(32u, cnt - s0), dst, inst, vtx, ep.instances, ep.vertices);
             }
         }
         __syncwarp();  // every lane is done with rows[cur], s_li, s_dst before they are reused
@@ -946,7 +948,7 @@ struct SeqShared {
 // storage): the velocity system runs on the streamed rows (ep.integrate ticks; translation chunk written back in
 // place, sequentially), every key is recomputed and compared with the kept one, statistics go to `stats` for the host
 // to confirm — all of it on sequential reads. Entity-order rows are brought up to date lazily (sync_rows_kernel).
-template <typename KeyT, bool VALIDATE, bool GRAPH = false>
+template <typename KeyT, bool VALIDATE, bool GRAPH = false, bool ROWS = false>
 __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const EmitParams<KeyT> ep) {
     extern __shared__ __align__(128) unsigned char emit_smem_raw[];
     __shared__ uint32_t s_zdict[VALIDATE ? kMaxZDict : 1];
@@ -1091,11 +1093,11 @@ __global__ void __launch_bounds__(kThreads, 2) emit_sequential_kernel(const Emit
                         if (miss) acc.miss = true;
                     }
                 }
-                make_outputs_or_row(ep, w, sw, shh, tl, inst, vtx);
+                make_outputs_or_row<ROWS>(ep, w, sw, shh, tl, inst, vtx);
                 ep.order[dst] = sm.idx[cur][li];
             }
             const uint32_t nlive = cnt > (uint32_t)k * 32u ? min(32u, cnt - k * 32u) : 0u;
-            staged_store(sm.stage, lane, live, nlive, dst, inst, vtx, ep.instances, ep.vertices);
+            staged_store<!ROWS>(sm.stage, lane, live, nlive, dst, inst, vtx, ep.instances, ep.vertices);
         }
         __syncwarp();  // the buffers are free for the fetch of the tile after next
         cur ^= 1u;

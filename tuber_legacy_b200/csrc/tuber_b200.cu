@@ -1600,8 +1600,12 @@ tb_status fast_frame(tb_ctx* c, bool integrate, float4* d_inst, float4* d_vtx, u
         if (t0 < t1) {
             ep.tile_first = t0;
             ep.tile_end = nchunks == 1 ? 0u : t1;
-            TB_LAUNCH(c, "emit", (uint64_t)(t1 - t0) * 64 * (64 + 80 + (d_vtx ? 64 : 0) + 4 + (ep.integrate ? 12 + 16 : 0)), (emit_small_kernel<uint32_t, true>),
-                      std::min<uint32_t>(div_up(t1 - t0, kWarps), 2u * (uint32_t)c->sm_count), kThreads, sizeof(SmallShared), ep);
+            const uint32_t grid = std::min<uint32_t>(div_up(t1 - t0, kWarps), 2u * (uint32_t)c->sm_count);
+            const uint64_t bytes = (uint64_t)(t1 - t0) * 64 * (64 + (d_inst ? 80 : 0) + (d_vtx ? 64 : 0) + 4 + (ep.integrate ? 12 + 16 : 0));
+            if (ep.world_rows_out)
+                TB_LAUNCH(c, "emit", bytes, (emit_small_kernel<uint32_t, true, true>), grid, kThreads, sizeof(SmallShared), ep);
+            else
+                TB_LAUNCH(c, "emit", bytes, (emit_small_kernel<uint32_t, true>), grid, kThreads, sizeof(SmallShared), ep);
         }
         if (flags != nullptr)
             TB_LAUNCH(c, "list_signal", 8ull * nslots, list_signal_buckets_kernel, 1, nslots, 0, flags + (size_t)k * kListSlots, seq,
@@ -1759,6 +1763,8 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint32_t, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
+    cudaFuncSetAttribute(emit_sequential_kernel<uint64_t, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
     cudaFuncSetAttribute(emit_ordered_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OrderedShared));
@@ -1766,6 +1772,7 @@ tb_status tb_ctx_create(int device, uint64_t max_entities, tb_ctx** out) {
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_small_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+    cudaFuncSetAttribute(emit_small_kernel<uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
     cudaFuncSetAttribute(emit_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ListShared));
     cudaFuncSetAttribute(emit_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ListShared));
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -3530,7 +3537,7 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
             ep.tile_first = t0;
             ep.tile_end = t1;
             TB_LAUNCH(c, "emit_sequential", (uint64_t)(t1 - t0) * 64 * (64 + 80 + 4 + 4 + sizeof(KeyT) + (ep.integrate ? 28 : 0)),
-                      (emit_sequential_kernel<KeyT, true>), std::min<uint32_t>(2u * (uint32_t)c->sm_count, div_up(t1 - t0, kWarps)), kThreads,
+                      (emit_sequential_kernel<KeyT, true, false, true>), std::min<uint32_t>(2u * (uint32_t)c->sm_count, div_up(t1 - t0, kWarps)), kThreads,
                       sizeof(SeqShared), ep);
         }
         // a rank that emits nothing still reports, so that the presenter's waits end; its vote below voids the frame
