@@ -415,8 +415,8 @@ TB_API tb_status tb_shard_place(tb_ctx* ctx, const void* d_all_hists /* nranks x
  * completion flag; root expands chunk after chunk of the rows into instances and quad vertices (same arithmetic, same
  * bits) as soon as every rank has passed it, and a closing sum carries every rank's verdict. If
  * any rank saw a key change, all of them redo the frame in full inside the same call (out->sort_passes == 0 tells a
- * steady frame from a placed one). A rank whose flags stay away for about two seconds makes root fail with TB_ERR_COMM
- * instead of waiting on the device forever. */
+ * steady frame from a placed one). Root's device-side wait for a rank's flags gives up after about two seconds: root then
+ * votes against the frame like a rank whose keys moved, so a slow rank costs a full frame, never a hung device. */
 #define TB_SHARD_ID_BYTES 128
 TB_API tb_status tb_shard_unique_id(uint8_t id[TB_SHARD_ID_BYTES]);
 TB_API tb_status tb_shard_local_id(uint8_t id[TB_SHARD_ID_BYTES]);

@@ -3468,7 +3468,9 @@ void expand_whole_list(tb_ctx* c, uint32_t total) {
 
 // The presenting rank's side of the completion flags: per chunk, wait for every rank's flag(s) and regenerate the quad
 // vertices of what has arrived since the previous chunk (list_wait_kernel writes the range table on the device).
-tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq, uint32_t nslots, const uint32_t* d_starts) {
+// *silent: a rank's flags stayed away past the wait kernel's patience. Not an error by itself: the caller votes against the
+// frame in the closing sum (which it must still join — the other ranks are on their way there) and everyone redoes it in full.
+tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq, uint32_t nslots, const uint32_t* d_starts, bool* silent) {
     const long long patience = 4000000000ll;  // about two seconds of SM clocks
     const uint32_t total = (uint32_t)c->shard_global_count;
     TB_CUDA(c, cudaMemsetAsync(c->list_state, 0, 4, c->stream));
@@ -3479,9 +3481,9 @@ tb_status expand_list_behind_the_ranks(tb_ctx* c, uint32_t nchunks, uint32_t seq
                   (const float4*)c->list_rows, 0u, 0u, (float4*)c->list_inst, (float4*)c->list_vtx, (const uint32_t*)(c->list_state + kListTable),
                   list_camera(c));
     }
-    uint32_t silent = 0;
-    TB_CUDA(c, peek_sync(c, &silent, c->list_state, 4));
-    if (silent != 0) return fail(c, TB_ERR_COMM, "a rank did not report its part of the draw list in time");
+    uint32_t gave_up = 0;
+    TB_CUDA(c, peek_sync(c, &gave_up, c->list_state, 4));
+    *silent = gave_up != 0;
     return TB_OK;
 }
 
@@ -3549,10 +3551,11 @@ tb_status list_fast_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
     // then expands the whole list after the closing barrier
     const bool overlap = !comm.shares_device();
     if (root && total > 0 && overlap) {
-        if ((s = expand_list_behind_the_ranks(c, nchunks, seq, 1, nullptr))) return s;
+        bool silent = false;
+        if ((s = expand_list_behind_the_ranks(c, nchunks, seq, 1, nullptr, &silent))) return s;
         uint32_t reached = 0;
         TB_CUDA(c, peek_sync(c, &reached, c->list_state + kListDone, 4));
-        if (reached != total) confirmed = false;
+        if (silent || reached != total) confirmed = false;
     }
     if (emit) {
         if ((s = read_header(c))) return s;
@@ -3624,7 +3627,9 @@ tb_status list_static_frame(tb_ctx* c, tb_frame_out* out, bool* ok_all) {
         uint32_t* d_starts = c->list_state + kListStateWords;
         TB_LAUNCH(c, "list_starts", (uint64_t)comm.nranks * nb * 4, list_starts_kernel, 1, 1, 0, (const uint32_t*)c->shard_all_hists, (uint32_t)comm.nranks, nb,
                   d_starts);
-        if ((s = expand_list_behind_the_ranks(c, kListChunksUsed, seq, nb, d_starts))) return s;
+        bool silent = false;
+        if ((s = expand_list_behind_the_ranks(c, kListChunksUsed, seq, nb, d_starts, &silent))) return s;
+        if (silent) confirmed = false;
     }
     int unconfirmed = 0;
     if (!comm.sum(c->stream, confirmed ? 0 : 1, &unconfirmed)) return fail(c, TB_ERR_COMM, comm.err);
